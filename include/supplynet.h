@@ -1,0 +1,164 @@
+/*
+ * supplynet.h — C ABI of the B200-native batched supply-network (beer game) simulator.
+ *
+ * The reference (qihuazhong/multi-echelon-drl) is pure Python and has no FFI; this header
+ * is the boundary a maintainer would bind with ctypes.  Each entry
+ * point names the reference interface it replaces (file:line into the reference tree).
+ *
+ * Conventions
+ *   - Every pointer marked "device" is caller-owned CUDA device memory (e.g. a torch
+ *     tensor's data_ptr()).  The library never allocates or frees device memory and keeps
+ *     no state between calls: all simulator state lives in the caller's `state` buffer.
+ *   - All launches are asynchronous on the caller's stream (`stream` is a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).
+ *   - Structure-of-arrays: a "row" is one quantity for all envs, `ld` elements apart
+ *     (ld >= n_envs, ld % 4 == 0, base pointers 16-byte aligned).
+ *   - `dtype` selects the arithmetic type of quantities: SN_I32 (bit-exact integer
+ *     rollouts), SN_F32 / SN_F64 (fractional orders, e.g. TD3 actions).
+ *   - Return value: SN_OK (0) or a negative SN_ERR_* code; sn_last_error() gives text.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SUPPLYNET_H
+#define SUPPLYNET_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_ABI_VERSION 1
+
+#define SN_MAX_FACILITIES 4
+#define SN_OBS_PER_FACILITY 7   /* supplynetwork.py:151-169 */
+#define SN_STATE_WORDS 40       /* 28 observable + 12 hidden words per env */
+#define SN_INIT_WORDS 19        /* inv[4], sales orders (2,2,2,1), shipments (2,2,2,2) */
+#define SN_STATS_WORDS 16
+
+enum { SN_I32 = 0, SN_F32 = 1, SN_F64 = 2 };
+enum { SN_RULE_A = 0, SN_RULE_D_PLUS_A = 1 };
+enum {
+  SN_POLICY_ACTIONS = 0,      /* actions streamed from memory, [T][N][n_agents]            */
+  SN_POLICY_BASE_STOCK = 1    /* utils/heuristics.py base-stock evaluated in-kernel per env */
+};
+
+enum {
+  SN_OK = 0,
+  SN_ERR_INVALID = -1,      /* bad argument (maps to ValueError)                          */
+  SN_ERR_UNSUPPORTED = -2,  /* topology / lead times outside the serial beer-game chain   */
+  SN_ERR_TERMINAL = -3,     /* step after the episode ended (envs.py:88-89 ValueError)     */
+  SN_ERR_CUDA = -4,         /* CUDA runtime error                                          */
+  SN_ERR_TYPE = -5          /* non-integral constant with SN_I32 (maps to TypeError)       */
+};
+
+/* Scenario description: the constants hard-coded in the reference's factories
+ * (envs.py:163-286 "normal"/basic, :289-414 "uniform"/complex, :501-596 classic) plus the
+ * ordering rule of utils/wrappers.py:6-31.  Node k: 0 retailer .. 3 manufacturer; arc k is the
+ * arc whose customer is node k. */
+typedef struct sn_spec {
+  int32_t n_facilities;                       /* must be 4                                    */
+  int32_t info_leadtime[SN_MAX_FACILITIES];   /* must be 2,2,2,1 (envs.py:355-392)            */
+  int32_t ship_leadtime[SN_MAX_FACILITIES];   /* must be 2,2,2,2                              */
+  int32_t n_agents;                           /* 1..4                                         */
+  int32_t agents[SN_MAX_FACILITIES];          /* node index per action column, caller order   */
+                                              /* (supplynetwork.py:217); contiguous set       */
+  int32_t global_observable;                  /* envs.py:72-75                                */
+  int32_t max_episode_steps;                  /* envs.py:98                                   */
+  int32_t rule;                               /* SN_RULE_*                                    */
+  double holding_cost[SN_MAX_FACILITIES];     /* Node.unit_holding_cost                       */
+  double backorder_cost[SN_MAX_FACILITIES];   /* Node.unit_backorder_cost                     */
+  double coplayer_target[SN_MAX_FACILITIES];  /* BaseStockPolicy target of non-agent nodes    */
+  double coplayer_lb, coplayer_ub;            /* utils/heuristics.py:16 (0, 16)               */
+  double dpa_offset, dpa_lb, dpa_ub;          /* utils/wrappers.py:6                          */
+} sn_spec;
+
+/* Base-stock policy parameters (utils/heuristics.py:13-33), used by sn_heuristic and by
+ * sn_rollout with SN_POLICY_BASE_STOCK.  One target per action column. */
+typedef struct sn_policy {
+  double target[SN_MAX_FACILITIES];
+  double lb, ub;
+  int32_t rule;              /* SN_RULE_A: target-IP; SN_RULE_D_PLUS_A: target-IP-latest_demand */
+  int32_t row0_broadcast;    /* 1 = reproduce the reference's batch quirk (row 0 for all envs)   */
+} sn_policy;
+
+int32_t sn_abi_version(void);
+const char* sn_last_error(void);
+
+/* Number of observation columns for this spec: 7 * (4 if global_observable else n_agents)
+ * (envs.py:402-405).  Negative on invalid spec. */
+int32_t sn_obs_dim(const sn_spec* spec);
+
+/* Validates a spec for `dtype` (replaces the implicit checks of SupplyNetwork.__init__,
+ * supplynetwork.py:22-56; rejects non-contiguous agent sets that crash the reference at :199). */
+int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype);
+
+/* reset — replaces InventoryManagementEnvMultiPlayer.reset (envs.py:64-80):
+ * SupplyNetwork.reset (supplynetwork.py:94-105; Arc.reset network_components.py:138-168,
+ * Node.reset :293-319) followed by before_action(0) (supplynetwork.py:182-210).
+ *   init      device, dtype [SN_INIT_WORDS][ld]: inv[0..3]; sales orders so[k][j] for k=0..3
+ *             (j < info_leadtime[k], j = periods-1 until the supplier sees it); shipments
+ *             sh[k][j] for k=0..3 (j = periods-1 until arrival)
+ *   demand0   device, dtype [ld]: demand of period 0 (Node.reset :317-319)
+ *   state     device, dtype [SN_STATE_WORDS][ld] (out)
+ *   obs       device, float [n_envs][obs_dim] row-major (out, may be NULL) */
+int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
+                 const void* init, const void* demand0, void* state, float* obs, void* stream);
+
+/* step — replaces InventoryManagementEnvMultiPlayer.step (envs.py:82-113) for all envs in
+ * lockstep, including the d+a action rule (utils/wrappers.py:23-27) when spec->rule says so.
+ *   period        the period being played (0-based); the step is terminal when
+ *                 period + 1 >= max_episode_steps, in which case `obs` receives the terminal
+ *                 observation (no before_action; envs.py:98-101) and `state` is left at an
+ *                 unspecified post-terminal value: call sn_reset next.
+ *   actions       device, dtype [n_envs][n_agents] row-major (what VecEnv.step receives)
+ *   demand_next   device, dtype [ld]: demand of period+1 (Node.update_demand,
+ *                 network_components.py:347-348)
+ *   reward        device, float [n_envs] (out): SupplyNetwork.get_cost (supplynetwork.py:285-310),
+ *                 summed in double in the reference's order, rounded once to float
+ *   reward64      device, double [n_envs] (out, may be NULL): the unrounded value
+ *   cost          device, double [8][ld] (out, may be NULL): per-facility holding[0..3] and
+ *                 backorder[4..7] cost of this period (the cost-history entries :303-305)
+ *   ep_return     device, double [n_envs] (in/out, may be NULL): += reward (Monitor's "r")
+ *   stats         device, double [SN_STATS_WORDS] (in/out, may be NULL): += totals over envs:
+ *                 [0] env-steps, [1] sum reward, [2..5] sum holding cost per facility,
+ *                 [6..9] sum backorder cost per facility (warp/block reduced, one atomic per block)
+ * Returns SN_ERR_TERMINAL if period >= max_episode_steps. */
+int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period,
+                void* state, const void* actions, const void* demand_next,
+                float* obs, float* reward, double* reward64, double* cost, double* ep_return,
+                double* stats, void* stream);
+
+/* observation of the current state — SupplyNetwork.get_state (supplynetwork.py:114-171)
+ * flattened as envs.py:103-110.  obs: device float [n_envs][obs_dim]. */
+int32_t sn_observe(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
+                   const void* state, float* obs, void* stream);
+
+/* heuristic — replaces BaseStockPolicy.get_order_quantity (utils/heuristics.py:35-75), the
+ * ndarray path HgeTD3.predict calls (hge.py:157-167), evaluated per env.
+ *   obs      device, float [n_envs][7*n_cols] row-major (un-normalised observations)
+ *   actions  device, float [n_envs][n_cols] (out) */
+int32_t sn_heuristic(const sn_policy* policy, int32_t n_cols, int64_t n_envs,
+                     const float* obs, float* actions, void* stream);
+
+/* rollout — n_steps consecutive periods fused in one launch with the per-env state held
+ * on-chip (envs.py:82-113 iterated; policy = streamed actions or in-kernel base stock).
+ *   period0       first period to play; period0 + n_steps <= max_episode_steps
+ *   demand        device, dtype [max_episode_steps+3][ld] (utils/demands.py:21 "size+3"); row t is
+ *                 the demand of period t
+ *   actions       device, dtype [n_steps][n_envs][n_agents] (SN_POLICY_ACTIONS) or NULL
+ *   policy        base-stock parameters (SN_POLICY_BASE_STOCK) or NULL
+ *   traj_obs      device, float [n_steps][n_envs][obs_dim] (out, may be NULL)
+ *   traj_reward   device, float [n_steps][n_envs] (out, may be NULL)
+ *   traj_actions  device, float [n_steps][n_envs][n_agents] (out, may be NULL): the actions taken
+ *   obs           device, float [n_envs][obs_dim] (out, may be NULL): observation after the last step
+ *   ep_return     device, double [n_envs] (in/out, may be NULL)
+ *   stats         device, double [SN_STATS_WORDS] (in/out, may be NULL), as in sn_step */
+int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period0,
+                   int32_t n_steps, void* state, const void* demand, int32_t policy_kind,
+                   const void* actions, const sn_policy* policy, float* traj_obs, float* traj_reward,
+                   float* traj_actions, float* obs, double* ep_return, double* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPPLYNET_H */

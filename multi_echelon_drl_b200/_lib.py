@@ -1,0 +1,105 @@
+"""ctypes binding of the C ABI in include/supplynet.h (libsupplynet.so, built in-tree).
+
+There is deliberately no fallback: if the shared library is missing or a CUDA call fails the
+caller gets an exception, never a CPU result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsupplynet.so")
+
+SN_I32, SN_F32, SN_F64 = 0, 1, 2
+SN_RULE_A, SN_RULE_D_PLUS_A = 0, 1
+SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
+SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
+SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 1
+
+
+class SnSpec(C.Structure):
+    _fields_ = [
+        ("n_facilities", C.c_int32),
+        ("info_leadtime", C.c_int32 * 4),
+        ("ship_leadtime", C.c_int32 * 4),
+        ("n_agents", C.c_int32),
+        ("agents", C.c_int32 * 4),
+        ("global_observable", C.c_int32),
+        ("max_episode_steps", C.c_int32),
+        ("rule", C.c_int32),
+        ("holding_cost", C.c_double * 4),
+        ("backorder_cost", C.c_double * 4),
+        ("coplayer_target", C.c_double * 4),
+        ("coplayer_lb", C.c_double),
+        ("coplayer_ub", C.c_double),
+        ("dpa_offset", C.c_double),
+        ("dpa_lb", C.c_double),
+        ("dpa_ub", C.c_double),
+    ]
+
+
+class SnPolicy(C.Structure):
+    _fields_ = [
+        ("target", C.c_double * 4),
+        ("lb", C.c_double),
+        ("ub", C.c_double),
+        ("rule", C.c_int32),
+        ("row0_broadcast", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/supplynet.h one to one
+_P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
+SIGNATURES = {
+    "sn_abi_version": (_I32, []),
+    "sn_last_error": (C.c_char_p, []),
+    "sn_obs_dim": (_I32, [C.POINTER(SnSpec)]),
+    "sn_spec_validate": (_I32, [C.POINTER(SnSpec), _I32]),
+    "sn_reset": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P, _P, _P]),
+    "sn_step": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_observe": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P]),
+    "sn_heuristic": (_I32, [C.POINTER(SnPolicy), _I32, _I64, _P, _P, _P]),
+    "sn_rollout": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
+                          _P, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class SupplyNetError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsupplynet.so (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C multi_echelon_drl_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    if lib.sn_abi_version() != ABI_VERSION:
+        raise ImportError(f"libsupplynet ABI {lib.sn_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    """Map status codes to the exceptions the reference raises at the same places."""
+    if rc >= 0:
+        return rc
+    msg = load().sn_last_error().decode()
+    if rc == SN_ERR_TERMINAL or rc == SN_ERR_INVALID:
+        raise ValueError(msg)                      # envs.py:88-89
+    if rc == SN_ERR_TYPE:
+        raise TypeError(msg)                       # network_components.py:26-29
+    if rc == SN_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise SupplyNetError(msg)

@@ -1,0 +1,272 @@
+// supplynet_core.cuh — per-env beer-game recurrence held entirely in registers.
+//
+// One `Env<T>` is the collapsed state of one reference SupplyNetwork (supplynetwork.py:10-343
+// over network_components.py:8-383) for the serial 4-echelon chain: the Order/Shipment object
+// lists become fixed-size pipelines because lead times are fixed and `Arc.fill_orders`
+// (network_components.py:203-234) ships min(inventory, backlog) in aggregate.
+//
+// State word map (row index into the [SN_STATE_WORDS][ld] structure-of-arrays buffer):
+//   7k+0  inv[k]          on-hand inventory of node k            (supplynetwork.py:123)
+//   7k+1  k=0: unf_ind    unfilled independent demand of the retailer; the observed
+//                         "unfilled_demand" is lat[0] + unf_ind                     (:130-136)
+//         k>0: B[k-1]     backlog of arc k-1 = observed "unfilled_demand" of node k
+//   7k+2  lat[k]          "latest_demand": k=0: current demand; k>0: order that reached node k
+//                         at the last before_action                                 (:139)
+//   7k+3..6 U[k][0..3]    unreceived pipeline of arc k, newest first               (:165-167)
+//   28+k  info[k], k<3    order slip of arc k still one period away from its supplier
+//   31+2k+j ship[k][j]    shipment on arc k arriving after j+1 more sweeps
+//   39    B[3]            backlog at the external supplier (arc 3)
+// The first 28 words are the "global" observation of the reference (envs.py:103-110) except
+// word 1, which the observation reports as lat[0] + unf_ind (kept apart so that fractional
+// quantities accumulate exactly as Node.fill_independent_demand does).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sn {
+
+constexpr int kF = 4;
+constexpr int kObsPerNode = 7;
+constexpr int kStateWords = 40;
+constexpr int kInitWords = 19;
+constexpr int kStatsWords = 16;
+
+template <typename T>
+struct DevSpec {
+  T target[kF];        // co-player base-stock targets
+  T clb, cub;          // co-player clip (utils/heuristics.py:16)
+  T off, lb, ub;       // d+a rule (utils/wrappers.py:25-27)
+  double h[kF], b[kF];
+  int slot[kF];        // action column of node k, -1 = co-player
+  int obs_node[kF];    // nodes whose 7 numbers form the observation, in output order
+  int n_obs;
+  int n_agents;
+  int lo;              // first agent index: nodes below it order inside before_action
+  int rule;
+  int t_max;
+};
+
+template <typename T>
+struct DevPolicy {
+  T target[kF];
+  T lb, ub;
+  int rule;
+};
+
+template <typename T>
+struct Env {
+  T inv[kF], lat[kF], U[kF][4], B[kF], info[3], ship[kF][2], unf_ind;
+
+  // "unfilled_demand" of node k as SupplyNetwork.get_state reports it (supplynetwork.py:130-136)
+  __device__ __forceinline__ T unfilled(int k) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+};
+
+template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+template <> __device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+template <typename T> __device__ __forceinline__ T tclamp(T x, T lo, T hi) { return tmin(tmax(x, lo), hi); }
+
+// utils/heuristics.py:43-57,60-75: target - (on_hand + on_order - unfilled) [- latest], clipped.
+// on_order is summed slot 0..3 in that order, as both reference paths do.
+template <typename T>
+__device__ __forceinline__ T base_stock(T target, T inv, const T (&U)[4], T unf, T lat, T lb, T ub, int rule) {
+  T on_order = ((U[0] + U[1]) + U[2]) + U[3];
+  T q = target - (inv + on_order - unf);
+  if (rule == 1) q = q - lat;
+  return tclamp(q, lb, ub);
+}
+
+// Pack / unpack between the word map above and registers ------------------------------------
+template <typename T>
+__device__ __forceinline__ void env_from_words(Env<T>& e, const T (&w)[kStateWords]) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    e.inv[k] = w[7 * k];
+    if (k == 0) e.unf_ind = w[1]; else e.B[k - 1] = w[7 * k + 1];
+    e.lat[k] = w[7 * k + 2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e.U[k][j] = w[7 * k + 3 + j];
+    e.ship[k][0] = w[31 + 2 * k];
+    e.ship[k][1] = w[32 + 2 * k];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) e.info[k] = w[28 + k];
+  e.B[3] = w[39];
+}
+
+template <typename T>
+__device__ __forceinline__ void env_to_words(const Env<T>& e, T (&w)[kStateWords]) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    w[7 * k] = e.inv[k];
+    w[7 * k + 1] = (k == 0) ? e.unf_ind : e.B[k - 1];
+    w[7 * k + 2] = e.lat[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[7 * k + 3 + j] = e.U[k][j];
+    w[31 + 2 * k] = e.ship[k][0];
+    w[32 + 2 * k] = e.ship[k][1];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[28 + k] = e.info[k];
+  w[39] = e.B[3];
+}
+
+// reset: Arc.reset / Node.reset (network_components.py:138-168, 293-319) + before_action(0).
+// init words: inv[0..3]; so[k][j] at 4 + {0,2,4,6}[k] + j; sh[k][j] at 11 + 2k + j.
+template <typename T>
+__device__ __forceinline__ void env_reset(Env<T>& e, const T (&in)[kInitWords], T d0) {
+  const int so_off[kF] = {4, 6, 8, 10};
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    const T so0 = in[so_off[k]];
+    const T so1 = (k < 3) ? in[so_off[k] + 1] : T(0);
+    const T sh0 = in[11 + 2 * k], sh1 = in[12 + 2 * k];
+    e.inv[k] = in[k];
+    // U = ([0]*4 + shipments + sales_orders)[::-1][:5]   (network_components.py:168), then
+    // before_action pops the last slot into its neighbour (supplynetwork.py:198-199).
+    if (k < 3) {            // [so1, so0, sh1, sh0, 0] -> [so1, so0, sh1, sh0]
+      e.U[k][0] = so1; e.U[k][1] = so0; e.U[k][2] = sh1; e.U[k][3] = sh0;
+      e.info[k] = so1;      // so0 reaches the supplier in before_action(0)
+    } else {                // [so0, sh1, sh0, 0, 0] -> [so0, sh1, sh0, 0]
+      e.U[k][0] = so0; e.U[k][1] = sh1; e.U[k][2] = sh0; e.U[k][3] = T(0);
+    }
+    e.ship[k][0] = sh0; e.ship[k][1] = sh1;
+    // order slip with remaining lead time 1 arrives now: backlog and latest demand of the supplier
+    e.B[k] = so0;
+    if (k < 3) e.lat[k + 1] = so0;
+  }
+  e.unf_ind = T(0);
+  e.lat[0] = d0;            // current_external_demand (network_components.py:317-319)
+}
+
+// Observation of node k (supplynetwork.py:151-169).  A co-player with index < first agent has
+// already ordered inside before_action when the reference observes it, so (on non-terminal
+// observations) its pipeline shows [its order, U0, U1, U2] (5-slot list, first four read).
+template <typename T>
+__device__ __forceinline__ void node_obs(const Env<T>& e, const DevSpec<T>& sp, int k, bool terminal, float* o) {
+  T u0 = T(0), u1 = T(0), u2 = T(0), u3 = T(0), inv = T(0), unf = T(0), lat = T(0), tg = T(0);
+#pragma unroll
+  for (int j = 0; j < kF; ++j)
+    if (j == k) {
+      inv = e.inv[j]; unf = e.unfilled(j); lat = e.lat[j]; tg = sp.target[j];
+      u0 = e.U[j][0]; u1 = e.U[j][1]; u2 = e.U[j][2]; u3 = e.U[j][3];
+    }
+  if (k < sp.lo && !terminal) {
+    const T U[4] = {u0, u1, u2, u3};
+    const T q = tmax(base_stock(tg, inv, U, unf, lat, sp.clb, sp.cub, 0), T(0));
+    u3 = u2; u2 = u1; u1 = u0; u0 = q;
+  }
+  o[0] = (float)inv; o[1] = (float)unf; o[2] = (float)lat;
+  o[3] = (float)u0; o[4] = (float)u1; o[5] = (float)u2; o[6] = (float)u3;
+}
+
+// envs.py:103-110: concatenation over internal nodes (global) or agent-managed facilities.
+template <typename T>
+__device__ __forceinline__ void env_obs(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float (&o)[28]) {
+#pragma unroll
+  for (int i = 0; i < kF; ++i)
+    if (i < sp.n_obs) node_obs(e, sp, sp.obs_node[i], terminal, &o[7 * i]);
+}
+
+struct StepOut {
+  double reward;
+  double hold[kF], back[kF];
+};
+
+// Orders of all four nodes for this period.  Each depends only on start-of-period quantities
+// (every information lead time is >= 1), so they are computed before the shipment sweep:
+// agent-managed nodes take their action column (through the d+a rule of utils/wrappers.py:25-27
+// when selected), the others their own base-stock policy (network_components.py:361-366).
+template <typename T>
+__device__ __forceinline__ void env_orders(const Env<T>& e, const DevSpec<T>& sp, const T (&a)[kF], T (&q)[kF]) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    T x;
+    if (sp.slot[k] >= 0) {
+      x = a[0];
+#pragma unroll
+      for (int i = 1; i < kF; ++i) if (sp.slot[k] == i) x = a[i];
+      if (sp.rule == 1) x = tclamp(e.lat[k] + x + sp.off, sp.lb, sp.ub);
+    } else {
+      x = base_stock(sp.target[k], e.inv[k], e.U[k], e.unfilled(k), e.lat[k], sp.clb, sp.cub, 0);
+    }
+    q[k] = tmax(x, T(0));                                                  // network_components.py:368-374
+  }
+}
+
+// One period: agent_action + after_action + get_cost + (before_action | terminal observation).
+//   q[k]      order placed by node k this period (env_orders)
+//   d_next    demand of the next period
+//   terminal  period + 1 >= max_episode_steps
+// On a terminal step `e` becomes the *terminal observation view* (envs.py:98-110: no
+// before_action, 5-slot pipelines of which the first four are read, stale latest demand) and is
+// not a valid state any more.
+template <typename T>
+__device__ __forceinline__ void env_step(Env<T>& e, const DevSpec<T>& sp, const T (&q)[kF], T d_next,
+                                         bool terminal, StepOut& out) {
+  // ---- after_action sweep, upstream first (supplynetwork.py:241-264)
+  T U4[kF];   // fifth (oldest) slot of [q, U0, U1, U2, U3] after this period's arrivals
+#pragma unroll
+  for (int k = kF - 1; k >= 0; --k) {
+    T u[5] = {q[k], e.U[k][0], e.U[k][1], e.U[k][2], e.U[k][3]};           // U.insert(0, q)
+    const T arr = e.ship[k][0];                                            // advance_and_receive_shipments
+    e.ship[k][0] = e.ship[k][1];
+    e.inv[k] = e.inv[k] + arr;
+    T rem = arr;
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {                                         // :250-255, oldest slot first
+      const T f = tmin(u[i], rem);
+      u[i] = u[i] - f;
+      rem = rem - f;
+    }
+    T s;
+    if (k == kF - 1) {
+      s = e.B[k];                                                          // external supplier: unlimited
+    } else {
+      s = tmin(e.inv[k + 1], e.B[k]);                                      // Arc.fill_orders in aggregate
+      e.inv[k + 1] = e.inv[k + 1] - s;
+    }
+    e.ship[k][1] = s;
+    e.B[k] = e.B[k] - s;
+    e.U[k][0] = u[0]; e.U[k][1] = u[1]; e.U[k][2] = u[2]; e.U[k][3] = u[3];
+    U4[k] = u[4];
+  }
+  // retailer fills independent demand (network_components.py:323-345)
+  const T tot = e.lat[0] + e.unf_ind;
+  const T sold = tmax(T(0), tmin(e.inv[0], tot));
+  e.inv[0] = e.inv[0] - sold;
+  e.unf_ind = tot - sold;
+
+  // ---- get_cost (supplynetwork.py:285-310): node-list order, c_h and c_b accumulated apart
+  double ch = 0.0, cb = 0.0;
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
+    out.hold[k] = -(double)e.inv[k] * sp.h[k];
+    out.back[k] = -(double)unfk * sp.b[k];
+    ch += out.hold[k];
+    cb += out.back[k];
+  }
+  out.reward = ch + cb;
+
+  e.lat[0] = d_next;                                                       // Node.update_demand (:266-268)
+  // ---- next period (envs.py:96-101)
+  if (!terminal) {
+    // before_action (supplynetwork.py:185-199): slips advance, the arrived slip joins the backlog
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T arrived = e.info[k];
+      e.info[k] = q[k];
+      e.lat[k + 1] = arrived;
+      e.B[k] = e.B[k] + arrived;
+    }
+    e.B[3] = e.B[3] + q[3];                   // info lead time 1: this period's order arrives now
+#pragma unroll
+    for (int k = 0; k < kF; ++k) e.U[k][3] = e.U[k][3] + U4[k];            // pop last, merge (:198-199)
+  }
+}
+
+}  // namespace sn

@@ -1,0 +1,664 @@
+// supplynet_kernels.cu — sm_100a kernels and the C ABI of include/supplynet.h.
+//
+// Kernels (one thread = one env, structure-of-arrays state so every row access of a warp is
+// one fully used 128-byte line):
+//   k_reset    init rows -> state rows (+ observation)
+//   k_step     one period for all envs: 40 state rows in, 40 out, actions/demand in, reward out
+//   k_observe  state -> observation
+//   k_rollout  n_steps periods with the env held in registers; actions streamed or base-stock
+//              policy evaluated in-kernel; optional trajectory out
+//   k_heuristic  BaseStockPolicy on a batch of observations
+// Row-major float observations ([n_envs][obs_dim], what a VecEnv returns) are staged per warp
+// in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
+// the 112-byte-per-thread pattern reaches L2 as full lines.
+#include "supplynet_core.cuh"
+#include "../../include/supplynet.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace sn {
+
+constexpr int kBlock = 128;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+
+// ------------------------------------------------------------------------------------------
+// Observation tile writer.  Each warp owns 32 consecutive envs = one contiguous span of
+// 32*od floats in the row-major output.  Lanes deposit their `od` floats in shared memory
+// (stride od words: conflict-free for od = 7, 21, 28-as-float4), then lane 0 issues one bulk
+// store.  Partial warps (tail of the batch) and unaligned outputs use plain stores.
+struct ObsStager {
+  float* smem;     // this warp's staging area: [2][32*28] floats
+  int lane;
+  __device__ __forceinline__ ObsStager(float* block_smem) {
+    const int warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    smem = block_smem + warp * (2 * 32 * 28);
+  }
+  // `buf` alternates 0/1 between consecutive calls of the same warp; at most one earlier
+  // bulk store of this warp may still be reading the other buffer.
+  __device__ __forceinline__ void store(float* gobs, int64_t env0_of_warp, int64_t n_envs, int od, bool valid,
+                                        const float (&o)[28], int buf, bool use_tma) {
+    const bool full = (env0_of_warp + 32 <= n_envs);
+    if (use_tma && full) {
+      float* s = smem + buf * (32 * 28);
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      float* mine = s + lane * od;
+      if (od == 28) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          reinterpret_cast<float4*>(mine)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 28; ++j)
+          if (j < od) mine[j] = o[j];
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store_s2g(gobs + env0_of_warp * od, s, (uint32_t)(32 * od * sizeof(float)));
+        bulk_commit();
+      }
+    } else if (valid) {
+      float* g = gobs + (env0_of_warp + lane) * od;
+#pragma unroll
+      for (int j = 0; j < 28; ++j)
+        if (j < od) g[j] = o[j];
+    }
+  }
+  __device__ __forceinline__ void drain() {
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+};
+
+// actions row-major [n][na]
+template <typename T>
+__device__ __forceinline__ void load_actions(const T* __restrict__ act, int64_t env, int na, T (&a)[kF]) {
+  const T* p = act + env * na;
+  if (na == 4 && sizeof(T) == 4) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    a[0] = *reinterpret_cast<const T*>(&v.x);
+    a[1] = *reinterpret_cast<const T*>(&v.y);
+    a[2] = *reinterpret_cast<const T*>(&v.z);
+    a[3] = *reinterpret_cast<const T*>(&v.w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kF; ++i) a[i] = (i < na) ? __ldg(p + i) : T(0);
+  }
+}
+
+// block-level reduction of per-thread totals into stats[] (one atomic per block per word)
+template <int NV>
+__device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __restrict__ stats, double* red /*[warps][NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[warp * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) x += red[w * NV + threadIdx.x];
+    atomicAdd(&stats[threadIdx.x], x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
+        const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs, int use_tma) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = env < n;
+  Env<T> e;
+  if (valid) {
+    T in[kInitWords];
+#pragma unroll
+    for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + env);
+    env_reset(e, in, __ldg(demand0 + env));
+    T w[kStateWords];
+    env_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+  }
+  if (obs != nullptr) {
+    float o[28];
+    if (valid) env_obs(e, sp, false, o);
+    ObsStager st(smem_f);
+    st.store(obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+    st.drain();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
+          float* __restrict__ obs, int use_tma) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = env < n;
+  Env<T> e;
+  float o[28];
+  if (valid) {
+    T w[kStateWords];
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
+    env_from_words(e, w);
+    env_obs(e, sp, false, o);
+  }
+  ObsStager st(smem_f);
+  st.store(obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+  st.drain();
+}
+
+struct StepPtrs {
+  float* obs;
+  float* reward;
+  double* reward64;
+  double* cost;
+  double* ep_return;
+  double* stats;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
+       const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ double red[kWarpsPerBlock * 10];
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = env < n;
+  Env<T> e;
+  StepOut so;
+  so.reward = 0.0;
+#pragma unroll
+  for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
+  if (valid) {
+    T w[kStateWords];
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
+    T a[kF];
+    load_actions(actions, env, sp.n_agents, a);
+    const T dn = __ldg(demand_next + env);
+    env_from_words(e, w);
+    T q[kF];
+    env_orders(e, sp, a, q);
+    env_step(e, sp, q, dn, terminal != 0, so);
+    env_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+    if (out.reward) out.reward[env] = (float)so.reward;
+    if (out.reward64) out.reward64[env] = so.reward;
+    if (out.cost) {
+#pragma unroll
+      for (int k = 0; k < kF; ++k) {
+        out.cost[k * ld + env] = so.hold[k];
+        out.cost[(kF + k) * ld + env] = so.back[k];
+      }
+    }
+    if (out.ep_return) out.ep_return[env] += so.reward;
+  }
+  if (out.obs != nullptr) {
+    float o[28];
+    if (valid) env_obs(e, sp, terminal != 0, o);
+    ObsStager st(smem_f);
+    st.store(out.obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+    st.drain();
+  }
+  if (out.stats != nullptr) {
+    double v[10];
+    v[0] = valid ? 1.0 : 0.0;
+    v[1] = so.reward;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) { v[2 + k] = so.hold[k]; v[6 + k] = so.back[k]; }
+    block_reduce_add<10>(v, out.stats, red);
+  }
+}
+
+struct RolloutPtrs {
+  float* traj_obs;
+  float* traj_reward;
+  float* traj_actions;
+  float* obs;
+  double* ep_return;
+  double* stats;
+};
+
+template <typename T, int POLICY>
+__global__ void __launch_bounds__(kBlock)
+k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
+          int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
+          const T* __restrict__ actions, const RolloutPtrs out, int use_tma) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ double red[kWarpsPerBlock * 10];
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = env < n;
+  const int64_t envc = valid ? env : (n - 1);       // tail lanes shadow the last env (loads only)
+  const int na = sp.n_agents;
+  const int od = 7 * sp.n_obs;
+  ObsStager st(smem_f);
+
+  Env<T> e;
+  {
+    T w[kStateWords];
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + envc];
+    env_from_words(e, w);
+  }
+  double acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+
+  // software pipeline: inputs of step t+1 are requested before step t is computed
+  T a_pre[kF] = {T(0), T(0), T(0), T(0)};
+  if (POLICY == SN_POLICY_ACTIONS) load_actions(actions, envc, na, a_pre);
+  T d_pre = __ldg(demand + (int64_t)(period0 + 1) * ld + envc);
+
+  for (int s = 0; s < n_steps; ++s) {
+    const int t = period0 + s;
+    const bool terminal = (t + 1 >= sp.t_max);
+    T a[kF];
+#pragma unroll
+    for (int i = 0; i < kF; ++i) a[i] = a_pre[i];
+    const T dn = d_pre;
+    if (s + 1 < n_steps) {
+      if (POLICY == SN_POLICY_ACTIONS) load_actions(actions + (int64_t)(s + 1) * n * na, envc, na, a_pre);
+      d_pre = __ldg(demand + (int64_t)(t + 2) * ld + envc);
+    }
+    if (POLICY == SN_POLICY_BASE_STOCK) {
+      // BaseStockPolicy.get_order_quantity on this env's own observation (utils/heuristics.py:43-57)
+#pragma unroll
+      for (int k = 0; k < kF; ++k) {
+        if (sp.slot[k] >= 0) {
+          T tg = pol.target[0];
+#pragma unroll
+          for (int i = 1; i < kF; ++i) if (sp.slot[k] == i) tg = pol.target[i];
+          const T x = base_stock(tg, e.inv[k], e.U[k], e.unfilled(k), e.lat[k], pol.lb, pol.ub, pol.rule);
+#pragma unroll
+          for (int i = 0; i < kF; ++i) if (sp.slot[k] == i) a[i] = x;
+        }
+      }
+    }
+    if (out.traj_actions != nullptr && valid) {
+      float* g = out.traj_actions + ((int64_t)s * n + env) * na;
+      if (na == 4) {
+        *reinterpret_cast<float4*>(g) = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kF; ++i) if (i < na) g[i] = (float)a[i];
+      }
+    }
+    T q[kF];
+    env_orders(e, sp, a, q);
+    StepOut so;
+    env_step(e, sp, q, dn, terminal, so);
+    acc[0] += 1.0;
+    acc[1] += so.reward;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
+    if (out.traj_reward != nullptr && valid) out.traj_reward[(int64_t)s * n + env] = (float)so.reward;
+    if (out.traj_obs != nullptr) {
+      float o[28];
+      env_obs(e, sp, terminal, o);
+      st.store(out.traj_obs + (int64_t)s * n * od, env - (threadIdx.x & 31), n, od, valid, o, s & 1, use_tma != 0);
+    }
+  }
+
+  const bool ended = (period0 + n_steps >= sp.t_max);
+  if (out.obs != nullptr) {
+    float o[28];
+    env_obs(e, sp, ended, o);
+    st.store(out.obs, env - (threadIdx.x & 31), n, od, valid, o, n_steps & 1, use_tma != 0);
+  }
+  st.drain();
+  if (valid) {
+    T w[kStateWords];
+    env_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+    if (out.ep_return) out.ep_return[env] += acc[1];
+  }
+  if (out.stats != nullptr) {
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+    }
+    block_reduce_add<10>(acc, out.stats, red);
+  }
+}
+
+// BaseStockPolicy.get_order_quantity, ndarray path (utils/heuristics.py:43-57,75), per env.
+// float32 sums of the observation terms, float64 subtraction from the target and clip, as numpy
+// evaluates `int64_targets - (f32 + f32 - f32) [- f32]`.
+__global__ void __launch_bounds__(kBlock)
+k_heuristic(const __grid_constant__ sn_policy pol, int ncols, int64_t n, const float* __restrict__ obs,
+            float* __restrict__ actions) {
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (env >= n) return;
+  const int od = 7 * ncols;
+  const float* p = obs + (pol.row0_broadcast ? 0 : env * od);
+  float o[28];
+  if (ncols == 4 && !pol.row0_broadcast) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + j);
+      o[4 * j] = v.x; o[4 * j + 1] = v.y; o[4 * j + 2] = v.z; o[4 * j + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 28; ++j) o[j] = (j < od) ? __ldg(p + j) : 0.f;
+  }
+  float r[kF];
+#pragma unroll
+  for (int c = 0; c < kF; ++c) {
+    const float on_order = __fadd_rn(__fadd_rn(__fadd_rn(o[7 * c + 3], o[7 * c + 4]), o[7 * c + 5]), o[7 * c + 6]);
+    const float ip = __fsub_rn(__fadd_rn(o[7 * c], on_order), o[7 * c + 1]);
+    double q = pol.target[c] - (double)ip;
+    if (pol.rule == SN_RULE_D_PLUS_A) q -= (double)o[7 * c + 2];
+    q = fmin(fmax(q, pol.lb), pol.ub);
+    r[c] = (float)q;
+  }
+  float* g = actions + env * ncols;
+  if (ncols == 4) {
+    *reinterpret_cast<float4*>(g) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < kF; ++c) if (c < ncols) g[c] = r[c];
+  }
+}
+
+}  // namespace sn
+
+// ==========================================================================================
+// Host side: validation, spec lowering, launches.
+// ==========================================================================================
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && std::fabs(x) < 2147483647.0; }
+
+int validate(const sn_spec* s, int dtype) {
+  if (s == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
+  if (dtype != SN_I32 && dtype != SN_F32 && dtype != SN_F64) return fail(SN_ERR_INVALID, "unknown dtype %d", dtype);
+  if (s->n_facilities != 4) return fail(SN_ERR_UNSUPPORTED, "only the 4-echelon serial chain is supported (n_facilities=%d)", s->n_facilities);
+  const int li[4] = {2, 2, 2, 1};
+  for (int k = 0; k < 4; ++k) {
+    if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2)
+      return fail(SN_ERR_UNSUPPORTED, "arc %d: lead times (%d,%d) unsupported; the beer-game chain uses info (2,2,2,1), shipment 2",
+                  k, s->info_leadtime[k], s->ship_leadtime[k]);
+  }
+  if (s->n_agents < 1 || s->n_agents > 4) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
+  int seen = 0, lo = 4, hi = -1;
+  for (int i = 0; i < s->n_agents; ++i) {
+    const int k = s->agents[i];
+    if (k < 0 || k > 3) return fail(SN_ERR_INVALID, "agents[%d]=%d out of range", i, k);
+    if (seen & (1 << k)) return fail(SN_ERR_INVALID, "facility %d listed twice", k);
+    seen |= 1 << k;
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+  if (hi - lo + 1 != s->n_agents)
+    return fail(SN_ERR_INVALID, "agent-managed facilities must be a contiguous block of the chain "
+                                "(the reference crashes otherwise, supplynetwork.py:199)");
+  if (s->max_episode_steps < 1) return fail(SN_ERR_INVALID, "max_episode_steps=%d", s->max_episode_steps);
+  if (s->rule != SN_RULE_A && s->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown rule %d", s->rule);
+  if (dtype == SN_I32) {
+    for (int k = 0; k < 4; ++k)
+      if (!is_integral(s->coplayer_target[k])) return fail(SN_ERR_TYPE, "coplayer_target[%d] must be integral for SN_I32", k);
+    if (!is_integral(s->coplayer_lb) || !is_integral(s->coplayer_ub)) return fail(SN_ERR_TYPE, "co-player bounds must be integral for SN_I32");
+    if (s->rule == SN_RULE_D_PLUS_A && (!is_integral(s->dpa_offset) || !is_integral(s->dpa_lb) || !is_integral(s->dpa_ub)))
+      return fail(SN_ERR_TYPE, "d+a offset/bounds must be integral for SN_I32");
+  }
+  return SN_OK;
+}
+
+template <typename T>
+sn::DevSpec<T> lower(const sn_spec* s) {
+  sn::DevSpec<T> d;
+  std::memset(&d, 0, sizeof(d));
+  int lo = 4;
+  for (int k = 0; k < 4; ++k) {
+    d.target[k] = (T)s->coplayer_target[k];
+    d.h[k] = s->holding_cost[k];
+    d.b[k] = s->backorder_cost[k];
+    d.slot[k] = -1;
+  }
+  for (int i = 0; i < s->n_agents; ++i) {
+    d.slot[s->agents[i]] = i;
+    lo = s->agents[i] < lo ? s->agents[i] : lo;
+  }
+  d.clb = (T)s->coplayer_lb; d.cub = (T)s->coplayer_ub;
+  d.off = (T)s->dpa_offset; d.lb = (T)s->dpa_lb; d.ub = (T)s->dpa_ub;
+  if (s->global_observable) {
+    d.n_obs = 4;
+    for (int k = 0; k < 4; ++k) d.obs_node[k] = k;
+  } else {
+    d.n_obs = s->n_agents;
+    for (int i = 0; i < s->n_agents; ++i) d.obs_node[i] = s->agents[i];
+  }
+  d.n_agents = s->n_agents;
+  d.lo = lo;
+  d.rule = s->rule;
+  d.t_max = s->max_episode_steps;
+  return d;
+}
+
+template <typename T>
+int lower_policy(const sn_policy* p, int dtype, int ncols, sn::DevPolicy<T>* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (p == nullptr) return SN_OK;
+  for (int i = 0; i < 4; ++i) {
+    if (dtype == SN_I32 && i < ncols && !is_integral(p->target[i])) return fail(SN_ERR_TYPE, "policy target[%d] must be integral for SN_I32", i);
+    out->target[i] = (T)p->target[i];
+  }
+  if (dtype == SN_I32 && (!is_integral(p->lb) || !is_integral(p->ub))) return fail(SN_ERR_TYPE, "policy bounds must be integral for SN_I32");
+  out->lb = (T)p->lb; out->ub = (T)p->ub; out->rule = p->rule;
+  return SN_OK;
+}
+
+int check_batch(int64_t n, int64_t ld) {
+  if (n < 1) return fail(SN_ERR_INVALID, "n_envs=%lld must be >= 1", (long long)n);
+  if (ld < n || (ld % 4) != 0) return fail(SN_ERR_INVALID, "ld=%lld must be >= n_envs and a multiple of 4", (long long)ld);
+  if ((n + sn::kBlock - 1) / sn::kBlock > 2147483647LL) return fail(SN_ERR_INVALID, "n_envs too large");
+  return SN_OK;
+}
+
+int cuda_ok(const char* what) {
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+  return SN_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// TMA bulk stores need a 16-byte aligned destination for every warp span (32*od*4 bytes is
+// always a multiple of 16) and a 16-byte multiple size.
+inline int tma_ok(const float* obs) { return obs != nullptr && aligned16(obs) ? 1 : 0; }
+
+constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * 28 * sizeof(float);   // 28,672 B
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + sn::kBlock - 1) / sn::kBlock); }
+
+template <typename T>
+int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
+             float* obs, cudaStream_t st) {
+  const auto d = lower<T>(spec);
+  sn::k_reset<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
+  return cuda_ok("sn_reset launch");
+}
+
+template <typename T>
+int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
+  const auto d = lower<T>(spec);
+  sn::k_observe<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
+  return cuda_ok("sn_observe launch");
+}
+
+template <typename T>
+int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
+            const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
+  const auto d = lower<T>(spec);
+  sn::k_step<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
+                                                          (const T*)demand_next, out, tma_ok(out.obs));
+  return cuda_ok("sn_step launch");
+}
+
+template <typename T>
+int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period0, int n_steps, void* state,
+               const void* demand, int policy_kind, const void* actions, const sn_policy* policy,
+               const sn::RolloutPtrs& out, cudaStream_t st) {
+  const auto d = lower<T>(spec);
+  sn::DevPolicy<T> p;
+  const int rc = lower_policy<T>(policy, dtype, spec->n_agents, &p);
+  if (rc != SN_OK) return rc;
+  const int tma = (out.traj_obs == nullptr || aligned16(out.traj_obs)) && (out.obs == nullptr || aligned16(out.obs)) &&
+                  (((int64_t)n * 7 * d.n_obs * 4) % 16 == 0);
+  if (policy_kind == SN_POLICY_ACTIONS)
+    sn::k_rollout<T, SN_POLICY_ACTIONS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(
+        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma);
+  else
+    sn::k_rollout<T, SN_POLICY_BASE_STOCK><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(
+        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, tma);
+  return cuda_ok("sn_rollout launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sn_abi_version(void) { return SN_ABI_VERSION; }
+
+const char* sn_last_error(void) { return g_err; }
+
+int32_t sn_obs_dim(const sn_spec* spec) {
+  if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
+  if (spec->n_agents < 1 || spec->n_agents > 4) return fail(SN_ERR_INVALID, "n_agents=%d out of range", spec->n_agents);
+  return SN_OBS_PER_FACILITY * (spec->global_observable ? 4 : spec->n_agents);
+}
+
+int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype) { return validate(spec, dtype); }
+
+int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const void* init,
+                 const void* demand0, void* state, float* obs, void* stream) {
+  int rc = validate(spec, dtype);
+  if (rc != SN_OK) return rc;
+  if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
+  if (!init || !demand0 || !state) return fail(SN_ERR_INVALID, "sn_reset: init, demand0 and state must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: return do_reset<int32_t>(spec, n_envs, ld, init, demand0, state, obs, st);
+    case SN_F32: return do_reset<float>(spec, n_envs, ld, init, demand0, state, obs, st);
+    default: return do_reset<double>(spec, n_envs, ld, init, demand0, state, obs, st);
+  }
+}
+
+int32_t sn_observe(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const void* state, float* obs,
+                   void* stream) {
+  int rc = validate(spec, dtype);
+  if (rc != SN_OK) return rc;
+  if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
+  if (!state || !obs) return fail(SN_ERR_INVALID, "sn_observe: state and obs must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: return do_observe<int32_t>(spec, n_envs, ld, state, obs, st);
+    case SN_F32: return do_observe<float>(spec, n_envs, ld, state, obs, st);
+    default: return do_observe<double>(spec, n_envs, ld, state, obs, st);
+  }
+}
+
+int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period, void* state,
+                const void* actions, const void* demand_next, float* obs, float* reward, double* reward64,
+                double* cost, double* ep_return, double* stats, void* stream) {
+  int rc = validate(spec, dtype);
+  if (rc != SN_OK) return rc;
+  if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
+  if (period < 0) return fail(SN_ERR_INVALID, "period=%d", period);
+  if (period >= spec->max_episode_steps)
+    return fail(SN_ERR_TERMINAL, "Cannot take action when the state is terminal.");     // envs.py:88-89
+  if (!state || !actions || !demand_next) return fail(SN_ERR_INVALID, "sn_step: state, actions and demand_next must be non-NULL");
+  if (spec->n_agents == 4 && dtype != SN_F64 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_step: actions must be 16-byte aligned");
+  const int terminal = (period + 1 >= spec->max_episode_steps) ? 1 : 0;
+  const sn::StepPtrs out{obs, reward, reward64, cost, ep_return, stats};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: return do_step<int32_t>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
+    case SN_F32: return do_step<float>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
+    default: return do_step<double>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
+  }
+}
+
+int32_t sn_heuristic(const sn_policy* policy, int32_t n_cols, int64_t n_envs, const float* obs, float* actions,
+                     void* stream) {
+  if (!policy || !obs || !actions) return fail(SN_ERR_INVALID, "sn_heuristic: NULL argument");
+  if (n_cols < 1 || n_cols > 4) return fail(SN_ERR_INVALID, "n_cols=%d out of range", n_cols);
+  if (n_envs < 1) return fail(SN_ERR_INVALID, "n_envs=%lld must be >= 1", (long long)n_envs);
+  if (policy->rule != SN_RULE_A && policy->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown rule %d", policy->rule);
+  if (n_cols == 4 && (!aligned16(obs) || !aligned16(actions))) return fail(SN_ERR_INVALID, "sn_heuristic: obs/actions must be 16-byte aligned");
+  sn::k_heuristic<<<grid_for(n_envs), sn::kBlock, 0, (cudaStream_t)stream>>>(*policy, n_cols, n_envs, obs, actions);
+  return cuda_ok("sn_heuristic launch");
+}
+
+int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period0, int32_t n_steps,
+                   void* state, const void* demand, int32_t policy_kind, const void* actions,
+                   const sn_policy* policy, float* traj_obs, float* traj_reward, float* traj_actions, float* obs,
+                   double* ep_return, double* stats, void* stream) {
+  int rc = validate(spec, dtype);
+  if (rc != SN_OK) return rc;
+  if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
+  if (period0 < 0 || n_steps < 1) return fail(SN_ERR_INVALID, "period0=%d n_steps=%d", period0, n_steps);
+  if (period0 >= spec->max_episode_steps)
+    return fail(SN_ERR_TERMINAL, "Cannot take action when the state is terminal.");
+  if (period0 + n_steps > spec->max_episode_steps)
+    return fail(SN_ERR_INVALID, "rollout of %d steps from period %d crosses the episode end (%d)", n_steps, period0, spec->max_episode_steps);
+  if (!state || !demand) return fail(SN_ERR_INVALID, "sn_rollout: state and demand must be non-NULL");
+  if (policy_kind == SN_POLICY_ACTIONS) {
+    if (!actions) return fail(SN_ERR_INVALID, "sn_rollout: actions must be non-NULL for SN_POLICY_ACTIONS");
+    if (spec->n_agents == 4 && dtype != SN_F64 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_rollout: actions must be 16-byte aligned");
+  } else if (policy_kind == SN_POLICY_BASE_STOCK) {
+    if (!policy) return fail(SN_ERR_INVALID, "sn_rollout: policy must be non-NULL for SN_POLICY_BASE_STOCK");
+    if (policy->rule != SN_RULE_A && policy->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown policy rule %d", policy->rule);
+  } else {
+    return fail(SN_ERR_INVALID, "unknown policy_kind %d", policy_kind);
+  }
+  if (traj_actions && spec->n_agents == 4 && !aligned16(traj_actions)) return fail(SN_ERR_INVALID, "sn_rollout: traj_actions must be 16-byte aligned");
+  const sn::RolloutPtrs out{traj_obs, traj_reward, traj_actions, obs, ep_return, stats};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: return do_rollout<int32_t>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
+    case SN_F32: return do_rollout<float>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
+    default: return do_rollout<double>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
+  }
+}
+
+}  // extern "C"

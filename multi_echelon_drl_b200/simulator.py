@@ -1,0 +1,215 @@
+"""BatchedSupplyNetwork: N independent serial beer games stepped in lockstep on one B200.
+
+This is the device-side stand-in for N instances of the reference's `SupplyNetwork` wrapped in
+`InventoryManagementEnvMultiPlayer` (supplynetwork.py:10-343, envs.py:29-117).  It owns the
+structure-of-arrays state tensor and the per-episode demand table and drives the CUDA kernels
+through the C ABI (include/supplynet.h).  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spec import ScenarioSpec
+
+_DTYPES = {
+    "int32": (_lib.SN_I32, torch.int32), "i32": (_lib.SN_I32, torch.int32),
+    "float32": (_lib.SN_F32, torch.float32), "f32": (_lib.SN_F32, torch.float32),
+    "float64": (_lib.SN_F64, torch.float64), "f64": (_lib.SN_F64, torch.float64),
+}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BasePolicyParams:
+    """Parameters of a base-stock policy (utils/heuristics.py:13-33) in C form."""
+
+    def __init__(self, target_levels, lb=0, ub=16, rule="a", row0_broadcast=False):
+        tl = np.asarray(target_levels, dtype=np.float64).reshape(-1)
+        if not 1 <= tl.shape[0] <= 4:
+            raise ValueError("target_levels must have 1..4 entries")
+        if rule not in ("a", "d+a"):
+            raise ValueError(f"rule must be 'a' or 'd+a', got {rule!r}")
+        self.n_cols = tl.shape[0]
+        self.c = _lib.SnPolicy()
+        for i in range(4):
+            self.c.target[i] = float(tl[i]) if i < self.n_cols else 0.0
+        self.c.lb, self.c.ub = float(lb), float(ub)
+        self.c.rule = _lib.SN_RULE_D_PLUS_A if rule == "d+a" else _lib.SN_RULE_A
+        self.c.row0_broadcast = int(bool(row0_broadcast))
+
+
+class BatchedSupplyNetwork:
+    def __init__(self, spec: ScenarioSpec, n_envs: int, device="cuda", dtype="int32"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedSupplyNetwork needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _lib.load()
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self.spec = spec
+        self.n_envs = int(n_envs)
+        if self.n_envs < 1:
+            raise ValueError("n_envs must be >= 1")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedSupplyNetwork needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype_code, self.tdtype = _DTYPES[dtype]
+        self.dtype = dtype
+        self.ld = (self.n_envs + 31) // 32 * 32            # rows 128-byte aligned
+        self.T = spec.max_episode_steps
+        self._c_spec = spec.to_c()
+        _lib.check(self.lib.sn_spec_validate(C.byref(self._c_spec), self.dtype_code))
+        self.obs_dim = spec.obs_dim
+        self.n_agents = spec.n_agents
+        dev, n, ld = self.device, self.n_envs, self.ld
+        self.state = torch.zeros((_lib.SN_STATE_WORDS, ld), dtype=self.tdtype, device=dev)
+        self.init = torch.zeros((_lib.SN_INIT_WORDS, ld), dtype=self.tdtype, device=dev)
+        self.demand = torch.zeros((self.T + 3, ld), dtype=self.tdtype, device=dev)
+        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.ep_return = torch.zeros((n,), dtype=torch.float64, device=dev)
+        self.stats = torch.zeros((_lib.SN_STATS_WORDS,), dtype=torch.float64, device=dev)
+        self.period = 0
+        self.terminal = True          # no episode loaded yet
+        self.track_stats = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_rows(self, x, width) -> torch.Tensor:
+        """[n, width] host/device array -> [width, ld] device tensor of the quantity dtype."""
+        t = torch.as_tensor(x)
+        if t.dim() != 2 or t.shape[0] != self.n_envs or t.shape[1] != width:
+            raise ValueError(f"expected shape ({self.n_envs}, {width}), got {tuple(t.shape)}")
+        if self.dtype_code == _lib.SN_I32 and t.is_floating_point():
+            if not bool((t == t.round()).all()):
+                raise TypeError("integer simulator (dtype='int32') needs integral quantities")
+        t = t.to(device=self.device, dtype=self.tdtype, non_blocking=True)
+        out = torch.zeros((width, self.ld), dtype=self.tdtype, device=self.device)
+        out[:, : self.n_envs] = t.t()
+        return out
+
+    # ------------------------------------------------------------------ episode inputs
+    def load_episode(self, init, demand):
+        """init [n,19] (inv[4]; so[k][j]; sh[k][j]), demand [n, >=T+1] (utils/demands.py streams)."""
+        d = torch.as_tensor(demand)
+        if d.dim() != 2 or d.shape[1] < self.T + 1:
+            raise ValueError(f"demand must be [n_envs, >= {self.T + 1}]")
+        width = min(d.shape[1], self.T + 3)
+        self.init.copy_(self._to_rows(init, _lib.SN_INIT_WORDS))
+        self.demand.zero_()
+        self.demand[:width].copy_(self._to_rows(d[:, :width], width))
+
+    # ------------------------------------------------------------------ env API
+    def reset(self, obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """envs.py:64-80 for all envs; returns obs float32 [n, obs_dim] (device)."""
+        obs = self.obs if obs_out is None else obs_out
+        _lib.check(self.lib.sn_reset(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, _ptr(self.init),
+                                     _ptr(self.demand[0]), _ptr(self.state), _ptr(obs), self._stream()))
+        self.period = 0
+        self.terminal = False
+        self.ep_return.zero_()
+        return obs
+
+    def _check_actions(self, actions: torch.Tensor, lead=()) -> torch.Tensor:
+        shape = tuple(lead) + (self.n_envs, self.n_agents)
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dim() == len(shape) - 1 and self.n_agents == 1:
+            actions = actions.unsqueeze(-1)
+        if tuple(actions.shape) != shape:
+            raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
+        if self.dtype_code == _lib.SN_I32 and actions.is_floating_point():
+            if not bool((actions == actions.round()).all()):
+                raise TypeError("integer simulator (dtype='int32') needs integral order quantities")
+        return actions.to(device=self.device, dtype=self.tdtype).contiguous()
+
+    def step(self, actions, obs_out=None, reward_out=None, reward64_out=None, cost_out=None):
+        """envs.py:82-113 for all envs.  Returns (obs, reward, done) with obs/reward on the device;
+        `done` is a python bool because all envs run in lockstep."""
+        if self.terminal:
+            raise ValueError("Cannot take action when the state is terminal.")       # envs.py:88-89
+        a = self._check_actions(actions)
+        obs = self.obs if obs_out is None else obs_out
+        rew = self.reward if reward_out is None else reward_out
+        _lib.check(self.lib.sn_step(
+            C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, self.period, _ptr(self.state), _ptr(a),
+            _ptr(self.demand[self.period + 1]), _ptr(obs), _ptr(rew), _ptr(reward64_out), _ptr(cost_out),
+            _ptr(self.ep_return), _ptr(self.stats) if self.track_stats else None, self._stream()))
+        self.period += 1
+        self.terminal = self.period >= self.T
+        return obs, rew, self.terminal
+
+    def observe(self, obs_out=None) -> torch.Tensor:
+        obs = self.obs if obs_out is None else obs_out
+        _lib.check(self.lib.sn_observe(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, _ptr(self.state),
+                                       _ptr(obs), self._stream()))
+        return obs
+
+    def rollout(self, n_steps: Optional[int] = None, actions=None, policy: Optional[BasePolicyParams] = None,
+                record_obs=False, record_reward=False, record_actions=False, traj_obs=None, traj_reward=None,
+                traj_actions=None):
+        """n_steps fused periods.  Exactly one of `actions` ([n_steps, n, n_agents]) / `policy`."""
+        if self.terminal:
+            raise ValueError("Cannot take action when the state is terminal.")
+        if n_steps is None:
+            n_steps = self.T - self.period
+        if (actions is None) == (policy is None):
+            raise ValueError("give exactly one of actions= or policy=")
+        n, dev = self.n_envs, self.device
+        if actions is not None:
+            a = self._check_actions(actions, lead=(n_steps,))
+            kind, pol = _lib.SN_POLICY_ACTIONS, None
+        else:
+            if policy.n_cols != self.n_agents:
+                raise ValueError(f"policy has {policy.n_cols} targets, env has {self.n_agents} action columns")
+            a, kind, pol = None, _lib.SN_POLICY_BASE_STOCK, C.byref(policy.c)
+        if record_obs and traj_obs is None:
+            traj_obs = torch.empty((n_steps, n, self.obs_dim), dtype=torch.float32, device=dev)
+        if record_reward and traj_reward is None:
+            traj_reward = torch.empty((n_steps, n), dtype=torch.float32, device=dev)
+        if record_actions and traj_actions is None:
+            traj_actions = torch.empty((n_steps, n, self.n_agents), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.sn_rollout(
+            C.byref(self._c_spec), self.dtype_code, n, self.ld, self.period, n_steps, _ptr(self.state),
+            _ptr(self.demand), kind, _ptr(a), pol, _ptr(traj_obs), _ptr(traj_reward), _ptr(traj_actions),
+            _ptr(self.obs), _ptr(self.ep_return), _ptr(self.stats) if self.track_stats else None, self._stream()))
+        self.period += n_steps
+        self.terminal = self.period >= self.T
+        return dict(obs=self.obs, traj_obs=traj_obs, traj_reward=traj_reward, traj_actions=traj_actions,
+                    done=self.terminal)
+
+    # ------------------------------------------------------------------ snapshot
+    def get_state(self):
+        return dict(state=self.state.clone(), demand=self.demand.clone(), init=self.init.clone(),
+                    ep_return=self.ep_return.clone(), period=self.period, terminal=self.terminal)
+
+    def set_state(self, snap):
+        self.state.copy_(snap["state"]); self.demand.copy_(snap["demand"]); self.init.copy_(snap["init"])
+        self.ep_return.copy_(snap["ep_return"])
+        self.period, self.terminal = int(snap["period"]), bool(snap["terminal"])
+
+
+def heuristic_actions(policy: BasePolicyParams, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BaseStockPolicy.get_order_quantity (utils/heuristics.py:43-57,75) on a device batch."""
+    lib = _lib.load()
+    if obs.device.type != "cuda":
+        raise RuntimeError("heuristic_actions needs a CUDA tensor; there is no CPU fallback")
+    if obs.dim() != 2 or obs.shape[1] != 7 * policy.n_cols:
+        raise ValueError(f"obs must be [n, {7 * policy.n_cols}], got {tuple(obs.shape)}")
+    obs = obs.to(torch.float32).contiguous()
+    n = obs.shape[0]
+    if out is None:
+        out = torch.empty((n, policy.n_cols), dtype=torch.float32, device=obs.device)
+    stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+    _lib.check(lib.sn_heuristic(C.byref(policy.c), policy.n_cols, n, _ptr(obs), _ptr(out), stream))
+    return out

@@ -1,0 +1,143 @@
+"""Scenario description for the batched beer-game simulator.
+
+`ScenarioSpec` carries what the reference hard-codes in its env factories (envs.py:163-286
+"normal"/basic, :289-414 "uniform"/complex, :501-596 classic) plus the
+ordering rule of utils/wrappers.py.  It is lowered to the C struct `sn_spec` of
+include/supplynet.h for every kernel launch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Optional, Sequence, Tuple
+
+from . import _lib
+
+NODE_NAMES = ("retailer", "wholesaler", "distributor", "manufacturer")   # order_sequence, utils/graph.py:5-32
+INFO_LEADTIME = (2, 2, 2, 1)     # arc k: customer = node k (envs.py:355-392, beergame.yaml:26-50)
+SHIP_LEADTIME = (2, 2, 2, 2)
+OBS_PER_FACILITY = 7             # on_hand, unfilled_demand, latest_demand, unreceived_pipeline_0..3
+
+
+def node_index(name_or_index) -> int:
+    if isinstance(name_or_index, str):
+        try:
+            return NODE_NAMES.index(name_or_index)
+        except ValueError:
+            raise ValueError(f"unknown facility {name_or_index!r}; expected one of {NODE_NAMES}") from None
+    k = int(name_or_index)
+    if not 0 <= k < 4:
+        raise ValueError(f"facility index {k} out of range")
+    return k
+
+
+@dataclass(frozen=True)
+class ScenarioSpec:
+    name: str
+    holding_cost: Tuple[float, ...]
+    backorder_cost: Tuple[float, ...]
+    coplayer_target: Tuple[float, ...]
+    agents: Tuple[int, ...] = (0, 1, 2, 3)          # action-column order (supplynetwork.py:217)
+    global_observable: bool = False
+    max_episode_steps: int = 100
+    coplayer_lb: float = 0.0                         # BaseStockPolicy defaults, utils/heuristics.py:16
+    coplayer_ub: float = 16.0
+    rule: str = "a"                                  # 'a' | 'd+a'
+    dpa_offset: float = 0.0
+    dpa_lb: float = 0.0
+    dpa_ub: float = 16.0
+    action_low: float = 0.0                          # action space bounds (envs.py:269-272, 397-400)
+    action_high: float = 16.0
+    # demand / initial-state generators (host side, utils/demands.py + Arc/Node.reset)
+    demand_pattern: str = "uniform"                  # 'uniform' | 'normal' | 'classic_beer_game'
+    demand_params: Tuple[float, float] = (0, 8)      # (low, high) or (mean, sd)
+    random_init: bool = True
+    init_inventory: Tuple[int, int] = (0, 25)        # randint(lo, hi) if random_init else lo
+    init_pipeline: Tuple[int, int] = (0, 9)          # shipments and sales orders alike
+    fixed_inventory: int = 12
+    fixed_shipments: Tuple[int, int] = (4, 4)
+    fixed_sales_orders: Tuple[int, int] = (4, 4)
+
+    def __post_init__(self):
+        ag = tuple(node_index(a) for a in self.agents)
+        object.__setattr__(self, "agents", ag)
+        if not 1 <= len(ag) <= 4 or len(set(ag)) != len(ag):
+            raise ValueError(f"agent_managed_facilities {self.agents} must name 1..4 distinct facilities")
+        if max(ag) - min(ag) + 1 != len(ag):
+            # the reference never lets the in-between node order and crashes at supplynetwork.py:199
+            raise ValueError("agent-managed facilities must form a contiguous block of the chain")
+        if self.rule not in ("a", "d+a"):
+            raise ValueError(f"ordering rule must be 'a' or 'd+a', got {self.rule!r}")
+
+    # ------------------------------------------------------------------ derived
+    @property
+    def n_agents(self) -> int:
+        return len(self.agents)
+
+    @property
+    def obs_nodes(self) -> Tuple[int, ...]:
+        return (0, 1, 2, 3) if self.global_observable else self.agents
+
+    @property
+    def obs_dim(self) -> int:
+        return OBS_PER_FACILITY * len(self.obs_nodes)
+
+    def with_rule(self, rule: str, offset: float, lb: float, ub: float) -> "ScenarioSpec":
+        return replace(self, rule=rule, dpa_offset=offset, dpa_lb=lb, dpa_ub=ub)
+
+    def to_c(self) -> _lib.SnSpec:
+        s = _lib.SnSpec()
+        s.n_facilities = 4
+        for k in range(4):
+            s.info_leadtime[k] = INFO_LEADTIME[k]
+            s.ship_leadtime[k] = SHIP_LEADTIME[k]
+            s.holding_cost[k] = float(self.holding_cost[k])
+            s.backorder_cost[k] = float(self.backorder_cost[k])
+            s.coplayer_target[k] = float(self.coplayer_target[k])
+            s.agents[k] = self.agents[k] if k < len(self.agents) else 0
+        s.n_agents = len(self.agents)
+        s.global_observable = int(self.global_observable)
+        s.max_episode_steps = int(self.max_episode_steps)
+        s.rule = _lib.SN_RULE_D_PLUS_A if self.rule == "d+a" else _lib.SN_RULE_A
+        s.coplayer_lb, s.coplayer_ub = float(self.coplayer_lb), float(self.coplayer_ub)
+        s.dpa_offset, s.dpa_lb, s.dpa_ub = float(self.dpa_offset), float(self.dpa_lb), float(self.dpa_ub)
+        return s
+
+
+def _agents(agent_managed_facilities, default):
+    if agent_managed_facilities is None:
+        agent_managed_facilities = default
+    return tuple(node_index(a) for a in agent_managed_facilities)
+
+
+def uniform_spec(agent_managed_facilities=None, global_observable=False, max_episode_steps=100,
+                 random_init=True) -> ScenarioSpec:
+    """The "complex" scenario, make_beer_game_uniform_multi_facility (envs.py:289-414)."""
+    return ScenarioSpec(
+        name="uniform", holding_cost=(0.5,) * 4, backorder_cost=(1.0,) * 4, coplayer_target=(19, 20, 20, 14),
+        agents=_agents(agent_managed_facilities, NODE_NAMES), global_observable=global_observable,
+        max_episode_steps=max_episode_steps, action_low=0, action_high=16, demand_pattern="uniform",
+        demand_params=(0, 8), random_init=random_init, init_inventory=(0, 25), init_pipeline=(0, 9),
+        fixed_inventory=12, fixed_shipments=(4, 4), fixed_sales_orders=(4, 4))
+
+
+def normal_spec(agent_managed_facilities=None, global_observable=False, max_episode_steps=100,
+                random_init=False) -> ScenarioSpec:
+    """The "basic" scenario, make_beer_game_normal_multi_facility (envs.py:163-286).  Co-players
+    keep the default clip [0, 16] although the action range is [0, 20]."""
+    return ScenarioSpec(
+        name="normal", holding_cost=(1.0, 0.75, 0.5, 0.25), backorder_cost=(10.0, 0.0, 0.0, 0.0),
+        coplayer_target=(48, 43, 41, 30), agents=_agents(agent_managed_facilities, ("retailer",)),
+        global_observable=global_observable, max_episode_steps=max_episode_steps, action_low=0, action_high=20,
+        demand_pattern="normal", demand_params=(10, 2), random_init=random_init, init_inventory=(0, 21),
+        init_pipeline=(0, 21), fixed_inventory=10, fixed_shipments=(10, 0), fixed_sales_orders=(10, 0))
+
+
+def classic_spec(agent_managed_facilities=None, max_episode_steps=35, demand_pattern="classic_beer_game") -> ScenarioSpec:
+    """make_beer_game (envs.py:501-596): fixed initial state only (random_init is never wired, Q16)."""
+    params = {"classic_beer_game": (4, 8), "normal": (10, 2), "uniform": (0, 2)}[demand_pattern]
+    return ScenarioSpec(
+        name="classic", holding_cost=(0.5,) * 4, backorder_cost=(1.0,) * 4, coplayer_target=(32, 32, 32, 24),
+        agents=_agents(agent_managed_facilities, ("retailer",)), global_observable=False,
+        max_episode_steps=max_episode_steps, action_low=0, action_high=16, demand_pattern=demand_pattern,
+        demand_params=params, random_init=False, fixed_inventory=12, fixed_shipments=(4, 4),
+        fixed_sales_orders=(4, 4))

@@ -1,0 +1,136 @@
+"""Host-side demand and initial-state streams (mirror of the reference's utils/demands.py).
+
+Per north_star the random draws stay on the host so that inputs match the reference: the
+reference draws everything from numpy's legacy global RNG (utils/demands.py:44,47;
+network_components.py:143,157,297).  Two generators are offered:
+
+  * `seeded_episode_inputs(spec, seeds)`  - one `np.random.RandomState(seed)` per env, consumed in
+    exactly the order of `np.random.seed(seed); env.reset()` in the reference, so env i
+    reproduces the reference env seeded with seeds[i].  ~150 us per env: for parity subsets.
+  * `bulk_episode_inputs(spec, n, rng)`   - the same distributions drawn with a few vectorised
+    calls from one stream, for throughput runs (not stream-compatible with per-env seeding).
+
+Both return `init [n, 19]` (inv[4]; sales orders so[k][j], k=0..3, 2+2+2+1; shipments sh[k][j],
+4x2 - the row order of `sn_reset`) and `demand [n, T+3]` (utils/demands.py:21 "size + 3").
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..spec import INFO_LEADTIME, SHIP_LEADTIME, ScenarioSpec
+
+INIT_WORDS = 19
+_SO_OFF = (4, 6, 8, 10)
+_SH_OFF = (11, 13, 15, 17)
+
+
+class Demand:
+    """Batched counterpart of the reference's `Demand` (utils/demands.py:5-67): same constructor
+    arguments and patterns; `sample(n, rng)` draws the per-episode demand arrays of n envs."""
+
+    def __init__(self, demand_pattern="classic_beer_game", data_path=None, size=100, low=None, high=None,
+                 mean=None, sd=None):
+        self.demands_pattern = demand_pattern
+        self.size = size + 3
+        self.low, self.high, self.mean, self.sd = low, high, mean, sd
+        self.samples = np.load(data_path) if data_path is not None else None
+        self.sample_pointer = 0
+        if isinstance(demand_pattern, str):
+            if demand_pattern == "uniform" and (low is None or high is None):
+                raise ValueError('"low" and "high" need to be provided when uniform distribution pattern is specified')
+            if demand_pattern == "normal" and (mean is None or sd is None):
+                raise ValueError('"mean" and "sd" need to be provided when normal distribution pattern is specified')
+            if demand_pattern not in ("uniform", "normal", "classic_beer_game", "samples"):
+                raise ValueError("Demand pattern not recognized")
+
+    def draw(self, rs) -> np.ndarray:
+        """One episode from `rs` (a RandomState or the np.random module), consuming it exactly like
+        Demand.reset (utils/demands.py:37-59)."""
+        p = self.demands_pattern
+        if isinstance(p, (np.ndarray, list, tuple)):
+            return np.asarray(p)
+        if p == "uniform":
+            return rs.randint(self.low, self.high + 1, self.size)
+        if p == "normal":
+            return np.round(np.maximum(self.mean + self.sd * rs.randn(self.size), 0)).astype(int)
+        if p == "classic_beer_game":
+            return np.array([4] * 4 + [8] * (self.size - 4))
+        row = self.samples[self.sample_pointer % self.samples.shape[0]]      # "samples"
+        self.sample_pointer += 1
+        return np.asarray(row)
+
+    def sample(self, n: int, rs) -> np.ndarray:
+        """[n, size] demands in a few vectorised draws."""
+        p = self.demands_pattern
+        if isinstance(p, (np.ndarray, list, tuple)):
+            return np.broadcast_to(np.asarray(p), (n, len(p))).copy()
+        if p == "uniform":
+            return rs.randint(self.low, self.high + 1, (n, self.size))
+        if p == "normal":
+            return np.round(np.maximum(self.mean + self.sd * rs.randn(n, self.size), 0)).astype(int)
+        if p == "classic_beer_game":
+            return np.broadcast_to(np.array([4] * 4 + [8] * (self.size - 4)), (n, self.size)).copy()
+        rows = [self.draw(rs) for _ in range(n)]
+        return np.stack(rows)
+
+
+def demand_for(spec: ScenarioSpec) -> Demand:
+    a, b = spec.demand_params
+    if spec.demand_pattern == "uniform":
+        return Demand("uniform", low=int(a), high=int(b), size=spec.max_episode_steps)
+    if spec.demand_pattern == "normal":
+        return Demand("normal", mean=a, sd=b, size=spec.max_episode_steps)
+    return Demand(spec.demand_pattern, size=spec.max_episode_steps)
+
+
+def _fixed_init(spec: ScenarioSpec) -> np.ndarray:
+    v = np.zeros(INIT_WORDS, dtype=np.int64)
+    v[:4] = spec.fixed_inventory
+    for k in range(4):
+        for j in range(INFO_LEADTIME[k]):
+            v[_SO_OFF[k] + j] = spec.fixed_sales_orders[j]
+        for j in range(SHIP_LEADTIME[k]):
+            v[_SH_OFF[k] + j] = spec.fixed_shipments[j]
+    return v
+
+
+def seeded_episode_inputs(spec: ScenarioSpec, seeds):
+    """Per-env streams in the reference's draw order: inv_retailer, demand[T+3], inv_wholesaler,
+    inv_distributor, inv_manufacturer, then per arc in the factories' arc-list order
+    (ext->man, man->dis, dis->who, who->ret): shipments, then sales orders."""
+    seeds = np.asarray(seeds).reshape(-1)
+    n = seeds.shape[0]
+    dem = demand_for(spec)
+    init = np.zeros((n, INIT_WORDS), dtype=np.int64)
+    demand = np.zeros((n, dem.size), dtype=np.int64)
+    fixed = _fixed_init(spec)
+    for i, seed in enumerate(seeds):
+        rs = np.random.RandomState(int(seed))
+        if not spec.random_init:
+            init[i] = fixed
+            demand[i] = dem.draw(rs)
+            continue
+        lo, hi = spec.init_inventory
+        plo, phi = spec.init_pipeline
+        init[i, 0] = rs.randint(lo, hi)
+        demand[i] = dem.draw(rs)
+        for k in (1, 2, 3):
+            init[i, k] = rs.randint(lo, hi)
+        for k in (3, 2, 1, 0):
+            for j in range(SHIP_LEADTIME[k]):
+                init[i, _SH_OFF[k] + j] = rs.randint(plo, phi)
+            for j in range(INFO_LEADTIME[k]):
+                init[i, _SO_OFF[k] + j] = rs.randint(plo, phi)
+    return init, demand
+
+
+def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
+    """Same distributions, vectorised draws from one stream `rs` (RandomState)."""
+    dem = demand_for(spec)
+    if spec.random_init:
+        init = np.empty((n, INIT_WORDS), dtype=np.int64)
+        init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
+        init[:, 4:] = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, INIT_WORDS - 4))
+    else:
+        init = np.broadcast_to(_fixed_init(spec), (n, INIT_WORDS)).copy()
+    return init, dem.sample(n, rs)

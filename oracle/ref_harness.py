@@ -1,0 +1,125 @@
+"""Harness around the UNMODIFIED reference at /root/reference (TEST INFRASTRUCTURE ONLY).
+
+This module only works in the build container, where /root/reference is mounted.  It is
+used by `tests/golden/make_golden.py` (to generate the committed golden vectors) and by
+the `-m "not gpu"` differential tests when the reference is present (they skip otherwise).
+Nothing in the product package, `bench.py`, `smoke()` or the `-m gpu` tests imports it:
+the GPU box has no /root/reference.
+
+It does three things:
+  * puts a stand-in `gym` package (oracle/gym_shim) on sys.path, because the reference's
+    envs.py imports gym 0.21 which is not installed here;
+  * builds reference envs (`make_beer_game*` factories, envs.py:163-596) and, optionally,
+    applies the reference's d+a wrapper (utils/wrappers.py:6-31);
+  * reads the post-reset initial state out of the reference objects so the same
+    numbers can be fed to the oracle restatement and to the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("SUPPLYNET_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gym_shim")
+
+NODE_NAMES = ["retailer", "wholesaler", "distributor", "manufacturer"]
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "supplynetwork.py"))
+
+
+def import_reference():
+    """Import the reference modules in place (no copy) and return them as a namespace dict."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    for p in (_SHIM, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import envs as ref_envs  # noqa
+    import supplynetwork as ref_sn  # noqa
+    import network_components as ref_nc  # noqa
+    from utils import heuristics as ref_heur, demands as ref_dem, wrappers as ref_wrap, graph as ref_graph  # noqa
+
+    return dict(envs=ref_envs, sn=ref_sn, nc=ref_nc, heuristics=ref_heur, demands=ref_dem,
+                wrappers=ref_wrap, graph=ref_graph)
+
+
+def make_env(scenario: str, agents, global_observable=False, random_init=True, max_episode_steps=100,
+             dplusa=None):
+    """scenario in {'uniform','normal','classic'}; agents = list of node names (caller order).
+    dplusa = None or (offset, lb, ub)."""
+    ref = import_reference()
+    E = ref["envs"]
+    if scenario == "uniform":
+        env = E.make_beer_game_uniform_multi_facility(
+            agent_managed_facilities=list(agents), box_action_space=True, random_init=random_init,
+            global_observable=global_observable, max_episode_steps=max_episode_steps)
+    elif scenario == "normal":
+        env = E.make_beer_game_normal_multi_facility(
+            agent_managed_facilities=list(agents), box_action_space=True, random_init=random_init,
+            global_observable=global_observable, max_episode_steps=max_episode_steps)
+    elif scenario == "classic":
+        env = E.make_beer_game(agent_managed_facilities=list(agents), max_period=max_episode_steps)
+        env.global_observable = global_observable
+    else:
+        raise ValueError(scenario)
+    if dplusa is not None:
+        off, lb, ub = dplusa
+        env = ref["wrappers"].wrap_action_d_plus_a(env, offset=off, lb=lb, ub=ub)
+    return env
+
+
+def read_initial_state(env):
+    """Read (inv0[4], so[4][<=2], sh[4][2], demand[T+3]) out of a reference env right after
+    `sn.reset()` and BEFORE `before_action(0)`.  Arc index k = arc whose customer is node k."""
+    sn = env.sn
+    inv0 = [sn.nodes[n].current_inventory for n in NODE_NAMES]
+    sup = ["wholesaler", "distributor", "manufacturer", "external_supplier"]
+    so, sh = [], []
+    for k, n in enumerate(NODE_NAMES):
+        arc = sn.arcs[(sup[k], n)]
+        so.append([o.order_quantity for o in sorted(arc.sales_orders, key=lambda o: o.remaining_lead_time)])
+        sh.append([s.quantity for s in sorted(arc.shipments, key=lambda s: s.time_till_arrival)])
+    dem = np.asarray(sn.nodes["retailer"].demands._demands).copy()
+    return inv0, so, sh, dem
+
+
+def reset_and_capture(env, seed=None):
+    """np.random.seed(seed); replicate env.reset() (envs.py:64-80) but capture the raw initial
+    state between sn.reset() and before_action(0).  Returns (obs, init) like env.reset()."""
+    if seed is not None:
+        np.random.seed(seed)
+    env.terminal = False
+    env.sn.reset()
+    env.period = 0
+    init = read_initial_state(env)
+    env.sn.before_action(0)
+    names = env.sn.internal_nodes if env.global_observable else env.sn.agent_managed_facilities
+    obs = np.array([list(env.sn.get_state(a).values()) for a in names], dtype=np.float32).flatten()
+    return obs, init
+
+
+def rollout(env, actions, seed=None, collect_costs=False):
+    """Run the reference for len(actions) steps.  Returns dict(obs0, init, obs[T], rew[T], done[T])."""
+    obs0, init = reset_and_capture(env, seed)
+    obs_l, rew_l, done_l = [], [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for a in actions:
+            o, r, d, _ = env.step(a)
+            obs_l.append(o)
+            rew_l.append(r)
+            done_l.append(d)
+            if d:
+                break
+    out = dict(obs0=obs0, init=init, obs=np.stack(obs_l), rew=np.array(rew_l, dtype=np.float64),
+               done=np.array(done_l))
+    if collect_costs:
+        h = np.array([env.sn.nodes[n].holding_cost_history for n in NODE_NAMES], dtype=np.float64).T
+        b = np.array([env.sn.nodes[n].backorder_cost_history for n in NODE_NAMES], dtype=np.float64).T
+        out["holding"], out["backorder"] = h, b
+    return out

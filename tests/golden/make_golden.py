@@ -1,0 +1,165 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference).
+
+Run in the build container only:  python tests/golden/make_golden.py
+The reference is pure Python and cannot travel to the GPU box, so its outputs are committed
+here as small fixtures; every test that needs "what the reference does" reads these files.
+
+Files written
+  rollouts.npz    per case: inputs (init state, demand, actions) and the reference's outputs
+                  (obs0, obs[T], reward[T], done[T], per-facility holding/backorder cost[T,4])
+  heuristic.npz   BaseStockPolicy.get_order_quantity (utils/heuristics.py:35-75) on single-row
+                  observations, ndarray path and dict path, rules 'a' and 'd+a'
+  seeded.npz      `np.random.seed(s); env.reset()` initial state + demand for both scenarios
+                  (pins the RNG draw order replayed by the host-side stream generator)
+  classic.npz     the classic beer game episodes behind the 13 totals of
+                  tests/test_supplynetwork.py:25-69, with per-step outputs
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+NODE = H.NODE_NAMES
+SCN = {"uniform": dict(hi=16, dpa=(-8, 0, 16)), "normal": dict(hi=20, dpa=(-10, 0, 20))}
+
+
+def flat_init(init):
+    inv0, so, sh, dem = init
+    # 19 numbers in the product's init order: inv[4], so[k][*] (k=0..3), sh[k][*] (k=0..3)
+    v = list(inv0)
+    for k in range(4):
+        v += list(so[k])
+    for k in range(4):
+        v += list(sh[k])
+    return np.array(v, dtype=np.int64), np.asarray(dem, dtype=np.int64)
+
+
+def gen_rollouts():
+    cases = {}
+    meta = []
+    agsets = [(0, 1, 2, 3), (0,), (1,), (2,), (3,), (0, 1), (1, 2, 3), (2, 3), (3, 2, 1, 0)]
+    cid = 0
+    for scn, par in SCN.items():
+        for ag in agsets:
+            for glob in (False, True):
+                for rule in ("a", "d+a"):
+                    for kind in ("int", "float"):
+                        if kind == "float" and (glob or len(ag) not in (1, 4)):
+                            continue
+                        seed = 100 + cid
+                        T = 100
+                        env = H.make_env(scn, [NODE[k] for k in ag], glob, True, T,
+                                         dplusa=par["dpa"] if rule == "d+a" else None)
+                        rs = np.random.RandomState(5000 + cid)
+                        if kind == "int":
+                            lo = -2 if rule == "a" else 0           # negatives exercise the clamp
+                            acts = rs.randint(lo, par["hi"] + 4, (T, len(ag))).astype(np.int64)
+                            feed = [a for a in acts]
+                        else:
+                            acts = (rs.rand(T, len(ag)) * par["hi"]).astype(np.float32)
+                            feed = [a for a in acts]
+                        r = H.rollout(env, feed, seed=seed, collect_costs=True)
+                        init, dem = flat_init(r["init"])
+                        p = f"c{cid:03d}_"
+                        cases[p + "init"] = init
+                        cases[p + "demand"] = dem
+                        cases[p + "actions"] = acts
+                        cases[p + "obs0"] = r["obs0"]
+                        cases[p + "obs"] = r["obs"]
+                        cases[p + "rew"] = r["rew"]
+                        cases[p + "done"] = r["done"]
+                        cases[p + "holding"] = r["holding"]
+                        cases[p + "backorder"] = r["backorder"]
+                        meta.append(f"{cid}|{scn}|{','.join(map(str, ag))}|{int(glob)}|{rule}|{kind}|{seed}")
+                        cid += 1
+    cases["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "rollouts.npz"), **cases)
+    print("rollouts:", cid, "cases")
+
+
+def gen_heuristic():
+    ref = H.import_reference()
+    BSP = ref["heuristics"].BaseStockPolicy
+    idx = {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1, "latest_demand": 2}
+    rs = np.random.RandomState(7)
+    out = {}
+    n = 64
+    for name, targets, lb, ub in (("uniform", [19, 20, 20, 14], 0, 16), ("normal", [48, 43, 41, 30], 0, 20)):
+        obs = rs.randint(0, 30, (n, 28)).astype(np.float32)
+        obs[n // 2:] += rs.rand(n - n // 2, 28).astype(np.float32)      # fractional rows
+        for rule in ("a", "d+a"):
+            pol = BSP(targets, idx, 7, lb, ub, rule)
+            nd = np.stack([pol.get_order_quantity(obs[i:i + 1]) for i in range(n)])     # ndarray path
+            keys = ["on_hand", "unfilled_demand", "latest_demand"] + [f"unreceived_pipeline_{i}" for i in range(4)]
+            dct = np.zeros((n, 4))
+            for i in range(n):
+                for f in range(4):
+                    p1 = BSP([targets[f]], idx, 7, lb, ub, rule)
+                    d = {k: obs[i, 7 * f + j] for j, k in enumerate(keys)}
+                    dct[i, f] = p1.get_order_quantity({"x": d}).item()               # dict path
+            out[f"{name}_{rule}_nd"] = nd
+            out[f"{name}_{rule}_dict"] = dct
+        out[f"{name}_obs"] = obs
+        # the reference's batch quirk (row 0 only), SURVEY Q7
+        pol = BSP(targets, idx, 7, lb, ub, "a")
+        out[f"{name}_row0_batch2"] = pol.get_order_quantity(obs[:2])
+    np.savez_compressed(os.path.join(OUT, "heuristic.npz"), **out)
+    print("heuristic ok")
+
+
+def gen_seeded():
+    out = {}
+    for scn in SCN:
+        env = H.make_env(scn, NODE, True, True, 100)
+        for seed in (0, 1, 2, 12345, 2**31 - 1):
+            obs0, init = H.reset_and_capture(env, seed)
+            i, d = flat_init(init)
+            out[f"{scn}_{seed}_init"] = i
+            out[f"{scn}_{seed}_demand"] = d
+            out[f"{scn}_{seed}_obs0"] = obs0
+    np.savez_compressed(os.path.join(OUT, "seeded.npz"), **out)
+    print("seeded ok")
+
+
+def gen_classic():
+    """tests/test_supplynetwork.py:25-69 — the totals themselves live in the test file."""
+    out = {}
+    z, f, w = [0] * 20, [4] * 20, [12] * 20
+    e = [0, 0] + [8] * 18
+    runs = [("retailer", (0,), [z, f, w]), ("manufacturer", (3,), [e, f, w]),
+            ("distributor", (2,), [e, f, w]), ("wholesaler", (1,), [e, f, w])]
+    cid = 0
+    for name, ag, qs in runs:
+        env = H.make_env("classic", [name], False, False, 35)
+        for q in qs:
+            acts = np.array(q).reshape(20, 1)
+            r = H.rollout(env, [a for a in acts], collect_costs=True)
+            i, d = flat_init(r["init"])
+            p = f"k{cid:02d}_"
+            out.update({p + "init": i, p + "demand": d, p + "actions": acts, p + "obs0": r["obs0"],
+                        p + "obs": r["obs"], p + "rew": r["rew"], p + "agents": np.array(ag)})
+            cid += 1
+    env = H.make_env("classic", ["retailer", "wholesaler"], False, False, 35)
+    acts = np.array([0, 8] + [0, 4] + [0, 0] * 18).reshape(20, 2)
+    r = H.rollout(env, [a for a in acts], collect_costs=True)
+    i, d = flat_init(r["init"])
+    p = f"k{cid:02d}_"
+    out.update({p + "init": i, p + "demand": d, p + "actions": acts, p + "obs0": r["obs0"],
+                p + "obs": r["obs"], p + "rew": r["rew"], p + "agents": np.array([0, 1])})
+    np.savez_compressed(os.path.join(OUT, "classic.npz"), **out)
+    print("classic:", cid + 1, "episodes; totals:",
+          [float(out[f"k{c:02d}_rew"].sum()) for c in range(cid + 1)])
+
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore", RuntimeWarning)
+    gen_rollouts()
+    gen_heuristic()
+    gen_seeded()
+    gen_classic()

@@ -1,0 +1,236 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs golden vectors of the unmodified reference
+and vs the numpy oracle on seeded inputs.  Integer quantities must be bit-exact; float paths are
+held to 1e-6 relative to the scale of the state (tolerances written at each assert)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import CLASSIC_TOTALS, load_golden_classic, load_golden_rollouts  # noqa: E402
+from helpers import DPA, oracle_rollout  # noqa: E402
+
+
+def _make(scenario, agents, glob, rule, T, n, dtype):
+    from multi_echelon_drl_b200 import classic_spec, normal_spec, uniform_spec
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    if scenario == "uniform":
+        spec = uniform_spec(agents, glob, T)
+    elif scenario == "normal":
+        spec = normal_spec(agents, glob, T)
+    else:
+        spec = classic_spec(agents, T)
+    if rule == "d+a":
+        spec = spec.with_rule("d+a", *DPA[scenario])
+    return BatchedSupplyNetwork(spec, n, "cuda", dtype)
+
+
+GOLD = load_golden_rollouts()
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["id"] for c in GOLD])
+def test_step_matches_reference_golden(case):
+    """sn_reset + sn_step, one env, against trajectories recorded from the reference itself."""
+    is_int = case["kind"] == "int"
+    sim = _make(case["scenario"], case["agents"], case["global_observable"], case["rule"], 100, 1,
+                "int32" if is_int else "float32")
+    sim.load_episode(case["init"][None], case["demand"][None])
+    obs0 = sim.reset().cpu().numpy()
+    T = case["actions"].shape[0]
+    cost = torch.zeros((8, sim.ld), dtype=torch.float64, device="cuda")
+    r64 = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    if is_int:
+        assert np.array_equal(obs0[0], case["obs0"])
+    else:
+        np.testing.assert_allclose(obs0[0], case["obs0"], rtol=1e-6, atol=2e-4)
+    for t in range(T):
+        obs, rew, done = sim.step(torch.as_tensor(case["actions"][t][None]), reward64_out=r64, cost_out=cost)
+        o, r, c = obs.cpu().numpy()[0], r64.item(), cost[:, 0].cpu().numpy()
+        if is_int:      # bit-exact: integer quantities, dyadic cost coefficients
+            assert np.array_equal(o, case["obs"][t]), t
+            assert r == case["rew"][t], t
+            assert np.array_equal(c[:4], case["holding"][t]) and np.array_equal(c[4:], case["backorder"][t]), t
+            assert rew.item() == np.float32(case["rew"][t])
+        else:           # float32 arithmetic vs the reference's mixed float32/python arithmetic:
+            # 1e-6 relative to the state scale (quantities reach a few hundred => atol 2e-4 * scale-ish)
+            np.testing.assert_allclose(o, case["obs"][t], rtol=1e-6, atol=5e-4)
+            np.testing.assert_allclose(r, case["rew"][t], rtol=1e-6, atol=5e-3)
+        assert done == bool(case["done"][t])
+    with pytest.raises(ValueError):
+        sim.step(torch.as_tensor(case["actions"][0][None]))            # envs.py:88-89
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD if c["kind"] == "int"][::3], ids=lambda c: c["id"])
+def test_rollout_matches_reference_golden(case):
+    """sn_rollout (fused, streamed actions) reproduces the same golden trajectory, incl. terminal obs."""
+    sim = _make(case["scenario"], case["agents"], case["global_observable"], case["rule"], 100, 1, "int32")
+    sim.load_episode(case["init"][None], case["demand"][None])
+    sim.reset()
+    acts = torch.as_tensor(case["actions"][:, None, :])
+    out = sim.rollout(40, actions=acts[:40], record_obs=True, record_reward=True)     # split: state write-back
+    out2 = sim.rollout(60, actions=acts[40:], record_obs=True, record_reward=True)
+    obs = torch.cat([out["traj_obs"], out2["traj_obs"]]).cpu().numpy()[:, 0]
+    rew = torch.cat([out["traj_reward"], out2["traj_reward"]]).cpu().numpy()[:, 0]
+    assert np.array_equal(obs, case["obs"])
+    assert np.array_equal(rew, case["rew"].astype(np.float32))
+    assert np.array_equal(out2["obs"].cpu().numpy()[0], case["obs"][-1]) and out2["done"]
+    assert sim.ep_return.item() == case["rew"].sum()
+
+
+def test_classic_beer_game_totals():
+    """The 13 golden episode totals of the reference's tests/test_supplynetwork.py:25-69."""
+    for ep, total in zip(load_golden_classic(), CLASSIC_TOTALS):
+        sim = _make("classic", tuple(int(a) for a in ep["agents"]), False, "a", 35, 1, "int32")
+        sim.load_episode(ep["init"][None], ep["demand"][None])
+        assert np.array_equal(sim.reset().cpu().numpy()[0], ep["obs0"])
+        tot = 0.0
+        for t in range(20):
+            obs, rew, done = sim.step(torch.as_tensor(ep["actions"][t][None]))
+            assert np.array_equal(obs.cpu().numpy()[0], ep["obs"][t])
+            tot += rew.item()
+        assert tot == total
+
+
+def _seeded_batch(scenario, n, T, seed):
+    from multi_echelon_drl_b200 import normal_spec, uniform_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    spec = uniform_spec(max_episode_steps=T) if scenario == "uniform" else normal_spec(max_episode_steps=T, random_init=True)
+    return bulk_episode_inputs(spec, n, np.random.RandomState(seed))
+
+
+@pytest.mark.parametrize("scenario,agents,glob,rule", [
+    ("uniform", (0, 1, 2, 3), True, "a"), ("uniform", (0, 1, 2, 3), False, "d+a"),
+    ("normal", (0,), False, "a"), ("normal", (1, 2), True, "a"), ("uniform", (3,), True, "d+a"),
+    ("uniform", (3, 2, 1, 0), False, "a"),
+])
+def test_batch_step_vs_oracle(scenario, agents, glob, rule):
+    """4,133 envs (ragged: not a multiple of 32/128) x 100 steps, step kernel vs numpy oracle, bit-exact."""
+    n, T = 4133, 100
+    init, demand = _seeded_batch(scenario, n, T, 11)
+    hi = 17 if scenario == "uniform" else 21
+    acts = np.random.RandomState(5).randint(-1, hi + 2, (T, n, len(agents)))
+    ref = oracle_rollout(scenario, agents, glob, rule, T, init, demand, acts)
+    sim = _make(scenario, agents, glob, rule, T, n, "int32")
+    sim.track_stats = True
+    sim.load_episode(init, demand)
+    assert np.array_equal(sim.reset().cpu().numpy(), ref["obs0"])
+    r64 = torch.zeros((n,), dtype=torch.float64, device="cuda")
+    for t in range(T):
+        obs, rew, done = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
+        assert np.array_equal(obs.cpu().numpy(), ref["obs"][t]), t
+        assert np.array_equal(r64.cpu().numpy(), ref["rew"][t]), t
+    assert done
+    st = sim.stats.cpu().numpy()
+    assert st[0] == n * T and st[1] == ref["rew"].sum()
+    assert np.array_equal(st[2:6], ref["holding"].sum((0, 1))) and np.array_equal(st[6:10], ref["backorder"].sum((0, 1)))
+    assert np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 129, 1000])
+def test_ragged_sizes_rollout(n):
+    """Edge sizes around warp / block boundaries: fused rollout with trajectory vs oracle."""
+    T = 30
+    init, demand = _seeded_batch("uniform", n, T, n)
+    acts = np.random.RandomState(n).randint(0, 17, (T, n, 4))
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts)
+    sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+    sim.load_episode(init, demand)
+    sim.reset()
+    out = sim.rollout(T, actions=torch.as_tensor(acts), record_obs=True, record_reward=True)
+    assert np.array_equal(out["traj_obs"].cpu().numpy(), ref["obs"])
+    assert np.array_equal(out["traj_reward"].cpu().numpy(), ref["rew"].astype(np.float32))
+
+
+@pytest.mark.parametrize("prule,erule", [("a", "a"), ("d+a", "d+a"), ("a", "d+a")])
+@pytest.mark.parametrize("scenario", ["uniform", "normal"])
+def test_heuristic_rollout_vs_oracle(scenario, prule, erule):
+    """Config-3 mode: base-stock policy evaluated in-kernel per env (utils/heuristics.py), fused
+    100-step rollout, vs the oracle driven by the oracle's own heuristic restatement."""
+    n, T = 2050, 100
+    init, demand = _seeded_batch(scenario, n, T, 3)
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    tg, ub = ([19, 20, 20, 14], 16) if scenario == "uniform" else ([48, 43, 41, 30], 20)
+    ref = oracle_rollout(scenario, (0, 1, 2, 3), True, erule, T, init, demand, None, policy=(tg, 0, ub, prule))
+    sim = _make(scenario, (0, 1, 2, 3), True, erule, T, n, "int32")
+    sim.track_stats = True
+    sim.load_episode(init, demand)
+    sim.reset()
+    out = sim.rollout(T, policy=BasePolicyParams(tg, 0, ub, prule), record_obs=True, record_reward=True,
+                      record_actions=True)
+    assert np.array_equal(out["traj_actions"].cpu().numpy(), ref["actions"].astype(np.float32))
+    assert np.array_equal(out["traj_obs"].cpu().numpy(), ref["obs"])
+    assert np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))
+    assert sim.stats[1].item() == ref["rew"].sum()
+
+
+def test_heuristic_kernel_vs_reference_golden():
+    """sn_heuristic vs BaseStockPolicy.get_order_quantity outputs recorded from the reference
+    (ndarray path and dict path agree there; tolerance 1e-6 relative for the fractional rows)."""
+    import os
+    from conftest import GOLDEN
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
+    z = np.load(os.path.join(GOLDEN, "heuristic.npz"))
+    for name, tg, ub in (("uniform", [19, 20, 20, 14], 16), ("normal", [48, 43, 41, 30], 20)):
+        obs = torch.as_tensor(z[f"{name}_obs"]).cuda()
+        for rule in ("a", "d+a"):
+            got = heuristic_actions(BasePolicyParams(tg, 0, ub, rule), obs).cpu().numpy()
+            want = z[f"{name}_{rule}_nd"][:, 0, :] if z[f"{name}_{rule}_nd"].ndim == 3 else z[f"{name}_{rule}_nd"]
+            assert np.array_equal(got[:32], want[:32].astype(np.float32))          # integer rows: exact
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(got, z[f"{name}_{rule}_dict"], rtol=1e-6, atol=1e-5)
+        # the reference's batch quirk: only row 0 is read
+        got = heuristic_actions(BasePolicyParams(tg, 0, ub, "a", row0_broadcast=True), obs[:2]).cpu().numpy()
+        np.testing.assert_allclose(got[0], z[f"{name}_row0_batch2"].reshape(-1), rtol=1e-6)
+        np.testing.assert_allclose(got[1], z[f"{name}_row0_batch2"].reshape(-1), rtol=1e-6)
+
+
+def test_float_paths_vs_oracle():
+    """Fractional (TD3-like) orders: f32 and f64 kernels vs the float64 oracle.
+    f64: 1e-9 relative (same arithmetic up to aggregation order); f32: 1e-6 of the state scale."""
+    n, T = 1500, 100
+    init, demand = _seeded_batch("uniform", n, T, 9)
+    acts = (np.random.RandomState(2).rand(T, n, 4) * 16).astype(np.float32)
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts.astype(np.float64), dtype=np.float64)
+    scale = max(1.0, np.abs(ref["obs"]).max())
+    for dt, tol in (("float64", 1e-9), ("float32", 1e-6)):
+        sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, dt)
+        sim.load_episode(init, demand)
+        sim.reset()
+        out = sim.rollout(T, actions=torch.as_tensor(acts), record_obs=True, record_reward=True)
+        err = np.abs(out["traj_obs"].cpu().numpy().astype(np.float64) - ref["obs"]).max()
+        assert err <= max(tol, 1.2e-7) * scale * 8, (dt, err, scale)     # obs itself is rounded to f32
+        rerr = np.abs(out["traj_reward"].cpu().numpy() - ref["rew"]).max()
+        assert rerr <= max(tol, 1.2e-7) * np.abs(ref["rew"]).max() * 8, (dt, rerr)
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (65,536 envs, complex scenario, centralized, fixed actions):
+    (i) step-by-step kernel and fused rollout agree bit-for-bit; (ii) per-env results are invariant
+    to batch position (first 4,096 envs equal a 4,096-env run = shard invariance); (iii) the
+    reference's runtime invariant on_order == sum(pipeline) (supplynetwork.py:159-160) holds."""
+    n, T = 65536, 100
+    init, demand = _seeded_batch("uniform", n, T, 1234)
+    acts = np.random.RandomState(77).randint(0, 17, (T, n, 4)).astype(np.int32)
+    a = torch.as_tensor(acts).cuda()
+    sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+    sim.load_episode(init, demand)
+    sim.reset()
+    out = sim.rollout(T, actions=a, record_obs=True, record_reward=True)
+    ret_fused = sim.ep_return.clone()
+    sim2 = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+    sim2.load_episode(init, demand)
+    sim2.reset()
+    for t in range(T):
+        obs, rew, _ = sim2.step(a[t])
+        assert torch.equal(obs, out["traj_obs"][t]) and torch.equal(rew, out["traj_reward"][t])
+        if t == 50:
+            s = sim2.state[:, :n].to(torch.int64)
+            for k in range(4):
+                on_order = s[7 * k + 3:7 * k + 7].sum(0)
+                pipe = s[31 + 2 * k] + s[32 + 2 * k] + (s[28 + k] if k < 3 else 0) + (s[7 * (k + 1) + 1] if k < 3 else s[39])
+                assert torch.equal(on_order, pipe)
+    assert torch.equal(ret_fused, sim2.ep_return)
+    m = 4096
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init[:m], demand[:m], acts[:, :m])
+    assert np.array_equal(out["traj_obs"][:, :m].cpu().numpy(), ref["obs"])
+    assert np.array_equal(ret_fused[:m].cpu().numpy(), ref["rew"].sum(0))
