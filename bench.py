@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched beer game on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE config 2 — complex ("uniform") scenario, MultiFacility
+centralized control with full information, 65,536 envs per GPU, fixed integer actions, 100-period
+episodes.  One bench *step* = one full parity rollout of that batch: sn_reset + sn_rollout streaming
+the actions [100, N, 4] and demands in and the complete trajectory (obs [100, N, 28] f32, reward
+[100, N] f32) out = 6,553,600 env-steps and ~0.9 GB of HBM traffic per step (inputs + outputs are
+several times the 126 MB L2, so no L2 flush is needed between steps).
+
+  value   device-resident throughput: inputs already in HBM, outputs left in HBM
+  e2e     the same rollout through the public Python API with HOST (pinned) buffers: init/demand/
+          actions copied host->device and the trajectory copied device->host inside the timed region
+  roofline  k_rollout: algorithmic bytes (137 B per env-step) / CUDA-event time of that
+          kernel / measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the C port of the oracle (oracle/beergame_c.c) on the host cores, bounded sample
+
+`--impl reference` times the CPU implementation of the same path (oracle port; the reference itself
+is pure Python and is not present on the GPU box) with all host threads.
+Multi-GPU: one process per GPU (torchrun), envs sharded by rank, no data-path collective; the only
+collective is the NCCL all-reduce of the 16-double statistics vector per episode.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS = 65536
+T = 100
+BYTES_PER_ENV_STEP_ROLLOUT = 137      # in: action 16 + demand 4; out: obs 112 + reward 4 + done 1
+BYTES_PER_ENV_STEP_SINGLE = 345       # single-step VecEnv mode (state r/w + action + demand + reward + done)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:      # noqa: BLE001
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(n, seed):
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    spec = uniform_spec(("retailer", "wholesaler", "distributor", "manufacturer"), True, T, True)
+    rs = np.random.RandomState(seed)
+    init, demand = bulk_episode_inputs(spec, n, rs)
+    actions = rs.randint(0, 17, (T, n, 4)).astype(np.int32)
+    return spec, init.astype(np.int32), demand.astype(np.int32), actions
+
+
+def cpu_port_throughput(init, demand, actions, threads, budget_s, with_traj=True):
+    """C port of the oracle on `threads` host threads; repeats the 65,536-env rollout until
+    ~budget_s seconds of work are done.  Returns (env-steps/s, sample description)."""
+    from oracle import beergame_c as OC
+    from oracle import beergame_np as O
+    ospec = O.scenario_spec("uniform", (0, 1, 2, 3), True, T)
+    n = init.shape[0]
+    OC.rollout(ospec, init[:1024], demand[:1024], actions[:, :1024], n_threads=threads)      # warm-up
+    lib = OC.load()
+    import ctypes as C
+    s = OC.make_spec(ospec)
+    od = 28
+    obs = np.zeros((T, n, od), np.float32) if with_traj else None
+    rew = np.zeros((T, n), np.float64) if with_traj else None
+    ret = np.zeros((n,), np.float64)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        lib.bg_rollout(C.byref(s), n, T, p(init), p(demand), p(actions), None, threads, None, p(obs), p(rew), p(ret))
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or reps >= 200:
+            break
+    return n * T * reps / dt, f"{reps} x ({n} envs x {T} periods, trajectory {'written' if with_traj else 'discarded'}) in {dt:.1f}s"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, init, demand, actions = make_inputs(N_ENVS, 1234)
+    threads = os.cpu_count() or 1
+    from oracle import beergame_c as OC
+    OC.load()
+    vals = []
+    per_step_budget = min(20.0, 120.0 / max(1, args.steps + args.warmup))
+    for i in range(args.warmup + args.steps):
+        v, sample = cpu_port_throughput(init, demand, actions, threads, per_step_budget)
+        if i >= args.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    v1, _ = cpu_port_throughput(init, demand, actions, 1, 3.0)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec (batched beer game)", "value": v, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N_ENVS * T / v * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i64", "data": "synthetic",
+        "config": {"workload": "config2: complex scenario, MultiFacility centralized full-info, 65,536 envs x 100 "
+                               "periods fixed-action parity rollout with full trajectory out (CPU port of the oracle)"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_value": v1,
+                         "note": "C port of the reference algorithm (oracle/beergame_c.c); the reference itself is "
+                                 "pure Python (~5e3 env-steps/s/core measured in the build container, DESIGN.md)"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+
+    n = args.envs
+    spec, init, demand, actions = make_inputs(n, 1234 + rank)
+    sim = BatchedSupplyNetwork(spec, n, dev, "int32")
+    sim.track_stats = True
+    # host (pinned) buffers for the e2e arm
+    h_init = torch.from_numpy(init).pin_memory()
+    h_demand = torch.from_numpy(demand).pin_memory()
+    h_actions = torch.from_numpy(actions).pin_memory()
+    h_traj_obs = torch.empty((T, n, 28), dtype=torch.float32).pin_memory()
+    h_traj_rew = torch.empty((T, n), dtype=torch.float32).pin_memory()
+    # device-resident inputs / outputs
+    sim.load_episode(h_init, h_demand)
+    d_actions = h_actions.to(dev)
+    traj_obs = torch.empty((T, n, 28), dtype=torch.float32, device=dev)
+    traj_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+    stats_sum = torch.zeros(16, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    k_events = []
+
+    def device_step(record):
+        sim.reset()
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        sim.rollout(T, actions=d_actions, traj_obs=traj_obs, traj_reward=traj_rew)
+        if record:
+            e1.record()
+            k_events.append((e0, e1))
+        if world > 1:                       # the path's only collective: episode statistics
+            stats_sum.copy_(sim.stats)
+            dist.all_reduce(stats_sum)
+
+    def e2e_step():
+        sim.load_episode(h_init, h_demand)                    # H2D init + demand
+        sim.reset()
+        sim.rollout(T, actions=h_actions, traj_obs=traj_obs, traj_reward=traj_rew)   # H2D actions
+        h_traj_obs.copy_(traj_obs, non_blocking=True)         # D2H trajectory
+        h_traj_rew.copy_(traj_rew, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup, **kw):
+        for _ in range(warmup):
+            fn(**kw) if kw else fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn(**kw) if kw else fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(args.warmup):
+        device_step(False)
+    ms_dev = timed(device_step, args.steps, 0, record=True)
+    clocks = sampler.finish() if sampler else None
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
+    ms_e2e = timed(e2e_step, max(1, min(args.steps, 10)), min(args.warmup, 3))
+    e2e_steps = max(1, min(args.steps, 10))
+
+    # correctness guard on the numbers just produced: statistics vector vs the trajectory it wrote
+    sim.stats.zero_()
+    device_step(False)
+    torch.cuda.synchronize()
+    assert float(sim.stats[0].item()) == n * T, "stats vector: wrong env-step count"
+    assert float(sim.stats[1].item()) == float(traj_rew.double().sum().item()), "stats vector disagrees with trajectory"
+
+    env_steps_per_step = n * T * world
+    value = env_steps_per_step / (ms_dev / args.steps * 1e-3)
+    e2e_value = env_steps_per_step / (ms_e2e / e2e_steps * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    achieved = n * T * BYTES_PER_ENV_STEP_ROLLOUT / (kernel_ms * 1e-3) / 1e9
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = single_step_numbers(torch, dev, peak)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, sample = cpu_port_throughput(init, demand, actions, threads, 10.0)
+            v1, _ = cpu_port_throughput(init, demand, actions, 1, 3.0)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                   "single_thread_value": v1}
+        h2d = init.nbytes + demand.nbytes + actions.nbytes
+        d2h = h_traj_obs.numel() * 4 + h_traj_rew.numel() * 4
+        line = {
+            "metric": "env-steps/sec (batched beer game)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": "config2: complex (uniform) scenario, MultiFacility centralized full-info, "
+                                   f"{n} envs/GPU x {T} periods fixed-action parity rollout, full trajectory out",
+                       "envs_per_gpu": n, "periods": T, "step": "sn_reset + sn_rollout (1 episode of the batch)",
+                       "l2": "inputs+outputs ~0.9 GB per step >> 126 MB L2, no flush needed",
+                       "parallelism": f"env-sharded x{world}, stats all-reduce only"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "api": "BatchedSupplyNetwork.load_episode/reset/rollout with pinned host tensors + trajectory D2H"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_rollout<int,ACTIONS>", "kernel_ms": kernel_ms,
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def single_step_numbers(torch, dev, peak):
+    """Secondary figures: the single-period step kernel (VecEnv mode, 345 B/env-step) at the config-2
+    size (L2-resident, launch-bound) and at an HBM-honest 4M envs, plus the in-kernel base-stock
+    heuristic rollout (config 3 mode, per GPU)."""
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, BatchedSupplyNetwork
+    out = {}
+    for tag, n in (("single_step_65536", 65536), ("single_step_4M", 4 * 1024 * 1024)):
+        spec = uniform_spec(("retailer", "wholesaler", "distributor", "manufacturer"), True, T, True)
+        sim = BatchedSupplyNetwork(spec, n, dev, "int32")
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        sim.demand.copy_(torch.randint(0, 9, sim.demand.shape, generator=g, device=dev, dtype=torch.int32))
+        sim.init.copy_(torch.randint(0, 9, sim.init.shape, generator=g, device=dev, dtype=torch.int32))
+        acts = torch.randint(0, 17, (n, 4), generator=g, device=dev, dtype=torch.int32)
+        res = {}
+        for with_obs in (False, True):
+            sim.reset()
+            steps = T - 1
+            obs_arg = sim.obs if with_obs else None
+            import ctypes as C
+            from multi_echelon_drl_b200 import _lib
+
+            def one(t):
+                _lib.check(sim.lib.sn_step(C.byref(sim._c_spec), sim.dtype_code, n, sim.ld, t, C.c_void_p(sim.state.data_ptr()),
+                                           C.c_void_p(acts.data_ptr()), C.c_void_p(sim.demand[t + 1].data_ptr()),
+                                           C.c_void_p(obs_arg.data_ptr()) if with_obs else None,
+                                           C.c_void_p(sim.reward.data_ptr()), None, None, None, None,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            for t in range(5):
+                one(t)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for t in range(5, steps):
+                one(t)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / (steps - 5)
+            bps = BYTES_PER_ENV_STEP_SINGLE + (112 if with_obs else 0)
+            res["with_obs" if with_obs else "state_only"] = {
+                "env_steps_per_s": n / (ms * 1e-3), "us_per_launch": ms * 1e3,
+                "achieved_gbs": n * bps / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": n * bps / (ms * 1e-3) / 1e9 / peak,
+                "bytes_per_env_step": bps}
+        out[tag] = res
+        del sim
+    # config-3 mode: heuristic rollout, stats only (ALU/latency bound, ~4 B/env-step of HBM traffic)
+    n = 131072
+    spec = uniform_spec(("retailer", "wholesaler", "distributor", "manufacturer"), True, T, True)
+    sim = BatchedSupplyNetwork(spec, n, dev, "int32")
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    sim.demand.copy_(torch.randint(0, 9, sim.demand.shape, generator=g, device=dev, dtype=torch.int32))
+    sim.init.copy_(torch.randint(0, 9, sim.init.shape, generator=g, device=dev, dtype=torch.int32))
+    pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
+    for _ in range(3):
+        sim.reset(); sim.rollout(T, policy=pol)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    reps = 20
+    for _ in range(reps):
+        sim.reset(); sim.rollout(T, policy=pol)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    out["heuristic_rollout_131072"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_episode": ms,
+                                       "bound": "alu/latency (state on-chip, 4 B/env-step HBM)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default: BASELINE config 2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,7 +38,7 @@ struct DevSpec {
   T off, lb, ub;       // d+a rule (utils/wrappers.py:25-27)
   double h[kF], b[kF];
   int slot[kF];        // action column of node k, -1 = co-player
-  int obs_node[kF];    // nodes whose 7 numbers form the observation, in output order
+  int pos[kF];         // position of node k's 7 numbers in the observation, -1 = not observed
   int n_obs;
   int n_agents;
   int lo;              // first agent index: nodes below it order inside before_action
@@ -48,7 +48,7 @@ struct DevSpec {
 
 template <typename T>
 struct DevPolicy {
-  T target[kF];
+  T target[kF];        // indexed by NODE (the host permutes the per-column targets)
   T lb, ub;
   int rule;
 };
@@ -142,33 +142,56 @@ __device__ __forceinline__ void env_reset(Env<T>& e, const T (&in)[kInitWords], 
   e.lat[0] = d0;            // current_external_demand (network_components.py:317-319)
 }
 
-// Observation of node k (supplynetwork.py:151-169).  A co-player with index < first agent has
-// already ordered inside before_action when the reference observes it, so (on non-terminal
-// observations) its pipeline shows [its order, U0, U1, U2] (5-slot list, first four read).
-template <typename T>
-__device__ __forceinline__ void node_obs(const Env<T>& e, const DevSpec<T>& sp, int k, bool terminal, float* o) {
-  T u0 = T(0), u1 = T(0), u2 = T(0), u3 = T(0), inv = T(0), unf = T(0), lat = T(0), tg = T(0);
-#pragma unroll
-  for (int j = 0; j < kF; ++j)
-    if (j == k) {
-      inv = e.inv[j]; unf = e.unfilled(j); lat = e.lat[j]; tg = sp.target[j];
-      u0 = e.U[j][0]; u1 = e.U[j][1]; u2 = e.U[j][2]; u3 = e.U[j][3];
-    }
-  if (k < sp.lo && !terminal) {
-    const T U[4] = {u0, u1, u2, u3};
-    const T q = tmax(base_stock(tg, inv, U, unf, lat, sp.clb, sp.cub, 0), T(0));
+// Observation of node K (supplynetwork.py:151-169), K a compile-time constant so that every
+// operand is a fixed register.  A co-player with index < first agent has already ordered inside
+// before_action when the reference observes it, so (on non-terminal observations) its pipeline
+// shows [its order, U0, U1, U2] (5-slot list, first four read).
+template <int K, typename T>
+__device__ __forceinline__ void node_view(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float (&v)[7]) {
+  T u0 = e.U[K][0], u1 = e.U[K][1], u2 = e.U[K][2], u3 = e.U[K][3];
+  const T unf = e.unfilled(K);
+  if (K < kF - 1 && K < sp.lo && !terminal) {
+    const T q = tmax(base_stock(sp.target[K], e.inv[K], e.U[K], unf, e.lat[K], sp.clb, sp.cub, 0), T(0));
     u3 = u2; u2 = u1; u1 = u0; u0 = q;
   }
-  o[0] = (float)inv; o[1] = (float)unf; o[2] = (float)lat;
-  o[3] = (float)u0; o[4] = (float)u1; o[5] = (float)u2; o[6] = (float)u3;
+  v[0] = (float)e.inv[K]; v[1] = (float)unf; v[2] = (float)e.lat[K];
+  v[3] = (float)u0; v[4] = (float)u1; v[5] = (float)u2; v[6] = (float)u3;
 }
 
-// envs.py:103-110: concatenation over internal nodes (global) or agent-managed facilities.
-template <typename T>
-__device__ __forceinline__ void env_obs(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float (&o)[28]) {
+// envs.py:103-110: concatenation over internal nodes (global) or agent-managed facilities, written
+// to `dst` (this env's row, shared or global memory).  Node K lands at dst + 7*pos[K]: the position
+// is a memory offset, never a register select.  IDENT = all four nodes in chain order (the
+// centralized / full-information layout): 28 floats as seven 16-byte stores.
+template <bool IDENT, typename T>
+__device__ __forceinline__ void emit_obs(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float* dst) {
+  if (IDENT) {
+    float o[28];
+    { float v[7]; node_view<0>(e, sp, terminal, v);
 #pragma unroll
-  for (int i = 0; i < kF; ++i)
-    if (i < sp.n_obs) node_obs(e, sp, sp.obs_node[i], terminal, &o[7 * i]);
+      for (int j = 0; j < 7; ++j) o[j] = v[j]; }
+    { float v[7]; node_view<1>(e, sp, terminal, v);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) o[7 + j] = v[j]; }
+    { float v[7]; node_view<2>(e, sp, terminal, v);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) o[14 + j] = v[j]; }
+    { float v[7]; node_view<3>(e, sp, terminal, v);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) o[21 + j] = v[j]; }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  } else {
+#define SN_EMIT_NODE(K)                                        \
+    if (sp.pos[K] >= 0) {                                      \
+      float v[7];                                              \
+      node_view<K>(e, sp, terminal, v);                        \
+      float* d = dst + 7 * sp.pos[K];                          \
+      _Pragma("unroll") for (int j = 0; j < 7; ++j) d[j] = v[j]; \
+    }
+    SN_EMIT_NODE(0) SN_EMIT_NODE(1) SN_EMIT_NODE(2) SN_EMIT_NODE(3)
+#undef SN_EMIT_NODE
+  }
 }
 
 struct StepOut {
@@ -178,17 +201,16 @@ struct StepOut {
 
 // Orders of all four nodes for this period.  Each depends only on start-of-period quantities
 // (every information lead time is >= 1), so they are computed before the shipment sweep:
-// agent-managed nodes take their action column (through the d+a rule of utils/wrappers.py:25-27
-// when selected), the others their own base-stock policy (network_components.py:361-366).
-template <typename T>
+// agent-managed nodes take their action (through the d+a rule of utils/wrappers.py:25-27 when
+// selected), the others their own base-stock policy (network_components.py:361-366).
+//   a[k]  action of NODE k (already gathered from its action column); ignored for co-players
+template <bool IDENT, typename T>
 __device__ __forceinline__ void env_orders(const Env<T>& e, const DevSpec<T>& sp, const T (&a)[kF], T (&q)[kF]) {
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     T x;
-    if (sp.slot[k] >= 0) {
-      x = a[0];
-#pragma unroll
-      for (int i = 1; i < kF; ++i) if (sp.slot[k] == i) x = a[i];
+    if (IDENT || sp.slot[k] >= 0) {
+      x = a[k];
       if (sp.rule == 1) x = tclamp(e.lat[k] + x + sp.off, sp.lb, sp.ub);
     } else {
       x = base_stock(sp.target[k], e.inv[k], e.U[k], e.unfilled(k), e.lat[k], sp.clb, sp.cub, 0);

@@ -41,46 +41,28 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // ------------------------------------------------------------------------------------------
 // Observation tile writer.  Each warp owns 32 consecutive envs = one contiguous span of
 // 32*od floats in the row-major output.  Lanes deposit their `od` floats in shared memory
-// (stride od words: conflict-free for od = 7, 21, 28-as-float4), then lane 0 issues one bulk
-// store.  Partial warps (tail of the batch) and unaligned outputs use plain stores.
+// (stride od words: conflict-free for od = 7, 21 and for od = 28 written as float4), then lane 0
+// issues one bulk store.  Partial warps (tail of the batch) and unaligned outputs use plain stores.
 struct ObsStager {
   float* smem;     // this warp's staging area: [2][32*28] floats
   int lane;
   __device__ __forceinline__ ObsStager(float* block_smem) {
-    const int warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
-    smem = block_smem + warp * (2 * 32 * 28);
+    smem = block_smem + (threadIdx.x >> 5) * (2 * 32 * 28);
   }
-  // `buf` alternates 0/1 between consecutive calls of the same warp; at most one earlier
-  // bulk store of this warp may still be reading the other buffer.
-  __device__ __forceinline__ void store(float* gobs, int64_t env0_of_warp, int64_t n_envs, int od, bool valid,
-                                        const float (&o)[28], int buf, bool use_tma) {
-    const bool full = (env0_of_warp + 32 <= n_envs);
-    if (use_tma && full) {
-      float* s = smem + buf * (32 * 28);
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      float* mine = s + lane * od;
-      if (od == 28) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-          reinterpret_cast<float4*>(mine)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 28; ++j)
-          if (j < od) mine[j] = o[j];
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_store_s2g(gobs + env0_of_warp * od, s, (uint32_t)(32 * od * sizeof(float)));
-        bulk_commit();
-      }
-    } else if (valid) {
-      float* g = gobs + (env0_of_warp + lane) * od;
-#pragma unroll
-      for (int j = 0; j < 28; ++j)
-        if (j < od) g[j] = o[j];
+  // Staging row of this lane in buffer `buf`.  `buf` alternates 0/1 between consecutive stores of
+  // the same warp; at most one earlier bulk store may still be reading the other buffer.
+  __device__ __forceinline__ float* begin(int od, int buf) {
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    return smem + buf * (32 * 28) + lane * od;
+  }
+  __device__ __forceinline__ void commit(float* gdst_warp, int od, int buf) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store_s2g(gdst_warp, smem + buf * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
+      bulk_commit();
     }
   }
   __device__ __forceinline__ void drain() {
@@ -89,25 +71,63 @@ struct ObsStager {
   }
 };
 
-// actions row-major [n][na]
-template <typename T>
-__device__ __forceinline__ void load_actions(const T* __restrict__ act, int64_t env, int na, T (&a)[kF]) {
-  const T* p = act + env * na;
-  if (na == 4 && sizeof(T) == 4) {
-    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
-    a[0] = *reinterpret_cast<const T*>(&v.x);
-    a[1] = *reinterpret_cast<const T*>(&v.y);
-    a[2] = *reinterpret_cast<const T*>(&v.z);
-    a[3] = *reinterpret_cast<const T*>(&v.w);
+// Writes this env's observation row: through the warp's TMA staging buffer when the warp is full
+// and the output aligned, with plain stores otherwise.
+template <bool IDENT, typename T>
+__device__ __forceinline__ void write_obs(ObsStager& st, const Env<T>& e, const DevSpec<T>& sp, bool terminal,
+                                          float* __restrict__ gobs, int64_t env, int64_t n, int od, bool valid,
+                                          int buf, bool use_tma) {
+  const int64_t env0 = env - st.lane;
+  if (use_tma && env0 + 32 <= n) {
+    float* row = st.begin(od, buf);
+    emit_obs<IDENT>(e, sp, terminal, row);
+    st.commit(gobs + env0 * od, od, buf);
+  } else if (valid) {
+    emit_obs<IDENT>(e, sp, terminal, gobs + env * od);
+  }
+}
+
+// actions are row-major [n][na]; a[k] receives the action of NODE k (co-players: untouched)
+template <bool IDENT, typename T>
+__device__ __forceinline__ void load_actions(const T* __restrict__ act, int64_t env, const DevSpec<T>& sp, T (&a)[kF]) {
+  if (IDENT) {
+    if (sizeof(T) == 4) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(act + env * 4));
+      a[0] = *reinterpret_cast<const T*>(&v.x);
+      a[1] = *reinterpret_cast<const T*>(&v.y);
+      a[2] = *reinterpret_cast<const T*>(&v.z);
+      a[3] = *reinterpret_cast<const T*>(&v.w);
+    } else {
+      const int4 lo = __ldg(reinterpret_cast<const int4*>(act + env * 4));
+      const int4 hi = __ldg(reinterpret_cast<const int4*>(act + env * 4) + 1);
+      const T* pl = reinterpret_cast<const T*>(&lo);
+      const T* ph = reinterpret_cast<const T*>(&hi);
+      a[0] = pl[0]; a[1] = pl[1]; a[2] = ph[0]; a[3] = ph[1];
+    }
   } else {
+    const T* p = act + env * sp.n_agents;
 #pragma unroll
-    for (int i = 0; i < kF; ++i) a[i] = (i < na) ? __ldg(p + i) : T(0);
+    for (int k = 0; k < kF; ++k)
+      if (sp.slot[k] >= 0) a[k] = __ldg(p + sp.slot[k]);
+  }
+}
+
+template <bool IDENT, typename T>
+__device__ __forceinline__ void store_actions_f32(float* __restrict__ dst, int64_t env, const DevSpec<T>& sp,
+                                                  const T (&a)[kF]) {
+  if (IDENT) {
+    *reinterpret_cast<float4*>(dst + env * 4) = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+  } else {
+    float* p = dst + env * sp.n_agents;
+#pragma unroll
+    for (int k = 0; k < kF; ++k)
+      if (sp.slot[k] >= 0) p[sp.slot[k]] = (float)a[k];
   }
 }
 
 // block-level reduction of per-thread totals into stats[] (one atomic per block per word)
-template <int NV>
-__device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __restrict__ stats, double* red /*[warps][NV]*/) {
+template <int NV, int WARPS>
+__device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __restrict__ stats, double* red /*[WARPS][NV]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -120,13 +140,28 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __rest
   if (threadIdx.x < NV) {
     double x = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) x += red[w * NV + threadIdx.x];
+    for (int w = 0; w < WARPS; ++w) x += red[w * NV + threadIdx.x];
     atomicAdd(&stats[threadIdx.x], x);
   }
 }
 
-// ------------------------------------------------------------------------------------------
 template <typename T>
+__device__ __forceinline__ void load_state(const T* __restrict__ state, int64_t ld, int64_t env, Env<T>& e) {
+  T w[kStateWords];
+#pragma unroll
+  for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
+  env_from_words(e, w);
+}
+template <typename T>
+__device__ __forceinline__ void store_state(T* __restrict__ state, int64_t ld, int64_t env, const Env<T>& e) {
+  T w[kStateWords];
+  env_to_words(e, w);
+#pragma unroll
+  for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T, bool IDENT>
 __global__ void __launch_bounds__(kBlock)
 k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
         const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs, int use_tma) {
@@ -139,21 +174,16 @@ k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* _
 #pragma unroll
     for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + env);
     env_reset(e, in, __ldg(demand0 + env));
-    T w[kStateWords];
-    env_to_words(e, w);
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+    store_state(state, ld, env, e);
   }
   if (obs != nullptr) {
-    float o[28];
-    if (valid) env_obs(e, sp, false, o);
     ObsStager st(smem_f);
-    st.store(obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
     st.drain();
   }
 }
 
-template <typename T>
+template <typename T, bool IDENT>
 __global__ void __launch_bounds__(kBlock)
 k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
           float* __restrict__ obs, int use_tma) {
@@ -161,16 +191,9 @@ k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T*
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
   Env<T> e;
-  float o[28];
-  if (valid) {
-    T w[kStateWords];
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
-    env_from_words(e, w);
-    env_obs(e, sp, false, o);
-  }
+  if (valid) load_state(state, ld, env, e);
   ObsStager st(smem_f);
-  st.store(obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+  write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
   st.drain();
 }
 
@@ -183,7 +206,7 @@ struct StepPtrs {
   double* stats;
 };
 
-template <typename T>
+template <typename T, bool IDENT>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
        const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
@@ -197,19 +220,14 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
 #pragma unroll
   for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
   if (valid) {
-    T w[kStateWords];
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
-    T a[kF];
-    load_actions(actions, env, sp.n_agents, a);
+    load_state(state, ld, env, e);
+    T a[kF] = {T(0), T(0), T(0), T(0)};
+    load_actions<IDENT>(actions, env, sp, a);
     const T dn = __ldg(demand_next + env);
-    env_from_words(e, w);
     T q[kF];
-    env_orders(e, sp, a, q);
+    env_orders<IDENT>(e, sp, a, q);
     env_step(e, sp, q, dn, terminal != 0, so);
-    env_to_words(e, w);
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+    store_state(state, ld, env, e);
     if (out.reward) out.reward[env] = (float)so.reward;
     if (out.reward64) out.reward64[env] = so.reward;
     if (out.cost) {
@@ -222,10 +240,8 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     if (out.ep_return) out.ep_return[env] += so.reward;
   }
   if (out.obs != nullptr) {
-    float o[28];
-    if (valid) env_obs(e, sp, terminal != 0, o);
     ObsStager st(smem_f);
-    st.store(out.obs, env - (threadIdx.x & 31), n, 7 * sp.n_obs, valid, o, 0, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, terminal != 0, out.obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
     st.drain();
   }
   if (out.stats != nullptr) {
@@ -234,7 +250,7 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     v[1] = so.reward;
 #pragma unroll
     for (int k = 0; k < kF; ++k) { v[2 + k] = so.hold[k]; v[6 + k] = so.back[k]; }
-    block_reduce_add<10>(v, out.stats, red);
+    block_reduce_add<10, kWarpsPerBlock>(v, out.stats, red);
   }
 }
 
@@ -247,36 +263,34 @@ struct RolloutPtrs {
   double* stats;
 };
 
-template <typename T, int POLICY>
-__global__ void __launch_bounds__(kBlock)
+constexpr int kRolloutBlock = 64;     // small blocks: 65,536 envs spread evenly over 148 SMs
+
+template <typename T, int POLICY, bool IDENT>
+__global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
           int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
           const T* __restrict__ actions, const RolloutPtrs out, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[kWarpsPerBlock * 10];
-  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  __shared__ double red[(kRolloutBlock / 32) * 10];
+  const int64_t env = (int64_t)blockIdx.x * kRolloutBlock + threadIdx.x;
   const bool valid = env < n;
   const int64_t envc = valid ? env : (n - 1);       // tail lanes shadow the last env (loads only)
-  const int na = sp.n_agents;
   const int od = 7 * sp.n_obs;
+  const int64_t act_stride = n * sp.n_agents;
   ObsStager st(smem_f);
 
   Env<T> e;
-  {
-    T w[kStateWords];
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + envc];
-    env_from_words(e, w);
-  }
+  load_state(state, ld, envc, e);
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
 
-  // software pipeline: inputs of step t+1 are requested before step t is computed
+  // software pipeline: inputs of step s+1 are requested before step s is computed
   T a_pre[kF] = {T(0), T(0), T(0), T(0)};
-  if (POLICY == SN_POLICY_ACTIONS) load_actions(actions, envc, na, a_pre);
+  if (POLICY == SN_POLICY_ACTIONS) load_actions<IDENT>(actions, envc, sp, a_pre);
   T d_pre = __ldg(demand + (int64_t)(period0 + 1) * ld + envc);
 
+#pragma unroll 2
   for (int s = 0; s < n_steps; ++s) {
     const int t = period0 + s;
     const bool terminal = (t + 1 >= sp.t_max);
@@ -285,34 +299,19 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
     for (int i = 0; i < kF; ++i) a[i] = a_pre[i];
     const T dn = d_pre;
     if (s + 1 < n_steps) {
-      if (POLICY == SN_POLICY_ACTIONS) load_actions(actions + (int64_t)(s + 1) * n * na, envc, na, a_pre);
+      if (POLICY == SN_POLICY_ACTIONS) load_actions<IDENT>(actions + (int64_t)(s + 1) * act_stride, envc, sp, a_pre);
       d_pre = __ldg(demand + (int64_t)(t + 2) * ld + envc);
     }
     if (POLICY == SN_POLICY_BASE_STOCK) {
       // BaseStockPolicy.get_order_quantity on this env's own observation (utils/heuristics.py:43-57)
 #pragma unroll
-      for (int k = 0; k < kF; ++k) {
-        if (sp.slot[k] >= 0) {
-          T tg = pol.target[0];
-#pragma unroll
-          for (int i = 1; i < kF; ++i) if (sp.slot[k] == i) tg = pol.target[i];
-          const T x = base_stock(tg, e.inv[k], e.U[k], e.unfilled(k), e.lat[k], pol.lb, pol.ub, pol.rule);
-#pragma unroll
-          for (int i = 0; i < kF; ++i) if (sp.slot[k] == i) a[i] = x;
-        }
-      }
+      for (int k = 0; k < kF; ++k)
+        if (IDENT || sp.slot[k] >= 0)
+          a[k] = base_stock(pol.target[k], e.inv[k], e.U[k], e.unfilled(k), e.lat[k], pol.lb, pol.ub, pol.rule);
     }
-    if (out.traj_actions != nullptr && valid) {
-      float* g = out.traj_actions + ((int64_t)s * n + env) * na;
-      if (na == 4) {
-        *reinterpret_cast<float4*>(g) = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < kF; ++i) if (i < na) g[i] = (float)a[i];
-      }
-    }
+    if (out.traj_actions != nullptr && valid) store_actions_f32<IDENT>(out.traj_actions + (int64_t)s * act_stride, env, sp, a);
     T q[kF];
-    env_orders(e, sp, a, q);
+    env_orders<IDENT>(e, sp, a, q);
     StepOut so;
     env_step(e, sp, q, dn, terminal, so);
     acc[0] += 1.0;
@@ -320,25 +319,15 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
 #pragma unroll
     for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
     if (out.traj_reward != nullptr && valid) out.traj_reward[(int64_t)s * n + env] = (float)so.reward;
-    if (out.traj_obs != nullptr) {
-      float o[28];
-      env_obs(e, sp, terminal, o);
-      st.store(out.traj_obs + (int64_t)s * n * od, env - (threadIdx.x & 31), n, od, valid, o, s & 1, use_tma != 0);
-    }
+    if (out.traj_obs != nullptr)
+      write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, s & 1, use_tma != 0);
   }
 
   const bool ended = (period0 + n_steps >= sp.t_max);
-  if (out.obs != nullptr) {
-    float o[28];
-    env_obs(e, sp, ended, o);
-    st.store(out.obs, env - (threadIdx.x & 31), n, od, valid, o, n_steps & 1, use_tma != 0);
-  }
+  if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
   st.drain();
   if (valid) {
-    T w[kStateWords];
-    env_to_words(e, w);
-#pragma unroll
-    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+    store_state(state, ld, env, e);
     if (out.ep_return) out.ep_return[env] += acc[1];
   }
   if (out.stats != nullptr) {
@@ -346,7 +335,7 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
 #pragma unroll
       for (int i = 0; i < 10; ++i) acc[i] = 0.0;
     }
-    block_reduce_add<10>(acc, out.stats, red);
+    block_reduce_add<10, kRolloutBlock / 32>(acc, out.stats, red);
   }
 }
 
@@ -463,10 +452,11 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   d.off = (T)s->dpa_offset; d.lb = (T)s->dpa_lb; d.ub = (T)s->dpa_ub;
   if (s->global_observable) {
     d.n_obs = 4;
-    for (int k = 0; k < 4; ++k) d.obs_node[k] = k;
+    for (int k = 0; k < 4; ++k) d.pos[k] = k;
   } else {
     d.n_obs = s->n_agents;
-    for (int i = 0; i < s->n_agents; ++i) d.obs_node[i] = s->agents[i];
+    for (int k = 0; k < 4; ++k) d.pos[k] = -1;
+    for (int i = 0; i < s->n_agents; ++i) d.pos[s->agents[i]] = i;
   }
   d.n_agents = s->n_agents;
   d.lo = lo;
@@ -475,13 +465,20 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   return d;
 }
 
+// centralized, full layout: action column k = node k and all four nodes observed in chain order
+bool is_identity(const sn_spec* s) {
+  if (s->n_agents != 4) return false;
+  for (int k = 0; k < 4; ++k) if (s->agents[k] != k) return false;
+  return true;      // obs: global or local both give positions 0..3
+}
+
 template <typename T>
-int lower_policy(const sn_policy* p, int dtype, int ncols, sn::DevPolicy<T>* out) {
+int lower_policy(const sn_policy* p, const sn_spec* s, int dtype, sn::DevPolicy<T>* out) {
   std::memset(out, 0, sizeof(*out));
   if (p == nullptr) return SN_OK;
-  for (int i = 0; i < 4; ++i) {
-    if (dtype == SN_I32 && i < ncols && !is_integral(p->target[i])) return fail(SN_ERR_TYPE, "policy target[%d] must be integral for SN_I32", i);
-    out->target[i] = (T)p->target[i];
+  for (int i = 0; i < s->n_agents; ++i) {
+    if (dtype == SN_I32 && !is_integral(p->target[i])) return fail(SN_ERR_TYPE, "policy target[%d] must be integral for SN_I32", i);
+    out->target[s->agents[i]] = (T)p->target[i];       // per-column -> per-node
   }
   if (dtype == SN_I32 && (!is_integral(p->lb) || !is_integral(p->ub))) return fail(SN_ERR_TYPE, "policy bounds must be integral for SN_I32");
   out->lb = (T)p->lb; out->ub = (T)p->ub; out->rule = p->rule;
@@ -506,22 +503,29 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // always a multiple of 16) and a 16-byte multiple size.
 inline int tma_ok(const float* obs) { return obs != nullptr && aligned16(obs) ? 1 : 0; }
 
-constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * 28 * sizeof(float);   // 28,672 B
+constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * 28 * sizeof(float);                 // 28,672 B
+constexpr size_t kRolloutSmem = (sn::kRolloutBlock / 32) * 2 * 32 * 28 * sizeof(float);         // 14,336 B
 
-inline unsigned grid_for(int64_t n) { return (unsigned)((n + sn::kBlock - 1) / sn::kBlock); }
+inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)((n + block - 1) / block); }
 
 template <typename T>
 int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
              float* obs, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  sn::k_reset<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
+  if (is_identity(spec))
+    sn::k_reset<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
+  else
+    sn::k_reset<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
   return cuda_ok("sn_reset launch");
 }
 
 template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  sn::k_observe<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
+  if (is_identity(spec))
+    sn::k_observe<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
+  else
+    sn::k_observe<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
   return cuda_ok("sn_observe launch");
 }
 
@@ -529,9 +533,21 @@ template <typename T>
 int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
             const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  sn::k_step<T><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
-                                                          (const T*)demand_next, out, tma_ok(out.obs));
+  if (is_identity(spec))
+    sn::k_step<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
+                                                                  (const T*)demand_next, out, tma_ok(out.obs));
+  else
+    sn::k_step<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
+                                                                   (const T*)demand_next, out, tma_ok(out.obs));
   return cuda_ok("sn_step launch");
+}
+
+template <typename T, int POLICY, bool IDENT>
+void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
+                    void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
+                    cudaStream_t st) {
+  sn::k_rollout<T, POLICY, IDENT><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
+      d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma);
 }
 
 template <typename T>
@@ -540,16 +556,18 @@ int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period
                const sn::RolloutPtrs& out, cudaStream_t st) {
   const auto d = lower<T>(spec);
   sn::DevPolicy<T> p;
-  const int rc = lower_policy<T>(policy, dtype, spec->n_agents, &p);
+  const int rc = lower_policy<T>(policy, spec, dtype, &p);
   if (rc != SN_OK) return rc;
   const int tma = (out.traj_obs == nullptr || aligned16(out.traj_obs)) && (out.obs == nullptr || aligned16(out.obs)) &&
                   (((int64_t)n * 7 * d.n_obs * 4) % 16 == 0);
-  if (policy_kind == SN_POLICY_ACTIONS)
-    sn::k_rollout<T, SN_POLICY_ACTIONS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(
-        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma);
-  else
-    sn::k_rollout<T, SN_POLICY_BASE_STOCK><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(
-        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, tma);
+  const bool ident = is_identity(spec);
+  if (policy_kind == SN_POLICY_ACTIONS) {
+    if (ident) launch_rollout<T, SN_POLICY_ACTIONS, true>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st);
+    else launch_rollout<T, SN_POLICY_ACTIONS, false>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st);
+  } else {
+    if (ident) launch_rollout<T, SN_POLICY_BASE_STOCK, true>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st);
+    else launch_rollout<T, SN_POLICY_BASE_STOCK, false>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st);
+  }
   return cuda_ok("sn_rollout launch");
 }
 
@@ -607,7 +625,7 @@ int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, 
   if (period >= spec->max_episode_steps)
     return fail(SN_ERR_TERMINAL, "Cannot take action when the state is terminal.");     // envs.py:88-89
   if (!state || !actions || !demand_next) return fail(SN_ERR_INVALID, "sn_step: state, actions and demand_next must be non-NULL");
-  if (spec->n_agents == 4 && dtype != SN_F64 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_step: actions must be 16-byte aligned");
+  if (spec->n_agents == 4 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_step: actions must be 16-byte aligned");
   const int terminal = (period + 1 >= spec->max_episode_steps) ? 1 : 0;
   const sn::StepPtrs out{obs, reward, reward64, cost, ep_return, stats};
   cudaStream_t st = (cudaStream_t)stream;
@@ -644,7 +662,7 @@ int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   if (!state || !demand) return fail(SN_ERR_INVALID, "sn_rollout: state and demand must be non-NULL");
   if (policy_kind == SN_POLICY_ACTIONS) {
     if (!actions) return fail(SN_ERR_INVALID, "sn_rollout: actions must be non-NULL for SN_POLICY_ACTIONS");
-    if (spec->n_agents == 4 && dtype != SN_F64 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_rollout: actions must be 16-byte aligned");
+    if (spec->n_agents == 4 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_rollout: actions must be 16-byte aligned");
   } else if (policy_kind == SN_POLICY_BASE_STOCK) {
     if (!policy) return fail(SN_ERR_INVALID, "sn_rollout: policy must be non-NULL for SN_POLICY_BASE_STOCK");
     if (policy->rule != SN_RULE_A && policy->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown policy rule %d", policy->rule);

@@ -1,0 +1,64 @@
+"""Env factories with the reference's names and arguments (envs.py:163-286, 289-414, 501-596),
+returning a batched `SupplyNetVecEnv` instead of one gym env.
+
+    ref:   env  = make_beer_game_uniform_multi_facility(agent_managed_facilities=[...], box_action_space=True, ...)
+           venv = make_vec_env(lambda: env, n_env=2)
+    here:  venv = make_beer_game_uniform_multi_facility(agent_managed_facilities=[...], box_action_space=True, ...,
+                                                       n_envs=65536, device="cuda")
+
+Extra keyword arguments (n_envs, device, dtype, seed, episode_source, output) select the batch; every
+reference argument keeps its meaning.  `env_mode="test"` needs the demand sample files the reference
+loads from ./data/deepbeerinventory/*.npy, which are not part of the reference repo either.
+"""
+from __future__ import annotations
+
+from . import spec as _spec
+from .vec_env import SupplyNetVecEnv
+
+
+def _check_mode(env_mode):
+    if env_mode == "test":
+        raise FileNotFoundError("env_mode='test' reads ./data/deepbeerinventory/*.npy, which the reference "
+                                "repository does not ship; pass demands through load_episode instead")
+    if env_mode != "train":
+        raise ValueError(env_mode)
+
+
+def make_beer_game_uniform_multi_facility(global_observable=False, agent_managed_facilities=None,
+                                          max_episode_steps=100, return_dict=False, random_init=True,
+                                          env_mode="train", box_action_space=False, *, n_envs=1, device="cuda",
+                                          dtype="float32", seed=0, episode_source="device", output="torch"):
+    """The complex scenario (envs.py:289-414): demand U{0..8}, h=0.5, b=1, co-player targets 19/20/20/14."""
+    _check_mode(env_mode)
+    if return_dict:
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered by the batched env")
+    sp = _spec.uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    return SupplyNetVecEnv(sp, n_envs, device, dtype, seed, episode_source, output, bool(box_action_space))
+
+
+def make_beer_game_normal_multi_facility(global_observable=False, agent_managed_facilities=None,
+                                         max_episode_steps=100, return_dict=False, random_init=False,
+                                         env_mode="train", box_action_space=False, *, n_envs=1, device="cuda",
+                                         dtype="float32", seed=0, episode_source="device", output="torch"):
+    """The basic scenario (envs.py:163-286): demand round(max(N(10,2),0)), h=(1,.75,.5,.25), b=(10,0,0,0)."""
+    _check_mode(env_mode)
+    if return_dict:
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered by the batched env")
+    sp = _spec.normal_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    return SupplyNetVecEnv(sp, n_envs, device, dtype, seed, episode_source, output, bool(box_action_space))
+
+
+def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game", max_period=35, return_dict=False,
+                   random_init=False, seed=None, *, n_envs=1, device="cuda", dtype="int32",
+                   episode_source="numpy_bulk", output="torch"):
+    """The classic beer game (envs.py:501-596): demand 4,4,4,4,8,8,...; MultiDiscrete([17]*F) actions.
+    `random_init` is accepted and ignored exactly as in the reference (never passed to Arc, Q16)."""
+    if demand_type == "deterministic_random":
+        raise NotImplementedError("demand_type='deterministic_random' (envs.py:519-520) is not offered")
+    if demand_type not in ("classic_beer_game", "normal", "uniform"):
+        raise ValueError()
+    if return_dict:
+        raise NotImplementedError("return_dict=True is not offered by the batched env")
+    sp = _spec.classic_spec(agent_managed_facilities, max_period, demand_type)
+    return SupplyNetVecEnv(sp, n_envs, device, dtype, 0 if seed is None else seed, episode_source, output,
+                           box_action_space=False, multi_discrete=True)

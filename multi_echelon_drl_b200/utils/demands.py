@@ -99,13 +99,30 @@ def seeded_episode_inputs(spec: ScenarioSpec, seeds):
     inv_distributor, inv_manufacturer, then per arc in the factories' arc-list order
     (ext->man, man->dis, dis->who, who->ret): shipments, then sales orders."""
     seeds = np.asarray(seeds).reshape(-1)
-    n = seeds.shape[0]
+    return seeded_episode_inputs_from_streams(spec, [np.random.RandomState(int(s)) for s in seeds])
+
+
+def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
+    """Same distributions, vectorised draws from one stream `rs` (RandomState)."""
+    dem = demand_for(spec)
+    if spec.random_init:
+        init = np.empty((n, INIT_WORDS), dtype=np.int64)
+        init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
+        init[:, 4:] = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, INIT_WORDS - 4))
+    else:
+        init = np.broadcast_to(_fixed_init(spec), (n, INIT_WORDS)).copy()
+    return init, dem.sample(n, rs)
+
+
+def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
+    """Like seeded_episode_inputs but continuing persistent per-env RandomState objects, so that env i
+    over successive resets equals one reference env seeded once and reset repeatedly."""
+    n = len(streams)
     dem = demand_for(spec)
     init = np.zeros((n, INIT_WORDS), dtype=np.int64)
     demand = np.zeros((n, dem.size), dtype=np.int64)
     fixed = _fixed_init(spec)
-    for i, seed in enumerate(seeds):
-        rs = np.random.RandomState(int(seed))
+    for i, rs in enumerate(streams):
         if not spec.random_init:
             init[i] = fixed
             demand[i] = dem.draw(rs)
@@ -122,15 +139,3 @@ def seeded_episode_inputs(spec: ScenarioSpec, seeds):
             for j in range(INFO_LEADTIME[k]):
                 init[i, _SO_OFF[k] + j] = rs.randint(plo, phi)
     return init, demand
-
-
-def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
-    """Same distributions, vectorised draws from one stream `rs` (RandomState)."""
-    dem = demand_for(spec)
-    if spec.random_init:
-        init = np.empty((n, INIT_WORDS), dtype=np.int64)
-        init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
-        init[:, 4:] = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, INIT_WORDS - 4))
-    else:
-        init = np.broadcast_to(_fixed_init(spec), (n, INIT_WORDS)).copy()
-    return init, dem.sample(n, rs)

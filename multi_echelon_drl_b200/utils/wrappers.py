@@ -1,0 +1,19 @@
+"""The d+a ordering rule (reference utils/wrappers.py:6-31) for the batched env.
+
+The reference monkey-patches env.step so that the action `a` is turned into the order
+clip(latest_demand + a + offset, lb, ub).  Here the rule is a field of the scenario spec and is
+applied inside the step / rollout kernels; `wrap_action_d_plus_a` keeps the reference's name and
+arguments and returns the same env object with the rule switched on."""
+from __future__ import annotations
+
+
+def wrap_action_d_plus_a(env, offset=-8, lb: int = 0, ub: int = 16):
+    from .. import _lib
+    import ctypes as C
+    sim = env.sim
+    spec = env.spec.with_rule("d+a", offset, lb, ub)
+    c_spec = spec.to_c()
+    _lib.check(sim.lib.sn_spec_validate(C.byref(c_spec), sim.dtype_code))
+    env.spec = spec
+    sim.spec, sim._c_spec = spec, c_spec
+    return env

@@ -1,0 +1,242 @@
+"""SupplyNetVecEnv: the stable-baselines3 VecEnv surface on top of the CUDA simulator.
+
+Stands in for `VecNormalize?(make_vec_env(env_factory, n_env))` = DummyVecEnv[Monitor[TimeLimit[env]]]
+of the reference's trainers (train_td3.py:82-101, train_a2c.py:68-86, train_dqn.py:69-87) with
+thousands to millions of envs instead of 2.  Observations, rewards and dones are torch tensors that
+already live on the device (`output="torch"`, north_star) or numpy arrays staged through pinned host
+memory (`output="numpy"`, what SB3 itself consumes).
+
+SB3 1.x semantics reproduced: old 4-tuple step API, auto-reset on done with
+`infos[i]["terminal_observation"]`, Monitor's `infos[i]["episode"] = {"r", "l", "t"}`,
+`infos[i]["TimeLimit.truncated"] = False` (the env terminates itself at max_episode_steps == the
+registry's TimeLimit, register_envs.py:77).  All envs share one period counter: episodes have a
+fixed length, so a batch that starts together ends together.
+"""
+from __future__ import annotations
+
+import time
+from collections.abc import Sequence
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import spaces
+from .simulator import BatchedSupplyNetwork
+from .spec import ScenarioSpec
+from .utils import demands as _dem
+
+
+class LazyInfos(Sequence):
+    """Behaves like SB3's list of per-env info dicts without materialising N dicts per step;
+    the batched tensors are available as attributes."""
+
+    def __init__(self, n, terminal_observation=None, episode_return=None, episode_length=0, elapsed=0.0):
+        self.n = n
+        self.terminal_observation = terminal_observation      # [n, obs_dim] or None
+        self.episode_return = episode_return                  # [n] float64 or None
+        self.episode_length = episode_length
+        self.elapsed = elapsed
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self.n))]
+        if not -self.n <= i < self.n:
+            raise IndexError(i)
+        if self.terminal_observation is None:
+            return {}
+        return {"terminal_observation": self.terminal_observation[i],
+                "episode": {"r": round(float(self.episode_return[i]), 6), "l": self.episode_length,
+                            "t": round(self.elapsed, 6)},
+                "TimeLimit.truncated": False}
+
+
+class SupplyNetVecEnv:
+    """VecEnv duck type (num_envs, observation_space, action_space, reset, step_async, step_wait, step,
+    close, seed, get_attr, set_attr, env_method, env_is_wrapped)."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, spec: ScenarioSpec, n_envs: int, device="cuda", dtype="float32", seed: int = 0,
+                 episode_source: str = "device", output: str = "torch", box_action_space: bool = True,
+                 multi_discrete: bool = False):
+        if episode_source not in ("device", "numpy_bulk", "numpy_seeded"):
+            raise ValueError("episode_source must be 'device', 'numpy_bulk' or 'numpy_seeded'")
+        if output not in ("torch", "numpy"):
+            raise ValueError("output must be 'torch' or 'numpy'")
+        if spec.n_agents > 1 and not box_action_space and not multi_discrete:
+            raise ValueError("length of agent_managed_facilities >= 1, only box_action_space is allowed. "
+                             "Please specify box_action_space=True")                    # envs.py:175-179
+        self.spec = spec
+        self.num_envs = int(n_envs)
+        self.sim = BatchedSupplyNetwork(spec, n_envs, device, dtype)
+        self.device = self.sim.device
+        self.output = output
+        self.episode_source = episode_source
+        # spaces exactly as the factories build them (envs.py:269-277, 397-405, 587-588)
+        if multi_discrete:
+            self.action_space = spaces.MultiDiscrete([int(spec.action_high) + 1] * spec.n_agents)
+        elif box_action_space:
+            self.action_space = spaces.Box(spec.action_low, spec.action_high, shape=(spec.n_agents,))
+        else:
+            self.action_space = spaces.Discrete(int(spec.action_high) + 1)
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(spec.obs_dim,))
+        self._actions = None
+        self._t0 = time.time()
+        self.episodes_done = 0
+        n, od = self.num_envs, spec.obs_dim
+        self._obs = torch.zeros((n, od), dtype=torch.float32, device=self.device)
+        self._term_obs = torch.zeros((n, od), dtype=torch.float32, device=self.device)
+        self._dones = torch.zeros((n,), dtype=torch.bool, device=self.device)
+        self._last_returns = torch.zeros((n,), dtype=torch.float64, device=self.device)
+        if output == "numpy":
+            self._h_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype).pin_memory()
+            self._d_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype, device=self.device)
+            self._h_obs = torch.zeros((n, od), dtype=torch.float32).pin_memory()
+            self._h_rew = torch.zeros((n,), dtype=torch.float32).pin_memory()
+            self._h_term = torch.zeros((n, od), dtype=torch.float32).pin_memory()
+        self.seed(seed)
+
+    # ------------------------------------------------------------------ episode inputs
+    def seed(self, seed: Optional[int] = None):
+        """Unlike the reference (whose env.seed only seeds an unused generator, envs.py:115-117, Q9)
+        this really seeds the per-env demand / initial-state streams."""
+        seed = 0 if seed is None else int(seed)
+        self._seed = seed
+        if self.episode_source == "device":
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(seed)
+        elif self.episode_source == "numpy_bulk":
+            self._rs = np.random.RandomState(seed)
+        else:
+            self._streams = [np.random.RandomState(seed + i) for i in range(self.num_envs)]
+        return [seed + i for i in range(self.num_envs)]
+
+    def _next_episode(self):
+        sp, sim = self.spec, self.sim
+        if self.episode_source == "device":
+            self._device_episode()
+        elif self.episode_source == "numpy_bulk":
+            init, demand = _dem.bulk_episode_inputs(sp, self.num_envs, self._rs)
+            sim.load_episode(init, demand)
+        else:
+            init, demand = _dem.seeded_episode_inputs_from_streams(sp, self._streams)
+            sim.load_episode(init, demand)
+
+    def _device_episode(self):
+        """Same distributions as utils/demands.py / Arc.reset / Node.reset, drawn on the device with
+        torch's Philox generator directly in the structure-of-arrays layout (throughput path; not
+        stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity)."""
+        sp, sim, g = self.spec, self.sim, self._gen
+        n, dev = sim.ld, self.device
+        T3 = sp.max_episode_steps + 3
+        a, b = sp.demand_params
+        if sp.demand_pattern == "uniform":
+            d = torch.randint(int(a), int(b) + 1, (T3, n), generator=g, device=dev, dtype=torch.int32)
+        elif sp.demand_pattern == "normal":
+            d = torch.round(torch.clamp_min(a + b * torch.randn((T3, n), generator=g, device=dev), 0))
+        else:
+            row = torch.tensor([4] * 4 + [8] * (T3 - 4), device=dev)
+            d = row[:, None].expand(T3, n)
+        sim.demand.copy_(d.to(sim.tdtype))
+        if sp.random_init:
+            sim.init[:4] = torch.randint(sp.init_inventory[0], sp.init_inventory[1], (4, n), generator=g, device=dev,
+                                         dtype=torch.int32).to(sim.tdtype)
+            sim.init[4:] = torch.randint(sp.init_pipeline[0], sp.init_pipeline[1], (15, n), generator=g, device=dev,
+                                         dtype=torch.int32).to(sim.tdtype)
+        else:
+            sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=dev).to(sim.tdtype)[:, None].expand(19, n))
+
+    # ------------------------------------------------------------------ VecEnv API
+    def reset(self):
+        self._next_episode()
+        self.sim.reset(self._obs)
+        self._t0 = time.time()
+        return self._out_obs()
+
+    def step_async(self, actions):
+        self._actions = actions
+
+    def step_wait(self):
+        sim = self.sim
+        actions = self._actions
+        if self.output == "numpy":
+            a = np.asarray(actions)
+            if a.ndim == 1:
+                a = a[:, None]
+            self._h_act.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(self._h_act.dtype))
+            self._d_act.copy_(self._h_act, non_blocking=True)
+            actions = self._d_act
+        elif isinstance(actions, torch.Tensor) and actions.dim() == 1:
+            actions = actions[:, None]
+        _, rew, done = sim.step(actions, obs_out=self._obs)
+        if done:
+            self._term_obs.copy_(self._obs)
+            self._last_returns.copy_(sim.ep_return)
+            self.episodes_done += self.num_envs
+            infos = LazyInfos(self.num_envs, self._term_obs, self._last_returns, sim.T, time.time() - self._t0)
+            self._next_episode()                    # auto-reset (DummyVecEnv.step_wait)
+            sim.reset(self._obs)
+            self._t0 = time.time()
+            self._dones.fill_(True)
+        else:
+            infos = LazyInfos(self.num_envs)
+            self._dones.fill_(False)
+        if self.output == "numpy":
+            self._h_obs.copy_(self._obs, non_blocking=True)
+            self._h_rew.copy_(rew, non_blocking=True)
+            if done:
+                self._h_term.copy_(self._term_obs, non_blocking=True)
+                infos.terminal_observation = self._h_term.numpy()
+                infos.episode_return = self._last_returns.cpu().numpy()
+            torch.cuda.current_stream(self.device).synchronize()
+            return (self._h_obs.numpy(), self._h_rew.numpy(), np.full((self.num_envs,), done, dtype=bool), infos)
+        return self._obs, rew, self._dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _out_obs(self):
+        if self.output == "numpy":
+            self._h_obs.copy_(self._obs, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._h_obs.numpy()
+        return self._obs
+
+    def close(self):
+        pass
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [getattr(self, attr_name)] * n
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [getattr(self, method_name)(*args, **kwargs)] * n
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [False] * n
+
+    def get_original_obs(self):
+        return self._obs
+
+    # convenience mirrors of the single-env attributes consumers read (envs.py:53-60)
+    @property
+    def period(self):
+        return self.sim.period
+
+    @property
+    def terminal(self):
+        return self.sim.terminal
+
+    @property
+    def max_episode_steps(self):
+        return self.spec.max_episode_steps
