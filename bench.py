@@ -3,7 +3,7 @@
 
 Workload (config.workload): BASELINE config 2 — complex ("uniform") scenario, MultiFacility
 centralized control with full information, 65,536 envs per GPU, fixed integer actions, 100-period
-episodes.  One bench *step* = one full parity rollout of that batch: sn_reset + sn_rollout streaming
+episodes.  One bench *step* = one full parity rollout of that batch: one sn_episode launch streaming
 the actions [100, N, 4] and demands in and the complete trajectory (obs [100, N, 28] f32, reward
 [100, N] f32) out = 6,553,600 env-steps and ~0.9 GB of HBM traffic per step (inputs + outputs are
 several times the 126 MB L2, so no L2 flush is needed between steps).
@@ -188,11 +188,10 @@ def run_native(args):
     k_events = []
 
     def device_step(record):
-        sim.reset()
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        sim.rollout(T, actions=d_actions, traj_obs=traj_obs, traj_reward=traj_rew)
+        sim.episode(T, actions=d_actions, traj_obs=traj_obs, traj_reward=traj_rew, write_state=False)
         if record:
             e1.record()
             k_events.append((e0, e1))
@@ -202,8 +201,7 @@ def run_native(args):
 
     def e2e_step():
         sim.load_episode(h_init, h_demand)                    # H2D init + demand
-        sim.reset()
-        sim.rollout(T, actions=h_actions, traj_obs=traj_obs, traj_reward=traj_rew)   # H2D actions
+        sim.episode(T, actions=h_actions, traj_obs=traj_obs, traj_reward=traj_rew, write_state=False)   # H2D actions
         h_traj_obs.copy_(traj_obs, non_blocking=True)         # D2H trajectory
         h_traj_rew.copy_(traj_rew, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -267,15 +265,15 @@ def run_native(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": "config2: complex (uniform) scenario, MultiFacility centralized full-info, "
                                    f"{n} envs/GPU x {T} periods fixed-action parity rollout, full trajectory out",
-                       "envs_per_gpu": n, "periods": T, "step": "sn_reset + sn_rollout (1 episode of the batch)",
+                       "envs_per_gpu": n, "periods": T, "step": "one sn_episode launch (in-kernel reset + 100 periods, 1 episode of the batch)",
                        "l2": "inputs+outputs ~0.9 GB per step >> 126 MB L2, no flush needed",
                        "parallelism": f"env-sharded x{world}, stats all-reduce only"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "BatchedSupplyNetwork.load_episode/reset/rollout with pinned host tensors + trajectory D2H"},
-            "gpu_launches": 2 * args.steps,
+                    "api": "BatchedSupplyNetwork.load_episode + episode with pinned host tensors + trajectory D2H"},
+            "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_rollout<int,ACTIONS>", "kernel_ms": kernel_ms,
+                         "traffic": None, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -316,18 +314,27 @@ def single_step_numbers(torch, dev, peak):
             for t in range(5):
                 one(t)
             torch.cuda.synchronize()
+            # the per-period launches are captured in a CUDA graph: at 65,536 envs one period is a few
+            # microseconds of work, far below the cost of issuing a launch from Python
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for t in range(5, steps):
+                    one(t)
+            graph.replay()
+            torch.cuda.synchronize()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
             s.record()
-            for t in range(5, steps):
-                one(t)
+            for _ in range(reps):
+                graph.replay()
             e.record()
             torch.cuda.synchronize()
-            ms = s.elapsed_time(e) / (steps - 5)
+            ms = s.elapsed_time(e) / (reps * (steps - 5))
             bps = BYTES_PER_ENV_STEP_SINGLE + (112 if with_obs else 0)
             res["with_obs" if with_obs else "state_only"] = {
                 "env_steps_per_s": n / (ms * 1e-3), "us_per_launch": ms * 1e3,
                 "achieved_gbs": n * bps / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": n * bps / (ms * 1e-3) / 1e9 / peak,
-                "bytes_per_env_step": bps}
+                "bytes_per_env_step": bps, "launch": "CUDA graph of 94 sn_step launches"}
         out[tag] = res
         del sim
     # config-3 mode: heuristic rollout, stats only (ALU/latency bound, ~4 B/env-step of HBM traffic)
@@ -339,13 +346,13 @@ def single_step_numbers(torch, dev, peak):
     sim.init.copy_(torch.randint(0, 9, sim.init.shape, generator=g, device=dev, dtype=torch.int32))
     pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
     for _ in range(3):
-        sim.reset(); sim.rollout(T, policy=pol)
+        sim.episode(T, policy=pol, write_state=False)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     reps = 20
     for _ in range(reps):
-        sim.reset(); sim.rollout(T, policy=pol)
+        sim.episode(T, policy=pol, write_state=False)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / reps

@@ -158,6 +158,21 @@ int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
                    const void* actions, const sn_policy* policy, float* traj_obs, float* traj_reward,
                    float* traj_actions, float* obs, double* ep_return, double* stats, void* stream);
 
+/* episode — sn_reset + sn_rollout from period 0 fused in ONE launch: the env is reset from `init`
+ * inside the kernel (envs.py:64-80) and stepped n_steps periods (envs.py:82-113) without the state
+ * ever living in HBM.  This is the form used for fixed-action parity rollouts and for base-stock /
+ * HGE heuristic rollouts (utils/heuristics.py) over whole episodes.
+ *   init, demand            as in sn_reset / sn_rollout
+ *   obs0                    device, float [n_envs][obs_dim] (out, may be NULL): what reset() returns
+ *   state                   device, dtype [SN_STATE_WORDS][ld] (out, may be NULL): state after n_steps
+ *   ep_return               device, double [n_envs] (out, may be NULL): OVERWRITTEN with the sum of rewards
+ *   other arguments         as in sn_rollout */
+int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t n_steps,
+                   const void* init, const void* demand, int32_t policy_kind, const void* actions,
+                   const sn_policy* policy, float* obs0, float* traj_obs, float* traj_reward,
+                   float* traj_actions, float* obs, void* state, double* ep_return, double* stats,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsupplynet.so")
+LIB_PATH = os.environ.get("SUPPLYNET_LIB", os.path.join(_HERE, "csrc", "libsupplynet.so"))   # override: A/B builds
 
 SN_I32, SN_F32, SN_F64 = 0, 1, 2
 SN_RULE_A, SN_RULE_D_PLUS_A = 0, 1
@@ -63,6 +63,8 @@ SIGNATURES = {
     "sn_heuristic": (_I32, [C.POINTER(SnPolicy), _I32, _I64, _P, _P, _P]),
     "sn_rollout": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P]),
+    "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
+                          _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

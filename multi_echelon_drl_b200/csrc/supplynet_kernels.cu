@@ -263,13 +263,23 @@ struct RolloutPtrs {
   double* stats;
 };
 
-constexpr int kRolloutBlock = 64;     // small blocks: 65,536 envs spread evenly over 148 SMs
+#ifndef SN_ROLLOUT_BLOCK
+#define SN_ROLLOUT_BLOCK 64             // small blocks: 65,536 envs spread evenly over 148 SMs
+#endif
+#ifndef SN_ROLLOUT_UNROLL
+#define SN_ROLLOUT_UNROLL 1             // A/B on B200: 1..4 within noise for the trajectory rollout, 1 best for the policy rollout
+#endif
+#define SN_STR2(x) #x
+#define SN_STR(x) SN_STR2(x)
+#define SN_PRAGMA_UNROLL(n) _Pragma(SN_STR(unroll n))
+constexpr int kRolloutBlock = SN_ROLLOUT_BLOCK;
 
 template <typename T, int POLICY, bool IDENT>
 __global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
           int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
-          const T* __restrict__ actions, const RolloutPtrs out, int use_tma) {
+          const T* __restrict__ actions, const RolloutPtrs out, int use_tma, const T* __restrict__ init,
+          float* __restrict__ obs0) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ double red[(kRolloutBlock / 32) * 10];
   const int64_t env = (int64_t)blockIdx.x * kRolloutBlock + threadIdx.x;
@@ -280,7 +290,16 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   ObsStager st(smem_f);
 
   Env<T> e;
-  load_state(state, ld, envc, e);
+  if (init != nullptr) {
+    // episode mode (sn_episode): reset in-kernel, the state never has to exist in HBM
+    T in[kInitWords];
+#pragma unroll
+    for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + envc);
+    env_reset(e, in, __ldg(demand + envc));
+    if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, 1, use_tma != 0);
+  } else {
+    load_state(state, ld, envc, e);
+  }
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
@@ -290,7 +309,7 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   if (POLICY == SN_POLICY_ACTIONS) load_actions<IDENT>(actions, envc, sp, a_pre);
   T d_pre = __ldg(demand + (int64_t)(period0 + 1) * ld + envc);
 
-#pragma unroll 2
+SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
   for (int s = 0; s < n_steps; ++s) {
     const int t = period0 + s;
     const bool terminal = (t + 1 >= sp.t_max);
@@ -327,8 +346,8 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
   st.drain();
   if (valid) {
-    store_state(state, ld, env, e);
-    if (out.ep_return) out.ep_return[env] += acc[1];
+    if (state != nullptr) store_state(state, ld, env, e);
+    if (out.ep_return) out.ep_return[env] = (init != nullptr ? 0.0 : out.ep_return[env]) + acc[1];
   }
   if (out.stats != nullptr) {
     if (!valid) {
@@ -545,28 +564,28 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* stat
 template <typename T, int POLICY, bool IDENT>
 void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
                     void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
-                    cudaStream_t st) {
+                    cudaStream_t st, const void* init, float* obs0) {
   sn::k_rollout<T, POLICY, IDENT><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
-      d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma);
+      d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
 }
 
 template <typename T>
 int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period0, int n_steps, void* state,
                const void* demand, int policy_kind, const void* actions, const sn_policy* policy,
-               const sn::RolloutPtrs& out, cudaStream_t st) {
+               const sn::RolloutPtrs& out, cudaStream_t st, const void* init = nullptr, float* obs0 = nullptr) {
   const auto d = lower<T>(spec);
   sn::DevPolicy<T> p;
   const int rc = lower_policy<T>(policy, spec, dtype, &p);
   if (rc != SN_OK) return rc;
   const int tma = (out.traj_obs == nullptr || aligned16(out.traj_obs)) && (out.obs == nullptr || aligned16(out.obs)) &&
-                  (((int64_t)n * 7 * d.n_obs * 4) % 16 == 0);
+                  (obs0 == nullptr || aligned16(obs0)) && (((int64_t)n * 7 * d.n_obs * 4) % 16 == 0);
   const bool ident = is_identity(spec);
   if (policy_kind == SN_POLICY_ACTIONS) {
-    if (ident) launch_rollout<T, SN_POLICY_ACTIONS, true>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st);
-    else launch_rollout<T, SN_POLICY_ACTIONS, false>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st);
+    if (ident) launch_rollout<T, SN_POLICY_ACTIONS, true>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0);
+    else launch_rollout<T, SN_POLICY_ACTIONS, false>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0);
   } else {
-    if (ident) launch_rollout<T, SN_POLICY_BASE_STOCK, true>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st);
-    else launch_rollout<T, SN_POLICY_BASE_STOCK, false>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st);
+    if (ident) launch_rollout<T, SN_POLICY_BASE_STOCK, true>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st, init, obs0);
+    else launch_rollout<T, SN_POLICY_BASE_STOCK, false>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st, init, obs0);
   }
   return cuda_ok("sn_rollout launch");
 }
@@ -676,6 +695,35 @@ int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
     case SN_I32: return do_rollout<int32_t>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
     case SN_F32: return do_rollout<float>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
     default: return do_rollout<double>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
+  }
+}
+
+int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t n_steps, const void* init,
+                   const void* demand, int32_t policy_kind, const void* actions, const sn_policy* policy, float* obs0,
+                   float* traj_obs, float* traj_reward, float* traj_actions, float* obs, void* state,
+                   double* ep_return, double* stats, void* stream) {
+  int rc = validate(spec, dtype);
+  if (rc != SN_OK) return rc;
+  if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
+  if (n_steps < 1 || n_steps > spec->max_episode_steps)
+    return fail(SN_ERR_INVALID, "sn_episode: n_steps=%d outside 1..%d", n_steps, spec->max_episode_steps);
+  if (!init || !demand) return fail(SN_ERR_INVALID, "sn_episode: init and demand must be non-NULL");
+  if (policy_kind == SN_POLICY_ACTIONS) {
+    if (!actions) return fail(SN_ERR_INVALID, "sn_episode: actions must be non-NULL for SN_POLICY_ACTIONS");
+    if (spec->n_agents == 4 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_episode: actions must be 16-byte aligned");
+  } else if (policy_kind == SN_POLICY_BASE_STOCK) {
+    if (!policy) return fail(SN_ERR_INVALID, "sn_episode: policy must be non-NULL for SN_POLICY_BASE_STOCK");
+    if (policy->rule != SN_RULE_A && policy->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown policy rule %d", policy->rule);
+  } else {
+    return fail(SN_ERR_INVALID, "unknown policy_kind %d", policy_kind);
+  }
+  if (traj_actions && spec->n_agents == 4 && !aligned16(traj_actions)) return fail(SN_ERR_INVALID, "sn_episode: traj_actions must be 16-byte aligned");
+  const sn::RolloutPtrs out{traj_obs, traj_reward, traj_actions, obs, ep_return, stats};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: return do_rollout<int32_t>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
+    case SN_F32: return do_rollout<float>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
+    default: return do_rollout<double>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
   }
 }
 

@@ -26,7 +26,7 @@ def _factory(kind, role, discrete, global_observable, dplusa=None, box=None):
     maker = make_beer_game_uniform_multi_facility if kind == "uniform" else make_beer_game_normal_multi_facility
 
     def func(**batch_kwargs):
-        env = maker(agent_managed_facilities=role, box_action_space=(~discrete if box is None else box),
+        env = maker(agent_managed_facilities=role, box_action_space=(~int(discrete) if box is None else box),
                     random_init=True, global_observable=global_observable, max_episode_steps=100, **batch_kwargs)
         if dplusa is not None:
             env = wrap_action_d_plus_a(env, offset=dplusa[0], lb=dplusa[1], ub=dplusa[2])

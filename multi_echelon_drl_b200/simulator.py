@@ -188,6 +188,39 @@ class BatchedSupplyNetwork:
         return dict(obs=self.obs, traj_obs=traj_obs, traj_reward=traj_reward, traj_actions=traj_actions,
                     done=self.terminal)
 
+    def episode(self, n_steps: Optional[int] = None, actions=None, policy: Optional[BasePolicyParams] = None,
+                record_obs=False, record_reward=False, record_actions=False, traj_obs=None, traj_reward=None,
+                traj_actions=None, obs0_out=None, write_state=True):
+        """reset() + rollout(n_steps) fused in one launch (sn_episode): the loaded episode is played
+        from period 0 with the state kept on-chip.  Returns the same dict as rollout() plus obs0."""
+        if n_steps is None:
+            n_steps = self.T
+        if (actions is None) == (policy is None):
+            raise ValueError("give exactly one of actions= or policy=")
+        n, dev = self.n_envs, self.device
+        if actions is not None:
+            a = self._check_actions(actions, lead=(n_steps,))
+            kind, pol = _lib.SN_POLICY_ACTIONS, None
+        else:
+            if policy.n_cols != self.n_agents:
+                raise ValueError(f"policy has {policy.n_cols} targets, env has {self.n_agents} action columns")
+            a, kind, pol = None, _lib.SN_POLICY_BASE_STOCK, C.byref(policy.c)
+        if record_obs and traj_obs is None:
+            traj_obs = torch.empty((n_steps, n, self.obs_dim), dtype=torch.float32, device=dev)
+        if record_reward and traj_reward is None:
+            traj_reward = torch.empty((n_steps, n), dtype=torch.float32, device=dev)
+        if record_actions and traj_actions is None:
+            traj_actions = torch.empty((n_steps, n, self.n_agents), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.sn_episode(
+            C.byref(self._c_spec), self.dtype_code, n, self.ld, n_steps, _ptr(self.init), _ptr(self.demand), kind,
+            _ptr(a), pol, _ptr(obs0_out), _ptr(traj_obs), _ptr(traj_reward), _ptr(traj_actions), _ptr(self.obs),
+            _ptr(self.state) if write_state else None, _ptr(self.ep_return),
+            _ptr(self.stats) if self.track_stats else None, self._stream()))
+        self.period = n_steps
+        self.terminal = self.period >= self.T
+        return dict(obs=self.obs, obs0=obs0_out, traj_obs=traj_obs, traj_reward=traj_reward,
+                    traj_actions=traj_actions, done=self.terminal)
+
     # ------------------------------------------------------------------ snapshot
     def get_state(self):
         return dict(state=self.state.clone(), demand=self.demand.clone(), init=self.init.clone(),

@@ -1,0 +1,112 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/supplynet.h
+declares; struct layouts of the ctypes binding match the header as compiled by gcc; host-only
+entry points (validation) behave; nothing here launches a kernel."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+HDR = os.path.join(ROOT, "include", "supplynet.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from multi_echelon_drl_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        subprocess.run(["make", "-C", os.path.dirname(_lib.LIB_PATH)], check=True)
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from multi_echelon_drl_b200 import _lib
+    text = open(HDR).read()
+    declared = set(re.findall(r"\b(sn_[a-z0-9_]+)\s*\(", text))
+    assert declared >= {"sn_abi_version", "sn_last_error", "sn_obs_dim", "sn_spec_validate", "sn_reset", "sn_step",
+                        "sn_observe", "sn_heuristic", "sn_rollout"}
+    for name in declared:
+        assert hasattr(lib, name), f"libsupplynet.so does not export {name}"
+    assert set(_lib.SIGNATURES) == declared, "ctypes binding and header disagree on the entry points"
+    assert lib.sn_abi_version() == 1
+
+
+def test_struct_layout_matches_header(tmp_path):
+    from multi_echelon_drl_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "supplynet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(sn_spec),offsetof(sn_spec,agents),offsetof(sn_spec,holding_cost),offsetof(sn_spec,dpa_ub),'
+                   'sizeof(sn_policy),offsetof(sn_policy,rule),offsetof(sn_policy,lb));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    S, P = _lib.SnSpec, _lib.SnPolicy
+    assert got == [C.sizeof(S), S.agents.offset, S.holding_cost.offset, S.dpa_ub.offset, C.sizeof(P), P.rule.offset,
+                   P.lb.offset]
+
+
+def test_spec_validation_and_error_mapping(lib):
+    from multi_echelon_drl_b200 import _lib, uniform_spec
+    spec = uniform_spec(["retailer", "wholesaler", "distributor", "manufacturer"], True)
+    c = spec.to_c()
+    for dt in (_lib.SN_I32, _lib.SN_F32, _lib.SN_F64):
+        assert lib.sn_spec_validate(C.byref(c), dt) == 0
+    assert lib.sn_obs_dim(C.byref(c)) == 28
+    c2 = uniform_spec(["wholesaler"], False).to_c()
+    assert lib.sn_obs_dim(C.byref(c2)) == 7
+    # non-contiguous agent set: the reference crashes at supplynetwork.py:199; we reject up front
+    c2.n_agents, c2.agents[0], c2.agents[1] = 2, 0, 2
+    assert lib.sn_spec_validate(C.byref(c2), _lib.SN_I32) == _lib.SN_ERR_INVALID
+    with pytest.raises(ValueError, match="contiguous"):
+        _lib.check(lib.sn_spec_validate(C.byref(c2), _lib.SN_I32))
+    # unsupported topology
+    c3 = spec.to_c()
+    c3.info_leadtime[0] = 3
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.sn_spec_validate(C.byref(c3), _lib.SN_I32))
+    # fractional constants with the integer simulator -> TypeError
+    c4 = spec.to_c()
+    c4.coplayer_target[1] = 19.5
+    with pytest.raises(TypeError):
+        _lib.check(lib.sn_spec_validate(C.byref(c4), _lib.SN_I32))
+    assert lib.sn_spec_validate(C.byref(c4), _lib.SN_F32) == 0
+    assert lib.sn_spec_validate(None, _lib.SN_I32) == _lib.SN_ERR_INVALID
+    assert lib.sn_spec_validate(C.byref(c), 7) == _lib.SN_ERR_INVALID
+
+
+def test_argument_checks_precede_any_launch(lib):
+    """Bad arguments are rejected on the host (no GPU needed to see the error)."""
+    from multi_echelon_drl_b200 import _lib, uniform_spec
+    c = uniform_spec(None, True).to_c()
+    rc = lib.sn_step(C.byref(c), _lib.SN_I32, 8, 8, 100, None, None, None, None, None, None, None, None, None, None)
+    assert rc == _lib.SN_ERR_TERMINAL and b"terminal" in lib.sn_last_error()      # envs.py:88-89
+    assert lib.sn_step(C.byref(c), _lib.SN_I32, 8, 6, 0, None, None, None, None, None, None, None, None, None, None) == _lib.SN_ERR_INVALID
+    assert lib.sn_rollout(C.byref(c), _lib.SN_I32, 8, 8, 90, 20, None, None, 0, None, None, None, None, None, None, None,
+                          None, None) == _lib.SN_ERR_INVALID
+    assert lib.sn_reset(C.byref(c), _lib.SN_I32, 0, 0, None, None, None, None, None) == _lib.SN_ERR_INVALID
+
+
+def test_product_fails_loudly_without_cuda():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, BatchedSupplyNetwork, heuristic_actions
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchedSupplyNetwork(uniform_spec(), 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        heuristic_actions(BasePolicyParams([19, 20, 20, 14]), torch.zeros(2, 28))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through oracle/ (checked on the source text)."""
+    pkg = os.path.join(ROOT, "multi_echelon_drl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "beergame_c" not in txt and "beergame_np" not in txt, f

@@ -234,3 +234,32 @@ def test_full_size_config2_properties():
     ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init[:m], demand[:m], acts[:, :m])
     assert np.array_equal(out["traj_obs"][:, :m].cpu().numpy(), ref["obs"])
     assert np.array_equal(ret_fused[:m].cpu().numpy(), ref["rew"].sum(0))
+
+
+@pytest.mark.parametrize("scenario,agents,glob,rule", [
+    ("uniform", (0, 1, 2, 3), True, "a"), ("normal", (1, 2, 3), False, "d+a"), ("uniform", (2,), True, "a"),
+])
+def test_episode_fused_reset_rollout_vs_oracle(scenario, agents, glob, rule):
+    """sn_episode: in-kernel reset + rollout in one launch (state never in HBM) == reset + steps."""
+    n, T = 3001, 100
+    init, demand = _seeded_batch(scenario, n, T, 17)
+    hi = 17 if scenario == "uniform" else 21
+    acts = np.random.RandomState(8).randint(0, hi, (T, n, len(agents)))
+    ref = oracle_rollout(scenario, agents, glob, rule, T, init, demand, acts)
+    sim = _make(scenario, agents, glob, rule, T, n, "int32")
+    sim.load_episode(init, demand)
+    obs0 = torch.zeros((n, sim.obs_dim), device="cuda")
+    sim.ep_return.fill_(123.0)                                  # must be overwritten, not accumulated
+    out = sim.episode(T, actions=torch.as_tensor(acts), record_obs=True, record_reward=True, obs0_out=obs0)
+    assert np.array_equal(obs0.cpu().numpy(), ref["obs0"])
+    assert np.array_equal(out["traj_obs"].cpu().numpy(), ref["obs"])
+    assert np.array_equal(out["traj_reward"].cpu().numpy(), ref["rew"].astype(np.float32))
+    assert np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))
+    assert np.array_equal(out["obs"].cpu().numpy(), ref["obs"][-1]) and out["done"]
+    # partial episode with state write-back, continued by single steps
+    out = sim.episode(60, actions=torch.as_tensor(acts[:60]))
+    assert not out["done"] and sim.period == 60
+    for t in range(60, T):
+        obs, _, done = sim.step(torch.as_tensor(acts[t]))
+        assert np.array_equal(obs.cpu().numpy(), ref["obs"][t])
+    assert done and np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))

@@ -1,0 +1,166 @@
+"""GPU tests of the VecEnv surface (SB3 duck type), registry ids, d+a wrapper and the heuristic
+class, checked against the numpy oracle on per-env seeded streams (the reference's RNG order)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import oracle_rollout  # noqa: E402
+
+
+def _oracle_episode(spec, scenario, seeds_streams, acts, rule="a"):
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs_from_streams
+    init, demand = seeded_episode_inputs_from_streams(spec, seeds_streams)
+    return oracle_rollout(scenario, spec.agents, spec.global_observable, rule, spec.max_episode_steps, init, demand, acts)
+
+
+def test_vecenv_autoreset_matches_oracle_over_three_episodes():
+    """numpy_seeded source: env i == reference env seeded with seed+i and reset repeatedly.
+    Checks obs/reward every step, terminal_observation, Monitor-style episode info, auto-reset obs."""
+    from multi_echelon_drl_b200 import register_envs as R
+    n, T, seed = 37, 100, 500
+    env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="int32", seed=seed,
+                 episode_source="numpy_seeded")
+    assert env.num_envs == n and env.observation_space.shape == (28,) and env.action_space.shape == (4,)
+    assert float(env.action_space.high[0]) == 16.0
+    streams = [np.random.RandomState(seed + i) for i in range(n)]
+    rs = np.random.RandomState(0)
+    obs = env.reset()
+    for ep in range(3):
+        acts = rs.randint(0, 17, (T, n, 4))
+        ref = _oracle_episode(env.spec, "uniform", streams, acts)
+        assert np.array_equal(obs.cpu().numpy(), ref["obs0"]), ep
+        for t in range(T):
+            obs, rew, dones, infos = env.step(torch.as_tensor(acts[t]).cuda())
+            assert np.array_equal(rew.cpu().numpy(), ref["rew"][t].astype(np.float32))
+            if t < T - 1:
+                assert not dones.any() and infos[0] == {} and len(infos) == n
+                assert np.array_equal(obs.cpu().numpy(), ref["obs"][t])
+            else:
+                assert dones.all()
+                assert np.array_equal(infos.terminal_observation.cpu().numpy(), ref["obs"][t])
+                i = 5
+                assert infos[i]["episode"]["r"] == round(float(ref["rew"][:, i].sum()), 6)
+                assert infos[i]["episode"]["l"] == T and infos[i]["TimeLimit.truncated"] is False
+                assert np.array_equal(infos[i]["terminal_observation"].cpu().numpy(), ref["obs"][t][i])
+                # obs is already the first observation of the next episode (DummyVecEnv auto-reset)
+    assert env.episodes_done == 3 * n
+
+
+def test_numpy_output_mode_and_decentralized_roles():
+    """output='numpy' (pinned host staging, what SB3 consumes) on a decentralized Retailer env with
+    local observation (config 1 semantics: BeerGameNormalRetailer-v0)."""
+    from multi_echelon_drl_b200 import register_envs as R
+    n, T, seed = 64, 100, 9
+    env = R.make("BeerGameNormalRetailer-v0", n_envs=n, dtype="int32", seed=seed, episode_source="numpy_seeded",
+                 output="numpy")
+    assert env.observation_space.shape == (7,) and env.action_space.shape == (1,) and float(env.action_space.high[0]) == 20.0
+    streams = [np.random.RandomState(seed + i) for i in range(n)]
+    acts = np.random.RandomState(1).randint(0, 21, (T, n, 1))
+    ref = _oracle_episode(env.spec, "normal", streams, acts)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.dtype == np.float32 and np.array_equal(obs, ref["obs0"])
+    for t in range(T):
+        obs, rew, dones, infos = env.step(acts[t])
+        assert isinstance(rew, np.ndarray) and np.array_equal(rew, ref["rew"][t].astype(np.float32))
+        if t < T - 1:
+            assert np.array_equal(obs, ref["obs"][t]) and not dones.any()
+    assert dones.all() and np.array_equal(infos.terminal_observation, ref["obs"][-1])
+    assert np.allclose(infos.episode_return, ref["rew"].sum(0))
+
+
+def test_dplusa_registry_id_and_wrapper():
+    """BeerGameUniformMultiFacilityDPlusA-v0 = wrap_action_d_plus_a(env, -8, 0, 16) (register_envs.py:8-15)."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.envs import make_beer_game_uniform_multi_facility
+    from multi_echelon_drl_b200.utils.wrappers import wrap_action_d_plus_a
+    n, T, seed = 33, 100, 77
+    env = R.make("BeerGameUniformMultiFacilityDPlusA-v0", n_envs=n, dtype="int32", seed=seed, episode_source="numpy_seeded")
+    assert env.spec.rule == "d+a" and env.spec.dpa_offset == -8 and env.observation_space.shape == (28,)
+    env2 = wrap_action_d_plus_a(make_beer_game_uniform_multi_facility(
+        agent_managed_facilities=["retailer", "wholesaler", "distributor", "manufacturer"], box_action_space=True,
+        random_init=True, n_envs=n, dtype="int32", seed=seed, episode_source="numpy_seeded"), offset=-8, lb=0, ub=16)
+    streams = [np.random.RandomState(seed + i) for i in range(n)]
+    acts = np.random.RandomState(3).randint(0, 17, (T, n, 4))
+    ref = _oracle_episode(env.spec, "uniform", streams, acts, rule="d+a")
+    o1, o2 = env.reset(), env2.reset()
+    assert torch.equal(o1, o2)
+    for t in range(T - 1):
+        o1, r1, _, _ = env.step(torch.as_tensor(acts[t]))
+        o2, r2, _, _ = env2.step(torch.as_tensor(acts[t]))
+        assert np.array_equal(o1.cpu().numpy(), ref["obs"][t]) and torch.equal(o1, o2) and torch.equal(r1, r2)
+
+
+def test_all_registry_ids_construct_and_step():
+    from multi_echelon_drl_b200 import register_envs as R
+    for env_id in R.registered_ids():
+        env = R.make(env_id, n_envs=5, seed=1)
+        obs = env.reset()
+        full = "FullInfo" in env_id
+        multi = "MultiFacility" in env_id
+        assert obs.shape == (5, 28 if (full or multi) else 7), env_id
+        na = 4 if multi else 1
+        a = torch.full((5, na), 4.0, device="cuda")
+        obs, rew, dones, infos = env.step(a)
+        assert obs.shape[0] == 5 and rew.shape == (5,) and dones.shape == (5,) and len(infos) == 5
+        assert torch.isfinite(obs).all() and (rew <= 0).all()
+    # the one genuinely Discrete id (register_envs.py:27-33); the others keep Box (Q3)
+    assert type(R.make("BeerGameUniformRetailerDiscreteDPlusA-v0", n_envs=2).action_space).__name__ == "Discrete"
+    assert type(R.make("BeerGameUniformRetailerDiscrete-v0", n_envs=2).action_space).__name__ == "Box"
+
+
+def test_device_episode_source_distributions_and_determinism():
+    from multi_echelon_drl_b200 import register_envs as R
+    e1 = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=4096, seed=3)
+    e2 = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=4096, seed=3)
+    assert torch.equal(e1.reset(), e2.reset())
+    d = e1.sim.demand[:, :4096]
+    assert d.min() == 0 and d.max() == 8 and abs(d.float().mean().item() - 4.0) < 0.05
+    init = e1.sim.init[:, :4096]
+    assert init[:4].min() == 0 and init[:4].max() == 24 and init[4:].max() == 8
+    e3 = R.make("BeerGameNormalRetailer-v0", n_envs=4096, seed=3)
+    e3.reset()
+    d = e3.sim.demand[:, :4096]
+    assert abs(d.float().mean().item() - 10.0) < 0.1 and abs(d.float().std().item() - 2.0) < 0.1 and (d == d.round()).all()
+
+
+def test_base_stock_policy_class_on_device_and_hge_contract():
+    """HgeTD3.predict's heuristic branch (hge.py:157-167) calls heuristic.get_order_quantity(original_obs):
+    per-env actions on device; driving the env with them equals the in-kernel policy rollout."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    idx = {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1, "latest_demand": 2}
+    bsp = BaseStockPolicy([19, 20, 20, 14], idx, 7, 0, 16, "a")
+    n = 300
+    env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="int32", seed=11, episode_source="numpy_bulk")
+    obs = env.reset()
+    snap = env.sim.get_state()
+    total = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(100):
+        a = bsp.get_order_quantity(env.get_original_obs())
+        assert a.shape == (n, 4) and a.is_cuda
+        if t < 99:
+            obs, rew, _, _ = env.step(a)
+            total += rew.double()
+    env.sim.set_state(snap)
+    env.sim.rollout(99, policy=BasePolicyParams([19, 20, 20, 14], 0, 16, "a"))
+    assert torch.equal(env.sim.ep_return, total)
+    out = bsp.get_order_quantity(obs.cpu().numpy())          # numpy in -> numpy float64 out, like the reference
+    assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (n, 4)
+
+
+def test_float_vecenv_accepts_fractional_actions_and_int_rejects_them():
+    from multi_echelon_drl_b200 import register_envs as R
+    envf = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=8, dtype="float32", seed=1)
+    envf.reset()
+    obs, rew, _, _ = envf.step(torch.full((8, 4), 3.25, device="cuda"))
+    assert (obs[:, 3] == 3.25).all()                     # newest pipeline slot of the retailer = its order
+    envi = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=8, dtype="int32", seed=1)
+    envi.reset()
+    with pytest.raises(TypeError):
+        envi.step(torch.full((8, 4), 3.25, device="cuda"))
+    # negative orders are clamped to 0 like network_components.py:368-374 (no warning spam on device)
+    obs, _, _, _ = envi.step(torch.full((8, 4), -5, device="cuda"))
+    assert (obs[:, 3] == 0).all()

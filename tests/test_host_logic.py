@@ -1,0 +1,148 @@
+"""Host-side logic that needs no GPU: scenario constants, seeded streams (RNG draw order of the
+reference), Demand patterns (the reference's tests/test_demands.py, adapted), registry ids, the
+lazy info list, the dict path of the heuristic."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+def test_scenario_constants_match_reference_factories():
+    from multi_echelon_drl_b200 import classic_spec, normal_spec, uniform_spec
+    u = uniform_spec()
+    assert u.agents == (0, 1, 2, 3) and u.holding_cost == (0.5,) * 4 and u.backorder_cost == (1.0,) * 4
+    assert u.coplayer_target == (19, 20, 20, 14) and (u.action_low, u.action_high) == (0, 16)       # envs.py:319-350,397-400
+    assert u.init_inventory == (0, 25) and u.init_pipeline == (0, 9) and u.random_init              # envs.py:325-328
+    nrm = normal_spec()
+    assert nrm.agents == (0,) and nrm.holding_cost == (1.0, 0.75, 0.5, 0.25) and nrm.backorder_cost == (10.0, 0, 0, 0)
+    assert nrm.coplayer_target == (48, 43, 41, 30) and nrm.action_high == 20 and not nrm.random_init  # envs.py:163-286
+    assert nrm.coplayer_ub == 16                                                                      # Q6
+    c = classic_spec()
+    assert c.coplayer_target == (32, 32, 32, 24) and c.max_episode_steps == 35 and not c.random_init
+    assert uniform_spec(["wholesaler"], False).obs_dim == 7 and uniform_spec(["wholesaler"], True).obs_dim == 28
+    assert uniform_spec(["distributor", "wholesaler"]).agents == (2, 1)                                # caller order kept (Q14)
+    with pytest.raises(ValueError):
+        uniform_spec(["retailer", "distributor"])                                                      # Q13
+    with pytest.raises(ValueError):
+        uniform_spec(["retailer", "retailer"])
+    with pytest.raises(ValueError):
+        uniform_spec(["nobody"])
+
+
+def test_seeded_streams_replay_reference_draw_order():
+    """np.random.seed(s); env.reset() in the reference == seeded_episode_inputs(spec, [s])."""
+    from multi_echelon_drl_b200 import normal_spec, uniform_spec
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs
+    z = np.load(f"{GOLDEN}/seeded.npz")
+    seeds = (0, 1, 2, 12345, 2**31 - 1)
+    for name, spec in (("uniform", uniform_spec()), ("normal", normal_spec(random_init=True))):
+        init, demand = seeded_episode_inputs(spec, seeds)
+        for i, s in enumerate(seeds):
+            assert np.array_equal(init[i], z[f"{name}_{s}_init"]), (name, s)
+            assert np.array_equal(demand[i], z[f"{name}_{s}_demand"]), (name, s)
+    # fixed-init variants draw only the demand
+    init, demand = seeded_episode_inputs(uniform_spec(random_init=False), [5])
+    assert init[0].tolist() == [12] * 4 + [4] * 15
+    assert np.array_equal(demand[0], np.random.RandomState(5).randint(0, 9, 103))
+    init, _ = seeded_episode_inputs(normal_spec(), [5])
+    assert init[0].tolist() == [10] * 4 + [10, 0, 10, 0, 10, 0, 10] + [10, 0] * 4
+
+
+def test_persistent_streams_continue_across_resets():
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs_from_streams
+    spec = uniform_spec()
+    streams = [np.random.RandomState(3)]
+    a = seeded_episode_inputs_from_streams(spec, streams)
+    b = seeded_episode_inputs_from_streams(spec, streams)
+    rs = np.random.RandomState(3)
+    n_draws = 122                                  # 4 inv + 103 demand + 8 ship + 7 SO
+    first = [rs.randint(0, 25)] + list(rs.randint(0, 9, 103)) + [rs.randint(0, 25) for _ in range(3)] + \
+            [rs.randint(0, 9) for _ in range(15)]
+    assert len(first) == n_draws and first[0] == a[0][0, 0] and list(a[1][0]) == first[1:104]
+    assert rs.randint(0, 25) == b[0][0, 0]         # second reset continues the same stream
+
+
+def test_demand_patterns_like_reference_tests():
+    """tests/test_demands.py of the reference: uniform hits both bounds inclusively; normal(10,4)
+    moments and clipping at 0; classic pattern; list passthrough; argument validation."""
+    from multi_echelon_drl_b200.utils.demands import Demand
+    rs = np.random.RandomState(0)
+    for lo, hi in ((0, 2), (0, 8)):
+        d = Demand("uniform", low=lo, high=hi, size=100).sample(4, rs)
+        assert d.shape == (4, 103) and d.min() == lo and d.max() == hi
+    d = Demand("normal", mean=10, sd=4, size=100000).sample(1, rs)[0]
+    assert abs(d.mean() - 10) < 0.1 and abs(d.std() - 4) < 0.04 and d.min() == 0
+    assert Demand("classic_beer_game", size=35).sample(2, rs)[1].tolist() == [4] * 4 + [8] * 34
+    assert Demand([1, 2, 3]).sample(2, rs).tolist() == [[1, 2, 3]] * 2
+    with pytest.raises(ValueError):
+        Demand("uniform")
+    with pytest.raises(ValueError):
+        Demand("normal", mean=1)
+    with pytest.raises(ValueError):
+        Demand("poisson")
+    # one stream, same draws as the reference's np.random calls
+    a = Demand("uniform", low=0, high=8, size=100).draw(np.random.RandomState(1))
+    assert np.array_equal(a, np.random.RandomState(1).randint(0, 9, 103))
+    b = Demand("normal", mean=10, sd=2, size=100).draw(np.random.RandomState(1))
+    assert np.array_equal(b, np.round(np.maximum(10 + 2 * np.random.RandomState(1).randn(103), 0)).astype(int))
+
+
+def test_registry_has_the_38_reference_ids():
+    from multi_echelon_drl_b200 import register_envs as R
+    ids = R.register_envs()
+    assert len(ids) == 38
+    for kind in ("Uniform", "Normal"):
+        assert f"BeerGame{kind}MultiFacilityFullInfo-v0" in ids and f"BeerGame{kind}MultiFacilityDPlusA-v0" in ids
+        for role in ("Retailer", "Wholesaler", "Distributor", "Manufacturer"):
+            for suffix in ("", "Discrete", "FullInfo", "DiscreteFullInfo"):
+                assert f"BeerGame{kind}{role}{suffix}-v0" in ids
+    assert "BeerGameUniformRetailerDPlusA-v0" in ids and "BeerGameUniformRetailerDiscreteDPlusA-v0" in ids
+    with pytest.raises(KeyError):
+        R.make("BeerGameNope-v0")
+
+
+def test_lazy_infos_behaves_like_a_list_of_dicts():
+    from multi_echelon_drl_b200.vec_env import LazyInfos
+    empty = LazyInfos(3)
+    assert len(empty) == 3 and empty[0] == {} and empty[-1] == {} and list(empty) == [{}, {}, {}]
+    with pytest.raises(IndexError):
+        empty[3]
+    obs = np.arange(6.0).reshape(3, 2)
+    done = LazyInfos(3, obs, np.array([-1.0, -2.5, -3.0]), 100, 1.25)
+    assert done[1]["episode"] == {"r": -2.5, "l": 100, "t": 1.25}
+    assert np.array_equal(done[2]["terminal_observation"], obs[2]) and done[0]["TimeLimit.truncated"] is False
+    assert len(done[0:2]) == 2
+
+
+def test_heuristic_dict_path_matches_reference_golden():
+    pytest.importorskip("torch")
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    z = np.load(f"{GOLDEN}/heuristic.npz")
+    keys = ["on_hand", "unfilled_demand", "latest_demand"] + [f"unreceived_pipeline_{i}" for i in range(4)]
+    obs = z["uniform_obs"]
+    for rule in ("a", "d+a"):
+        for f, tg in enumerate([19, 20, 20, 14]):
+            pol = BaseStockPolicy([tg], rule=rule)
+            for i in (0, 5, 40, 63):
+                st = {k: obs[i, 7 * f + j] for j, k in enumerate(keys)}
+                got = pol.get_order_quantity({"x": st})
+                assert got.shape == (1, 1)
+                np.testing.assert_allclose(got.item(), z[f"uniform_{rule}_dict"][i, f], rtol=1e-6, atol=1e-6)
+    with pytest.raises(TypeError):
+        BaseStockPolicy([1]).get_order_quantity(3)
+    with pytest.raises(NotImplementedError):
+        BaseStockPolicy([1], array_index={"on_hand": 1, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 0,
+                                          "latest_demand": 2})
+
+
+def test_shard_ranges_partition_the_batch():
+    from multi_echelon_drl_b200.distributed import shard_range
+    for n, w in ((1048576, 8), (65536, 4), (10, 3), (7, 8), (1, 1)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
