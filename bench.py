@@ -80,6 +80,16 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def ncu_traffic(n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (config-2 size only)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if n != N_ENVS or not os.path.isfile(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)["k_rollout_config2"]
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 def make_inputs(n, seed):
     from multi_echelon_drl_b200 import uniform_spec
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
@@ -178,7 +188,8 @@ def run_native(args):
     d_actions = h_actions.to(dev)
     traj_obs = torch.empty((T, n, 28), dtype=torch.float32, device=dev)
     traj_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
-    stats_sum = torch.zeros(16, dtype=torch.float64, device=dev)
+    stats_bufs = [torch.zeros(16, dtype=torch.float64, device=dev) for _ in range(2)]
+    pending, step_no = [], [0]
 
     def barrier():
         if world > 1:
@@ -195,16 +206,19 @@ def run_native(args):
         if record:
             e1.record()
             k_events.append((e0, e1))
-        if world > 1:                       # the path's only collective: episode statistics
-            stats_sum.copy_(sim.stats)
-            dist.all_reduce(stats_sum)
+        if world > 1:
+            # the path's only collective: episode statistics (16 doubles).  Issued asynchronously on
+            # NCCL's stream with two alternating buffers so that it overlaps the next episode's kernel.
+            step_no[0] += 1
+            buf = stats_bufs[step_no[0] % 2]
+            while len(pending) >= 2:
+                pending.pop(0).wait()
+            buf.copy_(sim.stats)
+            pending.append(dist.all_reduce(buf, async_op=True))
 
     def e2e_step():
-        sim.load_episode(h_init, h_demand)                    # H2D init + demand
-        sim.episode(T, actions=h_actions, traj_obs=traj_obs, traj_reward=traj_rew, write_state=False)   # H2D actions
-        h_traj_obs.copy_(traj_obs, non_blocking=True)         # D2H trajectory
-        h_traj_rew.copy_(traj_rew, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # host buffers in, host trajectory out; H2D / kernels / D2H pipelined over spans of periods
+        sim.episode_host(h_init, h_demand, h_actions, h_traj_obs, h_traj_rew, chunks=args.e2e_chunks)
 
     def timed(fn, steps, warmup, **kw):
         for _ in range(warmup):
@@ -214,6 +228,8 @@ def run_native(args):
         s.record()
         for _ in range(steps):
             fn(**kw) if kw else fn()
+        while pending:
+            pending.pop(0).wait()
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
@@ -270,10 +286,10 @@ def run_native(args):
                        "parallelism": f"env-sharded x{world}, stats all-reduce only"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "BatchedSupplyNetwork.load_episode + episode with pinned host tensors + trajectory D2H"},
+                    "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic(n), "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -368,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default: BASELINE config 2)")
+    ap.add_argument("--e2e-chunks", type=int, default=5, help="period spans of the pipelined host path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
     args = ap.parse_args()

@@ -221,6 +221,56 @@ class BatchedSupplyNetwork:
         return dict(obs=self.obs, obs0=obs0_out, traj_obs=traj_obs, traj_reward=traj_reward,
                     traj_actions=traj_actions, done=self.terminal)
 
+    def episode_host(self, h_init, h_demand, h_actions, h_traj_obs, h_traj_reward, chunks: int = 4):
+        """The reference-shaped call with HOST buffers: numpy/pinned-torch inputs in, full trajectory out
+        on the host (what `for t: obs, r, d, _ = venv.step(a[t])` hands back), pipelined so that PCIe
+        runs in both directions at once: the episode is cut into `chunks` spans of periods; actions of
+        span c+1 travel host->device and the trajectory of span c-1 travels device->host while span c
+        is computed (sn_episode for the first span, sn_rollout for the others).  Synchronises before
+        returning.  h_actions [T, n, n_agents] / h_traj_obs [T, n, obs_dim] f32 / h_traj_reward [T, n] f32
+        must be pinned torch tensors for the copies to overlap."""
+        T, n, dev = self.T, self.n_envs, self.device
+        h_actions = torch.as_tensor(h_actions)
+        if tuple(h_actions.shape) != (T, n, self.n_agents):
+            raise ValueError(f"h_actions must have shape {(T, n, self.n_agents)}")
+        if h_actions.dtype != self.tdtype:
+            raise TypeError(f"h_actions must have dtype {self.tdtype} for the pipelined host path")
+        if not hasattr(self, "_pipe"):
+            self._pipe = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
+                              act=torch.empty((T, n, self.n_agents), dtype=self.tdtype, device=dev),
+                              obs=torch.empty((T, n, self.obs_dim), dtype=torch.float32, device=dev),
+                              rew=torch.empty((T, n), dtype=torch.float32, device=dev))
+        pp = self._pipe
+        main = torch.cuda.current_stream(dev)
+        chunks = max(1, min(int(chunks), T))
+        bounds = [(c * T) // chunks for c in range(chunks + 1)]
+        pp["h2d"].wait_stream(main)
+        ev_in = []
+        with torch.cuda.stream(pp["h2d"]):
+            for c in range(chunks):
+                t0, t1 = bounds[c], bounds[c + 1]
+                pp["act"][t0:t1].copy_(h_actions[t0:t1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(pp["h2d"])
+                ev_in.append(ev)
+        self.load_episode(h_init, h_demand)                  # H2D init + demand on the main stream
+        for c in range(chunks):
+            t0, t1 = bounds[c], bounds[c + 1]
+            main.wait_event(ev_in[c])
+            if c == 0:
+                self.episode(t1, actions=pp["act"][:t1], traj_obs=pp["obs"][:t1], traj_reward=pp["rew"][:t1])
+            else:
+                self.rollout(t1 - t0, actions=pp["act"][t0:t1], traj_obs=pp["obs"][t0:t1], traj_reward=pp["rew"][t0:t1])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            pp["d2h"].wait_event(ev)
+            with torch.cuda.stream(pp["d2h"]):
+                h_traj_obs[t0:t1].copy_(pp["obs"][t0:t1], non_blocking=True)
+                h_traj_reward[t0:t1].copy_(pp["rew"][t0:t1], non_blocking=True)
+        main.wait_stream(pp["d2h"])
+        main.synchronize()
+        return h_traj_obs, h_traj_reward
+
     # ------------------------------------------------------------------ snapshot
     def get_state(self):
         return dict(state=self.state.clone(), demand=self.demand.clone(), init=self.init.clone(),

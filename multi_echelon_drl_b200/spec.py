@@ -141,3 +141,20 @@ def classic_spec(agent_managed_facilities=None, max_episode_steps=35, demand_pat
         max_episode_steps=max_episode_steps, action_low=0, action_high=16, demand_pattern=demand_pattern,
         demand_params=params, random_init=False, fixed_inventory=12, fixed_shipments=(4, 4),
         fixed_sales_orders=(4, 4))
+
+
+def specs_from_config(network_config: dict, agent_managed_facilities=None, global_observable=False,
+                      max_episode_steps=100, coplayer_target=(19, 20, 20, 14), random_init=True):
+    """ScenarioSpec per item from a network description (network_configs/*.yaml schema; what the
+    reference's `supplynetwork.from_dict` was meant to do, supplynetwork.py:345-397).  Multi-item
+    descriptions (`items:`) give one spec per item: items are independent copies of the chain with
+    their own cost vectors (the reference defines no item coupling)."""
+    from .utils.graph import chain_from_config
+    seq, info, ship, hold, back = chain_from_config(network_config)
+    if tuple(seq) != NODE_NAMES or info != INFO_LEADTIME or ship != SHIP_LEADTIME:
+        raise NotImplementedError(f"kernels implement the chain {NODE_NAMES} with lead times {INFO_LEADTIME}/"
+                                  f"{SHIP_LEADTIME}; got {seq} {info}/{ship}")
+    base = uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    return [replace(base, name=f"config-item{i}", holding_cost=tuple(float(x) for x in hold[i]),
+                    backorder_cost=tuple(float(x) for x in back[i]), coplayer_target=tuple(coplayer_target))
+            for i in range(len(hold))]

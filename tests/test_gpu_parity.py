@@ -263,3 +263,23 @@ def test_episode_fused_reset_rollout_vs_oracle(scenario, agents, glob, rule):
         obs, _, done = sim.step(torch.as_tensor(acts[t]))
         assert np.array_equal(obs.cpu().numpy(), ref["obs"][t])
     assert done and np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))
+
+
+@pytest.mark.parametrize("chunks", [1, 4, 7])
+def test_episode_host_pipelined_equals_plain(chunks):
+    """The pipelined host-buffer path (H2D / kernels / D2H overlapped over spans of periods) returns
+    exactly the trajectory of the plain path."""
+    n, T = 5000, 100
+    init, demand = _seeded_batch("uniform", n, T, 23)
+    acts = np.random.RandomState(4).randint(0, 17, (T, n, 4)).astype(np.int32)
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts)
+    sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+    h_obs = torch.empty((T, n, 28), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((T, n), dtype=torch.float32).pin_memory()
+    h_act = torch.from_numpy(acts).pin_memory()
+    for _ in range(2):                                      # twice: persistent pipeline buffers are reused
+        h_obs.zero_(); h_rew.zero_()
+        sim.episode_host(torch.from_numpy(init), torch.from_numpy(demand), h_act, h_obs, h_rew, chunks=chunks)
+        assert np.array_equal(h_obs.numpy(), ref["obs"])
+        assert np.array_equal(h_rew.numpy(), ref["rew"].astype(np.float32))
+        assert np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))

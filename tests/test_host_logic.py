@@ -146,3 +146,69 @@ def test_shard_ranges_partition_the_batch():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
+
+
+def test_parse_order_sequence_reference_cases():
+    """The three cases of the reference's tests/test_graph.py:11-49."""
+    from multi_echelon_drl_b200.utils.graph import parse_order_sequence
+    assert parse_order_sequence(
+        ["manufacturer", "distributor", "wholesaler", "retailer"],
+        {"is_external_supplier": ["manufacturer"], "manufacturer": ["distributor"], "distributor": ["wholesaler"],
+         "wholesaler": ["retailer"], "retailer": []}) == ["retailer", "wholesaler", "distributor", "manufacturer"]
+    assert parse_order_sequence(
+        ["1", "2", "3", "4", "5", "6", "7"],
+        {"6": ["4"], "5": ["2", "7"], "4": ["3", "1"], "2": ["1"], "3": [], "1": ["7"], "7": []}) == \
+        ["7", "1", "2", "3", "4", "5", "6"]
+    assert parse_order_sequence(
+        ["1", "2", "3", "4", "5", "6", "7", "8", "9"],
+        {"9": ["3"], "7": ["6", "2"], "3": ["5", "1"], "6": ["1"], "5": [], "1": ["2"], "2": ["4"], "4": ["8"],
+         "8": []}) == ["8", "4", "2", "1", "5", "3", "6", "7", "9"]
+
+
+def test_yaml_configs_lower_to_specs():
+    """tests/test_graph.py:52-63 (5 nodes, 4 arcs, info lead times 2 and 1) + a working loader."""
+    import os
+    from multi_echelon_drl_b200.spec import specs_from_config
+    from multi_echelon_drl_b200.utils.graph import chain_from_config, read_yaml
+    import multi_echelon_drl_b200 as pkg
+    d = os.path.join(os.path.dirname(pkg.__file__), "network_configs")
+    net = read_yaml(os.path.join(d, "beergame.yaml"))
+    assert len(net["nodes"]) == 5 and len(net["arcs"]) == 4
+    assert net["arcs"][0]["info_leadtime"] == 2 and net["arcs"][3]["info_leadtime"] == 1
+    seq, info, ship, hold, back = chain_from_config(net)
+    assert seq == ["retailer", "wholesaler", "distributor", "manufacturer"] and info == (2, 2, 2, 1) and ship == (2,) * 4
+    (spec,) = specs_from_config(net, ["retailer", "wholesaler", "distributor", "manufacturer"], True)
+    assert spec.holding_cost == (0.5,) * 4 and spec.backorder_cost == (1.0,) * 4 and spec.obs_dim == 28
+    multi = specs_from_config(read_yaml(os.path.join(d, "multi_item.yaml")))
+    assert len(multi) == 2 and multi[1].holding_cost == (0.75,) * 4 and multi[0].holding_cost == (0.5,) * 4
+    bad = read_yaml(os.path.join(d, "beergame.yaml"))
+    bad["arcs"][0]["info_leadtime"] = 3
+    with pytest.raises(NotImplementedError):
+        specs_from_config(bad)
+    bad = read_yaml(os.path.join(d, "beergame.yaml"))
+    bad["arcs"].append({"customer": "retailer", "supplier": "distributor", "info_leadtime": 1, "shipment_leadtime": 1})
+    with pytest.raises(NotImplementedError):
+        specs_from_config(bad)
+
+
+def test_hge_rate_schedule_and_single_coin():
+    torch = pytest.importorskip("torch")
+    from multi_echelon_drl_b200.hge import HgeRateSchedule, hge_predict
+    sch = HgeRateSchedule(0.5, 1000)
+    assert sch(0) == 0.5 and abs(sch(50_000) - 0.25) < 1e-12 and sch(100_000) == 0.0 and sch(200_000) == 0.0
+
+    class H:
+        def get_order_quantity(self, o):
+            return torch.full((o.shape[0], 4), 7.0)
+
+    obs = torch.zeros(6, 28)
+    pol = lambda o: torch.zeros(o.shape[0], 4)
+    rng = np.random.RandomState(0)
+    heads = sum(bool(hge_predict(pol, H(), obs, obs, 0.5, rng=rng)[1]) for _ in range(4000))
+    assert abs(heads / 4000 - 0.25) < 0.03                       # probability hge_rate**2 per call (hge.py:157)
+    a, used = hge_predict(pol, H(), obs, obs, 1.0, rng=rng)
+    assert used is True and (a == 7).all()
+    a, used = hge_predict(pol, H(), obs, obs, 1.0, deterministic=True)
+    assert used is False and (a == 0).all()
+    a, mask = hge_predict(pol, H(), obs, obs, 1.0, per_env=True)
+    assert mask.all() and (a == 7).all()
