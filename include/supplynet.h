@@ -173,6 +173,24 @@ int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
                    float* traj_actions, float* obs, void* state, double* ep_return, double* stats,
                    void* stream);
 
+/* ---- device-side VecNormalize (stable_baselines3 VecNormalize as used at train_td3.py:100-101;
+ * SB3 is third-party and not vendored: algorithm per SURVEY Appendix D, parity unpinned) ----------
+ * Running statistics are float64 vectors owned by the caller:
+ *   obs_rms = mean[obs_dim], var[obs_dim], count      ret_rms = mean, var, count
+ * (initialise mean 0, var 1, count 1e-4 like RunningMeanStd).  `scratch` is 2*obs_dim+2 doubles.
+ * sn_vecnorm_update: RunningMeanStd.update(obs) into obs_rms_out; if `reward` is given also
+ *   returns <- returns*gamma + reward and RunningMeanStd.update(returns) into ret_rms_out
+ *   (in/out buffers must differ; the caller swaps them).
+ * sn_vecnorm_apply: obs_out <- clip((obs-mean)/sqrt(var+eps), +-clip_obs);
+ *   reward_out <- clip(reward/sqrt(ret_var+eps), +-clip_reward); returns <- 0 if reset_returns.
+ *   Either the obs or the reward part may be skipped by passing NULL. */
+int32_t sn_vecnorm_update(int64_t n_envs, int32_t obs_dim, const float* obs, const float* reward, double gamma,
+                          double* returns, const double* obs_rms_in, double* obs_rms_out,
+                          const double* ret_rms_in, double* ret_rms_out, double* scratch, void* stream);
+int32_t sn_vecnorm_apply(int64_t n_envs, int32_t obs_dim, const float* obs, float* obs_out, const float* reward,
+                         float* reward_out, const double* obs_rms, const double* ret_rms, float clip_obs,
+                         float clip_reward, double epsilon, int32_t reset_returns, double* returns, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ SIGNATURES = {
     "sn_heuristic": (_I32, [C.POINTER(SnPolicy), _I32, _I64, _P, _P, _P]),
     "sn_rollout": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P]),
+    "sn_vecnorm_update": (_I32, [_I64, _I32, _P, _P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_vecnorm_apply": (_I32, [_I64, _I32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_double, _I32, _P, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -1,0 +1,187 @@
+"""Device-side VecNormalize for SupplyNetVecEnv.
+
+Counterpart of `VecNormalize(make_vec_env(...), clip_obs=100, clip_reward=1000)` in the reference's
+trainers (train_td3.py:100-101, train_a2c.py:86-87, train_dqn.py:87-88) with the running statistics,
+the discounted-return accumulators and the normalisation itself on the GPU (`sn_vecnorm_update`,
+`sn_vecnorm_apply`), so observations and rewards never leave the device.  `get_original_obs()` /
+`get_original_reward()` return the un-normalised tensors that the replay buffer and the HGE heuristic
+consume (hge.py:125); `save`/`load` persist the statistics like SaveEnvStatsCallback does
+(utils/callbacks.py:26-37).
+
+stable-baselines3 is third-party and absent here: semantics follow its documented behaviour
+(SURVEY Appendix D); parity with SB3 itself is unpinned, the tests check against a numpy restatement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+
+import torch
+
+from . import _lib
+from .vec_env import LazyInfos
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VecNormalize:
+    def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0,
+                 gamma=0.99, epsilon=1e-8):
+        if getattr(venv, "output", "torch") != "torch":
+            raise ValueError("VecNormalize runs on the device: build the env with output='torch'")
+        self.venv = venv
+        self.lib = _lib.load()
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = float(clip_obs), float(clip_reward), float(gamma), float(epsilon)
+        self.num_envs = venv.num_envs
+        self.observation_space, self.action_space = venv.observation_space, venv.action_space
+        self.device = venv.device
+        n, od, dev = self.num_envs, venv.spec.obs_dim, self.device
+        self.od = od
+        f64 = dict(dtype=torch.float64, device=dev)
+        # RunningMeanStd(epsilon=1e-4): mean 0, var 1, count 1e-4; two buffers each (in / out, swapped)
+        self._obs_rms = [self._fresh(od, f64), self._fresh(od, f64)]
+        self._ret_rms = [self._fresh(1, f64), self._fresh(1, f64)]
+        self.returns = torch.zeros(n, **f64)
+        self._scratch = torch.zeros(2 * od + 2, **f64)
+        self.old_obs = torch.zeros((n, od), dtype=torch.float32, device=dev)
+        self.old_reward = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self._nobs = torch.zeros((n, od), dtype=torch.float32, device=dev)
+        self._nrew = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self._nterm = torch.zeros((n, od), dtype=torch.float32, device=dev)
+
+    @staticmethod
+    def _fresh(d, kw):
+        t = torch.zeros(2 * d + 1, **kw)
+        t[d:2 * d] = 1.0
+        t[2 * d] = 1e-4
+        return t
+
+    # ------------------------------------------------------------------ statistics access
+    @property
+    def obs_rms(self):
+        r = self._obs_rms[0]
+        return {"mean": r[: self.od], "var": r[self.od: 2 * self.od], "count": r[2 * self.od]}
+
+    @property
+    def ret_rms(self):
+        r = self._ret_rms[0]
+        return {"mean": r[0], "var": r[1], "count": r[2]}
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _update(self, obs, reward):
+        rc = self.lib.sn_vecnorm_update(self.num_envs, self.od, _p(obs), _p(reward), self.gamma, _p(self.returns),
+                                        _p(self._obs_rms[0]), _p(self._obs_rms[1]), _p(self._ret_rms[0]),
+                                        _p(self._ret_rms[1]), _p(self._scratch), self._stream())
+        _lib.check(rc)
+        self._obs_rms.reverse()
+        self._ret_rms.reverse()
+
+    def _apply(self, obs, obs_out, reward, reward_out, reset_returns, n=None):
+        rc = self.lib.sn_vecnorm_apply(self.num_envs if n is None else n, self.od, _p(obs), _p(obs_out), _p(reward), _p(reward_out),
+                                       _p(self._obs_rms[0]), _p(self._ret_rms[0]), self.clip_obs, self.clip_reward,
+                                       self.epsilon, int(reset_returns), _p(self.returns), self._stream())
+        _lib.check(rc)
+
+    # ------------------------------------------------------------------ VecEnv API
+    def reset(self):
+        obs = self.venv.reset()
+        self.old_obs.copy_(obs)
+        self.returns.zero_()
+        if not self.norm_obs:
+            return obs
+        if self.training:
+            self._update(obs, None)
+        self._apply(obs, self._nobs, None, None, False)
+        return self._nobs
+
+    def step_async(self, actions):
+        self.venv.step_async(actions)
+
+    def step_wait(self):
+        obs, rew, dones, infos = self.venv.step_wait()
+        self.old_obs.copy_(obs)
+        self.old_reward.copy_(rew)
+        done = infos.terminal_observation is not None
+        if self.training:
+            # obs statistics and (if rewards are normalised) the discounted returns in one pass
+            self._update(obs if self.norm_obs else self.old_obs, rew if self.norm_reward else None)
+            if not self.norm_obs:                      # statistics of obs were updated needlessly: undo the swap
+                self._obs_rms.reverse()
+        out_obs, out_rew = obs, rew
+        self._apply(obs if self.norm_obs else None, self._nobs, rew if self.norm_reward else None, self._nrew,
+                    done and self.norm_reward)
+        if self.norm_obs:
+            out_obs = self._nobs
+        if self.norm_reward:
+            out_rew = self._nrew
+        elif done:
+            self.returns.zero_()
+        if done and self.norm_obs:
+            self._apply(infos.terminal_observation, self._nterm, None, None, False)
+            infos = LazyInfos(infos.n, self._nterm, infos.episode_return, infos.episode_length, infos.elapsed)
+        return out_obs, out_rew, dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def get_original_obs(self):
+        return self.old_obs
+
+    def get_original_reward(self):
+        return self.old_reward
+
+    def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
+        """Normalise any batch [m, obs_dim] with the current statistics (no update)."""
+        if not self.norm_obs:
+            return obs
+        out = torch.empty_like(obs, dtype=torch.float32)
+        self._apply(obs.to(torch.float32).contiguous(), out, None, None, False, n=obs.shape[0])
+        return out
+
+    def normalize_reward(self, reward: torch.Tensor) -> torch.Tensor:
+        if not self.norm_reward:
+            return reward
+        out = torch.empty_like(reward, dtype=torch.float32)
+        self._apply(None, None, reward.to(torch.float32).contiguous(), out, False, n=reward.shape[0])
+        return out
+
+    def close(self):
+        self.venv.close()
+
+    def seed(self, seed=None):
+        return self.venv.seed(seed)
+
+    def __getattr__(self, name):          # spec, sim, period, ... of the wrapped env
+        if name == "venv":
+            raise AttributeError(name)
+        return getattr(self.venv, name)
+
+    # ------------------------------------------------------------------ persistence
+    def state_dict(self):
+        return {"obs_rms": self._obs_rms[0].cpu(), "ret_rms": self._ret_rms[0].cpu(), "clip_obs": self.clip_obs,
+                "clip_reward": self.clip_reward, "gamma": self.gamma, "epsilon": self.epsilon,
+                "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
+
+    def load_state_dict(self, sd):
+        self._obs_rms[0].copy_(sd["obs_rms"])
+        self._ret_rms[0].copy_(sd["ret_rms"])
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
+            setattr(self, k, sd[k])
+
+    def save(self, save_path: str):
+        with open(save_path, "wb") as fh:
+            pickle.dump(self.state_dict(), fh)
+
+    @staticmethod
+    def load(load_path: str, venv):
+        with open(load_path, "rb") as fh:
+            sd = pickle.load(fh)
+        vn = VecNormalize(venv)
+        vn.load_state_dict(sd)
+        return vn

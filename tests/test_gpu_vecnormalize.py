@@ -1,0 +1,91 @@
+"""Device VecNormalize vs a numpy restatement of SB3's VecNormalize/RunningMeanStd (Appendix D;
+parity with SB3 itself is unpinned: SB3 is not installed).  Tolerance 1e-6 relative on normalised
+values (float32 outputs), 1e-10 on the float64 running statistics."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+class RMS:
+    def __init__(self, shape):
+        self.mean, self.var, self.count = np.zeros(shape), np.ones(shape), 1e-4
+
+    def update(self, x):
+        bm, bv, bc = x.mean(0), x.var(0), x.shape[0]
+        d = bm - self.mean
+        tot = self.count + bc
+        self.mean = self.mean + d * bc / tot
+        self.var = (self.var * self.count + bv * bc + d * d * self.count * bc / tot) / tot
+        self.count = tot
+
+
+def test_vecnormalize_matches_numpy_restatement(tmp_path):
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    n = 2048
+    env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=4, dtype="float32"),
+                       clip_obs=100.0, clip_reward=1000.0)
+    obs_rms, ret_rms, ret = RMS((28,)), RMS(()), np.zeros(n)
+    gamma, eps = 0.99, 1e-8
+    nobs = env.reset()
+    raw = env.get_original_obs().cpu().numpy().astype(np.float64)
+    obs_rms.update(raw)
+    np.testing.assert_allclose(nobs.cpu().numpy(), np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + eps), -100, 100),
+                               rtol=1e-5, atol=1e-5)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(205):                                    # crosses two episode ends (auto-reset)
+        a = torch.rand((n, 4), device="cuda", generator=g) * 16
+        nobs, nrew, dones, infos = env.step(a)
+        raw = env.get_original_obs().cpu().numpy().astype(np.float64)
+        r = env.get_original_reward().cpu().numpy().astype(np.float64)
+        obs_rms.update(raw)
+        ret = ret * gamma + r
+        ret_rms.update(ret)
+        np.testing.assert_allclose(nobs.cpu().numpy(), np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + eps), -100, 100),
+                                   rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(nrew.cpu().numpy(), np.clip(r / np.sqrt(ret_rms.var + eps), -1000, 1000), rtol=1e-5, atol=1e-6)
+        if dones.all():
+            tr = infos.terminal_observation.cpu().numpy()
+            assert np.abs(tr).max() <= 100.0 and np.isfinite(tr).all()
+            ret[:] = 0
+        np.testing.assert_allclose(env.returns.cpu().numpy(), ret, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(env.obs_rms["mean"].cpu().numpy(), obs_rms.mean, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(env.obs_rms["var"].cpu().numpy(), obs_rms.var, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(env.ret_rms["var"].item(), ret_rms.var, rtol=1e-8)
+    assert abs(env.obs_rms["count"].item() - obs_rms.count) < 1e-6
+    # frozen statistics (evaluation env): no update, same normalisation; save / load round trip
+    env.training = False
+    before = env._obs_rms[0].clone()
+    env.step(torch.zeros((n, 4), device="cuda"))
+    assert torch.equal(before, env._obs_rms[0])
+    path = str(tmp_path / "vecnormalize.pkl")
+    env.save(path)
+    env2 = VecNormalize.load(path, R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=5, dtype="float32"))
+    assert torch.equal(env2._obs_rms[0], env._obs_rms[0]) and env2.clip_obs == 100.0
+    x = torch.rand((n, 28), device="cuda") * 30
+    assert torch.equal(env.normalize_obs(x), env2.normalize_obs(x))
+
+
+def test_vecnormalize_small_obs_dim_and_reward_only():
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    n = 333
+    env = VecNormalize(R.make("BeerGameNormalRetailer-v0", n_envs=n, seed=1, dtype="float32"), norm_obs=False,
+                       clip_reward=1000.0, gamma=0.95)
+    o = env.reset()
+    assert o.shape == (n, 7)
+    ret_rms, ret = RMS(()), np.zeros(n)
+    for t in range(20):
+        o, nrew, _, _ = env.step(torch.full((n, 1), 9.0, device="cuda"))
+        assert torch.equal(o, env.get_original_obs())                 # observations untouched
+        r = env.get_original_reward().cpu().numpy().astype(np.float64)
+        ret = ret * 0.95 + r
+        ret_rms.update(ret)
+        np.testing.assert_allclose(nrew.cpu().numpy(), np.clip(r / np.sqrt(ret_rms.var + 1e-8), -1000, 1000), rtol=1e-5, atol=1e-6)
+    env7 = VecNormalize(R.make("BeerGameNormalRetailer-v0", n_envs=n, seed=1, dtype="float32"), clip_obs=100.0)
+    o = env7.reset()
+    raw = env7.get_original_obs().cpu().numpy().astype(np.float64)
+    rms = RMS((7,)); rms.update(raw)
+    np.testing.assert_allclose(o.cpu().numpy(), np.clip((raw - rms.mean) / np.sqrt(rms.var + 1e-8), -100, 100), rtol=1e-5, atol=1e-5)
