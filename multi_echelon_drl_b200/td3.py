@@ -1,0 +1,303 @@
+"""TD3 + heuristic-guided exploration on the device VecEnv (BASELINE config 5).
+
+Plain-PyTorch counterpart of the reference's training stack for the continuous-action case:
+`HgeTD3` (hge.py:47-172, a stable-baselines3 TD3 subclass), `HgeRateCallback`
+(utils/callbacks.py:5-23) and the wiring of train_td3.py:100-143.  SB3 is third-party and not
+installed here; behaviour follows SB3 1.x TD3 as documented: twin critics,
+delayed policy updates (policy_delay 2), target policy smoothing (noise 0.2, clip 0.5), Polyak tau,
+`learning_starts` uniform-random warm-up, Gaussian action noise added in the scaled [-1,1] action
+space (also to heuristic actions, hge.py:129-137), replay buffer holding ORIGINAL observations and
+rewards that are normalised with the current VecNormalize statistics at sample time.
+
+Everything stays on the GPU: observations / rewards come from the CUDA env kernels, the heuristic is
+`sn_heuristic`, the replay buffer is a set of device tensors, the MLPs are torch.nn modules (the small
+actor/critic MLPs stay in PyTorch per north_star).  Parity with SB3's numerics is unpinned.
+
+Difference on purpose: SB3 runs `gradient_steps = train_freq * n_envs` updates per rollout
+(gradient_steps=-1, hge.py:66); with thousands of envs that is impractical, so `gradient_steps` is
+explicit here (default: train_freq).  `gradient_steps=-1` reproduces SB3's rule.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .hge import HgeRateSchedule, hge_predict
+from .vec_normalize import VecNormalize
+
+
+def mlp(inp, hidden, out, out_act=None):
+    layers, d = [], inp
+    for h in hidden:
+        layers += [nn.Linear(d, h), nn.ReLU()]
+        d = h
+    layers.append(nn.Linear(d, out))
+    if out_act is not None:
+        layers.append(out_act)
+    return nn.Sequential(*layers)
+
+
+class ReplayBuffer:
+    """Ring buffer of device tensors; `add` takes one vector step (n_envs transitions)."""
+
+    def __init__(self, capacity, obs_dim, act_dim, device):
+        self.capacity, self.pos, self.full = int(capacity), 0, False
+        kw = dict(dtype=torch.float32, device=device)
+        self.obs = torch.zeros((capacity, obs_dim), **kw)
+        self.next_obs = torch.zeros((capacity, obs_dim), **kw)
+        self.act = torch.zeros((capacity, act_dim), **kw)
+        self.rew = torch.zeros((capacity,), **kw)
+        self.done = torch.zeros((capacity,), **kw)
+
+    def __len__(self):
+        return self.capacity if self.full else self.pos
+
+    def add(self, obs, next_obs, act, rew, done):
+        n = obs.shape[0]
+        if n > self.capacity:
+            raise ValueError("replay buffer smaller than one vector step")
+        idx = (torch.arange(n, device=obs.device) + self.pos) % self.capacity
+        self.obs[idx], self.next_obs[idx], self.act[idx] = obs, next_obs, act
+        self.rew[idx], self.done[idx] = rew, done.to(torch.float32)
+        self.full = self.full or (self.pos + n >= self.capacity)
+        self.pos = (self.pos + n) % self.capacity
+
+    def sample(self, batch_size, generator=None):
+        idx = torch.randint(0, len(self), (batch_size,), device=self.obs.device, generator=generator)
+        return self.obs[idx], self.act[idx], self.next_obs[idx], self.rew[idx], self.done[idx]
+
+
+@dataclass
+class TD3Config:
+    """Defaults = setup_exmaple_centralized.yaml:6-15 through train_td3.py:103-123."""
+    batch_size: int = 128
+    net_arch: tuple = (768,)              # [width * num_layers]: ONE hidden layer (train_td3.py:103)
+    learning_rate: float = 1e-3
+    tau: float = 0.01
+    train_freq: int = 32
+    gradient_steps: int = 32
+    action_noise_std: float = 0.4
+    gamma: float = 0.95
+    hge_rate_at_start: float = 0.5
+    hge_decay_periods: int = 1000
+    buffer_size: int = 1_000_000
+    learning_starts: int = 100
+    policy_delay: int = 2
+    target_policy_noise: float = 0.2
+    target_noise_clip: float = 0.5
+    seed: int = 0
+
+
+@dataclass
+class Timers:
+    env_step: float = 0.0
+    heuristic: float = 0.0
+    policy_forward: float = 0.0
+    update: float = 0.0
+    events: list = field(default_factory=list)
+
+    def span(self, name):
+        return _Span(self, name)
+
+    def flush(self):
+        torch.cuda.synchronize()
+        for name, a, b in self.events:
+            setattr(self, name, getattr(self, name) + a.elapsed_time(b) * 1e-3)
+        self.events.clear()
+
+
+class _Span:
+    def __init__(self, timers, name):
+        self.t, self.name = timers, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        b = torch.cuda.Event(enable_timing=True)
+        b.record()
+        self.t.events.append((self.name, self.a, b))
+
+
+class HgeTD3:
+    """model = HgeTD3(env, heuristic, cfg); model.learn(total_timesteps)."""
+
+    def __init__(self, env, heuristic=None, cfg: Optional[TD3Config] = None, ddp: bool = False):
+        self.env, self.heuristic, self.cfg = env, heuristic, cfg or TD3Config()
+        c = self.cfg
+        self.device = env.device
+        self.vec_normalize = env if isinstance(env, VecNormalize) else None
+        od, ad = env.observation_space.shape[0], env.action_space.shape[0]
+        self.low = torch.as_tensor(np.asarray(env.action_space.low), dtype=torch.float32, device=self.device)
+        self.high = torch.as_tensor(np.asarray(env.action_space.high), dtype=torch.float32, device=self.device)
+        torch.manual_seed(c.seed)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(c.seed)
+        self.rng = np.random.RandomState(c.seed)
+        mk = lambda m: m.to(self.device)
+        self.actor = mk(mlp(od, c.net_arch, ad, nn.Tanh()))
+        self.actor_target = mk(mlp(od, c.net_arch, ad, nn.Tanh()))
+        self.critics = nn.ModuleList([mk(mlp(od + ad, c.net_arch, 1)) for _ in range(2)])
+        self.critics_target = nn.ModuleList([mk(mlp(od + ad, c.net_arch, 1)) for _ in range(2)])
+        self.actor_target.load_state_dict(self.actor.state_dict())
+        self.critics_target.load_state_dict(self.critics.state_dict())
+        if ddp:
+            self._broadcast_parameters()
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=c.learning_rate)
+        self.critic_opt = torch.optim.Adam(self.critics.parameters(), lr=c.learning_rate)
+        self.buffer = ReplayBuffer(c.buffer_size, od, ad, self.device)
+        self.hge_schedule = HgeRateSchedule(c.hge_rate_at_start, c.hge_decay_periods)
+        self.hge_rate = c.hge_rate_at_start if heuristic is not None else 0.0
+        self.num_timesteps, self.n_updates = 0, 0
+        self.timers = Timers()
+        self.episode_returns = []
+
+    # ---- action scaling like SB3's policy.scale_action / unscale_action
+    def scale_action(self, a):
+        return 2.0 * (a - self.low) / (self.high - self.low) - 1.0
+
+    def unscale_action(self, s):
+        return self.low + 0.5 * (s + 1.0) * (self.high - self.low)
+
+    @torch.no_grad()
+    def predict(self, observation, deterministic=False, original_obs=None):
+        """HgeTD3.predict (hge.py:144-172): one coin per call with probability hge_rate**2."""
+        def policy(o):
+            with self.timers.span("policy_forward"):
+                return self.unscale_action(self.actor(o))
+
+        if self.heuristic is None or deterministic:
+            return policy(observation)
+
+        class _H:
+            def get_order_quantity(_, o):
+                with self.timers.span("heuristic"):
+                    return self.heuristic.get_order_quantity(o)
+
+        a, _ = hge_predict(policy, _H(), observation, original_obs if original_obs is not None else observation,
+                           self.hge_rate, deterministic, rng=self.rng)
+        return a
+
+    @torch.no_grad()
+    def _sample_action(self, obs, original_obs):
+        c, n = self.cfg, obs.shape[0]
+        if self.num_timesteps < c.learning_starts:
+            u = torch.rand((n, self.low.shape[0]), device=self.device, generator=self.gen)
+            unscaled = self.low + u * (self.high - self.low)
+        else:
+            unscaled = self.predict(obs, False, original_obs)
+        scaled = self.scale_action(unscaled.to(torch.float32))
+        if c.action_noise_std > 0:
+            noise = torch.randn(scaled.shape, device=self.device, generator=self.gen) * c.action_noise_std
+            scaled = torch.clamp(scaled + noise, -1.0, 1.0)
+        return self.unscale_action(scaled), scaled
+
+    def _normalize(self, obs, rew):
+        if self.vec_normalize is None:
+            return obs, rew
+        return self.vec_normalize.normalize_obs(obs), self.vec_normalize.normalize_reward(rew)
+
+    def train(self, gradient_steps):
+        c = self.cfg
+        for _ in range(gradient_steps):
+            self.n_updates += 1
+            obs, act, nobs, rew, done = self.buffer.sample(c.batch_size, self.gen)
+            obs, rew = self._normalize(obs, rew)
+            nobs, _ = self._normalize(nobs, rew)
+            with torch.no_grad():
+                noise = (torch.randn(act.shape, device=self.device, generator=self.gen) * c.target_policy_noise
+                         ).clamp(-c.target_noise_clip, c.target_noise_clip)
+                na = (self.actor_target(nobs) + noise).clamp(-1.0, 1.0)
+                x = torch.cat([nobs, na], dim=1)
+                q_next = torch.min(self.critics_target[0](x), self.critics_target[1](x)).squeeze(1)
+                target = rew + (1.0 - done) * c.gamma * q_next
+            x = torch.cat([obs, act], dim=1)
+            qs = [m(x).squeeze(1) for m in self.critics]
+            critic_loss = sum(F.mse_loss(q, target) for q in qs)
+            self.critic_opt.zero_grad(set_to_none=True)
+            critic_loss.backward()
+            self._allreduce_grads(self.critics)
+            self.critic_opt.step()
+            if self.n_updates % c.policy_delay == 0:
+                actor_loss = -self.critics[0](torch.cat([obs, self.actor(obs)], dim=1)).mean()
+                self.actor_opt.zero_grad(set_to_none=True)
+                actor_loss.backward()
+                self._allreduce_grads(self.actor)
+                self.actor_opt.step()
+                with torch.no_grad():
+                    for p, pt in zip(self.actor.parameters(), self.actor_target.parameters()):
+                        pt.mul_(1 - c.tau).add_(p, alpha=c.tau)
+                    for p, pt in zip(self.critics.parameters(), self.critics_target.parameters()):
+                        pt.mul_(1 - c.tau).add_(p, alpha=c.tau)
+
+    def _broadcast_parameters(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for m in (self.actor, self.actor_target, self.critics, self.critics_target):
+                for p in m.parameters():
+                    dist.broadcast(p.data, src=0)
+
+    @staticmethod
+    def _allreduce_grads(module):
+        """Data-parallel training across GPUs: average gradients over ranks (NCCL over NVLink)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        grads = [p.grad for p in module.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= dist.get_world_size()
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def learn(self, total_timesteps, log_interval=None):
+        """OffPolicyAlgorithm.learn: collect train_freq vector steps, then train (train_td3.py:138-143)."""
+        c, env = self.cfg, self.env
+        n = env.num_envs
+        obs = env.reset()
+        orig = env.get_original_obs().clone()
+        t0 = time.time()
+        while self.num_timesteps < total_timesteps:
+            for _ in range(c.train_freq):
+                self.hge_rate = self.hge_schedule(self.num_timesteps) if self.heuristic is not None else 0.0
+                action, buffer_action = self._sample_action(obs, orig)
+                with self.timers.span("env_step"):
+                    new_obs, rew, dones, infos = env.step(action)
+                new_orig = env.get_original_obs()
+                raw_rew = env.get_original_reward() if self.vec_normalize is not None else rew
+                done = bool(infos.terminal_observation is not None)
+                # at an episode end the stored next observation is the terminal one, not the reset one
+                next_for_buffer = new_orig
+                if done:
+                    next_for_buffer = infos.terminal_observation if self.vec_normalize is None else \
+                        self.vec_normalize.venv._term_obs
+                    self.episode_returns.append(float(infos.episode_return.mean().item()))
+                self.buffer.add(orig, next_for_buffer, buffer_action, raw_rew, dones)
+                obs, orig = new_obs, new_orig.clone()
+                self.num_timesteps += n
+            if self.num_timesteps >= c.learning_starts and len(self.buffer) >= c.batch_size:
+                steps = c.gradient_steps if c.gradient_steps >= 0 else c.train_freq * n
+                with self.timers.span("update"):
+                    self.train(steps)
+            if log_interval and (self.num_timesteps // n) % log_interval < c.train_freq:
+                self.timers.flush()
+                last = self.episode_returns[-1] if self.episode_returns else float("nan")
+                print(f"timesteps {self.num_timesteps:>12,}  updates {self.n_updates:>7,}  hge_rate {self.hge_rate:.3f}  "
+                      f"mean episode return {last:10.1f}  fps {self.num_timesteps / (time.time() - t0):,.0f}", flush=True)
+        self.timers.flush()
+        return self
+
+    def time_split(self):
+        t = self.timers
+        tot = max(t.env_step + t.heuristic + t.policy_forward + t.update, 1e-12)
+        return {"env_step_s": t.env_step, "heuristic_s": t.heuristic, "policy_forward_s": t.policy_forward,
+                "update_s": t.update, "env_step_frac": t.env_step / tot, "update_frac": t.update / tot}

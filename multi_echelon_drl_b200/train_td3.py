@@ -1,0 +1,83 @@
+"""Command line of the reference's train_td3.py (train_td3.py:18-147) on the GPU VecEnv.
+
+    python -m multi_echelon_drl_b200.train_td3 -g 1 -p setup.yaml --name run --ordering-rule a \
+        --role MultiFacility --scenario complex [--n-envs 4096] [--timesteps N]
+
+Flags -g/-p/--name/--ordering-rule/--role/--scenario keep the reference's meaning.  Under torchrun every
+rank owns n-envs envs (sharded by rank) and gradients are averaged over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+
+import torch
+import yaml
+
+from .register_envs import make
+from .td3 import HgeTD3, TD3Config
+from .utils.heuristics import BaseStockPolicy
+from .utils.wrappers import wrap_action_d_plus_a
+from .vec_normalize import VecNormalize
+
+ROLES = ["Retailer", "Wholesaler", "Distributor", "Manufacturer", "MultiFacility"]
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-g", "--global-info", type=bool, default=False)     # any non-empty string is True (Q5)
+    ap.add_argument("-p", "--parameters", type=str, default=None, help="experiment YAML (setup_exmaple_*.yaml layout)")
+    ap.add_argument("--name", type=str, default="td3")
+    ap.add_argument("--ordering-rule", type=str, default="a", choices=["a", "d+a"])
+    ap.add_argument("--role", type=str, default="MultiFacility", choices=ROLES)
+    ap.add_argument("--scenario", type=str, default="complex", choices=["basic", "complex"])
+    ap.add_argument("--n-envs", type=int, default=4096)
+    ap.add_argument("--timesteps", type=int, default=None)
+    ap.add_argument("--log-interval", type=int, default=320)
+    args = ap.parse_args(argv)
+
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    setup = {"hyperparameters": {"td3": {}}}
+    if args.parameters:
+        with open(args.parameters) as fh:
+            setup = yaml.safe_load(fh)
+    p = setup.get("hyperparameters", {}).get("td3", {})
+    if args.scenario == "basic":                      # train_td3.py:52-61
+        targets, demand_type, (lb, ub), offset = [48, 43, 41, 30], "Normal", (0, 20), -10
+    else:
+        targets, demand_type, (lb, ub), offset = [19, 20, 20, 14], "Uniform", (0, 16), -8
+    if p.get("hge_rate_at_start", 0) > 0 and args.role != "MultiFacility":
+        raise ValueError("HGE is only supported for the MultiFacility role")          # train_td3.py:65-66
+    env_name = f"BeerGame{demand_type}{args.role}{'FullInfo' * bool(args.global_info)}-v0"
+    bsp = BaseStockPolicy(targets, {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1,
+                                    "latest_demand": 2}, 7, lb, ub, args.ordering_rule)
+    env = make(env_name, n_envs=args.n_envs, dtype="float32", seed=1000 * rank)
+    if args.ordering_rule == "d+a":
+        env = wrap_action_d_plus_a(env, offset=offset, lb=lb, ub=ub)          # train_td3.py:86-91
+    env = VecNormalize(env, clip_obs=100.0, clip_reward=1000.0)
+    cfg = TD3Config(batch_size=p.get("batch_size", 128),
+                    net_arch=(p.get("width", 256) * p.get("num_layers", 3),),
+                    learning_rate=p.get("learning_rate", 1e-3), tau=p.get("tau", 0.01), train_freq=p.get("train_freq", 32),
+                    gradient_steps=p.get("gradient_steps", p.get("train_freq", 32)),
+                    action_noise_std=p.get("action_noise_std", 0.4), gamma=p.get("gamma", 0.95),
+                    hge_rate_at_start=p.get("hge_rate_at_start", 0.5), seed=rank)
+    heuristic = bsp if cfg.hge_rate_at_start > 0 else None
+    model = HgeTD3(env, heuristic, cfg, ddp=world > 1)
+    total = args.timesteps or setup.get("max_time_steps", 10_000_000)
+    model.learn(total, log_interval=args.log_interval if rank == 0 else None)
+    if rank == 0:
+        out = {"name": args.name, "env": env_name, "n_envs_per_gpu": args.n_envs, "n_gpus": world,
+               "timesteps": model.num_timesteps, "updates": model.n_updates, "time_split": model.time_split(),
+               "last_mean_episode_return": model.episode_returns[-1] if model.episode_returns else None}
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
