@@ -24,6 +24,8 @@ def timeit(fn, reps=20):
 def f1(): sim.period, sim.terminal = 0, False; sim.rollout(T, actions=a, traj_obs=to, traj_reward=tr)
 def f2(): sim.period, sim.terminal = 0, False; sim.rollout(T, policy=pol)
 def f3(): sim.period, sim.terminal = 0, False; sim.rollout(T, actions=a)
-m1, m2, m3 = timeit(f1), timeit(f2), timeit(f3)
+def f4(): sim.period, sim.terminal = 0, False; sim.rollout(T, actions=a, traj_obs=to)
+def f5(): sim.period, sim.terminal = 0, False; sim.rollout(T, actions=a, traj_reward=tr)
+m1, m2, m3, m4, m5 = timeit(f1), timeit(f2), timeit(f3), timeit(f4), timeit(f5)
 print(json.dumps({"lib": os.environ.get("SUPPLYNET_LIB", "default"), "n": n, "traj_ms": m1, "traj_GBs": n*T*137/m1/1e6,
-                  "heur_ms": m2, "heur_Gsteps": n*T/m2/1e6, "actions_only_ms": m3}))
+                  "heur_ms": m2, "heur_Gsteps": n*T/m2/1e6, "actions_only_ms": m3, "obs_only_ms": m4, "reward_only_ms": m5}))

@@ -283,3 +283,40 @@ def test_episode_host_pipelined_equals_plain(chunks):
         assert np.array_equal(h_obs.numpy(), ref["obs"])
         assert np.array_equal(h_rew.numpy(), ref["rew"].astype(np.float32))
         assert np.array_equal(sim.ep_return.cpu().numpy(), ref["rew"].sum(0))
+
+
+@pytest.mark.parametrize("n", [1, 33, 95, 130])
+def test_no_out_of_bounds_writes_canaries(n):
+    """compute-sanitizer is closed on this pool, so bounds are checked with guard bands: every output
+    buffer is a window inside a larger sentinel-filled allocation; padding lanes of the state rows
+    ([n, ld)) must stay untouched as well."""
+    T, G = 12, 64
+    init, demand = _seeded_batch("uniform", n, T, 5)
+    acts = np.random.RandomState(1).randint(0, 17, (T, n, 4))
+    for agents, glob in (((0, 1, 2, 3), True), ((1,), False), ((2, 1), True)):
+        sim = _make("uniform", agents, glob, "a", T, n, "int32")
+        od, na = sim.obs_dim, sim.n_agents
+        sim.state.fill_(-77)
+        sim.load_episode(init, demand)
+
+        def window(shape, dtype=torch.float32):
+            numel = int(np.prod(shape))
+            big = torch.full((numel + 2 * G,), -12345.0 if dtype.is_floating_point else -12345, dtype=dtype, device="cuda")
+            return big, big[G:G + numel].view(shape)
+
+        b_obs, obs = window((n, od))
+        b_to, traj_obs = window((T, n, od))
+        b_tr, traj_rew = window((T, n))
+        b_ta, traj_act = window((T, n, na))
+        b_rw, rew = window((n,))
+        sim.reset(obs_out=obs)
+        sim.step(torch.as_tensor(acts[0][:, :na]), obs_out=obs, reward_out=rew)
+        sim.rollout(T - 1, actions=torch.as_tensor(acts[1:, :, :na]), traj_obs=traj_obs[1:], traj_reward=traj_rew[1:],
+                    traj_actions=traj_act[1:])
+        sim.episode(T, actions=torch.as_tensor(acts[:, :, :na]), traj_obs=traj_obs, traj_reward=traj_rew,
+                    traj_actions=traj_act, obs0_out=obs)
+        torch.cuda.synchronize()
+        for big in (b_obs, b_to, b_tr, b_ta, b_rw):
+            assert (big[:G] == -12345).all() and (big[-G:] == -12345).all()
+        assert (sim.state[:, n:] == -77).all()
+        assert torch.isfinite(traj_obs).all() and (traj_obs != -12345).all()
