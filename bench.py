@@ -243,10 +243,10 @@ def run_native(args):
     for _ in range(args.warmup):
         device_step(False)
     ms_dev = timed(device_step, args.steps, 0, record=True)
-    clocks = sampler.finish() if sampler else None
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
     ms_e2e = timed(e2e_step, max(1, min(args.steps, 10)), min(args.warmup, 3))
     e2e_steps = max(1, min(args.steps, 10))
+    clocks = sampler.finish() if sampler else None       # sampled across both timed regions
 
     # correctness guard on the numbers just produced: statistics vector vs the trajectory it wrote
     sim.stats.zero_()
@@ -373,7 +373,34 @@ def single_step_numbers(torch, dev, peak):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / reps
     out["heuristic_rollout_131072"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_episode": ms,
-                                       "bound": "alu/latency (state on-chip, 4 B/env-step HBM)"}
+                                       "bound": "alu/latency (state on-chip, 4 B/env-step HBM)",
+                                       "config": "config 3 per-GPU share: 131,072 envs, base-stock [19,20,20,14] in-kernel"}
+    del sim
+    # config-4 mode: 262,144 envs x 2 items (independent item chains, per-item costs), single-step API
+    from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
+    from dataclasses import replace
+    n = 262144
+    specs = [spec, replace(spec, holding_cost=(0.75,) * 4)]
+    mi = MultiItemSupplyNetwork(specs, n, dev, "int32")
+    for it in mi.items:
+        it.demand.copy_(torch.randint(0, 9, it.demand.shape, generator=g, device=dev, dtype=torch.int32))
+        it.init.copy_(torch.randint(0, 9, it.init.shape, generator=g, device=dev, dtype=torch.int32))
+    acts = torch.randint(0, 17, (n, 8), generator=g, device=dev, dtype=torch.int32)
+    mi.reset()
+    for _ in range(5):
+        mi.step(acts)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    reps = 60
+    for _ in range(reps):
+        mi.step(acts)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    out["multi_item_262144x2_step"] = {"env_steps_per_s": n / (ms * 1e-3), "item_chain_steps_per_s": 2 * n / (ms * 1e-3),
+                                       "us_per_step": ms * 1e3,
+                                       "config": "config 4: 262,144 envs x 2 items, obs 56 / action 8, eager per-period calls"}
     return out
 
 

@@ -164,3 +164,45 @@ def test_float_vecenv_accepts_fractional_actions_and_int_rejects_them():
     # negative orders are clamped to 0 like network_components.py:368-374 (no warning spam on device)
     obs, _, _, _ = envi.step(torch.full((8, 4), -5, device="cuda"))
     assert (obs[:, 3] == 0).all()
+
+
+def test_multi_item_network_equals_independent_item_chains():
+    """Config 4 semantics (parity unpinned: the reference has no multi-item behaviour): two items from
+    network_configs/multi_item.yaml = two independent chains with their own holding costs; obs is the
+    concatenation, reward the sum.  Checked against the oracle run once per item."""
+    import os
+    import multi_echelon_drl_b200 as pkg
+    from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
+    from multi_echelon_drl_b200.spec import specs_from_config
+    from multi_echelon_drl_b200.utils.graph import read_yaml
+    from oracle import beergame_np as O
+    from helpers import split_init
+    net = read_yaml(os.path.join(os.path.dirname(pkg.__file__), "network_configs", "multi_item.yaml"))
+    ag = ["retailer", "wholesaler", "distributor", "manufacturer"]
+    specs = specs_from_config(net, ag, True, 100)
+    n, T = 517, 100
+    rs = np.random.RandomState(3)
+    init = np.concatenate([rs.randint(0, 25, (n, 2, 4)), rs.randint(0, 9, (n, 2, 15))], axis=2)
+    demand = rs.randint(0, 9, (n, 2, T + 3))
+    acts = rs.randint(0, 17, (T, n, 8))
+    sim = MultiItemSupplyNetwork(specs, n, "cuda", "int32")
+    assert sim.obs_dim == 56 and sim.n_agents == 8
+    sim.load_episode(init, demand)
+    obs = sim.reset()
+    orcs = []
+    for i, h in enumerate(([0.5] * 4, [0.75] * 4)):
+        sp = O.OracleSpec(h, [1.0] * 4, [19, 20, 20, 14], (0, 1, 2, 3), True, T)
+        orc = O.BeerGameOracle(sp, n)
+        inv0, so, sh = split_init(init[:, i])
+        o0 = orc.reset(inv0, so, sh, demand[:, i])
+        assert np.array_equal(obs[:, 28 * i:28 * (i + 1)].cpu().numpy(), o0)
+        orcs.append(orc)
+    for t in range(T):
+        obs, rew, done = sim.step(torch.as_tensor(acts[t]))
+        want_r = np.zeros(n)
+        for i, orc in enumerate(orcs):
+            o, r, _ = orc.step(acts[t][:, 4 * i:4 * (i + 1)])
+            assert np.array_equal(obs[:, 28 * i:28 * (i + 1)].cpu().numpy(), o), (t, i)
+            want_r += r
+        assert np.array_equal(rew.cpu().numpy(), want_r.astype(np.float32))
+    assert done and sim.terminal
