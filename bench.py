@@ -353,6 +353,23 @@ def single_step_numbers(torch, dev, peak):
                 "bytes_per_env_step": bps, "launch": "CUDA graph of 94 sn_step launches"}
         out[tag] = res
         del sim
+    # the literal drop-in call: SB3-style VecEnv.step with numpy in / numpy out (pinned staging, H2D of the
+    # actions and D2H of obs + reward every step), BeerGameUniformMultiFacilityFullInfo-v0, 65,536 envs
+    from multi_echelon_drl_b200.register_envs import make
+    venv = make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=65536, dtype="float32", seed=0, output="numpy")
+    venv.reset()
+    a_np = np.full((65536, 4), 4.0, dtype=np.float32)
+    for _ in range(5):
+        venv.step(a_np)
+    t0 = time.perf_counter()
+    reps = 190
+    for _ in range(reps):
+        venv.step(a_np)
+    dt = time.perf_counter() - t0
+    out["vecenv_numpy_step_65536"] = {"env_steps_per_s": 65536 * reps / dt, "us_per_step": dt / reps * 1e6,
+                                      "h2d_bytes_per_step": a_np.nbytes, "d2h_bytes_per_step": 65536 * (28 * 4 + 4),
+                                      "note": "wall clock incl. host staging copies, auto-reset every 100 steps"}
+    del venv
     # config-3 mode: heuristic rollout, stats only (ALU/latency bound, ~4 B/env-step of HBM traffic)
     n = 131072
     spec = uniform_spec(("retailer", "wholesaler", "distributor", "manufacturer"), True, T, True)

@@ -90,7 +90,10 @@ class SupplyNetVecEnv:
         n, od = self.num_envs, spec.obs_dim
         self._obs = torch.zeros((n, od), dtype=torch.float32, device=self.device)
         self._term_obs = torch.zeros((n, od), dtype=torch.float32, device=self.device)
-        self._dones = torch.zeros((n,), dtype=torch.bool, device=self.device)
+        self._all_false = torch.zeros((n,), dtype=torch.bool, device=self.device)
+        self._all_true = torch.ones((n,), dtype=torch.bool, device=self.device)
+        self._np_false, self._np_true = np.zeros((n,), dtype=bool), np.ones((n,), dtype=bool)
+        self._no_infos = LazyInfos(n)
         self._last_returns = torch.zeros((n,), dtype=torch.float64, device=self.device)
         if output == "numpy":
             self._h_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype).pin_memory()
@@ -181,10 +184,8 @@ class SupplyNetVecEnv:
             self._next_episode()                    # auto-reset (DummyVecEnv.step_wait)
             sim.reset(self._obs)
             self._t0 = time.time()
-            self._dones.fill_(True)
         else:
-            infos = LazyInfos(self.num_envs)
-            self._dones.fill_(False)
+            infos = self._no_infos
         if self.output == "numpy":
             self._h_obs.copy_(self._obs, non_blocking=True)
             self._h_rew.copy_(rew, non_blocking=True)
@@ -193,8 +194,8 @@ class SupplyNetVecEnv:
                 infos.terminal_observation = self._h_term.numpy()
                 infos.episode_return = self._last_returns.cpu().numpy()
             torch.cuda.current_stream(self.device).synchronize()
-            return (self._h_obs.numpy(), self._h_rew.numpy(), np.full((self.num_envs,), done, dtype=bool), infos)
-        return self._obs, rew, self._dones, infos
+            return (self._h_obs.numpy(), self._h_rew.numpy(), self._np_true if done else self._np_false, infos)
+        return self._obs, rew, (self._all_true if done else self._all_false), infos
 
     def step(self, actions):
         self.step_async(actions)

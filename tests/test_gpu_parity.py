@@ -320,3 +320,32 @@ def test_no_out_of_bounds_writes_canaries(n):
             assert (big[:G] == -12345).all() and (big[-G:] == -12345).all()
         assert (sim.state[:, n:] == -77).all()
         assert torch.isfinite(traj_obs).all() and (traj_obs != -12345).all()
+
+
+def test_unaligned_output_buffers_take_the_plain_store_path():
+    """Observation / trajectory pointers that are not 16-byte aligned cannot use TMA bulk stores; the
+    kernels must fall back to plain stores and still be exact.  Unaligned ACTION rows are rejected."""
+    n, T = 257, 10
+    init, demand = _seeded_batch("uniform", n, T, 6)
+    acts = np.random.RandomState(2).randint(0, 17, (T, n, 4))
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts)
+    sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+    sim.load_episode(init, demand)
+    big = torch.zeros(T * n * 28 + 8, device="cuda")
+    traj = big[1:1 + T * n * 28].view(T, n, 28)                    # 4-byte offset: misaligned for TMA
+    assert traj.data_ptr() % 16 != 0
+    obs0 = torch.zeros(n * 28 + 8, device="cuda")[3:3 + n * 28].view(n, 28)
+    sim.episode(T, actions=torch.as_tensor(acts), traj_obs=traj, obs0_out=obs0)
+    assert np.array_equal(traj.cpu().numpy(), ref["obs"]) and np.array_equal(obs0.cpu().numpy(), ref["obs0"])
+    o = torch.zeros(n * 28 + 8, device="cuda")[1:1 + n * 28].view(n, 28)
+    sim.reset(obs_out=o)
+    assert np.array_equal(o.cpu().numpy(), ref["obs0"])
+    sim.step(torch.as_tensor(acts[0]), obs_out=o)
+    assert np.array_equal(o.cpu().numpy(), ref["obs"][0])
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    a = torch.zeros(n * 4 + 4, dtype=torch.int32, device="cuda")[1:]
+    rc = sim.lib.sn_step(C.byref(sim._c_spec), sim.dtype_code, n, sim.ld, 1, C.c_void_p(sim.state.data_ptr()),
+                         C.c_void_p(a.data_ptr()), C.c_void_p(sim.demand[2].data_ptr()), None, None, None, None, None,
+                         None, None)
+    assert rc == _lib.SN_ERR_INVALID and b"aligned" in sim.lib.sn_last_error()
