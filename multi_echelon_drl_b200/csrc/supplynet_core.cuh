@@ -178,9 +178,14 @@ __device__ __forceinline__ void emit_obs(const Env<T>& e, const DevSpec<T>& sp, 
     { float v[7]; node_view<3>(e, sp, terminal, v);
 #pragma unroll
       for (int j = 0; j < 7; ++j) o[21 + j] = v[j]; }
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
-      reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      for (int j = 0; j < 7; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {                       // caller's buffer is not 16-byte aligned (plain-store path only)
+#pragma unroll
+      for (int j = 0; j < 28; ++j) dst[j] = o[j];
+    }
   } else {
 #define SN_EMIT_NODE(K)                                        \
     if (sp.pos[K] >= 0) {                                      \
