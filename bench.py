@@ -393,6 +393,23 @@ def single_step_numbers(torch, dev, peak):
                                        "bound": "alu/latency (state on-chip, 4 B/env-step HBM)",
                                        "config": "config 3 per-GPU share: 131,072 envs, base-stock [19,20,20,14] in-kernel"}
     del sim
+    # config 3 end to end on one GPU's share: 10 episodes, fresh device-generated demand / initial state per episode
+    from multi_echelon_drl_b200.distributed import summarize
+    venv = make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=131072, dtype="int32", seed=3)
+    venv.run_policy_episodes(pol, 2)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    st = venv.run_policy_episodes(pol, 10)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    summ = summarize(st)
+    out["heuristic_10_episodes_131072"] = {"env_steps_per_s": 131072 * T * 10 / (ms * 1e-3), "ms_total": ms,
+                                           "mean_episode_return": summ["mean_episode_return"],
+                                           "std_episode_return": summ["std_episode_return"],
+                                           "note": "incl. per-episode demand/init generation (torch Philox) and episode moments"}
+    del venv
     # config-4 mode: 262,144 envs x 2 items (independent item chains, per-item costs), single-step API
     from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
     from dataclasses import replace

@@ -10,10 +10,13 @@ from __future__ import annotations
 def wrap_action_d_plus_a(env, offset=-8, lb: int = 0, ub: int = 16):
     from .. import _lib
     import ctypes as C
-    sim = env.sim
-    spec = env.spec.with_rule("d+a", offset, lb, ub)
+    base = env
+    while hasattr(base, "venv"):           # reach the SupplyNetVecEnv through wrappers such as VecNormalize
+        base = base.venv
+    sim = base.sim
+    spec = base.spec.with_rule("d+a", offset, lb, ub)
     c_spec = spec.to_c()
     _lib.check(sim.lib.sn_spec_validate(C.byref(c_spec), sim.dtype_code))
-    env.spec = spec
+    base.spec = spec
     sim.spec, sim._c_spec = spec, c_spec
     return env

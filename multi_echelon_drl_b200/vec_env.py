@@ -134,24 +134,26 @@ class SupplyNetVecEnv:
         torch's Philox generator directly in the structure-of-arrays layout (throughput path; not
         stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity)."""
         sp, sim, g = self.spec, self.sim, self._gen
-        n, dev = sim.ld, self.device
-        T3 = sp.max_episode_steps + 3
         a, b = sp.demand_params
+        # in-place generation in the quantity dtype: one pass over the table, no temporaries
         if sp.demand_pattern == "uniform":
-            d = torch.randint(int(a), int(b) + 1, (T3, n), generator=g, device=dev, dtype=torch.int32)
+            sim.demand.random_(int(a), int(b) + 1, generator=g)
         elif sp.demand_pattern == "normal":
-            d = torch.round(torch.clamp_min(a + b * torch.randn((T3, n), generator=g, device=dev), 0))
+            if sim.demand.is_floating_point():
+                sim.demand.normal_(float(a), float(b), generator=g).clamp_min_(0).round_()
+            else:
+                d = torch.empty(sim.demand.shape, dtype=torch.float32, device=self.device)
+                d.normal_(float(a), float(b), generator=g).clamp_min_(0).round_()
+                sim.demand.copy_(d)
         else:
-            row = torch.tensor([4] * 4 + [8] * (T3 - 4), device=dev)
-            d = row[:, None].expand(T3, n)
-        sim.demand.copy_(d.to(sim.tdtype))
+            sim.demand[:4].fill_(4)
+            sim.demand[4:].fill_(8)
         if sp.random_init:
-            sim.init[:4] = torch.randint(sp.init_inventory[0], sp.init_inventory[1], (4, n), generator=g, device=dev,
-                                         dtype=torch.int32).to(sim.tdtype)
-            sim.init[4:] = torch.randint(sp.init_pipeline[0], sp.init_pipeline[1], (15, n), generator=g, device=dev,
-                                         dtype=torch.int32).to(sim.tdtype)
+            sim.init[:4].random_(sp.init_inventory[0], sp.init_inventory[1], generator=g)
+            sim.init[4:].random_(sp.init_pipeline[0], sp.init_pipeline[1], generator=g)
         else:
-            sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=dev).to(sim.tdtype)[:, None].expand(19, n))
+            sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=self.device).to(sim.tdtype)[:, None]
+                           .expand(19, sim.ld))
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
@@ -207,6 +209,26 @@ class SupplyNetVecEnv:
             torch.cuda.current_stream(self.device).synchronize()
             return self._h_obs.numpy()
         return self._obs
+
+    def run_policy_episodes(self, policy, n_episodes: int = 1):
+        """Config-3 mode: play `n_episodes` whole episodes with a base-stock policy evaluated inside the
+        rollout kernel (one `sn_episode` launch per episode, state on-chip), drawing fresh demand /
+        initial states per episode from this env's episode source.  `policy` is a
+        `utils.heuristics.BaseStockPolicy` or `simulator.BasePolicyParams`.  Returns the statistics
+        vector (float64 [16], see distributed.py) accumulated over the episodes, on the device."""
+        from .distributed import add_episode_moments
+        params = getattr(policy, "params", policy)
+        sim = self.sim
+        keep = sim.track_stats
+        sim.track_stats = True
+        sim.stats.zero_()
+        for _ in range(int(n_episodes)):
+            self._next_episode()
+            sim.episode(policy=params, write_state=False)
+            add_episode_moments(sim.stats, sim.ep_return)
+            self.episodes_done += self.num_envs
+        sim.track_stats = keep
+        return sim.stats
 
     def close(self):
         pass

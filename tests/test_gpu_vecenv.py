@@ -206,3 +206,32 @@ def test_multi_item_network_equals_independent_item_chains():
             want_r += r
         assert np.array_equal(rew.cpu().numpy(), want_r.astype(np.float32))
     assert done and sim.terminal
+
+
+def test_run_policy_episodes_statistics_match_oracle():
+    """Config-3 path: whole episodes with the in-kernel base-stock policy; statistics vector vs oracle."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.distributed import summarize
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    n, seed, E = 200, 42, 3
+    env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="int32", seed=seed, episode_source="numpy_seeded")
+    st = env.run_policy_episodes(BaseStockPolicy([19, 20, 20, 14], lb=0, ub=16, rule="a"), E).cpu().numpy()
+    streams = [np.random.RandomState(seed + i) for i in range(n)]
+    rets, hold, back = [], np.zeros(4), np.zeros(4)
+    for _ in range(E):
+        ref = _oracle_episode_policy(env.spec, streams)
+        rets.append(ref["rew"].sum(0)); hold += ref["holding"].sum((0, 1)); back += ref["backorder"].sum((0, 1))
+    rets = np.concatenate(rets)
+    assert st[0] == n * 100 * E and st[1] == rets.sum() and st[10] == n * E and st[11] == rets.sum()
+    assert np.array_equal(st[2:6], hold) and np.array_equal(st[6:10], back)
+    assert abs(st[12] - (rets ** 2).sum()) < 1e-6 * (rets ** 2).sum()
+    s = summarize(torch.as_tensor(st))
+    assert abs(s["mean_episode_return"] - rets.mean()) < 1e-9 and abs(s["std_episode_return"] - rets.std()) < 1e-6
+    assert -1500 < s["mean_episode_return"] < -1100          # SURVEY App. A anchor: about -1300 for this heuristic
+
+
+def _oracle_episode_policy(spec, streams):
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs_from_streams
+    init, demand = seeded_episode_inputs_from_streams(spec, streams)
+    return oracle_rollout("uniform", spec.agents, spec.global_observable, "a", 100, init, demand, None,
+                          policy=([19, 20, 20, 14], 0, 16, "a"))
