@@ -349,3 +349,29 @@ def test_unaligned_output_buffers_take_the_plain_store_path():
                          C.c_void_p(a.data_ptr()), C.c_void_p(sim.demand[2].data_ptr()), None, None, None, None, None,
                          None, None)
     assert rc == _lib.SN_ERR_INVALID and b"aligned" in sim.lib.sn_last_error()
+
+
+def test_full_size_config3_heuristic_paths_agree():
+    """BASELINE config 3, one GPU's share at full size (131,072 envs, base-stock [19,20,20,14], rule 'a'):
+    (i) the in-kernel policy rollout (sn_episode) equals driving sn_step with sn_heuristic's actions
+    computed from the observations; (ii) d+a heuristic through the d+a env rule likewise; (iii) a
+    4,096-env prefix equals the oracle; (iv) mean return near the reference anchor (-1300)."""
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
+    n, T = 131072, 100
+    init, demand = _seeded_batch("uniform", n, T, 31)
+    for rule in ("a", "d+a"):
+        pol = BasePolicyParams([19, 20, 20, 14], 0, 16, rule)
+        sim = _make("uniform", (0, 1, 2, 3), True, rule, T, n, "int32")
+        sim.load_episode(init, demand)
+        sim.episode(T, policy=pol, write_state=False)
+        fused = sim.ep_return.clone()
+        obs = sim.reset()
+        for t in range(T):
+            obs, _, _ = sim.step(heuristic_actions(pol, obs))
+        assert torch.equal(fused, sim.ep_return), rule
+        m = 4096
+        ref = oracle_rollout("uniform", (0, 1, 2, 3), True, rule, T, init[:m], demand[:m], None,
+                             policy=([19, 20, 20, 14], 0, 16, rule))
+        assert np.array_equal(fused[:m].cpu().numpy(), ref["rew"].sum(0)), rule
+        if rule == "a":
+            assert -1400 < fused.mean().item() < -1200
