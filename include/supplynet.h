@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 1
+#define SN_ABI_VERSION 2
 
 #define SN_MAX_FACILITIES 4
+#define SN_MAX_ITEMS 4
 #define SN_OBS_PER_FACILITY 7   /* supplynetwork.py:151-169 */
 #define SN_STATE_WORDS 40       /* 28 observable + 12 hidden words per env */
 #define SN_INIT_WORDS 19        /* inv[4], sales orders (2,2,2,1), shipments (2,2,2,2) */
@@ -70,6 +71,15 @@ typedef struct sn_spec {
   double coplayer_target[SN_MAX_FACILITIES];  /* BaseStockPolicy target of non-agent nodes    */
   double coplayer_lb, coplayer_ub;            /* utils/heuristics.py:16 (0, 16)               */
   double dpa_offset, dpa_lb, dpa_ub;          /* utils/wrappers.py:6                          */
+  /* Multi-item networks (network_configs/multi_item.yaml: per-item cost lists).  Items are independent
+   * copies of the chain: with n_items = I > 1 the batch holds n_envs*I chains, chain c = env*I + item
+   * (item-minor), so the row-major observation [n_chains][7*F'] IS the concatenation over items
+   * [n_envs][I*7*F'] and likewise for actions; rewards are per chain.  Item 0 uses holding_cost /
+   * backorder_cost above, item i >= 1 uses item_*_cost[i-1].  n_items = 0 is read as 1. */
+  int32_t n_items;
+  int32_t reserved_;
+  double item_holding_cost[SN_MAX_ITEMS - 1][SN_MAX_FACILITIES];
+  double item_backorder_cost[SN_MAX_ITEMS - 1][SN_MAX_FACILITIES];
 } sn_spec;
 
 /* Base-stock policy parameters (utils/heuristics.py:13-33), used by sn_heuristic and by

@@ -30,13 +30,15 @@ constexpr int kObsPerNode = 7;
 constexpr int kStateWords = 40;
 constexpr int kInitWords = 19;
 constexpr int kStatsWords = 16;
+constexpr int kMaxItems = 4;
 
 template <typename T>
 struct DevSpec {
   T target[kF];        // co-player base-stock targets
   T clb, cub;          // co-player clip (utils/heuristics.py:16)
   T off, lb, ub;       // d+a rule (utils/wrappers.py:25-27)
-  double h[kF], b[kF];
+  double h[kMaxItems][kF], b[kMaxItems][kF];   // per item (chain c belongs to item c % n_items)
+  int n_items;
   int slot[kF];        // action column of node k, -1 = co-player
   int pos[kF];         // position of node k's 7 numbers in the observation, -1 = not observed
   int n_obs;
@@ -204,6 +206,12 @@ struct StepOut {
   double hold[kF], back[kF];
 };
 
+// item of the chain `env` (multi-item batches interleave the items, see sn_spec); 0 for single-item
+template <typename T>
+__device__ __forceinline__ int chain_item(const DevSpec<T>& sp, int64_t env) {
+  return sp.n_items > 1 ? (int)((uint32_t)env % (uint32_t)sp.n_items) : 0;
+}
+
 // Orders of all four nodes for this period.  Each depends only on start-of-period quantities
 // (every information lead time is >= 1), so they are computed before the shipment sweep:
 // agent-managed nodes take their action (through the d+a rule of utils/wrappers.py:25-27 when
@@ -231,8 +239,8 @@ __device__ __forceinline__ void env_orders(const Env<T>& e, const DevSpec<T>& sp
 // On a terminal step `e` becomes the *terminal observation view* (envs.py:98-110: no
 // before_action, 5-slot pipelines of which the first four are read, stale latest demand) and is
 // not a valid state any more.
-template <typename T>
-__device__ __forceinline__ void env_step(Env<T>& e, const DevSpec<T>& sp, const T (&q)[kF], T d_next,
+template <bool MULTI, typename T>
+__device__ __forceinline__ void env_step(Env<T>& e, const DevSpec<T>& sp, int item, const T (&q)[kF], T d_next,
                                          bool terminal, StepOut& out) {
   // ---- after_action sweep, upstream first (supplynetwork.py:241-264)
   T U4[kF];   // fifth (oldest) slot of [q, U0, U1, U2, U3] after this period's arrivals
@@ -269,13 +277,24 @@ __device__ __forceinline__ void env_step(Env<T>& e, const DevSpec<T>& sp, const 
 
   // ---- get_cost (supplynetwork.py:285-310): node-list order, c_h and c_b accumulated apart
   double ch = 0.0, cb = 0.0;
+  if (MULTI) {                     // per-chain cost vector (dynamic constant-bank index)
 #pragma unroll
-  for (int k = 0; k < kF; ++k) {
-    const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
-    out.hold[k] = -(double)e.inv[k] * sp.h[k];
-    out.back[k] = -(double)unfk * sp.b[k];
-    ch += out.hold[k];
-    cb += out.back[k];
+    for (int k = 0; k < kF; ++k) {
+      const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
+      out.hold[k] = -(double)e.inv[k] * sp.h[item][k];
+      out.back[k] = -(double)unfk * sp.b[item][k];
+      ch += out.hold[k];
+      cb += out.back[k];
+    }
+  } else {                         // single item: coefficients fold into the multiply as constant operands
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+      const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
+      out.hold[k] = -(double)e.inv[k] * sp.h[0][k];
+      out.back[k] = -(double)unfk * sp.b[0][k];
+      ch += out.hold[k];
+      cb += out.back[k];
+    }
   }
   out.reward = ch + cb;
 

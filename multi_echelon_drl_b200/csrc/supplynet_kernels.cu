@@ -226,7 +226,8 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     const T dn = __ldg(demand_next + env);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
-    env_step(e, sp, q, dn, terminal != 0, so);
+    if (sp.n_items > 1) env_step<true>(e, sp, chain_item(sp, env), q, dn, terminal != 0, so);
+    else env_step<false>(e, sp, 0, q, dn, terminal != 0, so);
     store_state(state, ld, env, e);
     if (out.reward) out.reward[env] = (float)so.reward;
     if (out.reward64) out.reward64[env] = so.reward;
@@ -274,7 +275,7 @@ struct RolloutPtrs {
 #define SN_PRAGMA_UNROLL(n) _Pragma(SN_STR(unroll n))
 constexpr int kRolloutBlock = SN_ROLLOUT_BLOCK;
 
-template <typename T, int POLICY, bool IDENT>
+template <typename T, int POLICY, bool IDENT, bool MULTI>
 __global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
           int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
@@ -303,6 +304,7 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+  const int item = MULTI ? chain_item(sp, envc) : 0;
 
   // software pipeline: inputs of step s+1 are requested before step s is computed
   T a_pre[kF] = {T(0), T(0), T(0), T(0)};
@@ -332,7 +334,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
     StepOut so;
-    env_step(e, sp, q, dn, terminal, so);
+    env_step<MULTI>(e, sp, item, q, dn, terminal, so);
     acc[0] += 1.0;
     acc[1] += so.reward;
 #pragma unroll
@@ -442,6 +444,7 @@ int validate(const sn_spec* s, int dtype) {
                                 "(the reference crashes otherwise, supplynetwork.py:199)");
   if (s->max_episode_steps < 1) return fail(SN_ERR_INVALID, "max_episode_steps=%d", s->max_episode_steps);
   if (s->rule != SN_RULE_A && s->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown rule %d", s->rule);
+  if (s->n_items < 0 || s->n_items > SN_MAX_ITEMS) return fail(SN_ERR_INVALID, "n_items=%d outside 0..%d", s->n_items, SN_MAX_ITEMS);
   if (dtype == SN_I32) {
     for (int k = 0; k < 4; ++k)
       if (!is_integral(s->coplayer_target[k])) return fail(SN_ERR_TYPE, "coplayer_target[%d] must be integral for SN_I32", k);
@@ -459,10 +462,15 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   int lo = 4;
   for (int k = 0; k < 4; ++k) {
     d.target[k] = (T)s->coplayer_target[k];
-    d.h[k] = s->holding_cost[k];
-    d.b[k] = s->backorder_cost[k];
+    d.h[0][k] = s->holding_cost[k];
+    d.b[0][k] = s->backorder_cost[k];
+    for (int i = 1; i < SN_MAX_ITEMS; ++i) {
+      d.h[i][k] = s->item_holding_cost[i - 1][k];
+      d.b[i][k] = s->item_backorder_cost[i - 1][k];
+    }
     d.slot[k] = -1;
   }
+  d.n_items = s->n_items > 1 ? s->n_items : 1;
   for (int i = 0; i < s->n_agents; ++i) {
     d.slot[s->agents[i]] = i;
     lo = s->agents[i] < lo ? s->agents[i] : lo;
@@ -565,8 +573,12 @@ template <typename T, int POLICY, bool IDENT>
 void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
                     void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
                     cudaStream_t st, const void* init, float* obs0) {
-  sn::k_rollout<T, POLICY, IDENT><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
-      d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
+  if (d.n_items > 1)
+    sn::k_rollout<T, POLICY, IDENT, true><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
+        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
+  else
+    sn::k_rollout<T, POLICY, IDENT, false><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
+        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
 }
 
 template <typename T>

@@ -3,14 +3,19 @@
 The reference has no working multi-item behaviour: its multi_item.yaml is a TODO stub, `from_dict`
 ignores `items` and crashes (supplynetwork.py:359-365), and list-valued costs would break `get_cost`
 (supplynetwork.py:299).  Semantics defined here (parity unpinned): I items are I
-independent copies of the chain with per-item cost vectors; the observation is the concatenation
-of the items' observations ([N, I*obs_dim]), the action the concatenation of the items' order
-columns ([N, I*n_agents]) and the reward the sum over items.  Each item is one
-`BatchedSupplyNetwork` (own spec, own state rows) driven by the same kernels.
+independent copies of the chain with per-item cost vectors; the observation of an env is the
+concatenation of its items' observations ([N, I*obs_dim]), the action the concatenation of the items'
+order columns ([N, I*n_agents]) and the reward the sum over items.
+
+Native layout: ONE batch of N*I chains, chain c = env*I + item (item-minor).  The kernels pick the cost
+vector by `c % I` (sn_spec.n_items / item_*_cost), so the row-major tensors they already read and
+write ARE the concatenated ones: obs [N*I, obs_dim] viewed as [N, I*obs_dim], actions likewise.  No
+gather/scatter pass exists; only the reward is reduced over the I adjacent chains of an env.
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from dataclasses import replace
+from typing import Sequence
 
 import torch
 
@@ -18,64 +23,58 @@ from .simulator import BatchedSupplyNetwork
 from .spec import ScenarioSpec
 
 
+def combine_item_specs(specs: Sequence[ScenarioSpec]) -> ScenarioSpec:
+    if not 1 <= len(specs) <= 4:
+        raise ValueError("1..4 items are supported")
+    base = specs[0]
+    for s in specs[1:]:
+        if replace(s, name=base.name, holding_cost=base.holding_cost, backorder_cost=base.backorder_cost) != base:
+            raise ValueError("items may differ in holding/backorder cost only")
+    return replace(base, extra_item_costs=tuple((tuple(s.holding_cost), tuple(s.backorder_cost)) for s in specs[1:]))
+
+
 class MultiItemSupplyNetwork:
     def __init__(self, specs: Sequence[ScenarioSpec], n_envs: int, device="cuda", dtype="int32"):
-        if len(specs) < 1:
-            raise ValueError("need at least one item")
-        if len({(s.agents, s.global_observable, s.max_episode_steps) for s in specs}) != 1:
-            raise ValueError("all items must share agents, observability and episode length")
-        self.items: List[BatchedSupplyNetwork] = [BatchedSupplyNetwork(s, n_envs, device, dtype) for s in specs]
-        it = self.items[0]
-        self.n_items, self.n_envs, self.device = len(specs), n_envs, it.device
-        self.item_obs_dim, self.item_agents = it.obs_dim, it.n_agents
-        self.obs_dim, self.n_agents = self.n_items * it.obs_dim, self.n_items * it.n_agents
-        self.T = it.T
-        self.obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
-        self.reward = torch.zeros((n_envs,), dtype=torch.float32, device=self.device)
-        self._r64 = [torch.zeros((n_envs,), dtype=torch.float64, device=self.device) for _ in specs]
+        self.spec = combine_item_specs(specs)
+        self.n_items, self.n_envs = len(specs), int(n_envs)
+        self.sim = BatchedSupplyNetwork(self.spec, self.n_envs * self.n_items, device, dtype)
+        s = self.sim
+        self.device, self.T = s.device, s.T
+        self.item_obs_dim, self.item_agents = s.obs_dim, s.n_agents
+        self.obs_dim, self.n_agents = self.n_items * s.obs_dim, self.n_items * s.n_agents
+        self.obs = s.obs.view(self.n_envs, self.obs_dim)                       # same memory, concatenated view
+        self._r64 = torch.zeros((self.n_envs * self.n_items,), dtype=torch.float64, device=self.device)
+        self.reward = torch.zeros((self.n_envs,), dtype=torch.float32, device=self.device)
 
     @property
     def period(self):
-        return self.items[0].period
+        return self.sim.period
 
     @property
     def terminal(self):
-        return self.items[0].terminal
+        return self.sim.terminal
 
     def load_episode(self, init, demand):
         """init [n, I, 19], demand [n, I, >=T+1]: per-item streams."""
         init, demand = torch.as_tensor(init), torch.as_tensor(demand)
-        for i, it in enumerate(self.items):
-            it.load_episode(init[:, i], demand[:, i])
-
-    def _gather_obs(self):
-        d = self.item_obs_dim
-        for i, it in enumerate(self.items):
-            self.obs[:, i * d:(i + 1) * d] = it.obs
-        return self.obs
+        n, i = self.n_envs, self.n_items
+        self.sim.load_episode(init.reshape(n * i, init.shape[-1]), demand.reshape(n * i, demand.shape[-1]))
 
     def reset(self):
-        for it in self.items:
-            it.reset()
-        return self._gather_obs()
+        self.sim.reset()
+        return self.obs
 
     def step(self, actions):
+        """actions [n, I*n_agents] (item-major columns) -> (obs [n, I*obs_dim], reward [n], done)."""
         actions = torch.as_tensor(actions)
         if tuple(actions.shape) != (self.n_envs, self.n_agents):
             raise ValueError(f"actions must have shape {(self.n_envs, self.n_agents)}, got {tuple(actions.shape)}")
-        a = self.item_agents
-        done = False
-        for i, it in enumerate(self.items):
-            _, _, done = it.step(actions[:, i * a:(i + 1) * a], reward64_out=self._r64[i])
-        total = self._r64[0].clone()
-        for r in self._r64[1:]:
-            total += r
-        self.reward.copy_(total)                 # summed in double, rounded once like the single-item reward
-        return self._gather_obs(), self.reward, done
+        a = actions.reshape(self.n_envs * self.n_items, self.item_agents)     # a view when contiguous
+        _, _, done = self.sim.step(a, reward64_out=self._r64)
+        # summed over the items of an env in double, rounded once like the single-item reward
+        self.reward.copy_(self._r64.view(self.n_envs, self.n_items).sum(1))
+        return self.obs, self.reward, done
 
     @property
     def ep_return(self):
-        tot = self.items[0].ep_return.clone()
-        for it in self.items[1:]:
-            tot += it.ep_return
-        return tot
+        return self.sim.ep_return.view(self.n_envs, self.n_items).sum(1)

@@ -56,6 +56,9 @@ class ScenarioSpec:
     fixed_inventory: int = 12
     fixed_shipments: Tuple[int, int] = (4, 4)
     fixed_sales_orders: Tuple[int, int] = (4, 4)
+    # multi-item: cost vectors of items 1.. (item 0 uses holding_cost / backorder_cost); chains are
+    # interleaved item-minor, so obs/action rows of one env are the concatenation over its items
+    extra_item_costs: Tuple[Tuple[Tuple[float, ...], Tuple[float, ...]], ...] = ()
 
     def __post_init__(self):
         ag = tuple(node_index(a) for a in self.agents)
@@ -69,6 +72,10 @@ class ScenarioSpec:
             raise ValueError(f"ordering rule must be 'a' or 'd+a', got {self.rule!r}")
 
     # ------------------------------------------------------------------ derived
+    @property
+    def n_items(self) -> int:
+        return 1 + len(self.extra_item_costs)
+
     @property
     def n_agents(self) -> int:
         return len(self.agents)
@@ -100,6 +107,13 @@ class ScenarioSpec:
         s.rule = _lib.SN_RULE_D_PLUS_A if self.rule == "d+a" else _lib.SN_RULE_A
         s.coplayer_lb, s.coplayer_ub = float(self.coplayer_lb), float(self.coplayer_ub)
         s.dpa_offset, s.dpa_lb, s.dpa_ub = float(self.dpa_offset), float(self.dpa_lb), float(self.dpa_ub)
+        if len(self.extra_item_costs) > 3:
+            raise ValueError("at most 4 items")
+        s.n_items = self.n_items
+        for i, (h, b) in enumerate(self.extra_item_costs):
+            for k in range(4):
+                s.item_holding_cost[i][k] = float(h[k])
+                s.item_backorder_cost[i][k] = float(b[k])
         return s
 
 

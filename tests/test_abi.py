@@ -31,21 +31,22 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"libsupplynet.so does not export {name}"
     assert set(_lib.SIGNATURES) == declared, "ctypes binding and header disagree on the entry points"
-    assert lib.sn_abi_version() == 1
+    assert lib.sn_abi_version() == 2
 
 
 def test_struct_layout_matches_header(tmp_path):
     from multi_echelon_drl_b200 import _lib
     src = tmp_path / "layout.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "supplynet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "supplynet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(sn_spec),offsetof(sn_spec,agents),offsetof(sn_spec,holding_cost),offsetof(sn_spec,dpa_ub),'
-                   'sizeof(sn_policy),offsetof(sn_policy,rule),offsetof(sn_policy,lb));return 0;}\n')
+                   'sizeof(sn_policy),offsetof(sn_policy,rule),offsetof(sn_policy,lb),offsetof(sn_spec,n_items),'
+                   'offsetof(sn_spec,item_backorder_cost));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     S, P = _lib.SnSpec, _lib.SnPolicy
     assert got == [C.sizeof(S), S.agents.offset, S.holding_cost.offset, S.dpa_ub.offset, C.sizeof(P), P.rule.offset,
-                   P.lb.offset]
+                   P.lb.offset, S.n_items.offset, S.item_backorder_cost.offset]
 
 
 def test_spec_validation_and_error_mapping(lib):
