@@ -136,12 +136,13 @@ def run_reference(args):
     OC.load()
     vals = []
     per_step_budget = min(20.0, 120.0 / max(1, args.steps + args.warmup))
+    per_step_budget = float(os.environ.get("BENCH_CPU_BUDGET_S", per_step_budget))     # tests shrink the sample
     for i in range(args.warmup + args.steps):
         v, sample = cpu_port_throughput(init, demand, actions, threads, per_step_budget)
         if i >= args.warmup:
             vals.append(v)
     v = float(np.mean(vals))
-    v1, _ = cpu_port_throughput(init, demand, actions, 1, 3.0)
+    v1, _ = cpu_port_throughput(init, demand, actions, 1, min(3.0, per_step_budget))
     line = {
         "impl": "reference", "metric": "env-steps/sec (batched beer game)", "value": v, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N_ENVS * T / v * 1e3,
