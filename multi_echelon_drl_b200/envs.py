@@ -7,12 +7,16 @@ returning a batched `SupplyNetVecEnv` instead of one gym env.
                                                        n_envs=65536, device="cuda")
 
 Extra keyword arguments (n_envs, device, dtype, seed, episode_source, output) select the batch; every
-reference argument keeps its meaning.  `env_mode="test"` needs the demand sample files the reference
+reference argument keeps its meaning.  Without `n_envs` the factories return a single gym-style env
+(`BeerGameEnv`, the duck type of the reference's InventoryManagementEnvMultiPlayer), exactly like the
+reference; with `n_envs=N` they return the batched `SupplyNetVecEnv`.  `env_mode="test"` needs the demand sample files the reference
 loads from ./data/deepbeerinventory/*.npy, which are not part of the reference repo either.
 """
 from __future__ import annotations
 
+from . import spaces
 from . import spec as _spec
+from .gym_env import BeerGameEnv
 from .vec_env import SupplyNetVecEnv
 
 
@@ -24,32 +28,44 @@ def _check_mode(env_mode):
         raise ValueError(env_mode)
 
 
+def _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space):
+    if len(sp.agents) > 1 and not box_action_space:
+        raise ValueError("length of agent_managed_facilities >= 1, only box_action_space is allowed. Please specify"
+                         "box_action_space=True")                                            # envs.py:175-179
+    if n_envs is None:             # the reference's return type: one gym-style env
+        space = spaces.Box(sp.action_low, sp.action_high, shape=(sp.n_agents,)) if box_action_space else \
+            spaces.Discrete(int(sp.action_high) + 1)
+        return BeerGameEnv(sp, device, dtype or "int32", space, seed)
+    return SupplyNetVecEnv(sp, n_envs, device, dtype or "float32", 0 if seed is None else seed, episode_source, output,
+                           bool(box_action_space))
+
+
 def make_beer_game_uniform_multi_facility(global_observable=False, agent_managed_facilities=None,
                                           max_episode_steps=100, return_dict=False, random_init=True,
-                                          env_mode="train", box_action_space=False, *, n_envs=1, device="cuda",
-                                          dtype="float32", seed=0, episode_source="device", output="torch"):
+                                          env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
+                                          dtype=None, seed=None, episode_source="device", output="torch"):
     """The complex scenario (envs.py:289-414): demand U{0..8}, h=0.5, b=1, co-player targets 19/20/20/14."""
     _check_mode(env_mode)
     if return_dict:
-        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered by the batched env")
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
-    return SupplyNetVecEnv(sp, n_envs, device, dtype, seed, episode_source, output, bool(box_action_space))
+    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
 
 
 def make_beer_game_normal_multi_facility(global_observable=False, agent_managed_facilities=None,
                                          max_episode_steps=100, return_dict=False, random_init=False,
-                                         env_mode="train", box_action_space=False, *, n_envs=1, device="cuda",
-                                         dtype="float32", seed=0, episode_source="device", output="torch"):
+                                         env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
+                                         dtype=None, seed=None, episode_source="device", output="torch"):
     """The basic scenario (envs.py:163-286): demand round(max(N(10,2),0)), h=(1,.75,.5,.25), b=(10,0,0,0)."""
     _check_mode(env_mode)
     if return_dict:
-        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered by the batched env")
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.normal_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
-    return SupplyNetVecEnv(sp, n_envs, device, dtype, seed, episode_source, output, bool(box_action_space))
+    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
 
 
 def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game", max_period=35, return_dict=False,
-                   random_init=False, seed=None, *, n_envs=1, device="cuda", dtype="int32",
+                   random_init=False, seed=None, *, n_envs=None, device="cuda", dtype="int32",
                    episode_source="numpy_bulk", output="torch"):
     """The classic beer game (envs.py:501-596): demand 4,4,4,4,8,8,...; MultiDiscrete([17]*F) actions.
     `random_init` is accepted and ignored exactly as in the reference (never passed to Arc, Q16)."""
@@ -60,5 +76,10 @@ def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game
     if return_dict:
         raise NotImplementedError("return_dict=True is not offered by the batched env")
     sp = _spec.classic_spec(agent_managed_facilities, max_period, demand_type)
+    if n_envs is None:
+        if seed:
+            import numpy as np
+            np.random.seed(seed)                     # envs.py:511-512
+        return BeerGameEnv(sp, device, dtype, spaces.MultiDiscrete([17] * sp.n_agents))
     return SupplyNetVecEnv(sp, n_envs, device, dtype, 0 if seed is None else seed, episode_source, output,
                            box_action_space=False, multi_discrete=True)
