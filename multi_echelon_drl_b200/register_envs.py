@@ -59,7 +59,10 @@ def registered_ids():
     return sorted(_REGISTRY)
 
 
-def make(env_id: str, n_envs: int = 1, **batch_kwargs):
+def make(env_id: str, n_envs=None, **batch_kwargs):
+    """`make(id)` -> one gym-style env like `gym.make(id)` in the reference (episode length 100 =
+    the registry's max_episode_steps, so no TimeLimit wrapper is needed); `make(id, n_envs=N)` -> the
+    batched VecEnv."""
     if not _REGISTRY:
         register_envs()
     if env_id not in _REGISTRY:

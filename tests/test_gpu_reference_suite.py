@@ -107,3 +107,22 @@ def test_single_env_errors_and_sn_view_match_reference_behaviour():
                                                 agent_managed_facilities=["retailer", "wholesaler", "distributor", "manufacturer"])
     np.random.seed(12345)
     assert np.array_equal(env.reset(), z["uniform_12345_obs0"])
+
+
+def test_registry_make_without_batch_returns_single_env_incl_dplusa():
+    """gym.make(id) counterpart: single env; the DPlusA ids apply the d+a rule (register_envs.py:8-15)."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from helpers import oracle_rollout
+    env = R.make("BeerGameUniformMultiFacilityDPlusA-v0", seed=5)
+    assert env.observation_space.shape == (28,) and env.max_episode_steps == 100 and env.spec.rule == "d+a"
+    obs0 = env.reset()
+    init, demand = env.sim.init[:, :1].t().cpu().numpy(), env.sim.demand[:, :1].t().cpu().numpy()
+    acts = np.random.RandomState(0).randint(0, 17, (100, 1, 4))
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), False, "d+a", 100, init, demand, acts)
+    assert np.array_equal(obs0, ref["obs0"][0])
+    for t in range(100):
+        obs, rew, done, _ = env.step(acts[t, 0])
+        assert np.array_equal(obs, ref["obs"][t, 0]) and rew == ref["rew"][t, 0]
+    assert done
+    single = R.make("BeerGameNormalWholesalerFullInfo-v0")
+    assert single.reset().shape == (28,) and single.action_space.shape == (1,)
