@@ -207,11 +207,13 @@ def run_native(args):
         if record:
             e1.record()
             k_events.append((e0, e1))
-        if world > 1:
-            # the path's only collective: episode statistics (16 doubles).  Issued asynchronously on
-            # NCCL's stream with two alternating buffers so that it overlaps the next episode's kernel.
-            step_no[0] += 1
-            buf = stats_bufs[step_no[0] % 2]
+        step_no[0] += 1
+        if world > 1 and step_no[0] % args.stats_interval == 0:
+            # the path's only collective: the statistics vector (16 doubles) that the kernels keep
+            # accumulating on every rank, all-reduced once per log interval (every --stats-interval
+            # episodes, and once more at the end of the timed region).  Issued asynchronously on NCCL's
+            # stream with two alternating buffers so that it overlaps the next episode's kernel.
+            buf = stats_bufs[(step_no[0] // args.stats_interval) % 2]
             while len(pending) >= 2:
                 pending.pop(0).wait()
             buf.copy_(sim.stats)
@@ -229,6 +231,9 @@ def run_native(args):
         s.record()
         for _ in range(steps):
             fn(**kw) if kw else fn()
+        if world > 1 and fn is device_step:           # end-of-interval reduction of the accumulated statistics
+            stats_bufs[0].copy_(sim.stats)
+            pending.append(dist.all_reduce(stats_bufs[0], async_op=True))
         while pending:
             pending.pop(0).wait()
         e.record()
@@ -284,7 +289,7 @@ def run_native(args):
                                    f"{n} envs/GPU x {T} periods fixed-action parity rollout, full trajectory out",
                        "envs_per_gpu": n, "periods": T, "step": "one sn_episode launch (in-kernel reset + 100 periods, 1 episode of the batch)",
                        "l2": "inputs+outputs ~0.9 GB per step >> 126 MB L2, no flush needed",
-                       "parallelism": f"env-sharded x{world}, stats all-reduce only"},
+                       "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of the 16-double statistics vector every {args.stats_interval} episodes"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks},
@@ -445,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default: BASELINE config 2)")
+    ap.add_argument("--stats-interval", type=int, default=10, help="episodes between statistics all-reduces (N>1)")
     ap.add_argument("--e2e-chunks", type=int, default=5, help="period spans of the pipelined host path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
