@@ -54,8 +54,15 @@ class LazyInfos(Sequence):
                 "TimeLimit.truncated": False}
 
 
-class SupplyNetVecEnv:
-    """VecEnv duck type (num_envs, observation_space, action_space, reset, step_async, step_wait, step,
+try:                                       # pragma: no cover - stable-baselines3 is not installed in this image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase      # type: ignore
+except Exception:                          # noqa: BLE001
+    _VecEnvBase = object                   # duck type only
+
+
+class SupplyNetVecEnv(_VecEnvBase):
+    """VecEnv duck type; a real `stable_baselines3.common.vec_env.VecEnv` subclass when SB3 is importable, so
+    that SB3 algorithms accept it without re-wrapping (use output="numpy" for them).  VecEnv duck type (num_envs, observation_space, action_space, reset, step_async, step_wait, step,
     close, seed, get_attr, set_attr, env_method, env_is_wrapped)."""
 
     metadata = {"render.modes": []}
@@ -72,6 +79,7 @@ class SupplyNetVecEnv:
                              "Please specify box_action_space=True")                    # envs.py:175-179
         self.spec = spec
         self.num_envs = int(n_envs)
+        self.render_mode = None
         self.sim = BatchedSupplyNetwork(spec, n_envs, device, dtype)
         self.device = self.sim.device
         self.output = output
