@@ -92,6 +92,8 @@ class SupplyNetVecEnv(_VecEnvBase):
         else:
             self.action_space = spaces.Discrete(int(spec.action_high) + 1)
         self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(spec.obs_dim,))
+        if _VecEnvBase is not object:      # pragma: no cover - let SB3 set up its own bookkeeping (reset_infos, ...)
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self._actions = None
         self._t0 = time.time()
         self.episodes_done = 0
