@@ -20,12 +20,18 @@ from .gym_env import BeerGameEnv
 from .vec_env import SupplyNetVecEnv
 
 
-def _check_mode(env_mode):
-    if env_mode == "test":
-        raise FileNotFoundError("env_mode='test' reads ./data/deepbeerinventory/*.npy, which the reference "
-                                "repository does not ship; pass demands through load_episode instead")
-    if env_mode != "train":
+def _apply_mode(sp, env_mode, data_path):
+    """env_mode='test' replays demand rows from a sample file (envs.py:183-185, 309-311); the reference
+    repository does not ship those .npy files, so the path must exist here too."""
+    import os
+    from dataclasses import replace
+    if env_mode == "train":
+        return sp
+    if env_mode != "test":
         raise ValueError(env_mode)
+    if not os.path.isfile(data_path):
+        raise FileNotFoundError(f"env_mode='test' needs the demand sample file {data_path} (not part of the reference repo)")
+    return replace(sp, demand_pattern="samples", demand_path=data_path)
 
 
 def _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space):
@@ -45,10 +51,12 @@ def make_beer_game_uniform_multi_facility(global_observable=False, agent_managed
                                           env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
                                           dtype=None, seed=None, episode_source="device", output="torch"):
     """The complex scenario (envs.py:289-414): demand U{0..8}, h=0.5, b=1, co-player targets 19/20/20/14."""
-    _check_mode(env_mode)
     if return_dict:
         raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    sp = _apply_mode(sp, env_mode, "./data/deepbeerinventory/demandTs0-9.npy")
+    if sp.demand_pattern == "samples" and episode_source == "device":
+        episode_source = "numpy_bulk"
     return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
 
 
@@ -57,10 +65,12 @@ def make_beer_game_normal_multi_facility(global_observable=False, agent_managed_
                                          env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
                                          dtype=None, seed=None, episode_source="device", output="torch"):
     """The basic scenario (envs.py:163-286): demand round(max(N(10,2),0)), h=(1,.75,.5,.25), b=(10,0,0,0)."""
-    _check_mode(env_mode)
     if return_dict:
         raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.normal_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    sp = _apply_mode(sp, env_mode, "./data/deepbeerinventory/demandTs1-10-2.npy")
+    if sp.demand_pattern == "samples" and episode_source == "device":
+        episode_source = "numpy_bulk"
     return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
 
 

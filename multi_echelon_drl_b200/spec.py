@@ -48,8 +48,9 @@ class ScenarioSpec:
     action_low: float = 0.0                          # action space bounds (envs.py:269-272, 397-400)
     action_high: float = 16.0
     # demand / initial-state generators (host side, utils/demands.py + Arc/Node.reset)
-    demand_pattern: str = "uniform"                  # 'uniform' | 'normal' | 'classic_beer_game'
+    demand_pattern: str = "uniform"                  # 'uniform' | 'normal' | 'classic_beer_game' | 'samples'
     demand_params: Tuple[float, float] = (0, 8)      # (low, high) or (mean, sd)
+    demand_path: Optional[str] = None                # .npy of demand rows for 'samples' (utils/demands.py:26-29)
     random_init: bool = True
     init_inventory: Tuple[int, int] = (0, 25)        # randint(lo, hi) if random_init else lo
     init_pipeline: Tuple[int, int] = (0, 9)          # shipments and sales orders alike

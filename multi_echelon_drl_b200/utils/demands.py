@@ -70,16 +70,26 @@ class Demand:
             return np.round(np.maximum(self.mean + self.sd * rs.randn(n, self.size), 0)).astype(int)
         if p == "classic_beer_game":
             return np.broadcast_to(np.array([4] * 4 + [8] * (self.size - 4)), (n, self.size)).copy()
-        rows = [self.draw(rs) for _ in range(n)]
+        rows = [self.draw(rs)[: self.size] for _ in range(n)]
         return np.stack(rows)
 
 
+_SAMPLE_DEMANDS = {}
+
+
 def demand_for(spec: ScenarioSpec) -> Demand:
+    if spec.demand_pattern == "samples":       # one object per file: its row pointer advances across resets
+        key = spec.demand_path
+        if key not in _SAMPLE_DEMANDS:
+            _SAMPLE_DEMANDS[key] = Demand("samples", data_path=spec.demand_path, size=spec.max_episode_steps)
+        return _SAMPLE_DEMANDS[key]
     a, b = spec.demand_params
     if spec.demand_pattern == "uniform":
         return Demand("uniform", low=int(a), high=int(b), size=spec.max_episode_steps)
     if spec.demand_pattern == "normal":
         return Demand("normal", mean=a, sd=b, size=spec.max_episode_steps)
+    if spec.demand_pattern == "samples":
+        return Demand("samples", data_path=spec.demand_path, size=spec.max_episode_steps)
     return Demand(spec.demand_pattern, size=spec.max_episode_steps)
 
 

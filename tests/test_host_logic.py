@@ -212,3 +212,26 @@ def test_hge_rate_schedule_and_single_coin():
     assert used is False and (a == 0).all()
     a, mask = hge_predict(pol, H(), obs, obs, 1.0, per_env=True)
     assert mask.all() and (a == 7).all()
+
+
+def test_samples_demand_pattern_cycles_rows(tmp_path):
+    """Demand('samples', data_path=...) (utils/demands.py:26-29,54-56): rows of the file, cyclically."""
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.utils.demands import Demand, bulk_episode_inputs, seeded_episode_inputs
+    from dataclasses import replace
+    rows = np.arange(3 * 103).reshape(3, 103) % 9
+    path = str(tmp_path / "demand.npy")
+    np.save(path, rows)
+    d = Demand("samples", data_path=path, size=100)
+    got = [d.draw(None) for _ in range(4)]
+    assert np.array_equal(got[0], rows[0]) and np.array_equal(got[2], rows[2]) and np.array_equal(got[3], rows[0])
+    spec = replace(uniform_spec(), demand_pattern="samples", demand_path=path)
+    _, dem = bulk_episode_inputs(spec, 4, np.random.RandomState(0))
+    assert np.array_equal(dem[0], rows[0]) and np.array_equal(dem[3], rows[0]) and dem.shape == (4, 103)
+    _, dem2 = seeded_episode_inputs(spec, [1])
+    assert np.array_equal(dem2[0], rows[1])                  # the file pointer keeps advancing across resets
+    from multi_echelon_drl_b200.envs import make_beer_game_uniform_multi_facility
+    with pytest.raises(FileNotFoundError):
+        make_beer_game_uniform_multi_facility(env_mode="test", box_action_space=True)
+    with pytest.raises(ValueError):
+        make_beer_game_uniform_multi_facility(env_mode="validate", box_action_space=True)
