@@ -27,13 +27,15 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 2
+#define SN_ABI_VERSION 3
 
 #define SN_MAX_FACILITIES 4
 #define SN_MAX_ITEMS 4
 #define SN_OBS_PER_FACILITY 7   /* supplynetwork.py:151-169 */
 #define SN_STATE_WORDS 40       /* 28 observable + 12 hidden words per env */
 #define SN_INIT_WORDS 19        /* inv[4], sales orders (2,2,2,1), shipments (2,2,2,2) */
+#define SN_GEN_STATE_WORDS 57   /* chains with other lead times: 28 + 4x3 order slips + 4x4 shipments + 1 */
+#define SN_GEN_INIT_WORDS 36    /* inv[4]; so[k][0..3] at 4+4k; sh[k][0..3] at 20+4k (unused slots 0)      */
 #define SN_STATS_WORDS 16
 
 enum { SN_I32 = 0, SN_F32 = 1, SN_F64 = 2 };
@@ -58,8 +60,8 @@ enum {
  * arc whose customer is node k. */
 typedef struct sn_spec {
   int32_t n_facilities;                       /* must be 4                                    */
-  int32_t info_leadtime[SN_MAX_FACILITIES];   /* must be 2,2,2,1 (envs.py:355-392)            */
-  int32_t ship_leadtime[SN_MAX_FACILITIES];   /* must be 2,2,2,2                              */
+  int32_t info_leadtime[SN_MAX_FACILITIES];   /* Arc.information_leadtime, 1..4; beer game 2,2,2,1 */
+  int32_t ship_leadtime[SN_MAX_FACILITIES];   /* Arc.shipment_leadtime, 1..4, info+ship <= 5; 2,2,2,2 */
   int32_t n_agents;                           /* 1..4                                         */
   int32_t agents[SN_MAX_FACILITIES];          /* node index per action column, caller order   */
                                               /* (supplynetwork.py:217); contiguous set       */
@@ -102,14 +104,20 @@ int32_t sn_obs_dim(const sn_spec* spec);
  * supplynetwork.py:22-56; rejects non-contiguous agent sets that crash the reference at :199). */
 int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype);
 
+/* Rows of the `state` / `init` buffers for this spec: SN_STATE_WORDS / SN_INIT_WORDS for the beer game's
+ * lead times (tuned kernels), SN_GEN_STATE_WORDS / SN_GEN_INIT_WORDS for any other supported lead times
+ * (generic kernels, network_components.py:108-168 with Arc(information_leadtime, shipment_leadtime)). */
+int32_t sn_state_words(const sn_spec* spec);
+int32_t sn_init_words(const sn_spec* spec);
+
 /* reset — replaces InventoryManagementEnvMultiPlayer.reset (envs.py:64-80):
  * SupplyNetwork.reset (supplynetwork.py:94-105; Arc.reset network_components.py:138-168,
  * Node.reset :293-319) followed by before_action(0) (supplynetwork.py:182-210).
- *   init      device, dtype [SN_INIT_WORDS][ld]: inv[0..3]; sales orders so[k][j] for k=0..3
+ *   init      device, dtype [sn_init_words(spec)][ld]: inv[0..3]; sales orders so[k][j] for k=0..3
  *             (j < info_leadtime[k], j = periods-1 until the supplier sees it); shipments
  *             sh[k][j] for k=0..3 (j = periods-1 until arrival)
  *   demand0   device, dtype [ld]: demand of period 0 (Node.reset :317-319)
- *   state     device, dtype [SN_STATE_WORDS][ld] (out)
+ *   state     device, dtype [sn_state_words(spec)][ld] (out)
  *   obs       device, float [n_envs][obs_dim] row-major (out, may be NULL) */
 int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
                  const void* init, const void* demand0, void* state, float* obs, void* stream);

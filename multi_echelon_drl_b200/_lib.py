@@ -16,7 +16,7 @@ SN_RULE_A, SN_RULE_D_PLUS_A = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SnSpec(C.Structure):
@@ -61,6 +61,8 @@ SIGNATURES = {
     "sn_last_error": (C.c_char_p, []),
     "sn_obs_dim": (_I32, [C.POINTER(SnSpec)]),
     "sn_spec_validate": (_I32, [C.POINTER(SnSpec), _I32]),
+    "sn_state_words": (_I32, [C.POINTER(SnSpec)]),
+    "sn_init_words": (_I32, [C.POINTER(SnSpec)]),
     "sn_reset": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P, _P, _P]),
     "sn_step": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_observe": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P]),

@@ -39,6 +39,7 @@ struct DevSpec {
   T off, lb, ub;       // d+a rule (utils/wrappers.py:25-27)
   double h[kMaxItems][kF], b[kMaxItems][kF];   // per item (chain c belongs to item c % n_items)
   int n_items;
+  int li[kF], ls[kF];  // information / shipment lead time of arc k (generic path, supplynet_generic.cuh)
   int slot[kF];        // action column of node k, -1 = co-player
   int pos[kF];         // position of node k's 7 numbers in the observation, -1 = not observed
   int n_obs;
@@ -148,8 +149,8 @@ __device__ __forceinline__ void env_reset(Env<T>& e, const T (&in)[kInitWords], 
 // operand is a fixed register.  A co-player with index < first agent has already ordered inside
 // before_action when the reference observes it, so (on non-terminal observations) its pipeline
 // shows [its order, U0, U1, U2] (5-slot list, first four read).
-template <int K, typename T>
-__device__ __forceinline__ void node_view(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float (&v)[7]) {
+template <int K, typename T, typename E>
+__device__ __forceinline__ void node_view(const E& e, const DevSpec<T>& sp, bool terminal, float (&v)[7]) {
   T u0 = e.U[K][0], u1 = e.U[K][1], u2 = e.U[K][2], u3 = e.U[K][3];
   const T unf = e.unfilled(K);
   if (K < kF - 1 && K < sp.lo && !terminal) {
@@ -164,8 +165,8 @@ __device__ __forceinline__ void node_view(const Env<T>& e, const DevSpec<T>& sp,
 // to `dst` (this env's row, shared or global memory).  Node K lands at dst + 7*pos[K]: the position
 // is a memory offset, never a register select.  IDENT = all four nodes in chain order (the
 // centralized / full-information layout): 28 floats as seven 16-byte stores.
-template <bool IDENT, typename T>
-__device__ __forceinline__ void emit_obs(const Env<T>& e, const DevSpec<T>& sp, bool terminal, float* dst) {
+template <bool IDENT, typename T, typename E>
+__device__ __forceinline__ void emit_obs(const E& e, const DevSpec<T>& sp, bool terminal, float* dst) {
   if (IDENT) {
     float o[28];
     { float v[7]; node_view<0>(e, sp, terminal, v);
@@ -217,8 +218,8 @@ __device__ __forceinline__ int chain_item(const DevSpec<T>& sp, int64_t env) {
 // agent-managed nodes take their action (through the d+a rule of utils/wrappers.py:25-27 when
 // selected), the others their own base-stock policy (network_components.py:361-366).
 //   a[k]  action of NODE k (already gathered from its action column); ignored for co-players
-template <bool IDENT, typename T>
-__device__ __forceinline__ void env_orders(const Env<T>& e, const DevSpec<T>& sp, const T (&a)[kF], T (&q)[kF]) {
+template <bool IDENT, typename T, typename E>
+__device__ __forceinline__ void env_orders(const E& e, const DevSpec<T>& sp, const T (&a)[kF], T (&q)[kF]) {
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     T x;

@@ -1,0 +1,176 @@
+// supplynet_generic.cuh — the same recurrence for serial chains with ARBITRARY per-arc lead times
+// (first step: Arc(information_leadtime, shipment_leadtime) other than the beer game's
+// 2,2,2,1 / 2,2,2,2).  The tuned `Env<T>` of supplynet_core.cuh hard-wires those; `GEnv<T>` keeps up to
+// 3 in-flight order slips and 4 shipment slots per arc and takes the lead times from the spec at run time
+// (all positions are resolved with uniform selects over unrolled slots: registers only, no local memory).
+//
+// Supported: information and shipment lead times in 1..4 with info + shipment <= 5 per arc.  Beyond that
+// the reference itself fails its on_order == sum(unreceived) assertion at reset (supplynetwork.py:159-160),
+// because Arc.reset keeps only five pipeline slots (network_components.py:168).
+//
+// State word map of the generic path ([SN_GEN_STATE_WORDS = 57][ld]):
+//   0..27   observation words exactly as in supplynet_core.cuh
+//   28+3k+j info[k][j]   order slip of arc k reaching its supplier after j+1 more before_actions (j < Li-1)
+//   40+4k+j ship[k][j]   shipment on arc k arriving after j+1 more sweeps (j < Ls)
+//   56      B[3]
+// Init words ([SN_GEN_INIT_WORDS = 36][ld]): inv[4]; so[k][j] at 4+4k+j; sh[k][j] at 20+4k+j (unused = 0).
+#pragma once
+#include "supplynet_core.cuh"
+
+namespace sn {
+
+constexpr int kGI = 3;                                   // live slips per arc after before_action (Li - 1 <= 3)
+constexpr int kGS = 4;                                   // shipment slots per arc
+constexpr int kGStateWords = 28 + kF * kGI + kF * kGS + 1;   // 57
+constexpr int kGInitWords = 4 + 4 * kF + 4 * kF;             // 36
+
+template <typename T>
+struct GEnv {
+  T inv[kF], lat[kF], U[kF][4], B[kF], info[kF][kGI], ship[kF][kGS], unf_ind;
+  __device__ __forceinline__ T unfilled(int k) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+};
+
+template <typename T>
+__device__ __forceinline__ void genv_from_words(GEnv<T>& e, const T (&w)[kGStateWords]) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    e.inv[k] = w[7 * k];
+    if (k == 0) e.unf_ind = w[1]; else e.B[k - 1] = w[7 * k + 1];
+    e.lat[k] = w[7 * k + 2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e.U[k][j] = w[7 * k + 3 + j];
+#pragma unroll
+    for (int j = 0; j < kGI; ++j) e.info[k][j] = w[28 + kGI * k + j];
+#pragma unroll
+    for (int j = 0; j < kGS; ++j) e.ship[k][j] = w[40 + kGS * k + j];
+  }
+  e.B[3] = w[56];
+}
+
+template <typename T>
+__device__ __forceinline__ void genv_to_words(const GEnv<T>& e, T (&w)[kGStateWords]) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    w[7 * k] = e.inv[k];
+    w[7 * k + 1] = (k == 0) ? e.unf_ind : e.B[k - 1];
+    w[7 * k + 2] = e.lat[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[7 * k + 3 + j] = e.U[k][j];
+#pragma unroll
+    for (int j = 0; j < kGI; ++j) w[28 + kGI * k + j] = e.info[k][j];
+#pragma unroll
+    for (int j = 0; j < kGS; ++j) w[40 + kGS * k + j] = e.ship[k][j];
+  }
+  w[56] = e.B[3];
+}
+
+// Arc.reset / Node.reset + before_action(0) for run-time lead times (network_components.py:138-168).
+template <typename T>
+__device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, const T (&in)[kGInitWords], T d0) {
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    const int li = sp.li[k], ls = sp.ls[k];
+    T so[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      so[j] = (j < li) ? in[4 + 4 * k + j] : T(0);
+      sh[j] = (j < ls) ? in[20 + 4 * k + j] : T(0);
+    }
+    e.inv[k] = in[k];
+    // ([0]*4 + shipments + sales_orders)[::-1][:5]: newest slip first, then shipments latest first
+    T seq[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      T v = T(0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (li - 1 - i == j) v = so[j];
+        if (i >= li && ls - 1 - (i - li) == j) v = sh[j];
+      }
+      seq[i] = v;
+    }
+    // before_action(0): the list loses its last slot into its neighbour; so[0] reaches the supplier
+    e.U[k][0] = seq[0]; e.U[k][1] = seq[1]; e.U[k][2] = seq[2]; e.U[k][3] = seq[3] + seq[4];
+    e.B[k] = so[0];
+    if (k < 3) e.lat[k + 1] = so[0];
+#pragma unroll
+    for (int j = 0; j < kGI; ++j) e.info[k][j] = so[j + 1];        // already 0 beyond li
+#pragma unroll
+    for (int j = 0; j < kGS; ++j) e.ship[k][j] = sh[j];
+  }
+  e.unf_ind = T(0);
+  e.lat[0] = d0;
+}
+
+// One period; same algebra as env_step with run-time pipeline lengths.
+template <typename T>
+__device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, const T (&q)[kF], T d_next, bool terminal,
+                                          StepOut& out) {
+  T U4[kF];
+#pragma unroll
+  for (int k = kF - 1; k >= 0; --k) {
+    T u[5] = {q[k], e.U[k][0], e.U[k][1], e.U[k][2], e.U[k][3]};
+    const T arr = e.ship[k][0];
+#pragma unroll
+    for (int j = 0; j < kGS - 1; ++j) e.ship[k][j] = e.ship[k][j + 1];
+    e.ship[k][kGS - 1] = T(0);
+    e.inv[k] = e.inv[k] + arr;
+    T rem = arr;
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      const T f = tmin(u[i], rem);
+      u[i] = u[i] - f;
+      rem = rem - f;
+    }
+    T s;
+    if (k == kF - 1) {
+      s = e.B[k];
+    } else {
+      s = tmin(e.inv[k + 1], e.B[k]);
+      e.inv[k + 1] = e.inv[k + 1] - s;
+    }
+    const int ls = sp.ls[k];
+#pragma unroll
+    for (int j = 0; j < kGS; ++j)
+      if (j == ls - 1) e.ship[k][j] = s;                          // Shipment(quantity, shipment_leadtime)
+    e.B[k] = e.B[k] - s;
+    e.U[k][0] = u[0]; e.U[k][1] = u[1]; e.U[k][2] = u[2]; e.U[k][3] = u[3];
+    U4[k] = u[4];
+  }
+  const T tot = e.lat[0] + e.unf_ind;
+  const T sold = tmax(T(0), tmin(e.inv[0], tot));
+  e.inv[0] = e.inv[0] - sold;
+  e.unf_ind = tot - sold;
+
+  double ch = 0.0, cb = 0.0;
+#pragma unroll
+  for (int k = 0; k < kF; ++k) {
+    const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
+    out.hold[k] = -(double)e.inv[k] * sp.h[0][k];
+    out.back[k] = -(double)unfk * sp.b[0][k];
+    ch += out.hold[k];
+    cb += out.back[k];
+  }
+  out.reward = ch + cb;
+
+  e.lat[0] = d_next;
+  if (!terminal) {
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+      const int li = sp.li[k];
+      // Order(q, 0, info_leadtime): with lead time 1 this period's order is what arrives now
+      const T arrived = (li == 1) ? q[k] : e.info[k][0];
+#pragma unroll
+      for (int j = 0; j < kGI - 1; ++j) e.info[k][j] = e.info[k][j + 1];
+      e.info[k][kGI - 1] = T(0);
+#pragma unroll
+      for (int j = 0; j < kGI; ++j)
+        if (j == li - 2) e.info[k][j] = q[k];
+      if (k < 3) e.lat[k + 1] = arrived;
+      e.B[k] = e.B[k] + arrived;
+      e.U[k][3] = e.U[k][3] + U4[k];
+    }
+  }
+}
+
+}  // namespace sn

@@ -12,6 +12,7 @@
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
 // the 112-byte-per-thread pattern reaches L2 as full lines.
 #include "supplynet_core.cuh"
+#include "supplynet_generic.cuh"
 #include "../../include/supplynet.h"
 
 #include <cmath>
@@ -73,8 +74,8 @@ struct ObsStager {
 
 // Writes this env's observation row: through the warp's TMA staging buffer when the warp is full
 // and the output aligned, with plain stores otherwise.
-template <bool IDENT, typename T>
-__device__ __forceinline__ void write_obs(ObsStager& st, const Env<T>& e, const DevSpec<T>& sp, bool terminal,
+template <bool IDENT, typename T, typename E>
+__device__ __forceinline__ void write_obs(ObsStager& st, const E& e, const DevSpec<T>& sp, bool terminal,
                                           float* __restrict__ gobs, int64_t env, int64_t n, int od, bool valid,
                                           int buf, bool use_tma) {
   const int64_t env0 = env - st.lane;
@@ -145,36 +146,78 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __rest
   }
 }
 
+// Per-topology operations the kernels are written against: StdOps = the beer game's lead times
+// (tuned, 40 state words), GenOps = run-time per-arc lead times (supplynet_generic.cuh, 57 words).
 template <typename T>
-__device__ __forceinline__ void load_state(const T* __restrict__ state, int64_t ld, int64_t env, Env<T>& e) {
-  T w[kStateWords];
+struct StdOps {
+  using E = Env<T>;
+  static __device__ __forceinline__ void load(const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
+    T w[kStateWords];
 #pragma unroll
-  for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
-  env_from_words(e, w);
-}
+    for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
+    env_from_words(e, w);
+  }
+  static __device__ __forceinline__ void store(T* __restrict__ state, int64_t ld, int64_t env, const E& e) {
+    T w[kStateWords];
+    env_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
+  }
+  static __device__ __forceinline__ void reset(E& e, const DevSpec<T>&, const T* __restrict__ init, int64_t ld,
+                                               int64_t env, T d0) {
+    T in[kInitWords];
+#pragma unroll
+    for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + env);
+    env_reset(e, in, d0);
+  }
+  template <bool MULTI>
+  static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int item, const T (&q)[kF], T dn, bool terminal,
+                                              StepOut& so) {
+    env_step<MULTI>(e, sp, item, q, dn, terminal, so);
+  }
+};
+
 template <typename T>
-__device__ __forceinline__ void store_state(T* __restrict__ state, int64_t ld, int64_t env, const Env<T>& e) {
-  T w[kStateWords];
-  env_to_words(e, w);
+struct GenOps {
+  using E = GEnv<T>;
+  static __device__ __forceinline__ void load(const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
+    T w[kGStateWords];
 #pragma unroll
-  for (int i = 0; i < kStateWords; ++i) state[i * ld + env] = w[i];
-}
+    for (int i = 0; i < kGStateWords; ++i) w[i] = state[i * ld + env];
+    genv_from_words(e, w);
+  }
+  static __device__ __forceinline__ void store(T* __restrict__ state, int64_t ld, int64_t env, const E& e) {
+    T w[kGStateWords];
+    genv_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kGStateWords; ++i) state[i * ld + env] = w[i];
+  }
+  static __device__ __forceinline__ void reset(E& e, const DevSpec<T>& sp, const T* __restrict__ init, int64_t ld,
+                                               int64_t env, T d0) {
+    T in[kGInitWords];
+#pragma unroll
+    for (int w = 0; w < kGInitWords; ++w) in[w] = __ldg(init + w * ld + env);
+    genv_reset(e, sp, in, d0);
+  }
+  template <bool MULTI>
+  static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int, const T (&q)[kF], T dn, bool terminal,
+                                              StepOut& so) {
+    genv_step(e, sp, q, dn, terminal, so);
+  }
+};
 
 // ------------------------------------------------------------------------------------------
-template <typename T, bool IDENT>
+template <typename T, bool IDENT, typename Ops>
 __global__ void __launch_bounds__(kBlock)
 k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
         const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
-  Env<T> e;
+  typename Ops::E e;
   if (valid) {
-    T in[kInitWords];
-#pragma unroll
-    for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + env);
-    env_reset(e, in, __ldg(demand0 + env));
-    store_state(state, ld, env, e);
+    Ops::reset(e, sp, init, ld, env, __ldg(demand0 + env));
+    Ops::store(state, ld, env, e);
   }
   if (obs != nullptr) {
     ObsStager st(smem_f);
@@ -183,15 +226,15 @@ k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* _
   }
 }
 
-template <typename T, bool IDENT>
+template <typename T, bool IDENT, typename Ops>
 __global__ void __launch_bounds__(kBlock)
 k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
           float* __restrict__ obs, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
-  Env<T> e;
-  if (valid) load_state(state, ld, env, e);
+  typename Ops::E e;
+  if (valid) Ops::load(state, ld, env, e);
   ObsStager st(smem_f);
   write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
   st.drain();
@@ -206,7 +249,7 @@ struct StepPtrs {
   double* stats;
 };
 
-template <typename T, bool IDENT>
+template <typename T, bool IDENT, typename Ops>
 __global__ void __launch_bounds__(kBlock)
 k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
        const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
@@ -214,21 +257,21 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
   __shared__ double red[kWarpsPerBlock * 10];
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
-  Env<T> e;
+  typename Ops::E e;
   StepOut so;
   so.reward = 0.0;
 #pragma unroll
   for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
   if (valid) {
-    load_state(state, ld, env, e);
+    Ops::load(state, ld, env, e);
     T a[kF] = {T(0), T(0), T(0), T(0)};
     load_actions<IDENT>(actions, env, sp, a);
     const T dn = __ldg(demand_next + env);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
-    if (sp.n_items > 1) env_step<true>(e, sp, chain_item(sp, env), q, dn, terminal != 0, so);
-    else env_step<false>(e, sp, 0, q, dn, terminal != 0, so);
-    store_state(state, ld, env, e);
+    if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal != 0, so);
+    else Ops::template step<false>(e, sp, 0, q, dn, terminal != 0, so);
+    Ops::store(state, ld, env, e);
     if (out.reward) out.reward[env] = (float)so.reward;
     if (out.reward64) out.reward64[env] = so.reward;
     if (out.cost) {
@@ -275,7 +318,7 @@ struct RolloutPtrs {
 #define SN_PRAGMA_UNROLL(n) _Pragma(SN_STR(unroll n))
 constexpr int kRolloutBlock = SN_ROLLOUT_BLOCK;
 
-template <typename T, int POLICY, bool IDENT, bool MULTI>
+template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 __global__ void __launch_bounds__(kRolloutBlock)
 k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
           int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
@@ -290,16 +333,13 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   const int64_t act_stride = n * sp.n_agents;
   ObsStager st(smem_f);
 
-  Env<T> e;
+  typename Ops::E e;
   if (init != nullptr) {
     // episode mode (sn_episode): reset in-kernel, the state never has to exist in HBM
-    T in[kInitWords];
-#pragma unroll
-    for (int w = 0; w < kInitWords; ++w) in[w] = __ldg(init + w * ld + envc);
-    env_reset(e, in, __ldg(demand + envc));
+    Ops::reset(e, sp, init, ld, envc, __ldg(demand + envc));
     if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, 1, use_tma != 0);
   } else {
-    load_state(state, ld, envc, e);
+    Ops::load(state, ld, envc, e);
   }
   double acc[10];
 #pragma unroll
@@ -334,7 +374,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
     StepOut so;
-    env_step<MULTI>(e, sp, item, q, dn, terminal, so);
+    Ops::template step<MULTI>(e, sp, item, q, dn, terminal, so);
     acc[0] += 1.0;
     acc[1] += so.reward;
 #pragma unroll
@@ -348,7 +388,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
   if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
   st.drain();
   if (valid) {
-    if (state != nullptr) store_state(state, ld, env, e);
+    if (state != nullptr) Ops::store(state, ld, env, e);
     if (out.ep_return) out.ep_return[env] = (init != nullptr ? 0.0 : out.ep_return[env]) + acc[1];
   }
   if (out.stats != nullptr) {
@@ -419,16 +459,28 @@ int fail(int code, const char* fmt, ...) {
 
 bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && std::fabs(x) < 2147483647.0; }
 
+// the beer game's lead times (envs.py:355-392): tuned kernels; anything else takes the generic path
+bool is_standard(const sn_spec* s) {
+  const int li[4] = {2, 2, 2, 1};
+  for (int k = 0; k < 4; ++k)
+    if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2) return false;
+  return true;
+}
+
 int validate(const sn_spec* s, int dtype) {
   if (s == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
   if (dtype != SN_I32 && dtype != SN_F32 && dtype != SN_F64) return fail(SN_ERR_INVALID, "unknown dtype %d", dtype);
   if (s->n_facilities != 4) return fail(SN_ERR_UNSUPPORTED, "only the 4-echelon serial chain is supported (n_facilities=%d)", s->n_facilities);
-  const int li[4] = {2, 2, 2, 1};
   for (int k = 0; k < 4; ++k) {
-    if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2)
-      return fail(SN_ERR_UNSUPPORTED, "arc %d: lead times (%d,%d) unsupported; the beer-game chain uses info (2,2,2,1), shipment 2",
-                  k, s->info_leadtime[k], s->ship_leadtime[k]);
+    const int li = s->info_leadtime[k], ls = s->ship_leadtime[k];
+    if (li < 1 || li > 4 || ls < 1 || ls > 4)
+      return fail(SN_ERR_UNSUPPORTED, "arc %d: lead times (%d,%d) outside 1..4", k, li, ls);
+    if (li + ls > 5)
+      return fail(SN_ERR_UNSUPPORTED, "arc %d: information + shipment lead time %d+%d > 5; the reference keeps five pipeline "
+                                      "slots (network_components.py:168) and fails its own on_order assertion beyond that", k, li, ls);
   }
+  if (!is_standard(s) && s->n_items > 1)
+    return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported with the beer game's lead times only");
   if (s->n_agents < 1 || s->n_agents > 4) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
   int seen = 0, lo = 4, hi = -1;
   for (int i = 0; i < s->n_agents; ++i) {
@@ -471,6 +523,7 @@ sn::DevSpec<T> lower(const sn_spec* s) {
     d.slot[k] = -1;
   }
   d.n_items = s->n_items > 1 ? s->n_items : 1;
+  for (int k = 0; k < 4; ++k) { d.li[k] = s->info_leadtime[k]; d.ls[k] = s->ship_leadtime[k]; }
   for (int i = 0; i < s->n_agents; ++i) {
     d.slot[s->agents[i]] = i;
     lo = s->agents[i] < lo ? s->agents[i] : lo;
@@ -535,24 +588,31 @@ constexpr size_t kRolloutSmem = (sn::kRolloutBlock / 32) * 2 * 32 * 28 * sizeof(
 
 inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)((n + block - 1) / block); }
 
+// launch with <IDENT, Ops> chosen from the spec: tuned standard kernels (identity specialised or not)
+// or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
+#define SN_DISPATCH_TOPO(spec, CALL)                                   \
+  do {                                                                 \
+    if (!is_standard(spec)) { CALL(false, sn::GenOps<T>); }            \
+    else if (is_identity(spec)) { CALL(true, sn::StdOps<T>); }         \
+    else { CALL(false, sn::StdOps<T>); }                               \
+  } while (0)
+
 template <typename T>
 int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
              float* obs, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  if (is_identity(spec))
-    sn::k_reset<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
-  else
-    sn::k_reset<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs));
+#define SN_CALL(ID, OPS) sn::k_reset<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs))
+  SN_DISPATCH_TOPO(spec, SN_CALL);
+#undef SN_CALL
   return cuda_ok("sn_reset launch");
 }
 
 template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  if (is_identity(spec))
-    sn::k_observe<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
-  else
-    sn::k_observe<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs));
+#define SN_CALL(ID, OPS) sn::k_observe<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs))
+  SN_DISPATCH_TOPO(spec, SN_CALL);
+#undef SN_CALL
   return cuda_ok("sn_observe launch");
 }
 
@@ -560,25 +620,34 @@ template <typename T>
 int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
             const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
   const auto d = lower<T>(spec);
-  if (is_identity(spec))
-    sn::k_step<T, true><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
-                                                                  (const T*)demand_next, out, tma_ok(out.obs));
-  else
-    sn::k_step<T, false><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions,
-                                                                   (const T*)demand_next, out, tma_ok(out.obs));
+#define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out, tma_ok(out.obs))
+  SN_DISPATCH_TOPO(spec, SN_CALL);
+#undef SN_CALL
   return cuda_ok("sn_step launch");
 }
 
-template <typename T, int POLICY, bool IDENT>
+template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
                     void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
                     cudaStream_t st, const void* init, float* obs0) {
-  if (d.n_items > 1)
-    sn::k_rollout<T, POLICY, IDENT, true><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
-        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
-  else
-    sn::k_rollout<T, POLICY, IDENT, false><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
-        d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
+  sn::k_rollout<T, POLICY, IDENT, MULTI, Ops><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
+      d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
+}
+
+template <typename T, int POLICY>
+void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld,
+                        int period0, int n_steps, void* state, const void* demand, const void* actions,
+                        const sn::RolloutPtrs& out, int tma, cudaStream_t st, const void* init, float* obs0) {
+#define SN_ARGS d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0
+  if (!is_standard(spec)) launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
+  else if (is_identity(spec)) {
+    if (d.n_items > 1) launch_rollout<T, POLICY, true, true, sn::StdOps<T>>(SN_ARGS);
+    else launch_rollout<T, POLICY, true, false, sn::StdOps<T>>(SN_ARGS);
+  } else {
+    if (d.n_items > 1) launch_rollout<T, POLICY, false, true, sn::StdOps<T>>(SN_ARGS);
+    else launch_rollout<T, POLICY, false, false, sn::StdOps<T>>(SN_ARGS);
+  }
+#undef SN_ARGS
 }
 
 template <typename T>
@@ -591,14 +660,10 @@ int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period
   if (rc != SN_OK) return rc;
   const int tma = (out.traj_obs == nullptr || aligned16(out.traj_obs)) && (out.obs == nullptr || aligned16(out.obs)) &&
                   (obs0 == nullptr || aligned16(obs0)) && (((int64_t)n * 7 * d.n_obs * 4) % 16 == 0);
-  const bool ident = is_identity(spec);
-  if (policy_kind == SN_POLICY_ACTIONS) {
-    if (ident) launch_rollout<T, SN_POLICY_ACTIONS, true>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0);
-    else launch_rollout<T, SN_POLICY_ACTIONS, false>(d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0);
-  } else {
-    if (ident) launch_rollout<T, SN_POLICY_BASE_STOCK, true>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st, init, obs0);
-    else launch_rollout<T, SN_POLICY_BASE_STOCK, false>(d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st, init, obs0);
-  }
+  if (policy_kind == SN_POLICY_ACTIONS)
+    launch_rollout_for<T, SN_POLICY_ACTIONS>(spec, d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0);
+  else
+    launch_rollout_for<T, SN_POLICY_BASE_STOCK>(spec, d, p, n, ld, period0, n_steps, state, demand, nullptr, out, tma, st, init, obs0);
   return cuda_ok("sn_rollout launch");
 }
 
@@ -617,6 +682,16 @@ int32_t sn_obs_dim(const sn_spec* spec) {
 }
 
 int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype) { return validate(spec, dtype); }
+
+int32_t sn_state_words(const sn_spec* spec) {
+  if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
+  return is_standard(spec) ? SN_STATE_WORDS : SN_GEN_STATE_WORDS;
+}
+
+int32_t sn_init_words(const sn_spec* spec) {
+  if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
+  return is_standard(spec) ? SN_INIT_WORDS : SN_GEN_INIT_WORDS;
+}
 
 int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const void* init,
                  const void* demand0, void* state, float* obs, void* stream) {

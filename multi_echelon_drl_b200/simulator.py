@@ -70,8 +70,10 @@ class BatchedSupplyNetwork:
         self.obs_dim = spec.obs_dim
         self.n_agents = spec.n_agents
         dev, n, ld = self.device, self.n_envs, self.ld
-        self.state = torch.zeros((_lib.SN_STATE_WORDS, ld), dtype=self.tdtype, device=dev)
-        self.init = torch.zeros((_lib.SN_INIT_WORDS, ld), dtype=self.tdtype, device=dev)
+        self.state_words = self.lib.sn_state_words(C.byref(self._c_spec))      # 40 (beer-game lead times) or 57
+        self.init_words = self.lib.sn_init_words(C.byref(self._c_spec))        # 19 or 36
+        self.state = torch.zeros((self.state_words, ld), dtype=self.tdtype, device=dev)
+        self.init = torch.zeros((self.init_words, ld), dtype=self.tdtype, device=dev)
         self.demand = torch.zeros((self.T + 3, ld), dtype=self.tdtype, device=dev)
         self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
         self.reward = torch.zeros((n,), dtype=torch.float32, device=dev)
@@ -100,12 +102,13 @@ class BatchedSupplyNetwork:
 
     # ------------------------------------------------------------------ episode inputs
     def load_episode(self, init, demand):
-        """init [n,19] (inv[4]; so[k][j]; sh[k][j]), demand [n, >=T+1] (utils/demands.py streams)."""
+        """init [n, init_words] (19: inv[4]; so[k][j]; sh[k][j] packed for the beer game's lead times; 36:
+        inv[4]; so[k][0..3]; sh[k][0..3] for other lead times), demand [n, >=T+1] (utils/demands.py streams)."""
         d = torch.as_tensor(demand)
         if d.dim() != 2 or d.shape[1] < self.T + 1:
             raise ValueError(f"demand must be [n_envs, >= {self.T + 1}]")
         width = min(d.shape[1], self.T + 3)
-        self.init.copy_(self._to_rows(init, _lib.SN_INIT_WORDS))
+        self.init.copy_(self._to_rows(init, self.init_words))
         self.demand.zero_()
         self.demand[:width].copy_(self._to_rows(d[:, :width], width))
 

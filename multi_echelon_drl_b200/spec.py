@@ -60,6 +60,10 @@ class ScenarioSpec:
     # multi-item: cost vectors of items 1.. (item 0 uses holding_cost / backorder_cost); chains are
     # interleaved item-minor, so obs/action rows of one env are the concatenation over its items
     extra_item_costs: Tuple[Tuple[Tuple[float, ...], Tuple[float, ...]], ...] = ()
+    # per-arc lead times (arc k: customer = node k).  The beer game's values select the tuned kernels,
+    # anything else (1..4, info + shipment <= 5) the generic ones
+    info_leadtime: Tuple[int, ...] = INFO_LEADTIME
+    ship_leadtime: Tuple[int, ...] = SHIP_LEADTIME
 
     def __post_init__(self):
         ag = tuple(node_index(a) for a in self.agents)
@@ -71,8 +75,16 @@ class ScenarioSpec:
             raise ValueError("agent-managed facilities must form a contiguous block of the chain")
         if self.rule not in ("a", "d+a"):
             raise ValueError(f"ordering rule must be 'a' or 'd+a', got {self.rule!r}")
+        object.__setattr__(self, "info_leadtime", tuple(int(x) for x in self.info_leadtime))
+        object.__setattr__(self, "ship_leadtime", tuple(int(x) for x in self.ship_leadtime))
+        if len(self.info_leadtime) != 4 or len(self.ship_leadtime) != 4:
+            raise ValueError("info_leadtime and ship_leadtime need one entry per arc (4)")
 
     # ------------------------------------------------------------------ derived
+    @property
+    def standard_leadtimes(self) -> bool:
+        return self.info_leadtime == INFO_LEADTIME and self.ship_leadtime == SHIP_LEADTIME
+
     @property
     def n_items(self) -> int:
         return 1 + len(self.extra_item_costs)
@@ -96,8 +108,8 @@ class ScenarioSpec:
         s = _lib.SnSpec()
         s.n_facilities = 4
         for k in range(4):
-            s.info_leadtime[k] = INFO_LEADTIME[k]
-            s.ship_leadtime[k] = SHIP_LEADTIME[k]
+            s.info_leadtime[k] = self.info_leadtime[k]
+            s.ship_leadtime[k] = self.ship_leadtime[k]
             s.holding_cost[k] = float(self.holding_cost[k])
             s.backorder_cost[k] = float(self.backorder_cost[k])
             s.coplayer_target[k] = float(self.coplayer_target[k])
@@ -166,10 +178,12 @@ def specs_from_config(network_config: dict, agent_managed_facilities=None, globa
     their own cost vectors (the reference defines no item coupling)."""
     from .utils.graph import chain_from_config
     seq, info, ship, hold, back = chain_from_config(network_config)
-    if tuple(seq) != NODE_NAMES or info != INFO_LEADTIME or ship != SHIP_LEADTIME:
-        raise NotImplementedError(f"kernels implement the chain {NODE_NAMES} with lead times {INFO_LEADTIME}/"
-                                  f"{SHIP_LEADTIME}; got {seq} {info}/{ship}")
-    base = uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
+    if tuple(seq) != NODE_NAMES:
+        raise NotImplementedError(f"kernels implement the 4-echelon chain {NODE_NAMES}; got {seq}")
+    if any(not 1 <= l <= 4 for l in info + ship) or any(a + b > 5 for a, b in zip(info, ship)):
+        raise NotImplementedError(f"lead times must be 1..4 with info + shipment <= 5 per arc; got {info}/{ship}")
+    base = replace(uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init),
+                   info_leadtime=info, ship_leadtime=ship)
     return [replace(base, name=f"config-item{i}", holding_cost=tuple(float(x) for x in hold[i]),
                     backorder_cost=tuple(float(x) for x in back[i]), coplayer_target=tuple(coplayer_target))
             for i in range(len(hold))]

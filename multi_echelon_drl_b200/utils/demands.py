@@ -93,14 +93,23 @@ def demand_for(spec: ScenarioSpec) -> Demand:
     return Demand(spec.demand_pattern, size=spec.max_episode_steps)
 
 
+def init_layout(spec: ScenarioSpec):
+    """(n_words, so_offsets[4], sh_offsets[4]) of the init rows: packed 19 words for the beer game's lead
+    times (tuned kernels), 36 words (4 slots per pipeline) for any other lead times (generic kernels)."""
+    if spec.standard_leadtimes:
+        return INIT_WORDS, _SO_OFF, _SH_OFF
+    return 36, tuple(4 + 4 * k for k in range(4)), tuple(20 + 4 * k for k in range(4))
+
+
 def _fixed_init(spec: ScenarioSpec) -> np.ndarray:
-    v = np.zeros(INIT_WORDS, dtype=np.int64)
+    n_words, so_off, sh_off = init_layout(spec)
+    v = np.zeros(n_words, dtype=np.int64)
     v[:4] = spec.fixed_inventory
     for k in range(4):
-        for j in range(INFO_LEADTIME[k]):
-            v[_SO_OFF[k] + j] = spec.fixed_sales_orders[j]
-        for j in range(SHIP_LEADTIME[k]):
-            v[_SH_OFF[k] + j] = spec.fixed_shipments[j]
+        for j in range(spec.info_leadtime[k]):
+            v[so_off[k] + j] = spec.fixed_sales_orders[min(j, len(spec.fixed_sales_orders) - 1)]
+        for j in range(spec.ship_leadtime[k]):
+            v[sh_off[k] + j] = spec.fixed_shipments[min(j, len(spec.fixed_shipments) - 1)]
     return v
 
 
@@ -115,12 +124,20 @@ def seeded_episode_inputs(spec: ScenarioSpec, seeds):
 def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
     """Same distributions, vectorised draws from one stream `rs` (RandomState)."""
     dem = demand_for(spec)
+    n_words, so_off, sh_off = init_layout(spec)
     if spec.random_init:
-        init = np.empty((n, INIT_WORDS), dtype=np.int64)
+        init = np.zeros((n, n_words), dtype=np.int64)
         init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
-        init[:, 4:] = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, INIT_WORDS - 4))
+        pipe = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, n_words - 4))
+        if not spec.standard_leadtimes:             # slots beyond an arc's lead time stay empty
+            mask = np.zeros(n_words - 4, dtype=bool)
+            for k in range(4):
+                mask[so_off[k] - 4: so_off[k] - 4 + spec.info_leadtime[k]] = True
+                mask[sh_off[k] - 4: sh_off[k] - 4 + spec.ship_leadtime[k]] = True
+            pipe = pipe * mask
+        init[:, 4:] = pipe
     else:
-        init = np.broadcast_to(_fixed_init(spec), (n, INIT_WORDS)).copy()
+        init = np.broadcast_to(_fixed_init(spec), (n, n_words)).copy()
     return init, dem.sample(n, rs)
 
 
@@ -129,7 +146,8 @@ def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
     over successive resets equals one reference env seeded once and reset repeatedly."""
     n = len(streams)
     dem = demand_for(spec)
-    init = np.zeros((n, INIT_WORDS), dtype=np.int64)
+    n_words, so_off, sh_off = init_layout(spec)
+    init = np.zeros((n, n_words), dtype=np.int64)
     demand = np.zeros((n, dem.size), dtype=np.int64)
     fixed = _fixed_init(spec)
     for i, rs in enumerate(streams):
@@ -144,8 +162,8 @@ def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
         for k in (1, 2, 3):
             init[i, k] = rs.randint(lo, hi)
         for k in (3, 2, 1, 0):
-            for j in range(SHIP_LEADTIME[k]):
-                init[i, _SH_OFF[k] + j] = rs.randint(plo, phi)
-            for j in range(INFO_LEADTIME[k]):
-                init[i, _SO_OFF[k] + j] = rs.randint(plo, phi)
+            for j in range(spec.ship_leadtime[k]):
+                init[i, sh_off[k] + j] = rs.randint(plo, phi)
+            for j in range(spec.info_leadtime[k]):
+                init[i, so_off[k] + j] = rs.randint(plo, phi)
     return init, demand

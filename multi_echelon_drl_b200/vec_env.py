@@ -161,9 +161,10 @@ class SupplyNetVecEnv(_VecEnvBase):
         if sp.random_init:
             sim.init[:4].random_(sp.init_inventory[0], sp.init_inventory[1], generator=g)
             sim.init[4:].random_(sp.init_pipeline[0], sp.init_pipeline[1], generator=g)
+            # (for non-standard lead times the kernels ignore pipeline slots beyond an arc's lead time)
         else:
             sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=self.device).to(sim.tdtype)[:, None]
-                           .expand(19, sim.ld))
+                           .expand(sim.init_words, sim.ld))
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):

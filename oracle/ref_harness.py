@@ -123,3 +123,38 @@ def rollout(env, actions, seed=None, collect_costs=False):
         b = np.array([env.sn.nodes[n].backorder_cost_history for n in NODE_NAMES], dtype=np.float64).T
         out["holding"], out["backorder"] = h, b
     return out
+
+
+def make_custom_chain_env(info_lt, ship_lt, agents, global_observable=False, max_episode_steps=100,
+                          holding=(0.5, 0.5, 0.5, 0.5), backorder=(1, 1, 1, 1), targets=(19, 20, 20, 14),
+                          init_inventory=(0, 25), init_pipeline=(0, 9), dplusa=None):
+    """A 4-echelon serial chain like envs.py:289-414 but with per-arc lead times chosen by the caller,
+    built directly from the reference's Node / Arc / SupplyNetwork / InventoryManagementEnvMultiPlayer
+    classes (random initial state, uniform demand 0..8).  info_lt / ship_lt are indexed by arc k whose
+    customer is node k (retailer first)."""
+    ref = import_reference()
+    E, NC, SN, HE, DE = ref["envs"], ref["nc"], ref["sn"], ref["heuristics"], ref["demands"]
+    import gym
+    idx = {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1, "latest_demand": 2}
+    pol = [HE.BaseStockPolicy(target_levels=[t], array_index=idx, state_dim_per_facility=7) for t in targets]
+    demand = DE.Demand("uniform", low=0, high=8, size=max_episode_steps)
+    nodes = []
+    for k, name in enumerate(NODE_NAMES):
+        kw = dict(name=name, initial_inventory=list(init_inventory), holding_cost=holding[k], backorder_cost=backorder[k],
+                  policy=pol[k])
+        if k == 0:
+            kw.update(is_demand_source=True, demands=demand)
+        nodes.append(NC.Node(**kw))
+    nodes.append(NC.Node(name="external_supplier", is_external_supplier=True))
+    sup = ["wholesaler", "distributor", "manufacturer", "external_supplier"]
+    arcs = [NC.Arc(sup[k], NODE_NAMES[k], info_lt[k], ship_lt[k], initial_shipments=list(init_pipeline),
+                   initial_sales_orders=list(init_pipeline), random_init=True) for k in (3, 2, 1, 0)]
+    names = [NODE_NAMES[k] for k in agents]
+    net = SN.SupplyNetwork(nodes=nodes, arcs=arcs, agent_managed_facilities=names)
+    n_obs = 4 if global_observable else len(names)
+    env = E.InventoryManagementEnvMultiPlayer(
+        net, max_episode_steps=max_episode_steps, action_space=gym.spaces.Box(0, 16, shape=(len(names),)),
+        observation_space=gym.spaces.Box(low=-np.inf, high=np.inf, shape=(7 * n_obs,)), global_observable=global_observable)
+    if dplusa is not None:
+        env = ref["wrappers"].wrap_action_d_plus_a(env, offset=dplusa[0], lb=dplusa[1], ub=dplusa[2])
+    return env

@@ -13,6 +13,7 @@ Files written
                   (pins the RNG draw order replayed by the host-side stream generator)
   classic.npz     the classic beer game episodes behind the 13 totals of
                   tests/test_supplynetwork.py:25-69, with per-step outputs
+  leadtimes.npz   serial chains with other per-arc lead times (general-chain path)
 """
 import os
 import sys
@@ -157,9 +158,46 @@ def gen_classic():
           [float(out[f"k{c:02d}_rew"].sum()) for c in range(cid + 1)])
 
 
+def flat_init_generic(init):
+    """36 numbers: inv[4], so[k][0..3] (k = 0..3, unused slots 0), sh[k][0..3]."""
+    inv0, so, sh, dem = init
+    v = np.zeros(36, dtype=np.int64)
+    v[:4] = inv0
+    for k in range(4):
+        v[4 + 4 * k: 4 + 4 * k + len(so[k])] = so[k]
+        v[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
+    return v, np.asarray(dem, dtype=np.int64)
+
+
+def gen_leadtimes():
+    """Serial chains with per-arc lead times other than the beer game's, built from the reference's own
+    Node/Arc/SupplyNetwork classes (oracle/ref_harness.make_custom_chain_env).  info+shipment <= 5 per arc:
+    beyond that the reference's own on_order assertion (supplynetwork.py:159-160) fails at reset."""
+    combos = [((2, 2, 2, 1), (2, 2, 2, 2)), ((1, 1, 1, 1), (1, 1, 1, 1)), ((3, 2, 1, 2), (2, 3, 4, 1)),
+              ((4, 1, 2, 3), (1, 4, 3, 2)), ((1, 4, 1, 2), (4, 1, 4, 3)), ((2, 3, 2, 2), (3, 2, 1, 3))]
+    out, meta, cid = {}, [], 0
+    for li, ls in combos:
+        for ag in ((0, 1, 2, 3), (1,), (2, 3), (3, 2, 1, 0)):
+            for glob, rule in ((False, "a"), (True, "d+a"), (True, "a")):
+                seed = 900 + cid
+                env = H.make_custom_chain_env(li, ls, ag, glob, dplusa=(-8, 0, 16) if rule == "d+a" else None)
+                acts = np.random.RandomState(7000 + cid).randint(-1, 19, (100, len(ag))).astype(np.int64)
+                r = H.rollout(env, [a for a in acts], seed=seed, collect_costs=True)
+                init, dem = flat_init_generic(r["init"])
+                p = f"g{cid:03d}_"
+                out.update({p + "init": init, p + "demand": dem, p + "actions": acts, p + "obs0": r["obs0"],
+                            p + "obs": r["obs"], p + "rew": r["rew"]})
+                meta.append(f"{cid}|{','.join(map(str, li))}|{','.join(map(str, ls))}|{','.join(map(str, ag))}|{int(glob)}|{rule}")
+                cid += 1
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "leadtimes.npz"), **out)
+    print("leadtimes:", cid, "cases")
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore", RuntimeWarning)
     gen_rollouts()
     gen_heuristic()
     gen_seeded()
     gen_classic()
+    gen_leadtimes()

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"libsupplynet.so does not export {name}"
     assert set(_lib.SIGNATURES) == declared, "ctypes binding and header disagree on the entry points"
-    assert lib.sn_abi_version() == 2
+    assert lib.sn_abi_version() == 3
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -63,9 +63,16 @@ def test_spec_validation_and_error_mapping(lib):
     assert lib.sn_spec_validate(C.byref(c2), _lib.SN_I32) == _lib.SN_ERR_INVALID
     with pytest.raises(ValueError, match="contiguous"):
         _lib.check(lib.sn_spec_validate(C.byref(c2), _lib.SN_I32))
-    # unsupported topology
+    # lead times: 1..4 with info + shipment <= 5 (generic kernels, 57 state words); else unsupported
+    assert lib.sn_state_words(C.byref(c)) == 40 and lib.sn_init_words(C.byref(c)) == 19
     c3 = spec.to_c()
     c3.info_leadtime[0] = 3
+    assert lib.sn_spec_validate(C.byref(c3), _lib.SN_I32) == 0
+    assert lib.sn_state_words(C.byref(c3)) == 57 and lib.sn_init_words(C.byref(c3)) == 36
+    c3.info_leadtime[0] = 4
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.sn_spec_validate(C.byref(c3), _lib.SN_I32))
+    c3.info_leadtime[0], c3.ship_leadtime[0] = 0, 2
     with pytest.raises(NotImplementedError):
         _lib.check(lib.sn_spec_validate(C.byref(c3), _lib.SN_I32))
     # fractional constants with the integer simulator -> TypeError

@@ -1,0 +1,107 @@
+"""Generic lead-time kernels (serial chains with per-arc information / shipment lead times other than the
+beer game's) vs golden trajectories recorded from the reference's own Node/Arc/SupplyNetwork classes and vs
+the oracle on batches.  Integer quantities: bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from test_oracle_golden import LEADTIME_CASES, oracle_leadtime_rollout  # noqa: E402
+
+
+def _sim(case, n, dtype="int32"):
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    spec = replace(uniform_spec(case["agents"], case["glob"], 100), info_leadtime=case["li"], ship_leadtime=case["ls"])
+    if case["rule"] == "d+a":
+        spec = spec.with_rule("d+a", -8, 0, 16)
+    return BatchedSupplyNetwork(spec, n, "cuda", dtype)
+
+
+def _init_for(sim, case, init36):
+    """golden inits are stored in the 36-word layout; the beer game's own lead times use the packed 19."""
+    if sim.init_words == 36:
+        return init36
+    cols = list(range(4))
+    for k in range(4):
+        cols += [4 + 4 * k + j for j in range(case["li"][k])]
+    for k in range(4):
+        cols += [20 + 4 * k + j for j in range(case["ls"][k])]
+    return init36[:, cols]
+
+
+@pytest.mark.parametrize("case", LEADTIME_CASES, ids=[c["id"] for c in LEADTIME_CASES])
+def test_step_and_rollout_match_reference_golden(case):
+    sim = _sim(case, 1)
+    assert sim.state_words == (40 if case["li"] == (2, 2, 2, 1) and case["ls"] == (2, 2, 2, 2) else 57)
+    sim.load_episode(_init_for(sim, case, case["init"][None]), case["demand"][None])
+    assert np.array_equal(sim.reset().cpu().numpy()[0], case["obs0"])
+    r64 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for t in range(100):
+        obs, _, done = sim.step(torch.as_tensor(case["actions"][t][None]), reward64_out=r64)
+        assert np.array_equal(obs.cpu().numpy()[0], case["obs"][t]), t
+        assert r64.item() == case["rew"][t], t
+    assert done
+    out = sim.episode(100, actions=torch.as_tensor(case["actions"][:, None, :]), record_obs=True, record_reward=True)
+    assert np.array_equal(out["traj_obs"].cpu().numpy()[:, 0], case["obs"])
+    assert sim.ep_return.item() == case["rew"].sum()
+
+
+@pytest.mark.parametrize("li,ls,agents,glob,rule", [
+    ((1, 1, 1, 1), (1, 1, 1, 1), (0, 1, 2, 3), True, "a"),
+    ((4, 1, 2, 3), (1, 4, 3, 2), (0, 1, 2, 3), True, "d+a"),
+    ((3, 2, 1, 2), (2, 3, 4, 1), (2,), False, "a"),
+    ((1, 4, 1, 2), (4, 1, 4, 3), (1, 2, 3), True, "a"),
+])
+def test_generic_batch_vs_oracle_and_policy_rollout(li, ls, agents, glob, rule):
+    """3,001 envs (ragged) x 100: step kernel, fused rollout with trajectory, in-kernel base-stock policy."""
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    case = dict(li=li, ls=ls, agents=agents, glob=glob, rule=rule)
+    n = 3001
+    sim = _sim(case, n)
+    init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(5))
+    assert init.shape == (n, 36)
+    acts = np.random.RandomState(6).randint(-1, 19, (100, n, len(agents)))
+    obs0, obs, rew = oracle_leadtime_rollout(case, init, demand, acts)
+    sim.load_episode(init, demand)
+    assert np.array_equal(sim.reset().cpu().numpy(), obs0)
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(100):
+        o, _, _ = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
+        assert np.array_equal(o.cpu().numpy(), obs[t]), t
+        assert np.array_equal(r64.cpu().numpy(), rew[t]), t
+    out = sim.episode(100, actions=torch.as_tensor(acts), record_obs=True)
+    assert np.array_equal(out["traj_obs"].cpu().numpy(), obs)
+    assert np.array_equal(sim.ep_return.cpu().numpy(), rew.sum(0))
+    # in-kernel policy == heuristic kernel + step kernel
+    from multi_echelon_drl_b200.simulator import heuristic_actions
+    if len(agents) == 4 and glob:
+        pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
+        sim.episode(100, policy=pol, write_state=False)
+        fused = sim.ep_return.clone()
+        o = sim.reset()
+        for t in range(100):
+            o, _, _ = sim.step(heuristic_actions(pol, o))
+        assert torch.equal(fused, sim.ep_return)
+
+
+def test_vecenv_with_other_lead_times_and_unsupported_ones():
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    spec = replace(uniform_spec(None, True), info_leadtime=(1, 2, 3, 1), ship_leadtime=(3, 3, 2, 4))
+    env = SupplyNetVecEnv(spec, 512, seed=3, dtype="int32")
+    obs = env.reset()
+    s = env.sim.state[:, :512].to(torch.int64)
+    for k in range(4):                                   # reference invariant: on_order == sum(pipeline)
+        on_order = s[7 * k + 3:7 * k + 7].sum(0)
+        pipe = s[28 + 3 * k:31 + 3 * k].sum(0) + s[40 + 4 * k:44 + 4 * k].sum(0) + (s[7 * (k + 1) + 1] if k < 3 else s[56])
+        assert torch.equal(on_order, pipe)
+    for _ in range(150):
+        obs, rew, dones, infos = env.step(torch.full((512, 4), 4, device="cuda"))
+    assert torch.isfinite(obs).all() and env.episodes_done == 512
+    with pytest.raises(NotImplementedError):
+        SupplyNetVecEnv(replace(uniform_spec(), info_leadtime=(3, 2, 2, 1), ship_leadtime=(3, 2, 2, 2)), 8)

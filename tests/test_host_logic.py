@@ -181,8 +181,12 @@ def test_yaml_configs_lower_to_specs():
     assert spec.holding_cost == (0.5,) * 4 and spec.backorder_cost == (1.0,) * 4 and spec.obs_dim == 28
     multi = specs_from_config(read_yaml(os.path.join(d, "multi_item.yaml")))
     assert len(multi) == 2 and multi[1].holding_cost == (0.75,) * 4 and multi[0].holding_cost == (0.5,) * 4
+    other = read_yaml(os.path.join(d, "beergame.yaml"))
+    other["arcs"][0]["info_leadtime"] = 3                # 3 + 2 <= 5: generic lead-time kernels
+    (sp3,) = specs_from_config(other)
+    assert sp3.info_leadtime == (3, 2, 2, 1) and not sp3.standard_leadtimes and spec.standard_leadtimes
     bad = read_yaml(os.path.join(d, "beergame.yaml"))
-    bad["arcs"][0]["info_leadtime"] = 3
+    bad["arcs"][0]["info_leadtime"] = 4                  # 4 + 2 > 5: the reference's own assertion fails there
     with pytest.raises(NotImplementedError):
         specs_from_config(bad)
     bad = read_yaml(os.path.join(d, "beergame.yaml"))

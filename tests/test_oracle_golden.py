@@ -114,3 +114,46 @@ def test_oracle_vs_live_reference():
                 flat = np.array(list(inv0) + [x for k in range(4) for x in so[k]] + [x for k in range(4) for x in sh[k]])
                 ref = oracle_rollout(scn, ag, glob, "a", 100, flat[None], dem[None], acts[:, None, :])
                 assert np.array_equal(ref["obs"][:, 0], r["obs"]) and np.array_equal(ref["rew"][:, 0], r["rew"])
+
+
+def _leadtime_cases():
+    z = np.load(f"{GOLDEN}/leadtimes.npz")
+    out = []
+    for m in z["meta"]:
+        cid, li, ls, ag, glob, rule = str(m).split("|")
+        p = f"g{int(cid):03d}_"
+        out.append(dict(id=f"li{li.replace(',', '')}-ls{ls.replace(',', '')}-ag{ag.replace(',', '')}-g{glob}-{rule}",
+                        li=tuple(int(x) for x in li.split(",")), ls=tuple(int(x) for x in ls.split(",")),
+                        agents=tuple(int(x) for x in ag.split(",")), glob=bool(int(glob)), rule=rule,
+                        init=z[p + "init"], demand=z[p + "demand"], actions=z[p + "actions"], obs0=z[p + "obs0"],
+                        obs=z[p + "obs"], rew=z[p + "rew"]))
+    return out
+
+
+LEADTIME_CASES = _leadtime_cases()
+
+
+def oracle_leadtime_rollout(case, init36, demand, actions):
+    """Oracle with per-arc lead times; init36 [n,36] = inv[4], so[k][0..3], sh[k][0..3]."""
+    from dataclasses import replace
+    spec = replace(O.scenario_spec("uniform", case["agents"], case["glob"], 100, case["rule"]), info_lt=case["li"],
+                   ship_lt=case["ls"])
+    n = init36.shape[0]
+    orc = O.BeerGameOracle(spec, n)
+    so = [init36[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] for k in range(4)]
+    sh = [init36[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] for k in range(4)]
+    obs0 = orc.reset(init36[:, :4], so, sh, demand)
+    obs, rew = [], []
+    for t in range(actions.shape[0]):
+        o, r, _ = orc.step(actions[t])
+        orc.check_invariant()
+        obs.append(o); rew.append(r)
+    return obs0, np.stack(obs), np.stack(rew)
+
+
+@pytest.mark.parametrize("case", LEADTIME_CASES, ids=[c["id"] for c in LEADTIME_CASES])
+def test_oracle_matches_golden_other_lead_times(case):
+    """Serial chains with other per-arc lead times, recorded from the reference's own Node/Arc classes."""
+    obs0, obs, rew = oracle_leadtime_rollout(case, case["init"][None], case["demand"][None], case["actions"][:, None, :])
+    assert np.array_equal(obs0[0], case["obs0"])
+    assert np.array_equal(obs[:, 0], case["obs"]) and np.array_equal(rew[:, 0], case["rew"])
