@@ -2,7 +2,7 @@
 // (first step: Arc(information_leadtime, shipment_leadtime) other than the beer game's
 // 2,2,2,1 / 2,2,2,2).  The tuned `Env<T>` of supplynet_core.cuh hard-wires those; `GEnv<T>` keeps up to
 // 3 in-flight order slips and 4 shipment slots per arc and takes the lead times from the spec at run time
-// (all positions are resolved with uniform selects over unrolled slots: registers only, no local memory).
+// (slot positions are applied with 0/1 mask arithmetic over unrolled slots: registers only, no local memory).
 //
 // Supported: information and shipment lead times in 1..4 with info + shipment <= 5 per arc.  Beyond that
 // the reference itself fails its on_order == sum(unreceived) assertion at reset (supplynetwork.py:159-160),
@@ -64,6 +64,13 @@ __device__ __forceinline__ void genv_to_words(const GEnv<T>& e, T (&w)[kGStateWo
   w[56] = e.B[3];
 }
 
+// Run-time slot positions are applied with 0/1 mask arithmetic (x += m * v) instead of compare-selects
+// over the slot arrays: nvcc turns select chains over array elements into dynamically indexed local-memory
+// accesses (LDL/STL), which cost this path 3x (profiles/r1_notes.md).  Multiplying by an exact 0 or 1 and
+// adding into a slot that is known to be empty is exact for integers and for finite floats.
+template <typename T>
+__device__ __forceinline__ T mask_of(bool c) { return c ? T(1) : T(0); }
+
 // Arc.reset / Node.reset + before_action(0) for run-time lead times (network_components.py:138-168).
 template <typename T>
 __device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, const T (&in)[kGInitWords], T d0) {
@@ -73,8 +80,8 @@ __device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, con
     T so[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      so[j] = (j < li) ? in[4 + 4 * k + j] : T(0);
-      sh[j] = (j < ls) ? in[20 + 4 * k + j] : T(0);
+      so[j] = in[4 + 4 * k + j] * mask_of<T>(j < li);
+      sh[j] = in[20 + 4 * k + j] * mask_of<T>(j < ls);
     }
     e.inv[k] = in[k];
     // ([0]*4 + shipments + sales_orders)[::-1][:5]: newest slip first, then shipments latest first
@@ -84,8 +91,8 @@ __device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, con
       T v = T(0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (li - 1 - i == j) v = so[j];
-        if (i >= li && ls - 1 - (i - li) == j) v = sh[j];
+        v = v + so[j] * mask_of<T>(li - 1 - i == j);
+        v = v + sh[j] * mask_of<T>(i >= li && ls - 1 - (i - li) == j);
       }
       seq[i] = v;
     }
@@ -111,9 +118,6 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
   for (int k = kF - 1; k >= 0; --k) {
     T u[5] = {q[k], e.U[k][0], e.U[k][1], e.U[k][2], e.U[k][3]};
     const T arr = e.ship[k][0];
-#pragma unroll
-    for (int j = 0; j < kGS - 1; ++j) e.ship[k][j] = e.ship[k][j + 1];
-    e.ship[k][kGS - 1] = T(0);
     e.inv[k] = e.inv[k] + arr;
     T rem = arr;
 #pragma unroll
@@ -129,10 +133,13 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
       s = tmin(e.inv[k + 1], e.B[k]);
       e.inv[k + 1] = e.inv[k + 1] - s;
     }
+    // advance the shipments and append Shipment(s, shipment_leadtime): slot ls-1 is empty after the shift
     const int ls = sp.ls[k];
 #pragma unroll
-    for (int j = 0; j < kGS; ++j)
-      if (j == ls - 1) e.ship[k][j] = s;                          // Shipment(quantity, shipment_leadtime)
+    for (int j = 0; j < kGS; ++j) {
+      const T next = (j + 1 < kGS) ? e.ship[k][j + 1] : T(0);
+      e.ship[k][j] = next + s * mask_of<T>(j == ls - 1);
+    }
     e.B[k] = e.B[k] - s;
     e.U[k][0] = u[0]; e.U[k][1] = u[1]; e.U[k][2] = u[2]; e.U[k][3] = u[3];
     U4[k] = u[4];
@@ -159,13 +166,13 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
     for (int k = 0; k < kF; ++k) {
       const int li = sp.li[k];
       // Order(q, 0, info_leadtime): with lead time 1 this period's order is what arrives now
-      const T arrived = (li == 1) ? q[k] : e.info[k][0];
+      const T head = e.info[k][0];
+      const T arrived = (li == 1) ? q[k] : head;
 #pragma unroll
-      for (int j = 0; j < kGI - 1; ++j) e.info[k][j] = e.info[k][j + 1];
-      e.info[k][kGI - 1] = T(0);
-#pragma unroll
-      for (int j = 0; j < kGI; ++j)
-        if (j == li - 2) e.info[k][j] = q[k];
+      for (int j = 0; j < kGI; ++j) {
+        const T next = (j + 1 < kGI) ? e.info[k][j + 1] : T(0);
+        e.info[k][j] = next + q[k] * mask_of<T>(j == li - 2);
+      }
       if (k < 3) e.lat[k + 1] = arrived;
       e.B[k] = e.B[k] + arrived;
       e.U[k][3] = e.U[k][3] + U4[k];

@@ -318,8 +318,9 @@ struct RolloutPtrs {
 #define SN_PRAGMA_UNROLL(n) _Pragma(SN_STR(unroll n))
 constexpr int kRolloutBlock = SN_ROLLOUT_BLOCK;
 
+// 7 blocks of 64 threads per SM (<= 144 registers): 65,536 envs = 1,024 blocks fit the 148 SMs in ONE wave
 template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
-__global__ void __launch_bounds__(kRolloutBlock)
+__global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock)
 k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
           int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
           const T* __restrict__ actions, const RolloutPtrs out, int use_tma, const T* __restrict__ init,
