@@ -22,7 +22,13 @@
 
 namespace sn {
 
-constexpr int kBlock = 128;
+#ifndef SN_BLOCK
+#define SN_BLOCK 128
+#endif
+#ifndef SN_STEP_MIN_BLOCKS
+#define SN_STEP_MIN_BLOCKS 1
+#endif
+constexpr int kBlock = SN_BLOCK;
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 // ------------------------------------------------------------------------------------------
@@ -250,7 +256,7 @@ struct StepPtrs {
 };
 
 template <typename T, bool IDENT, typename Ops>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, SN_STEP_MIN_BLOCKS)
 k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
        const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
