@@ -8,6 +8,9 @@
 //   k_rollout  n_steps periods with the env held in registers; actions streamed or base-stock
 //              policy evaluated in-kernel; optional trajectory out
 //   k_heuristic  BaseStockPolicy on a batch of observations
+// Every env kernel is written against an `Ops` trait: StdOps = the beer game's lead times (tuned,
+// supplynet_core.cuh), GenOps = run-time per-arc lead times (supplynet_generic.cuh).  The device-side
+// VecNormalize kernels live in vecnorm_kernels.cu.
 // Row-major float observations ([n_envs][obs_dim], what a VecEnv returns) are staged per warp
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
 // the 112-byte-per-thread pattern reaches L2 as full lines.
