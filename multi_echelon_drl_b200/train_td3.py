@@ -42,10 +42,12 @@ def main(argv=None):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    setup = {"hyperparameters": {"td3": {}}}
-    if args.parameters:
-        with open(args.parameters) as fh:
-            setup = yaml.safe_load(fh)
+    # default setup = the example YAML that fits the role (the reference requires -p)
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = args.parameters or os.path.join(here, "setup_example_centralized.yaml" if args.role == "MultiFacility"
+                                           else "setup_example_decentralized.yaml")
+    with open(path) as fh:
+        setup = yaml.safe_load(fh)
     p = setup.get("hyperparameters", {}).get("td3", {})
     if args.scenario == "basic":                      # train_td3.py:52-61
         targets, demand_type, (lb, ub), offset = [48, 43, 41, 30], "Normal", (0, 20), -10
