@@ -640,6 +640,14 @@ template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
                     void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
                     cudaStream_t st, const void* init, float* obs0) {
+  if (kRolloutSmem > 48 * 1024) {            // only with experimental block sizes (SN_ROLLOUT_BLOCK > 192)
+    static bool opted_in = false;
+    if (!opted_in) {
+      cudaFuncSetAttribute(sn::k_rollout<T, POLICY, IDENT, MULTI, Ops>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kRolloutSmem);
+      opted_in = true;
+    }
+  }
   sn::k_rollout<T, POLICY, IDENT, MULTI, Ops><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
       d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
 }
