@@ -54,6 +54,8 @@ def test_td3_learns_to_beat_random_on_basic_retailer():
                     learning_starts=n * 100)
     model = HgeTD3(env, None, cfg)
     model.learn(n * 100 * 14)
-    first, last = model.episode_returns[0], min(model.episode_returns[-3:])
-    assert last > 0.8 * first, (first, model.episode_returns)        # returns are negative costs: higher is better
-    assert max(model.episode_returns[-3:]) > first * 0.75
+    # returns are negative costs (higher is better).  Over seeds 0..2 the random warm-up episode costs about
+    # 17,000 and training reaches 2,500-3,000 (profiles/td3_margin_probe.py); TD3 can be unstable late in a run,
+    # so the check is on the best of the last six episodes with a wide margin.
+    first, best_late = model.episode_returns[0], max(model.episode_returns[-6:])
+    assert best_late > 0.6 * first, (first, model.episode_returns)
