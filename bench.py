@@ -191,6 +191,7 @@ def run_native(args):
     traj_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     stats_bufs = [torch.zeros(16, dtype=torch.float64, device=dev) for _ in range(2)]
     pending, step_no = [], [0]
+    per_rank_ms = {}
 
     def barrier():
         if world > 1:
@@ -240,6 +241,9 @@ def run_native(args):
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank_ms[fn.__name__] = [round(float(x.item()) / steps, 5) for x in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -299,6 +303,8 @@ def run_native(args):
                          "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,
         }
+        if world > 1:
+            line["per_rank_ms_per_step"] = per_rank_ms      # device time of every rank (value uses the max)
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
