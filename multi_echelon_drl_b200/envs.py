@@ -34,14 +34,16 @@ def _apply_mode(sp, env_mode, data_path):
     return replace(sp, demand_pattern="samples", demand_path=data_path)
 
 
-def _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space):
+def _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space, return_dict=False):
     if len(sp.agents) > 1 and not box_action_space:
         raise ValueError("length of agent_managed_facilities >= 1, only box_action_space is allowed. Please specify"
                          "box_action_space=True")                                            # envs.py:175-179
     if n_envs is None:             # the reference's return type: one gym-style env
         space = spaces.Box(sp.action_low, sp.action_high, shape=(sp.n_agents,)) if box_action_space else \
             spaces.Discrete(int(sp.action_high) + 1)
-        return BeerGameEnv(sp, device, dtype or "int32", space, seed)
+        return BeerGameEnv(sp, device, dtype or "int32", space, seed, return_dict)
+    if return_dict:
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is offered by the single env only")
     return SupplyNetVecEnv(sp, n_envs, device, dtype or "float32", 0 if seed is None else seed, episode_source, output,
                            bool(box_action_space))
 
@@ -51,13 +53,11 @@ def make_beer_game_uniform_multi_facility(global_observable=False, agent_managed
                                           env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
                                           dtype=None, seed=None, episode_source="device", output="torch"):
     """The complex scenario (envs.py:289-414): demand U{0..8}, h=0.5, b=1, co-player targets 19/20/20/14."""
-    if return_dict:
-        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
     sp = _apply_mode(sp, env_mode, "./data/deepbeerinventory/demandTs0-9.npy")
     if sp.demand_pattern == "samples" and episode_source == "device":
         episode_source = "numpy_bulk"
-    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
+    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space, return_dict)
 
 
 def make_beer_game_normal_multi_facility(global_observable=False, agent_managed_facilities=None,
@@ -65,13 +65,11 @@ def make_beer_game_normal_multi_facility(global_observable=False, agent_managed_
                                          env_mode="train", box_action_space=False, *, n_envs=None, device="cuda",
                                          dtype=None, seed=None, episode_source="device", output="torch"):
     """The basic scenario (envs.py:163-286): demand round(max(N(10,2),0)), h=(1,.75,.5,.25), b=(10,0,0,0)."""
-    if return_dict:
-        raise NotImplementedError("return_dict=True (per-agent dict observations) is not offered")
     sp = _spec.normal_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init)
     sp = _apply_mode(sp, env_mode, "./data/deepbeerinventory/demandTs1-10-2.npy")
     if sp.demand_pattern == "samples" and episode_source == "device":
         episode_source = "numpy_bulk"
-    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space)
+    return _build(sp, n_envs, device, dtype, seed, episode_source, output, box_action_space, return_dict)
 
 
 def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game", max_period=35, return_dict=False,
@@ -83,13 +81,13 @@ def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game
         raise NotImplementedError("demand_type='deterministic_random' (envs.py:519-520) is not offered")
     if demand_type not in ("classic_beer_game", "normal", "uniform"):
         raise ValueError()
-    if return_dict:
-        raise NotImplementedError("return_dict=True is not offered by the batched env")
     sp = _spec.classic_spec(agent_managed_facilities, max_period, demand_type)
     if n_envs is None:
         if seed:
             import numpy as np
             np.random.seed(seed)                     # envs.py:511-512
-        return BeerGameEnv(sp, device, dtype, spaces.MultiDiscrete([17] * sp.n_agents))
+        return BeerGameEnv(sp, device, dtype, spaces.MultiDiscrete([17] * sp.n_agents), None, return_dict)
+    if return_dict:
+        raise NotImplementedError("return_dict=True (per-agent dict observations) is offered by the single env only")
     return SupplyNetVecEnv(sp, n_envs, device, dtype, 0 if seed is None else seed, episode_source, output,
                            box_action_space=False, multi_discrete=True)

@@ -52,8 +52,10 @@ class BeerGameEnv:
     metadata = {"render.modes": []}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, spec: ScenarioSpec, device="cuda", dtype="int32", action_space=None, seed=None):
+    def __init__(self, spec: ScenarioSpec, device="cuda", dtype="int32", action_space=None, seed=None,
+                 return_dict: bool = False):
         self.spec = spec
+        self.return_dict = return_dict        # envs.py:59,77-78: {agent: state dict} instead of the flat array
         self.sim = BatchedSupplyNetwork(spec, 1, device, dtype)
         self.max_episode_steps = spec.max_episode_steps
         self.global_observable = spec.global_observable
@@ -77,7 +79,7 @@ class BeerGameEnv:
         self.sim.load_episode(init, demand)
         obs = self.sim.reset()
         self.period, self.terminal = 0, False
-        return obs.cpu().numpy()[0]
+        return self._format(obs.cpu().numpy()[0])
 
     def step(self, quantity):
         if self.terminal:
@@ -90,7 +92,14 @@ class BeerGameEnv:
             raise ValueError(f"expected {self.spec.n_agents} order quantities, got {q.shape[1]}")
         obs, _, done = self.sim.step(torch.as_tensor(q), reward64_out=self._r64)
         self.period, self.terminal = self.sim.period, done
-        return obs.cpu().numpy()[0], float(self._r64.item()), bool(done), {}
+        return self._format(obs.cpu().numpy()[0]), float(self._r64.item()), bool(done), {}
+
+    def _format(self, flat: np.ndarray):
+        if not self.return_dict:
+            return flat
+        cast = (lambda x: int(x)) if self.sim.dtype == "int32" else float
+        names = [NODE_NAMES[k] for k in self.spec.obs_nodes]
+        return {name: {key: cast(x) for key, x in zip(_KEYS, flat[7 * i:7 * i + 7])} for i, name in enumerate(names)}
 
     def _full_observation(self) -> np.ndarray:
         """Global 28-number observation of the current state, whatever this env's own observability."""

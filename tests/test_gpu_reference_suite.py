@@ -126,3 +126,18 @@ def test_registry_make_without_batch_returns_single_env_incl_dplusa():
     assert done
     single = R.make("BeerGameNormalWholesalerFullInfo-v0")
     assert single.reset().shape == (28,) and single.action_space.shape == (1,)
+
+
+def test_return_dict_observations_like_the_reference():
+    """return_dict=True (envs.py:59,77-78): {agent: {on_hand, unfilled_demand, latest_demand, unreceived_pipeline_i}}."""
+    from multi_echelon_drl_b200.envs import make_beer_game
+    env = make_beer_game(agent_managed_facilities=["retailer", "wholesaler"], return_dict=True)
+    obs = env.reset()
+    assert list(obs) == ["retailer", "wholesaler"]
+    assert obs["wholesaler"] == {"on_hand": 12, "unfilled_demand": 4, "latest_demand": 4, "unreceived_pipeline_0": 4,
+                                 "unreceived_pipeline_1": 4, "unreceived_pipeline_2": 4, "unreceived_pipeline_3": 4}
+    flat_env = make_beer_game(agent_managed_facilities=["retailer", "wholesaler"])
+    flat = flat_env.reset()
+    obs, r, d, _ = env.step(np.array([3, 5]))
+    f2, r2, _, _ = flat_env.step(np.array([3, 5]))
+    assert r == r2 and [v for a in obs.values() for v in a.values()] == f2.tolist()
