@@ -63,7 +63,7 @@ def main(argv=None):
         env = wrap_action_d_plus_a(env, offset=offset, lb=lb, ub=ub)          # train_td3.py:86-91
     env = VecNormalize(env, clip_obs=100.0, clip_reward=1000.0)
     cfg = TD3Config(batch_size=p.get("batch_size", 128),
-                    net_arch=(p.get("width", 256) * p.get("num_layers", 3),),
+                    net_arch=(p.get("network_width", p.get("width", 256)) * p.get("num_layers", 3),),
                     learning_rate=p.get("learning_rate", 1e-3), tau=p.get("tau", 0.01), train_freq=p.get("train_freq", 32),
                     gradient_steps=p.get("gradient_steps", p.get("train_freq", 32)),
                     action_noise_std=p.get("action_noise_std", 0.4), gamma=p.get("gamma", 0.95),
