@@ -27,7 +27,8 @@ ROLES = ["Retailer", "Wholesaler", "Distributor", "Manufacturer", "MultiFacility
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("-g", "--global-info", type=bool, default=False)     # any non-empty string is True (Q5)
-    ap.add_argument("-p", "--parameters", type=str, default=None, help="experiment YAML (setup_exmaple_*.yaml layout)")
+    ap.add_argument("-p", "--hyperparameters", "--parameters", dest="parameters", type=str, default=None,
+                    help="Path to the experiment setup file (.yaml); default: the packaged example for the role")
     ap.add_argument("--name", type=str, default="td3")
     ap.add_argument("--ordering-rule", type=str, default="a", choices=["a", "d+a"])
     ap.add_argument("--role", type=str, default="MultiFacility", choices=ROLES)
@@ -54,13 +55,13 @@ def main(argv=None):
     else:
         targets, demand_type, (lb, ub), offset = [19, 20, 20, 14], "Uniform", (0, 16), -8
     if p.get("hge_rate_at_start", 0) > 0 and args.role != "MultiFacility":
-        raise ValueError("HGE is only supported for the MultiFacility role")          # train_td3.py:65-66
+        raise NotImplementedError("For now the TD3 with HGE only supports centralized setting")    # train_td3.py:65-66
     env_name = f"BeerGame{demand_type}{args.role}{'FullInfo' * bool(args.global_info)}-v0"
     bsp = BaseStockPolicy(targets, {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1,
                                     "latest_demand": 2}, 7, lb, ub, args.ordering_rule)
     env = make(env_name, n_envs=args.n_envs, dtype="float32", seed=1000 * rank)
     if args.ordering_rule == "d+a":
-        env = wrap_action_d_plus_a(env, offset=offset, lb=lb, ub=ub)          # train_td3.py:86-91
+        env = wrap_action_d_plus_a(env, offset=-(ub - lb) / 2, lb=lb, ub=ub)  # train_td3.py:86-91
     env = VecNormalize(env, clip_obs=100.0, clip_reward=1000.0)
     cfg = TD3Config(batch_size=p.get("batch_size", 128),
                     net_arch=(p.get("network_width", p.get("width", 256)) * p.get("num_layers", 3),),
