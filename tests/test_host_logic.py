@@ -239,3 +239,63 @@ def test_samples_demand_pattern_cycles_rows(tmp_path):
         make_beer_game_uniform_multi_facility(env_mode="test", box_action_space=True)
     with pytest.raises(ValueError):
         make_beer_game_uniform_multi_facility(env_mode="validate", box_action_space=True)
+
+
+def test_multi_item_spec_combination_rules():
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.multi_item import combine_item_specs
+    a = uniform_spec(None, True)
+    b = replace(a, holding_cost=(0.75,) * 4, backorder_cost=(2.0,) * 4)
+    c = combine_item_specs([a, b])
+    assert c.n_items == 2 and c.extra_item_costs == (((0.75,) * 4, (2.0,) * 4),)
+    cs = c.to_c()
+    assert cs.n_items == 2 and list(cs.item_holding_cost[0]) == [0.75] * 4 and list(cs.item_backorder_cost[0]) == [2.0] * 4
+    assert list(cs.holding_cost) == [0.5] * 4
+    with pytest.raises(ValueError):
+        combine_item_specs([a, replace(a, coplayer_target=(1, 2, 3, 4))])       # only costs may differ
+    with pytest.raises(ValueError):
+        combine_item_specs([a] * 5)
+    with pytest.raises(ValueError):
+        combine_item_specs([])
+
+
+def test_spec_lowering_to_c_struct_roundtrip():
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import normal_spec
+    s = replace(normal_spec(["wholesaler", "retailer"], True, 50, True), info_leadtime=(1, 2, 3, 1), ship_leadtime=(4, 3, 2, 2))
+    s = s.with_rule("d+a", -10, 0, 20)
+    c = s.to_c()
+    assert (c.n_facilities, c.n_agents, list(c.agents)[:2], c.global_observable, c.max_episode_steps, c.rule) == (4, 2, [1, 0], 1, 50, 1)
+    assert list(c.info_leadtime) == [1, 2, 3, 1] and list(c.ship_leadtime) == [4, 3, 2, 2]
+    assert list(c.holding_cost) == [1.0, 0.75, 0.5, 0.25] and list(c.backorder_cost) == [10.0, 0, 0, 0]
+    assert list(c.coplayer_target) == [48, 43, 41, 30] and (c.coplayer_lb, c.coplayer_ub) == (0.0, 16.0)
+    assert (c.dpa_offset, c.dpa_lb, c.dpa_ub) == (-10.0, 0.0, 20.0) and c.n_items == 1
+    assert s.obs_dim == 28 and s.obs_nodes == (0, 1, 2, 3) and not s.standard_leadtimes
+    with pytest.raises(ValueError):
+        replace(s, info_leadtime=(1, 2, 3))
+    with pytest.raises(ValueError):
+        s.with_rule("a+d", 0, 0, 1)
+
+
+def test_init_layouts_for_standard_and_generic_lead_times():
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs, init_layout, seeded_episode_inputs
+    std = uniform_spec()
+    gen = replace(std, info_leadtime=(1, 3, 2, 1), ship_leadtime=(4, 2, 3, 1))
+    assert init_layout(std) == (19, (4, 6, 8, 10), (11, 13, 15, 17))
+    assert init_layout(gen) == (36, (4, 8, 12, 16), (20, 24, 28, 32))
+    init, _ = bulk_episode_inputs(gen, 50, np.random.RandomState(0))
+    assert init.shape == (50, 36)
+    for k, (li, ls) in enumerate(zip(gen.info_leadtime, gen.ship_leadtime)):     # slots beyond the lead time stay empty
+        assert (init[:, 4 + 4 * k + li: 8 + 4 * k] == 0).all() and (init[:, 20 + 4 * k + ls: 24 + 4 * k] == 0).all()
+    # per-env streams follow the reference's draw order with the arc's own number of draws
+    init, demand = seeded_episode_inputs(gen, [7])
+    rs = np.random.RandomState(7)
+    inv_r = rs.randint(0, 25); dem = rs.randint(0, 9, 103); rest = [rs.randint(0, 25) for _ in range(3)]
+    assert init[0, 0] == inv_r and np.array_equal(demand[0], dem) and init[0, 1:4].tolist() == rest
+    for k in (3, 2, 1, 0):
+        sh = [rs.randint(0, 9) for _ in range(gen.ship_leadtime[k])]
+        so = [rs.randint(0, 9) for _ in range(gen.info_leadtime[k])]
+        assert init[0, 20 + 4 * k: 20 + 4 * k + len(sh)].tolist() == sh and init[0, 4 + 4 * k: 4 + 4 * k + len(so)].tolist() == so
