@@ -157,3 +157,28 @@ def test_oracle_matches_golden_other_lead_times(case):
     obs0, obs, rew = oracle_leadtime_rollout(case, case["init"][None], case["demand"][None], case["actions"][:, None, :])
     assert np.array_equal(obs0[0], case["obs0"])
     assert np.array_equal(obs[:, 0], case["obs"]) and np.array_equal(rew[:, 0], case["rew"])
+
+
+def test_seeded_streams_for_other_lead_times_match_reference():
+    """The product's per-env stream generator replays the reference's RNG draw order for chains with other
+    lead times too (number of shipment / sales-order draws per arc follows the arc's lead times)."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs
+    z = np.load(f"{GOLDEN}/leadtimes.npz")
+    for cid, case in enumerate(LEADTIME_CASES):
+        spec = replace(uniform_spec(case["agents"], case["glob"], 100), info_leadtime=case["li"], ship_leadtime=case["ls"])
+        init, demand = seeded_episode_inputs(spec, [900 + cid])
+        if spec.standard_leadtimes:           # packed 19-word layout -> compare through the 36-word one
+            full = np.zeros(36, dtype=np.int64)
+            full[:4] = init[0, :4]
+            off = 4
+            for k in range(4):
+                full[4 + 4 * k: 4 + 4 * k + case["li"][k]] = init[0, off: off + case["li"][k]]; off += case["li"][k]
+            for k in range(4):
+                full[20 + 4 * k: 22 + 4 * k] = init[0, off: off + 2]; off += 2
+            got = full
+        else:
+            got = init[0]
+        assert np.array_equal(got, case["init"]), case["id"]
+        assert np.array_equal(demand[0], case["demand"]), case["id"]
