@@ -13,8 +13,6 @@ quantities that are not numbers (network_components.py:21-29).
 """
 from __future__ import annotations
 
-import numbers
-
 import numpy as np
 import torch
 

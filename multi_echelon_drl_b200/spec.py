@@ -7,8 +7,8 @@ include/supplynet.h for every kernel launch.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, replace
-from typing import Optional, Sequence, Tuple
+from dataclasses import dataclass, replace
+from typing import Optional, Tuple
 
 from . import _lib
 

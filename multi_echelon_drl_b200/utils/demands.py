@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..spec import INFO_LEADTIME, SHIP_LEADTIME, ScenarioSpec
+from ..spec import ScenarioSpec
 
 INIT_WORDS = 19
 _SO_OFF = (4, 6, 8, 10)
