@@ -37,7 +37,6 @@ class _SupplyNetworkView:
     def get_state(self, node_name: str) -> dict:
         """The 7 numbers of node `node_name` as the reference's dict (observation of the current state,
         global view)."""
-        from dataclasses import replace
         env = self._env
         k = NODE_NAMES.index(node_name)
         full = env._full_observation()
