@@ -296,6 +296,43 @@ class HgeTD3:
         self.timers.flush()
         return self
 
+    @torch.no_grad()
+    def evaluate(self, eval_env, n_episodes: int = 1):
+        """EvalCallback's evaluate_policy (train_td3.py:126-135: 100 deterministic episodes): plays
+        `n_episodes` episodes of every env of `eval_env` with the deterministic actor.  `eval_env` is a
+        VecNormalize whose observation statistics are synchronised from the training env first (SB3's
+        sync_envs_normalization) and frozen; returns are the ORIGINAL (un-normalised) episode returns.
+        Returns (mean, std, number of episodes)."""
+        if self.vec_normalize is not None and isinstance(eval_env, VecNormalize):
+            eval_env._obs_rms[0].copy_(self.vec_normalize._obs_rms[0])
+            eval_env._ret_rms[0].copy_(self.vec_normalize._ret_rms[0])
+            eval_env.training = False
+        rets = []
+        obs = eval_env.reset()
+        while len(rets) < n_episodes:
+            obs, _, dones, infos = eval_env.step(self.unscale_action(self.actor(obs)))
+            if infos.terminal_observation is not None:
+                rets.append(infos.episode_return.clone())
+        r = torch.cat(rets)
+        return float(r.mean().item()), float(r.std().item()), int(r.numel())
+
+    def save(self, path: str):
+        """Best-model / env-statistics checkpoint (EvalCallback best_model_save_path + SaveEnvStatsCallback,
+        utils/callbacks.py:26-37)."""
+        torch.save({"actor": self.actor.state_dict(), "critics": self.critics.state_dict(),
+                    "actor_target": self.actor_target.state_dict(), "critics_target": self.critics_target.state_dict(),
+                    "vec_normalize": self.vec_normalize.state_dict() if self.vec_normalize is not None else None,
+                    "num_timesteps": self.num_timesteps, "n_updates": self.n_updates}, path)
+
+    def load(self, path: str):
+        sd = torch.load(path, map_location=self.device)
+        self.actor.load_state_dict(sd["actor"]); self.critics.load_state_dict(sd["critics"])
+        self.actor_target.load_state_dict(sd["actor_target"]); self.critics_target.load_state_dict(sd["critics_target"])
+        if sd["vec_normalize"] is not None and self.vec_normalize is not None:
+            self.vec_normalize.load_state_dict(sd["vec_normalize"])
+        self.num_timesteps, self.n_updates = sd["num_timesteps"], sd["n_updates"]
+        return self
+
     def time_split(self):
         t = self.timers
         tot = max(t.env_step + t.heuristic + t.policy_forward + t.update, 1e-12)

@@ -59,3 +59,31 @@ def test_td3_learns_to_beat_random_on_basic_retailer():
     # so the check is on the best of the last six episodes with a wide margin.
     first, best_late = model.episode_returns[0], max(model.episode_returns[-6:])
     assert best_late > 0.6 * first, (first, model.episode_returns)
+
+
+def test_evaluate_and_checkpoint_roundtrip(tmp_path):
+    """EvalCallback-style deterministic evaluation on a frozen, statistics-synchronised VecNormalize, and the
+    best-model + env-statistics checkpoint (SaveEnvStatsCallback)."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    mk = lambda seed: VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=128, dtype="float32", seed=seed),
+                                   clip_obs=100.0, clip_reward=1000.0)
+    cfg = TD3Config(net_arch=(32,), train_freq=8, gradient_steps=2, buffer_size=128 * 40, learning_starts=128 * 8,
+                    hge_rate_at_start=0.0)
+    model = HgeTD3(mk(0), None, cfg)
+    model.learn(128 * 24)
+    eval_env = mk(99)
+    mean, std, n = model.evaluate(eval_env, n_episodes=2)
+    assert n == 256 and np.isfinite(mean) and mean < 0 and std > 0
+    assert torch.equal(eval_env._obs_rms[0], model.vec_normalize._obs_rms[0]) and eval_env.training is False
+    mean2, _, _ = model.evaluate(mk(99), n_episodes=2)
+    assert mean2 == mean                                    # deterministic policy + same env seed
+    path = str(tmp_path / "best_model.pt")
+    model.save(path)
+    other = HgeTD3(mk(0), None, cfg).load(path)
+    assert other.num_timesteps == model.num_timesteps
+    for a, b in zip(other.actor.parameters(), model.actor.parameters()):
+        assert torch.equal(a, b)
+    assert torch.equal(other.vec_normalize._obs_rms[0], model.vec_normalize._obs_rms[0])
+    assert other.evaluate(mk(99), n_episodes=2)[0] == mean
