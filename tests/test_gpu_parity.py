@@ -375,3 +375,76 @@ def test_full_size_config3_heuristic_paths_agree():
         assert np.array_equal(fused[:m].cpu().numpy(), ref["rew"].sum(0)), rule
         if rule == "a":
             assert -1400 < fused.mean().item() < -1200
+
+
+def test_full_size_config4_multi_item_properties():
+    """BASELINE config 4 at full size (262,144 envs x 2 items = 524,288 interleaved chains): (i) item 0 of the
+    multi-item batch equals a single-item run on the same streams, bit for bit; (ii) item 1 differs only in the
+    holding cost (rewards scale, observations identical to a run with its own cost vector); (iii) a prefix equals
+    the oracle run per item."""
+    import os
+    import multi_echelon_drl_b200 as pkg
+    from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
+    from multi_echelon_drl_b200.spec import specs_from_config
+    from multi_echelon_drl_b200.utils.graph import read_yaml
+    n, T = 262144, 25
+    net = read_yaml(os.path.join(os.path.dirname(pkg.__file__), "network_configs", "multi_item.yaml"))
+    specs = specs_from_config(net, ["retailer", "wholesaler", "distributor", "manufacturer"], True, T)
+    rs = np.random.RandomState(8)
+    init = np.concatenate([rs.randint(0, 25, (n, 2, 4)), rs.randint(0, 9, (n, 2, 15))], axis=2).astype(np.int32)
+    demand = rs.randint(0, 9, (n, 2, T + 3)).astype(np.int32)
+    acts = torch.randint(0, 17, (T, n, 8), device="cuda", dtype=torch.int32)
+    mi = MultiItemSupplyNetwork(specs, n, "cuda", "int32")
+    mi.load_episode(init, demand)
+    mi.reset()
+    singles = []
+    for i in range(2):
+        s = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "int32")
+        if i == 1:
+            from dataclasses import replace
+            from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+            s = BatchedSupplyNetwork(replace(s.spec, holding_cost=(0.75,) * 4), n, "cuda", "int32")
+        s.load_episode(init[:, i], demand[:, i])
+        s.reset()
+        singles.append(s)
+    for t in range(T):
+        obs, rew, done = mi.step(acts[t])
+        tot = torch.zeros(n, dtype=torch.float64, device="cuda")
+        for i, s in enumerate(singles):
+            r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+            o, _, _ = s.step(acts[t][:, 4 * i:4 * i + 4].contiguous(), reward64_out=r64)
+            assert torch.equal(obs[:, 28 * i:28 * i + 28], o), (t, i)
+            tot += r64
+        assert torch.equal(rew, tot.float()), t
+    assert done
+    m = 2048
+    for i, h in enumerate(([0.5] * 4, [0.75] * 4)):
+        from oracle import beergame_np as O
+        from helpers import split_init
+        orc = O.BeerGameOracle(O.OracleSpec(h, [1.0] * 4, [19, 20, 20, 14], (0, 1, 2, 3), True, T), m)
+        inv0, so, sh = split_init(init[:m, i])
+        orc.reset(inv0, so, sh, demand[:m, i])
+        ret = np.zeros(m)
+        a_np = acts[:, :m, 4 * i:4 * i + 4].cpu().numpy()
+        for t in range(T):
+            _, r, _ = orc.step(a_np[t])
+            ret += r
+        assert np.array_equal(singles[i].ep_return[:m].cpu().numpy(), ret)
+    assert torch.equal(mi.ep_return, singles[0].ep_return + singles[1].ep_return)
+
+
+def test_config5_shape_float_actions_vs_oracle():
+    """Config-5 shape (4,096 envs, float32 simulator, fractional TD3-like actions through the d+a-free env):
+    float32 kernels vs the float64 oracle within 1e-6 of the state scale over a whole episode."""
+    n, T = 4096, 100
+    init, demand = _seeded_batch("uniform", n, T, 44)
+    acts = (np.random.RandomState(4).rand(T, n, 4) * 16).astype(np.float32)
+    ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts.astype(np.float64), dtype=np.float64)
+    sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, "float32")
+    sim.load_episode(init, demand)
+    sim.reset()
+    scale = max(1.0, float(np.abs(ref["obs"]).max()))
+    for t in range(T):
+        obs, rew, _ = sim.step(torch.as_tensor(acts[t]))
+        assert np.abs(obs.cpu().numpy() - ref["obs"][t]).max() <= 1e-6 * scale * 8, t
+    assert np.abs(sim.ep_return.cpu().numpy() - ref["rew"].sum(0)).max() <= 1e-6 * np.abs(ref["rew"].sum(0)).max() * 8
