@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 3
+#define SN_ABI_VERSION 4
 
 #define SN_MAX_FACILITIES 4
 #define SN_MAX_ITEMS 4
@@ -139,7 +139,9 @@ int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
  *   ep_return     device, double [n_envs] (in/out, may be NULL): += reward (Monitor's "r")
  *   stats         device, double [SN_STATS_WORDS] (in/out, may be NULL): += totals over envs:
  *                 [0] env-steps, [1] sum reward, [2..5] sum holding cost per facility,
- *                 [6..9] sum backorder cost per facility (warp/block reduced, one atomic per block)
+ *                 [6..9] sum backorder cost per facility (warp/block reduced, one atomic per block);
+ *                 when the step ends the episode and ep_return is given also [10] episodes,
+ *                 [11] sum of episode returns, [12] sum of squared episode returns
  * Returns SN_ERR_TERMINAL if period >= max_episode_steps. */
 int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period,
                 void* state, const void* actions, const void* demand_next,
@@ -208,6 +210,17 @@ int32_t sn_vecnorm_update(int64_t n_envs, int32_t obs_dim, const float* obs, con
 int32_t sn_vecnorm_apply(int64_t n_envs, int32_t obs_dim, const float* obs, float* obs_out, const float* reward,
                          float* reward_out, const double* obs_rms, const double* ret_rms, float clip_obs,
                          float clip_reward, double epsilon, int32_t reset_returns, double* returns, void* stream);
+
+/* ---- device-side table generation for throughput runs -------------------------------------------------
+ * Fill `count` elements of a demand / init table (dtype as everywhere) with the reference's distributions,
+ * drawn from a Philox-4x32-10 counter stream (seed, offset + element/4): uniform integers in
+ * [low, high_exclusive) like np.random.randint (utils/demands.py:44; network_components.py:143,157,297), or
+ * round(max(mean + sd*N(0,1), 0)) (utils/demands.py:47).  Same distributions as the reference, NOT numpy's
+ * MT19937 streams: parity runs feed host-generated tables.  dst must be 16-byte aligned. */
+int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
+                        uint64_t offset, void* stream);
+int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
+                              uint64_t offset, void* stream);
 
 #ifdef __cplusplus
 }

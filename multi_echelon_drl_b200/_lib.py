@@ -16,7 +16,7 @@ SN_RULE_A, SN_RULE_D_PLUS_A = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SnSpec(C.Structure):
@@ -71,6 +71,8 @@ SIGNATURES = {
                           _P, _P, _P, _P, _P, _P, _P]),
     "sn_vecnorm_update": (_I32, [_I64, _I32, _P, _P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
     "sn_vecnorm_apply": (_I32, [_I64, _I32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_double, _I32, _P, _P]),
+    "sn_fill_uniform": (_I32, [_I32, _P, _I64, _I32, _I32, C.c_uint64, C.c_uint64, _P]),
+    "sn_fill_normal_demand": (_I32, [_I32, _P, _I64, C.c_double, C.c_double, C.c_uint64, C.c_uint64, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -1,0 +1,105 @@
+// random_fill.cu — device-side generation of demand / initial-state tables for THROUGHPUT runs
+// (episode_source="device" of the VecEnv).  Philox-4x32-10 counter-based generator: element i of a
+// fill with (seed, offset) is a pure function of (seed, offset + i/4), so tables are reproducible and
+// independent of the launch geometry.  These streams have the reference's distributions
+// (utils/demands.py:44,47; network_components.py:143,157,297) but are NOT numpy's MT19937 streams:
+// parity runs use host-generated tables (utils/demands.py seeded_episode_inputs) instead.
+#include "../../include/supplynet.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace snr {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fill_uniform(T* __restrict__ dst, int64_t count, int32_t lo, uint32_t range, uint64_t seed, uint64_t offset) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // quad index
+  const int64_t i = q * 4;
+  if (i >= count) return;
+  const uint64_t c = offset + (uint64_t)q;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+  T v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = (T)(lo + (int32_t)(((uint64_t)u[j] * range) >> 32));   // multiply-shift: bias < range / 2^32
+  if (i + 4 <= count && sizeof(T) == 4) {
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i + j < count) dst[i + j] = v[j];
+  }
+}
+
+// round(max(mean + sd * z, 0)) with z ~ N(0,1) by Box-Muller (utils/demands.py:47)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fill_normal_demand(T* __restrict__ dst, int64_t count, float mean, float sd, uint64_t seed, uint64_t offset) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = q * 4;
+  if (i >= count) return;
+  const uint64_t c = offset + (uint64_t)q;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;                   // 2^-32
+  const float u0 = ((float)r.x + 0.5f) * k, u1 = (float)r.y * k, u2 = ((float)r.z + 0.5f) * k, u3 = (float)r.w * k;
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i + j < count) dst[i + j] = (T)rintf(fmaxf(mean + sd * z[j], 0.0f));
+}
+
+}  // namespace snr
+
+extern "C" {
+
+int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
+                        uint64_t offset, void* stream) {
+  if (!dst || count < 1 || high_exclusive <= low) return SN_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) return SN_ERR_INVALID;
+  const uint32_t range = (uint32_t)(high_exclusive - low);
+  const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: snr::k_fill_uniform<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, low, range, seed, offset); break;
+    case SN_F32: snr::k_fill_uniform<float><<<grid, 256, 0, st>>>((float*)dst, count, low, range, seed, offset); break;
+    case SN_F64: snr::k_fill_uniform<double><<<grid, 256, 0, st>>>((double*)dst, count, low, range, seed, offset); break;
+    default: return SN_ERR_INVALID;
+  }
+  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+}
+
+int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
+                              uint64_t offset, void* stream) {
+  if (!dst || count < 1 || sd < 0) return SN_ERR_INVALID;
+  const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: snr::k_fill_normal_demand<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, (float)mean, (float)sd, seed, offset); break;
+    case SN_F32: snr::k_fill_normal_demand<float><<<grid, 256, 0, st>>>((float*)dst, count, (float)mean, (float)sd, seed, offset); break;
+    case SN_F64: snr::k_fill_normal_demand<double><<<grid, 256, 0, st>>>((double*)dst, count, (float)mean, (float)sd, seed, offset); break;
+    default: return SN_ERR_INVALID;
+  }
+  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kBlock, SN_STEP_MIN_BLOCKS)
 k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
        const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[kWarpsPerBlock * 10];
+  __shared__ double red[kWarpsPerBlock * 13];
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
   typename Ops::E e;
@@ -298,12 +298,18 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     st.drain();
   }
   if (out.stats != nullptr) {
-    double v[10];
+    double v[13];
     v[0] = valid ? 1.0 : 0.0;
     v[1] = so.reward;
 #pragma unroll
     for (int k = 0; k < kF; ++k) { v[2 + k] = so.hold[k]; v[6 + k] = so.back[k]; }
-    block_reduce_add<10, kWarpsPerBlock>(v, out.stats, red);
+    // episode moments (Monitor's episode statistics) when this step ends the episode
+    const bool ep = valid && terminal != 0 && out.ep_return != nullptr;
+    const double ret = ep ? out.ep_return[env] : 0.0;
+    v[10] = ep ? 1.0 : 0.0;
+    v[11] = ret;
+    v[12] = ret * ret;
+    block_reduce_add<13, kWarpsPerBlock>(v, out.stats, red);
   }
 }
 
@@ -335,7 +341,7 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
           const T* __restrict__ actions, const RolloutPtrs out, int use_tma, const T* __restrict__ init,
           float* __restrict__ obs0) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[(kRolloutBlock / 32) * 10];
+  __shared__ double red[(kRolloutBlock / 32) * 13];
   const int64_t env = (int64_t)blockIdx.x * kRolloutBlock + threadIdx.x;
   const bool valid = env < n;
   const int64_t envc = valid ? env : (n - 1);       // tail lanes shadow the last env (loads only)
@@ -397,16 +403,24 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
   const bool ended = (period0 + n_steps >= sp.t_max);
   if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
   st.drain();
+  double ep_total = acc[1];                 // return of the whole episode, if this launch can know it
   if (valid) {
     if (state != nullptr) Ops::store(state, ld, env, e);
-    if (out.ep_return) out.ep_return[env] = (init != nullptr ? 0.0 : out.ep_return[env]) + acc[1];
+    if (out.ep_return) {
+      ep_total = (init != nullptr ? 0.0 : out.ep_return[env]) + acc[1];
+      out.ep_return[env] = ep_total;
+    }
   }
   if (out.stats != nullptr) {
-    if (!valid) {
+    double v[13];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) acc[i] = 0.0;
-    }
-    block_reduce_add<10, kRolloutBlock / 32>(acc, out.stats, red);
+    for (int i = 0; i < 10; ++i) v[i] = valid ? acc[i] : 0.0;
+    // episode moments when the episode ends in this launch and its full return is known here
+    const bool ep = valid && ended && (init != nullptr || out.ep_return != nullptr || period0 == 0);
+    v[10] = ep ? 1.0 : 0.0;
+    v[11] = ep ? ep_total : 0.0;
+    v[12] = ep ? ep_total * ep_total : 0.0;
+    block_reduce_add<13, kRolloutBlock / 32>(v, out.stats, red);
   }
 }
 

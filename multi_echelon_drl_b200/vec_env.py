@@ -21,7 +21,9 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import spaces
+import ctypes as C
+
+from . import _lib, spaces
 from .simulator import BatchedSupplyNetwork
 from .spec import ScenarioSpec
 from .utils import demands as _dem
@@ -120,8 +122,7 @@ class SupplyNetVecEnv(_VecEnvBase):
         seed = 0 if seed is None else int(seed)
         self._seed = seed
         if self.episode_source == "device":
-            self._gen = torch.Generator(device=self.device)
-            self._gen.manual_seed(seed)
+            self._ctr = 0                      # Philox counter offset: advances with every generated table
         elif self.episode_source == "numpy_bulk":
             self._rs = np.random.RandomState(seed)
         else:
@@ -141,26 +142,30 @@ class SupplyNetVecEnv(_VecEnvBase):
 
     def _device_episode(self):
         """Same distributions as utils/demands.py / Arc.reset / Node.reset, drawn on the device with
-        torch's Philox generator directly in the structure-of-arrays layout (throughput path; not
-        stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity)."""
-        sp, sim, g = self.spec, self.sim, self._gen
+        the library's Philox-4x32-10 counter streams directly in the structure-of-arrays layout (throughput
+        path; not stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity)."""
+        sp, sim = self.spec, self.sim
+        lib, dt, st = sim.lib, sim.dtype_code, sim._stream()
         a, b = sp.demand_params
-        # in-place generation in the quantity dtype: one pass over the table, no temporaries
+        seed = self._seed & 0xFFFFFFFFFFFFFFFF
+
+        def fill_uniform(t, lo, hi):
+            _lib.check(lib.sn_fill_uniform(dt, C.c_void_p(t.data_ptr()), t.numel(), int(lo), int(hi), seed, self._ctr, st))
+            self._ctr += (t.numel() + 3) // 4
+
+        # one launch per table, written in place in the structure-of-arrays layout (sn_fill_* in random_fill.cu)
         if sp.demand_pattern == "uniform":
-            sim.demand.random_(int(a), int(b) + 1, generator=g)
+            fill_uniform(sim.demand, a, int(b) + 1)
         elif sp.demand_pattern == "normal":
-            if sim.demand.is_floating_point():
-                sim.demand.normal_(float(a), float(b), generator=g).clamp_min_(0).round_()
-            else:
-                d = torch.empty(sim.demand.shape, dtype=torch.float32, device=self.device)
-                d.normal_(float(a), float(b), generator=g).clamp_min_(0).round_()
-                sim.demand.copy_(d)
+            _lib.check(lib.sn_fill_normal_demand(dt, C.c_void_p(sim.demand.data_ptr()), sim.demand.numel(), float(a),
+                                                 float(b), seed, self._ctr, st))
+            self._ctr += (sim.demand.numel() + 3) // 4
         else:
             sim.demand[:4].fill_(4)
             sim.demand[4:].fill_(8)
         if sp.random_init:
-            sim.init[:4].random_(sp.init_inventory[0], sp.init_inventory[1], generator=g)
-            sim.init[4:].random_(sp.init_pipeline[0], sp.init_pipeline[1], generator=g)
+            fill_uniform(sim.init[:4], sp.init_inventory[0], sp.init_inventory[1])
+            fill_uniform(sim.init[4:], sp.init_pipeline[0], sp.init_pipeline[1])
             # (for non-standard lead times the kernels ignore pipeline slots beyond an arc's lead time)
         else:
             sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=self.device).to(sim.tdtype)[:, None]
@@ -227,7 +232,6 @@ class SupplyNetVecEnv(_VecEnvBase):
         initial states per episode from this env's episode source.  `policy` is a
         `utils.heuristics.BaseStockPolicy` or `simulator.BasePolicyParams`.  Returns the statistics
         vector (float64 [16], see distributed.py) accumulated over the episodes, on the device."""
-        from .distributed import add_episode_moments
         params = getattr(policy, "params", policy)
         sim = self.sim
         keep = sim.track_stats
@@ -235,8 +239,7 @@ class SupplyNetVecEnv(_VecEnvBase):
         sim.stats.zero_()
         for _ in range(int(n_episodes)):
             self._next_episode()
-            sim.episode(policy=params, write_state=False)
-            add_episode_moments(sim.stats, sim.ep_return)
+            sim.episode(policy=params, write_state=False)      # statistics incl. episode moments accumulate in-kernel
             self.episodes_done += self.num_envs
         sim.track_stats = keep
         return sim.stats

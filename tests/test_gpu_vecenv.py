@@ -268,3 +268,36 @@ def test_kernels_are_cuda_graph_capturable():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(sim.ep_return, want_ret) and torch.equal(sim.obs, want_obs)
+
+
+def test_philox_table_generation_kernels():
+    """sn_fill_uniform / sn_fill_normal_demand: bounds, moments, determinism in (seed, offset), independence of
+    the launch geometry (a table equals the concatenation of its parts when offsets continue), ragged counts."""
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = 1_000_003
+    for code, dt in ((_lib.SN_I32, torch.int32), (_lib.SN_F32, torch.float32), (_lib.SN_F64, torch.float64)):
+        a = torch.full((n + 5,), -7, dtype=dt, device="cuda")
+        _lib.check(lib.sn_fill_uniform(code, C.c_void_p(a.data_ptr()), n, 0, 9, 123, 0, st))
+        v = a[:n].double()
+        assert (a[n:] == -7).all() and v.min() == 0 and v.max() == 8 and (v == v.round()).all()
+        assert abs(v.mean().item() - 4.0) < 0.01 and abs(v.var().item() - 80 / 12) < 0.05
+        b = torch.empty_like(a)
+        _lib.check(lib.sn_fill_uniform(code, C.c_void_p(b.data_ptr()), n, 0, 9, 123, 0, st))
+        assert torch.equal(a[:n], b[:n])
+        _lib.check(lib.sn_fill_uniform(code, C.c_void_p(b.data_ptr()), n, 0, 9, 124, 0, st))
+        assert not torch.equal(a[:n], b[:n])
+    # offsets continue the stream: two halves == one table
+    whole = torch.empty(4096, dtype=torch.int32, device="cuda")
+    parts = torch.empty(4096, dtype=torch.int32, device="cuda")
+    _lib.check(lib.sn_fill_uniform(_lib.SN_I32, C.c_void_p(whole.data_ptr()), 4096, 3, 25, 9, 100, st))
+    _lib.check(lib.sn_fill_uniform(_lib.SN_I32, C.c_void_p(parts.data_ptr()), 2048, 3, 25, 9, 100, st))
+    _lib.check(lib.sn_fill_uniform(_lib.SN_I32, C.c_void_p(parts[2048:].data_ptr()), 2048, 3, 25, 9, 100 + 512, st))
+    assert torch.equal(whole, parts) and whole.min() == 3 and whole.max() == 24
+    d = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib.sn_fill_normal_demand(_lib.SN_I32, C.c_void_p(d.data_ptr()), n, 10.0, 4.0, 5, 0, st))
+    dd = d.double()                                   # the reference's own test: N(10,4) clipped at 0 (tests/test_demands.py:46-49)
+    assert abs(dd.mean().item() - 10) < 0.1 and abs(dd.std().item() - 4) < 0.04 and dd.min() == 0
+    assert lib.sn_fill_uniform(_lib.SN_I32, C.c_void_p(d.data_ptr()), n, 5, 5, 0, 0, st) == _lib.SN_ERR_INVALID
