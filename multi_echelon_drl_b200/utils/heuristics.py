@@ -8,8 +8,9 @@
 Differences from the reference, on purpose:
   * a batch is evaluated per env.  The reference flattens the batch and reads only row 0
     (utils/heuristics.py:44-52); `row0_broadcast=True` reproduces that literally.
-  * the dict path (per-agent state dicts, used by the reference's co-players inside the env) is kept
-    as plain Python for API parity; inside the batched env the co-players' policy runs in the kernel.
+  * the dict path (per-agent state dicts, used by the reference's co-players inside the env) goes through
+    the same kernel (there is no CPU evaluation anywhere); inside the batched env the co-players' policy is
+    part of the step kernel.
 """
 from __future__ import annotations
 
@@ -44,15 +45,17 @@ class BaseStockPolicy(InventoryPolicy):
 
     def get_order_quantity(self, observation):
         if isinstance(observation, dict):
-            # reference dict path (utils/heuristics.py:60-75): one entry per agent -> shape (n_agents, n_targets)
-            out = []
-            for _, st in observation.items():
-                on_order = sum(st[f"unreceived_pipeline_{i}"] for i in range(4))
-                q = self.target_levels - (st["on_hand"] + on_order - st["unfilled_demand"])
-                if self.rule == "d+a":
-                    q = q - st["latest_demand"]
-                out.append(q)
-            return np.clip(out, self.lb, self.ub)
+            # reference dict path (utils/heuristics.py:60-75): one entry per agent -> shape (n_agents, n_targets),
+            # every target applied to that agent's own state.  Evaluated by the same CUDA kernel: the agent's 7
+            # numbers are replicated once per target column.
+            keys = ("on_hand", "unfilled_demand", "latest_demand", "unreceived_pipeline_0", "unreceived_pipeline_1",
+                    "unreceived_pipeline_2", "unreceived_pipeline_3")
+            m = self.target_levels.shape[0]
+            if m > 4:
+                raise NotImplementedError("the kernel evaluates at most 4 targets per state")
+            rows = np.array([[st[k] for k in keys] * m for st in observation.values()], dtype=np.float32)
+            out = heuristic_actions(self.params, torch.as_tensor(rows).cuda())
+            return out.cpu().numpy().astype(np.float64)
         if isinstance(observation, np.ndarray):
             observation = torch.as_tensor(observation, dtype=torch.float32).cuda()
             return heuristic_actions(self.params, observation).cpu().numpy().astype(np.float64)

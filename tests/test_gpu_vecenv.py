@@ -301,3 +301,31 @@ def test_philox_table_generation_kernels():
     dd = d.double()                                   # the reference's own test: N(10,4) clipped at 0 (tests/test_demands.py:46-49)
     assert abs(dd.mean().item() - 10) < 0.1 and abs(dd.std().item() - 4) < 0.04 and dd.min() == 0
     assert lib.sn_fill_uniform(_lib.SN_I32, C.c_void_p(d.data_ptr()), n, 5, 5, 0, 0, st) == _lib.SN_ERR_INVALID
+
+
+def test_heuristic_dict_path_matches_reference_golden():
+    from conftest import GOLDEN
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    z = np.load(f"{GOLDEN}/heuristic.npz")
+    keys = ["on_hand", "unfilled_demand", "latest_demand"] + [f"unreceived_pipeline_{i}" for i in range(4)]
+    obs = z["uniform_obs"]
+    for rule in ("a", "d+a"):
+        for f, tg in enumerate([19, 20, 20, 14]):
+            pol = BaseStockPolicy([tg], rule=rule)
+            for i in (0, 5, 40, 63):
+                st = {k: obs[i, 7 * f + j] for j, k in enumerate(keys)}
+                got = pol.get_order_quantity({"x": st})
+                assert got.shape == (1, 1)
+                np.testing.assert_allclose(got.item(), z[f"uniform_{rule}_dict"][i, f], rtol=1e-6, atol=1e-6)
+    both = BaseStockPolicy([19, 14], rule="a").get_order_quantity({"x": {k: obs[0, j] for j, k in enumerate(keys)}})
+    st0 = {"x": {k: obs[0, j] for j, k in enumerate(keys)}}
+    assert both.shape == (1, 2)                                          # two targets applied to one state
+    assert both[0, 0] == BaseStockPolicy([19], rule="a").get_order_quantity(st0).item()
+    assert both[0, 1] == BaseStockPolicy([14], rule="a").get_order_quantity(st0).item()
+    with pytest.raises(TypeError):
+        BaseStockPolicy([1]).get_order_quantity(3)
+    with pytest.raises(NotImplementedError):
+        BaseStockPolicy([1], array_index={"on_hand": 1, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 0,
+                                          "latest_demand": 2})
+
+

@@ -115,27 +115,6 @@ def test_lazy_infos_behaves_like_a_list_of_dicts():
     assert len(done[0:2]) == 2
 
 
-def test_heuristic_dict_path_matches_reference_golden():
-    pytest.importorskip("torch")
-    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
-    z = np.load(f"{GOLDEN}/heuristic.npz")
-    keys = ["on_hand", "unfilled_demand", "latest_demand"] + [f"unreceived_pipeline_{i}" for i in range(4)]
-    obs = z["uniform_obs"]
-    for rule in ("a", "d+a"):
-        for f, tg in enumerate([19, 20, 20, 14]):
-            pol = BaseStockPolicy([tg], rule=rule)
-            for i in (0, 5, 40, 63):
-                st = {k: obs[i, 7 * f + j] for j, k in enumerate(keys)}
-                got = pol.get_order_quantity({"x": st})
-                assert got.shape == (1, 1)
-                np.testing.assert_allclose(got.item(), z[f"uniform_{rule}_dict"][i, f], rtol=1e-6, atol=1e-6)
-    with pytest.raises(TypeError):
-        BaseStockPolicy([1]).get_order_quantity(3)
-    with pytest.raises(NotImplementedError):
-        BaseStockPolicy([1], array_index={"on_hand": 1, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 0,
-                                          "latest_demand": 2})
-
-
 def test_shard_ranges_partition_the_batch():
     from multi_echelon_drl_b200.distributed import shard_range
     for n, w in ((1048576, 8), (65536, 4), (10, 3), (7, 8), (1, 1)):
