@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 4
+#define SN_ABI_VERSION 5
 
 #define SN_MAX_FACILITIES 4
 #define SN_MAX_ITEMS 4
@@ -59,7 +59,7 @@ enum {
  * ordering rule of utils/wrappers.py:6-31.  Node k: 0 retailer .. 3 manufacturer; arc k is the
  * arc whose customer is node k. */
 typedef struct sn_spec {
-  int32_t n_facilities;                       /* must be 4                                    */
+  int32_t n_facilities;                       /* 1..4: the first n of retailer..manufacturer; arc n-1 buys from the external supplier */
   int32_t info_leadtime[SN_MAX_FACILITIES];   /* Arc.information_leadtime, 1..4; beer game 2,2,2,1 */
   int32_t ship_leadtime[SN_MAX_FACILITIES];   /* Arc.shipment_leadtime, 1..4, info+ship <= 5; 2,2,2,2 */
   int32_t n_agents;                           /* 1..4                                         */

@@ -40,6 +40,10 @@ struct DevSpec {
   double h[kMaxItems][kF], b[kMaxItems][kF];   // per item (chain c belongs to item c % n_items)
   int n_items;
   int li[kF], ls[kF];  // information / shipment lead time of arc k (generic path, supplynet_generic.cuh)
+  int nf;              // real facilities (1..4).  Chains shorter than 4 run on the generic path with the missing
+                       // upstream nodes as phantoms: stock `big`, zero costs, never ordering, never observed, so
+                       // that node nf behaves exactly like the unlimited external supplier of arc nf-1
+  T big;
   int slot[kF];        // action column of node k, -1 = co-player
   int pos[kF];         // position of node k's 7 numbers in the observation, -1 = not observed
   int n_obs;

@@ -4,7 +4,8 @@
 // 3 in-flight order slips and 4 shipment slots per arc and takes the lead times from the spec at run time
 // (slot positions are applied with 0/1 mask arithmetic over unrolled slots: registers only, no local memory).
 //
-// Supported: information and shipment lead times in 1..4 with info + shipment <= 5 per arc.  Beyond that
+// Supported: chains of 1..4 facilities (shorter chains pad the missing upstream nodes with phantoms, see
+// DevSpec::nf), information and shipment lead times in 1..4 with info + shipment <= 5 per arc.  Beyond that
 // the reference itself fails its on_order == sum(unreceived) assertion at reset (supplynetwork.py:159-160),
 // because Arc.reset keeps only five pipeline slots (network_components.py:168).
 //
@@ -77,13 +78,14 @@ __device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, con
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     const int li = sp.li[k], ls = sp.ls[k];
+    const bool real = k < sp.nf;                    // phantom nodes of a shorter chain: empty pipelines, stock `big`
     T so[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      so[j] = in[4 + 4 * k + j] * mask_of<T>(j < li);
-      sh[j] = in[20 + 4 * k + j] * mask_of<T>(j < ls);
+      so[j] = in[4 + 4 * k + j] * mask_of<T>(real && j < li);
+      sh[j] = in[20 + 4 * k + j] * mask_of<T>(real && j < ls);
     }
-    e.inv[k] = in[k];
+    e.inv[k] = real ? in[k] : sp.big;
     // ([0]*4 + shipments + sales_orders)[::-1][:5]: newest slip first, then shipments latest first
     T seq[5];
 #pragma unroll

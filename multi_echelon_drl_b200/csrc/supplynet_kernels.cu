@@ -485,6 +485,7 @@ bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && st
 
 // the beer game's lead times (envs.py:355-392): tuned kernels; anything else takes the generic path
 bool is_standard(const sn_spec* s) {
+  if (s->n_facilities != 4) return false;
   const int li[4] = {2, 2, 2, 1};
   for (int k = 0; k < 4; ++k)
     if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2) return false;
@@ -494,8 +495,9 @@ bool is_standard(const sn_spec* s) {
 int validate(const sn_spec* s, int dtype) {
   if (s == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
   if (dtype != SN_I32 && dtype != SN_F32 && dtype != SN_F64) return fail(SN_ERR_INVALID, "unknown dtype %d", dtype);
-  if (s->n_facilities != 4) return fail(SN_ERR_UNSUPPORTED, "only the 4-echelon serial chain is supported (n_facilities=%d)", s->n_facilities);
-  for (int k = 0; k < 4; ++k) {
+  if (s->n_facilities < 1 || s->n_facilities > 4)
+    return fail(SN_ERR_UNSUPPORTED, "serial chains of 1..4 facilities are supported (n_facilities=%d)", s->n_facilities);
+  for (int k = 0; k < s->n_facilities; ++k) {
     const int li = s->info_leadtime[k], ls = s->ship_leadtime[k];
     if (li < 1 || li > 4 || ls < 1 || ls > 4)
       return fail(SN_ERR_UNSUPPORTED, "arc %d: lead times (%d,%d) outside 1..4", k, li, ls);
@@ -505,11 +507,11 @@ int validate(const sn_spec* s, int dtype) {
   }
   if (!is_standard(s) && s->n_items > 1)
     return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported with the beer game's lead times only");
-  if (s->n_agents < 1 || s->n_agents > 4) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
+  if (s->n_agents < 1 || s->n_agents > s->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
   int seen = 0, lo = 4, hi = -1;
   for (int i = 0; i < s->n_agents; ++i) {
     const int k = s->agents[i];
-    if (k < 0 || k > 3) return fail(SN_ERR_INVALID, "agents[%d]=%d out of range", i, k);
+    if (k < 0 || k >= s->n_facilities) return fail(SN_ERR_INVALID, "agents[%d]=%d out of range", i, k);
     if (seen & (1 << k)) return fail(SN_ERR_INVALID, "facility %d listed twice", k);
     seen |= 1 << k;
     lo = k < lo ? k : lo;
@@ -522,7 +524,7 @@ int validate(const sn_spec* s, int dtype) {
   if (s->rule != SN_RULE_A && s->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown rule %d", s->rule);
   if (s->n_items < 0 || s->n_items > SN_MAX_ITEMS) return fail(SN_ERR_INVALID, "n_items=%d outside 0..%d", s->n_items, SN_MAX_ITEMS);
   if (dtype == SN_I32) {
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < s->n_facilities; ++k)
       if (!is_integral(s->coplayer_target[k])) return fail(SN_ERR_TYPE, "coplayer_target[%d] must be integral for SN_I32", k);
     if (!is_integral(s->coplayer_lb) || !is_integral(s->coplayer_ub)) return fail(SN_ERR_TYPE, "co-player bounds must be integral for SN_I32");
     if (s->rule == SN_RULE_D_PLUS_A && (!is_integral(s->dpa_offset) || !is_integral(s->dpa_lb) || !is_integral(s->dpa_ub)))
@@ -531,23 +533,37 @@ int validate(const sn_spec* s, int dtype) {
   return SN_OK;
 }
 
+template <typename T> T big_quantity();
+template <> int32_t big_quantity<int32_t>() { return 1 << 29; }
+template <> float big_quantity<float>() { return 1e30f; }
+template <> double big_quantity<double>() { return 1e30; }
+
 template <typename T>
 sn::DevSpec<T> lower(const sn_spec* s) {
   sn::DevSpec<T> d;
   std::memset(&d, 0, sizeof(d));
+  const int nf = s->n_facilities;
+  const int std_li[4] = {2, 2, 2, 1};
   int lo = 4;
+  d.nf = nf;
+  d.big = big_quantity<T>();
   for (int k = 0; k < 4; ++k) {
-    d.target[k] = (T)s->coplayer_target[k];
-    d.h[0][k] = s->holding_cost[k];
-    d.b[0][k] = s->backorder_cost[k];
+    const bool real = k < nf;
+    // phantom nodes (k >= nf): a target far below any inventory position makes their order clip to 0,
+    // zero cost coefficients keep them out of the reward, any valid lead times will do
+    d.target[k] = real ? (T)s->coplayer_target[k] : -d.big;
+    d.h[0][k] = real ? s->holding_cost[k] : 0.0;
+    d.b[0][k] = real ? s->backorder_cost[k] : 0.0;
     for (int i = 1; i < SN_MAX_ITEMS; ++i) {
-      d.h[i][k] = s->item_holding_cost[i - 1][k];
-      d.b[i][k] = s->item_backorder_cost[i - 1][k];
+      d.h[i][k] = real ? s->item_holding_cost[i - 1][k] : 0.0;
+      d.b[i][k] = real ? s->item_backorder_cost[i - 1][k] : 0.0;
     }
+    d.li[k] = real ? s->info_leadtime[k] : std_li[k];
+    d.ls[k] = real ? s->ship_leadtime[k] : 2;
     d.slot[k] = -1;
+    d.pos[k] = -1;
   }
   d.n_items = s->n_items > 1 ? s->n_items : 1;
-  for (int k = 0; k < 4; ++k) { d.li[k] = s->info_leadtime[k]; d.ls[k] = s->ship_leadtime[k]; }
   for (int i = 0; i < s->n_agents; ++i) {
     d.slot[s->agents[i]] = i;
     lo = s->agents[i] < lo ? s->agents[i] : lo;
@@ -555,11 +571,10 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   d.clb = (T)s->coplayer_lb; d.cub = (T)s->coplayer_ub;
   d.off = (T)s->dpa_offset; d.lb = (T)s->dpa_lb; d.ub = (T)s->dpa_ub;
   if (s->global_observable) {
-    d.n_obs = 4;
-    for (int k = 0; k < 4; ++k) d.pos[k] = k;
+    d.n_obs = nf;
+    for (int k = 0; k < nf; ++k) d.pos[k] = k;
   } else {
     d.n_obs = s->n_agents;
-    for (int k = 0; k < 4; ++k) d.pos[k] = -1;
     for (int i = 0; i < s->n_agents; ++i) d.pos[s->agents[i]] = i;
   }
   d.n_agents = s->n_agents;
@@ -571,7 +586,7 @@ sn::DevSpec<T> lower(const sn_spec* s) {
 
 // centralized, full layout: action column k = node k and all four nodes observed in chain order
 bool is_identity(const sn_spec* s) {
-  if (s->n_agents != 4) return false;
+  if (s->n_facilities != 4 || s->n_agents != 4) return false;
   for (int k = 0; k < 4; ++k) if (s->agents[k] != k) return false;
   return true;      // obs: global or local both give positions 0..3
 }
@@ -709,8 +724,9 @@ const char* sn_last_error(void) { return g_err; }
 
 int32_t sn_obs_dim(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
-  if (spec->n_agents < 1 || spec->n_agents > 4) return fail(SN_ERR_INVALID, "n_agents=%d out of range", spec->n_agents);
-  return SN_OBS_PER_FACILITY * (spec->global_observable ? 4 : spec->n_agents);
+  if (spec->n_facilities < 1 || spec->n_facilities > 4) return fail(SN_ERR_UNSUPPORTED, "n_facilities=%d", spec->n_facilities);
+  if (spec->n_agents < 1 || spec->n_agents > spec->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", spec->n_agents);
+  return SN_OBS_PER_FACILITY * (spec->global_observable ? spec->n_facilities : spec->n_agents);
 }
 
 int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype) { return validate(spec, dtype); }

@@ -30,9 +30,9 @@ class _SupplyNetworkView:
 
     def __init__(self, env):
         self._env = env
-        self.internal_nodes = list(NODE_NAMES)
+        self.internal_nodes = list(env.spec.node_names)
         self.agent_managed_facilities = [NODE_NAMES[k] for k in env.spec.agents]
-        self.order_sequence = list(NODE_NAMES) + ["external_supplier"]
+        self.order_sequence = list(env.spec.node_names) + ["external_supplier"]
 
     def get_state(self, node_name: str) -> dict:
         """The 7 numbers of node `node_name` as the reference's dict (observation of the current state,
@@ -99,14 +99,14 @@ class BeerGameEnv:
         return {name: {key: cast(x) for key, x in zip(_KEYS, flat[7 * i:7 * i + 7])} for i, name in enumerate(names)}
 
     def _full_observation(self) -> np.ndarray:
-        """Global 28-number observation of the current state, whatever this env's own observability."""
+        """Global observation (7 numbers per facility) of the current state, whatever this env's own observability."""
         if self.spec.global_observable:
             return self.sim.observe().cpu().numpy()[0]
         from dataclasses import replace
         import ctypes as C
         from . import _lib
         g = replace(self.spec, global_observable=True).to_c()
-        out = torch.zeros((1, 28), dtype=torch.float32, device=self.sim.device)
+        out = torch.zeros((1, 7 * self.spec.n_facilities), dtype=torch.float32, device=self.sim.device)
         s = self.sim
         _lib.check(s.lib.sn_observe(C.byref(g), s.dtype_code, 1, s.ld, C.c_void_p(s.state.data_ptr()),
                                     C.c_void_p(out.data_ptr()), s._stream()))

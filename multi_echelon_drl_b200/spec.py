@@ -64,12 +64,19 @@ class ScenarioSpec:
     # anything else (1..4, info + shipment <= 5) the generic ones
     info_leadtime: Tuple[int, ...] = INFO_LEADTIME
     ship_leadtime: Tuple[int, ...] = SHIP_LEADTIME
+    # chain length: the first n_facilities of retailer..manufacturer; the last one buys from the external supplier.
+    # Per-facility tuples (costs, targets, lead times) then have n_facilities entries.  Shorter chains run on the
+    # generic kernels with the missing upstream nodes as phantoms (supplynet_core.cuh, DevSpec::nf).
+    n_facilities: int = 4
 
     def __post_init__(self):
+        nf = int(self.n_facilities)
+        if not 1 <= nf <= 4:
+            raise ValueError("n_facilities must be 1..4")
         ag = tuple(node_index(a) for a in self.agents)
         object.__setattr__(self, "agents", ag)
-        if not 1 <= len(ag) <= 4 or len(set(ag)) != len(ag):
-            raise ValueError(f"agent_managed_facilities {self.agents} must name 1..4 distinct facilities")
+        if not 1 <= len(ag) <= nf or len(set(ag)) != len(ag) or max(ag) >= nf:
+            raise ValueError(f"agent_managed_facilities {self.agents} must name 1..{nf} distinct facilities of the chain")
         if max(ag) - min(ag) + 1 != len(ag):
             # the reference never lets the in-between node order and crashes at supplynetwork.py:199
             raise ValueError("agent-managed facilities must form a contiguous block of the chain")
@@ -77,13 +84,19 @@ class ScenarioSpec:
             raise ValueError(f"ordering rule must be 'a' or 'd+a', got {self.rule!r}")
         object.__setattr__(self, "info_leadtime", tuple(int(x) for x in self.info_leadtime))
         object.__setattr__(self, "ship_leadtime", tuple(int(x) for x in self.ship_leadtime))
-        if len(self.info_leadtime) != 4 or len(self.ship_leadtime) != 4:
-            raise ValueError("info_leadtime and ship_leadtime need one entry per arc (4)")
+        for name in ("info_leadtime", "ship_leadtime", "holding_cost", "backorder_cost", "coplayer_target"):
+            if len(getattr(self, name)) < nf:
+                raise ValueError(f"{name} needs one entry per facility ({nf})")
 
     # ------------------------------------------------------------------ derived
     @property
     def standard_leadtimes(self) -> bool:
-        return self.info_leadtime == INFO_LEADTIME and self.ship_leadtime == SHIP_LEADTIME
+        """True for the beer game itself (4 facilities, lead times 2,2,2,1 / 2,2,2,2): tuned kernels, packed tables."""
+        return self.n_facilities == 4 and self.info_leadtime == INFO_LEADTIME and self.ship_leadtime == SHIP_LEADTIME
+
+    @property
+    def node_names(self) -> Tuple[str, ...]:
+        return NODE_NAMES[: self.n_facilities]
 
     @property
     def n_items(self) -> int:
@@ -95,7 +108,7 @@ class ScenarioSpec:
 
     @property
     def obs_nodes(self) -> Tuple[int, ...]:
-        return (0, 1, 2, 3) if self.global_observable else self.agents
+        return tuple(range(self.n_facilities)) if self.global_observable else self.agents
 
     @property
     def obs_dim(self) -> int:
@@ -106,13 +119,14 @@ class ScenarioSpec:
 
     def to_c(self) -> _lib.SnSpec:
         s = _lib.SnSpec()
-        s.n_facilities = 4
-        for k in range(4):
+        s.n_facilities = self.n_facilities
+        for k in range(self.n_facilities):
             s.info_leadtime[k] = self.info_leadtime[k]
             s.ship_leadtime[k] = self.ship_leadtime[k]
             s.holding_cost[k] = float(self.holding_cost[k])
             s.backorder_cost[k] = float(self.backorder_cost[k])
             s.coplayer_target[k] = float(self.coplayer_target[k])
+        for k in range(4):
             s.agents[k] = self.agents[k] if k < len(self.agents) else 0
         s.n_agents = len(self.agents)
         s.global_observable = int(self.global_observable)
@@ -124,7 +138,7 @@ class ScenarioSpec:
             raise ValueError("at most 4 items")
         s.n_items = self.n_items
         for i, (h, b) in enumerate(self.extra_item_costs):
-            for k in range(4):
+            for k in range(self.n_facilities):
                 s.item_holding_cost[i][k] = float(h[k])
                 s.item_backorder_cost[i][k] = float(b[k])
         return s
@@ -178,12 +192,14 @@ def specs_from_config(network_config: dict, agent_managed_facilities=None, globa
     their own cost vectors (the reference defines no item coupling)."""
     from .utils.graph import chain_from_config
     seq, info, ship, hold, back = chain_from_config(network_config)
-    if tuple(seq) != NODE_NAMES:
-        raise NotImplementedError(f"kernels implement the 4-echelon chain {NODE_NAMES}; got {seq}")
+    nf = len(seq)
+    if not 1 <= nf <= 4 or tuple(seq) != NODE_NAMES[:nf]:
+        raise NotImplementedError(f"kernels implement serial chains made of the first 1..4 of {NODE_NAMES}; got {seq}")
     if any(not 1 <= l <= 4 for l in info + ship) or any(a + b > 5 for a, b in zip(info, ship)):
         raise NotImplementedError(f"lead times must be 1..4 with info + shipment <= 5 per arc; got {info}/{ship}")
-    base = replace(uniform_spec(agent_managed_facilities, global_observable, max_episode_steps, random_init),
-                   info_leadtime=info, ship_leadtime=ship)
-    return [replace(base, name=f"config-item{i}", holding_cost=tuple(float(x) for x in hold[i]),
-                    backorder_cost=tuple(float(x) for x in back[i]), coplayer_target=tuple(coplayer_target))
+    agents = _agents(agent_managed_facilities, NODE_NAMES[:nf])
+    u = uniform_spec(None, global_observable, max_episode_steps, random_init)
+    return [replace(u, name=f"config-item{i}", n_facilities=nf, agents=agents, info_leadtime=info, ship_leadtime=ship,
+                    holding_cost=tuple(float(x) for x in hold[i]), backorder_cost=tuple(float(x) for x in back[i]),
+                    coplayer_target=tuple(coplayer_target)[:nf])
             for i in range(len(hold))]

@@ -104,8 +104,8 @@ def init_layout(spec: ScenarioSpec):
 def _fixed_init(spec: ScenarioSpec) -> np.ndarray:
     n_words, so_off, sh_off = init_layout(spec)
     v = np.zeros(n_words, dtype=np.int64)
-    v[:4] = spec.fixed_inventory
-    for k in range(4):
+    v[:spec.n_facilities] = spec.fixed_inventory
+    for k in range(spec.n_facilities):
         for j in range(spec.info_leadtime[k]):
             v[so_off[k] + j] = spec.fixed_sales_orders[min(j, len(spec.fixed_sales_orders) - 1)]
         for j in range(spec.ship_leadtime[k]):
@@ -128,10 +128,11 @@ def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
     if spec.random_init:
         init = np.zeros((n, n_words), dtype=np.int64)
         init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
+        init[:, spec.n_facilities:4] = 0
         pipe = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, n_words - 4))
-        if not spec.standard_leadtimes:             # slots beyond an arc's lead time stay empty
+        if not spec.standard_leadtimes:             # slots beyond an arc's lead time (or chain) stay empty
             mask = np.zeros(n_words - 4, dtype=bool)
-            for k in range(4):
+            for k in range(spec.n_facilities):
                 mask[so_off[k] - 4: so_off[k] - 4 + spec.info_leadtime[k]] = True
                 mask[sh_off[k] - 4: sh_off[k] - 4 + spec.ship_leadtime[k]] = True
             pipe = pipe * mask
@@ -159,9 +160,9 @@ def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
         plo, phi = spec.init_pipeline
         init[i, 0] = rs.randint(lo, hi)
         demand[i] = dem.draw(rs)
-        for k in (1, 2, 3):
+        for k in range(1, spec.n_facilities):
             init[i, k] = rs.randint(lo, hi)
-        for k in (3, 2, 1, 0):
+        for k in range(spec.n_facilities - 1, -1, -1):
             for j in range(spec.ship_leadtime[k]):
                 init[i, sh_off[k] + j] = rs.randint(plo, phi)
             for j in range(spec.info_leadtime[k]):

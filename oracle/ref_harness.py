@@ -74,13 +74,14 @@ def make_env(scenario: str, agents, global_observable=False, random_init=True, m
 
 
 def read_initial_state(env):
-    """Read (inv0[4], so[4][<=2], sh[4][2], demand[T+3]) out of a reference env right after
+    """Read (inv0[F], so[F][*], sh[F][*], demand[T+3]) out of a reference env right after
     `sn.reset()` and BEFORE `before_action(0)`.  Arc index k = arc whose customer is node k."""
     sn = env.sn
-    inv0 = [sn.nodes[n].current_inventory for n in NODE_NAMES]
-    sup = ["wholesaler", "distributor", "manufacturer", "external_supplier"]
+    names = [n for n in NODE_NAMES if n in sn.nodes]
+    inv0 = [sn.nodes[n].current_inventory for n in names]
+    sup = names[1:] + ["external_supplier"]
     so, sh = [], []
-    for k, n in enumerate(NODE_NAMES):
+    for k, n in enumerate(names):
         arc = sn.arcs[(sup[k], n)]
         so.append([o.order_quantity for o in sorted(arc.sales_orders, key=lambda o: o.remaining_lead_time)])
         sh.append([s.quantity for s in sorted(arc.shipments, key=lambda s: s.time_till_arrival)])
@@ -119,8 +120,9 @@ def rollout(env, actions, seed=None, collect_costs=False):
     out = dict(obs0=obs0, init=init, obs=np.stack(obs_l), rew=np.array(rew_l, dtype=np.float64),
                done=np.array(done_l))
     if collect_costs:
-        h = np.array([env.sn.nodes[n].holding_cost_history for n in NODE_NAMES], dtype=np.float64).T
-        b = np.array([env.sn.nodes[n].backorder_cost_history for n in NODE_NAMES], dtype=np.float64).T
+        names = [n for n in NODE_NAMES if n in env.sn.nodes]
+        h = np.array([env.sn.nodes[n].holding_cost_history for n in names], dtype=np.float64).T
+        b = np.array([env.sn.nodes[n].backorder_cost_history for n in names], dtype=np.float64).T
         out["holding"], out["backorder"] = h, b
     return out
 
@@ -138,20 +140,22 @@ def make_custom_chain_env(info_lt, ship_lt, agents, global_observable=False, max
     idx = {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1, "latest_demand": 2}
     pol = [HE.BaseStockPolicy(target_levels=[t], array_index=idx, state_dim_per_facility=7) for t in targets]
     demand = DE.Demand("uniform", low=0, high=8, size=max_episode_steps)
+    nf = len(info_lt)                            # chain length: the first nf of retailer..manufacturer
+    chain = NODE_NAMES[:nf]
     nodes = []
-    for k, name in enumerate(NODE_NAMES):
+    for k, name in enumerate(chain):
         kw = dict(name=name, initial_inventory=list(init_inventory), holding_cost=holding[k], backorder_cost=backorder[k],
                   policy=pol[k])
         if k == 0:
             kw.update(is_demand_source=True, demands=demand)
         nodes.append(NC.Node(**kw))
     nodes.append(NC.Node(name="external_supplier", is_external_supplier=True))
-    sup = ["wholesaler", "distributor", "manufacturer", "external_supplier"]
-    arcs = [NC.Arc(sup[k], NODE_NAMES[k], info_lt[k], ship_lt[k], initial_shipments=list(init_pipeline),
-                   initial_sales_orders=list(init_pipeline), random_init=True) for k in (3, 2, 1, 0)]
-    names = [NODE_NAMES[k] for k in agents]
+    sup = chain[1:] + ["external_supplier"]
+    arcs = [NC.Arc(sup[k], chain[k], info_lt[k], ship_lt[k], initial_shipments=list(init_pipeline),
+                   initial_sales_orders=list(init_pipeline), random_init=True) for k in range(nf - 1, -1, -1)]
+    names = [chain[k] for k in agents]
     net = SN.SupplyNetwork(nodes=nodes, arcs=arcs, agent_managed_facilities=names)
-    n_obs = 4 if global_observable else len(names)
+    n_obs = nf if global_observable else len(names)
     env = E.InventoryManagementEnvMultiPlayer(
         net, max_episode_steps=max_episode_steps, action_space=gym.spaces.Box(0, 16, shape=(len(names),)),
         observation_space=gym.spaces.Box(low=-np.inf, high=np.inf, shape=(7 * n_obs,)), global_observable=global_observable)

@@ -14,6 +14,7 @@ Files written
   classic.npz     the classic beer game episodes behind the 13 totals of
                   tests/test_supplynetwork.py:25-69, with per-step outputs
   leadtimes.npz   serial chains with other per-arc lead times (general-chain path)
+  chains.npz      serial chains with 1..3 facilities
 """
 import os
 import sys
@@ -159,11 +160,12 @@ def gen_classic():
 
 
 def flat_init_generic(init):
-    """36 numbers: inv[4], so[k][0..3] (k = 0..3, unused slots 0), sh[k][0..3]."""
+    """36 numbers: inv[4], so[k][0..3] (k = 0..3, unused slots 0), sh[k][0..3]; shorter chains leave the
+    rows of the missing facilities at 0."""
     inv0, so, sh, dem = init
     v = np.zeros(36, dtype=np.int64)
-    v[:4] = inv0
-    for k in range(4):
+    v[:len(inv0)] = inv0
+    for k in range(len(inv0)):
         v[4 + 4 * k: 4 + 4 * k + len(so[k])] = so[k]
         v[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
     return v, np.asarray(dem, dtype=np.int64)
@@ -194,6 +196,33 @@ def gen_leadtimes():
     print("leadtimes:", cid, "cases")
 
 
+def gen_short_chains():
+    """Serial chains with fewer than four facilities (first F of retailer..manufacturer, then the external
+    supplier), again built from the reference's own classes."""
+    cases = [((2, 1), (2, 2), [(0, 1), (0,), (1,), (1, 0)]), ((1,), (2,), [(0,)]),
+             ((2, 2, 1), (2, 2, 2), [(0, 1, 2), (1,), (1, 2), (0,)]), ((3, 1, 2), (1, 4, 3), [(0, 1, 2), (2,), (2, 1, 0)]),
+             ((1, 3), (4, 2), [(0, 1), (1,)])]
+    out, meta, cid = {}, [], 0
+    for li, ls, agsets in cases:
+        nf = len(li)
+        for ag in agsets:
+            for glob, rule in ((False, "a"), (True, "d+a"), (True, "a")):
+                seed = 1300 + cid
+                env = H.make_custom_chain_env(li, ls, ag, glob, targets=(19, 20, 20, 14)[:nf],
+                                              dplusa=(-8, 0, 16) if rule == "d+a" else None)
+                acts = np.random.RandomState(8000 + cid).randint(-1, 19, (100, len(ag))).astype(np.int64)
+                r = H.rollout(env, [a for a in acts], seed=seed, collect_costs=True)
+                init, dem = flat_init_generic(r["init"])
+                p = f"s{cid:03d}_"
+                out.update({p + "init": init, p + "demand": dem, p + "actions": acts, p + "obs0": r["obs0"],
+                            p + "obs": r["obs"], p + "rew": r["rew"]})
+                meta.append(f"{cid}|{','.join(map(str, li))}|{','.join(map(str, ls))}|{','.join(map(str, ag))}|{int(glob)}|{rule}")
+                cid += 1
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "chains.npz"), **out)
+    print("short chains:", cid, "cases")
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore", RuntimeWarning)
     gen_rollouts()
@@ -201,3 +230,4 @@ if __name__ == "__main__":
     gen_seeded()
     gen_classic()
     gen_leadtimes()
+    gen_short_chains()

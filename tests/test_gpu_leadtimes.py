@@ -7,17 +7,12 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from test_oracle_golden import LEADTIME_CASES, oracle_leadtime_rollout  # noqa: E402
+from test_oracle_golden import CHAIN_CASES, LEADTIME_CASES, chain_spec, oracle_leadtime_rollout  # noqa: E402
 
 
 def _sim(case, n, dtype="int32"):
-    from dataclasses import replace
-    from multi_echelon_drl_b200 import uniform_spec
     from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
-    spec = replace(uniform_spec(case["agents"], case["glob"], 100), info_leadtime=case["li"], ship_leadtime=case["ls"])
-    if case["rule"] == "d+a":
-        spec = spec.with_rule("d+a", -8, 0, 16)
-    return BatchedSupplyNetwork(spec, n, "cuda", dtype)
+    return BatchedSupplyNetwork(chain_spec(case), n, "cuda", dtype)
 
 
 def _init_for(sim, case, init36):
@@ -32,10 +27,11 @@ def _init_for(sim, case, init36):
     return init36[:, cols]
 
 
-@pytest.mark.parametrize("case", LEADTIME_CASES, ids=[c["id"] for c in LEADTIME_CASES])
+@pytest.mark.parametrize("case", LEADTIME_CASES + CHAIN_CASES, ids=[c["id"] for c in LEADTIME_CASES + CHAIN_CASES])
 def test_step_and_rollout_match_reference_golden(case):
     sim = _sim(case, 1)
     assert sim.state_words == (40 if case["li"] == (2, 2, 2, 1) and case["ls"] == (2, 2, 2, 2) else 57)
+    assert sim.obs_dim == case["obs0"].shape[0]
     sim.load_episode(_init_for(sim, case, case["init"][None]), case["demand"][None])
     assert np.array_equal(sim.reset().cpu().numpy()[0], case["obs0"])
     r64 = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -54,6 +50,9 @@ def test_step_and_rollout_match_reference_golden(case):
     ((4, 1, 2, 3), (1, 4, 3, 2), (0, 1, 2, 3), True, "d+a"),
     ((3, 2, 1, 2), (2, 3, 4, 1), (2,), False, "a"),
     ((1, 4, 1, 2), (4, 1, 4, 3), (1, 2, 3), True, "a"),
+    ((2, 2, 1), (2, 2, 2), (0, 1, 2), True, "a"),          # three facilities
+    ((3, 1), (2, 4), (1,), True, "d+a"),                   # two
+    ((2,), (3,), (0,), False, "a"),                        # a single facility buying from the external supplier
 ])
 def test_generic_batch_vs_oracle_and_policy_rollout(li, ls, agents, glob, rule):
     """3,001 envs (ragged) x 100: step kernel, fused rollout with trajectory, in-kernel base-stock policy."""
@@ -78,8 +77,8 @@ def test_generic_batch_vs_oracle_and_policy_rollout(li, ls, agents, glob, rule):
     assert np.array_equal(sim.ep_return.cpu().numpy(), rew.sum(0))
     # in-kernel policy == heuristic kernel + step kernel
     from multi_echelon_drl_b200.simulator import heuristic_actions
-    if len(agents) == 4 and glob:
-        pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
+    if len(agents) == len(li) and glob:
+        pol = BasePolicyParams([19, 20, 20, 14][:len(li)], 0, 16, "a")
         sim.episode(100, policy=pol, write_state=False)
         fused = sim.ep_return.clone()
         o = sim.reset()
@@ -105,3 +104,36 @@ def test_vecenv_with_other_lead_times_and_unsupported_ones():
     assert torch.isfinite(obs).all() and env.episodes_done == 512
     with pytest.raises(NotImplementedError):
         SupplyNetVecEnv(replace(uniform_spec(), info_leadtime=(3, 2, 2, 1), ship_leadtime=(3, 2, 2, 2)), 8)
+
+
+def test_vecenv_on_a_two_facility_chain():
+    """retailer + wholesaler in front of the external supplier: 14-number global observation, two actions,
+    the same on-order invariant, and whole episodes through the in-kernel base-stock policy."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    u = uniform_spec(None, True)
+    spec = replace(u, n_facilities=2, agents=(0, 1), info_leadtime=(2, 1), ship_leadtime=(2, 2), holding_cost=(0.5, 0.5),
+                   backorder_cost=(1.0, 1.0), coplayer_target=(19.0, 20.0))
+    env = SupplyNetVecEnv(spec, 700, seed=11, dtype="int32")
+    obs = env.reset()
+    assert obs.shape == (700, 14) and env.action_space.shape == (2,)
+    s = env.sim.state[:, :700].to(torch.int64)
+    for k in range(2):
+        on_order = s[7 * k + 3:7 * k + 7].sum(0)
+        pipe = s[28 + 3 * k:31 + 3 * k].sum(0) + s[40 + 4 * k:44 + 4 * k].sum(0) + s[7 * (k + 1) + 1]
+        assert torch.equal(on_order, pipe)
+    assert (s[14] >= (1 << 28)).all() and (s[21] >= (1 << 28)).all()      # phantom upstream stock
+    assert not s[28 + 6:28 + 12].any() and not s[40 + 8:40 + 16].any()    # phantom pipelines stay empty
+    total = torch.zeros(700, dtype=torch.float64, device="cuda")
+    for _ in range(100):
+        obs, rew, dones, infos = env.step(torch.full((700, 2), 4, device="cuda"))
+        total += rew.double()
+    assert dones.all() and (total < 0).all()
+    stats = env.run_policy_episodes(BasePolicyParams([19, 20], 0, 16, "a"), n_episodes=2)
+    stats = stats.cpu().numpy()
+    assert stats[0] == 1400 * 100 and stats[10] == 1400 and stats[11] < 0 and stats[11] == stats[1]
+    assert stats[4] == 0 and stats[5] == 0 and stats[8] == 0 and stats[9] == 0     # phantom nodes cost nothing
+    with pytest.raises(ValueError):
+        replace(spec, agents=(2,))

@@ -278,3 +278,39 @@ def test_init_layouts_for_standard_and_generic_lead_times():
         sh = [rs.randint(0, 9) for _ in range(gen.ship_leadtime[k])]
         so = [rs.randint(0, 9) for _ in range(gen.info_leadtime[k])]
         assert init[0, 20 + 4 * k: 20 + 4 * k + len(sh)].tolist() == sh and init[0, 4 + 4 * k: 4 + 4 * k + len(so)].tolist() == so
+
+
+def test_short_chain_specs_and_yaml():
+    """Chains of 1..3 facilities: spec validation, observation layout, YAML factory, C-side validation."""
+    import ctypes as C
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import _lib, uniform_spec
+    from multi_echelon_drl_b200.spec import specs_from_config
+    u = uniform_spec(None, True)
+    s2 = replace(u, n_facilities=2, agents=(1, 0), info_leadtime=(2, 1), ship_leadtime=(2, 2))
+    assert s2.obs_nodes == (0, 1) and s2.obs_dim == 14 and s2.node_names == ("retailer", "wholesaler")
+    assert not s2.standard_leadtimes
+    assert replace(s2, global_observable=False).obs_nodes == (1, 0)
+    with pytest.raises(ValueError):
+        replace(u, n_facilities=2, agents=(0, 2))
+    with pytest.raises(ValueError):
+        replace(u, n_facilities=5)
+    with pytest.raises(ValueError):
+        replace(u, n_facilities=3, agents=(0,), info_leadtime=(2, 2))
+    lib = _lib.load()
+    c = s2.to_c()
+    assert c.n_facilities == 2 and lib.sn_spec_validate(C.byref(c), _lib.SN_I32) == 0
+    assert lib.sn_obs_dim(C.byref(c)) == 14 and lib.sn_state_words(C.byref(c)) == 57 and lib.sn_init_words(C.byref(c)) == 36
+    c.agents[0] = 2
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0 and b"agents" in lib.sn_last_error()
+    cfg = dict(nodes=[dict(name="retailer", holding_cost=0.5, backorder_cost=1, demand_path="uniform:0:8"),
+                      dict(name="wholesaler", holding_cost=0.25, backorder_cost=2),
+                      dict(name="external_supplier", is_external_supplier=True)],
+               arcs=[dict(customer="wholesaler", supplier="external_supplier", info_leadtime=1, shipment_leadtime=3),
+                     dict(customer="retailer", supplier="wholesaler", info_leadtime=2, shipment_leadtime=2)])
+    (sp,) = specs_from_config(cfg, ["wholesaler"], True, 100)
+    assert sp.n_facilities == 2 and sp.agents == (1,) and sp.info_leadtime == (2, 1) and sp.ship_leadtime == (2, 3)
+    assert sp.holding_cost == (0.5, 0.25) and sp.backorder_cost == (1.0, 2.0) and sp.obs_dim == 14
+    assert sp.coplayer_target == (19, 20)
+    with pytest.raises(NotImplementedError):      # a chain that does not start at the retailer
+        specs_from_config(dict(nodes=cfg["nodes"][1:], arcs=cfg["arcs"][:1]), ["wholesaler"])

@@ -116,12 +116,12 @@ def test_oracle_vs_live_reference():
                 assert np.array_equal(ref["obs"][:, 0], r["obs"]) and np.array_equal(ref["rew"][:, 0], r["rew"])
 
 
-def _leadtime_cases():
-    z = np.load(f"{GOLDEN}/leadtimes.npz")
+def _leadtime_cases(fname="leadtimes.npz", prefix="g"):
+    z = np.load(f"{GOLDEN}/{fname}")
     out = []
     for m in z["meta"]:
         cid, li, ls, ag, glob, rule = str(m).split("|")
-        p = f"g{int(cid):03d}_"
+        p = f"{prefix}{int(cid):03d}_"
         out.append(dict(id=f"li{li.replace(',', '')}-ls{ls.replace(',', '')}-ag{ag.replace(',', '')}-g{glob}-{rule}",
                         li=tuple(int(x) for x in li.split(",")), ls=tuple(int(x) for x in ls.split(",")),
                         agents=tuple(int(x) for x in ag.split(",")), glob=bool(int(glob)), rule=rule,
@@ -131,17 +131,19 @@ def _leadtime_cases():
 
 
 LEADTIME_CASES = _leadtime_cases()
+CHAIN_CASES = _leadtime_cases("chains.npz", "s")          # chains of 1..3 facilities
 
 
 def oracle_leadtime_rollout(case, init36, demand, actions):
     """Oracle with per-arc lead times; init36 [n,36] = inv[4], so[k][0..3], sh[k][0..3]."""
     from dataclasses import replace
+    nf = len(case["li"])
     spec = replace(O.scenario_spec("uniform", case["agents"], case["glob"], 100, case["rule"]), info_lt=case["li"],
-                   ship_lt=case["ls"])
+                   ship_lt=case["ls"], n_facilities=nf)
     n = init36.shape[0]
     orc = O.BeerGameOracle(spec, n)
-    so = [init36[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] for k in range(4)]
-    sh = [init36[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] for k in range(4)]
+    so = [init36[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] for k in range(nf)]
+    sh = [init36[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] for k in range(nf)]
     obs0 = orc.reset(init36[:, :4], so, sh, demand)
     obs, rew = [], []
     for t in range(actions.shape[0]):
@@ -157,6 +159,45 @@ def test_oracle_matches_golden_other_lead_times(case):
     obs0, obs, rew = oracle_leadtime_rollout(case, case["init"][None], case["demand"][None], case["actions"][:, None, :])
     assert np.array_equal(obs0[0], case["obs0"])
     assert np.array_equal(obs[:, 0], case["obs"]) and np.array_equal(rew[:, 0], case["rew"])
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=[c["id"] for c in CHAIN_CASES])
+def test_oracle_matches_golden_short_chains(case):
+    """Chains of one to three facilities in front of the external supplier (reference Node/Arc classes)."""
+    obs0, obs, rew = oracle_leadtime_rollout(case, case["init"][None], case["demand"][None], case["actions"][:, None, :])
+    assert obs0.shape[1] == 7 * (len(case["li"]) if case["glob"] else len(case["agents"]))
+    assert np.array_equal(obs0[0], case["obs0"])
+    assert np.array_equal(obs[:, 0], case["obs"]) and np.array_equal(rew[:, 0], case["rew"])
+
+
+def chain_spec(case, t_max=100):
+    """Product ScenarioSpec of a lead-time / short-chain golden case."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    nf = len(case["li"])
+    u = uniform_spec(None, case["glob"], t_max)
+    spec = replace(u, n_facilities=nf, agents=case["agents"], info_leadtime=case["li"], ship_leadtime=case["ls"],
+                   holding_cost=u.holding_cost[:nf], backorder_cost=u.backorder_cost[:nf],
+                   coplayer_target=u.coplayer_target[:nf])
+    return spec.with_rule("d+a", -8, 0, 16) if case["rule"] == "d+a" else spec
+
+
+def test_seeded_streams_for_short_chains_match_reference():
+    from multi_echelon_drl_b200.utils.demands import seeded_episode_inputs, bulk_episode_inputs
+    for cid, case in enumerate(CHAIN_CASES):
+        spec = chain_spec(case)
+        assert spec.obs_dim == case["obs0"].shape[0] and not spec.standard_leadtimes
+        init, demand = seeded_episode_inputs(spec, [1300 + cid])
+        assert np.array_equal(init[0], case["init"]), case["id"]
+        assert np.array_equal(demand[0], case["demand"]), case["id"]
+        bulk, _ = bulk_episode_inputs(spec, 64, np.random.RandomState(1))
+        nf = len(case["li"])
+        used = np.zeros(36, dtype=bool)
+        used[:nf] = True
+        for k in range(nf):
+            used[4 + 4 * k: 4 + 4 * k + case["li"][k]] = True
+            used[20 + 4 * k: 20 + 4 * k + case["ls"][k]] = True
+        assert not bulk[:, ~used].any()
 
 
 def test_seeded_streams_for_other_lead_times_match_reference():
