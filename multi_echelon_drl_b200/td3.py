@@ -54,6 +54,7 @@ class ReplayBuffer:
         self.act = torch.zeros((capacity, act_dim), **kw)
         self.rew = torch.zeros((capacity,), **kw)
         self.done = torch.zeros((capacity,), **kw)
+        self.size_t = torch.zeros((), dtype=torch.float64, device=device)   # len(self) on the device (graph replays read it)
 
     def __len__(self):
         return self.capacity if self.full else self.pos
@@ -67,9 +68,17 @@ class ReplayBuffer:
         self.rew[idx], self.done[idx] = rew, done.to(torch.float32)
         self.full = self.full or (self.pos + n >= self.capacity)
         self.pos = (self.pos + n) % self.capacity
+        self.size_t.fill_(float(len(self)))
 
     def sample(self, batch_size, generator=None):
         idx = torch.randint(0, len(self), (batch_size,), device=self.obs.device, generator=generator)
+        return self.obs[idx], self.act[idx], self.next_obs[idx], self.rew[idx], self.done[idx]
+
+    def sample_on_device(self, batch_size):
+        """Same draw with the buffer length read from device memory and the default CUDA generator: safe to
+        capture in a CUDA graph (the length baked into `sample` would go stale across replays)."""
+        u = torch.rand(batch_size, device=self.obs.device, dtype=torch.float64)
+        idx = (u * self.size_t).long()
         return self.obs[idx], self.act[idx], self.next_obs[idx], self.rew[idx], self.done[idx]
 
 
@@ -92,6 +101,9 @@ class TD3Config:
     target_policy_noise: float = 0.2
     target_noise_clip: float = 0.5
     seed: int = 0
+    # replay `policy_delay` consecutive updates (sampling, normalisation, both losses, Adam, Polyak) as ONE CUDA graph:
+    # the update is ~150 small launches on [128 x 768] tensors, i.e. launch-bound when run eagerly
+    cuda_graph: bool = True
 
 
 @dataclass
@@ -150,8 +162,9 @@ class HgeTD3:
         self.critics_target.load_state_dict(self.critics.state_dict())
         if ddp:
             self._broadcast_parameters()
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=c.learning_rate)
-        self.critic_opt = torch.optim.Adam(self.critics.parameters(), lr=c.learning_rate)
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
+        self.critic_opt = torch.optim.Adam(self.critics.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
+        self._graph, self._graph_warm = None, 0
         self.buffer = ReplayBuffer(c.buffer_size, od, ad, self.device)
         self.hge_schedule = HgeRateSchedule(c.hge_rate_at_start, c.hge_decay_periods)
         self.hge_rate = c.hge_rate_at_start if heuristic is not None else 0.0
@@ -199,43 +212,88 @@ class HgeTD3:
             scaled = torch.clamp(scaled + noise, -1.0, 1.0)
         return self.unscale_action(scaled), scaled
 
-    def _normalize(self, obs, rew):
+    def _normalize(self, obs, rew, stats=None):
         if self.vec_normalize is None:
             return obs, rew
-        return self.vec_normalize.normalize_obs(obs), self.vec_normalize.normalize_reward(rew)
+        return self.vec_normalize.normalize_obs(obs, stats), self.vec_normalize.normalize_reward(rew, stats)
+
+    def _update(self, do_actor: bool, on_device_sampling: bool = False, stats=None):
+        """One TD3 gradient step (SB3 TD3.train body): critics always, actor + Polyak when `do_actor`."""
+        c = self.cfg
+        gen = None if on_device_sampling else self.gen
+        obs, act, nobs, rew, done = (self.buffer.sample_on_device(c.batch_size) if on_device_sampling
+                                     else self.buffer.sample(c.batch_size, self.gen))
+        obs, rew = self._normalize(obs, rew, stats)
+        nobs, _ = self._normalize(nobs, rew, stats)
+        with torch.no_grad():
+            noise = (torch.randn(act.shape, device=self.device, generator=gen) * c.target_policy_noise
+                     ).clamp(-c.target_noise_clip, c.target_noise_clip)
+            na = (self.actor_target(nobs) + noise).clamp(-1.0, 1.0)
+            x = torch.cat([nobs, na], dim=1)
+            q_next = torch.min(self.critics_target[0](x), self.critics_target[1](x)).squeeze(1)
+            target = rew + (1.0 - done) * c.gamma * q_next
+        x = torch.cat([obs, act], dim=1)
+        qs = [m(x).squeeze(1) for m in self.critics]
+        critic_loss = sum(F.mse_loss(q, target) for q in qs)
+        self.critic_opt.zero_grad(set_to_none=True)
+        critic_loss.backward()
+        self._allreduce_grads(self.critics)
+        self.critic_opt.step()
+        if do_actor:
+            actor_loss = -self.critics[0](torch.cat([obs, self.actor(obs)], dim=1)).mean()
+            self.actor_opt.zero_grad(set_to_none=True)
+            actor_loss.backward()
+            self._allreduce_grads(self.actor)
+            self.actor_opt.step()
+            with torch.no_grad():
+                ps = list(self.actor.parameters()) + list(self.critics.parameters())
+                pts = list(self.actor_target.parameters()) + list(self.critics_target.parameters())
+                torch._foreach_mul_(pts, 1 - c.tau)
+                torch._foreach_add_(pts, ps, alpha=c.tau)
+
+    def _cycle(self, stats):
+        """`policy_delay` updates, the last one with the actor step: the unit that is captured and replayed."""
+        for i in range(self.cfg.policy_delay):
+            self._update(i == self.cfg.policy_delay - 1, on_device_sampling=True, stats=stats)
 
     def train(self, gradient_steps):
         c = self.cfg
-        for _ in range(gradient_steps):
-            self.n_updates += 1
-            obs, act, nobs, rew, done = self.buffer.sample(c.batch_size, self.gen)
-            obs, rew = self._normalize(obs, rew)
-            nobs, _ = self._normalize(nobs, rew)
-            with torch.no_grad():
-                noise = (torch.randn(act.shape, device=self.device, generator=self.gen) * c.target_policy_noise
-                         ).clamp(-c.target_noise_clip, c.target_noise_clip)
-                na = (self.actor_target(nobs) + noise).clamp(-1.0, 1.0)
-                x = torch.cat([nobs, na], dim=1)
-                q_next = torch.min(self.critics_target[0](x), self.critics_target[1](x)).squeeze(1)
-                target = rew + (1.0 - done) * c.gamma * q_next
-            x = torch.cat([obs, act], dim=1)
-            qs = [m(x).squeeze(1) for m in self.critics]
-            critic_loss = sum(F.mse_loss(q, target) for q in qs)
-            self.critic_opt.zero_grad(set_to_none=True)
-            critic_loss.backward()
-            self._allreduce_grads(self.critics)
-            self.critic_opt.step()
-            if self.n_updates % c.policy_delay == 0:
-                actor_loss = -self.critics[0](torch.cat([obs, self.actor(obs)], dim=1)).mean()
+        cycles = 0
+        if c.cuda_graph:
+            while gradient_steps and self.n_updates % c.policy_delay:      # align to the actor-update cadence
+                self.n_updates += 1
+                gradient_steps -= 1
+                self._update(self.n_updates % c.policy_delay == 0)
+            cycles = gradient_steps // c.policy_delay
+        if cycles:
+            stats = self.vec_normalize.frozen_stats() if self.vec_normalize is not None else None
+            if self._graph is None and self._graph_warm < 3:
+                # the first cycles run eagerly on a side stream (optimizer state, cuBLAS workspaces), as
+                # torch.cuda.graph requires before capture; they are real updates
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    while cycles and self._graph_warm < 3:
+                        self._cycle(stats)
+                        self._graph_warm += 1
+                        cycles -= 1
+                        self.n_updates += c.policy_delay
+                        gradient_steps -= c.policy_delay
+                torch.cuda.current_stream(self.device).wait_stream(side)
+            if cycles and self._graph is None:
+                self.critic_opt.zero_grad(set_to_none=True)
                 self.actor_opt.zero_grad(set_to_none=True)
-                actor_loss.backward()
-                self._allreduce_grads(self.actor)
-                self.actor_opt.step()
-                with torch.no_grad():
-                    for p, pt in zip(self.actor.parameters(), self.actor_target.parameters()):
-                        pt.mul_(1 - c.tau).add_(p, alpha=c.tau)
-                    for p, pt in zip(self.critics.parameters(), self.critics_target.parameters()):
-                        pt.mul_(1 - c.tau).add_(p, alpha=c.tau)
+                self._graph = torch.cuda.CUDAGraph()
+                # thread_local: the NCCL watchdog thread may query events while this thread captures
+                with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                    self._cycle(stats)
+            for _ in range(cycles):
+                self._graph.replay()
+            self.n_updates += cycles * c.policy_delay
+            gradient_steps -= cycles * c.policy_delay
+        for _ in range(gradient_steps):               # eager path (cuda_graph off, or a remainder)
+            self.n_updates += 1
+            self._update(self.n_updates % c.policy_delay == 0)
 
     def _broadcast_parameters(self):
         import torch.distributed as dist
@@ -332,6 +390,16 @@ class HgeTD3:
             self.vec_normalize.load_state_dict(sd["vec_normalize"])
         self.num_timesteps, self.n_updates = sd["num_timesteps"], sd["n_updates"]
         return self
+
+    def close(self):
+        """Drop the captured update graph (it holds NCCL work when gradients are averaged across ranks: the
+        process group must not be destroyed under it)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.device)
 
     def time_split(self):
         t = self.timers

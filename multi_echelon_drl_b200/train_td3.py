@@ -36,6 +36,7 @@ def main(argv=None):
     ap.add_argument("--n-envs", type=int, default=4096)
     ap.add_argument("--timesteps", type=int, default=None)
     ap.add_argument("--log-interval", type=int, default=320)
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the TD3 update eagerly instead of as a CUDA graph")
     args = ap.parse_args(argv)
 
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
@@ -68,17 +69,21 @@ def main(argv=None):
                     learning_rate=p.get("learning_rate", 1e-3), tau=p.get("tau", 0.01), train_freq=p.get("train_freq", 32),
                     gradient_steps=p.get("gradient_steps", p.get("train_freq", 32)),
                     action_noise_std=p.get("action_noise_std", 0.4), gamma=p.get("gamma", 0.95),
-                    hge_rate_at_start=p.get("hge_rate_at_start", 0.5), seed=rank)
+                    hge_rate_at_start=p.get("hge_rate_at_start", 0.5), seed=rank,
+                    cuda_graph=not args.no_cuda_graph)
     heuristic = bsp if cfg.hge_rate_at_start > 0 else None
     model = HgeTD3(env, heuristic, cfg, ddp=world > 1)
     total = args.timesteps or setup.get("max_time_steps", 10_000_000)
     model.learn(total, log_interval=args.log_interval if rank == 0 else None)
     if rank == 0:
         out = {"name": args.name, "env": env_name, "n_envs_per_gpu": args.n_envs, "n_gpus": world,
-               "timesteps": model.num_timesteps, "updates": model.n_updates, "time_split": model.time_split(),
+               "timesteps": model.num_timesteps, "updates": model.n_updates, "cuda_graph": cfg.cuda_graph,
+               "time_split": model.time_split(),
                "last_mean_episode_return": model.episode_returns[-1] if model.episode_returns else None}
         print(json.dumps(out))
+    model.close()
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

@@ -81,9 +81,19 @@ class VecNormalize:
         self._obs_rms.reverse()
         self._ret_rms.reverse()
 
-    def _apply(self, obs, obs_out, reward, reward_out, reset_returns, n=None):
+    def frozen_stats(self):
+        """Copy of the current statistics in buffers whose addresses never change (the live ones are
+        ping-pong pairs): what a captured CUDA graph normalises with; refresh by calling this again."""
+        if not hasattr(self, "_frozen"):
+            self._frozen = (torch.empty_like(self._obs_rms[0]), torch.empty_like(self._ret_rms[0]))
+        self._frozen[0].copy_(self._obs_rms[0])
+        self._frozen[1].copy_(self._ret_rms[0])
+        return self._frozen
+
+    def _apply(self, obs, obs_out, reward, reward_out, reset_returns, n=None, stats=None):
+        obs_rms, ret_rms = stats if stats is not None else (self._obs_rms[0], self._ret_rms[0])
         rc = self.lib.sn_vecnorm_apply(self.num_envs if n is None else n, self.od, _p(obs), _p(obs_out), _p(reward), _p(reward_out),
-                                       _p(self._obs_rms[0]), _p(self._ret_rms[0]), self.clip_obs, self.clip_reward,
+                                       _p(obs_rms), _p(ret_rms), self.clip_obs, self.clip_reward,
                                        self.epsilon, int(reset_returns), _p(self.returns), self._stream())
         _lib.check(rc)
 
@@ -136,19 +146,20 @@ class VecNormalize:
     def get_original_reward(self):
         return self.old_reward
 
-    def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
-        """Normalise any batch [m, obs_dim] with the current statistics (no update)."""
+    def normalize_obs(self, obs: torch.Tensor, stats=None) -> torch.Tensor:
+        """Normalise any batch [m, obs_dim] with the current statistics (no update), or with `stats` =
+        `frozen_stats()`."""
         if not self.norm_obs:
             return obs
         out = torch.empty_like(obs, dtype=torch.float32)
-        self._apply(obs.to(torch.float32).contiguous(), out, None, None, False, n=obs.shape[0])
+        self._apply(obs.to(torch.float32).contiguous(), out, None, None, False, n=obs.shape[0], stats=stats)
         return out
 
-    def normalize_reward(self, reward: torch.Tensor) -> torch.Tensor:
+    def normalize_reward(self, reward: torch.Tensor, stats=None) -> torch.Tensor:
         if not self.norm_reward:
             return reward
         out = torch.empty_like(reward, dtype=torch.float32)
-        self._apply(None, None, reward.to(torch.float32).contiguous(), out, False, n=reward.shape[0])
+        self._apply(None, None, reward.to(torch.float32).contiguous(), out, False, n=reward.shape[0], stats=stats)
         return out
 
     def close(self):
