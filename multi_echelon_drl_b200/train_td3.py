@@ -74,10 +74,15 @@ def main(argv=None):
     heuristic = bsp if cfg.hge_rate_at_start > 0 else None
     model = HgeTD3(env, heuristic, cfg, ddp=world > 1)
     total = args.timesteps or setup.get("max_time_steps", 10_000_000)
+    import time
+    t0 = time.time()
     model.learn(total, log_interval=args.log_interval if rank == 0 else None)
+    torch.cuda.synchronize()
+    wall = time.time() - t0
     if rank == 0:
         out = {"name": args.name, "env": env_name, "n_envs_per_gpu": args.n_envs, "n_gpus": world,
                "timesteps": model.num_timesteps, "updates": model.n_updates, "cuda_graph": cfg.cuda_graph,
+               "wall_s": wall, "env_steps_per_s": model.num_timesteps * world / wall,
                "time_split": model.time_split(),
                "last_mean_episode_return": model.episode_returns[-1] if model.episode_returns else None}
         print(json.dumps(out))

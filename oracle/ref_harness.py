@@ -162,3 +162,76 @@ def make_custom_chain_env(info_lt, ship_lt, agents, global_observable=False, max
     if dplusa is not None:
         env = ref["wrappers"].wrap_action_d_plus_a(env, offset=dplusa[0], lb=dplusa[1], ub=dplusa[2])
     return env
+
+
+# ---------------------------------------------------------------------- distribution trees
+def make_network_env(nodes, arcs, agents, global_observable=False, max_episode_steps=100,
+                     init_inventory=(0, 25), init_pipeline=(0, 9), dplusa=None, external_name="external_supplier"):
+    """Any network the reference's classes accept, built like envs.py:289-414 builds the chain.
+    nodes: list of dict(name, target, holding, backorder, demand=None | (low, high))  (internal nodes, node-list
+    order; the external supplier is appended); arcs: list of (source, target, info_lt, ship_lt) in arc-list order;
+    agents: node names in caller order."""
+    ref = import_reference()
+    E, NC, SN, HE, DE = ref["envs"], ref["nc"], ref["sn"], ref["heuristics"], ref["demands"]
+    import gym
+    idx = {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1, "latest_demand": 2}
+    objs = []
+    for nd in nodes:
+        kw = dict(name=nd["name"], initial_inventory=list(init_inventory), holding_cost=nd["holding"],
+                  backorder_cost=nd["backorder"],
+                  policy=HE.BaseStockPolicy(target_levels=[nd["target"]], array_index=idx, state_dim_per_facility=7))
+        if nd.get("demand") is not None:
+            lo, hi = nd["demand"]
+            kw.update(is_demand_source=True, demands=DE.Demand("uniform", low=lo, high=hi, size=max_episode_steps))
+        objs.append(NC.Node(**kw))
+    objs.append(NC.Node(name=external_name, is_external_supplier=True))
+    arc_objs = [NC.Arc(s, t, li, ls, initial_shipments=list(init_pipeline), initial_sales_orders=list(init_pipeline),
+                       random_init=True) for (s, t, li, ls) in arcs]
+    net = SN.SupplyNetwork(nodes=objs, arcs=arc_objs, agent_managed_facilities=list(agents))
+    n_obs = len(nodes) if global_observable else len(agents)
+    env = E.InventoryManagementEnvMultiPlayer(
+        net, max_episode_steps=max_episode_steps, action_space=gym.spaces.Box(0, 16, shape=(len(agents),)),
+        observation_space=gym.spaces.Box(low=-np.inf, high=np.inf, shape=(7 * n_obs,)), global_observable=global_observable)
+    if dplusa is not None:
+        env = ref["wrappers"].wrap_action_d_plus_a(env, offset=dplusa[0], lb=dplusa[1], ub=dplusa[2])
+    return env
+
+
+def read_network_state(env, names):
+    """(inv0[N], so[N][*], sh[N][*], demands[n_sources][T+3]) of a reference env right after sn.reset(); per node
+    the pipelines of its (single) upstream arc, nearest first; demand streams in node order of the sources."""
+    sn = env.sn
+    inv0 = [sn.nodes[n].current_inventory for n in names]
+    so, sh = [], []
+    for n in names:
+        (sup,) = sn.suppliers[n]
+        arc = sn.arcs[(sup, n)]
+        so.append([o.order_quantity for o in sorted(arc.sales_orders, key=lambda o: o.remaining_lead_time)])
+        sh.append([s.quantity for s in sorted(arc.shipments, key=lambda s: s.time_till_arrival)])
+    dem = [np.asarray(sn.nodes[n].demands._demands).copy() for n in names if sn.nodes[n].is_demand_source]
+    return inv0, so, sh, dem
+
+
+def network_rollout(env, names, actions, seed):
+    """Like rollout() for a network env: dict(obs0, init, obs[T], rew[T], holding[T,N], backorder[T,N])."""
+    np.random.seed(seed)
+    env.terminal = False
+    env.sn.reset()
+    env.period = 0
+    init = read_network_state(env, names)
+    env.sn.before_action(0)
+    obs_names = env.sn.internal_nodes if env.global_observable else env.sn.agent_managed_facilities
+    obs0 = np.array([list(env.sn.get_state(a).values()) for a in obs_names], dtype=np.float32).flatten()
+    obs_l, rew_l = [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for a in actions:
+            o, r, d, _ = env.step(a)
+            obs_l.append(o)
+            rew_l.append(r)
+            if d:
+                break
+    h = np.array([env.sn.nodes[n].holding_cost_history for n in names], dtype=np.float64).T
+    b = np.array([env.sn.nodes[n].backorder_cost_history for n in names], dtype=np.float64).T
+    return dict(obs0=obs0, init=init, obs=np.stack(obs_l), rew=np.array(rew_l, dtype=np.float64), holding=h, backorder=b,
+                order_sequence=list(env.sn.order_sequence))

@@ -15,6 +15,7 @@ Files written
                   tests/test_supplynetwork.py:25-69, with per-step outputs
   leadtimes.npz   serial chains with other per-arc lead times (general-chain path)
   chains.npz      serial chains with 1..3 facilities
+  trees.npz       distribution trees (one supplier per node, several customers and / or own demand per node)
 """
 import os
 import sys
@@ -223,6 +224,76 @@ def gen_short_chains():
     print("short chains:", cid, "cases")
 
 
+# Distribution trees.  Per topology: nodes in node-list order as (name, supplier name | "EXT", demand range |
+# None, base-stock target, holding cost, backorder cost, info lead time, shipment lead time of its upstream arc)
+# and the arc-list order (arcs named by their customer).  Names and arc order are chosen so that the reference's
+# order sequence (utils/graph.py:5-32) differs from the node-list order in some of them.
+TREES = {
+    "two_ret": ([("ret_a", "whole", (0, 8), 19, 0.5, 1, 2, 2), ("ret_b", "whole", (0, 4), 15, 0.5, 1, 1, 3),
+                 ("whole", "EXT", None, 30, 0.5, 1, 1, 2)], ["whole", "ret_a", "ret_b"]),
+    "two_ret_rev": ([("whole", "EXT", None, 30, 0.25, 2, 2, 2), ("ret_b", "whole", (0, 4), 15, 0.5, 1, 1, 3),
+                     ("ret_a", "whole", (0, 8), 19, 1.0, 0.5, 2, 2)], ["ret_b", "ret_a", "whole"]),
+    "three_ret": ([("r1", "hub", (0, 8), 19, 0.5, 1, 2, 2), ("r2", "hub", (0, 6), 12, 0.5, 1, 2, 1),
+                   ("r3", "hub", (0, 3), 9, 0.5, 1, 1, 1), ("hub", "EXT", None, 40, 0.5, 1, 2, 3)],
+                  ["hub", "r3", "r1", "r2"]),
+    "two_level": ([("shop", "dist_a", (0, 8), 19, 0.5, 1, 2, 2), ("dist_a", "maker", None, 20, 0.5, 1, 2, 2),
+                   ("dist_b", "maker", (0, 5), 14, 0.5, 1, 1, 2), ("maker", "EXT", None, 25, 0.5, 1, 1, 2)],
+                  ["maker", "dist_b", "dist_a", "shop"]),
+    "src_with_cust": ([("outlet", "store", (0, 5), 12, 0.5, 1, 1, 2), ("store", "depot", (0, 6), 22, 0.5, 1, 2, 2),
+                       ("depot", "EXT", None, 25, 0.5, 1, 1, 3)], ["depot", "store", "outlet"]),
+    "two_roots": ([("a_shop", "a_dc", (0, 8), 19, 0.5, 1, 2, 2), ("a_dc", "EXT", None, 20, 0.5, 1, 1, 2),
+                   ("b_shop", "b_dc", (0, 8), 19, 0.5, 1, 2, 2), ("b_dc", "EXT", None, 20, 0.5, 1, 2, 1)],
+                  ["a_dc", "a_shop", "b_dc", "b_shop"]),
+    "chain_as_tree": ([("retailer", "wholesaler", (0, 8), 19, 0.5, 1, 2, 2), ("wholesaler", "distributor", None, 20, 0.5, 1, 2, 2),
+                       ("distributor", "manufacturer", None, 20, 0.5, 1, 2, 2), ("manufacturer", "EXT", None, 14, 0.5, 1, 1, 2)],
+                      ["manufacturer", "distributor", "wholesaler", "retailer"]),
+}
+TREE_AGENTS = {   # node indices, caller order; all contiguous in the respective order sequence
+    "two_ret": [(0, 1, 2), (2,), (1,), (1, 2), (2, 1, 0)],
+    "two_ret_rev": [(0, 1, 2), (0,), (2,), (2, 0), (1, 2)],
+    "three_ret": [(0, 1, 2, 3), (3,), (2,), (1, 3), (0, 1), (3, 1, 0)],
+    "two_level": [(0, 1, 2, 3), (3,), (1,), (2, 3), (1, 2), (0, 1, 2)],
+    "src_with_cust": [(0, 1, 2), (1,), (2,), (0, 1)],
+    "two_roots": [(0, 1, 2, 3), (1, 2), (3,), (0,), (2, 3)],
+    "chain_as_tree": [(0, 1, 2, 3), (2,), (3, 2)],
+}
+
+
+def gen_trees():
+    import json
+    out, meta, cid = {}, [], 0
+    for topo, (nodes, arc_order) in TREES.items():
+        names = [n[0] for n in nodes]
+        byname = {n[0]: n for n in nodes}
+        nd = [dict(name=n[0], target=n[3], holding=n[4], backorder=n[5], demand=n[2]) for n in nodes]
+        arcs = [("external_supplier" if byname[c][1] == "EXT" else byname[c][1], c, byname[c][6], byname[c][7])
+                for c in arc_order]
+        for ag in TREE_AGENTS[topo]:
+            for glob, rule in ((False, "a"), (True, "d+a"), (True, "a")):
+                seed = 2100 + cid
+                env = H.make_network_env(nd, arcs, [names[a] for a in ag], glob,
+                                         dplusa=(-8, 0, 16) if rule == "d+a" else None)
+                acts = np.random.RandomState(9000 + cid).randint(-1, 19, (100, len(ag))).astype(np.int64)
+                r = H.network_rollout(env, names, [a for a in acts], seed)
+                inv0, so, sh, dem = r["init"]
+                init, _ = flat_init_generic((inv0, so, sh, []))
+                p = f"t{cid:03d}_"
+                out.update({p + "init": init, p + "demand": np.asarray(dem, dtype=np.int64), p + "actions": acts,
+                            p + "obs0": r["obs0"], p + "obs": r["obs"], p + "rew": r["rew"],
+                            p + "holding": r["holding"], p + "backorder": r["backorder"]})
+                meta.append(json.dumps(dict(
+                    cid=cid, topo=topo, names=names, supplier=[-1 if n[1] == "EXT" else names.index(n[1]) for n in nodes],
+                    demand=[list(n[2]) if n[2] else None for n in nodes], target=[n[3] for n in nodes],
+                    holding=[n[4] for n in nodes], backorder=[n[5] for n in nodes], li=[n[6] for n in nodes],
+                    ls=[n[7] for n in nodes], arc_order=[names.index(c) for c in arc_order], agents=list(ag),
+                    glob=glob, rule=rule, seed=seed,
+                    order_sequence=[s for s in r["order_sequence"] if s != "external_supplier"])))
+                cid += 1
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "trees.npz"), **out)
+    print("trees:", cid, "cases")
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore", RuntimeWarning)
     gen_rollouts()
@@ -231,3 +302,4 @@ if __name__ == "__main__":
     gen_classic()
     gen_leadtimes()
     gen_short_chains()
+    gen_trees()

@@ -1,0 +1,130 @@
+"""Distribution-tree oracle (oracle/network_np.py) vs trajectories recorded from the reference's own classes on
+tree networks (tests/golden/trees.npz), vs the serial-chain oracle, and - when /root/reference is mounted -
+vs the live reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.network_np import EXTERNAL, TreeOracle, TreeSpec
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cases():
+    z = np.load(f"{GOLDEN}/trees.npz")
+    out = []
+    for m in z["meta"]:
+        c = json.loads(str(m))
+        p = f"t{c['cid']:03d}_"
+        c["id"] = f"{c['topo']}-ag{''.join(map(str, c['agents']))}-g{int(c['glob'])}-{c['rule']}"
+        for k in ("init", "actions", "obs0", "obs", "rew"):
+            c[k] = z[p + k]
+        c["demand_table"] = z[p + "demand"]                       # [n_sources, T+3]; c["demand"] stays the per-node ranges
+        c["ref_holding"], c["ref_backorder"] = z[p + "holding"], z[p + "backorder"]   # c["holding"] = coefficients
+        out.append(c)
+    return out
+
+
+TREE_CASES = _cases()
+
+
+def oracle_spec(case) -> TreeSpec:
+    return TreeSpec(names=case["names"], supplier=case["supplier"], demand_source=[d is not None for d in case["demand"]],
+                    info_lt=case["li"], ship_lt=case["ls"], holding_cost=case["holding"], backorder_cost=case["backorder"],
+                    coplayer_target=case["target"], arc_order=case["arc_order"], agents=tuple(case["agents"]),
+                    global_observable=case["glob"], rule=case["rule"])
+
+
+def tree_oracle_rollout(case, init36, demand, actions, return_costs=False):
+    """init36 [n, 36] (inv[4], so[k][0..3], sh[k][0..3] by node); demand [n, n_sources, T+3]; actions [T, n, n_agents]."""
+    spec = oracle_spec(case)
+    n, N = init36.shape[0], len(case["names"])
+    orc = TreeOracle(spec, n)
+    so = [init36[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] for k in range(N)]
+    sh = [init36[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] for k in range(N)]
+    obs0 = orc.reset(init36[:, :N], so, sh, demand)
+    obs, rew, hold, back = [], [], [], []
+    for t in range(actions.shape[0]):
+        o, r, _ = orc.step(actions[t])
+        orc.check_invariant()
+        obs.append(o); rew.append(r); hold.append(orc.holding.copy()); back.append(orc.backorder.copy())
+    if return_costs:
+        return obs0, np.stack(obs), np.stack(rew), np.stack(hold), np.stack(back)
+    return obs0, np.stack(obs), np.stack(rew)
+
+
+@pytest.mark.parametrize("case", TREE_CASES, ids=[c["id"] for c in TREE_CASES])
+def test_tree_oracle_matches_reference_golden(case):
+    obs0, obs, rew, hold, back = tree_oracle_rollout(case, case["init"][None], case["demand_table"][None],
+                                                     case["actions"][:, None, :], return_costs=True)
+    spec = oracle_spec(case)
+    assert [case["names"][k] for k in spec.sequence] == case["order_sequence"]
+    assert np.array_equal(obs0[0], case["obs0"])
+    assert np.array_equal(obs[:, 0], case["obs"]) and np.array_equal(rew[:, 0], case["rew"])
+    assert np.array_equal(hold[:, 0], case["ref_holding"]) and np.array_equal(back[:, 0], case["ref_backorder"])
+
+
+def test_tree_oracle_equals_chain_oracle_on_chains():
+    """A serial chain is a tree: both restatements agree on a batch, for two lead-time sets and agent sets."""
+    from dataclasses import replace
+    from oracle import beergame_np as O
+    rs = np.random.RandomState(3)
+    for li, ls, ag, glob, rule in (((2, 2, 2, 1), (2, 2, 2, 2), (0, 1, 2, 3), True, "a"), ((3, 1, 2, 2), (2, 4, 3, 1), (2, 1), False, "d+a"),
+                                   ((1, 2, 2), (2, 2, 3), (1,), True, "a")):
+        nf, n = len(li), 64
+        init = np.zeros((n, 36), dtype=np.int64)
+        init[:, :nf] = rs.randint(0, 25, (n, nf))
+        for k in range(nf):
+            init[:, 4 + 4 * k: 4 + 4 * k + li[k]] = rs.randint(0, 9, (n, li[k]))
+            init[:, 20 + 4 * k: 20 + 4 * k + ls[k]] = rs.randint(0, 9, (n, ls[k]))
+        dem = rs.randint(0, 9, (n, 103))
+        acts = rs.randint(-1, 19, (100, n, len(ag)))
+        cs = replace(O.scenario_spec("uniform", ag, glob, 100, rule), info_lt=li, ship_lt=ls, n_facilities=nf)
+        chain = O.BeerGameOracle(cs, n)
+        o0 = chain.reset(init[:, :4], [init[:, 4 + 4 * k: 4 + 4 * k + li[k]] for k in range(nf)],
+                         [init[:, 20 + 4 * k: 20 + 4 * k + ls[k]] for k in range(nf)], dem)
+        names = ["retailer", "wholesaler", "distributor", "manufacturer"][:nf]
+        case = dict(names=names, supplier=list(range(1, nf)) + [EXTERNAL], demand=[(0, 8)] + [None] * (nf - 1), li=li, ls=ls,
+                    holding=[0.5] * nf, backorder=[1.0] * nf, target=[19, 20, 20, 14][:nf], arc_order=list(range(nf - 1, -1, -1)),
+                    agents=ag, glob=glob, rule=rule)
+        t0, tobs, trew = tree_oracle_rollout(case, init, dem[:, None, :], acts)
+        assert np.array_equal(o0, t0)
+        for t in range(100):
+            o, r, _ = chain.step(acts[t])
+            assert np.array_equal(o, tobs[t]) and np.array_equal(r, trew[t]), t
+
+
+def test_tree_spec_rejects_agents_not_contiguous_in_order_sequence():
+    c = TREE_CASES[0]
+    with pytest.raises(ValueError):
+        TreeSpec(names=["shop", "dist_a", "dist_b", "maker"], supplier=[1, 3, 3, EXTERNAL], demand_source=[True, False, True, False],
+                 info_lt=[2, 2, 1, 1], ship_lt=[2, 2, 2, 2], holding_cost=[0.5] * 4, backorder_cost=[1] * 4,
+                 coplayer_target=[19, 20, 14, 25], arc_order=[3, 2, 1, 0], agents=(0, 2))   # shop, [dist_a], dist_b
+    assert c is not None
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_harness", fromlist=["x"]).reference_available(),
+                    reason="/root/reference not mounted (GPU box)")
+def test_tree_oracle_vs_live_reference():
+    from oracle import ref_harness as H
+    for cid in (0, 17, 33, 58, 71, 90):
+        c = TREE_CASES[cid]
+        names = c["names"]
+        nd = [dict(name=names[k], target=c["target"][k], holding=c["holding"][k], backorder=c["backorder"][k],
+                   demand=tuple(c["demand"][k]) if c["demand"][k] else None) for k in range(len(names))]
+        arcs = [("external_supplier" if c["supplier"][k] < 0 else names[c["supplier"][k]], names[k], c["li"][k], c["ls"][k])
+                for k in c["arc_order"]]
+        env = H.make_network_env(nd, arcs, [names[a] for a in c["agents"]], c["glob"],
+                                 dplusa=(-8, 0, 16) if c["rule"] == "d+a" else None)
+        acts = np.random.RandomState(cid).randint(0, 17, (100, len(c["agents"])))
+        r = H.network_rollout(env, names, [a for a in acts], seed=5000 + cid)
+        inv0, so, sh, dem = r["init"]
+        init = np.zeros(36, dtype=np.int64)
+        init[:len(inv0)] = inv0
+        for k in range(len(inv0)):
+            init[4 + 4 * k: 4 + 4 * k + len(so[k])] = so[k]
+            init[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
+        o0, obs, rew = tree_oracle_rollout(c, init[None], np.asarray(dem)[None], acts[:, None, :])
+        assert np.array_equal(o0[0], r["obs0"]) and np.array_equal(obs[:, 0], r["obs"]) and np.array_equal(rew[:, 0], r["rew"])
