@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 5
+#define SN_ABI_VERSION 6
 
 #define SN_MAX_FACILITIES 4
 #define SN_MAX_ITEMS 4
@@ -36,10 +36,13 @@ extern "C" {
 #define SN_INIT_WORDS 19        /* inv[4], sales orders (2,2,2,1), shipments (2,2,2,2) */
 #define SN_GEN_STATE_WORDS 57   /* chains with other lead times: 28 + 4x3 order slips + 4x4 shipments + 1 */
 #define SN_GEN_INIT_WORDS 36    /* inv[4]; so[k][0..3] at 4+4k; sh[k][0..3] at 20+4k (unused slots 0)      */
+#define SN_TREE_STATE_WORDS 64  /* distribution trees: 28 + 12 + 16 + backlog[4] + current external demand[4] */
 #define SN_STATS_WORDS 16
 
 enum { SN_I32 = 0, SN_F32 = 1, SN_F64 = 2 };
 enum { SN_RULE_A = 0, SN_RULE_D_PLUS_A = 1 };
+enum { SN_TOPO_CHAIN = 0, SN_TOPO_TREE = 1 };
+#define SN_EXTERNAL (-1)
 enum {
   SN_POLICY_ACTIONS = 0,      /* actions streamed from memory, [T][N][n_agents]            */
   SN_POLICY_BASE_STOCK = 1    /* utils/heuristics.py base-stock evaluated in-kernel per env */
@@ -79,9 +82,24 @@ typedef struct sn_spec {
    * [n_envs][I*7*F'] and likewise for actions; rewards are per chain.  Item 0 uses holding_cost /
    * backorder_cost above, item i >= 1 uses item_*_cost[i-1].  n_items = 0 is read as 1. */
   int32_t n_items;
-  int32_t reserved_;
+  int32_t topology;                           /* SN_TOPO_CHAIN (0): the fields below are ignored; SN_TOPO_TREE */
   double item_holding_cost[SN_MAX_ITEMS - 1][SN_MAX_FACILITIES];
   double item_backorder_cost[SN_MAX_ITEMS - 1][SN_MAX_FACILITIES];
+  /* Distribution trees (SN_TOPO_TREE): every internal node k buys from ONE supplier and may serve several
+   * customers and / or its own external demand.  This is what SupplyNetwork does for such node/arc lists
+   * (supplynetwork.py:22-56, 182-268): node k is the k-th internal node of the node list (observation and cost
+   * order); its upstream arc carries info_leadtime[k] / ship_leadtime[k].  The demand tables then hold one row
+   * per demand source and period, sources in node order: demand [T+3][n_sources][ld], demand0 / demand_next
+   * [n_sources][ld].  Multi-supplier (assembly) nodes are not supported: the reference's own state keys collide
+   * there (supplynetwork.py:165-167). */
+  int32_t supplier[SN_MAX_FACILITIES];        /* supplier node of node k, SN_EXTERNAL = the external supplier   */
+  int32_t demand_source[SN_MAX_FACILITIES];   /* Node.is_demand_source                                           */
+  int32_t order_pos[SN_MAX_FACILITIES];       /* position of node k among the internal nodes in the order sequence
+                                               * (utils/graph.py:5-32): customers before suppliers; the agents
+                                               * must be contiguous in it (supplynetwork.py:201,231)             */
+  int32_t customer_rank[SN_MAX_FACILITIES];   /* rank of node k among its supplier's customers in customers_dict
+                                               * order (= arc-list order, supplynetwork.py:22-25): the supplier
+                                               * serves rank 0 first (Arc.fill_orders per arc, :260-262)         */
 } sn_spec;
 
 /* Base-stock policy parameters (utils/heuristics.py:13-33), used by sn_heuristic and by
@@ -106,7 +124,8 @@ int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype);
 
 /* Rows of the `state` / `init` buffers for this spec: SN_STATE_WORDS / SN_INIT_WORDS for the beer game's
  * lead times (tuned kernels), SN_GEN_STATE_WORDS / SN_GEN_INIT_WORDS for any other supported lead times
- * (generic kernels, network_components.py:108-168 with Arc(information_leadtime, shipment_leadtime)). */
+ * (generic kernels, network_components.py:108-168 with Arc(information_leadtime, shipment_leadtime)),
+ * SN_TREE_STATE_WORDS / SN_GEN_INIT_WORDS for SN_TOPO_TREE. */
 int32_t sn_state_words(const sn_spec* spec);
 int32_t sn_init_words(const sn_spec* spec);
 

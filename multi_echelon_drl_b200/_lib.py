@@ -13,10 +13,11 @@ LIB_PATH = os.environ.get("SUPPLYNET_LIB", os.path.join(_HERE, "csrc", "libsuppl
 
 SN_I32, SN_F32, SN_F64 = 0, 1, 2
 SN_RULE_A, SN_RULE_D_PLUS_A = 0, 1
+SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class SnSpec(C.Structure):
@@ -38,9 +39,13 @@ class SnSpec(C.Structure):
         ("dpa_lb", C.c_double),
         ("dpa_ub", C.c_double),
         ("n_items", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("topology", C.c_int32),
         ("item_holding_cost", (C.c_double * 4) * 3),
         ("item_backorder_cost", (C.c_double * 4) * 3),
+        ("supplier", C.c_int32 * 4),
+        ("demand_source", C.c_int32 * 4),
+        ("order_pos", C.c_int32 * 4),
+        ("customer_rank", C.c_int32 * 4),
     ]
 
 

@@ -51,6 +51,15 @@ struct DevSpec {
   int lo;              // first agent index: nodes below it order inside before_action
   int rule;
   int t_max;
+  // distribution trees (supplynet_tree.cuh); chains leave these at their chain values
+  int sup[kF];         // supplier node of node k, -1 = external supplier (also for phantom nodes)
+  int rank[kF];        // rank of node k among its supplier's customers (served in this order)
+  int max_rank;        // largest rank in use (rounds of the fill loop)
+  int lat_src[kF];     // customer whose arrived order is node j's latest demand (the customer latest in the order
+                       // sequence overwrites the others, supplynetwork.py:193), -1 = none
+  int src[kF];         // row of node k's demand stream in the demand tables, -1 = not a demand source
+  int n_src;
+  int pre[kF];         // node k orders inside before_action (its place in the order sequence is ahead of the first agent)
 };
 
 template <typename T>
@@ -66,6 +75,8 @@ struct Env {
 
   // "unfilled_demand" of node k as SupplyNetwork.get_state reports it (supplynetwork.py:130-136)
   __device__ __forceinline__ T unfilled(int k) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+  // co-player that orders inside before_action (chain position below the first agent)
+  static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return k < kF - 1 && k < sp.lo; }
 };
 
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
@@ -157,7 +168,7 @@ template <int K, typename T, typename E>
 __device__ __forceinline__ void node_view(const E& e, const DevSpec<T>& sp, bool terminal, float (&v)[7]) {
   T u0 = e.U[K][0], u1 = e.U[K][1], u2 = e.U[K][2], u3 = e.U[K][3];
   const T unf = e.unfilled(K);
-  if (K < kF - 1 && K < sp.lo && !terminal) {
+  if (E::pre_agent(K, sp) && !terminal) {
     const T q = tmax(base_stock(sp.target[K], e.inv[K], e.U[K], unf, e.lat[K], sp.clb, sp.cub, 0), T(0));
     u3 = u2; u2 = u1; u1 = u0; u0 = q;
   }

@@ -15,7 +15,7 @@
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
 // the 112-byte-per-thread pattern reaches L2 as full lines.
 #include "supplynet_core.cuh"
-#include "supplynet_generic.cuh"
+#include "supplynet_tree.cuh"
 #include "../../include/supplynet.h"
 
 #include <cmath>
@@ -160,7 +160,12 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __rest
 template <typename T>
 struct StdOps {
   using E = Env<T>;
-  static __device__ __forceinline__ void load(const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
+  using D = T;                                     // demand of one period: one number per env
+  static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
+  static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t, int64_t env, const DevSpec<T>&) {
+    return __ldg(row + env);
+  }
+  static __device__ __forceinline__ void load(const DevSpec<T>&, const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
     T w[kStateWords];
 #pragma unroll
     for (int i = 0; i < kStateWords; ++i) w[i] = state[i * ld + env];
@@ -189,7 +194,12 @@ struct StdOps {
 template <typename T>
 struct GenOps {
   using E = GEnv<T>;
-  static __device__ __forceinline__ void load(const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
+  using D = T;
+  static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
+  static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t, int64_t env, const DevSpec<T>&) {
+    return __ldg(row + env);
+  }
+  static __device__ __forceinline__ void load(const DevSpec<T>&, const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
     T w[kGStateWords];
 #pragma unroll
     for (int i = 0; i < kGStateWords; ++i) w[i] = state[i * ld + env];
@@ -215,6 +225,44 @@ struct GenOps {
   }
 };
 
+// distribution trees (supplynet_tree.cuh, 64 words): one demand row per source and period
+template <typename T>
+struct TreeOps {
+  using E = TEnv<T>;
+  using D = TreeDem<T>;
+  static __device__ __forceinline__ int64_t dstride(const DevSpec<T>& sp, int64_t ld) { return ld * sp.n_src; }
+  static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t ld, int64_t env, const DevSpec<T>& sp) {
+    D d;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) d.v[k] = sp.src[k] >= 0 ? __ldg(row + sp.src[k] * ld + env) : T(0);
+    return d;
+  }
+  static __device__ __forceinline__ void load(const DevSpec<T>& sp, const T* __restrict__ state, int64_t ld, int64_t env, E& e) {
+    T w[kTStateWords];
+#pragma unroll
+    for (int i = 0; i < kTStateWords; ++i) w[i] = state[i * ld + env];
+    tenv_from_words(e, sp, w);
+  }
+  static __device__ __forceinline__ void store(T* __restrict__ state, int64_t ld, int64_t env, const E& e) {
+    T w[kTStateWords];
+    tenv_to_words(e, w);
+#pragma unroll
+    for (int i = 0; i < kTStateWords; ++i) state[i * ld + env] = w[i];
+  }
+  static __device__ __forceinline__ void reset(E& e, const DevSpec<T>& sp, const T* __restrict__ init, int64_t ld,
+                                               int64_t env, const D& d0) {
+    T in[kGInitWords];
+#pragma unroll
+    for (int w = 0; w < kGInitWords; ++w) in[w] = __ldg(init + w * ld + env);
+    tenv_reset(e, sp, in, d0);
+  }
+  template <bool MULTI>
+  static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int, const T (&q)[kF], const D& dn, bool terminal,
+                                              StepOut& so) {
+    tenv_step(e, sp, q, dn, terminal, so);
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 template <typename T, bool IDENT, typename Ops>
 __global__ void __launch_bounds__(kBlock)
@@ -225,7 +273,7 @@ k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* _
   const bool valid = env < n;
   typename Ops::E e;
   if (valid) {
-    Ops::reset(e, sp, init, ld, env, __ldg(demand0 + env));
+    Ops::reset(e, sp, init, ld, env, Ops::load_demand(demand0, ld, env, sp));
     Ops::store(state, ld, env, e);
   }
   if (obs != nullptr) {
@@ -243,7 +291,7 @@ k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T*
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
   typename Ops::E e;
-  if (valid) Ops::load(state, ld, env, e);
+  if (valid) Ops::load(sp, state, ld, env, e);
   ObsStager st(smem_f);
   write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
   st.drain();
@@ -272,10 +320,10 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
 #pragma unroll
   for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
   if (valid) {
-    Ops::load(state, ld, env, e);
+    Ops::load(sp, state, ld, env, e);
     T a[kF] = {T(0), T(0), T(0), T(0)};
     load_actions<IDENT>(actions, env, sp, a);
-    const T dn = __ldg(demand_next + env);
+    const typename Ops::D dn = Ops::load_demand(demand_next, ld, env, sp);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
     if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal != 0, so);
@@ -352,10 +400,10 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   typename Ops::E e;
   if (init != nullptr) {
     // episode mode (sn_episode): reset in-kernel, the state never has to exist in HBM
-    Ops::reset(e, sp, init, ld, envc, __ldg(demand + envc));
+    Ops::reset(e, sp, init, ld, envc, Ops::load_demand(demand, ld, envc, sp));
     if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, 1, use_tma != 0);
   } else {
-    Ops::load(state, ld, envc, e);
+    Ops::load(sp, state, ld, envc, e);
   }
   double acc[10];
 #pragma unroll
@@ -365,7 +413,8 @@ k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPoli
   // software pipeline: inputs of step s+1 are requested before step s is computed
   T a_pre[kF] = {T(0), T(0), T(0), T(0)};
   if (POLICY == SN_POLICY_ACTIONS) load_actions<IDENT>(actions, envc, sp, a_pre);
-  T d_pre = __ldg(demand + (int64_t)(period0 + 1) * ld + envc);
+  const int64_t dstride = Ops::dstride(sp, ld);
+  typename Ops::D d_pre = Ops::load_demand(demand + (int64_t)(period0 + 1) * dstride, ld, envc, sp);
 
 SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
   for (int s = 0; s < n_steps; ++s) {
@@ -374,10 +423,10 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     T a[kF];
 #pragma unroll
     for (int i = 0; i < kF; ++i) a[i] = a_pre[i];
-    const T dn = d_pre;
+    const typename Ops::D dn = d_pre;
     if (s + 1 < n_steps) {
       if (POLICY == SN_POLICY_ACTIONS) load_actions<IDENT>(actions + (int64_t)(s + 1) * act_stride, envc, sp, a_pre);
-      d_pre = __ldg(demand + (int64_t)(t + 2) * ld + envc);
+      d_pre = Ops::load_demand(demand + (int64_t)(t + 2) * dstride, ld, envc, sp);
     }
     if (POLICY == SN_POLICY_BASE_STOCK) {
       // BaseStockPolicy.get_order_quantity on this env's own observation (utils/heuristics.py:43-57)
@@ -484,8 +533,10 @@ int fail(int code, const char* fmt, ...) {
 bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && std::fabs(x) < 2147483647.0; }
 
 // the beer game's lead times (envs.py:355-392): tuned kernels; anything else takes the generic path
+bool is_tree(const sn_spec* s) { return s->topology == SN_TOPO_TREE; }
+
 bool is_standard(const sn_spec* s) {
-  if (s->n_facilities != 4) return false;
+  if (s->n_facilities != 4 || is_tree(s)) return false;
   const int li[4] = {2, 2, 2, 1};
   for (int k = 0; k < 4; ++k)
     if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2) return false;
@@ -506,7 +557,7 @@ int validate(const sn_spec* s, int dtype) {
                                       "slots (network_components.py:168) and fails its own on_order assertion beyond that", k, li, ls);
   }
   if (!is_standard(s) && s->n_items > 1)
-    return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported with the beer game's lead times only");
+    return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported for the beer game's chain and lead times only");
   if (s->n_agents < 1 || s->n_agents > s->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
   int seen = 0, lo = 4, hi = -1;
   for (int i = 0; i < s->n_agents; ++i) {
@@ -517,7 +568,40 @@ int validate(const sn_spec* s, int dtype) {
     lo = k < lo ? k : lo;
     hi = k > hi ? k : hi;
   }
-  if (hi - lo + 1 != s->n_agents)
+  if (s->topology != SN_TOPO_CHAIN && s->topology != SN_TOPO_TREE) return fail(SN_ERR_INVALID, "unknown topology %d", s->topology);
+  if (is_tree(s)) {
+    const int nf = s->n_facilities;
+    int pos_seen = 0, n_src = 0, plo = 4, phi = -1;
+    for (int k = 0; k < nf; ++k) {
+      const int sup = s->supplier[k], op = s->order_pos[k];
+      if (sup != SN_EXTERNAL && (sup < 0 || sup >= nf || sup == k)) return fail(SN_ERR_INVALID, "supplier[%d]=%d out of range", k, sup);
+      if (op < 0 || op >= nf || (pos_seen & (1 << op))) return fail(SN_ERR_INVALID, "order_pos must be a permutation of 0..%d", nf - 1);
+      pos_seen |= 1 << op;
+      n_src += s->demand_source[k] ? 1 : 0;
+    }
+    for (int k = 0; k < nf; ++k) {
+      const int sup = s->supplier[k];
+      if (sup >= 0 && s->order_pos[sup] <= s->order_pos[k])
+        return fail(SN_ERR_INVALID, "node %d must order before its supplier %d (utils/graph.py:5-32)", k, sup);
+      int same = 0, lower = 0;                 // ranks among the customers of one supplier: 0..m-1, distinct
+      for (int c = 0; c < nf; ++c)
+        if (s->supplier[c] == sup) {
+          ++same;
+          if (c != k && s->customer_rank[c] == s->customer_rank[k]) return fail(SN_ERR_INVALID, "customer_rank of nodes %d and %d collide", k, c);
+          lower += s->customer_rank[c] < s->customer_rank[k] ? 1 : 0;
+        }
+      if (s->customer_rank[k] != lower || s->customer_rank[k] >= same) return fail(SN_ERR_INVALID, "customer_rank[%d]=%d is not a rank among its supplier's customers", k, s->customer_rank[k]);
+    }
+    if (n_src < 1) return fail(SN_ERR_INVALID, "a tree needs at least one demand source");
+    for (int i = 0; i < s->n_agents; ++i) {
+      const int op = s->order_pos[s->agents[i]];
+      plo = op < plo ? op : plo;
+      phi = op > phi ? op : phi;
+    }
+    if (phi - plo + 1 != s->n_agents)
+      return fail(SN_ERR_INVALID, "agent-managed facilities must be contiguous in the order sequence "
+                                  "(the reference crashes otherwise, supplynetwork.py:199)");
+  } else if (hi - lo + 1 != s->n_agents)
     return fail(SN_ERR_INVALID, "agent-managed facilities must be a contiguous block of the chain "
                                 "(the reference crashes otherwise, supplynetwork.py:199)");
   if (s->max_episode_steps < 1) return fail(SN_ERR_INVALID, "max_episode_steps=%d", s->max_episode_steps);
@@ -581,6 +665,31 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   d.lo = lo;
   d.rule = s->rule;
   d.t_max = s->max_episode_steps;
+  // topology tables (supplynet_tree.cuh); a chain is the tree k -> k+1 with the retailer as the only source
+  const bool tree = is_tree(s);
+  int first_agent_pos = 4;
+  for (int i = 0; i < s->n_agents; ++i) {
+    const int op = tree ? s->order_pos[s->agents[i]] : s->agents[i];
+    first_agent_pos = op < first_agent_pos ? op : first_agent_pos;
+  }
+  d.n_src = 0;
+  d.max_rank = 0;
+  for (int k = 0; k < 4; ++k) {
+    const bool real = k < nf;
+    d.sup[k] = !real ? -1 : tree ? s->supplier[k] : (k + 1 < nf ? k + 1 : -1);
+    d.rank[k] = (real && tree && d.sup[k] >= 0) ? s->customer_rank[k] : 0;   // the external supplier serves all at once
+    if (d.rank[k] > d.max_rank) d.max_rank = d.rank[k];
+    const bool source = real && (tree ? s->demand_source[k] != 0 : k == 0);
+    d.src[k] = source ? d.n_src++ : -1;
+    d.pre[k] = real && (tree ? s->order_pos[k] : k) < first_agent_pos ? 1 : 0;
+    d.lat_src[k] = -1;
+  }
+  for (int j = 0; j < nf; ++j) {          // the customer latest in the order sequence provides latest_demand
+    int best = -1;
+    for (int c = 0; c < nf; ++c)
+      if (d.sup[c] == j && (best < 0 || (tree ? s->order_pos[c] > s->order_pos[best] : c > best))) best = c;
+    d.lat_src[j] = best;
+  }
   return d;
 }
 
@@ -631,7 +740,8 @@ inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)(
 // or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
 #define SN_DISPATCH_TOPO(spec, CALL)                                   \
   do {                                                                 \
-    if (!is_standard(spec)) { CALL(false, sn::GenOps<T>); }            \
+    if (is_tree(spec)) { CALL(false, sn::TreeOps<T>); }                \
+    else if (!is_standard(spec)) { CALL(false, sn::GenOps<T>); }       \
     else if (is_identity(spec)) { CALL(true, sn::StdOps<T>); }         \
     else { CALL(false, sn::StdOps<T>); }                               \
   } while (0)
@@ -686,7 +796,8 @@ void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::
                         int period0, int n_steps, void* state, const void* demand, const void* actions,
                         const sn::RolloutPtrs& out, int tma, cudaStream_t st, const void* init, float* obs0) {
 #define SN_ARGS d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0
-  if (!is_standard(spec)) launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
+  if (is_tree(spec)) launch_rollout<T, POLICY, false, false, sn::TreeOps<T>>(SN_ARGS);
+  else if (!is_standard(spec)) launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
   else if (is_identity(spec)) {
     if (d.n_items > 1) launch_rollout<T, POLICY, true, true, sn::StdOps<T>>(SN_ARGS);
     else launch_rollout<T, POLICY, true, false, sn::StdOps<T>>(SN_ARGS);
@@ -733,7 +844,7 @@ int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype) { return validate(s
 
 int32_t sn_state_words(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
-  return is_standard(spec) ? SN_STATE_WORDS : SN_GEN_STATE_WORDS;
+  return is_tree(spec) ? SN_TREE_STATE_WORDS : is_standard(spec) ? SN_STATE_WORDS : SN_GEN_STATE_WORDS;
 }
 
 int32_t sn_init_words(const sn_spec* spec) {

@@ -74,7 +74,10 @@ class BatchedSupplyNetwork:
         self.init_words = self.lib.sn_init_words(C.byref(self._c_spec))        # 19 or 36
         self.state = torch.zeros((self.state_words, ld), dtype=self.tdtype, device=dev)
         self.init = torch.zeros((self.init_words, ld), dtype=self.tdtype, device=dev)
-        self.demand = torch.zeros((self.T + 3, ld), dtype=self.tdtype, device=dev)
+        # chains: demand[t] is the [ld] row of period t; trees: [n_sources][ld] rows per period (sources in node order)
+        self.n_sources = spec.n_sources
+        self.demand = torch.zeros((self.T + 3, self.n_sources, ld) if spec.is_tree else (self.T + 3, ld),
+                                  dtype=self.tdtype, device=dev)
         self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
         self.reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self.ep_return = torch.zeros((n,), dtype=torch.float64, device=dev)
@@ -105,6 +108,16 @@ class BatchedSupplyNetwork:
         """init [n, init_words] (19: inv[4]; so[k][j]; sh[k][j] packed for the beer game's lead times; 36:
         inv[4]; so[k][0..3]; sh[k][0..3] for other lead times), demand [n, >=T+1] (utils/demands.py streams)."""
         d = torch.as_tensor(demand)
+        if self.spec.is_tree:
+            """trees: demand [n, n_sources, >=T+1], one stream per demand source (node order)"""
+            if d.dim() != 3 or d.shape[1] != self.n_sources or d.shape[2] < self.T + 1:
+                raise ValueError(f"demand must be [n_envs, {self.n_sources}, >= {self.T + 1}]")
+            width = min(d.shape[2], self.T + 3)
+            self.init.copy_(self._to_rows(init, self.init_words))
+            self.demand.zero_()
+            for s in range(self.n_sources):
+                self.demand[:width, s].copy_(self._to_rows(d[:, s, :width], width))
+            return
         if d.dim() != 2 or d.shape[1] < self.T + 1:
             raise ValueError(f"demand must be [n_envs, >= {self.T + 1}]")
         width = min(d.shape[1], self.T + 3)

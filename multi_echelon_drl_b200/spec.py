@@ -68,18 +68,35 @@ class ScenarioSpec:
     # Per-facility tuples (costs, targets, lead times) then have n_facilities entries.  Shorter chains run on the
     # generic kernels with the missing upstream nodes as phantoms (supplynet_core.cuh, DevSpec::nf).
     n_facilities: int = 4
+    # Distribution trees (topology='tree'): every node buys from ONE supplier and may serve several customers and / or
+    # its own external demand - what the reference's SupplyNetwork does for such node / arc lists.  Node k is the k-th
+    # internal node of the node list (observation and cost order); per-node tuples are indexed by it and lead times
+    # belong to the node's upstream arc.  See include/supplynet.h (SN_TOPO_TREE) and csrc/supplynet_tree.cuh.
+    topology: str = "chain"
+    names: Tuple[str, ...] = ()                      # tree: internal node names, node-list order
+    suppliers: Tuple[int, ...] = ()                  # tree: supplier node of node k, -1 = the external supplier
+    demand_sources: Tuple[bool, ...] = ()            # tree: Node.is_demand_source
+    arc_order: Tuple[int, ...] = ()                  # tree: upstream arcs (named by their customer node) in arc-list order
+    source_demand_params: Tuple[Tuple[float, float], ...] = ()   # tree: per demand source (node order); default demand_params
+    external_name: str = "external_supplier"
 
     def __post_init__(self):
         nf = int(self.n_facilities)
         if not 1 <= nf <= 4:
             raise ValueError("n_facilities must be 1..4")
-        ag = tuple(node_index(a) for a in self.agents)
+        if self.topology not in ("chain", "tree"):
+            raise ValueError(f"topology must be 'chain' or 'tree', got {self.topology!r}")
+        if self.topology == "tree":
+            self._init_tree(nf)
+        ag = tuple(self.node_index(a) for a in self.agents)
         object.__setattr__(self, "agents", ag)
         if not 1 <= len(ag) <= nf or len(set(ag)) != len(ag) or max(ag) >= nf:
-            raise ValueError(f"agent_managed_facilities {self.agents} must name 1..{nf} distinct facilities of the chain")
-        if max(ag) - min(ag) + 1 != len(ag):
+            raise ValueError(f"agent_managed_facilities {self.agents} must name 1..{nf} distinct facilities of the network")
+        pos = sorted(self.order_pos[a] for a in ag)
+        if pos[-1] - pos[0] + 1 != len(ag):
             # the reference never lets the in-between node order and crashes at supplynetwork.py:199
-            raise ValueError("agent-managed facilities must form a contiguous block of the chain")
+            raise ValueError("agent-managed facilities must form a contiguous block of the chain "
+                             "(of the order sequence, for trees)")
         if self.rule not in ("a", "d+a"):
             raise ValueError(f"ordering rule must be 'a' or 'd+a', got {self.rule!r}")
         object.__setattr__(self, "info_leadtime", tuple(int(x) for x in self.info_leadtime))
@@ -88,15 +105,80 @@ class ScenarioSpec:
             if len(getattr(self, name)) < nf:
                 raise ValueError(f"{name} needs one entry per facility ({nf})")
 
+    def _init_tree(self, nf):
+        from .utils.graph import parse_order_sequence
+        names = tuple(self.names)
+        sup = tuple(int(x) for x in self.suppliers)
+        if len(names) != nf or len(set(names)) != nf or len(sup) != nf or self.external_name in names:
+            raise ValueError(f"a tree of {nf} facilities needs {nf} distinct names and one supplier index per node")
+        if any(not (-1 <= x < nf) or x == k for k, x in enumerate(sup)):
+            raise ValueError("suppliers[k] must be another node's index or -1 (the external supplier)")
+        arcs = tuple(int(x) for x in self.arc_order) if len(self.arc_order) else tuple(range(nf))
+        if sorted(arcs) != list(range(nf)):
+            raise ValueError("arc_order must list every node's upstream arc once")
+        src = tuple(bool(x) for x in self.demand_sources)
+        if len(src) != nf or not any(src):
+            raise ValueError("demand_sources needs one flag per node and at least one demand source")
+        customers = {names[k]: [names[c] for c in arcs if sup[c] == k] for k in range(nf)}
+        customers[self.external_name] = [names[c] for c in arcs if sup[c] < 0]
+        seq = parse_order_sequence(list(names) + [self.external_name], customers)      # utils/graph.py:5-32
+        internal = [n for n in seq if n != self.external_name]
+        order_pos = tuple(internal.index(n) for n in names)
+        if any(sup[k] >= 0 and order_pos[sup[k]] <= order_pos[k] for k in range(nf)):
+            raise ValueError("the supplier relation has a cycle")
+        rank = tuple([c for c in arcs if sup[c] == sup[k]].index(k) for k in range(nf))
+        n_src = sum(src)
+        sdp = tuple(tuple(p) for p in self.source_demand_params) or (tuple(self.demand_params),) * n_src
+        if len(sdp) != n_src:
+            raise ValueError("source_demand_params needs one (a, b) per demand source")
+        for k, v in (("names", names), ("suppliers", sup), ("arc_order", arcs), ("demand_sources", src),
+                     ("source_demand_params", sdp), ("_order_pos", order_pos), ("_customer_rank", rank)):
+            object.__setattr__(self, k, v)
+
     # ------------------------------------------------------------------ derived
+    def node_index(self, name_or_index) -> int:
+        if self.topology == "tree" and isinstance(name_or_index, str):
+            if name_or_index not in self.names:
+                raise ValueError(f"unknown facility {name_or_index!r}; expected one of {self.names}")
+            return self.names.index(name_or_index)
+        return node_index(name_or_index)
+
+    @property
+    def is_tree(self) -> bool:
+        return self.topology == "tree"
+
+    @property
+    def order_pos(self) -> Tuple[int, ...]:
+        """Position of node k among the internal nodes in the order sequence (chains: k itself)."""
+        return self._order_pos if self.is_tree else tuple(range(self.n_facilities))
+
+    @property
+    def order_sequence(self) -> Tuple[str, ...]:
+        pos = self.order_pos
+        return tuple(self.node_names[pos.index(i)] for i in range(self.n_facilities))
+
+    @property
+    def customer_rank(self) -> Tuple[int, ...]:
+        return self._customer_rank if self.is_tree else (0,) * self.n_facilities
+
+    @property
+    def source_nodes(self) -> Tuple[int, ...]:
+        """Nodes with an external demand stream, in node order (= row order of the demand tables)."""
+        return tuple(k for k in range(self.n_facilities) if self.demand_sources[k]) if self.is_tree else (0,)
+
+    @property
+    def n_sources(self) -> int:
+        return len(self.source_nodes)
+
     @property
     def standard_leadtimes(self) -> bool:
         """True for the beer game itself (4 facilities, lead times 2,2,2,1 / 2,2,2,2): tuned kernels, packed tables."""
-        return self.n_facilities == 4 and self.info_leadtime == INFO_LEADTIME and self.ship_leadtime == SHIP_LEADTIME
+        return (not self.is_tree and self.n_facilities == 4 and self.info_leadtime == INFO_LEADTIME
+                and self.ship_leadtime == SHIP_LEADTIME)
 
     @property
     def node_names(self) -> Tuple[str, ...]:
-        return NODE_NAMES[: self.n_facilities]
+        return tuple(self.names) if self.is_tree else NODE_NAMES[: self.n_facilities]
 
     @property
     def n_items(self) -> int:
@@ -137,6 +219,13 @@ class ScenarioSpec:
         if len(self.extra_item_costs) > 3:
             raise ValueError("at most 4 items")
         s.n_items = self.n_items
+        if self.is_tree:
+            s.topology = _lib.SN_TOPO_TREE
+            for k in range(self.n_facilities):
+                s.supplier[k] = self.suppliers[k]
+                s.demand_source[k] = int(self.demand_sources[k])
+                s.order_pos[k] = self.order_pos[k]
+                s.customer_rank[k] = self.customer_rank[k]
         for i, (h, b) in enumerate(self.extra_item_costs):
             for k in range(self.n_facilities):
                 s.item_holding_cost[i][k] = float(h[k])
@@ -182,6 +271,45 @@ def classic_spec(agent_managed_facilities=None, max_episode_steps=35, demand_pat
         max_episode_steps=max_episode_steps, action_low=0, action_high=16, demand_pattern=demand_pattern,
         demand_params=params, random_init=False, fixed_inventory=12, fixed_shipments=(4, 4),
         fixed_sales_orders=(4, 4))
+
+
+def tree_spec(nodes, arcs, agent_managed_facilities, global_observable=False, max_episode_steps=100, random_init=True,
+              demand_pattern="uniform", name="tree", **overrides) -> ScenarioSpec:
+    """Distribution-tree scenario from node / arc lists shaped like the reference's constructors take them
+    (SupplyNetwork(nodes=[Node...], arcs=[Arc...]), envs.py:289-414):
+      nodes  list of dict(name, holding_cost, backorder_cost, target [co-player base-stock level],
+             demand=None | (a, b) [external demand stream: uniform low/high or normal mean/sd]) - internal nodes in
+             node-list order;
+      arcs   list of (supplier_name, customer_name, info_leadtime, shipment_leadtime) in arc-list order; a supplier
+             name that is not a node is the external supplier.
+    Up to four internal nodes, one supplier per node."""
+    names = tuple(n["name"] for n in nodes)
+    nf = len(names)
+    if not 1 <= nf <= 4:
+        raise NotImplementedError("kernels hold up to four internal nodes per network")
+    up = {}
+    for (s_name, c_name, li, ls) in arcs:
+        if c_name not in names:
+            raise ValueError(f"arc customer {c_name!r} is not an internal node")
+        if c_name in up:
+            raise NotImplementedError(f"node {c_name!r} has more than one supplier; only distribution trees are supported")
+        up[c_name] = (names.index(s_name) if s_name in names else -1, int(li), int(ls))
+    if set(up) != set(names):
+        raise ValueError("every internal node needs exactly one upstream arc")
+    ext = [s_name for (s_name, _, _, _) in arcs if s_name not in names]
+    u = uniform_spec(None, global_observable, max_episode_steps, random_init)
+    src = tuple(n.get("demand") is not None for n in nodes)
+    spec = replace(
+        u, name=name, topology="tree", n_facilities=nf, names=names, suppliers=tuple(up[n][0] for n in names),
+        info_leadtime=tuple(up[n][1] for n in names), ship_leadtime=tuple(up[n][2] for n in names),
+        arc_order=tuple(names.index(c) for (_, c, _, _) in arcs), demand_sources=src, demand_pattern=demand_pattern,
+        source_demand_params=tuple(tuple(n["demand"]) for n in nodes if n.get("demand") is not None),
+        holding_cost=tuple(float(n.get("holding_cost", 0.5)) for n in nodes),
+        backorder_cost=tuple(float(n.get("backorder_cost", 1.0)) for n in nodes),
+        coplayer_target=tuple(float(n.get("target", 20)) for n in nodes),
+        external_name=ext[0] if ext else "external_supplier",
+        agents=tuple(agent_managed_facilities if agent_managed_facilities is not None else range(nf)), **overrides)
+    return spec
 
 
 def specs_from_config(network_config: dict, agent_managed_facilities=None, global_observable=False,

@@ -77,7 +77,12 @@ class Demand:
 _SAMPLE_DEMANDS = {}
 
 
-def demand_for(spec: ScenarioSpec) -> Demand:
+def demand_for(spec: ScenarioSpec, source: int = 0) -> Demand:
+    """Demand object of the `source`-th demand source (trees may give every source its own parameters)."""
+    if spec.is_tree and spec.demand_pattern in ("uniform", "normal"):
+        a, b = spec.source_demand_params[source]
+        return (Demand("uniform", low=int(a), high=int(b), size=spec.max_episode_steps) if spec.demand_pattern == "uniform"
+                else Demand("normal", mean=a, sd=b, size=spec.max_episode_steps))
     if spec.demand_pattern == "samples":       # one object per file: its row pointer advances across resets
         key = spec.demand_path
         if key not in _SAMPLE_DEMANDS:
@@ -122,7 +127,8 @@ def seeded_episode_inputs(spec: ScenarioSpec, seeds):
 
 
 def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
-    """Same distributions, vectorised draws from one stream `rs` (RandomState)."""
+    """Same distributions, vectorised draws from one stream `rs` (RandomState).  Trees: demand is
+    [n, n_sources, T+3], one stream per demand source in node order."""
     dem = demand_for(spec)
     n_words, so_off, sh_off = init_layout(spec)
     if spec.random_init:
@@ -139,6 +145,8 @@ def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
         init[:, 4:] = pipe
     else:
         init = np.broadcast_to(_fixed_init(spec), (n, n_words)).copy()
+    if spec.is_tree:
+        return init, np.stack([demand_for(spec, s).sample(n, rs) for s in range(spec.n_sources)], axis=1)
     return init, dem.sample(n, rs)
 
 
@@ -149,8 +157,29 @@ def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
     dem = demand_for(spec)
     n_words, so_off, sh_off = init_layout(spec)
     init = np.zeros((n, n_words), dtype=np.int64)
-    demand = np.zeros((n, dem.size), dtype=np.int64)
     fixed = _fixed_init(spec)
+    if spec.is_tree:
+        # SupplyNetwork.reset (supplynetwork.py:94-105): nodes in node-list order (inventory, then the demand
+        # episode of a demand source), then arcs in arc-list order (shipments, then sales orders)
+        dems = [demand_for(spec, s) for s in range(spec.n_sources)]
+        demand = np.zeros((n, spec.n_sources, dem.size), dtype=np.int64)
+        for i, rs in enumerate(streams):
+            if not spec.random_init:
+                init[i] = fixed
+            for k in range(spec.n_facilities):
+                if spec.random_init:
+                    init[i, k] = rs.randint(*spec.init_inventory)
+                if spec.demand_sources[k]:
+                    s = spec.source_nodes.index(k)
+                    demand[i, s] = dems[s].draw(rs)
+            if spec.random_init:
+                for k in spec.arc_order:
+                    for j in range(spec.ship_leadtime[k]):
+                        init[i, sh_off[k] + j] = rs.randint(*spec.init_pipeline)
+                    for j in range(spec.info_leadtime[k]):
+                        init[i, so_off[k] + j] = rs.randint(*spec.init_pipeline)
+        return init, demand
+    demand = np.zeros((n, dem.size), dtype=np.int64)
     for i, rs in enumerate(streams):
         if not spec.random_init:
             init[i] = fixed

@@ -154,7 +154,17 @@ class SupplyNetVecEnv(_VecEnvBase):
             self._ctr += (t.numel() + 3) // 4
 
         # one launch per table, written in place in the structure-of-arrays layout (sn_fill_* in random_fill.cu)
-        if sp.demand_pattern == "uniform":
+        if sp.is_tree and len(set(sp.source_demand_params)) > 1:
+            # demand sources with their own parameters: one strided [T+3][ld] slice of the table per source
+            for s, (pa, pb) in enumerate(sp.source_demand_params):
+                if sp.demand_pattern == "uniform":
+                    sim.demand[:, s].random_(int(pa), int(pb) + 1)
+                elif sp.demand_pattern == "normal":
+                    t = torch.randn(sim.demand[:, s].shape, device=self.device) * float(pb) + float(pa)
+                    sim.demand[:, s].copy_(t.clamp_(min=0).round_())
+                else:
+                    raise NotImplementedError("tree networks draw uniform or normal demand")
+        elif sp.demand_pattern == "uniform":
             fill_uniform(sim.demand, a, int(b) + 1)
         elif sp.demand_pattern == "normal":
             _lib.check(lib.sn_fill_normal_demand(dt, C.c_void_p(sim.demand.data_ptr()), sim.demand.numel(), float(a),

@@ -1,0 +1,158 @@
+"""Distribution trees on the CUDA path (SN_TOPO_TREE, supplynet_tree.cuh) vs trajectories recorded from the
+reference's own classes (tests/golden/trees.npz), vs the tree oracle on batches, and vs the chain kernels on
+networks that are chains.  Integer quantities: bit-exact; float quantities: 1e-6 relative."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from test_oracle_trees import TREE_CASES, tree_oracle_rollout, tree_product_spec  # noqa: E402
+
+
+def _sim(case, n, dtype="int32"):
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    return BatchedSupplyNetwork(tree_product_spec(case), n, "cuda", dtype)
+
+
+@pytest.mark.parametrize("case", TREE_CASES, ids=[c["id"] for c in TREE_CASES])
+def test_tree_step_and_rollout_match_reference_golden(case):
+    sim = _sim(case, 1)
+    assert sim.state_words == 64 and sim.obs_dim == case["obs0"].shape[0]
+    sim.load_episode(case["init"][None], case["demand_table"][None])
+    assert np.array_equal(sim.reset().cpu().numpy()[0], case["obs0"])
+    r64 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    cost = torch.zeros((8, sim.ld), dtype=torch.float64, device="cuda")
+    N = len(case["names"])
+    for t in range(100):
+        obs, _, done = sim.step(torch.as_tensor(case["actions"][t][None]), reward64_out=r64, cost_out=cost)
+        assert np.array_equal(obs.cpu().numpy()[0], case["obs"][t]), t
+        assert r64.item() == case["rew"][t], t
+        c = cost[:, 0].cpu().numpy()
+        assert np.array_equal(c[:N], case["ref_holding"][t]) and np.array_equal(c[4:4 + N], case["ref_backorder"][t]), t
+    assert done
+    out = sim.episode(100, actions=torch.as_tensor(case["actions"][:, None, :]), record_obs=True, record_reward=True)
+    assert np.array_equal(out["traj_obs"].cpu().numpy()[:, 0], case["obs"])
+    assert sim.ep_return.item() == case["rew"].sum()
+
+
+@pytest.mark.parametrize("cid,dtype", [(3, "int32"), (20, "int32"), (37, "int32"), (55, "int32"), (70, "int32"), (88, "int32"),
+                                       (37, "float32"), (55, "float64")])
+def test_tree_batch_vs_oracle(cid, dtype):
+    """3,001 envs (ragged) x 100 with bulk-drawn initial states and per-source demand streams: step kernel, fused
+    rollout, rollout resumed mid-episode, in-kernel base-stock policy."""
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    case = TREE_CASES[cid]
+    n = 3001
+    sim = _sim(case, n, dtype)
+    init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(cid))
+    rs = np.random.RandomState(cid + 1)
+    acts = rs.randint(-1, 19, (100, n, len(case["agents"])))
+    if dtype != "int32":
+        acts = acts + rs.rand(*acts.shape).round(3)
+    import oracle.network_np as NP
+    spec = None
+    if dtype == "int32":
+        obs0, obs, rew = tree_oracle_rollout(case, init, demand, acts)
+    else:
+        from test_oracle_trees import oracle_spec
+        orc = NP.TreeOracle(oracle_spec(case), n, dtype=np.float64)
+        N = len(case["names"])
+        obs0 = orc.reset(init[:, :N].astype(np.float64), [init[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]].astype(np.float64) for k in range(N)],
+                         [init[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]].astype(np.float64) for k in range(N)], demand)
+        obs, rew = [], []
+        for t in range(100):
+            o, r, _ = orc.step(acts[t]); obs.append(o); rew.append(r)
+        obs, rew = np.stack(obs), np.stack(rew)
+    sim.load_episode(init, demand)
+    close = (lambda a, b: np.array_equal(a, b)) if dtype == "int32" else \
+        (lambda a, b: np.allclose(a, b, rtol=1e-6 if dtype == "float64" else 2e-5, atol=1e-6 if dtype == "float64" else 2e-3))
+    assert close(sim.reset().cpu().numpy(), obs0)
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(100):
+        o, _, _ = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
+        assert close(o.cpu().numpy(), obs[t]), t
+        assert close(r64.cpu().numpy(), rew[t]), t
+    stepped_return = sim.ep_return.clone()
+    out = sim.episode(100, actions=torch.as_tensor(acts), record_obs=True)
+    assert close(out["traj_obs"].cpu().numpy(), obs)
+    assert close(sim.ep_return.cpu().numpy(), rew.sum(0))
+    if dtype == "int32":
+        assert torch.equal(sim.ep_return, stepped_return)
+        # resume: 37 periods stepped, the rest as one rollout launch
+        sim.reset()
+        for t in range(37):
+            sim.step(torch.as_tensor(acts[t]))
+        out = sim.rollout(63, actions=torch.as_tensor(acts[37:]), record_obs=True)
+        assert np.array_equal(out["traj_obs"].cpu().numpy(), obs[37:]) and torch.equal(sim.ep_return, stepped_return)
+        # in-kernel base-stock policy == heuristic kernel + step kernel
+        if case["glob"] and len(case["agents"]) == len(case["names"]) and list(case["agents"]) == sorted(case["agents"]):
+            pol = BasePolicyParams(case["target"], 0, 16, "a")
+            sim.episode(100, policy=pol, write_state=False)
+            fused = sim.ep_return.clone()
+            o = sim.reset()
+            for t in range(100):
+                o, _, _ = sim.step(heuristic_actions(pol, o))
+            assert torch.equal(fused, sim.ep_return)
+
+
+@pytest.mark.parametrize("li,ls,agents,glob,rule", [((2, 2, 2, 1), (2, 2, 2, 2), (0, 1, 2, 3), True, "a"),
+                                                    ((3, 1, 2, 2), (2, 4, 3, 1), (2, 1), False, "d+a"),
+                                                    ((1, 2, 2), (2, 2, 3), (1,), True, "a")])
+def test_chain_through_tree_kernels_equals_chain_kernels(li, ls, agents, glob, rule):
+    """A serial chain described as a tree runs on the tree kernels and gives what the chain kernels give."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    nf, n = len(li), 2049
+    names = ["retailer", "wholesaler", "distributor", "manufacturer"][:nf]
+    u = uniform_spec(None, glob, 100)
+    chain = replace(u, n_facilities=nf, agents=agents, info_leadtime=li, ship_leadtime=ls, holding_cost=u.holding_cost[:nf],
+                    backorder_cost=u.backorder_cost[:nf], coplayer_target=u.coplayer_target[:nf])
+    nodes = [dict(name=names[k], holding_cost=0.5, backorder_cost=1.0, target=u.coplayer_target[k], demand=(0, 8) if k == 0 else None)
+             for k in range(nf)]
+    arcs = [(names[k + 1] if k + 1 < nf else "external_supplier", names[k], li[k], ls[k]) for k in range(nf - 1, -1, -1)]
+    tree = tree_spec(nodes, arcs, [names[a] for a in agents], glob)
+    if rule == "d+a":
+        chain, tree = chain.with_rule("d+a", -8, 0, 16), tree.with_rule("d+a", -8, 0, 16)
+    a, b = BatchedSupplyNetwork(chain, n), BatchedSupplyNetwork(tree, n)
+    assert b.state_words == 64
+    init, dem = bulk_episode_inputs(tree, n, np.random.RandomState(4))
+    init_chain = init
+    if a.init_words == 19:
+        cols = list(range(4)) + [4 + 4 * k + j for k in range(4) for j in range(li[k])] + [20 + 4 * k + j for k in range(4) for j in range(ls[k])]
+        init_chain = init[:, cols]
+    a.load_episode(init_chain, dem[:, 0]); b.load_episode(init, dem)
+    acts = torch.as_tensor(np.random.RandomState(5).randint(-1, 19, (100, n, len(agents))))
+    oa = a.episode(100, actions=acts, record_obs=True, record_reward=True)
+    ob = b.episode(100, actions=acts, record_obs=True, record_reward=True)
+    assert torch.equal(oa["traj_obs"], ob["traj_obs"]) and torch.equal(oa["traj_reward"], ob["traj_reward"])
+    assert torch.equal(a.ep_return, b.ep_return)
+
+
+def test_vecenv_on_a_tree_and_statistics():
+    """SupplyNetVecEnv on a two-level tree with two demand sources: device-drawn episodes, auto-reset, on-order
+    invariant, policy episodes; per-source demand ranges are honoured."""
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    case = TREE_CASES[[c["topo"] for c in TREE_CASES].index("two_level")]
+    assert case["glob"] is False
+    spec = tree_product_spec(dict(case, agents=[0, 1, 2, 3], glob=True, rule="a"))
+    env = SupplyNetVecEnv(spec, 1000, seed=2, dtype="int32")
+    obs = env.reset()
+    assert obs.shape == (1000, 28) and env.action_space.shape == (4,)
+    dem = env.sim.demand[:, :, :1000]
+    assert dem.shape[:2] == (103, 2) and int(dem[:, 0].max()) == 8 and int(dem[:, 1].max()) == 5 and int(dem.min()) == 0
+    s = env.sim.state[:, :1000].to(torch.int64)
+    for k in range(4):                                   # on_order == sum(pipeline) on every arc
+        on_order = s[7 * k + 3:7 * k + 7].sum(0)
+        pipe = s[28 + 3 * k:31 + 3 * k].sum(0) + s[40 + 4 * k:44 + 4 * k].sum(0) + s[56 + k]
+        assert torch.equal(on_order, pipe)
+    for _ in range(230):
+        obs, rew, dones, infos = env.step(torch.full((1000, 4), 5, device="cuda"))
+    assert torch.isfinite(obs).all() and env.episodes_done == 2000
+    stats = env.run_policy_episodes(BasePolicyParams(case["target"], 0, 16, "a"), n_episodes=3).cpu().numpy()
+    assert stats[0] == 3000 * 100 and stats[10] == 3000 and stats[11] < 0 and stats[11] == stats[1]

@@ -128,3 +128,74 @@ def test_tree_oracle_vs_live_reference():
             init[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
         o0, obs, rew = tree_oracle_rollout(c, init[None], np.asarray(dem)[None], acts[:, None, :])
         assert np.array_equal(o0[0], r["obs0"]) and np.array_equal(obs[:, 0], r["obs"]) and np.array_equal(rew[:, 0], r["rew"])
+
+
+# ---------------------------------------------------------------------- host side of the product on trees
+def tree_product_spec(case, t_max=100):
+    """Product ScenarioSpec of a tree golden case (multi_echelon_drl_b200.spec.tree_spec)."""
+    from multi_echelon_drl_b200.spec import tree_spec
+    names = case["names"]
+    nodes = [dict(name=names[k], holding_cost=case["holding"][k], backorder_cost=case["backorder"][k], target=case["target"][k],
+                  demand=tuple(case["demand"][k]) if case["demand"][k] else None) for k in range(len(names))]
+    arcs = [("external_supplier" if case["supplier"][k] < 0 else names[case["supplier"][k]], names[k], case["li"][k], case["ls"][k])
+            for k in case["arc_order"]]
+    sp = tree_spec(nodes, arcs, [names[a] for a in case["agents"]], case["glob"], t_max)
+    return sp.with_rule("d+a", -8, 0, 16) if case["rule"] == "d+a" else sp
+
+
+def test_product_tree_specs_order_sequence_streams_and_c_validation():
+    """The host side agrees with the reference on every golden tree: order sequence (utils/graph.py:5-32), the RNG
+    draw order of SupplyNetwork.reset (initial state and demand streams from one seed), and the C library accepts
+    the lowered spec with the right buffer sizes."""
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs, seeded_episode_inputs
+    lib = _lib.load()
+    for c in TREE_CASES:
+        sp = tree_product_spec(c)
+        assert list(sp.order_sequence) == c["order_sequence"], c["id"]
+        init, dem = seeded_episode_inputs(sp, [c["seed"]])
+        assert np.array_equal(init[0], c["init"]) and np.array_equal(dem[0], c["demand_table"]), c["id"]
+        cs = sp.to_c()
+        assert lib.sn_spec_validate(C.byref(cs), _lib.SN_I32) == 0, lib.sn_last_error()
+        assert lib.sn_state_words(C.byref(cs)) == 64 and lib.sn_init_words(C.byref(cs)) == 36
+        assert lib.sn_obs_dim(C.byref(cs)) == c["obs0"].shape[0] == sp.obs_dim
+        binit, bdem = bulk_episode_inputs(sp, 16, np.random.RandomState(0))
+        assert binit.shape == (16, 36) and bdem.shape == (16, sp.n_sources, 103)
+        for s, k in enumerate(sp.source_nodes):
+            assert bdem[:, s].max() <= c["demand"][k][1]
+
+
+def test_tree_spec_and_c_validation_errors():
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    from multi_echelon_drl_b200.spec import tree_spec
+    lib = _lib.load()
+    nodes = [dict(name="shop", demand=(0, 8)), dict(name="dist_a"), dict(name="dist_b", demand=(0, 5)), dict(name="maker")]
+    arcs = [("ext", "maker", 1, 2), ("maker", "dist_b", 1, 2), ("maker", "dist_a", 2, 2), ("dist_a", "shop", 2, 2)]
+    sp = tree_spec(nodes, arcs, ["dist_a", "dist_b"])
+    assert sp.order_sequence == ("shop", "dist_a", "dist_b", "maker") and sp.customer_rank == (0, 1, 0, 0)
+    assert sp.n_sources == 2 and sp.source_nodes == (0, 2) and sp.external_name == "ext"
+    with pytest.raises(ValueError):                     # shop, [dist_a], dist_b: not contiguous in the order sequence
+        tree_spec(nodes, arcs, ["shop", "dist_b"])
+    with pytest.raises(NotImplementedError):            # two suppliers for one node
+        tree_spec(nodes, arcs + [("dist_b", "shop", 1, 1)], ["shop"])
+    with pytest.raises(ValueError):                     # a node without an upstream arc
+        tree_spec(nodes, arcs[:3], ["maker"])
+    with pytest.raises(ValueError):                     # no demand source
+        tree_spec([dict(name="a"), dict(name="b")], [("ext", "b", 1, 1), ("b", "a", 1, 1)], ["a"])
+    with pytest.raises(ValueError):                     # cycle
+        tree_spec([dict(name="a", demand=(0, 4)), dict(name="b")], [("a", "b", 1, 1), ("b", "a", 1, 1)], ["a"])
+    c = sp.to_c()
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) == 0
+    c.order_pos[1], c.order_pos[3] = c.order_pos[3], c.order_pos[1]          # supplier would order before its customer
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0 and b"order" in lib.sn_last_error()
+    c = sp.to_c()
+    c.customer_rank[1] = 0                                                    # collides with dist_b's rank
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0 and b"rank" in lib.sn_last_error()
+    c = sp.to_c()
+    c.supplier[0] = 0
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0
+    c = sp.to_c()
+    c.n_items = 2
+    assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0
