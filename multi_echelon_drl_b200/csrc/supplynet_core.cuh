@@ -60,6 +60,15 @@ struct DevSpec {
   int src[kF];         // row of node k's demand stream in the demand tables, -1 = not a demand source
   int n_src;
   int pre[kF];         // node k orders inside before_action (its place in the order sequence is ahead of the first agent)
+  // the same tables as exact 0/1 multipliers of the quantity type: the generic / tree step applies a run-time
+  // position as ONE multiply-add with a constant-bank operand (instead of compare + select + multiply)
+  T m_ls[kF][4];       // 1 at slot ls[k]-1: where this period's shipment enters the pipeline
+  T m_li[kF][3];       // 1 at slot li[k]-2: where this period's order slip enters the pipeline
+  T m_li1[kF];         // 1 if li[k] == 1: the slip placed now is the one that arrives now
+  T m_sup[kF][kF];     // [k][j] = 1 if node j supplies node k
+  T m_ext[kF];         // 1 if node k buys from the external supplier
+  T m_rank[kF - 1][kF];// [r][k] = 1 if node k has rank r among its supplier's customers
+  T m_lat[kF][kF];     // [j][k] = 1 if lat_src[j] == k
 };
 
 template <typename T>

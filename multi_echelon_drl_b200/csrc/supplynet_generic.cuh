@@ -137,11 +137,10 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
       e.inv[k + 1] = e.inv[k + 1] - s;
     }
     // advance the shipments and append Shipment(s, shipment_leadtime): slot ls-1 is empty after the shift
-    const int ls = sp.ls[k];
 #pragma unroll
     for (int j = 0; j < kGS; ++j) {
       const T next = (j + 1 < kGS) ? e.ship[k][j + 1] : T(0);
-      e.ship[k][j] = next + s * mask_of<T>(j == ls - 1);
+      e.ship[k][j] = next + s * sp.m_ls[k][j];
     }
     e.B[k] = e.B[k] - s;
     e.U[k][0] = u[0]; e.U[k][1] = u[1]; e.U[k][2] = u[2]; e.U[k][3] = u[3];
@@ -167,14 +166,12 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
   if (!terminal) {
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
-      const int li = sp.li[k];
-      // Order(q, 0, info_leadtime): with lead time 1 this period's order is what arrives now
-      const T head = e.info[k][0];
-      const T arrived = (li == 1) ? q[k] : head;
+      // Order(q, 0, info_leadtime): with lead time 1 this period's order is what arrives now (head is 0 then)
+      const T arrived = e.info[k][0] + q[k] * sp.m_li1[k];
 #pragma unroll
       for (int j = 0; j < kGI; ++j) {
         const T next = (j + 1 < kGI) ? e.info[k][j + 1] : T(0);
-        e.info[k][j] = next + q[k] * mask_of<T>(j == li - 2);
+        e.info[k][j] = next + q[k] * sp.m_li[k][j];
       }
       if (k < 3) e.lat[k + 1] = arrived;
       e.B[k] = e.B[k] + arrived;

@@ -684,12 +684,22 @@ sn::DevSpec<T> lower(const sn_spec* s) {
     d.pre[k] = real && (tree ? s->order_pos[k] : k) < first_agent_pos ? 1 : 0;
     d.lat_src[k] = -1;
   }
+  for (int k = 0; k < 4; ++k) {
+    for (int j = 0; j < 4; ++j) d.m_ls[k][j] = (T)(j == d.ls[k] - 1 ? 1 : 0);
+    for (int j = 0; j < 3; ++j) d.m_li[k][j] = (T)(j == d.li[k] - 2 ? 1 : 0);
+    d.m_li1[k] = (T)(d.li[k] == 1 ? 1 : 0);
+    for (int j = 0; j < 4; ++j) d.m_sup[k][j] = (T)(d.sup[k] == j ? 1 : 0);
+    d.m_ext[k] = (T)(d.sup[k] < 0 ? 1 : 0);
+    for (int r = 0; r < 3; ++r) d.m_rank[r][k] = (T)(d.rank[k] == r ? 1 : 0);
+  }
   for (int j = 0; j < nf; ++j) {          // the customer latest in the order sequence provides latest_demand
     int best = -1;
     for (int c = 0; c < nf; ++c)
       if (d.sup[c] == j && (best < 0 || (tree ? s->order_pos[c] > s->order_pos[best] : c > best))) best = c;
     d.lat_src[j] = best;
   }
+  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 4; ++k) d.m_lat[j][k] = (T)(d.lat_src[j] == k ? 1 : 0);
   return d;
 }
 

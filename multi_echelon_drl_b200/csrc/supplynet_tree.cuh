@@ -40,7 +40,7 @@ template <typename T>
 __device__ __forceinline__ T customers_backlog(const TEnv<T>& e, const DevSpec<T>& sp, int k) {
   T cb = T(0);
 #pragma unroll
-  for (int c = 0; c < kF; ++c) cb = cb + e.B[c] * mask_of<T>(sp.sup[c] == k);
+  for (int c = 0; c < kF; ++c) cb = cb + e.B[c] * sp.m_sup[c][k];
   return cb;
 }
 
@@ -97,7 +97,7 @@ __device__ __forceinline__ void set_latest(TEnv<T>& e, const DevSpec<T>& sp, con
   for (int j = 0; j < kF; ++j) {
     T v = T(0);
 #pragma unroll
-    for (int k = 0; k < kF; ++k) v = v + arrived[k] * mask_of<T>(sp.lat_src[j] == k);
+    for (int k = 0; k < kF; ++k) v = v + arrived[k] * sp.m_lat[j][k];
     e.latI[j] = v;                       // nodes without customers keep sum([]) = 0 (network_components.py:309)
   }
 }
@@ -170,17 +170,15 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
     if (r <= sp.max_rank) {                        // uniform over the grid
 #pragma unroll
       for (int k = 0; k < kF; ++k) {
-        const int s = sp.sup[k];
-        T inv_s = sp.big * mask_of<T>(s < 0);      // external supplier: unlimited
+        T inv_s = sp.big * sp.m_ext[k];            // external supplier: unlimited
 #pragma unroll
-        for (int j = 0; j < kF; ++j) inv_s = inv_s + e.inv[j] * mask_of<T>(s == j);
-        const T amt = tmin(inv_s, e.B[k]) * mask_of<T>(sp.rank[k] == r);
+        for (int j = 0; j < kF; ++j) inv_s = inv_s + e.inv[j] * sp.m_sup[k][j];
+        const T amt = tmin(inv_s, e.B[k]) * sp.m_rank[r][k];
 #pragma unroll
-        for (int j = 0; j < kF; ++j) e.inv[j] = e.inv[j] - amt * mask_of<T>(s == j);
+        for (int j = 0; j < kF; ++j) e.inv[j] = e.inv[j] - amt * sp.m_sup[k][j];
         e.B[k] = e.B[k] - amt;
-        const int ls = sp.ls[k];
 #pragma unroll
-        for (int j = 0; j < kGS; ++j) e.ship[k][j] = e.ship[k][j] + amt * mask_of<T>(j == ls - 1);
+        for (int j = 0; j < kGS; ++j) e.ship[k][j] = e.ship[k][j] + amt * sp.m_ls[k][j];
       }
     }
   }
@@ -209,13 +207,11 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
     T arrived[kF];
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
-      const int li = sp.li[k];
-      const T head = e.info[k][0];
-      arrived[k] = (li == 1) ? q[k] : head;
+      arrived[k] = e.info[k][0] + q[k] * sp.m_li1[k];       // lead time 1: the head slot is empty, q arrives now
 #pragma unroll
       for (int j = 0; j < kGI; ++j) {
         const T next = (j + 1 < kGI) ? e.info[k][j + 1] : T(0);
-        e.info[k][j] = next + q[k] * mask_of<T>(j == li - 2);
+        e.info[k][j] = next + q[k] * sp.m_li[k][j];
       }
       e.B[k] = e.B[k] + arrived[k];
       e.U[k][3] = e.U[k][3] + U4[k];
