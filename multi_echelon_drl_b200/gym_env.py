@@ -31,14 +31,14 @@ class _SupplyNetworkView:
     def __init__(self, env):
         self._env = env
         self.internal_nodes = list(env.spec.node_names)
-        self.agent_managed_facilities = [NODE_NAMES[k] for k in env.spec.agents]
-        self.order_sequence = list(env.spec.node_names) + ["external_supplier"]
+        self.agent_managed_facilities = [env.spec.node_names[k] for k in env.spec.agents]
+        self.order_sequence = list(env.spec.order_sequence) + [env.spec.external_name]
 
     def get_state(self, node_name: str) -> dict:
         """The 7 numbers of node `node_name` as the reference's dict (observation of the current state,
         global view)."""
         env = self._env
-        k = NODE_NAMES.index(node_name)
+        k = env.spec.node_names.index(node_name)
         full = env._full_observation()
         v = full[7 * k:7 * k + 7]
         cast = (lambda x: int(x)) if env.sim.dtype == "int32" else float
@@ -95,7 +95,7 @@ class BeerGameEnv:
         if not self.return_dict:
             return flat
         cast = (lambda x: int(x)) if self.sim.dtype == "int32" else float
-        names = [NODE_NAMES[k] for k in self.spec.obs_nodes]
+        names = [self.spec.node_names[k] for k in self.spec.obs_nodes]
         return {name: {key: cast(x) for key, x in zip(_KEYS, flat[7 * i:7 * i + 7])} for i, name in enumerate(names)}
 
     def _full_observation(self) -> np.ndarray:

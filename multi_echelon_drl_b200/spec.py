@@ -312,6 +312,33 @@ def tree_spec(nodes, arcs, agent_managed_facilities, global_observable=False, ma
     return spec
 
 
+def _tree_from_config(cfg, agent_managed_facilities, global_observable, max_episode_steps, coplayer_target, random_init):
+    """network_configs/*.yaml schema -> tree_spec.  A node with `demand_path` is a demand source; here the value
+    names a generator 'uniform:low:high' / 'normal:mean:sd' (the reference's sample files are not in its repo);
+    `target` per node (or coplayer_target by position) is the co-player base-stock level."""
+    if len(cfg.get("items", []) or []) > 1:
+        raise NotImplementedError("multi-item networks are supported for the serial beer-game chain only")
+    internal = [n for n in cfg["nodes"] if not n.get("is_external_supplier", False)]
+    pattern, nodes = None, []
+    for i, n in enumerate(internal):
+        demand = None
+        if n.get("demand_path"):
+            parts = str(n["demand_path"]).split(":")
+            if len(parts) != 3 or parts[0] not in ("uniform", "normal"):
+                raise NotImplementedError(f"demand_path {n['demand_path']!r}: expected 'uniform:low:high' or 'normal:mean:sd'")
+            if pattern not in (None, parts[0]):
+                raise NotImplementedError("all demand sources of a network must use the same demand pattern")
+            pattern, demand = parts[0], (float(parts[1]), float(parts[2]))
+        cost = lambda v: float(v[0] if isinstance(v, (list, tuple)) else v)
+        nodes.append(dict(name=n["name"], holding_cost=cost(n.get("holding_cost", 0)), backorder_cost=cost(n.get("backorder_cost", 0)),
+                          target=n.get("target", coplayer_target[min(i, len(coplayer_target) - 1)]), demand=demand))
+    arcs = [(a["supplier"], a["customer"], int(a.get("info_leadtime", 0)), int(a.get("shipment_leadtime", 0))) for a in cfg["arcs"]]
+    if any(not 1 <= l <= 4 for a in arcs for l in a[2:]) or any(a[2] + a[3] > 5 for a in arcs):
+        raise NotImplementedError("lead times must be 1..4 with info + shipment <= 5 per arc")
+    return tree_spec(nodes, arcs, agent_managed_facilities, global_observable, max_episode_steps, random_init,
+                     demand_pattern=pattern or "uniform", name="config-tree")
+
+
 def specs_from_config(network_config: dict, agent_managed_facilities=None, global_observable=False,
                       max_episode_steps=100, coplayer_target=(19, 20, 20, 14), random_init=True):
     """ScenarioSpec per item from a network description (network_configs/*.yaml schema; what the
@@ -319,9 +346,16 @@ def specs_from_config(network_config: dict, agent_managed_facilities=None, globa
     descriptions (`items:`) give one spec per item: items are independent copies of the chain with
     their own cost vectors (the reference defines no item coupling)."""
     from .utils.graph import chain_from_config
-    seq, info, ship, hold, back = chain_from_config(network_config)
+    try:
+        seq, info, ship, hold, back = chain_from_config(network_config)
+        if tuple(seq) != NODE_NAMES[:len(seq)]:
+            raise NotImplementedError("not the beer game's node names")
+    except NotImplementedError:
+        # not the serial chain retailer..manufacturer: a distribution tree (any names), if it is one
+        return [_tree_from_config(network_config, agent_managed_facilities, global_observable, max_episode_steps,
+                                  coplayer_target, random_init)]
     nf = len(seq)
-    if not 1 <= nf <= 4 or tuple(seq) != NODE_NAMES[:nf]:
+    if not 1 <= nf <= 4:
         raise NotImplementedError(f"kernels implement serial chains made of the first 1..4 of {NODE_NAMES}; got {seq}")
     if any(not 1 <= l <= 4 for l in info + ship) or any(a + b > 5 for a, b in zip(info, ship)):
         raise NotImplementedError(f"lead times must be 1..4 with info + shipment <= 5 per arc; got {info}/{ship}")

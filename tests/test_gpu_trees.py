@@ -156,3 +156,29 @@ def test_vecenv_on_a_tree_and_statistics():
     assert torch.isfinite(obs).all() and env.episodes_done == 2000
     stats = env.run_policy_episodes(BasePolicyParams(case["target"], 0, 16, "a"), n_episodes=3).cpu().numpy()
     assert stats[0] == 3000 * 100 and stats[10] == 3000 and stats[11] < 0 and stats[11] == stats[1]
+
+
+def test_single_env_from_yaml_replays_the_reference_episode():
+    """make_env_from_config on the packaged tree YAML: `np.random.seed(s); env.reset(); env.step(a)...` gives the
+    observations and rewards the reference gave for the same seed and actions (golden case of the same network)."""
+    import os
+    import multi_echelon_drl_b200 as pkg
+    from multi_echelon_drl_b200.envs import make_env_from_config
+    path = os.path.join(os.path.dirname(pkg.__file__), "network_configs", "distribution_tree.yaml")
+    for glob, rule, agents in ((True, "a", [1, 2]), (False, "a", [3])):
+        c = [c for c in TREE_CASES if c["topo"] == "two_level" and c["agents"] == agents and c["glob"] == glob and c["rule"] == rule][0]
+        env = make_env_from_config(path, [c["names"][a] for a in agents], glob)
+        assert env.sn.order_sequence == c["order_sequence"] + ["external_supplier"]
+        np.random.seed(c["seed"])
+        obs = env.reset()
+        assert np.array_equal(obs, c["obs0"])
+        for t in range(100):
+            obs, r, done, info = env.step(c["actions"][t])
+            assert np.array_equal(obs, c["obs"][t]) and r == c["rew"][t], t
+        assert done
+        st = env.sn.get_state("maker")
+        assert st["on_hand"] == (c["obs"][-1][21] if glob else c["obs"][-1][0])
+        with pytest.raises(ValueError):
+            env.step(c["actions"][0])
+    venv = make_env_from_config(path, ["shop", "dist_a", "dist_b", "maker"], True, n_envs=256, dtype="int32")
+    assert venv.reset().shape == (256, 28)

@@ -199,3 +199,21 @@ def test_tree_spec_and_c_validation_errors():
     c = sp.to_c()
     c.n_items = 2
     assert lib.sn_spec_validate(C.byref(c), _lib.SN_I32) != 0
+
+
+def test_yaml_description_of_a_tree_gives_the_golden_spec():
+    """network_configs/distribution_tree.yaml (the reference's YAML schema) lowers to the same spec as the node / arc
+    lists of the 'two_level' golden topology."""
+    import dataclasses
+    import multi_echelon_drl_b200 as pkg
+    from multi_echelon_drl_b200.spec import specs_from_config
+    from multi_echelon_drl_b200.utils.graph import read_yaml
+    cfg = read_yaml(os.path.join(os.path.dirname(pkg.__file__), "network_configs", "distribution_tree.yaml"))
+    c = [c for c in TREE_CASES if c["topo"] == "two_level" and c["agents"] == [1, 2] and c["glob"] and c["rule"] == "a"][0]
+    (sp,) = specs_from_config(cfg, ["dist_a", "dist_b"], True)
+    a, b = dataclasses.asdict(sp), dataclasses.asdict(tree_product_spec(c))
+    a.pop("name"); b.pop("name")
+    assert a == b
+    with pytest.raises(NotImplementedError):              # a node with two suppliers is not a distribution tree
+        bad = dict(cfg, arcs=cfg["arcs"] + [dict(customer="shop", supplier="dist_b", info_leadtime=1, shipment_leadtime=1)])
+        specs_from_config(bad, ["shop"], True)
