@@ -83,7 +83,8 @@ struct Env {
   T inv[kF], lat[kF], U[kF][4], B[kF], info[3], ship[kF][2], unf_ind;
 
   // "unfilled_demand" of node k as SupplyNetwork.get_state reports it (supplynetwork.py:130-136)
-  __device__ __forceinline__ T unfilled(int k) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+  __device__ __forceinline__ T unfilled(int k, const DevSpec<T>&) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+  __device__ __forceinline__ T latest(int k) const { return lat[k]; }                       // supplynetwork.py:139
   // co-player that orders inside before_action (chain position below the first agent)
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return k < kF - 1 && k < sp.lo; }
 };
@@ -176,12 +177,12 @@ __device__ __forceinline__ void env_reset(Env<T>& e, const T (&in)[kInitWords], 
 template <int K, typename T, typename E>
 __device__ __forceinline__ void node_view(const E& e, const DevSpec<T>& sp, bool terminal, float (&v)[7]) {
   T u0 = e.U[K][0], u1 = e.U[K][1], u2 = e.U[K][2], u3 = e.U[K][3];
-  const T unf = e.unfilled(K);
+  const T unf = e.unfilled(K, sp), lat = e.latest(K);
   if (E::pre_agent(K, sp) && !terminal) {
-    const T q = tmax(base_stock(sp.target[K], e.inv[K], e.U[K], unf, e.lat[K], sp.clb, sp.cub, 0), T(0));
+    const T q = tmax(base_stock(sp.target[K], e.inv[K], e.U[K], unf, lat, sp.clb, sp.cub, 0), T(0));
     u3 = u2; u2 = u1; u1 = u0; u0 = q;
   }
-  v[0] = (float)e.inv[K]; v[1] = (float)unf; v[2] = (float)e.lat[K];
+  v[0] = (float)e.inv[K]; v[1] = (float)unf; v[2] = (float)lat;
   v[3] = (float)u0; v[4] = (float)u1; v[5] = (float)u2; v[6] = (float)u3;
 }
 
@@ -249,9 +250,9 @@ __device__ __forceinline__ void env_orders(const E& e, const DevSpec<T>& sp, con
     T x;
     if (IDENT || sp.slot[k] >= 0) {
       x = a[k];
-      if (sp.rule == 1) x = tclamp(e.lat[k] + x + sp.off, sp.lb, sp.ub);
+      if (sp.rule == 1) x = tclamp(e.latest(k) + x + sp.off, sp.lb, sp.ub);
     } else {
-      x = base_stock(sp.target[k], e.inv[k], e.U[k], e.unfilled(k), e.lat[k], sp.clb, sp.cub, 0);
+      x = base_stock(sp.target[k], e.inv[k], e.U[k], e.unfilled(k, sp), e.latest(k), sp.clb, sp.cub, 0);
     }
     q[k] = tmax(x, T(0));                                                  // network_components.py:368-374
   }

@@ -28,7 +28,8 @@ constexpr int kGInitWords = 4 + 4 * kF + 4 * kF;             // 36
 template <typename T>
 struct GEnv {
   T inv[kF], lat[kF], U[kF][4], B[kF], info[kF][kGI], ship[kF][kGS], unf_ind;
-  __device__ __forceinline__ T unfilled(int k) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+  __device__ __forceinline__ T unfilled(int k, const DevSpec<T>&) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
+  __device__ __forceinline__ T latest(int k) const { return lat[k]; }
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return k < kF - 1 && k < sp.lo; }
 };
 

@@ -159,6 +159,7 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __rest
 // (tuned, 40 state words), GenOps = run-time per-arc lead times (supplynet_generic.cuh, 57 words).
 template <typename T>
 struct StdOps {
+  static constexpr bool kWide = false;
   using E = Env<T>;
   using D = T;                                     // demand of one period: one number per env
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
@@ -193,6 +194,7 @@ struct StdOps {
 
 template <typename T>
 struct GenOps {
+  static constexpr bool kWide = false;            // measured: 0.209 ms with 128 registers + 14 spill accesses, 0.245 ms wide
   using E = GEnv<T>;
   using D = T;
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
@@ -228,6 +230,7 @@ struct GenOps {
 // distribution trees (supplynet_tree.cuh, 64 words): one demand row per source and period
 template <typename T>
 struct TreeOps {
+  static constexpr bool kWide = true;             // k_rollout_wide, 144 registers: 0.315 ms vs 0.355 ms with 128 + ~100 spill accesses
   using E = TEnv<T>;
   using D = TreeDem<T>;
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>& sp, int64_t ld) { return ld * sp.n_src; }
@@ -241,7 +244,7 @@ struct TreeOps {
     T w[kTStateWords];
 #pragma unroll
     for (int i = 0; i < kTStateWords; ++i) w[i] = state[i * ld + env];
-    tenv_from_words(e, sp, w);
+    tenv_from_words(e, w);
   }
   static __device__ __forceinline__ void store(T* __restrict__ state, int64_t ld, int64_t env, const E& e) {
     T w[kTStateWords];
@@ -381,15 +384,13 @@ struct RolloutPtrs {
 #define SN_PRAGMA_UNROLL(n) _Pragma(SN_STR(unroll n))
 constexpr int kRolloutBlock = SN_ROLLOUT_BLOCK;
 
-// 7 blocks of 64 threads per SM (<= 144 registers): 65,536 envs = 1,024 blocks fit the 148 SMs in ONE wave
+// body of the fused rollout kernels below
 template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
-__global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock)
-k_rollout(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld,
-          int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
-          const T* __restrict__ actions, const RolloutPtrs out, int use_tma, const T* __restrict__ init,
-          float* __restrict__ obs0) {
-  extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[(kRolloutBlock / 32) * 13];
+__device__ __forceinline__ void
+rollout_body(const DevSpec<T>& sp, const DevPolicy<T>& pol, int64_t n, int64_t ld,
+             int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
+             const T* __restrict__ actions, const RolloutPtrs& out, int use_tma, const T* __restrict__ init,
+             float* __restrict__ obs0, float* smem_f, double* red) {
   const int64_t env = (int64_t)blockIdx.x * kRolloutBlock + threadIdx.x;
   const bool valid = env < n;
   const int64_t envc = valid ? env : (n - 1);       // tail lanes shadow the last env (loads only)
@@ -433,7 +434,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
 #pragma unroll
       for (int k = 0; k < kF; ++k)
         if (IDENT || sp.slot[k] >= 0)
-          a[k] = base_stock(pol.target[k], e.inv[k], e.U[k], e.unfilled(k), e.lat[k], pol.lb, pol.ub, pol.rule);
+          a[k] = base_stock(pol.target[k], e.inv[k], e.U[k], e.unfilled(k, sp), e.latest(k), pol.lb, pol.ub, pol.rule);
     }
     if (out.traj_actions != nullptr && valid) store_actions_f32<IDENT>(out.traj_actions + (int64_t)s * act_stride, env, sp, a);
     T q[kF];
@@ -471,6 +472,29 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     v[12] = ep ? ep_total * ep_total : 0.0;
     block_reduce_add<13, kRolloutBlock / 32>(v, out.stats, red);
   }
+}
+
+#define SN_ROLLOUT_PARAMS                                                                                          \
+  const __grid_constant__ DevSpec<T> sp, const __grid_constant__ DevPolicy<T> pol, int64_t n, int64_t ld, int period0, \
+      int n_steps, T *__restrict__ state, const T *__restrict__ demand, const T *__restrict__ actions,                 \
+      const RolloutPtrs out, int use_tma, const T *__restrict__ init, float *__restrict__ obs0
+#define SN_ROLLOUT_ARGS sp, pol, n, ld, period0, n_steps, state, demand, actions, out, use_tma, init, obs0
+
+// tuned beer-game chain: 7 blocks of 64 threads per SM: 65,536 envs = 1,024 blocks fit the 148 SMs in ONE wave
+template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
+__global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock) k_rollout(SN_ROLLOUT_PARAMS) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ double red[(kRolloutBlock / 32) * 13];
+  rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
+}
+
+// trees (Ops::kWide): same residency (7 x 64 threads x 144 registers fit the register file), but the full 144
+// registers instead of the 128 that ptxas settles on under __launch_bounds__(64, 7): a third of the spills
+template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
+__global__ void __maxnreg__(144) k_rollout_wide(SN_ROLLOUT_PARAMS) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ double red[(kRolloutBlock / 32) * 13];
+  rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
 }
 
 // BaseStockPolicy.get_order_quantity, ndarray path (utils/heuristics.py:43-57,75), per env.
@@ -789,15 +813,18 @@ template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 void launch_rollout(const sn::DevSpec<T>& d, const sn::DevPolicy<T>& p, int64_t n, int64_t ld, int period0, int n_steps,
                     void* state, const void* demand, const void* actions, const sn::RolloutPtrs& out, int tma,
                     cudaStream_t st, const void* init, float* obs0) {
+  auto kern = [] {
+    if constexpr (Ops::kWide) return &sn::k_rollout_wide<T, POLICY, IDENT, MULTI, Ops>;
+    else return &sn::k_rollout<T, POLICY, IDENT, MULTI, Ops>;
+  }();
   if (kRolloutSmem > 48 * 1024) {            // only with experimental block sizes (SN_ROLLOUT_BLOCK > 192)
     static bool opted_in = false;
     if (!opted_in) {
-      cudaFuncSetAttribute(sn::k_rollout<T, POLICY, IDENT, MULTI, Ops>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kRolloutSmem);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRolloutSmem);
       opted_in = true;
     }
   }
-  sn::k_rollout<T, POLICY, IDENT, MULTI, Ops><<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
+  kern<<<grid_for(n, sn::kRolloutBlock), sn::kRolloutBlock, kRolloutSmem, st>>>(
       d, p, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, tma, (const T*)init, obs0);
 }
 

@@ -29,9 +29,17 @@ struct TreeDem { T v[kF]; };      // current external demand per NODE (0 for nod
 
 template <typename T>
 struct TEnv {
-  T inv[kF], lat[kF], U[kF][4], B[kF], info[kF][kGI], ship[kF][kGS], unf_ind[kF], dem[kF], latI[kF], unfv[kF];
-  // lat[k] / unfv[k]: the observed latest_demand / unfilled_demand, derived by tenv_refresh
-  __device__ __forceinline__ T unfilled(int k) const { return unfv[k]; }
+  T inv[kF], U[kF][4], B[kF], info[kF][kGI], ship[kF][kGS], unf_ind[kF], dem[kF], latI[kF];
+  // observed unfilled_demand (supplynetwork.py:130-136): backlog of all customer arcs + (current external demand +
+  // unfilled independent demand); observed latest_demand (:139).  Recomputed where read: registers are scarcer
+  // than multiply-adds here.
+  __device__ __forceinline__ T unfilled(int k, const DevSpec<T>& sp) const {
+    T cb = T(0);
+#pragma unroll
+    for (int c = 0; c < kF; ++c) cb = cb + B[c] * sp.m_sup[c][k];
+    return cb + (dem[k] + unf_ind[k]);
+  }
+  __device__ __forceinline__ T latest(int k) const { return latI[k] + dem[k]; }
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return sp.pre[k] != 0; }
 };
 
@@ -45,16 +53,7 @@ __device__ __forceinline__ T customers_backlog(const TEnv<T>& e, const DevSpec<T
 }
 
 template <typename T>
-__device__ __forceinline__ void tenv_refresh(TEnv<T>& e, const DevSpec<T>& sp) {
-#pragma unroll
-  for (int k = 0; k < kF; ++k) {
-    e.unfv[k] = customers_backlog(e, sp, k) + (e.dem[k] + e.unf_ind[k]);      // supplynetwork.py:130-136
-    e.lat[k] = e.latI[k] + e.dem[k];                                           // :139
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void tenv_from_words(TEnv<T>& e, const DevSpec<T>& sp, const T (&w)[kTStateWords]) {
+__device__ __forceinline__ void tenv_from_words(TEnv<T>& e, const T (&w)[kTStateWords]) {
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     e.inv[k] = w[7 * k];
@@ -69,7 +68,6 @@ __device__ __forceinline__ void tenv_from_words(TEnv<T>& e, const DevSpec<T>& sp
     e.B[k] = w[56 + k];
     e.dem[k] = w[60 + k];
   }
-  tenv_refresh(e, sp);
 }
 
 template <typename T>
@@ -139,7 +137,6 @@ __device__ __forceinline__ void tenv_reset(TEnv<T>& e, const DevSpec<T>& sp, con
     e.dem[k] = d0.v[k];
   }
   set_latest(e, sp, arrived);
-  tenv_refresh(e, sp);
 }
 
 template <typename T>
@@ -218,7 +215,6 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
     }
     set_latest(e, sp, arrived);
   }
-  tenv_refresh(e, sp);
 }
 
 }  // namespace sn

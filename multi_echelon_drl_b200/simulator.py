@@ -108,8 +108,7 @@ class BatchedSupplyNetwork:
         """init [n, init_words] (19: inv[4]; so[k][j]; sh[k][j] packed for the beer game's lead times; 36:
         inv[4]; so[k][0..3]; sh[k][0..3] for other lead times), demand [n, >=T+1] (utils/demands.py streams)."""
         d = torch.as_tensor(demand)
-        if self.spec.is_tree:
-            """trees: demand [n, n_sources, >=T+1], one stream per demand source (node order)"""
+        if self.spec.is_tree:            # demand [n, n_sources, >=T+1]: one stream per demand source, node order
             if d.dim() != 3 or d.shape[1] != self.n_sources or d.shape[2] < self.T + 1:
                 raise ValueError(f"demand must be [n_envs, {self.n_sources}, >= {self.T + 1}]")
             width = min(d.shape[2], self.T + 3)
