@@ -446,6 +446,39 @@ def single_step_numbers(torch, dev, peak):
     out["multi_item_262144x2_step"] = {"env_steps_per_s": n / (ms * 1e-3), "item_chain_steps_per_s": 2 * n / (ms * 1e-3),
                                        "us_per_step": ms * 1e3,
                                        "config": "config 4: 262,144 envs x 2 items (one interleaved batch of 524,288 chains, per-item costs in-kernel), obs 56 / action 8, eager per-period calls"}
+    del mi
+    # other networks, same fixed-action rollout with trajectory out at config-2 size
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    n = N_ENVS
+    tree = tree_spec([dict(name="shop", demand=(0, 8), target=19), dict(name="dist_a", target=20),
+                      dict(name="dist_b", demand=(0, 5), target=14), dict(name="maker", target=25)],
+                     [("ext", "maker", 1, 2), ("maker", "dist_b", 1, 2), ("maker", "dist_a", 2, 2), ("dist_a", "shop", 2, 2)],
+                     ["shop", "dist_a", "dist_b", "maker"], True)
+    others = {"rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
+              "rollout_distribution_tree_65536": tree}
+    acts = torch.randint(0, 17, (T, n, 4), generator=g, device=dev, dtype=torch.int32)
+    t_obs = torch.empty((T, n, 28), dtype=torch.float32, device=dev)
+    t_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+    for key, sp in others.items():
+        sim = BatchedSupplyNetwork(sp, n, dev, "int32")
+        sim.load_episode(*bulk_episode_inputs(sp, n, np.random.RandomState(0)))
+        for _ in range(3):
+            sim.episode(T, actions=acts, traj_obs=t_obs, traj_reward=t_rew, write_state=False)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(10):
+            sim.episode(T, actions=acts, traj_obs=t_obs, traj_reward=t_rew, write_state=False)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        nbytes = n * T * (16 + 4 * sp.n_sources + 112 + 4)
+        out[key] = {"env_steps_per_s": n * T / (ms * 1e-3), "kernel_ms": ms, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
+                    "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "bound": "instruction issue (run-time topology / lead times as 0/1 multipliers)",
+                    "config": ("serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
+                               "two-level distribution tree, two demand sources (tree kernels)")}
+        del sim
     return out
 
 
@@ -503,8 +536,8 @@ def run_config3(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default: BASELINE config 2)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
