@@ -165,6 +165,7 @@ class HgeTD3:
         self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
         self.critic_opt = torch.optim.Adam(self.critics.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
         self._graph, self._graph_warm = None, 0
+        self._pi_graphs, self._pi_seen = {}, {}
         self.buffer = ReplayBuffer(c.buffer_size, od, ad, self.device)
         self.hge_schedule = HgeRateSchedule(c.hge_rate_at_start, c.hge_decay_periods)
         self.hge_rate = c.hge_rate_at_start if heuristic is not None else 0.0
@@ -184,7 +185,7 @@ class HgeTD3:
         """HgeTD3.predict (hge.py:144-172): one coin per call with probability hge_rate**2."""
         def policy(o):
             with self.timers.span("policy_forward"):
-                return self.unscale_action(self.actor(o))
+                return self._actor_forward(o)
 
         if self.heuristic is None or deterministic:
             return policy(observation)
@@ -197,6 +198,32 @@ class HgeTD3:
         a, _ = hge_predict(policy, _H(), observation, original_obs if original_obs is not None else observation,
                            self.hge_rate, deterministic, rng=self.rng)
         return a
+
+    @torch.no_grad()
+    def _actor_forward(self, o):
+        """unscale(actor(o)).  With cuda_graph the forward over the env's observation buffer (the same device
+        address at every step) is replayed as a graph: a handful of tiny GEMM / pointwise launches otherwise
+        cost more in launch overhead than in work.  The result is a buffer reused by the next call."""
+        if not self.cfg.cuda_graph:
+            return self.unscale_action(self.actor(o))
+        key = (o.data_ptr(), tuple(o.shape), o.dtype)
+        g = self._pi_graphs.get(key)
+        if g is None:
+            n_seen = self._pi_seen.get(key, 0)
+            self._pi_seen[key] = n_seen + 1
+            if n_seen < 3 or len(self._pi_graphs) >= 4:      # warm up eagerly first; few distinct buffers only
+                return self.unscale_action(self.actor(o))
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.unscale_action(self.actor(o))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out = self.unscale_action(self.actor(o))
+            g = self._pi_graphs[key] = (graph, out, o)       # keeps `o` alive: its address is baked into the graph
+        g[0].replay()
+        return g[1]
 
     @torch.no_grad()
     def _sample_action(self, obs, original_obs):
@@ -394,9 +421,10 @@ class HgeTD3:
     def close(self):
         """Drop the captured update graph (it holds NCCL work when gradients are averaged across ranks: the
         process group must not be destroyed under it)."""
-        if self._graph is not None:
+        if self._graph is not None or self._pi_graphs:
             torch.cuda.synchronize(self.device)
             self._graph = None
+            self._pi_graphs.clear()
             import gc
             gc.collect()
             torch.cuda.synchronize(self.device)

@@ -100,7 +100,7 @@ class VecNormalize:
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
         obs = self.venv.reset()
-        self.old_obs.copy_(obs)
+        self.old_obs = obs
         self.returns.zero_()
         if not self.norm_obs:
             return obs
@@ -114,8 +114,8 @@ class VecNormalize:
 
     def step_wait(self):
         obs, rew, dones, infos = self.venv.step_wait()
-        self.old_obs.copy_(obs)
-        self.old_reward.copy_(rew)
+        # the wrapped env hands out the same two device buffers at every step: keep references, not copies
+        self.old_obs, self.old_reward = obs, rew
         done = infos.terminal_observation is not None
         if self.training:
             # obs statistics and (if rewards are normalised) the discounted returns in one pass
@@ -141,9 +141,12 @@ class VecNormalize:
         return self.step_wait()
 
     def get_original_obs(self):
+        """Un-normalised observation of the last step: the wrapped env's own output buffer, valid until the next
+        step (clone it to keep it; SB3 returns a copy)."""
         return self.old_obs
 
     def get_original_reward(self):
+        """Un-normalised reward of the last step (same lifetime as get_original_obs)."""
         return self.old_reward
 
     def normalize_obs(self, obs: torch.Tensor, stats=None) -> torch.Tensor:
