@@ -18,7 +18,7 @@ import torch
 
 from . import spaces
 from .simulator import BatchedSupplyNetwork
-from .spec import NODE_NAMES, ScenarioSpec
+from .spec import ScenarioSpec
 from .utils import demands as _dem
 
 _KEYS = ("on_hand", "unfilled_demand", "latest_demand", "unreceived_pipeline_0", "unreceived_pipeline_1",

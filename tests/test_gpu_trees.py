@@ -52,7 +52,6 @@ def test_tree_batch_vs_oracle(cid, dtype):
     if dtype != "int32":
         acts = acts + rs.rand(*acts.shape).round(3)
     import oracle.network_np as NP
-    spec = None
     if dtype == "int32":
         obs0, obs, rew = tree_oracle_rollout(case, init, demand, acts)
     else:
