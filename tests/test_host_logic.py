@@ -312,5 +312,5 @@ def test_short_chain_specs_and_yaml():
     assert sp.n_facilities == 2 and sp.agents == (1,) and sp.info_leadtime == (2, 1) and sp.ship_leadtime == (2, 3)
     assert sp.holding_cost == (0.5, 0.25) and sp.backorder_cost == (1.0, 2.0) and sp.obs_dim == 14
     assert sp.coplayer_target == (19, 20)
-    with pytest.raises(NotImplementedError):      # a chain that does not start at the retailer
+    with pytest.raises(ValueError):               # no demand source left (other names go down the tree path, which says so)
         specs_from_config(dict(nodes=cfg["nodes"][1:], arcs=cfg["arcs"][:1]), ["wholesaler"])
