@@ -13,6 +13,8 @@ quantities that are not numbers (network_components.py:21-29).
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -85,6 +87,9 @@ class BeerGameEnv:
         if q.dtype == object or not (np.issubdtype(q.dtype, np.number) or np.issubdtype(q.dtype, np.bool_)):
             raise TypeError(f"order_quantity must be an instance of float, int or DemandGenerator, got {type(quantity)}")
         q = q.reshape(1, -1)
+        if self.spec.rule == "a" and (q < 0).any():       # network_components.py:368-374 (the kernel clamps)
+            warnings.warn(f"order quantity is {q.min()} but it should be non-negative. Quantity will be truncated to 0",
+                          category=RuntimeWarning)
         if q.shape[1] != self.spec.n_agents:
             raise ValueError(f"expected {self.spec.n_agents} order quantities, got {q.shape[1]}")
         obs, _, done = self.sim.step(torch.as_tensor(q), reward64_out=self._r64)

@@ -89,6 +89,8 @@ def test_single_env_errors_and_sn_view_match_reference_behaviour():
     env.reset()
     with pytest.raises(TypeError):
         env.step(["four"])                                                   # network_components.py:26-29
+    with pytest.warns(RuntimeWarning, match="non-negative"):
+        env.step(np.array([-3]))                                             # :368-374: warned and truncated to 0
     with pytest.raises(ValueError):
         make_beer_game_uniform_multi_facility(agent_managed_facilities=["retailer", "wholesaler"])   # needs box space
     # sn.get_state: the dict the d+a wrapper reads (utils/wrappers.py:24), classic initial state
