@@ -172,8 +172,12 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from multi_echelon_drl_b200.distributed import bind_to_gpu_cpus
     from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
 
+    # one process per GPU: stay on the CPUs / memory of the socket this GPU hangs off before pinning host buffers
+    all_cpus = os.sched_getaffinity(0)
+    cpus = None if args.no_numa_bind else bind_to_gpu_cpus(local)
     n = args.envs
     spec, init, demand, actions = make_inputs(n, 1234 + rank)
     sim = BatchedSupplyNetwork(spec, n, dev, "int32")
@@ -278,6 +282,7 @@ def run_native(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)            # the CPU baseline gets every host core again
             threads = os.cpu_count() or 1
             v, sample = cpu_port_throughput(init, demand, actions, threads, 10.0)
             v1, _ = cpu_port_throughput(init, demand, actions, 1, 3.0)
@@ -296,7 +301,8 @@ def run_native(args):
                        "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of the 16-double statistics vector every {args.stats_interval} episodes"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks},
+                    "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks,
+                    "cpu_binding": (f"{len(cpus)} CPUs next to the GPU (NVML affinity)" if cpus else "none")},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n), "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
@@ -545,6 +551,7 @@ def main():
     ap.add_argument("--stats-interval", type=int, default=10, help="episodes between statistics all-reduces (N>1)")
     ap.add_argument("--e2e-chunks", type=int, default=5, help="period spans of the pipelined host path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's socket")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -52,3 +52,27 @@ def summarize(stats: torch.Tensor) -> dict:
     return {"env_steps": s[0], "mean_reward": s[1] / steps, "holding_cost": s[2:6], "backorder_cost": s[6:10],
             "episodes": s[10], "mean_episode_return": mean,
             "std_episode_return": max(s[12] / eps - mean * mean, 0.0) ** 0.5}
+
+
+def bind_to_gpu_cpus(device_index: int) -> Optional[list]:
+    """Pin this process to the CPUs next to GPU `device_index` (NVML's ideal CPU affinity = the socket the GPU's PCIe
+    root hangs off), so that pinned host buffers allocated afterwards live in that socket's memory and the H2D / D2H
+    streams of the host-buffer path do not cross the inter-socket link.  One process per GPU calls this before it
+    allocates pinned memory.  Returns the CPU list, or None if nothing was changed (NVML missing, cpuset too narrow)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device_index)      # CUDA index -> PCI address -> NVML handle
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08X}:{p.pci_bus_id:02X}:{p.pci_device_id:02X}.0".encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        ideal = {c for c in range(n_cpu) if (int(words[c // 64]) >> (c % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(ideal & allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
