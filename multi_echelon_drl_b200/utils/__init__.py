@@ -1,0 +1,1 @@
+"""Host-side helpers with the reference's module names: heuristics, wrappers, demands, graph."""
