@@ -181,3 +181,29 @@ def test_single_env_from_yaml_replays_the_reference_episode():
             env.step(c["actions"][0])
     venv = make_env_from_config(path, ["shop", "dist_a", "dist_b", "maker"], True, n_envs=256, dtype="int32")
     assert venv.reset().shape == (256, 28)
+
+
+def test_random_trees_vs_oracle():
+    """24 random trees (structure, names, arc order, lead times, sources, agent sets, rules): fused episode and
+    stepwise kernels vs the tree oracle on 257 envs each, bit-exact."""
+    from test_oracle_trees import random_tree_case, random_tree_inputs
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    rs = np.random.RandomState(31)
+    for i in range(24):
+        c = random_tree_case(rs)
+        n = 257
+        init, dem, acts = random_tree_inputs(c, n, rs)
+        obs0, obs, rew = tree_oracle_rollout(c, init, dem, acts)
+        sim = BatchedSupplyNetwork(tree_product_spec(c), n, "cuda", "int32")
+        sim.load_episode(init, dem)
+        o0 = torch.empty((n, sim.obs_dim), dtype=torch.float32, device="cuda")
+        out = sim.episode(100, actions=torch.as_tensor(acts), record_obs=True, record_reward=True, obs0_out=o0)
+        assert np.array_equal(o0.cpu().numpy(), obs0), (i, c)
+        assert np.array_equal(out["traj_obs"].cpu().numpy(), obs), (i, c)
+        assert np.array_equal(sim.ep_return.cpu().numpy(), rew.sum(0)), (i, c)
+        if i % 4 == 0:
+            assert np.array_equal(sim.reset().cpu().numpy(), obs0)
+            r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+            for t in range(100):
+                o, _, _ = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
+                assert np.array_equal(o.cpu().numpy(), obs[t]) and np.array_equal(r64.cpu().numpy(), rew[t]), (i, t, c)

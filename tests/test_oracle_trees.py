@@ -217,3 +217,104 @@ def test_yaml_description_of_a_tree_gives_the_golden_spec():
     with pytest.raises(NotImplementedError):              # a node with two suppliers is not a distribution tree
         bad = dict(cfg, arcs=cfg["arcs"] + [dict(customer="shop", supplier="dist_b", info_leadtime=1, shipment_leadtime=1)])
         specs_from_config(bad, ["shop"], True)
+
+
+# ---------------------------------------------------------------------- random trees
+def random_tree_case(rs, n_nodes=None):
+    """A random distribution tree of 2..4 internal nodes: random supplier structure, names (they drive the order
+    sequence), arc-list order (priority among customers), lead times with info + shipment <= 5, demand sources at
+    the leaves and sometimes elsewhere, and an agent set that is contiguous in the resulting order sequence."""
+    from oracle.network_np import order_sequence
+    N = int(n_nodes or rs.randint(2, 5))
+    pool = ["alpha", "bravo", "charlie", "delta", "echo", "foxtrot", "golf", "hotel"]
+    names = list(rs.choice(pool, N, replace=False))
+    supplier = [EXTERNAL] * N
+    order = list(rs.permutation(N))               # order[i] may only buy from order[j], j < i, or the external supplier
+    for i in range(1, N):
+        if rs.rand() < 0.8:
+            supplier[order[i]] = int(order[rs.randint(0, i)])
+    has_customer = [any(supplier[c] == k for c in range(N)) for k in range(N)]
+    demand = [((0, int(rs.randint(3, 10))) if (not has_customer[k] or rs.rand() < 0.25) else None) for k in range(N)]
+    li, ls = [], []
+    for _ in range(N):
+        a = int(rs.randint(1, 5)); b = int(rs.randint(1, 6 - a)) if a < 5 else 1
+        li.append(a); ls.append(min(b, 4))
+    arc_order = [int(x) for x in rs.permutation(N)]
+    cd = {names[k]: [names[c] for c in arc_order if supplier[c] == k] for k in range(N)}
+    cd["external_supplier"] = [names[c] for c in arc_order if supplier[c] == EXTERNAL]
+    seq = [s for s in order_sequence(names + ["external_supplier"], cd) if s != "external_supplier"]
+    m = int(rs.randint(1, N + 1)); start = int(rs.randint(0, N - m + 1))
+    agents = [names.index(s) for s in seq[start:start + m]]
+    rs.shuffle(agents)
+    return dict(names=names, supplier=supplier, demand=demand, li=li, ls=ls, holding=[float(rs.choice([0.25, 0.5, 1.0])) for _ in range(N)],
+                backorder=[float(rs.choice([0.5, 1.0, 2.0])) for _ in range(N)], target=[int(rs.randint(8, 40)) for _ in range(N)],
+                arc_order=arc_order, agents=[int(a) for a in agents], glob=bool(rs.rand() < 0.5), rule=str(rs.choice(["a", "d+a"])),
+                order_sequence=seq)
+
+
+def random_tree_inputs(case, n, rs):
+    N = len(case["names"])
+    init = np.zeros((n, 36), dtype=np.int64)
+    init[:, :N] = rs.randint(0, 25, (n, N))
+    for k in range(N):
+        init[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] = rs.randint(0, 9, (n, case["li"][k]))
+        init[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] = rs.randint(0, 9, (n, case["ls"][k]))
+    dem = np.stack([rs.randint(d[0], d[1] + 1, (n, 103)) for d in case["demand"] if d is not None], axis=1)
+    acts = rs.randint(-1, 19, (100, n, len(case["agents"])))
+    return init, dem, acts
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_harness", fromlist=["x"]).reference_available(),
+                    reason="/root/reference not mounted (GPU box)")
+def test_random_trees_vs_live_reference():
+    """40 random trees: the restatement and the reference's own classes agree on every observation, reward and
+    per-node cost, and on the order sequence."""
+    from oracle import ref_harness as H
+    rs = np.random.RandomState(2024)
+    for i in range(40):
+        c = random_tree_case(rs)
+        names = c["names"]
+        nd = [dict(name=names[k], target=c["target"][k], holding=c["holding"][k], backorder=c["backorder"][k],
+                   demand=c["demand"][k]) for k in range(len(names))]
+        arcs = [("external_supplier" if c["supplier"][k] < 0 else names[c["supplier"][k]], names[k], c["li"][k], c["ls"][k])
+                for k in c["arc_order"]]
+        env = H.make_network_env(nd, arcs, [names[a] for a in c["agents"]], c["glob"],
+                                 dplusa=(-8, 0, 16) if c["rule"] == "d+a" else None)
+        acts = rs.randint(-1, 19, (100, len(c["agents"])))
+        r = H.network_rollout(env, names, [a for a in acts], seed=7000 + i)
+        assert [s for s in r["order_sequence"] if s != "external_supplier"] == c["order_sequence"], (i, c)
+        inv0, so, sh, dem = r["init"]
+        init = np.zeros(36, dtype=np.int64)
+        init[:len(inv0)] = inv0
+        for k in range(len(inv0)):
+            init[4 + 4 * k: 4 + 4 * k + len(so[k])] = so[k]
+            init[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
+        o0, obs, rew, hold, back = tree_oracle_rollout(c, init[None], np.asarray(dem)[None], acts[:, None, :], return_costs=True)
+        assert np.array_equal(o0[0], r["obs0"]), (i, c)
+        assert np.array_equal(obs[:, 0], r["obs"]) and np.array_equal(rew[:, 0], r["rew"]), (i, c)
+        assert np.array_equal(hold[:, 0], r["holding"]) and np.array_equal(back[:, 0], r["backorder"]), (i, c)
+
+
+def test_random_tree_specs_lower_consistently():
+    """Product spec of random trees: same order sequence as the oracle's restatement of utils/graph.py, accepted by
+    the C validation; quantities never go negative in the oracle (inventory, backlog, pipelines)."""
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(77)
+    for i in range(60):
+        c = random_tree_case(rs)
+        sp = tree_product_spec(c)
+        assert list(sp.order_sequence) == c["order_sequence"], c
+        cs = sp.to_c()
+        assert lib.sn_spec_validate(C.byref(cs), _lib.SN_I32) == 0, (lib.sn_last_error(), c)
+        if i < 10:
+            init, dem, acts = random_tree_inputs(c, 8, rs)
+            orc = TreeOracle(oracle_spec(c), 8)
+            N = len(c["names"])
+            orc.reset(init[:, :N], [init[:, 4 + 4 * k: 4 + 4 * k + c["li"][k]] for k in range(N)],
+                      [init[:, 20 + 4 * k: 20 + 4 * k + c["ls"][k]] for k in range(N)], dem)
+            for t in range(100):
+                orc.step(acts[t])
+                orc.check_invariant()
+                assert all((x >= 0).all() for x in orc.inv + orc.B + orc.unf_ind)
