@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 6
+#define SN_ABI_VERSION 7
 
-#define SN_MAX_FACILITIES 4
+#define SN_MAX_FACILITIES 8     /* size of the per-facility arrays; chains and the register-resident kernels use up to 4 */
+#define SN_MAX_CHAIN 4          /* chains, and trees on the register-resident kernels */
 #define SN_MAX_ITEMS 4
 #define SN_OBS_PER_FACILITY 7   /* supplynetwork.py:151-169 */
 #define SN_STATE_WORDS 40       /* 28 observable + 12 hidden words per env */
@@ -37,6 +38,8 @@ extern "C" {
 #define SN_GEN_STATE_WORDS 57   /* chains with other lead times: 28 + 4x3 order slips + 4x4 shipments + 1 */
 #define SN_GEN_INIT_WORDS 36    /* inv[4]; so[k][0..3] at 4+4k; sh[k][0..3] at 20+4k (unused slots 0)      */
 #define SN_TREE_STATE_WORDS 64  /* distribution trees: 28 + 12 + 16 + backlog[4] + current external demand[4] */
+#define SN_NET_STATE_WORDS 128  /* trees of 5..8 nodes: 16 words per node (inv, unf_ind, latest, U[4], info[3], ship[4], backlog, demand) */
+#define SN_NET_INIT_WORDS 72    /* trees of 5..8 nodes: inv[8]; so[k][0..3] at 8+4k; sh[k][0..3] at 40+4k */
 #define SN_STATS_WORDS 16
 
 enum { SN_I32 = 0, SN_F32 = 1, SN_F64 = 2 };
@@ -62,10 +65,11 @@ enum {
  * ordering rule of utils/wrappers.py:6-31.  Node k: 0 retailer .. 3 manufacturer; arc k is the
  * arc whose customer is node k. */
 typedef struct sn_spec {
-  int32_t n_facilities;                       /* 1..4: the first n of retailer..manufacturer; arc n-1 buys from the external supplier */
+  int32_t n_facilities;                       /* chains 1..4: the first n of retailer..manufacturer, arc n-1 buys from the
+                                               * external supplier; trees 1..8 internal nodes */
   int32_t info_leadtime[SN_MAX_FACILITIES];   /* Arc.information_leadtime, 1..4; beer game 2,2,2,1 */
   int32_t ship_leadtime[SN_MAX_FACILITIES];   /* Arc.shipment_leadtime, 1..4, info+ship <= 5; 2,2,2,2 */
-  int32_t n_agents;                           /* 1..4                                         */
+  int32_t n_agents;                           /* 1..n_facilities                              */
   int32_t agents[SN_MAX_FACILITIES];          /* node index per action column, caller order   */
                                               /* (supplynetwork.py:217); contiguous set       */
   int32_t global_observable;                  /* envs.py:72-75                                */
@@ -91,7 +95,11 @@ typedef struct sn_spec {
    * order); its upstream arc carries info_leadtime[k] / ship_leadtime[k].  The demand tables then hold one row
    * per demand source and period, sources in node order: demand [T+3][n_sources][ld], demand0 / demand_next
    * [n_sources][ld].  Multi-supplier (assembly) nodes are not supported: the reference's own state keys collide
-   * there (supplynetwork.py:165-167). */
+   * there (supplynetwork.py:165-167).
+   * Trees of up to four nodes run on register-resident kernels (SN_TREE_STATE_WORDS); trees of five to eight nodes on
+   * kernels that keep the env in shared memory and index the topology directly (SN_NET_STATE_WORDS / SN_NET_INIT_WORDS,
+   * observation 7 floats per node, up to 8 action columns, `cost` [16][ld]: holding[0..7], backorder[8..15]; the
+   * per-facility sums [2..9] of the statistics vector stay zero there). */
   int32_t supplier[SN_MAX_FACILITIES];        /* supplier node of node k, SN_EXTERNAL = the external supplier   */
   int32_t demand_source[SN_MAX_FACILITIES];   /* Node.is_demand_source                                           */
   int32_t order_pos[SN_MAX_FACILITIES];       /* position of node k among the internal nodes in the order sequence

@@ -17,22 +17,25 @@ SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 6
+ABI_VERSION = 7
+
+
+MAXF = 8            # SN_MAX_FACILITIES: size of the per-facility arrays (chains use the first four)
 
 
 class SnSpec(C.Structure):
     _fields_ = [
         ("n_facilities", C.c_int32),
-        ("info_leadtime", C.c_int32 * 4),
-        ("ship_leadtime", C.c_int32 * 4),
+        ("info_leadtime", C.c_int32 * MAXF),
+        ("ship_leadtime", C.c_int32 * MAXF),
         ("n_agents", C.c_int32),
-        ("agents", C.c_int32 * 4),
+        ("agents", C.c_int32 * MAXF),
         ("global_observable", C.c_int32),
         ("max_episode_steps", C.c_int32),
         ("rule", C.c_int32),
-        ("holding_cost", C.c_double * 4),
-        ("backorder_cost", C.c_double * 4),
-        ("coplayer_target", C.c_double * 4),
+        ("holding_cost", C.c_double * MAXF),
+        ("backorder_cost", C.c_double * MAXF),
+        ("coplayer_target", C.c_double * MAXF),
         ("coplayer_lb", C.c_double),
         ("coplayer_ub", C.c_double),
         ("dpa_offset", C.c_double),
@@ -40,18 +43,18 @@ class SnSpec(C.Structure):
         ("dpa_ub", C.c_double),
         ("n_items", C.c_int32),
         ("topology", C.c_int32),
-        ("item_holding_cost", (C.c_double * 4) * 3),
-        ("item_backorder_cost", (C.c_double * 4) * 3),
-        ("supplier", C.c_int32 * 4),
-        ("demand_source", C.c_int32 * 4),
-        ("order_pos", C.c_int32 * 4),
-        ("customer_rank", C.c_int32 * 4),
+        ("item_holding_cost", (C.c_double * MAXF) * 3),
+        ("item_backorder_cost", (C.c_double * MAXF) * 3),
+        ("supplier", C.c_int32 * MAXF),
+        ("demand_source", C.c_int32 * MAXF),
+        ("order_pos", C.c_int32 * MAXF),
+        ("customer_rank", C.c_int32 * MAXF),
     ]
 
 
 class SnPolicy(C.Structure):
     _fields_ = [
-        ("target", C.c_double * 4),
+        ("target", C.c_double * MAXF),
         ("lb", C.c_double),
         ("ub", C.c_double),
         ("rule", C.c_int32),

@@ -9,14 +9,17 @@
 //              policy evaluated in-kernel; optional trajectory out
 //   k_heuristic  BaseStockPolicy on a batch of observations
 // Every env kernel is written against an `Ops` trait: StdOps = the beer game's lead times (tuned,
-// supplynet_core.cuh), GenOps = run-time per-arc lead times (supplynet_generic.cuh).  The device-side
-// VecNormalize kernels live in vecnorm_kernels.cu.
+// supplynet_core.cuh), GenOps = run-time per-arc lead times and shorter chains (supplynet_generic.cuh),
+// TreeOps = distribution trees of up to four nodes (supplynet_tree.cuh).  Trees of five to eight nodes have
+// their own kernels with the env in shared memory (k_net_*, supplynet_net.cuh).  The device-side VecNormalize
+// kernels live in vecnorm_kernels.cu.
 // Row-major float observations ([n_envs][obs_dim], what a VecEnv returns) are staged per warp
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
 // the 112-byte-per-thread pattern reaches L2 as full lines.
+#include "../../include/supplynet.h"
 #include "supplynet_core.cuh"
 #include "supplynet_tree.cuh"
-#include "../../include/supplynet.h"
+#include "supplynet_net.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -497,6 +500,144 @@ __global__ void __maxnreg__(144) k_rollout_wide(SN_ROLLOUT_PARAMS) {
   rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
 }
 
+// ------------------------------------------------------------------------------------------
+// Trees of five to eight nodes (supplynet_net.cuh): env in shared memory, one thread per env; observations leave
+// through a per-warp staging buffer placed behind the env columns in dynamic shared memory.
+#define SN_NET_PROLOGUE                                                                                         \
+  extern __shared__ __align__(16) unsigned char smem_net[];                                                     \
+  const NetEnv<T> e{reinterpret_cast<T*>(smem_net)};                                                            \
+  const int64_t env = (int64_t)blockIdx.x * kNetBlock + threadIdx.x;                                            \
+  const bool valid = env < n;                                                                                   \
+  const int od = 7 * sp.n_obs;                                                                                  \
+  float* const stage = reinterpret_cast<float*>(smem_net + (size_t)kNetSmemWords * sp.nf * kNetBlock * sizeof(T)) + \
+                       (threadIdx.x >> 5) * 32 * od;                                                            \
+  const int64_t warp_env0 = env - (threadIdx.x & 31);                                                           \
+  const int n_valid = (int)(n - warp_env0 < 32 ? (n - warp_env0 > 0 ? n - warp_env0 : 0) : 32)
+
+template <typename T>
+__global__ void __launch_bounds__(kNetBlock)
+k_net_reset(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
+            const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs) {
+  SN_NET_PROLOGUE;
+  if (valid) {
+    net_reset(e, sp, init, ld, env, demand0);
+    net_store(e, sp, state, ld, env);
+  }
+  if (obs != nullptr) net_write_obs(e, sp, false, stage, obs + warp_env0 * od, n_valid);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNetBlock)
+k_net_observe(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
+              float* __restrict__ obs) {
+  SN_NET_PROLOGUE;
+  if (valid) net_load(e, sp, state, ld, env);
+  net_write_obs(e, sp, false, stage, obs + warp_env0 * od, n_valid);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNetBlock)
+k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
+           const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out) {
+  __shared__ double red[(kNetBlock / 32) * 13];
+  SN_NET_PROLOGUE;
+  double reward = 0.0;
+  if (valid) {
+    net_load(e, sp, state, ld, env);
+    const NetPolicy<T> none{};
+    net_orders<SN_POLICY_ACTIONS>(e, sp, none, actions + env * sp.n_agents, nullptr);
+    reward = net_step(e, sp, demand_next, ld, env, terminal != 0, out.cost);
+    net_store(e, sp, state, ld, env);
+    if (out.reward) out.reward[env] = (float)reward;
+    if (out.reward64) out.reward64[env] = reward;
+    if (out.ep_return) out.ep_return[env] += reward;
+  }
+  if (out.obs != nullptr) net_write_obs(e, sp, terminal != 0, stage, out.obs + warp_env0 * od, n_valid);
+  if (out.stats != nullptr) {
+    double v[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) v[i] = 0.0;          // [2..9]: per-facility sums are not kept for these networks
+    v[0] = valid ? 1.0 : 0.0;
+    v[1] = reward;
+    const bool ep = valid && terminal != 0 && out.ep_return != nullptr;
+    const double ret = ep ? out.ep_return[env] : 0.0;
+    v[10] = ep ? 1.0 : 0.0;
+    v[11] = ret;
+    v[12] = ret * ret;
+    block_reduce_add<13, kNetBlock / 32>(v, out.stats, red);
+  }
+}
+
+template <typename T, int POLICY>
+__global__ void __launch_bounds__(kNetBlock)
+k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ NetPolicy<T> pol, int64_t n, int64_t ld,
+              int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
+              const T* __restrict__ actions, const RolloutPtrs out, const T* __restrict__ init,
+              float* __restrict__ obs0) {
+  __shared__ double red[(kNetBlock / 32) * 13];
+  SN_NET_PROLOGUE;
+  const int64_t dstride = ld * sp.n_src, act_stride = n * sp.n_agents;
+  double total = 0.0, ep_total = 0.0;
+  const bool ended = (period0 + n_steps >= sp.t_max);
+  if (init != nullptr) {
+    if (valid) net_reset(e, sp, init, ld, env, demand);
+    if (obs0 != nullptr) net_write_obs(e, sp, false, stage, obs0 + warp_env0 * od, n_valid);
+  } else if (valid) {
+    net_load(e, sp, state, ld, env);
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    const int t = period0 + s;
+    const bool terminal = (t + 1 >= sp.t_max);
+    if (valid) {
+      net_orders<POLICY>(e, sp, pol, POLICY == SN_POLICY_ACTIONS ? actions + (int64_t)s * act_stride + env * sp.n_agents : nullptr,
+                         out.traj_actions != nullptr ? out.traj_actions + (int64_t)s * act_stride + env * sp.n_agents : nullptr);
+      const double r = net_step(e, sp, demand + (int64_t)(t + 1) * dstride, ld, env, terminal, (double*)nullptr);
+      total += r;
+      if (out.traj_reward != nullptr) out.traj_reward[(int64_t)s * n + env] = (float)r;
+    }
+    if (out.traj_obs != nullptr) net_write_obs(e, sp, terminal, stage, out.traj_obs + ((int64_t)s * n + warp_env0) * od, n_valid);
+  }
+  if (out.obs != nullptr) net_write_obs(e, sp, ended, stage, out.obs + warp_env0 * od, n_valid);
+  if (valid) {
+    if (state != nullptr) net_store(e, sp, state, ld, env);
+    ep_total = total;
+    if (out.ep_return) {
+      ep_total = (init != nullptr ? 0.0 : out.ep_return[env]) + total;
+      out.ep_return[env] = ep_total;
+    }
+  }
+  if (out.stats != nullptr) {
+    double v[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) v[i] = 0.0;
+    v[0] = valid ? (double)n_steps : 0.0;
+    v[1] = total;
+    const bool ep = valid && ended && (init != nullptr || out.ep_return != nullptr || period0 == 0);
+    v[10] = ep ? 1.0 : 0.0;
+    v[11] = ep ? ep_total : 0.0;
+    v[12] = ep ? ep_total * ep_total : 0.0;
+    block_reduce_add<13, kNetBlock / 32>(v, out.stats, red);
+  }
+}
+#undef SN_NET_PROLOGUE
+
+// base-stock heuristic for observations of more than four facilities (same arithmetic as k_heuristic, one column at a time)
+__global__ void __launch_bounds__(kBlock)
+k_heuristic_wide(const __grid_constant__ sn_policy pol, int ncols, int64_t n, const float* __restrict__ obs,
+                 float* __restrict__ actions) {
+  const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (env >= n) return;
+  const float* p = obs + (pol.row0_broadcast ? 0 : env * 7 * ncols);
+  for (int c = 0; c < ncols; ++c) {
+    const float* o = p + 7 * c;
+    const float on_order = __fadd_rn(__fadd_rn(__fadd_rn(__ldg(o + 3), __ldg(o + 4)), __ldg(o + 5)), __ldg(o + 6));
+    const float ip = __fsub_rn(__fadd_rn(__ldg(o), on_order), __ldg(o + 1));
+    double q = pol.target[c] - (double)ip;
+    if (pol.rule == SN_RULE_D_PLUS_A) q -= (double)__ldg(o + 2);
+    actions[env * ncols + c] = (float)fmin(fmax(q, pol.lb), pol.ub);
+  }
+}
+
 // BaseStockPolicy.get_order_quantity, ndarray path (utils/heuristics.py:43-57,75), per env.
 // float32 sums of the observation terms, float64 subtraction from the target and clip, as numpy
 // evaluates `int64_targets - (f32 + f32 - f32) [- f32]`.
@@ -558,6 +699,8 @@ bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && st
 
 // the beer game's lead times (envs.py:355-392): tuned kernels; anything else takes the generic path
 bool is_tree(const sn_spec* s) { return s->topology == SN_TOPO_TREE; }
+// trees of five to eight nodes: shared-memory kernels (supplynet_net.cuh)
+bool is_net(const sn_spec* s) { return is_tree(s) && s->n_facilities > SN_MAX_CHAIN; }
 
 bool is_standard(const sn_spec* s) {
   if (s->n_facilities != 4 || is_tree(s)) return false;
@@ -570,8 +713,8 @@ bool is_standard(const sn_spec* s) {
 int validate(const sn_spec* s, int dtype) {
   if (s == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
   if (dtype != SN_I32 && dtype != SN_F32 && dtype != SN_F64) return fail(SN_ERR_INVALID, "unknown dtype %d", dtype);
-  if (s->n_facilities < 1 || s->n_facilities > 4)
-    return fail(SN_ERR_UNSUPPORTED, "serial chains of 1..4 facilities are supported (n_facilities=%d)", s->n_facilities);
+  if (s->n_facilities < 1 || s->n_facilities > (s->topology == SN_TOPO_TREE ? SN_MAX_FACILITIES : SN_MAX_CHAIN))
+    return fail(SN_ERR_UNSUPPORTED, "serial chains of 1..4 facilities and trees of 1..8 nodes are supported (n_facilities=%d)", s->n_facilities);
   for (int k = 0; k < s->n_facilities; ++k) {
     const int li = s->info_leadtime[k], ls = s->ship_leadtime[k];
     if (li < 1 || li > 4 || ls < 1 || ls > 4)
@@ -583,7 +726,7 @@ int validate(const sn_spec* s, int dtype) {
   if (!is_standard(s) && s->n_items > 1)
     return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported for the beer game's chain and lead times only");
   if (s->n_agents < 1 || s->n_agents > s->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
-  int seen = 0, lo = 4, hi = -1;
+  int seen = 0, lo = SN_MAX_FACILITIES, hi = -1;
   for (int i = 0; i < s->n_agents; ++i) {
     const int k = s->agents[i];
     if (k < 0 || k >= s->n_facilities) return fail(SN_ERR_INVALID, "agents[%d]=%d out of range", i, k);
@@ -595,7 +738,7 @@ int validate(const sn_spec* s, int dtype) {
   if (s->topology != SN_TOPO_CHAIN && s->topology != SN_TOPO_TREE) return fail(SN_ERR_INVALID, "unknown topology %d", s->topology);
   if (is_tree(s)) {
     const int nf = s->n_facilities;
-    int pos_seen = 0, n_src = 0, plo = 4, phi = -1;
+    int pos_seen = 0, n_src = 0, plo = SN_MAX_FACILITIES, phi = -1;
     for (int k = 0; k < nf; ++k) {
       const int sup = s->supplier[k], op = s->order_pos[k];
       if (sup != SN_EXTERNAL && (sup < 0 || sup >= nf || sup == k)) return fail(SN_ERR_INVALID, "supplier[%d]=%d out of range", k, sup);
@@ -747,6 +890,87 @@ int lower_policy(const sn_policy* p, const sn_spec* s, int dtype, sn::DevPolicy<
   return SN_OK;
 }
 
+template <typename T>
+sn::NetSpec<T> lower_net(const sn_spec* s) {
+  sn::NetSpec<T> d;
+  std::memset(&d, 0, sizeof(d));
+  const int nf = s->n_facilities;
+  d.nf = nf;
+  d.n_agents = s->n_agents;
+  d.rule = s->rule;
+  d.t_max = s->max_episode_steps;
+  d.big = big_quantity<T>();
+  d.clb = (T)s->coplayer_lb; d.cub = (T)s->coplayer_ub;
+  d.off = (T)s->dpa_offset; d.lb = (T)s->dpa_lb; d.ub = (T)s->dpa_ub;
+  int first_agent_pos = SN_MAX_FACILITIES;
+  for (int i = 0; i < s->n_agents; ++i)
+    first_agent_pos = s->order_pos[s->agents[i]] < first_agent_pos ? s->order_pos[s->agents[i]] : first_agent_pos;
+  for (int k = 0; k < sn::kNF; ++k) {
+    const bool real = k < nf;
+    d.target[k] = real ? (T)s->coplayer_target[k] : T(0);
+    d.h[k] = real ? s->holding_cost[k] : 0.0;
+    d.b[k] = real ? s->backorder_cost[k] : 0.0;
+    d.li[k] = real ? s->info_leadtime[k] : 1;
+    d.ls[k] = real ? s->ship_leadtime[k] : 1;
+    d.sup[k] = real ? s->supplier[k] : -1;
+    d.slot[k] = d.pos[k] = -1;
+    d.src[k] = (real && s->demand_source[k]) ? d.n_src++ : -1;
+    d.pre[k] = real && s->order_pos[k] < first_agent_pos ? 1 : 0;
+  }
+  for (int i = 0; i < s->n_agents; ++i) d.slot[s->agents[i]] = i;
+  if (s->global_observable) {
+    d.n_obs = nf;
+    for (int k = 0; k < nf; ++k) d.pos[k] = k;
+  } else {
+    d.n_obs = s->n_agents;
+    for (int i = 0; i < s->n_agents; ++i) d.pos[s->agents[i]] = i;
+  }
+  // customers of every node in serving order; arcs by rank: a valid serving order for all suppliers at once
+  int n_list = 0, n_seq = 0;
+  for (int j = 0; j < nf; ++j) {
+    d.cust_start[j] = n_list;
+    int best = -1;
+    for (int r = 0; r < nf; ++r)
+      for (int c = 0; c < nf; ++c)
+        if (s->supplier[c] == j && s->customer_rank[c] == r) {
+          d.cust_list[n_list++] = c;
+          if (best < 0 || s->order_pos[c] > s->order_pos[best]) best = c;
+        }
+    d.lat_src[j] = best;
+  }
+  for (int j = nf; j <= sn::kNF; ++j) d.cust_start[j] = n_list;
+  for (int r = 0; r < nf; ++r)
+    for (int c = 0; c < nf; ++c)
+      if ((s->supplier[c] >= 0 ? s->customer_rank[c] : 0) == r) d.fill_seq[n_seq++] = c;
+  return d;
+}
+
+template <typename T>
+int lower_net_policy(const sn_policy* p, const sn_spec* s, int dtype, sn::NetPolicy<T>* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (p == nullptr) return SN_OK;
+  for (int i = 0; i < s->n_agents; ++i) {
+    if (dtype == SN_I32 && !is_integral(p->target[i])) return fail(SN_ERR_TYPE, "policy target[%d] must be integral for SN_I32", i);
+    out->target[s->agents[i]] = (T)p->target[i];
+  }
+  if (dtype == SN_I32 && (!is_integral(p->lb) || !is_integral(p->ub))) return fail(SN_ERR_TYPE, "policy bounds must be integral for SN_I32");
+  out->lb = (T)p->lb; out->ub = (T)p->ub; out->rule = p->rule;
+  return SN_OK;
+}
+
+// dynamic shared memory of the net kernels: the env columns of one block; above 48 KB the kernel must opt in
+template <typename T>
+size_t net_smem(const sn_spec* s) {
+  const int n_obs = s->global_observable ? s->n_facilities : s->n_agents;
+  return (size_t)sn::kNetSmemWords * s->n_facilities * sn::kNetBlock * sizeof(T)       // env columns
+         + (size_t)sn::kNetBlock * 7 * n_obs * sizeof(float);                              // observation staging, per warp
+}
+
+template <typename K>
+void net_opt_in(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 int check_batch(int64_t n, int64_t ld) {
   if (n < 1) return fail(SN_ERR_INVALID, "n_envs=%lld must be >= 1", (long long)n);
   if (ld < n || (ld % 4) != 0) return fail(SN_ERR_INVALID, "ld=%lld must be >= n_envs and a multiple of 4", (long long)ld);
@@ -783,6 +1007,12 @@ inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)(
 template <typename T>
 int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
              float* obs, cudaStream_t st) {
+  if (is_net(spec)) {
+    const size_t smem = net_smem<T>(spec);
+    net_opt_in(sn::k_net_reset<T>, smem);
+    sn::k_net_reset<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs);
+    return cuda_ok("sn_reset launch");
+  }
   const auto d = lower<T>(spec);
 #define SN_CALL(ID, OPS) sn::k_reset<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
@@ -792,6 +1022,12 @@ int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const
 
 template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
+  if (is_net(spec)) {
+    const size_t smem = net_smem<T>(spec);
+    net_opt_in(sn::k_net_observe<T>, smem);
+    sn::k_net_observe<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs);
+    return cuda_ok("sn_observe launch");
+  }
   const auto d = lower<T>(spec);
 #define SN_CALL(ID, OPS) sn::k_observe<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
@@ -802,6 +1038,12 @@ int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, fl
 template <typename T>
 int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
             const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
+  if (is_net(spec)) {
+    const size_t smem = net_smem<T>(spec);
+    net_opt_in(sn::k_net_step<T>, smem);
+    sn::k_net_step<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out);
+    return cuda_ok("sn_step launch");
+  }
   const auto d = lower<T>(spec);
 #define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out, tma_ok(out.obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
@@ -849,6 +1091,23 @@ template <typename T>
 int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period0, int n_steps, void* state,
                const void* demand, int policy_kind, const void* actions, const sn_policy* policy,
                const sn::RolloutPtrs& out, cudaStream_t st, const void* init = nullptr, float* obs0 = nullptr) {
+  if (is_net(spec)) {
+    sn::NetPolicy<T> np;
+    const int nrc = lower_net_policy<T>(policy, spec, dtype, &np);
+    if (nrc != SN_OK) return nrc;
+    const size_t smem = net_smem<T>(spec);
+    const auto nd = lower_net<T>(spec);
+    if (policy_kind == SN_POLICY_ACTIONS) {
+      net_opt_in(sn::k_net_rollout<T, SN_POLICY_ACTIONS>, smem);
+      sn::k_net_rollout<T, SN_POLICY_ACTIONS><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(
+          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, (const T*)init, obs0);
+    } else {
+      net_opt_in(sn::k_net_rollout<T, SN_POLICY_BASE_STOCK>, smem);
+      sn::k_net_rollout<T, SN_POLICY_BASE_STOCK><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(
+          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, (const T*)init, obs0);
+    }
+    return cuda_ok("sn_rollout launch");
+  }
   const auto d = lower<T>(spec);
   sn::DevPolicy<T> p;
   const int rc = lower_policy<T>(policy, spec, dtype, &p);
@@ -872,7 +1131,8 @@ const char* sn_last_error(void) { return g_err; }
 
 int32_t sn_obs_dim(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
-  if (spec->n_facilities < 1 || spec->n_facilities > 4) return fail(SN_ERR_UNSUPPORTED, "n_facilities=%d", spec->n_facilities);
+  if (spec->n_facilities < 1 || spec->n_facilities > (is_tree(spec) ? SN_MAX_FACILITIES : SN_MAX_CHAIN))
+    return fail(SN_ERR_UNSUPPORTED, "n_facilities=%d", spec->n_facilities);
   if (spec->n_agents < 1 || spec->n_agents > spec->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", spec->n_agents);
   return SN_OBS_PER_FACILITY * (spec->global_observable ? spec->n_facilities : spec->n_agents);
 }
@@ -881,12 +1141,12 @@ int32_t sn_spec_validate(const sn_spec* spec, int32_t dtype) { return validate(s
 
 int32_t sn_state_words(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
-  return is_tree(spec) ? SN_TREE_STATE_WORDS : is_standard(spec) ? SN_STATE_WORDS : SN_GEN_STATE_WORDS;
+  return is_net(spec) ? SN_NET_STATE_WORDS : is_tree(spec) ? SN_TREE_STATE_WORDS : is_standard(spec) ? SN_STATE_WORDS : SN_GEN_STATE_WORDS;
 }
 
 int32_t sn_init_words(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
-  return is_standard(spec) ? SN_INIT_WORDS : SN_GEN_INIT_WORDS;
+  return is_net(spec) ? SN_NET_INIT_WORDS : is_standard(spec) ? SN_INIT_WORDS : SN_GEN_INIT_WORDS;
 }
 
 int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const void* init,
@@ -941,11 +1201,12 @@ int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, 
 int32_t sn_heuristic(const sn_policy* policy, int32_t n_cols, int64_t n_envs, const float* obs, float* actions,
                      void* stream) {
   if (!policy || !obs || !actions) return fail(SN_ERR_INVALID, "sn_heuristic: NULL argument");
-  if (n_cols < 1 || n_cols > 4) return fail(SN_ERR_INVALID, "n_cols=%d out of range", n_cols);
+  if (n_cols < 1 || n_cols > SN_MAX_FACILITIES) return fail(SN_ERR_INVALID, "n_cols=%d out of range", n_cols);
   if (n_envs < 1) return fail(SN_ERR_INVALID, "n_envs=%lld must be >= 1", (long long)n_envs);
   if (policy->rule != SN_RULE_A && policy->rule != SN_RULE_D_PLUS_A) return fail(SN_ERR_INVALID, "unknown rule %d", policy->rule);
   if (n_cols == 4 && (!aligned16(obs) || !aligned16(actions))) return fail(SN_ERR_INVALID, "sn_heuristic: obs/actions must be 16-byte aligned");
-  sn::k_heuristic<<<grid_for(n_envs), sn::kBlock, 0, (cudaStream_t)stream>>>(*policy, n_cols, n_envs, obs, actions);
+  if (n_cols > SN_MAX_CHAIN) sn::k_heuristic_wide<<<grid_for(n_envs), sn::kBlock, 0, (cudaStream_t)stream>>>(*policy, n_cols, n_envs, obs, actions);
+  else sn::k_heuristic<<<grid_for(n_envs), sn::kBlock, 0, (cudaStream_t)stream>>>(*policy, n_cols, n_envs, obs, actions);
   return cuda_ok("sn_heuristic launch");
 }
 

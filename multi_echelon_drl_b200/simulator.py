@@ -32,13 +32,13 @@ class BasePolicyParams:
 
     def __init__(self, target_levels, lb=0, ub=16, rule="a", row0_broadcast=False):
         tl = np.asarray(target_levels, dtype=np.float64).reshape(-1)
-        if not 1 <= tl.shape[0] <= 4:
-            raise ValueError("target_levels must have 1..4 entries")
+        if not 1 <= tl.shape[0] <= _lib.MAXF:
+            raise ValueError(f"target_levels must have 1..{_lib.MAXF} entries")
         if rule not in ("a", "d+a"):
             raise ValueError(f"rule must be 'a' or 'd+a', got {rule!r}")
         self.n_cols = tl.shape[0]
         self.c = _lib.SnPolicy()
-        for i in range(4):
+        for i in range(_lib.MAXF):
             self.c.target[i] = float(tl[i]) if i < self.n_cols else 0.0
         self.c.lb, self.c.ub = float(lb), float(ub)
         self.c.rule = _lib.SN_RULE_D_PLUS_A if rule == "d+a" else _lib.SN_RULE_A

@@ -82,10 +82,10 @@ class ScenarioSpec:
 
     def __post_init__(self):
         nf = int(self.n_facilities)
-        if not 1 <= nf <= 4:
-            raise ValueError("n_facilities must be 1..4")
         if self.topology not in ("chain", "tree"):
             raise ValueError(f"topology must be 'chain' or 'tree', got {self.topology!r}")
+        if not 1 <= nf <= (8 if self.topology == "tree" else 4):
+            raise ValueError("n_facilities must be 1..4 (chains) or 1..8 (trees)")
         if self.topology == "tree":
             self._init_tree(nf)
         ag = tuple(self.node_index(a) for a in self.agents)
@@ -137,10 +137,15 @@ class ScenarioSpec:
 
     # ------------------------------------------------------------------ derived
     def node_index(self, name_or_index) -> int:
-        if self.topology == "tree" and isinstance(name_or_index, str):
-            if name_or_index not in self.names:
-                raise ValueError(f"unknown facility {name_or_index!r}; expected one of {self.names}")
-            return self.names.index(name_or_index)
+        if self.topology == "tree":
+            if isinstance(name_or_index, str):
+                if name_or_index not in self.names:
+                    raise ValueError(f"unknown facility {name_or_index!r}; expected one of {self.names}")
+                return self.names.index(name_or_index)
+            k = int(name_or_index)
+            if not 0 <= k < self.n_facilities:
+                raise ValueError(f"facility index {k} out of range")
+            return k
         return node_index(name_or_index)
 
     @property
@@ -208,7 +213,7 @@ class ScenarioSpec:
             s.holding_cost[k] = float(self.holding_cost[k])
             s.backorder_cost[k] = float(self.backorder_cost[k])
             s.coplayer_target[k] = float(self.coplayer_target[k])
-        for k in range(4):
+        for k in range(_lib.MAXF):
             s.agents[k] = self.agents[k] if k < len(self.agents) else 0
         s.n_agents = len(self.agents)
         s.global_observable = int(self.global_observable)
@@ -282,11 +287,11 @@ def tree_spec(nodes, arcs, agent_managed_facilities, global_observable=False, ma
              node-list order;
       arcs   list of (supplier_name, customer_name, info_leadtime, shipment_leadtime) in arc-list order; a supplier
              name that is not a node is the external supplier.
-    Up to four internal nodes, one supplier per node."""
+    Up to eight internal nodes (more than four run on the shared-memory kernels), one supplier per node."""
     names = tuple(n["name"] for n in nodes)
     nf = len(names)
-    if not 1 <= nf <= 4:
-        raise NotImplementedError("kernels hold up to four internal nodes per network")
+    if not 1 <= nf <= 8:
+        raise NotImplementedError("kernels hold up to eight internal nodes per network")
     up = {}
     for (s_name, c_name, li, ls) in arcs:
         if c_name not in names:

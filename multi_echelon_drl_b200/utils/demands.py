@@ -103,6 +103,8 @@ def init_layout(spec: ScenarioSpec):
     times (tuned kernels), 36 words (4 slots per pipeline) for any other lead times (generic kernels)."""
     if spec.standard_leadtimes:
         return INIT_WORDS, _SO_OFF, _SH_OFF
+    if spec.n_facilities > 4:                    # trees of 5..8 nodes: inv[8]; so[k][0..3] at 8+4k; sh[k][0..3] at 40+4k
+        return 72, tuple(8 + 4 * k for k in range(8)), tuple(40 + 4 * k for k in range(8))
     return 36, tuple(4 + 4 * k for k in range(4)), tuple(20 + 4 * k for k in range(4))
 
 
@@ -133,16 +135,17 @@ def bulk_episode_inputs(spec: ScenarioSpec, n: int, rs):
     n_words, so_off, sh_off = init_layout(spec)
     if spec.random_init:
         init = np.zeros((n, n_words), dtype=np.int64)
-        init[:, :4] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, 4))
-        init[:, spec.n_facilities:4] = 0
-        pipe = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, n_words - 4))
+        n_inv = so_off[0]                           # inventory rows: 4, or 8 for trees of more than four nodes
+        init[:, :n_inv] = rs.randint(spec.init_inventory[0], spec.init_inventory[1], (n, n_inv))
+        init[:, spec.n_facilities:n_inv] = 0
+        pipe = rs.randint(spec.init_pipeline[0], spec.init_pipeline[1], (n, n_words - n_inv))
         if not spec.standard_leadtimes:             # slots beyond an arc's lead time (or chain) stay empty
-            mask = np.zeros(n_words - 4, dtype=bool)
+            mask = np.zeros(n_words - n_inv, dtype=bool)
             for k in range(spec.n_facilities):
-                mask[so_off[k] - 4: so_off[k] - 4 + spec.info_leadtime[k]] = True
-                mask[sh_off[k] - 4: sh_off[k] - 4 + spec.ship_leadtime[k]] = True
+                mask[so_off[k] - n_inv: so_off[k] - n_inv + spec.info_leadtime[k]] = True
+                mask[sh_off[k] - n_inv: sh_off[k] - n_inv + spec.ship_leadtime[k]] = True
             pipe = pipe * mask
-        init[:, 4:] = pipe
+        init[:, n_inv:] = pipe
     else:
         init = np.broadcast_to(_fixed_init(spec), (n, n_words)).copy()
     if spec.is_tree:

@@ -174,8 +174,9 @@ class SupplyNetVecEnv(_VecEnvBase):
             sim.demand[:4].fill_(4)
             sim.demand[4:].fill_(8)
         if sp.random_init:
-            fill_uniform(sim.init[:4], sp.init_inventory[0], sp.init_inventory[1])
-            fill_uniform(sim.init[4:], sp.init_pipeline[0], sp.init_pipeline[1])
+            n_inv = 8 if sp.n_facilities > 4 else 4          # inventory rows of the init table (utils/demands.init_layout)
+            fill_uniform(sim.init[:n_inv], sp.init_inventory[0], sp.init_inventory[1])
+            fill_uniform(sim.init[n_inv:], sp.init_pipeline[0], sp.init_pipeline[1])
             # (for non-standard lead times the kernels ignore pipeline slots beyond an arc's lead time)
         else:
             sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=self.device).to(sim.tdtype)[:, None]

@@ -16,6 +16,7 @@ Files written
   leadtimes.npz   serial chains with other per-arc lead times (general-chain path)
   chains.npz      serial chains with 1..3 facilities
   trees.npz       distribution trees (one supplier per node, several customers and / or own demand per node)
+  trees8.npz      the same with five to eight internal nodes (72-word initial-state layout)
 """
 import os
 import sys
@@ -259,6 +260,82 @@ TREE_AGENTS = {   # node indices, caller order; all contiguous in the respective
 }
 
 
+BIG_TREES = {
+    "seven_two_levels": ([("s1", "dc_east", (0, 8), 19, 0.5, 1, 2, 2), ("s2", "dc_east", (0, 5), 13, 0.5, 1, 1, 2),
+                          ("s3", "dc_west", (0, 6), 15, 0.5, 1, 2, 1), ("s4", "dc_west", (0, 3), 9, 0.5, 2, 1, 1),
+                          ("dc_east", "plant", None, 30, 0.25, 1, 2, 2), ("dc_west", "plant", None, 24, 0.25, 1, 1, 3),
+                          ("plant", "EXT", None, 50, 0.125, 1, 1, 2)],
+                         ["plant", "dc_west", "dc_east", "s4", "s1", "s3", "s2"]),
+    "eight_hub": ([("hub", "factory", None, 60, 0.25, 1, 2, 2), ("r1", "hub", (0, 8), 19, 0.5, 1, 2, 2), ("r2", "hub", (0, 6), 14, 0.5, 1, 1, 1),
+                   ("r3", "hub", (0, 4), 10, 0.5, 1, 2, 1), ("r4", "hub", (0, 3), 8, 0.5, 1, 1, 2), ("r5", "hub", (0, 2), 6, 1.0, 1, 3, 1),
+                   ("factory", "EXT", None, 40, 0.125, 1, 1, 2), ("annex", "factory", (0, 5), 12, 0.5, 1, 1, 3)],
+                  ["factory", "annex", "hub", "r3", "r1", "r5", "r2", "r4"]),
+    "five_mixed": ([("kiosk", "shop_b", (0, 3), 8, 0.5, 1, 1, 1), ("shop_a", "dist", (0, 8), 19, 0.5, 1, 2, 2),
+                    ("shop_b", "dist", (0, 5), 16, 0.5, 1, 2, 2), ("dist", "maker", None, 35, 0.5, 1, 2, 2),
+                    ("maker", "EXT", None, 30, 0.5, 1, 1, 2)], ["maker", "dist", "shop_b", "shop_a", "kiosk"]),
+    "six_two_roots": ([("a1", "a_dc", (0, 8), 19, 0.5, 1, 2, 2), ("a2", "a_dc", (0, 4), 10, 0.5, 1, 1, 2), ("a_dc", "EXT", None, 30, 0.5, 1, 1, 2),
+                       ("b1", "b_dc", (0, 6), 15, 0.5, 1, 2, 1), ("b_dc", "b_plant", None, 20, 0.5, 1, 2, 2),
+                       ("b_plant", "EXT", None, 18, 0.5, 1, 1, 3)], ["a_dc", "a2", "a1", "b_plant", "b_dc", "b1"]),
+    "eight_chain": ([("n1", "n2", (0, 8), 19, 0.5, 1, 2, 2), ("n2", "n3", None, 20, 0.5, 1, 2, 2), ("n3", "n4", None, 20, 0.5, 1, 2, 2),
+                     ("n4", "n5", None, 20, 0.5, 1, 1, 2), ("n5", "n6", None, 20, 0.5, 1, 2, 1), ("n6", "n7", None, 20, 0.5, 1, 1, 1),
+                     ("n7", "n8", None, 20, 0.5, 1, 2, 2), ("n8", "EXT", None, 14, 0.5, 1, 1, 2)],
+                    ["n8", "n7", "n6", "n5", "n4", "n3", "n2", "n1"]),
+}
+
+
+def flat_init_net(init):
+    """72 numbers: inv[8]; so[k][0..3] at 8+4k; sh[k][0..3] at 40+4k (layout of the kernels for trees of 5..8 nodes)."""
+    inv0, so, sh, _ = init
+    v = np.zeros(72, dtype=np.int64)
+    v[:len(inv0)] = inv0
+    for k in range(len(inv0)):
+        v[8 + 4 * k: 8 + 4 * k + len(so[k])] = so[k]
+        v[40 + 4 * k: 40 + 4 * k + len(sh[k])] = sh[k]
+    return v
+
+
+def gen_big_trees():
+    """Trees of five to eight internal nodes; agent sets are drawn as contiguous windows of the order sequence."""
+    import json
+    rs = np.random.RandomState(99)
+    out, meta, cid = {}, [], 0
+    for topo, (nodes, arc_order) in BIG_TREES.items():
+        names = [n[0] for n in nodes]
+        byname = {n[0]: n for n in nodes}
+        nd = [dict(name=n[0], target=n[3], holding=n[4], backorder=n[5], demand=n[2]) for n in nodes]
+        arcs = [("external_supplier" if byname[c][1] == "EXT" else byname[c][1], c, byname[c][6], byname[c][7])
+                for c in arc_order]
+        probe = H.make_network_env(nd, arcs, [names[0]], False)
+        seq = [s for s in probe.sn.order_sequence if s != "external_supplier"]
+        N = len(names)
+        windows = [(0, N), (N - 1, 1), (0, 1), (1, 3), (N - 3, 3), (2, N - 2)]
+        for (start, m) in windows:
+            ag = [names.index(s) for s in seq[start:start + m]]
+            if cid % 2:
+                ag = ag[::-1]
+            for glob, rule in ((False, "a"), (True, "d+a")) if (start, m) != (0, N) else ((True, "a"), (False, "d+a")):
+                seed = 3100 + cid
+                env = H.make_network_env(nd, arcs, [names[a] for a in ag], glob,
+                                         dplusa=(-8, 0, 16) if rule == "d+a" else None)
+                acts = rs.randint(-1, 19, (100, len(ag))).astype(np.int64)
+                r = H.network_rollout(env, names, [a for a in acts], seed)
+                inv0, so, sh, dem = r["init"]
+                p = f"b{cid:03d}_"
+                out.update({p + "init": flat_init_net(r["init"]), p + "demand": np.asarray(dem, dtype=np.int64), p + "actions": acts,
+                            p + "obs0": r["obs0"], p + "obs": r["obs"], p + "rew": r["rew"],
+                            p + "holding": r["holding"], p + "backorder": r["backorder"]})
+                meta.append(json.dumps(dict(
+                    cid=cid, topo=topo, names=names, supplier=[-1 if n[1] == "EXT" else names.index(n[1]) for n in nodes],
+                    demand=[list(n[2]) if n[2] else None for n in nodes], target=[n[3] for n in nodes],
+                    holding=[n[4] for n in nodes], backorder=[n[5] for n in nodes], li=[n[6] for n in nodes],
+                    ls=[n[7] for n in nodes], arc_order=[names.index(c) for c in arc_order], agents=[int(a) for a in ag],
+                    glob=glob, rule=rule, seed=seed, order_sequence=seq)))
+                cid += 1
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "trees8.npz"), **out)
+    print("trees of 5..8 nodes:", cid, "cases")
+
+
 def gen_trees():
     import json
     out, meta, cid = {}, [], 0
@@ -303,3 +380,4 @@ if __name__ == "__main__":
     gen_leadtimes()
     gen_short_chains()
     gen_trees()
+    gen_big_trees()

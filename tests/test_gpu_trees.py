@@ -7,7 +7,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from test_oracle_trees import TREE_CASES, tree_oracle_rollout, tree_product_spec  # noqa: E402
+from test_oracle_trees import BIG_TREE_CASES, TREE_CASES, tree_oracle_rollout, tree_product_spec  # noqa: E402
 
 
 def _sim(case, n, dtype="int32"):
@@ -15,21 +15,23 @@ def _sim(case, n, dtype="int32"):
     return BatchedSupplyNetwork(tree_product_spec(case), n, "cuda", dtype)
 
 
-@pytest.mark.parametrize("case", TREE_CASES, ids=[c["id"] for c in TREE_CASES])
+@pytest.mark.parametrize("case", TREE_CASES + BIG_TREE_CASES, ids=[c["id"] for c in TREE_CASES + BIG_TREE_CASES])
 def test_tree_step_and_rollout_match_reference_golden(case):
+    """Up to four nodes: register-resident tree kernels (64 state words); five to eight: shared-memory kernels (128)."""
     sim = _sim(case, 1)
-    assert sim.state_words == 64 and sim.obs_dim == case["obs0"].shape[0]
+    N = len(case["names"])
+    half = 8 if N > 4 else 4                      # rows of the per-facility cost output: holding[half], backorder[half]
+    assert sim.state_words == (128 if N > 4 else 64) and sim.obs_dim == case["obs0"].shape[0]
     sim.load_episode(case["init"][None], case["demand_table"][None])
     assert np.array_equal(sim.reset().cpu().numpy()[0], case["obs0"])
     r64 = torch.zeros(1, dtype=torch.float64, device="cuda")
-    cost = torch.zeros((8, sim.ld), dtype=torch.float64, device="cuda")
-    N = len(case["names"])
+    cost = torch.zeros((2 * half, sim.ld), dtype=torch.float64, device="cuda")
     for t in range(100):
         obs, _, done = sim.step(torch.as_tensor(case["actions"][t][None]), reward64_out=r64, cost_out=cost)
         assert np.array_equal(obs.cpu().numpy()[0], case["obs"][t]), t
         assert r64.item() == case["rew"][t], t
         c = cost[:, 0].cpu().numpy()
-        assert np.array_equal(c[:N], case["ref_holding"][t]) and np.array_equal(c[4:4 + N], case["ref_backorder"][t]), t
+        assert np.array_equal(c[:N], case["ref_holding"][t]) and np.array_equal(c[half:half + N], case["ref_backorder"][t]), t
     assert done
     out = sim.episode(100, actions=torch.as_tensor(case["actions"][:, None, :]), record_obs=True, record_reward=True)
     assert np.array_equal(out["traj_obs"].cpu().numpy()[:, 0], case["obs"])
@@ -37,13 +39,15 @@ def test_tree_step_and_rollout_match_reference_golden(case):
 
 
 @pytest.mark.parametrize("cid,dtype", [(3, "int32"), (20, "int32"), (37, "int32"), (55, "int32"), (70, "int32"), (88, "int32"),
-                                       (37, "float32"), (55, "float64")])
+                                       (37, "float32"), (55, "float64"),
+                                       (1000, "int32"), (1013, "int32"), (1024, "int32"), (1037, "int32"), (1049, "int32"),
+                                       (1001, "float32"), (1024, "float64")])
 def test_tree_batch_vs_oracle(cid, dtype):
     """3,001 envs (ragged) x 100 with bulk-drawn initial states and per-source demand streams: step kernel, fused
     rollout, rollout resumed mid-episode, in-kernel base-stock policy."""
     from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
-    case = TREE_CASES[cid]
+    case = BIG_TREE_CASES[cid - 1000] if cid >= 1000 else TREE_CASES[cid]      # 1000+: five to eight nodes
     n = 3001
     sim = _sim(case, n, dtype)
     init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(cid))
@@ -58,8 +62,10 @@ def test_tree_batch_vs_oracle(cid, dtype):
         from test_oracle_trees import oracle_spec
         orc = NP.TreeOracle(oracle_spec(case), n, dtype=np.float64)
         N = len(case["names"])
-        obs0 = orc.reset(init[:, :N].astype(np.float64), [init[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]].astype(np.float64) for k in range(N)],
-                         [init[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]].astype(np.float64) for k in range(N)], demand)
+        from test_oracle_trees import init_layout
+        _, so0, sh0 = init_layout(N)
+        obs0 = orc.reset(init[:, :N].astype(np.float64), [init[:, so0 + 4 * k: so0 + 4 * k + case["li"][k]].astype(np.float64) for k in range(N)],
+                         [init[:, sh0 + 4 * k: sh0 + 4 * k + case["ls"][k]].astype(np.float64) for k in range(N)], demand)
         obs, rew = [], []
         for t in range(100):
             o, r, _ = orc.step(acts[t]); obs.append(o); rew.append(r)
@@ -184,13 +190,13 @@ def test_single_env_from_yaml_replays_the_reference_episode():
 
 
 def test_random_trees_vs_oracle():
-    """24 random trees (structure, names, arc order, lead times, sources, agent sets, rules): fused episode and
+    """40 random trees, 16 of them with five to eight nodes (structure, names, arc order, lead times, sources, agent sets, rules): fused episode and
     stepwise kernels vs the tree oracle on 257 envs each, bit-exact."""
     from test_oracle_trees import random_tree_case, random_tree_inputs
     from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
     rs = np.random.RandomState(31)
-    for i in range(24):
-        c = random_tree_case(rs)
+    for i in range(40):
+        c = random_tree_case(rs, None if i < 24 else 5 + i % 4)           # the last 16: five to eight nodes
         n = 257
         init, dem, acts = random_tree_inputs(c, n, rs)
         obs0, obs, rew = tree_oracle_rollout(c, init, dem, acts)
@@ -207,3 +213,34 @@ def test_random_trees_vs_oracle():
             for t in range(100):
                 o, _, _ = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
                 assert np.array_equal(o.cpu().numpy(), obs[t]) and np.array_equal(r64.cpu().numpy(), rew[t]), (i, t, c)
+
+
+def test_vecenv_and_heuristic_on_an_eight_node_tree():
+    """hub with five retailers under a factory that also feeds an annex (8 nodes, 6 demand sources): VecEnv with
+    device-drawn episodes, the wide heuristic kernel vs numpy, in-kernel policy episodes vs heuristic + step."""
+    from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    import oracle.beergame_np as O
+    case = BIG_TREE_CASES[[c["topo"] for c in BIG_TREE_CASES].index("eight_hub")]
+    spec = tree_product_spec(dict(case, agents=list(range(8)), glob=True, rule="a"))
+    env = SupplyNetVecEnv(spec, 777, seed=4, dtype="int32")
+    obs = env.reset()
+    assert obs.shape == (777, 56) and env.action_space.shape == (8,) and env.sim.state_words == 128 and env.sim.init_words == 72
+    pol = BasePolicyParams(case["target"], 0, 16, "a")
+    a = heuristic_actions(pol, obs)
+    assert np.array_equal(a.cpu().numpy(), O.base_stock_action(obs.cpu().numpy(), case["target"], 0, 16, "a", n_facilities=8).astype(np.float32))
+    s = env.sim.state[:, :777].to(torch.int64)
+    for k in range(8):                                   # on_order == sum(pipeline) on every arc
+        b = 16 * k
+        assert torch.equal(s[b + 3:b + 7].sum(0), s[b + 7:b + 10].sum(0) + s[b + 10:b + 14].sum(0) + s[b + 14])
+    total = torch.zeros(777, dtype=torch.float64, device="cuda")
+    for _ in range(100):
+        obs, rew, dones, infos = env.step(heuristic_actions(pol, obs))
+        total += rew.double()
+    assert dones.all() and torch.equal(infos.episode_return, total)
+    stepped = total.clone()
+    env.sim.episode(100, policy=pol, write_state=False)            # same episode tables: the auto-reset drew new ones
+    stats = env.run_policy_episodes(pol, n_episodes=2).cpu().numpy()
+    assert stats[0] == 2 * 777 * 100 and stats[10] == 2 * 777 and stats[11] < 0 and stats[11] == stats[1]
+    assert not stats[2:10].any()                                    # per-facility sums are not kept for these networks
+    assert (stepped < 0).all()

@@ -229,8 +229,8 @@ def test_multi_item_spec_combination_rules():
     c = combine_item_specs([a, b])
     assert c.n_items == 2 and c.extra_item_costs == (((0.75,) * 4, (2.0,) * 4),)
     cs = c.to_c()
-    assert cs.n_items == 2 and list(cs.item_holding_cost[0]) == [0.75] * 4 and list(cs.item_backorder_cost[0]) == [2.0] * 4
-    assert list(cs.holding_cost) == [0.5] * 4
+    assert cs.n_items == 2 and list(cs.item_holding_cost[0])[:4] == [0.75] * 4 and list(cs.item_backorder_cost[0])[:4] == [2.0] * 4
+    assert list(cs.holding_cost)[:4] == [0.5] * 4 and list(cs.holding_cost)[4:] == [0.0] * 4       # arrays are 8 wide (ABI v7)
     with pytest.raises(ValueError):
         combine_item_specs([a, replace(a, coplayer_target=(1, 2, 3, 4))])       # only costs may differ
     with pytest.raises(ValueError):
@@ -246,9 +246,10 @@ def test_spec_lowering_to_c_struct_roundtrip():
     s = s.with_rule("d+a", -10, 0, 20)
     c = s.to_c()
     assert (c.n_facilities, c.n_agents, list(c.agents)[:2], c.global_observable, c.max_episode_steps, c.rule) == (4, 2, [1, 0], 1, 50, 1)
-    assert list(c.info_leadtime) == [1, 2, 3, 1] and list(c.ship_leadtime) == [4, 3, 2, 2]
-    assert list(c.holding_cost) == [1.0, 0.75, 0.5, 0.25] and list(c.backorder_cost) == [10.0, 0, 0, 0]
-    assert list(c.coplayer_target) == [48, 43, 41, 30] and (c.coplayer_lb, c.coplayer_ub) == (0.0, 16.0)
+    assert list(c.info_leadtime)[:4] == [1, 2, 3, 1] and list(c.ship_leadtime)[:4] == [4, 3, 2, 2]
+    assert list(c.holding_cost)[:4] == [1.0, 0.75, 0.5, 0.25] and list(c.backorder_cost)[:4] == [10.0, 0, 0, 0]
+    assert list(c.coplayer_target)[:4] == [48, 43, 41, 30] and (c.coplayer_lb, c.coplayer_ub) == (0.0, 16.0)
+    assert len(c.info_leadtime) == 8 and not any(list(c.info_leadtime)[4:])
     assert (c.dpa_offset, c.dpa_lb, c.dpa_ub) == (-10.0, 0.0, 20.0) and c.n_items == 1
     assert s.obs_dim == 28 and s.obs_nodes == (0, 1, 2, 3) and not s.standard_leadtimes
     with pytest.raises(ValueError):

@@ -12,12 +12,12 @@ from oracle.network_np import EXTERNAL, TreeOracle, TreeSpec
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _cases():
-    z = np.load(f"{GOLDEN}/trees.npz")
+def _cases(fname="trees.npz", prefix="t"):
+    z = np.load(f"{GOLDEN}/{fname}")
     out = []
     for m in z["meta"]:
         c = json.loads(str(m))
-        p = f"t{c['cid']:03d}_"
+        p = f"{prefix}{c['cid']:03d}_"
         c["id"] = f"{c['topo']}-ag{''.join(map(str, c['agents']))}-g{int(c['glob'])}-{c['rule']}"
         for k in ("init", "actions", "obs0", "obs", "rew"):
             c[k] = z[p + k]
@@ -28,6 +28,12 @@ def _cases():
 
 
 TREE_CASES = _cases()
+BIG_TREE_CASES = _cases("trees8.npz", "b")             # five to eight internal nodes, 72-word initial-state layout
+
+
+def init_layout(n_nodes):
+    """(inventory rows, first sales-order row, first shipment row) of the init table: 36 words up to four nodes, 72 beyond."""
+    return (8, 8, 40) if n_nodes > 4 else (4, 4, 20)
 
 
 def oracle_spec(case) -> TreeSpec:
@@ -38,12 +44,13 @@ def oracle_spec(case) -> TreeSpec:
 
 
 def tree_oracle_rollout(case, init36, demand, actions, return_costs=False):
-    """init36 [n, 36] (inv[4], so[k][0..3], sh[k][0..3] by node); demand [n, n_sources, T+3]; actions [T, n, n_agents]."""
+    """init36 [n, 36 | 72] (inv, so[k][0..3], sh[k][0..3] by node); demand [n, n_sources, T+3]; actions [T, n, n_agents]."""
     spec = oracle_spec(case)
     n, N = init36.shape[0], len(case["names"])
     orc = TreeOracle(spec, n)
-    so = [init36[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] for k in range(N)]
-    sh = [init36[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] for k in range(N)]
+    _, so0, sh0 = init_layout(N)
+    so = [init36[:, so0 + 4 * k: so0 + 4 * k + case["li"][k]] for k in range(N)]
+    sh = [init36[:, sh0 + 4 * k: sh0 + 4 * k + case["ls"][k]] for k in range(N)]
     obs0 = orc.reset(init36[:, :N], so, sh, demand)
     obs, rew, hold, back = [], [], [], []
     for t in range(actions.shape[0]):
@@ -55,7 +62,7 @@ def tree_oracle_rollout(case, init36, demand, actions, return_costs=False):
     return obs0, np.stack(obs), np.stack(rew)
 
 
-@pytest.mark.parametrize("case", TREE_CASES, ids=[c["id"] for c in TREE_CASES])
+@pytest.mark.parametrize("case", TREE_CASES + BIG_TREE_CASES, ids=[c["id"] for c in TREE_CASES + BIG_TREE_CASES])
 def test_tree_oracle_matches_reference_golden(case):
     obs0, obs, rew, hold, back = tree_oracle_rollout(case, case["init"][None], case["demand_table"][None],
                                                      case["actions"][:, None, :], return_costs=True)
@@ -151,17 +158,19 @@ def test_product_tree_specs_order_sequence_streams_and_c_validation():
     from multi_echelon_drl_b200 import _lib
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs, seeded_episode_inputs
     lib = _lib.load()
-    for c in TREE_CASES:
+    for c in TREE_CASES + BIG_TREE_CASES:
         sp = tree_product_spec(c)
+        big = len(c["names"]) > 4
         assert list(sp.order_sequence) == c["order_sequence"], c["id"]
         init, dem = seeded_episode_inputs(sp, [c["seed"]])
         assert np.array_equal(init[0], c["init"]) and np.array_equal(dem[0], c["demand_table"]), c["id"]
         cs = sp.to_c()
         assert lib.sn_spec_validate(C.byref(cs), _lib.SN_I32) == 0, lib.sn_last_error()
-        assert lib.sn_state_words(C.byref(cs)) == 64 and lib.sn_init_words(C.byref(cs)) == 36
+        assert lib.sn_state_words(C.byref(cs)) == (128 if big else 64) and lib.sn_init_words(C.byref(cs)) == (72 if big else 36)
         assert lib.sn_obs_dim(C.byref(cs)) == c["obs0"].shape[0] == sp.obs_dim
         binit, bdem = bulk_episode_inputs(sp, 16, np.random.RandomState(0))
-        assert binit.shape == (16, 36) and bdem.shape == (16, sp.n_sources, 103)
+        assert binit.shape == (16, 72 if big else 36) and bdem.shape == (16, sp.n_sources, 103)
+        assert not binit[:, len(c["names"]):init_layout(len(c["names"]))[0]].any()
         for s, k in enumerate(sp.source_nodes):
             assert bdem[:, s].max() <= c["demand"][k][1]
 
@@ -225,7 +234,7 @@ def random_tree_case(rs, n_nodes=None):
     sequence), arc-list order (priority among customers), lead times with info + shipment <= 5, demand sources at
     the leaves and sometimes elsewhere, and an agent set that is contiguous in the resulting order sequence."""
     from oracle.network_np import order_sequence
-    N = int(n_nodes or rs.randint(2, 5))
+    N = int(n_nodes or rs.randint(2, 5))           # pass n_nodes for the larger ones (5..8)
     pool = ["alpha", "bravo", "charlie", "delta", "echo", "foxtrot", "golf", "hotel"]
     names = list(rs.choice(pool, N, replace=False))
     supplier = [EXTERNAL] * N
@@ -254,11 +263,12 @@ def random_tree_case(rs, n_nodes=None):
 
 def random_tree_inputs(case, n, rs):
     N = len(case["names"])
-    init = np.zeros((n, 36), dtype=np.int64)
+    _, so0, sh0 = init_layout(N)
+    init = np.zeros((n, 72 if N > 4 else 36), dtype=np.int64)
     init[:, :N] = rs.randint(0, 25, (n, N))
     for k in range(N):
-        init[:, 4 + 4 * k: 4 + 4 * k + case["li"][k]] = rs.randint(0, 9, (n, case["li"][k]))
-        init[:, 20 + 4 * k: 20 + 4 * k + case["ls"][k]] = rs.randint(0, 9, (n, case["ls"][k]))
+        init[:, so0 + 4 * k: so0 + 4 * k + case["li"][k]] = rs.randint(0, 9, (n, case["li"][k]))
+        init[:, sh0 + 4 * k: sh0 + 4 * k + case["ls"][k]] = rs.randint(0, 9, (n, case["ls"][k]))
     dem = np.stack([rs.randint(d[0], d[1] + 1, (n, 103)) for d in case["demand"] if d is not None], axis=1)
     acts = rs.randint(-1, 19, (100, n, len(case["agents"])))
     return init, dem, acts
@@ -267,12 +277,12 @@ def random_tree_inputs(case, n, rs):
 @pytest.mark.skipif(not __import__("oracle.ref_harness", fromlist=["x"]).reference_available(),
                     reason="/root/reference not mounted (GPU box)")
 def test_random_trees_vs_live_reference():
-    """40 random trees: the restatement and the reference's own classes agree on every observation, reward and
+    """56 random trees (16 of them with five to eight nodes): the restatement and the reference's own classes agree on every observation, reward and
     per-node cost, and on the order sequence."""
     from oracle import ref_harness as H
     rs = np.random.RandomState(2024)
-    for i in range(40):
-        c = random_tree_case(rs)
+    for i in range(56):
+        c = random_tree_case(rs, None if i < 40 else 5 + i % 4)          # the last 16: five to eight nodes
         names = c["names"]
         nd = [dict(name=names[k], target=c["target"][k], holding=c["holding"][k], backorder=c["backorder"][k],
                    demand=c["demand"][k]) for k in range(len(names))]
@@ -284,11 +294,12 @@ def test_random_trees_vs_live_reference():
         r = H.network_rollout(env, names, [a for a in acts], seed=7000 + i)
         assert [s for s in r["order_sequence"] if s != "external_supplier"] == c["order_sequence"], (i, c)
         inv0, so, sh, dem = r["init"]
-        init = np.zeros(36, dtype=np.int64)
+        _, so0, sh0 = init_layout(len(inv0))
+        init = np.zeros(72 if len(inv0) > 4 else 36, dtype=np.int64)
         init[:len(inv0)] = inv0
         for k in range(len(inv0)):
-            init[4 + 4 * k: 4 + 4 * k + len(so[k])] = so[k]
-            init[20 + 4 * k: 20 + 4 * k + len(sh[k])] = sh[k]
+            init[so0 + 4 * k: so0 + 4 * k + len(so[k])] = so[k]
+            init[sh0 + 4 * k: sh0 + 4 * k + len(sh[k])] = sh[k]
         o0, obs, rew, hold, back = tree_oracle_rollout(c, init[None], np.asarray(dem)[None], acts[:, None, :], return_costs=True)
         assert np.array_equal(o0[0], r["obs0"]), (i, c)
         assert np.array_equal(obs[:, 0], r["obs"]) and np.array_equal(rew[:, 0], r["rew"]), (i, c)
@@ -302,8 +313,8 @@ def test_random_tree_specs_lower_consistently():
     from multi_echelon_drl_b200 import _lib
     lib = _lib.load()
     rs = np.random.RandomState(77)
-    for i in range(60):
-        c = random_tree_case(rs)
+    for i in range(80):
+        c = random_tree_case(rs, None if i < 60 else 5 + i % 4)
         sp = tree_product_spec(c)
         assert list(sp.order_sequence) == c["order_sequence"], c
         cs = sp.to_c()
@@ -312,8 +323,9 @@ def test_random_tree_specs_lower_consistently():
             init, dem, acts = random_tree_inputs(c, 8, rs)
             orc = TreeOracle(oracle_spec(c), 8)
             N = len(c["names"])
-            orc.reset(init[:, :N], [init[:, 4 + 4 * k: 4 + 4 * k + c["li"][k]] for k in range(N)],
-                      [init[:, 20 + 4 * k: 20 + 4 * k + c["ls"][k]] for k in range(N)], dem)
+            _, so0, sh0 = init_layout(N)
+            orc.reset(init[:, :N], [init[:, so0 + 4 * k: so0 + 4 * k + c["li"][k]] for k in range(N)],
+                      [init[:, sh0 + 4 * k: sh0 + 4 * k + c["ls"][k]] for k in range(N)], dem)
             for t in range(100):
                 orc.step(acts[t])
                 orc.check_invariant()
