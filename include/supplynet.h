@@ -96,8 +96,8 @@ typedef struct sn_spec {
    * per demand source and period, sources in node order: demand [T+3][n_sources][ld], demand0 / demand_next
    * [n_sources][ld].  Multi-supplier (assembly) nodes are not supported: the reference's own state keys collide
    * there (supplynetwork.py:165-167).
-   * Trees of up to four nodes run on register-resident kernels (SN_TREE_STATE_WORDS); trees of five to eight nodes on
-   * kernels that keep the env in shared memory and index the topology directly (SN_NET_STATE_WORDS / SN_NET_INIT_WORDS,
+   * Trees of up to four nodes run on one-thread-per-env kernels (SN_TREE_STATE_WORDS); trees of five to eight nodes on
+   * kernels that give every node a lane of its own, eight lanes per env (SN_NET_STATE_WORDS / SN_NET_INIT_WORDS,
    * observation 7 floats per node, up to 8 action columns, `cost` [16][ld]: holding[0..7], backorder[8..15]; the
    * per-facility sums [2..9] of the statistics vector stay zero there). */
   int32_t supplier[SN_MAX_FACILITIES];        /* supplier node of node k, SN_EXTERNAL = the external supplier   */

@@ -25,6 +25,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 namespace sn {
 
@@ -501,29 +502,31 @@ __global__ void __maxnreg__(144) k_rollout_wide(SN_ROLLOUT_PARAMS) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Trees of five to eight nodes (supplynet_net.cuh): env in shared memory, one thread per env; observations leave
-// through a per-warp staging buffer placed behind the env columns in dynamic shared memory.
-#define SN_NET_PROLOGUE                                                                                         \
-  extern __shared__ __align__(16) unsigned char smem_net[];                                                     \
-  const NetEnv<T> e{reinterpret_cast<T*>(smem_net)};                                                            \
-  const int64_t env = (int64_t)blockIdx.x * kNetBlock + threadIdx.x;                                            \
-  const bool valid = env < n;                                                                                   \
-  const int od = 7 * sp.n_obs;                                                                                  \
-  float* const stage = reinterpret_cast<float*>(smem_net + (size_t)kNetSmemWords * sp.nf * kNetBlock * sizeof(T)) + \
-                       (threadIdx.x >> 5) * 32 * od;                                                            \
-  const int64_t warp_env0 = env - (threadIdx.x & 31);                                                           \
-  const int n_valid = (int)(n - warp_env0 < 32 ? (n - warp_env0 > 0 ? n - warp_env0 : 0) : 32)
+// Trees of five to eight nodes (supplynet_net.cuh): one lane per node, four envs per warp, 16 envs per block.
+#define SN_NET_PROLOGUE                                                                                        \
+  __shared__ float stage_all[(kNetBlock / 32) * kNetEnvsPerWarp * 7 * kNF];                                    \
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                                  \
+  const int64_t warp_env0 = ((int64_t)blockIdx.x * (kNetBlock / 32) + warp) * kNetEnvsPerWarp;                 \
+  const int64_t env = warp_env0 + (lane >> 3);                                                                 \
+  const bool valid = env < n;                                                                                  \
+  const int od = 7 * sp.n_obs;                                                                                 \
+  float* const stage = stage_all + warp * (kNetEnvsPerWarp * 7 * kNF);                                         \
+  const int n_valid = (int)(n - warp_env0 < kNetEnvsPerWarp ? (n - warp_env0 > 0 ? n - warp_env0 : 0) : kNetEnvsPerWarp)
 
 template <typename T>
 __global__ void __launch_bounds__(kNetBlock)
 k_net_reset(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
             const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs) {
   SN_NET_PROLOGUE;
-  if (valid) {
-    net_reset(e, sp, init, ld, env, demand0);
-    net_store(e, sp, state, ld, env);
+  const NetPolicy<T> none{};
+  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  LaneEnv<T> e;
+  lane_reset(e, c, init, ld, env, demand0);
+  lane_store(e, c, state, ld, env);
+  if (obs != nullptr) {
+    const T cb = group_sum(e.B, c.cust, c.base);
+    lane_write_obs(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
   }
-  if (obs != nullptr) net_write_obs(e, sp, false, stage, obs + warp_env0 * od, n_valid);
 }
 
 template <typename T>
@@ -531,8 +534,12 @@ __global__ void __launch_bounds__(kNetBlock)
 k_net_observe(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
               float* __restrict__ obs) {
   SN_NET_PROLOGUE;
-  if (valid) net_load(e, sp, state, ld, env);
-  net_write_obs(e, sp, false, stage, obs + warp_env0 * od, n_valid);
+  const NetPolicy<T> none{};
+  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  LaneEnv<T> e;
+  lane_load(e, c, state, ld, env);
+  const T cb = group_sum(e.B, c.cust, c.base);
+  lane_write_obs(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
 }
 
 template <typename T>
@@ -541,25 +548,38 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int ter
            const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out) {
   __shared__ double red[(kNetBlock / 32) * 13];
   SN_NET_PROLOGUE;
-  double reward = 0.0;
-  if (valid) {
-    net_load(e, sp, state, ld, env);
-    const NetPolicy<T> none{};
-    net_orders<SN_POLICY_ACTIONS>(e, sp, none, actions + env * sp.n_agents, nullptr);
-    reward = net_step(e, sp, demand_next, ld, env, terminal != 0, out.cost);
-    net_store(e, sp, state, ld, env);
+  const NetPolicy<T> none{};
+  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  LaneEnv<T> e;
+  lane_load(e, c, state, ld, env);
+  T bj[kNF];
+  group_all(e.B, c.base, bj);
+  const T a = (c.active && c.slot >= 0) ? __ldg(actions + env * sp.n_agents + c.slot) : T(0);
+  T taken;
+  const T q = lane_order<SN_POLICY_ACTIONS>(e, c, sp, none, masked_sum(bj, c.cust), a, taken);
+  double hold, back;
+  lane_step(e, c, sp, q, lane_demand(c, demand_next, ld, env), terminal != 0, bj, hold, back);
+  const double reward = group_reward(hold, back, c.base, sp.exact_costs != 0);
+  const T cb = masked_sum(bj, c.cust);
+  lane_store(e, c, state, ld, env);
+  const bool head = valid && c.k == 0;                 // one lane per env reports
+  if (c.active && out.cost) {
+    out.cost[(int64_t)c.k * ld + env] = hold;
+    out.cost[(int64_t)(kNF + c.k) * ld + env] = back;
+  }
+  if (head) {
     if (out.reward) out.reward[env] = (float)reward;
     if (out.reward64) out.reward64[env] = reward;
     if (out.ep_return) out.ep_return[env] += reward;
   }
-  if (out.obs != nullptr) net_write_obs(e, sp, terminal != 0, stage, out.obs + warp_env0 * od, n_valid);
+  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, terminal != 0, stage, out.obs + warp_env0 * od, n_valid);
   if (out.stats != nullptr) {
     double v[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) v[i] = 0.0;          // [2..9]: per-facility sums are not kept for these networks
-    v[0] = valid ? 1.0 : 0.0;
-    v[1] = reward;
-    const bool ep = valid && terminal != 0 && out.ep_return != nullptr;
+    v[0] = head ? 1.0 : 0.0;
+    v[1] = head ? reward : 0.0;
+    const bool ep = head && terminal != 0 && out.ep_return != nullptr;
     const double ret = ep ? out.ep_return[env] : 0.0;
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ret;
@@ -576,43 +596,58 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
               float* __restrict__ obs0) {
   __shared__ double red[(kNetBlock / 32) * 13];
   SN_NET_PROLOGUE;
+  const LaneCfg<T> c = lane_cfg(sp, pol, valid);
   const int64_t dstride = ld * sp.n_src, act_stride = n * sp.n_agents;
-  double total = 0.0, ep_total = 0.0;
-  const bool ended = (period0 + n_steps >= sp.t_max);
-  if (init != nullptr) {
-    if (valid) net_reset(e, sp, init, ld, env, demand);
-    if (obs0 != nullptr) net_write_obs(e, sp, false, stage, obs0 + warp_env0 * od, n_valid);
-  } else if (valid) {
-    net_load(e, sp, state, ld, env);
-  }
+  const bool head = valid && c.k == 0;
+  const bool acts = POLICY == SN_POLICY_ACTIONS && c.active && c.slot >= 0;
+  const int64_t act_off = env * sp.n_agents + c.slot;
+  LaneEnv<T> e;
+  T bj[kNF];                                   // backlog of the eight upstream arcs of this env (same copy in every lane)
+  if (init != nullptr) lane_reset(e, c, init, ld, env, demand);
+  else lane_load(e, c, state, ld, env);
+  group_all(e.B, c.base, bj);
+  T cb = masked_sum(bj, c.cust);
+  if (init != nullptr && obs0 != nullptr) lane_write_obs(e, c, sp, cb, false, stage, obs0 + warp_env0 * od, n_valid);
+  double total = 0.0;
+  // inputs of the next period are requested before this one is computed
+  T a_pre = acts ? __ldg(actions + act_off) : T(0);
+  T d_pre = lane_demand(c, demand + (int64_t)(period0 + 1) * dstride, ld, env);
   for (int s = 0; s < n_steps; ++s) {
     const int t = period0 + s;
     const bool terminal = (t + 1 >= sp.t_max);
-    if (valid) {
-      net_orders<POLICY>(e, sp, pol, POLICY == SN_POLICY_ACTIONS ? actions + (int64_t)s * act_stride + env * sp.n_agents : nullptr,
-                         out.traj_actions != nullptr ? out.traj_actions + (int64_t)s * act_stride + env * sp.n_agents : nullptr);
-      const double r = net_step(e, sp, demand + (int64_t)(t + 1) * dstride, ld, env, terminal, (double*)nullptr);
-      total += r;
-      if (out.traj_reward != nullptr) out.traj_reward[(int64_t)s * n + env] = (float)r;
+    const T a = a_pre, dn = d_pre;
+    if (s + 1 < n_steps) {
+      if (acts) a_pre = __ldg(actions + (int64_t)(s + 1) * act_stride + act_off);
+      d_pre = lane_demand(c, demand + (int64_t)(t + 2) * dstride, ld, env);
     }
-    if (out.traj_obs != nullptr) net_write_obs(e, sp, terminal, stage, out.traj_obs + ((int64_t)s * n + warp_env0) * od, n_valid);
+    T taken = T(0);
+    const T q = lane_order<POLICY>(e, c, sp, pol, cb, a, taken);
+    if (out.traj_actions != nullptr && c.active && c.slot >= 0)
+      out.traj_actions[(int64_t)s * act_stride + act_off] = (float)taken;
+    double hold, back;
+    lane_step(e, c, sp, q, dn, terminal, bj, hold, back);
+    cb = masked_sum(bj, c.cust);
+    const double r = group_reward(hold, back, c.base, sp.exact_costs != 0);
+    total += r;
+    if (out.traj_reward != nullptr && head) out.traj_reward[(int64_t)s * n + env] = (float)r;
+    if (out.traj_obs != nullptr)
+      lane_write_obs(e, c, sp, cb, terminal, stage, out.traj_obs + ((int64_t)s * n + warp_env0) * od, n_valid);
   }
-  if (out.obs != nullptr) net_write_obs(e, sp, ended, stage, out.obs + warp_env0 * od, n_valid);
-  if (valid) {
-    if (state != nullptr) net_store(e, sp, state, ld, env);
-    ep_total = total;
-    if (out.ep_return) {
-      ep_total = (init != nullptr ? 0.0 : out.ep_return[env]) + total;
-      out.ep_return[env] = ep_total;
-    }
+  const bool ended = (period0 + n_steps >= sp.t_max);
+  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, ended, stage, out.obs + warp_env0 * od, n_valid);
+  if (state != nullptr) lane_store(e, c, state, ld, env);
+  double ep_total = total;
+  if (head && out.ep_return) {
+    ep_total = (init != nullptr ? 0.0 : out.ep_return[env]) + total;
+    out.ep_return[env] = ep_total;
   }
   if (out.stats != nullptr) {
     double v[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) v[i] = 0.0;
-    v[0] = valid ? (double)n_steps : 0.0;
-    v[1] = total;
-    const bool ep = valid && ended && (init != nullptr || out.ep_return != nullptr || period0 == 0);
+    v[0] = head ? (double)n_steps : 0.0;
+    v[1] = head ? total : 0.0;
+    const bool ep = head && ended && (init != nullptr || out.ep_return != nullptr || period0 == 0);
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ep ? ep_total : 0.0;
     v[12] = ep ? ep_total * ep_total : 0.0;
@@ -925,23 +960,24 @@ sn::NetSpec<T> lower_net(const sn_spec* s) {
     d.n_obs = s->n_agents;
     for (int i = 0; i < s->n_agents; ++i) d.pos[s->agents[i]] = i;
   }
-  // customers of every node in serving order; arcs by rank: a valid serving order for all suppliers at once
-  int n_list = 0, n_seq = 0;
-  for (int j = 0; j < nf; ++j) {
-    d.cust_start[j] = n_list;
-    int best = -1;
-    for (int r = 0; r < nf; ++r)
-      for (int c = 0; c < nf; ++c)
-        if (s->supplier[c] == j && s->customer_rank[c] == r) {
-          d.cust_list[n_list++] = c;
-          if (best < 0 || s->order_pos[c] > s->order_pos[best]) best = c;
-        }
-    d.lat_src[j] = best;
+  // integer quantities and cost coefficients on a 2^-10 grid: every cost term and partial sum is exact in double
+  d.exact_costs = std::is_same<T, int32_t>::value ? 1 : 0;
+  for (int k = 0; k < nf; ++k) {
+    const double hs = s->holding_cost[k] * 1024.0, bs = s->backorder_cost[k] * 1024.0;
+    if (!(std::fabs(hs) < 1e9 && std::fabs(bs) < 1e9 && std::floor(hs) == hs && std::floor(bs) == bs)) d.exact_costs = 0;
   }
-  for (int j = nf; j <= sn::kNF; ++j) d.cust_start[j] = n_list;
-  for (int r = 0; r < nf; ++r)
-    for (int c = 0; c < nf; ++c)
-      if ((s->supplier[c] >= 0 ? s->customer_rank[c] : 0) == r) d.fill_seq[n_seq++] = c;
+  for (int k = 0; k < nf; ++k) {
+    int best = -1;
+    for (int c = 0; c < nf; ++c) {
+      if (s->supplier[c] == k) {                          // c is a customer of k
+        d.cust[k] |= 1u << c;
+        if (best < 0 || s->order_pos[c] > s->order_pos[best]) best = c;
+      }
+      if (c != k && s->supplier[k] >= 0 && s->supplier[c] == s->supplier[k] && s->customer_rank[c] < s->customer_rank[k])
+        d.before[k] |= 1u << c;                           // served before k by the same supplier
+    }
+    d.lat_src[k] = best;                                  // the customer latest in the order sequence (supplynetwork.py:193)
+  }
   return d;
 }
 
@@ -956,19 +992,6 @@ int lower_net_policy(const sn_policy* p, const sn_spec* s, int dtype, sn::NetPol
   if (dtype == SN_I32 && (!is_integral(p->lb) || !is_integral(p->ub))) return fail(SN_ERR_TYPE, "policy bounds must be integral for SN_I32");
   out->lb = (T)p->lb; out->ub = (T)p->ub; out->rule = p->rule;
   return SN_OK;
-}
-
-// dynamic shared memory of the net kernels: the env columns of one block; above 48 KB the kernel must opt in
-template <typename T>
-size_t net_smem(const sn_spec* s) {
-  const int n_obs = s->global_observable ? s->n_facilities : s->n_agents;
-  return (size_t)sn::kNetSmemWords * s->n_facilities * sn::kNetBlock * sizeof(T)       // env columns
-         + (size_t)sn::kNetBlock * 7 * n_obs * sizeof(float);                              // observation staging, per warp
-}
-
-template <typename K>
-void net_opt_in(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 int check_batch(int64_t n, int64_t ld) {
@@ -993,6 +1016,8 @@ constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * 28 * sizeof(float);   
 constexpr size_t kRolloutSmem = (sn::kRolloutBlock / 32) * 2 * 32 * 28 * sizeof(float);         // 14,336 B
 
 inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)((n + block - 1) / block); }
+// net kernels: eight lanes per env
+inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetBlock - 1) / sn::kNetBlock); }
 
 // launch with <IDENT, Ops> chosen from the spec: tuned standard kernels (identity specialised or not)
 // or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
@@ -1008,9 +1033,7 @@ template <typename T>
 int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
              float* obs, cudaStream_t st) {
   if (is_net(spec)) {
-    const size_t smem = net_smem<T>(spec);
-    net_opt_in(sn::k_net_reset<T>, smem);
-    sn::k_net_reset<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs);
+    sn::k_net_reset<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs);
     return cuda_ok("sn_reset launch");
   }
   const auto d = lower<T>(spec);
@@ -1023,9 +1046,7 @@ int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const
 template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
   if (is_net(spec)) {
-    const size_t smem = net_smem<T>(spec);
-    net_opt_in(sn::k_net_observe<T>, smem);
-    sn::k_net_observe<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs);
+    sn::k_net_observe<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs);
     return cuda_ok("sn_observe launch");
   }
   const auto d = lower<T>(spec);
@@ -1039,9 +1060,7 @@ template <typename T>
 int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
             const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
   if (is_net(spec)) {
-    const size_t smem = net_smem<T>(spec);
-    net_opt_in(sn::k_net_step<T>, smem);
-    sn::k_net_step<T><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(lower_net<T>(spec), n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out);
+    sn::k_net_step<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out);
     return cuda_ok("sn_step launch");
   }
   const auto d = lower<T>(spec);
@@ -1095,15 +1114,12 @@ int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period
     sn::NetPolicy<T> np;
     const int nrc = lower_net_policy<T>(policy, spec, dtype, &np);
     if (nrc != SN_OK) return nrc;
-    const size_t smem = net_smem<T>(spec);
     const auto nd = lower_net<T>(spec);
     if (policy_kind == SN_POLICY_ACTIONS) {
-      net_opt_in(sn::k_net_rollout<T, SN_POLICY_ACTIONS>, smem);
-      sn::k_net_rollout<T, SN_POLICY_ACTIONS><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(
+      sn::k_net_rollout<T, SN_POLICY_ACTIONS><<<net_grid(n), sn::kNetBlock, 0, st>>>(
           nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, (const T*)init, obs0);
     } else {
-      net_opt_in(sn::k_net_rollout<T, SN_POLICY_BASE_STOCK>, smem);
-      sn::k_net_rollout<T, SN_POLICY_BASE_STOCK><<<grid_for(n, sn::kNetBlock), sn::kNetBlock, smem, st>>>(
+      sn::k_net_rollout<T, SN_POLICY_BASE_STOCK><<<net_grid(n), sn::kNetBlock, 0, st>>>(
           nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, (const T*)init, obs0);
     }
     return cuda_ok("sn_rollout launch");

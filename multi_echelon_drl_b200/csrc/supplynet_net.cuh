@@ -1,11 +1,18 @@
 // supplynet_net.cuh — distribution trees of FIVE TO EIGHT internal nodes (continued).
 //
 // Same semantics as supplynet_tree.cuh (every node buys from one supplier, may serve several customers and / or its
-// own demand; what SupplyNetwork does for such node / arc lists, supplynetwork.py:182-268), different residency:
-// 8 nodes x 16 state words do not fit the register file at one-wave occupancy, so each env lives in SHARED MEMORY
-// for the duration of a launch (word-major, thread-minor: `sm[word][thread]`, conflict-free) and the topology is
-// applied by plain indexing (`inv[sup[k]]`) with loops over the run-time node count - no mask arithmetic, compact
-// code.  One thread per env, 64-thread blocks, (18 x nf x 64) quantity words of dynamic shared memory per block.
+// own demand; what SupplyNetwork does for such node / arc lists, supplynetwork.py:182-268), different decomposition:
+// 8 nodes x 16 state words do not fit one thread's registers at a useful occupancy, so an env is spread over EIGHT
+// LANES of a warp, one lane per node (four envs per warp).  A lane keeps its node's 16 words in registers and runs
+// the same per-node code as the chain kernels; what crosses nodes travels by warp shuffles inside the 8-lane group:
+//   * a customer reads its supplier's inventory (one shuffle) and the backlog of the customers served before it
+//     (8 shuffles + a bit mask), and takes s = min(B, max(0, A - P)): the closed form of "the supplier serves its
+//     customer arcs in rank order from what it has" (s_0 = min(A, B_0), s_1 = min(A - s_0, B_1), ...);
+//   * a supplier subtracts what its customers took and sums their backlog for its observation / cost (8 shuffles);
+//   * the latest demand of a node is the order that just reached it from one particular customer (one shuffle);
+//   * the reward is summed over the nodes in node order (the reference's order) with 2 x 8 double shuffles.
+// Observation rows are assembled per warp in shared memory (4 envs x 7 x n_obs floats) and leave coalesced.
+// An earlier version kept each env in shared memory under one thread (profiles/r1_notes.md): 4-5x slower.
 //
 // State word map in HBM ([SN_NET_STATE_WORDS = 128][ld]; node k owns words 16k .. 16k+15):
 //   +0 inv   +1 unf_ind   +2 latI (latest internal demand)   +3..6 U[0..3]   +7..9 info[0..2]   +10..13 ship[0..3]
@@ -17,19 +24,19 @@
 
 namespace sn {
 
-constexpr int kNF = 8;
-constexpr int kNetStateWords = 16 * kNF;     // 128
-constexpr int kNetInitWords = kNF + 8 * kNF; // 72
-constexpr int kNetBlock = 64;
-constexpr int kNetSmemWords = 18;            // per node: 16 state words + this period's order + the fifth pipeline slot
-
-enum { N_INV = 0, N_UNF = 1, N_LATI = 2, N_U = 3, N_INFO = 7, N_SHIP = 10, N_B = 14, N_DEM = 15, N_Q = 16, N_U4 = 17 };
+constexpr int kNF = 8;                        // lanes per env
+constexpr int kNetEnvsPerWarp = 32 / kNF;     // 4
+constexpr int kNetStateWords = 16 * kNF;      // 128
+constexpr int kNetInitWords = kNF + 8 * kNF;  // 72
+constexpr int kNetBlock = 128;                // 4 warps = 16 envs per block
+constexpr unsigned kFullMask = 0xffffffffu;
 
 template <typename T>
 struct NetSpec {
   int nf, n_agents, n_obs, n_src, rule, t_max;
-  T target[kNF];
+  int exact_costs;                 // cost sums cannot round (see group_reward)
   T clb, cub, off, lb, ub, big;
+  T target[kNF];
   double h[kNF], b[kNF];
   int li[kNF], ls[kNF];
   int sup[kNF];                    // supplier node, -1 = external supplier
@@ -37,9 +44,8 @@ struct NetSpec {
   int src[kNF];                    // demand-table row of node k, -1 = no external demand
   int pre[kNF];                    // orders inside before_action (ahead of the first agent in the order sequence)
   int lat_src[kNF];                // customer whose arriving order is node k's latest demand, -1 = none
-  int fill_seq[kNF];               // arcs in serving order: by customer rank (suppliers are independent of each other)
-  int cust_start[kNF + 1];         // customers of node k: cust_list[cust_start[k] .. cust_start[k+1])
-  int cust_list[kNF];
+  unsigned cust[kNF];              // bit j: node j is a customer of node k
+  unsigned before[kNF];            // bit j: node j has the same (internal) supplier as k and is served before it
 };
 
 template <typename T>
@@ -49,200 +55,278 @@ struct NetPolicy {
   int rule;
 };
 
-// one env in shared memory
+// what a lane needs to know about its node
 template <typename T>
-struct NetEnv {
-  T* sm;
-  __device__ __forceinline__ T& at(int node, int f) const { return sm[(node * kNetSmemWords + f) * kNetBlock + threadIdx.x]; }
-
-  __device__ __forceinline__ T unfilled(const NetSpec<T>& sp, int k) const {       // supplynetwork.py:130-136
-    T cb = T(0);
-    for (int i = sp.cust_start[k]; i < sp.cust_start[k + 1]; ++i) cb = cb + at(sp.cust_list[i], N_B);
-    return cb + (at(k, N_DEM) + at(k, N_UNF));
-  }
-  __device__ __forceinline__ T latest(int k) const { return at(k, N_LATI) + at(k, N_DEM); }   // :139
-  __device__ __forceinline__ T base_stock_order(const NetSpec<T>& sp, int k, T target, T lb, T ub, int rule) const {
-    const T U[4] = {at(k, N_U), at(k, N_U + 1), at(k, N_U + 2), at(k, N_U + 3)};
-    return base_stock(target, at(k, N_INV), U, unfilled(sp, k), latest(k), lb, ub, rule);
-  }
+struct LaneCfg {
+  bool active;                     // a real node of a real env
+  int k, base;                     // node index; first lane of this env's group
+  int li, ls, sup, slot, pos, src, pre, lat_src;
+  unsigned cust, before;
+  T target, pol_target;
+  double h, b;
 };
 
 template <typename T>
-__device__ __forceinline__ void net_load(const NetEnv<T>& e, const NetSpec<T>& sp, const T* __restrict__ state, int64_t ld, int64_t env) {
-  for (int k = 0; k < sp.nf; ++k)
+__device__ __forceinline__ LaneCfg<T> lane_cfg(const NetSpec<T>& sp, const NetPolicy<T>& pol, bool valid_env) {
+  LaneCfg<T> c;
+  const int lane = threadIdx.x & 31;
+  c.k = lane & (kNF - 1);
+  c.base = lane & ~(kNF - 1);
+  c.active = valid_env && c.k < sp.nf;
+  c.li = sp.li[c.k]; c.ls = sp.ls[c.k]; c.sup = sp.sup[c.k]; c.slot = sp.slot[c.k]; c.pos = sp.pos[c.k];
+  c.src = sp.src[c.k]; c.pre = sp.pre[c.k]; c.lat_src = sp.lat_src[c.k];
+  c.cust = sp.cust[c.k]; c.before = sp.before[c.k];
+  c.target = sp.target[c.k]; c.pol_target = pol.target[c.k];
+  c.h = sp.h[c.k]; c.b = sp.b[c.k];
+  return c;
+}
+
+// one node of one env; inactive lanes hold zeros
+template <typename T>
+struct LaneEnv {
+  T inv, unf, latI, U[4], info[3], ship[4], B, dem;
+};
+
+template <typename T>
+__device__ __forceinline__ void lane_zero(LaneEnv<T>& e) {
+  e.inv = e.unf = e.latI = e.B = e.dem = T(0);
 #pragma unroll
-    for (int f = 0; f < 16; ++f) e.at(k, f) = state[(int64_t)(16 * k + f) * ld + env];
+  for (int j = 0; j < 4; ++j) e.U[j] = e.ship[j] = T(0);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) e.info[j] = T(0);
+}
+
+// sum of `v` over the lanes of this env whose bit is set in `mask` (all 32 lanes take part)
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, unsigned mask, int base) {
+  T s = T(0);
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) {
+    const T x = __shfl_sync(kFullMask, v, base + j);
+    s = s + x * (T)((mask >> j) & 1u);
+  }
+  return s;
+}
+
+// the values of `v` held by the eight nodes of this env
+template <typename T>
+__device__ __forceinline__ void group_all(T v, int base, T (&out)[kNF]) {
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) out[j] = __shfl_sync(kFullMask, v, base + j);
+}
+
+// sum over the nodes whose bit is set in `mask` of values every lane already holds
+template <typename T>
+__device__ __forceinline__ T masked_sum(const T (&v)[kNF], unsigned mask) {
+  T s = T(0);
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) s = s + v[j] * (T)((mask >> j) & 1u);
+  return s;
+}
+
+// value of `v` held by node `node` of this env (node < 0: lane 0 of the group is read and must be ignored)
+template <typename T>
+__device__ __forceinline__ T group_get(T v, int node, int base) {
+  return __shfl_sync(kFullMask, v, base + (node < 0 ? 0 : node));
 }
 
 template <typename T>
-__device__ __forceinline__ void net_store(const NetEnv<T>& e, const NetSpec<T>& sp, T* __restrict__ state, int64_t ld, int64_t env) {
-  for (int k = 0; k < sp.nf; ++k)
+__device__ __forceinline__ void lane_load(LaneEnv<T>& e, const LaneCfg<T>& c, const T* __restrict__ state, int64_t ld, int64_t env) {
+  lane_zero(e);
+  if (!c.active) return;
+  const T* p = state + (int64_t)(16 * c.k) * ld + env;
+  e.inv = p[0]; e.unf = p[ld]; e.latI = p[2 * ld];
 #pragma unroll
-    for (int f = 0; f < 16; ++f) state[(int64_t)(16 * k + f) * ld + env] = e.at(k, f);
+  for (int j = 0; j < 4; ++j) e.U[j] = p[(3 + j) * ld];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) e.info[j] = p[(7 + j) * ld];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e.ship[j] = p[(10 + j) * ld];
+  e.B = p[14 * ld]; e.dem = p[15 * ld];
 }
 
-// current external demand of every node from one period's rows of the demand table
 template <typename T>
-__device__ __forceinline__ void net_set_demand(const NetEnv<T>& e, const NetSpec<T>& sp, const T* __restrict__ row, int64_t ld, int64_t env) {
-  for (int k = 0; k < sp.nf; ++k) e.at(k, N_DEM) = sp.src[k] >= 0 ? __ldg(row + (int64_t)sp.src[k] * ld + env) : T(0);
+__device__ __forceinline__ void lane_store(const LaneEnv<T>& e, const LaneCfg<T>& c, T* __restrict__ state, int64_t ld, int64_t env) {
+  if (!c.active) return;
+  T* p = state + (int64_t)(16 * c.k) * ld + env;
+  p[0] = e.inv; p[ld] = e.unf; p[2 * ld] = e.latI;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[(3 + j) * ld] = e.U[j];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) p[(7 + j) * ld] = e.info[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[(10 + j) * ld] = e.ship[j];
+  p[14 * ld] = e.B; p[15 * ld] = e.dem;
+}
+
+// external demand of this lane's node in one period's rows of the demand table (0 without a stream)
+template <typename T>
+__device__ __forceinline__ T lane_demand(const LaneCfg<T>& c, const T* __restrict__ row, int64_t ld, int64_t env) {
+  return (c.active && c.src >= 0) ? __ldg(row + (int64_t)c.src * ld + env) : T(0);
 }
 
 // Arc.reset / Node.reset + before_action(0) (network_components.py:138-168,293-319; supplynetwork.py:182-199)
 template <typename T>
-__device__ __forceinline__ void net_reset(const NetEnv<T>& e, const NetSpec<T>& sp, const T* __restrict__ init, int64_t ld,
-                                          int64_t env, const T* __restrict__ demand0) {
-  for (int k = 0; k < sp.nf; ++k) {
-    const int li = sp.li[k], ls = sp.ls[k];
-    T so[4], sh[4];
+__device__ __forceinline__ void lane_reset(LaneEnv<T>& e, const LaneCfg<T>& c, const T* __restrict__ init, int64_t ld,
+                                           int64_t env, const T* __restrict__ demand0) {
+  lane_zero(e);
+  T so[4] = {T(0), T(0), T(0), T(0)}, sh[4] = {T(0), T(0), T(0), T(0)};
+  if (c.active) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      so[j] = j < li ? __ldg(init + (int64_t)(kNF + 4 * k + j) * ld + env) : T(0);
-      sh[j] = j < ls ? __ldg(init + (int64_t)(5 * kNF + 4 * k + j) * ld + env) : T(0);
+      if (j < c.li) so[j] = __ldg(init + (int64_t)(kNF + 4 * c.k + j) * ld + env);
+      if (j < c.ls) sh[j] = __ldg(init + (int64_t)(5 * kNF + 4 * c.k + j) * ld + env);
     }
-    e.at(k, N_INV) = __ldg(init + (int64_t)k * ld + env);
-    // ([0]*4 + shipments + sales_orders)[::-1][:5]: newest slip first, then shipments latest first
-    T seq[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      T v = T(0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (li - 1 - i == j) v = so[j];
-        if (i >= li && ls - 1 - (i - li) == j) v = sh[j];
-      }
-      seq[i] = v;
-    }
-    e.at(k, N_U) = seq[0]; e.at(k, N_U + 1) = seq[1]; e.at(k, N_U + 2) = seq[2]; e.at(k, N_U + 3) = seq[3] + seq[4];
-    e.at(k, N_B) = so[0];                                    // the slip with remaining lead time 1 arrives now
-    e.at(k, N_INFO) = so[1]; e.at(k, N_INFO + 1) = so[2]; e.at(k, N_INFO + 2) = so[3];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) e.at(k, N_SHIP + j) = sh[j];
-    e.at(k, N_UNF) = T(0);
-    e.at(k, N_LATI) = T(0);
+    e.inv = __ldg(init + (int64_t)c.k * ld + env);
   }
-  for (int k = 0; k < sp.nf; ++k)
-    if (sp.lat_src[k] >= 0) e.at(k, N_LATI) = e.at(sp.lat_src[k], N_B);
-  net_set_demand(e, sp, demand0, ld, env);
+  // ([0]*4 + shipments + sales_orders)[::-1][:5]: newest slip first, then shipments latest first
+  T seq[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    T v = T(0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v = v + so[j] * (T)(c.li - 1 - i == j);
+      v = v + sh[j] * (T)(i >= c.li && c.ls - 1 - (i - c.li) == j);
+    }
+    seq[i] = v;
+  }
+  e.U[0] = seq[0]; e.U[1] = seq[1]; e.U[2] = seq[2]; e.U[3] = seq[3] + seq[4];
+  e.B = so[0];                                             // the slip with remaining lead time 1 arrives now
+  e.info[0] = so[1]; e.info[1] = so[2]; e.info[2] = so[3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e.ship[j] = sh[j];
+  const T from = group_get(so[0], c.lat_src, c.base);
+  e.latI = c.lat_src >= 0 ? from : T(0);
+  e.dem = lane_demand(c, demand0, ld, env);
 }
 
-// orders of all nodes for this period, into slot N_Q (depend on start-of-period quantities only)
-template <int POLICY, typename T>
-__device__ __forceinline__ void net_orders(const NetEnv<T>& e, const NetSpec<T>& sp, const NetPolicy<T>& pol,
-                                           const T* __restrict__ act_row /* this env's action row or NULL */,
-                                           float* __restrict__ act_out /* this env's row of traj_actions or NULL */) {
-  for (int k = 0; k < sp.nf; ++k) {
-    T x;
-    if (sp.slot[k] >= 0) {
-      if (POLICY == SN_POLICY_BASE_STOCK) x = e.base_stock_order(sp, k, pol.target[k], pol.lb, pol.ub, pol.rule);
-      else x = __ldg(act_row + sp.slot[k]);
-      if (act_out != nullptr) act_out[sp.slot[k]] = (float)x;
-      if (sp.rule == 1) x = tclamp(e.latest(k) + x + sp.off, sp.lb, sp.ub);          // utils/wrappers.py:25-27
-    } else {
-      x = e.base_stock_order(sp, k, sp.target[k], sp.clb, sp.cub, 0);                 // network_components.py:361-366
-    }
-    e.at(k, N_Q) = tmax(x, T(0));                                                     // :368-374
-  }
-}
-
-// One period (agent_action + after_action + get_cost + before_action unless terminal).  `cost` (may be NULL) receives
-// holding[0..7] / backorder[8..15] of this env at stride ld.
+// observed unfilled_demand / latest_demand (supplynetwork.py:130-139); `cust_backlog` = group_sum(B, cust)
 template <typename T>
-__device__ __forceinline__ double net_step(const NetEnv<T>& e, const NetSpec<T>& sp, const T* __restrict__ demand_next,
-                                           int64_t ld, int64_t env, bool terminal, double* __restrict__ cost) {
-  // receipts on every arc (supplynetwork.py:243-255)
-  for (int k = 0; k < sp.nf; ++k) {
-    T u[5] = {e.at(k, N_Q), e.at(k, N_U), e.at(k, N_U + 1), e.at(k, N_U + 2), e.at(k, N_U + 3)};
-    const T arr = e.at(k, N_SHIP);
-    e.at(k, N_INV) = e.at(k, N_INV) + arr;
-    T rem = arr;
+__device__ __forceinline__ T lane_unfilled(const LaneEnv<T>& e, T cust_backlog) { return cust_backlog + (e.dem + e.unf); }
+template <typename T>
+__device__ __forceinline__ T lane_latest(const LaneEnv<T>& e) { return e.latI + e.dem; }
+
+// this node's order for the period (depends on start-of-period quantities only)
+template <int POLICY, typename T>
+__device__ __forceinline__ T lane_order(const LaneEnv<T>& e, const LaneCfg<T>& c, const NetSpec<T>& sp, const NetPolicy<T>& pol,
+                                        T cust_backlog, T action, T& action_taken) {
+  const T unf = lane_unfilled(e, cust_backlog), lat = lane_latest(e);
+  T x;
+  if (c.slot >= 0) {
+    x = (POLICY == SN_POLICY_BASE_STOCK) ? base_stock(c.pol_target, e.inv, e.U, unf, lat, pol.lb, pol.ub, pol.rule) : action;
+    action_taken = x;
+    if (sp.rule == 1) x = tclamp(lat + x + sp.off, sp.lb, sp.ub);                    // utils/wrappers.py:25-27
+  } else {
+    x = base_stock(c.target, e.inv, e.U, unf, lat, sp.clb, sp.cub, 0);                // network_components.py:361-366
+  }
+  return c.active ? tmax(x, T(0)) : T(0);                                             // :368-374
+}
+
+// One period of this lane's node.  `bj` holds the backlog of all eight upstream arcs of this env (every lane keeps the
+// same copy: it is what customers-served-before-me and my-customers sums are taken from without further shuffles); it
+// is updated to the new state.  Returns the period's holding / backorder cost terms of the node.
+template <typename T>
+__device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, const NetSpec<T>& sp, T q, T d_next,
+                                          bool terminal, T (&bj)[kNF], double& hold, double& back) {
+  // receipt on the node's upstream arc (supplynetwork.py:243-255)
+  T u[5] = {q, e.U[0], e.U[1], e.U[2], e.U[3]};
+  const T arr = e.ship[0];
+  e.inv = e.inv + arr;
+  T rem = arr;
 #pragma unroll
-    for (int i = 4; i >= 0; --i) {
-      const T f = tmin(u[i], rem);
-      u[i] = u[i] - f;
-      rem = rem - f;
-    }
-    e.at(k, N_SHIP) = e.at(k, N_SHIP + 1); e.at(k, N_SHIP + 1) = e.at(k, N_SHIP + 2);
-    e.at(k, N_SHIP + 2) = e.at(k, N_SHIP + 3); e.at(k, N_SHIP + 3) = T(0);
-    e.at(k, N_U) = u[0]; e.at(k, N_U + 1) = u[1]; e.at(k, N_U + 2) = u[2]; e.at(k, N_U + 3) = u[3];
-    e.at(k, N_U4) = u[4];
+  for (int i = 4; i >= 0; --i) {
+    const T f = tmin(u[i], rem);
+    u[i] = u[i] - f;
+    rem = rem - f;
   }
-  // fills: every supplier serves its customer arcs in rank order from what it has (Arc.fill_orders, :260-262)
-  for (int i = 0; i < sp.nf; ++i) {
-    const int k = sp.fill_seq[i], s = sp.sup[k];
-    const T avail = s >= 0 ? e.at(s, N_INV) : sp.big;
-    const T amt = tmin(avail, e.at(k, N_B));
-    if (s >= 0) e.at(s, N_INV) = avail - amt;
-    e.at(k, N_B) = e.at(k, N_B) - amt;
-    e.at(k, N_SHIP + sp.ls[k] - 1) = e.at(k, N_SHIP + sp.ls[k] - 1) + amt;
+  e.ship[0] = e.ship[1]; e.ship[1] = e.ship[2]; e.ship[2] = e.ship[3]; e.ship[3] = T(0);
+  // fills (Arc.fill_orders in aggregate, :260-262): closed form of the rank-ordered service, see the header
+  const T a_sup = group_get(e.inv, c.sup, c.base);
+  const T avail = c.sup < 0 ? sp.big : a_sup;
+  const T amt = c.active ? tmin(e.B, tmax(T(0), avail - masked_sum(bj, c.before))) : T(0);
+  T amt_j[kNF];
+  group_all(amt, c.base, amt_j);
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) bj[j] = bj[j] - amt_j[j];
+  e.inv = e.inv - masked_sum(amt_j, c.cust);
+  e.B = e.B - amt;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e.ship[j] = e.ship[j] + amt * (T)(j == c.ls - 1);
+  // independent demand (network_components.py:323-345)
+  if (c.src >= 0) {
+    const T tot = e.dem + e.unf;
+    const T sold = tmax(T(0), tmin(e.inv, tot));
+    e.inv = e.inv - sold;
+    e.unf = tot - sold;
   }
-  // independent demand (network_components.py:323-345) and cost (supplynetwork.py:285-310)
-  double ch = 0.0, cb = 0.0;
-  for (int k = 0; k < sp.nf; ++k) {
-    if (sp.src[k] >= 0) {
-      const T tot = e.at(k, N_DEM) + e.at(k, N_UNF);
-      const T sold = tmax(T(0), tmin(e.at(k, N_INV), tot));
-      e.at(k, N_INV) = e.at(k, N_INV) - sold;
-      e.at(k, N_UNF) = tot - sold;
-    }
-  }
-  for (int k = 0; k < sp.nf; ++k) {
-    T unf = T(0);
-    for (int i = sp.cust_start[k]; i < sp.cust_start[k + 1]; ++i) unf = unf + e.at(sp.cust_list[i], N_B);
-    unf = unf + e.at(k, N_UNF);
-    const double hk = -(double)e.at(k, N_INV) * sp.h[k], bk = -(double)unf * sp.b[k];
-    ch += hk;
-    cb += bk;
-    if (cost != nullptr) {
-      cost[(int64_t)k * ld + env] = hk;
-      cost[(int64_t)(kNF + k) * ld + env] = bk;
-    }
-  }
-  net_set_demand(e, sp, demand_next, ld, env);                                       // Node.update_demand
+  // cost terms of this node (supplynetwork.py:285-310)
+  const T unf_post = masked_sum(bj, c.cust) + e.unf;
+  hold = -(double)e.inv * c.h;
+  back = -(double)unf_post * c.b;
+  e.dem = d_next;                                                                      // Node.update_demand
+  e.U[0] = u[0]; e.U[1] = u[1]; e.U[2] = u[2];
   if (!terminal) {
     // before_action (supplynetwork.py:185-199)
-    for (int k = 0; k < sp.nf; ++k) {
-      const int li = sp.li[k];
-      const T q = e.at(k, N_Q);
-      const T arrived = li == 1 ? q : e.at(k, N_INFO);
-      e.at(k, N_INFO) = e.at(k, N_INFO + 1); e.at(k, N_INFO + 1) = e.at(k, N_INFO + 2); e.at(k, N_INFO + 2) = T(0);
-      if (li >= 2) e.at(k, N_INFO + li - 2) = q;
-      e.at(k, N_B) = e.at(k, N_B) + arrived;
-      e.at(k, N_U + 3) = e.at(k, N_U + 3) + e.at(k, N_U4);
-      e.at(k, N_Q) = arrived;                           // kept for the latest-demand pass below
+    const T arrived = c.li == 1 ? q : e.info[0];
+    e.info[0] = e.info[1]; e.info[1] = e.info[2]; e.info[2] = T(0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) e.info[j] = e.info[j] + q * (T)(j == c.li - 2);
+    e.B = e.B + arrived;
+    e.U[3] = u[3] + u[4];
+    T arr_j[kNF];
+    group_all(arrived, c.base, arr_j);
+    T lat = T(0);
+#pragma unroll
+    for (int j = 0; j < kNF; ++j) {
+      bj[j] = bj[j] + arr_j[j];
+      lat = lat + arr_j[j] * (T)(j == c.lat_src);
     }
-    for (int k = 0; k < sp.nf; ++k) e.at(k, N_LATI) = sp.lat_src[k] >= 0 ? e.at(sp.lat_src[k], N_Q) : T(0);
+    e.latI = lat;
+  } else {
+    e.U[3] = u[3];                             // terminal view: 5-slot list of which the first four are read
+  }
+}
+
+// reward = (sum of holding terms in node order) + (sum of backorder terms in node order), like get_cost.  When every
+// term is an exact multiple of 2^-10 below 2^52 (integer quantities, cost coefficients that are multiples of 2^-10:
+// NetSpec::exact_costs) no addition rounds, the order is immaterial and a 3-step butterfly does (12 shuffles
+// instead of 32); otherwise the terms are added strictly in node order.
+__device__ __forceinline__ double group_reward(double hold, double back, int base, bool exact) {
+  if (exact) {
+#pragma unroll
+    for (int o = 1; o < kNF; o <<= 1) {
+      hold += __shfl_xor_sync(kFullMask, hold, o);
+      back += __shfl_xor_sync(kFullMask, back, o);
+    }
+    return hold + back;
+  }
+  double ch = 0.0, cb = 0.0;
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) {
+    ch += __shfl_sync(kFullMask, hold, base + j);
+    cb += __shfl_sync(kFullMask, back, base + j);
   }
   return ch + cb;
 }
 
-// observation (supplynetwork.py:151-169 per node, envs.py:103-110): node k lands at dst + 7*pos[k]
+// Observation rows of the warp's four envs, assembled in `stage` ([4][7*n_obs] floats) and copied out coalesced.
+//   dst       global address of the row of the warp's first env;  n_valid: real envs in this warp (0..4)
 template <typename T>
-__device__ __forceinline__ void net_emit_obs(const NetEnv<T>& e, const NetSpec<T>& sp, bool terminal, float* __restrict__ dst) {
-  for (int k = 0; k < sp.nf; ++k) {
-    if (sp.pos[k] < 0) continue;
-    T u0 = e.at(k, N_U), u1 = e.at(k, N_U + 1), u2 = e.at(k, N_U + 2), u3 = e.at(k, N_U + 3);
-    const T unf = e.unfilled(sp, k), lat = e.latest(k);
-    if (sp.pre[k] && !terminal) {          // already ordered inside before_action: 5-slot list, first four read
-      const T q = tmax(e.base_stock_order(sp, k, sp.target[k], sp.clb, sp.cub, 0), T(0));
+__device__ __forceinline__ void lane_write_obs(const LaneEnv<T>& e, const LaneCfg<T>& c, const NetSpec<T>& sp, T cust_backlog,
+                                               bool terminal, float* stage, float* __restrict__ dst, int n_valid) {
+  const int lane = threadIdx.x & 31, od = 7 * sp.n_obs;
+  if (c.active && c.pos >= 0) {
+    const T unf = lane_unfilled(e, cust_backlog), lat = lane_latest(e);
+    T u0 = e.U[0], u1 = e.U[1], u2 = e.U[2], u3 = e.U[3];
+    if (c.pre && !terminal) {          // already ordered inside before_action: 5-slot list, first four read
+      const T q = tmax(base_stock(c.target, e.inv, e.U, unf, lat, sp.clb, sp.cub, 0), T(0));
       u3 = u2; u2 = u1; u1 = u0; u0 = q;
     }
-    float* d = dst + 7 * sp.pos[k];
-    d[0] = (float)e.at(k, N_INV); d[1] = (float)unf; d[2] = (float)lat;
+    float* d = stage + (lane >> 3) * od + 7 * c.pos;
+    d[0] = (float)e.inv; d[1] = (float)unf; d[2] = (float)lat;
     d[3] = (float)u0; d[4] = (float)u1; d[5] = (float)u2; d[6] = (float)u3;
   }
-}
-
-// Row-major observations through a per-warp staging buffer in shared memory: every lane builds its row there, then the
-// warp copies the 32 consecutive rows to global memory with fully coalesced stores (a lane writing its own 7*n_obs
-// floats directly would touch 32 different lines per store instruction).  All 32 lanes must call this.
-//   stage      this warp's buffer, 32 * 7 * n_obs floats
-//   dst        global address of the row of the warp's first env
-//   n_valid    number of real envs in this warp (lanes >= n_valid only help copying)
-template <typename T>
-__device__ __forceinline__ void net_write_obs(const NetEnv<T>& e, const NetSpec<T>& sp, bool terminal, float* stage,
-                                              float* __restrict__ dst, int n_valid) {
-  const int lane = threadIdx.x & 31, od = 7 * sp.n_obs;
-  if (lane < n_valid) net_emit_obs(e, sp, terminal, stage + lane * od);
   __syncwarp();
   const int total = n_valid * od;
   for (int i = lane; i < total; i += 32) dst[i] = stage[i];

@@ -32,7 +32,7 @@ five = tree_spec([dict(name="kiosk", demand=(0, 3), target=8), dict(name="shop_a
                  ["kiosk", "shop_a", "shop_b", "dist", "maker"], True)
 specs = {"beer game (tuned)": uniform_spec(None, True), "other lead times (generic)": replace(uniform_spec(None, True), info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
          "tree, 2 levels, 2 sources": tree, "star, 3 retailers (3 fill rounds)": star,
-         "5-node tree (shared-memory kernels)": five, "8-node tree (shared-memory kernels)": big}
+         "5-node tree (lane-per-node kernels)": five, "8-node tree (lane-per-node kernels)": big}
 for name, sp in specs.items():
     sim = BatchedSupplyNetwork(sp, n)
     init, dem = bulk_episode_inputs(sp, n, np.random.RandomState(0))
