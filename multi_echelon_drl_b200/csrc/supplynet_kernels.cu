@@ -626,7 +626,7 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
       out.traj_actions[(int64_t)s * act_stride + act_off] = (float)taken;
     double hold, back;
     lane_step(e, c, sp, q, dn, terminal, bj, hold, back);
-    cb = masked_sum(bj, c.cust);
+    cb = weighted_sum(bj, c.cust_m);
     const double r = group_reward(hold, back, c.base, sp.exact_costs != 0);
     total += r;
     if (out.traj_reward != nullptr && head) out.traj_reward[(int64_t)s * n + env] = (float)r;

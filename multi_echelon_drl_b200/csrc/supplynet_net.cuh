@@ -62,6 +62,8 @@ struct LaneCfg {
   int k, base;                     // node index; first lane of this env's group
   int li, ls, sup, slot, pos, src, pre, lat_src;
   unsigned cust, before;
+  T cust_m[kNF], before_m[kNF];    // the same two bit masks as exact 0/1 multipliers: one multiply-add per node and sum
+  T ship_m[4], info_m[3], lat_m[kNF], li1_m;   // 1 at slot ls-1 / slot li-2 / node lat_src / if li == 1
   T target, pol_target;
   double h, b;
 };
@@ -76,6 +78,17 @@ __device__ __forceinline__ LaneCfg<T> lane_cfg(const NetSpec<T>& sp, const NetPo
   c.li = sp.li[c.k]; c.ls = sp.ls[c.k]; c.sup = sp.sup[c.k]; c.slot = sp.slot[c.k]; c.pos = sp.pos[c.k];
   c.src = sp.src[c.k]; c.pre = sp.pre[c.k]; c.lat_src = sp.lat_src[c.k];
   c.cust = sp.cust[c.k]; c.before = sp.before[c.k];
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) {
+    c.cust_m[j] = (T)((c.cust >> j) & 1u);
+    c.before_m[j] = (T)((c.before >> j) & 1u);
+    c.lat_m[j] = (T)(j == c.lat_src);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c.ship_m[j] = (T)(j == c.ls - 1);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) c.info_m[j] = (T)(j == c.li - 2);
+  c.li1_m = (T)(c.li == 1);
   c.target = sp.target[c.k]; c.pol_target = pol.target[c.k];
   c.h = sp.h[c.k]; c.b = sp.b[c.k];
   return c;
@@ -121,6 +134,14 @@ __device__ __forceinline__ T masked_sum(const T (&v)[kNF], unsigned mask) {
   T s = T(0);
 #pragma unroll
   for (int j = 0; j < kNF; ++j) s = s + v[j] * (T)((mask >> j) & 1u);
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ T weighted_sum(const T (&v)[kNF], const T (&w)[kNF]) {
+  T s = T(0);
+#pragma unroll
+  for (int j = 0; j < kNF; ++j) s = s + v[j] * w[j];
   return s;
 }
 
@@ -244,15 +265,15 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
   // fills (Arc.fill_orders in aggregate, :260-262): closed form of the rank-ordered service, see the header
   const T a_sup = group_get(e.inv, c.sup, c.base);
   const T avail = c.sup < 0 ? sp.big : a_sup;
-  const T amt = c.active ? tmin(e.B, tmax(T(0), avail - masked_sum(bj, c.before))) : T(0);
+  const T amt = c.active ? tmin(e.B, tmax(T(0), avail - weighted_sum(bj, c.before_m))) : T(0);
   T amt_j[kNF];
   group_all(amt, c.base, amt_j);
 #pragma unroll
   for (int j = 0; j < kNF; ++j) bj[j] = bj[j] - amt_j[j];
-  e.inv = e.inv - masked_sum(amt_j, c.cust);
+  e.inv = e.inv - weighted_sum(amt_j, c.cust_m);
   e.B = e.B - amt;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) e.ship[j] = e.ship[j] + amt * (T)(j == c.ls - 1);
+  for (int j = 0; j < 4; ++j) e.ship[j] = e.ship[j] + amt * c.ship_m[j];
   // independent demand (network_components.py:323-345)
   if (c.src >= 0) {
     const T tot = e.dem + e.unf;
@@ -261,17 +282,17 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
     e.unf = tot - sold;
   }
   // cost terms of this node (supplynetwork.py:285-310)
-  const T unf_post = masked_sum(bj, c.cust) + e.unf;
+  const T unf_post = weighted_sum(bj, c.cust_m) + e.unf;
   hold = -(double)e.inv * c.h;
   back = -(double)unf_post * c.b;
   e.dem = d_next;                                                                      // Node.update_demand
   e.U[0] = u[0]; e.U[1] = u[1]; e.U[2] = u[2];
   if (!terminal) {
     // before_action (supplynetwork.py:185-199)
-    const T arrived = c.li == 1 ? q : e.info[0];
+    const T arrived = e.info[0] + q * c.li1_m;        // lead time 1: the head slot is empty, q arrives now
     e.info[0] = e.info[1]; e.info[1] = e.info[2]; e.info[2] = T(0);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) e.info[j] = e.info[j] + q * (T)(j == c.li - 2);
+    for (int j = 0; j < 3; ++j) e.info[j] = e.info[j] + q * c.info_m[j];
     e.B = e.B + arrived;
     e.U[3] = u[3] + u[4];
     T arr_j[kNF];
@@ -280,7 +301,7 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
 #pragma unroll
     for (int j = 0; j < kNF; ++j) {
       bj[j] = bj[j] + arr_j[j];
-      lat = lat + arr_j[j] * (T)(j == c.lat_src);
+      lat = lat + arr_j[j] * c.lat_m[j];
     }
     e.latI = lat;
   } else {
