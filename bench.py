@@ -461,12 +461,19 @@ def single_step_numbers(torch, dev, peak):
                       dict(name="dist_b", demand=(0, 5), target=14), dict(name="maker", target=25)],
                      [("ext", "maker", 1, 2), ("maker", "dist_b", 1, 2), ("maker", "dist_a", 2, 2), ("dist_a", "shop", 2, 2)],
                      ["shop", "dist_a", "dist_b", "maker"], True)
+    big = tree_spec([dict(name="hub", target=60), dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=14),
+                     dict(name="r3", demand=(0, 4), target=10), dict(name="r4", demand=(0, 3), target=8),
+                     dict(name="r5", demand=(0, 2), target=6), dict(name="factory", target=40),
+                     dict(name="annex", demand=(0, 5), target=12)],
+                    [("ext", "factory", 1, 2), ("factory", "annex", 1, 3), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1),
+                     ("hub", "r1", 2, 2), ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)],
+                    ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"], True)
     others = {"rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
-              "rollout_distribution_tree_65536": tree}
-    acts = torch.randint(0, 17, (T, n, 4), generator=g, device=dev, dtype=torch.int32)
-    t_obs = torch.empty((T, n, 28), dtype=torch.float32, device=dev)
+              "rollout_distribution_tree_65536": tree, "rollout_tree_8_nodes_65536": big}
     t_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     for key, sp in others.items():
+        acts = torch.randint(0, 17, (T, n, sp.n_agents), generator=g, device=dev, dtype=torch.int32)
+        t_obs = torch.empty((T, n, sp.obs_dim), dtype=torch.float32, device=dev)
         sim = BatchedSupplyNetwork(sp, n, dev, "int32")
         sim.load_episode(*bulk_episode_inputs(sp, n, np.random.RandomState(0)))
         for _ in range(3):
@@ -479,11 +486,13 @@ def single_step_numbers(torch, dev, peak):
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / 10
-        nbytes = n * T * (16 + 4 * sp.n_sources + 112 + 4)
+        nbytes = n * T * (4 * sp.n_agents + 4 * sp.n_sources + 4 * sp.obs_dim + 4)
         out[key] = {"env_steps_per_s": n * T / (ms * 1e-3), "kernel_ms": ms, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
                     "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "bound": "instruction issue (run-time topology / lead times as 0/1 multipliers)",
                     "config": ("serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
-                               "two-level distribution tree, two demand sources (tree kernels)")}
+                               "two-level distribution tree, two demand sources (tree kernels)" if "distribution" in key else
+                               "8-node tree: factory -> {annex, hub -> 5 retailers}, 6 demand sources, obs 56 / action 8 "
+                               "(one lane per node)")}
         del sim
     return out
 
