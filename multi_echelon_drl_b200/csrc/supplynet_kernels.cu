@@ -964,7 +964,8 @@ sn::NetSpec<T> lower_net(const sn_spec* s) {
   d.exact_costs = std::is_same<T, int32_t>::value ? 1 : 0;
   for (int k = 0; k < nf; ++k) {
     const double hs = s->holding_cost[k] * 1024.0, bs = s->backorder_cost[k] * 1024.0;
-    if (!(std::fabs(hs) < 1e9 && std::fabs(bs) < 1e9 && std::floor(hs) == hs && std::floor(bs) == bs)) d.exact_costs = 0;
+    // |quantity| < 2^31 times |coefficient * 2^10| < 2^18 stays below 2^49: sixteen such terms sum exactly in a double
+    if (!(std::fabs(hs) < 262144.0 && std::fabs(bs) < 262144.0 && std::floor(hs) == hs && std::floor(bs) == bs)) d.exact_costs = 0;
   }
   for (int k = 0; k < nf; ++k) {
     int best = -1;
