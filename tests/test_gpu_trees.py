@@ -244,3 +244,28 @@ def test_vecenv_and_heuristic_on_an_eight_node_tree():
     assert stats[0] == 2 * 777 * 100 and stats[10] == 2 * 777 and stats[11] < 0 and stats[11] == stats[1]
     assert not stats[2:10].any()                                    # per-facility sums are not kept for these networks
     assert (stepped < 0).all()
+
+
+def test_big_tree_rewards_with_cost_coefficients_that_round():
+    """Cost coefficients off the 2^-10 grid (0.3, 0.7, 1.1): the lane-per-node kernels must then add the per-node terms
+    strictly in node order, like SupplyNetwork.get_cost; rewards stay bit-identical to the oracle's float64 sums."""
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    base = BIG_TREE_CASES[[c["topo"] for c in BIG_TREE_CASES].index("seven_two_levels")]
+    case = dict(base, holding=[0.3, 0.7, 1.1, 0.3, 0.123, 0.9, 0.45], backorder=[1.1, 0.7, 2.3, 0.3, 1.7, 0.6, 3.3])
+    n = 1025
+    sim = BatchedSupplyNetwork(tree_product_spec(case), n, "cuda", "int32")
+    init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(8))
+    acts = np.random.RandomState(9).randint(-1, 19, (100, n, len(case["agents"])))
+    obs0, obs, rew = tree_oracle_rollout(case, init, demand, acts)
+    sim.load_episode(init, demand)
+    sim.reset()
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(100):
+        o, _, _ = sim.step(torch.as_tensor(acts[t]), reward64_out=r64)
+        assert np.array_equal(o.cpu().numpy(), obs[t]) and np.array_equal(r64.cpu().numpy(), rew[t]), t
+    sim.episode(100, actions=torch.as_tensor(acts))
+    total = np.zeros(n)
+    for t in range(100):
+        total = total + rew[t]                       # the kernel accumulates the episode return period by period
+    assert np.array_equal(sim.ep_return.cpu().numpy(), total)
