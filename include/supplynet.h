@@ -224,7 +224,8 @@ int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
  * SB3 is third-party and not vendored: algorithm per SURVEY Appendix D, parity unpinned) ----------
  * Running statistics are float64 vectors owned by the caller:
  *   obs_rms = mean[obs_dim], var[obs_dim], count      ret_rms = mean, var, count
- * (initialise mean 0, var 1, count 1e-4 like RunningMeanStd).  `scratch` is 2*obs_dim+2 doubles.
+ * (initialise mean 0, var 1, count 1e-4 like RunningMeanStd).  `scratch` is 2*obs_dim+2 doubles;
+ * obs_dim is at most 56 (7 numbers for each of up to 8 facilities).
  * sn_vecnorm_update: RunningMeanStd.update(obs) into obs_rms_out; if `reward` is given also
  *   returns <- returns*gamma + reward and RunningMeanStd.update(returns) into ret_rms_out
  *   (in/out buffers must differ; the caller swaps them).

@@ -19,7 +19,7 @@
 
 namespace snv {
 
-constexpr int kMaxOd = 28;
+constexpr int kMaxOd = 56;      // 7 numbers x up to 8 facilities
 
 // scratch layout: [0..od) sum x, [od..2od) sum x^2, [2od] sum ret, [2od+1] sum ret^2
 __global__ void __launch_bounds__(256)

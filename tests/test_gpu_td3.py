@@ -141,3 +141,31 @@ def test_graphed_update_equals_eager_in_effect_and_is_faster():
     # targets moved by Polyak averaging in both
     assert times[True] < times[False], times
     print("update ms per step: eager %.3f graph %.3f" % (times[False] / 401, times[True] / 401))
+
+
+def test_td3_hge_runs_on_an_eight_node_tree():
+    """The whole stack composes on a network the reference's scripts never built: 8-node distribution tree (obs 56,
+    8 action columns) -> VecNormalize -> TD3 with heuristic-guided exploration (wide base-stock kernel)."""
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    names = ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"]
+    targets = [60, 19, 14, 10, 8, 6, 40, 12]
+    spec = tree_spec([dict(name=nm, target=t, demand=d) for nm, t, d in zip(
+        names, targets, [None, (0, 8), (0, 6), (0, 4), (0, 3), (0, 2), None, (0, 5)])],
+        [("ext", "factory", 1, 2), ("factory", "annex", 1, 3), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1), ("hub", "r1", 2, 2),
+         ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)], names, True)
+    n = 128
+    env = VecNormalize(SupplyNetVecEnv(spec, n, seed=1, dtype="float32"), clip_obs=100.0, clip_reward=1000.0)
+    assert env.observation_space.shape == (56,) and env.action_space.shape == (8,)
+    cfg = TD3Config(net_arch=(64,), train_freq=10, gradient_steps=4, buffer_size=n * 250, learning_starts=n * 10,
+                    hge_rate_at_start=0.9, hge_decay_periods=2)
+    model = HgeTD3(env, BaseStockPolicy(targets), cfg)
+    model.learn(n * 210)
+    assert model.n_updates > 0 and len(model.episode_returns) == 2 and all(np.isfinite(model.episode_returns))
+    assert model.timers.heuristic > 0                       # the heuristic branch was taken (p = 0.81 at the start)
+    assert model.buffer.obs.shape[1] == 56 and model.buffer.act.shape[1] == 8 and model.buffer.act.abs().max() <= 1
+    for p in model.actor.parameters():
+        assert torch.isfinite(p).all()

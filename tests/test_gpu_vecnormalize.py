@@ -89,3 +89,37 @@ def test_vecnormalize_small_obs_dim_and_reward_only():
     raw = env7.get_original_obs().cpu().numpy().astype(np.float64)
     rms = RMS((7,)); rms.update(raw)
     np.testing.assert_allclose(o.cpu().numpy(), np.clip((raw - rms.mean) / np.sqrt(rms.var + 1e-8), -100, 100), rtol=1e-5, atol=1e-5)
+
+
+def test_vecnormalize_on_56_dim_observations_of_an_eight_node_tree():
+    """Widest observation the library produces (7 numbers x 8 facilities): running statistics and normalisation
+    agree with the numpy restatement."""
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.vec_env import SupplyNetVecEnv
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    names = ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"]
+    spec = tree_spec([dict(name=nm, target=t, demand=d) for nm, t, d in zip(
+        names, [60, 19, 14, 10, 8, 6, 40, 12], [None, (0, 8), (0, 6), (0, 4), (0, 3), (0, 2), None, (0, 5)])],
+        [("ext", "factory", 1, 2), ("factory", "annex", 1, 3), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1), ("hub", "r1", 2, 2),
+         ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)], names, True)
+    n = 1000
+    env = VecNormalize(SupplyNetVecEnv(spec, n, seed=2, dtype="float32"), clip_obs=100.0, clip_reward=1000.0)
+    obs_rms, ret_rms, ret = RMS((56,)), RMS(()), np.zeros(n)
+    nobs = env.reset()
+    raw = env.get_original_obs().cpu().numpy().astype(np.float64)
+    obs_rms.update(raw)
+    np.testing.assert_allclose(nobs.cpu().numpy(), np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -100, 100),
+                               rtol=1e-5, atol=1e-5)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(40):
+        nobs, nrew, dones, infos = env.step(torch.rand((n, 8), device="cuda", generator=g) * 16)
+        raw = env.get_original_obs().cpu().numpy().astype(np.float64)
+        r = env.get_original_reward().cpu().numpy().astype(np.float64)
+        obs_rms.update(raw)
+        ret = ret * 0.99 + r
+        ret_rms.update(ret)
+        np.testing.assert_allclose(nobs.cpu().numpy(), np.clip((raw - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -100, 100),
+                                   rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(nrew.cpu().numpy(), np.clip(r / np.sqrt(ret_rms.var + 1e-8), -1000, 1000), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(env.obs_rms["mean"].cpu().numpy(), obs_rms.mean, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(env.obs_rms["var"].cpu().numpy(), obs_rms.var, rtol=1e-8, atol=1e-9)
