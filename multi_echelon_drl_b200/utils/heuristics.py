@@ -51,8 +51,8 @@ class BaseStockPolicy(InventoryPolicy):
             keys = ("on_hand", "unfilled_demand", "latest_demand", "unreceived_pipeline_0", "unreceived_pipeline_1",
                     "unreceived_pipeline_2", "unreceived_pipeline_3")
             m = self.target_levels.shape[0]
-            if m > 4:
-                raise NotImplementedError("the kernel evaluates at most 4 targets per state")
+            if m > 8:
+                raise NotImplementedError("the kernel evaluates at most 8 targets per state")
             rows = np.array([[st[k] for k in keys] * m for st in observation.values()], dtype=np.float32)
             out = heuristic_actions(self.params, torch.as_tensor(rows).cuda())
             return out.cpu().numpy().astype(np.float64)
