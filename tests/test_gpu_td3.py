@@ -161,7 +161,7 @@ def test_td3_hge_runs_on_an_eight_node_tree():
     env = VecNormalize(SupplyNetVecEnv(spec, n, seed=1, dtype="float32"), clip_obs=100.0, clip_reward=1000.0)
     assert env.observation_space.shape == (56,) and env.action_space.shape == (8,)
     cfg = TD3Config(net_arch=(64,), train_freq=10, gradient_steps=4, buffer_size=n * 250, learning_starts=n * 10,
-                    hge_rate_at_start=0.9, hge_decay_periods=2)
+                    hge_rate_at_start=0.9, hge_decay_periods=300)          # decays over 100 x 300 timesteps = 234 vector steps
     model = HgeTD3(env, BaseStockPolicy(targets), cfg)
     model.learn(n * 210)
     assert model.n_updates > 0 and len(model.episode_returns) == 2 and all(np.isfinite(model.episode_returns))
