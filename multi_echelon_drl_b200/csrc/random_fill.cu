@@ -5,6 +5,7 @@
 // (utils/demands.py:44,47; network_components.py:143,157,297) but are NOT numpy's MT19937 streams:
 // parity runs use host-generated tables (utils/demands.py seeded_episode_inputs) instead.
 #include "../../include/supplynet.h"
+#include "supplynet_error.h"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -74,8 +75,9 @@ extern "C" {
 
 int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
                         uint64_t offset, void* stream) {
-  if (!dst || count < 1 || high_exclusive <= low) return SN_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) return SN_ERR_INVALID;
+  using sn_detail::fail;
+  if (!dst || count < 1 || high_exclusive <= low) return fail(SN_ERR_INVALID, "sn_fill_uniform: dst NULL, count < 1 or empty range");
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) return fail(SN_ERR_INVALID, "sn_fill_uniform: dst must be 16-byte aligned");
   const uint32_t range = (uint32_t)(high_exclusive - low);
   const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
@@ -83,23 +85,24 @@ int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, in
     case SN_I32: snr::k_fill_uniform<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, low, range, seed, offset); break;
     case SN_F32: snr::k_fill_uniform<float><<<grid, 256, 0, st>>>((float*)dst, count, low, range, seed, offset); break;
     case SN_F64: snr::k_fill_uniform<double><<<grid, 256, 0, st>>>((double*)dst, count, low, range, seed, offset); break;
-    default: return SN_ERR_INVALID;
+    default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
   }
-  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
 }
 
 int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
                               uint64_t offset, void* stream) {
-  if (!dst || count < 1 || sd < 0) return SN_ERR_INVALID;
+  using sn_detail::fail;
+  if (!dst || count < 1 || sd < 0) return fail(SN_ERR_INVALID, "sn_fill_normal_demand: dst NULL, count < 1 or negative sd");
   const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case SN_I32: snr::k_fill_normal_demand<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, (float)mean, (float)sd, seed, offset); break;
     case SN_F32: snr::k_fill_normal_demand<float><<<grid, 256, 0, st>>>((float*)dst, count, (float)mean, (float)sd, seed, offset); break;
     case SN_F64: snr::k_fill_normal_demand<double><<<grid, 256, 0, st>>>((double*)dst, count, (float)mean, (float)sd, seed, offset); break;
-    default: return SN_ERR_INVALID;
+    default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
   }
-  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
 // the 112-byte-per-thread pattern reaches L2 as full lines.
 #include "../../include/supplynet.h"
+#include "supplynet_error.h"
 #include "supplynet_core.cuh"
 #include "supplynet_tree.cuh"
 #include "supplynet_net.cuh"
@@ -718,9 +719,8 @@ k_heuristic(const __grid_constant__ sn_policy pol, int ncols, int64_t n, const f
 // ==========================================================================================
 // Host side: validation, spec lowering, launches.
 // ==========================================================================================
-namespace {
-
-thread_local char g_err[512] = "";
+namespace sn_detail {
+static thread_local char g_err[512] = "";
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -729,6 +729,11 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+const char* last_error() { return g_err; }
+}  // namespace sn_detail
+
+namespace {
+using sn_detail::fail;
 
 bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && std::fabs(x) < 2147483647.0; }
 
@@ -1144,7 +1149,7 @@ extern "C" {
 
 int32_t sn_abi_version(void) { return SN_ABI_VERSION; }
 
-const char* sn_last_error(void) { return g_err; }
+const char* sn_last_error(void) { return sn_detail::last_error(); }
 
 int32_t sn_obs_dim(const sn_spec* spec) {
   if (spec == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");

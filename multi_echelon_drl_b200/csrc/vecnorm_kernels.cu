@@ -13,6 +13,7 @@
 // size is a multiple of obs_dim), a one-block finalize that merges them into the running statistics,
 // and an elementwise apply.
 #include "../../include/supplynet.h"
+#include "supplynet_error.h"
 
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -152,28 +153,35 @@ extern "C" {
 int32_t sn_vecnorm_update(int64_t n_envs, int32_t obs_dim, const float* obs, const float* reward, double gamma,
                           double* returns, const double* obs_rms_in, double* obs_rms_out, const double* ret_rms_in,
                           double* ret_rms_out, double* scratch, void* stream) {
-  if (n_envs < 1 || obs_dim < 1 || obs_dim > snv::kMaxOd) return SN_ERR_INVALID;
-  if (!obs || !obs_rms_in || !obs_rms_out || !ret_rms_in || !ret_rms_out || !scratch) return SN_ERR_INVALID;
-  if (reward && !returns) return SN_ERR_INVALID;
+  using sn_detail::fail;
+  if (n_envs < 1 || obs_dim < 1 || obs_dim > snv::kMaxOd)
+    return fail(SN_ERR_INVALID, "sn_vecnorm_update: n_envs=%lld, obs_dim=%d (1..%d)", (long long)n_envs, obs_dim, snv::kMaxOd);
+  if (!obs || !obs_rms_in || !obs_rms_out || !ret_rms_in || !ret_rms_out || !scratch)
+    return fail(SN_ERR_INVALID, "sn_vecnorm_update: obs, the four statistics buffers and scratch must be non-NULL");
+  if (reward && !returns) return fail(SN_ERR_INVALID, "sn_vecnorm_update: returns must be given with reward");
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * obs_dim + 2), st) != cudaSuccess) return SN_ERR_CUDA;
+  if (cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * obs_dim + 2), st) != cudaSuccess)
+    return fail(SN_ERR_CUDA, "sn_vecnorm_update: clearing scratch failed");
   const int tpb = threads_for(obs_dim);
   snv::k_moments<<<blocks_for(n_envs, obs_dim, tpb), 256, 0, st>>>(n_envs, obs_dim, tpb, obs, reward, gamma, returns, scratch);
   snv::k_finalize<<<1, 64, 0, st>>>(n_envs, obs_dim, reward != nullptr, scratch, obs_rms_in, obs_rms_out, ret_rms_in, ret_rms_out);
-  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_vecnorm: kernel launch failed");
 }
 
 int32_t sn_vecnorm_apply(int64_t n_envs, int32_t obs_dim, const float* obs, float* obs_out, const float* reward,
                          float* reward_out, const double* obs_rms, const double* ret_rms, float clip_obs,
                          float clip_reward, double epsilon, int32_t reset_returns, double* returns, void* stream) {
-  if (n_envs < 1 || obs_dim < 1 || obs_dim > snv::kMaxOd) return SN_ERR_INVALID;
-  if ((obs && (!obs_out || !obs_rms)) || (reward && (!reward_out || !ret_rms))) return SN_ERR_INVALID;
-  if (reward && reset_returns && !returns) return SN_ERR_INVALID;
+  using sn_detail::fail;
+  if (n_envs < 1 || obs_dim < 1 || obs_dim > snv::kMaxOd)
+    return fail(SN_ERR_INVALID, "sn_vecnorm_apply: n_envs=%lld, obs_dim=%d (1..%d)", (long long)n_envs, obs_dim, snv::kMaxOd);
+  if ((obs && (!obs_out || !obs_rms)) || (reward && (!reward_out || !ret_rms)))
+    return fail(SN_ERR_INVALID, "sn_vecnorm_apply: an input was given without its output / statistics buffer");
+  if (reward && reset_returns && !returns) return fail(SN_ERR_INVALID, "sn_vecnorm_apply: reset_returns needs returns");
   const int tpb = threads_for(obs_dim);
   snv::k_apply<<<blocks_for(n_envs, obs_dim, tpb), 256, 0, (cudaStream_t)stream>>>(
       n_envs, obs_dim, tpb, obs, obs_out, reward, reward_out, obs_rms, ret_rms, clip_obs, clip_reward, epsilon,
       reset_returns, returns);
-  return cudaGetLastError() == cudaSuccess ? SN_OK : SN_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_vecnorm: kernel launch failed");
 }
 
 }  // extern "C"

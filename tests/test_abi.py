@@ -118,3 +118,17 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "beergame_c" not in txt and "beergame_np" not in txt, f
+
+
+def test_every_entry_point_reports_through_sn_last_error(lib):
+    """Argument errors of the VecNormalize and table-fill entry points carry a message too (one error channel for the
+    whole library, csrc/supplynet_error.h)."""
+    from multi_echelon_drl_b200 import _lib
+    rc = lib.sn_vecnorm_apply(10, 99, None, None, None, None, None, None, 1.0, 1.0, 1e-8, 0, None, None)
+    assert rc == _lib.SN_ERR_INVALID and b"obs_dim=99" in lib.sn_last_error()
+    rc = lib.sn_vecnorm_update(0, 28, None, None, 0.99, None, None, None, None, None, None, None)
+    assert rc == _lib.SN_ERR_INVALID and b"sn_vecnorm_update" in lib.sn_last_error()
+    rc = lib.sn_fill_uniform(_lib.SN_I32, None, 10, 0, 5, 1, 0, None)
+    assert rc == _lib.SN_ERR_INVALID and b"sn_fill_uniform" in lib.sn_last_error()
+    with pytest.raises(ValueError, match="sn_fill_uniform"):
+        _lib.check(rc)
