@@ -139,7 +139,7 @@ def test_graphed_update_equals_eager_in_effect_and_is_faster():
     la, lb = critic_loss(a), critic_loss(b)
     assert la < 0.5 * l0 and lb < 0.5 * l0 and 0.33 < la / lb < 3.0, (l0, la, lb)
     # targets moved by Polyak averaging in both
-    assert times[True] < times[False], times
+    assert times[True] < 0.8 * times[False], times          # measured: 0.5 vs 1.66 ms per update
     print("update ms per step: eager %.3f graph %.3f" % (times[False] / 401, times[True] / 401))
 
 
