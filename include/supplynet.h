@@ -84,7 +84,8 @@ typedef struct sn_spec {
    * copies of the chain: with n_items = I > 1 the batch holds n_envs*I chains, chain c = env*I + item
    * (item-minor), so the row-major observation [n_chains][7*F'] IS the concatenation over items
    * [n_envs][I*7*F'] and likewise for actions; rewards are per chain.  Item 0 uses holding_cost /
-   * backorder_cost above, item i >= 1 uses item_*_cost[i-1].  n_items = 0 is read as 1. */
+   * backorder_cost above, item i >= 1 uses item_*_cost[i-1].  n_items = 0 is read as 1.  Serial chains only (any
+   * supported lead times and chain length); trees are single-item. */
   int32_t n_items;
   int32_t topology;                           /* SN_TOPO_CHAIN (0): the fields below are ignored; SN_TOPO_TREE */
   double item_holding_cost[SN_MAX_ITEMS - 1][SN_MAX_FACILITIES];

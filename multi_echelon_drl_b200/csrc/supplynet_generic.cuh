@@ -115,8 +115,8 @@ __device__ __forceinline__ void genv_reset(GEnv<T>& e, const DevSpec<T>& sp, con
 
 // One period; same algebra as env_step with run-time pipeline lengths.
 template <typename T>
-__device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, const T (&q)[kF], T d_next, bool terminal,
-                                          StepOut& out) {
+__device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, int item, const T (&q)[kF], T d_next,
+                                          bool terminal, StepOut& out) {
   T U4[kF];
 #pragma unroll
   for (int k = kF - 1; k >= 0; --k) {
@@ -156,8 +156,8 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, cons
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
-    out.hold[k] = -(double)e.inv[k] * sp.h[0][k];
-    out.back[k] = -(double)unfk * sp.b[0][k];
+    out.hold[k] = -(double)e.inv[k] * sp.h[item][k];        // item: cost vector of this chain (0 for single-item batches)
+    out.back[k] = -(double)unfk * sp.b[item][k];
     ch += out.hold[k];
     cb += out.back[k];
   }

@@ -226,9 +226,9 @@ struct GenOps {
     genv_reset(e, sp, in, d0);
   }
   template <bool MULTI>
-  static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int, const T (&q)[kF], T dn, bool terminal,
+  static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int item, const T (&q)[kF], T dn, bool terminal,
                                               StepOut& so) {
-    genv_step(e, sp, q, dn, terminal, so);
+    genv_step(e, sp, MULTI ? item : 0, q, dn, terminal, so);
   }
 };
 
@@ -763,8 +763,8 @@ int validate(const sn_spec* s, int dtype) {
       return fail(SN_ERR_UNSUPPORTED, "arc %d: information + shipment lead time %d+%d > 5; the reference keeps five pipeline "
                                       "slots (network_components.py:168) and fails its own on_order assertion beyond that", k, li, ls);
   }
-  if (!is_standard(s) && s->n_items > 1)
-    return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported for the beer game's chain and lead times only");
+  if (is_tree(s) && s->n_items > 1)
+    return fail(SN_ERR_UNSUPPORTED, "multi-item batches are supported for serial chains only");
   if (s->n_agents < 1 || s->n_agents > s->n_facilities) return fail(SN_ERR_INVALID, "n_agents=%d out of range", s->n_agents);
   int seen = 0, lo = SN_MAX_FACILITIES, hi = -1;
   for (int i = 0; i < s->n_agents; ++i) {
@@ -1101,7 +1101,10 @@ void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::
                         const sn::RolloutPtrs& out, int tma, cudaStream_t st, const void* init, float* obs0) {
 #define SN_ARGS d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0
   if (is_tree(spec)) launch_rollout<T, POLICY, false, false, sn::TreeOps<T>>(SN_ARGS);
-  else if (!is_standard(spec)) launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
+  else if (!is_standard(spec)) {
+    if (d.n_items > 1) launch_rollout<T, POLICY, false, true, sn::GenOps<T>>(SN_ARGS);
+    else launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
+  }
   else if (is_identity(spec)) {
     if (d.n_items > 1) launch_rollout<T, POLICY, true, true, sn::StdOps<T>>(SN_ARGS);
     else launch_rollout<T, POLICY, true, false, sn::StdOps<T>>(SN_ARGS);

@@ -137,3 +137,52 @@ def test_vecenv_on_a_two_facility_chain():
     assert stats[4] == 0 and stats[5] == 0 and stats[8] == 0 and stats[9] == 0     # phantom nodes cost nothing
     with pytest.raises(ValueError):
         replace(spec, agents=(2,))
+
+
+def test_multi_item_batches_on_other_lead_times_and_a_short_chain():
+    """Items are independent copies of the chain with their own cost vectors (multi_item.py); with lead times other
+    than the beer game's, and on a 3-facility chain, the interleaved batch equals one single-item run per item:
+    same observations, reward = sum over items; stepwise and as one fused episode launch."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import uniform_spec
+    from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    u = uniform_spec(None, True)
+    chains = [replace(u, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
+              replace(u, n_facilities=3, agents=(0, 1, 2), info_leadtime=(2, 1, 2), ship_leadtime=(2, 3, 1), holding_cost=u.holding_cost[:3],
+                      backorder_cost=u.backorder_cost[:3], coplayer_target=u.coplayer_target[:3])]
+    for base in chains:
+        nf, n = base.n_facilities, 1500
+        items = [base, replace(base, holding_cost=(0.75, 0.3, 1.0, 0.25)[:nf], backorder_cost=(2.0, 1.0, 0.5, 3.0)[:nf]),
+                 replace(base, holding_cost=(0.1,) * nf, backorder_cost=(4.0,) * nf)]
+        mi = MultiItemSupplyNetwork(items, n)
+        rs = np.random.RandomState(12)
+        inputs = [bulk_episode_inputs(base, n, rs) for _ in items]
+        init = np.stack([x[0] for x in inputs], axis=1)                  # [n, I, 36]
+        dem = np.stack([x[1] for x in inputs], axis=1)                   # [n, I, 103]
+        acts = rs.randint(-1, 19, (100, n, len(items) * nf))
+        mi.load_episode(init, dem)
+        singles = []
+        for i, sp in enumerate(items):
+            s = BatchedSupplyNetwork(sp, n)
+            s.load_episode(*inputs[i])
+            singles.append(s)
+        o = mi.reset()
+        for i, s in enumerate(singles):
+            assert torch.equal(o[:, i * 7 * nf:(i + 1) * 7 * nf], s.reset())
+        r64 = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in items]
+        for t in range(100):
+            o, r, done = mi.step(torch.as_tensor(acts[t]))
+            tot = torch.zeros(n, dtype=torch.float64, device="cuda")
+            for i, s in enumerate(singles):
+                so, _, _ = s.step(torch.as_tensor(acts[t][:, i * nf:(i + 1) * nf]), reward64_out=r64[i])
+                assert torch.equal(o[:, i * 7 * nf:(i + 1) * 7 * nf], so), (t, i)
+                tot += r64[i]
+            assert torch.equal(r, tot.float()), t
+        assert done
+        # the fused episode kernel picks the item's cost vector too
+        a_all = torch.as_tensor(acts).reshape(100, n * len(items), nf)
+        mi.sim.episode(100, actions=a_all)
+        expect = torch.stack([s.ep_return for s in singles], dim=1).sum(1)
+        assert torch.equal(mi.ep_return, expect)
