@@ -315,3 +315,14 @@ def test_short_chain_specs_and_yaml():
     assert sp.coplayer_target == (19, 20)
     with pytest.raises(ValueError):               # no demand source left (other names go down the tree path, which says so)
         specs_from_config(dict(nodes=cfg["nodes"][1:], arcs=cfg["arcs"][:1]), ["wholesaler"])
+
+
+def test_bind_to_gpu_cpus_is_a_no_op_without_a_gpu():
+    """bench.py pins each rank to its GPU's CPUs before allocating pinned buffers; without NVML / a GPU (this
+    container) or on single-node VMs nothing changes and None is returned."""
+    import os
+    from multi_echelon_drl_b200.distributed import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_cpus(0) is None or isinstance(bind_to_gpu_cpus(0), list)
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
