@@ -330,3 +330,39 @@ def test_random_tree_specs_lower_consistently():
                 orc.step(acts[t])
                 orc.check_invariant()
                 assert all((x >= 0).all() for x in orc.inv + orc.B + orc.unf_ind)
+
+
+def test_eight_node_spec_host_side():
+    """Host logic for trees of five to eight nodes: 72-word init layout, per-source demand tables, 8-wide C arrays,
+    limits (nine nodes, chains longer than four)."""
+    import ctypes as C
+    from dataclasses import replace
+    from multi_echelon_drl_b200 import _lib, uniform_spec
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.utils.demands import _fixed_init, bulk_episode_inputs, init_layout as product_layout
+    c = BIG_TREE_CASES[[x["topo"] for x in BIG_TREE_CASES].index("eight_hub")]
+    sp = tree_product_spec(c)
+    assert sp.n_facilities == 8 and sp.n_sources == 6 and sp.obs_dim == 7 * (8 if c["glob"] else len(c["agents"]))
+    n_words, so_off, sh_off = product_layout(sp)
+    assert n_words == 72 and so_off[:2] == (8, 12) and sh_off[:2] == (40, 44)
+    init, dem = bulk_episode_inputs(sp, 32, np.random.RandomState(0))
+    assert init.shape == (32, 72) and dem.shape == (32, 6, 103)
+    for k in range(8):                                     # slots beyond an arc's lead time stay empty
+        assert not init[:, so_off[k] + sp.info_leadtime[k]: so_off[k] + 4].any()
+        assert not init[:, sh_off[k] + sp.ship_leadtime[k]: sh_off[k] + 4].any()
+    fixed = _fixed_init(replace(sp, random_init=False))
+    assert fixed.shape == (72,) and (fixed[:8] == sp.fixed_inventory).all()
+    cs = sp.to_c()
+    assert len(cs.supplier) == 8 and list(cs.supplier) == list(sp.suppliers) and cs.topology == _lib.SN_TOPO_TREE
+    lib = _lib.load()
+    assert lib.sn_spec_validate(C.byref(cs), _lib.SN_F32) == 0
+    cs.n_facilities = 9
+    assert lib.sn_spec_validate(C.byref(cs), _lib.SN_F32) == _lib.SN_ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):               # nine internal nodes
+        tree_spec([dict(name=f"n{i}", demand=(0, 4) if i == 0 else None) for i in range(9)],
+                  [("ext", "n8", 1, 1)] + [(f"n{i + 1}", f"n{i}", 1, 1) for i in range(8)], ["n0"])
+    with pytest.raises(ValueError):                        # a plain chain spec stays limited to four facilities
+        replace(uniform_spec(None, True), n_facilities=5)
+    chain5 = uniform_spec(None, True).to_c()               # and so does the C side
+    chain5.n_facilities = 5
+    assert lib.sn_spec_validate(C.byref(chain5), _lib.SN_I32) == _lib.SN_ERR_UNSUPPORTED
