@@ -269,3 +269,27 @@ def test_big_tree_rewards_with_cost_coefficients_that_round():
     for t in range(100):
         total = total + rew[t]                       # the kernel accumulates the episode return period by period
     assert np.array_equal(sim.ep_return.cpu().numpy(), total)
+
+
+def test_single_env_on_big_trees_replays_the_reference_episodes():
+    """The gym-style single env on five- to eight-node networks: `np.random.seed(s); env.reset(); env.step(a)...`
+    reproduces the reference's observations and rewards (golden cases), and `sn.get_state(name)` reads any node."""
+    import warnings
+    from multi_echelon_drl_b200.gym_env import BeerGameEnv
+    for cid in (0, 7, 13, 26, 41, 55):
+        c = BIG_TREE_CASES[cid]
+        env = BeerGameEnv(tree_product_spec(c), "cuda", "int32")
+        assert env.sn.order_sequence == c["order_sequence"] + ["external_supplier"]
+        np.random.seed(c["seed"])
+        assert np.array_equal(env.reset(), c["obs0"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)          # golden actions include negative orders
+            for t in range(100):
+                obs, r, done, _ = env.step(c["actions"][t])
+                assert np.array_equal(obs, c["obs"][t]) and r == c["rew"][t], (cid, t)
+        assert done
+        last = c["names"][-1]
+        st = env.sn.get_state(last)
+        if c["glob"]:
+            assert st["on_hand"] == c["obs"][-1][7 * (len(c["names"]) - 1)]
+        assert set(st) == {"on_hand", "unfilled_demand", "latest_demand"} | {f"unreceived_pipeline_{i}" for i in range(4)}
