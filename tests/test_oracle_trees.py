@@ -366,3 +366,35 @@ def test_eight_node_spec_host_side():
     chain5 = uniform_spec(None, True).to_c()               # and so does the C side
     chain5.n_facilities = 5
     assert lib.sn_spec_validate(C.byref(chain5), _lib.SN_I32) == _lib.SN_ERR_UNSUPPORTED
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_harness", fromlist=["x"]).reference_available(),
+                    reason="/root/reference not mounted (GPU box)")
+def test_tree_oracle_float_actions_vs_live_reference():
+    """Fractional (TD3-like) float32 actions on trees: the reference runs them in mixed float32 / Python arithmetic
+    (numpy >= 2 scalar rules); the float64 restatement agrees to 1e-6 relative plus an absolute term for cancellation
+    residues of O(100) quantities - the tolerance the GPU float tests use against the restatement."""
+    from oracle import ref_harness as H
+    rs = np.random.RandomState(515)
+    for i in range(12):
+        c = random_tree_case(rs, None if i < 8 else 5 + i % 4)
+        names = c["names"]
+        nd = [dict(name=names[k], target=c["target"][k], holding=c["holding"][k], backorder=c["backorder"][k],
+                   demand=c["demand"][k]) for k in range(len(names))]
+        arcs = [("external_supplier" if c["supplier"][k] < 0 else names[c["supplier"][k]], names[k], c["li"][k], c["ls"][k])
+                for k in c["arc_order"]]
+        env = H.make_network_env(nd, arcs, [names[a] for a in c["agents"]], c["glob"],
+                                 dplusa=(-8, 0, 16) if c["rule"] == "d+a" else None)
+        acts = (rs.rand(100, len(c["agents"])) * 18 - 1).astype(np.float32)
+        r = H.network_rollout(env, names, [a for a in acts], seed=8000 + i)
+        inv0, so, sh, dem = r["init"]
+        N = len(inv0)
+        orc = TreeOracle(oracle_spec(c), 1, dtype=np.float64)
+        o0 = orc.reset(np.array([inv0], dtype=np.float64), [np.array([x], dtype=np.float64) for x in so],
+                       [np.array([x], dtype=np.float64) for x in sh], np.asarray(dem)[None])
+        assert np.array_equal(o0[0], r["obs0"])
+        for t in range(100):
+            o, rew, _ = orc.step(acts[t][None].astype(np.float64))
+            np.testing.assert_allclose(o[0], r["obs"][t], rtol=1e-6, atol=2e-4, err_msg=str((i, t)))
+            np.testing.assert_allclose(rew[0], r["rew"][t], rtol=1e-6, atol=2e-3, err_msg=str((i, t)))
+        assert N == len(names)
