@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 7
+#define SN_ABI_VERSION 8
 
 #define SN_MAX_FACILITIES 8     /* size of the per-facility arrays; chains and the register-resident kernels use up to 4 */
 #define SN_MAX_CHAIN 4          /* chains, and trees on the register-resident kernels */
@@ -41,6 +41,16 @@ extern "C" {
 #define SN_NET_STATE_WORDS 128  /* trees of 5..8 nodes: 16 words per node (inv, unf_ind, latest, U[4], info[3], ship[4], backlog, demand) */
 #define SN_NET_INIT_WORDS 72    /* trees of 5..8 nodes: inv[8]; so[k][0..3] at 8+4k; sh[k][0..3] at 40+4k */
 #define SN_STATS_WORDS 16
+#define SN_QTY_LIMIT_LOG2 26    /* SN_I32 is exact while orders, stocks and backlogs stay below 2^26 (see stats[13]) */
+
+/* Device control words of sn_step_ex (int32[SN_CTL_WORDS], caller-owned, zero-initialised):
+ * the period lives in device memory so that ONE captured CUDA graph serves every period of an episode. */
+#define SN_CTL_WORDS 4
+#define SN_CTL_PERIOD 0         /* period to play; read by the launch and advanced by it (set to 0 to start an episode) */
+#define SN_CTL_TICKET 1         /* internal (block ticket); leave at 0                                               */
+#define SN_CTL_FLAGS 2          /* sticky SN_FLAG_* bits                                                             */
+#define SN_FLAG_STEP_AFTER_TERMINAL 1   /* a launch found period >= max_episode_steps and did nothing (envs.py:88-89) */
+#define SN_FLAG_QTY_RANGE 2             /* SN_I32: a quantity reached 2^SN_QTY_LIMIT_LOG2, results may have wrapped    */
 
 enum { SN_I32 = 0, SN_F32 = 1, SN_F64 = 2 };
 enum { SN_RULE_A = 0, SN_RULE_D_PLUS_A = 1 };
@@ -169,12 +179,53 @@ int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
  *                 [0] env-steps, [1] sum reward, [2..5] sum holding cost per facility,
  *                 [6..9] sum backorder cost per facility (warp/block reduced, one atomic per block);
  *                 when the step ends the episode and ep_return is given also [10] episodes,
- *                 [11] sum of episode returns, [12] sum of squared episode returns
+ *                 [11] sum of episode returns, [12] sum of squared episode returns;
+ *                 [13] SN_I32 only: env-steps in which an action magnitude, order, inventory or backlog reached
+ *                 2^SN_QTY_LIMIT_LOG2 (the reference computes with unbounded Python ints; beyond that bound int32
+ *                 intermediates may wrap, so a non-zero count voids the bit-exactness claim for that run)
  * Returns SN_ERR_TERMINAL if period >= max_episode_steps. */
 int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period,
                 void* state, const void* actions, const void* demand_next,
                 float* obs, float* reward, double* reward64, double* cost, double* ep_return,
                 double* stats, void* stream);
+
+/* step, extended form — the same period step with the optional extras a device-resident training loop needs.
+ * sn_step(...) == sn_step_ex with ctl = env_reward = vn_* = NULL.
+ *   demand       ctl == NULL: the [ld] row(s) of period+1 exactly as sn_step's demand_next;
+ *                ctl != NULL: the whole table [max_episode_steps+3][...] as in sn_rollout (the launch picks the row)
+ *   period       host-side period; ignored when ctl != NULL
+ *   ctl          device int32[SN_CTL_WORDS] or NULL.  The launch plays period ctl[SN_CTL_PERIOD] and advances it
+ *                (envs.py:96), so identical launches (a replayed CUDA graph) walk through an episode; a launch that
+ *                finds the episode over does nothing and raises SN_FLAG_STEP_AFTER_TERMINAL in ctl[SN_CTL_FLAGS]
+ *   env_reward   device float [n_envs / n_items] (out, may be NULL; n_items 2 or 4): multi-item batches, reward of an
+ *                env = sum of its items' chain rewards in item order, in double, rounded once
+ *   vn_*         fused VecNormalize statistics (train_td3.py:100-101; needs ctl, beer-game lead times, n_items <= 1,
+ *                obs != NULL): RunningMeanStd.update(obs) into vn_obs_rms (mean[od], var[od], count) IN PLACE and, if
+ *                vn_returns != NULL, returns <- returns*vn_gamma + reward and RunningMeanStd.update(returns) into
+ *                vn_ret_rms (mean, var, count); vn_scratch is 2*obs_dim+2 doubles, zero before the first launch (the
+ *                launch leaves it zero).  Follow with sn_vecnorm_apply.  Not for the terminal step of an episode:
+ *                SB3 feeds the statistics the observation of the NEXT episode there (DummyVecEnv auto-reset). */
+typedef struct sn_step_io {
+  void* state;
+  const void* actions;
+  const void* demand;
+  int32_t period;
+  int32_t reserved;
+  int32_t* ctl;
+  float* obs;
+  float* reward;
+  float* env_reward;
+  double* reward64;
+  double* cost;
+  double* ep_return;
+  double* stats;
+  double* vn_scratch;
+  double* vn_obs_rms;
+  double* vn_ret_rms;
+  double* vn_returns;
+  double vn_gamma;
+} sn_step_io;
+int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const sn_step_io* io, void* stream);
 
 /* observation of the current state — SupplyNetwork.get_state (supplynetwork.py:114-171)
  * flattened as envs.py:103-110.  obs: device float [n_envs][obs_dim]. */
@@ -229,7 +280,7 @@ int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
  * obs_dim is at most 56 (7 numbers for each of up to 8 facilities).
  * sn_vecnorm_update: RunningMeanStd.update(obs) into obs_rms_out; if `reward` is given also
  *   returns <- returns*gamma + reward and RunningMeanStd.update(returns) into ret_rms_out
- *   (in/out buffers must differ; the caller swaps them).
+ *   (the in and out buffers may be the same: every statistic is read before any is written).
  * sn_vecnorm_apply: obs_out <- clip((obs-mean)/sqrt(var+eps), +-clip_obs);
  *   reward_out <- clip(reward/sqrt(ret_var+eps), +-clip_reward); returns <- 0 if reset_returns.
  *   Either the obs or the reward part may be skipped by passing NULL. */

@@ -17,7 +17,10 @@ SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 7
+ABI_VERSION = 8
+SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS = 4, 0, 1, 2
+SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
+SN_QTY_LIMIT_LOG2 = 26
 
 
 MAXF = 8            # SN_MAX_FACILITIES: size of the per-facility arrays (chains use the first four)
@@ -62,6 +65,18 @@ class SnPolicy(C.Structure):
     ]
 
 
+class SnStepIo(C.Structure):
+    """sn_step_io of include/supplynet.h: buffers of one period step (device pointers as integers / None)."""
+    _fields_ = [
+        ("state", C.c_void_p), ("actions", C.c_void_p), ("demand", C.c_void_p),
+        ("period", C.c_int32), ("reserved", C.c_int32),
+        ("ctl", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("env_reward", C.c_void_p),
+        ("reward64", C.c_void_p), ("cost", C.c_void_p), ("ep_return", C.c_void_p), ("stats", C.c_void_p),
+        ("vn_scratch", C.c_void_p), ("vn_obs_rms", C.c_void_p), ("vn_ret_rms", C.c_void_p),
+        ("vn_returns", C.c_void_p), ("vn_gamma", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/supplynet.h one to one
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
@@ -73,6 +88,7 @@ SIGNATURES = {
     "sn_init_words": (_I32, [C.POINTER(SnSpec)]),
     "sn_reset": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P, _P, _P]),
     "sn_step": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_step_ex": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, C.POINTER(SnStepIo), _P]),
     "sn_observe": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _P, _P, _P]),
     "sn_heuristic": (_I32, [C.POINTER(SnPolicy), _I32, _I64, _P, _P, _P]),
     "sn_rollout": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace sn {
 
@@ -87,6 +88,8 @@ struct Env {
   __device__ __forceinline__ T latest(int k) const { return lat[k]; }                       // supplynetwork.py:139
   // co-player that orders inside before_action (chain position below the first agent)
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return k < kF - 1 && k < sp.lo; }
+  // words outside inv[] / B[] that enter sums unclipped (range guard of the integer path, see qty_mask)
+  __device__ __forceinline__ uint32_t extra_qty_mask() const { return (uint32_t)unf_ind | (uint32_t)lat[0]; }
 };
 
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
@@ -225,6 +228,35 @@ __device__ __forceinline__ void emit_obs(const E& e, const DevSpec<T>& sp, bool 
     SN_EMIT_NODE(0) SN_EMIT_NODE(1) SN_EMIT_NODE(2) SN_EMIT_NODE(3)
 #undef SN_EMIT_NODE
   }
+}
+
+// Range guard of the integer path.  The reference computes with Python ints (unbounded); int32 rollouts equal it
+// exactly while no intermediate wraps, which holds as long as every order and every stock / backlog stays below
+// 2^26 (67,108,864): pipelines and on-order sums are sums of at most a handful of such terms.  The kernels report
+// (never correct) an env-step whose action magnitude, order, inventory or backlog reached that bound: a sticky count
+// in stats[13] / bit 1 of ctl[2].  Floating-point paths have no such limit.
+constexpr int kQtyLimitLog2 = 26;
+// OR of the magnitudes to be watched after a step; ORDERS = also the raw actions and the orders placed (not needed
+// when both come from a clipped in-kernel policy).  The remaining words are bounded by these: pipelines hold
+// earlier orders, shipments are min(inventory, backlog), on-order sums have at most eight such terms.
+template <bool ORDERS, typename T, typename E>
+__device__ __forceinline__ uint32_t qty_mask(const E& e, const T (&a)[kF], const T (&q)[kF]) {
+  if constexpr (std::is_same<T, int32_t>::value) {
+    uint32_t m = e.extra_qty_mask();
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+      m |= (uint32_t)e.inv[k] | (uint32_t)e.B[k];
+      if (ORDERS) m |= (uint32_t)q[k] | (uint32_t)(a[k] ^ (a[k] >> 31));
+    }
+    return m;
+  } else {
+    return 0u;
+  }
+}
+__device__ __forceinline__ bool qty_mask_over(uint32_t m) { return (m >> kQtyLimitLog2) != 0; }
+template <typename T, typename E>
+__device__ __forceinline__ bool qty_overflow(const E& e, const T (&a)[kF], const T (&q)[kF]) {
+  return qty_mask_over(qty_mask<true>(e, a, q));
 }
 
 struct StepOut {

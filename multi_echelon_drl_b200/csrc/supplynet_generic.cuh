@@ -31,6 +31,7 @@ struct GEnv {
   __device__ __forceinline__ T unfilled(int k, const DevSpec<T>&) const { return k == 0 ? lat[0] + unf_ind : B[k - 1]; }
   __device__ __forceinline__ T latest(int k) const { return lat[k]; }
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return k < kF - 1 && k < sp.lo; }
+  __device__ __forceinline__ uint32_t extra_qty_mask() const { return (uint32_t)unf_ind | (uint32_t)lat[0]; }
 };
 
 template <typename T>

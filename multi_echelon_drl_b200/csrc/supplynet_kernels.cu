@@ -22,9 +22,12 @@
 #include "supplynet_tree.cuh"
 #include "supplynet_net.cuh"
 
+#include <cuda.h>              // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -61,24 +64,28 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 struct ObsStager {
   float* smem;     // this warp's staging area: [2][32*28] floats
   int lane;
+  int cur;         // staging buffer of the next store; toggled by every commit, so two consecutive stores of a
+                   // warp never share a buffer whatever the caller's step parity is
   __device__ __forceinline__ ObsStager(float* block_smem) {
     lane = threadIdx.x & 31;
+    cur = 0;
     smem = block_smem + (threadIdx.x >> 5) * (2 * 32 * 28);
   }
-  // Staging row of this lane in buffer `buf`.  `buf` alternates 0/1 between consecutive stores of
-  // the same warp; at most one earlier bulk store may still be reading the other buffer.
-  __device__ __forceinline__ float* begin(int od, int buf) {
+  // Staging row of this lane in the current buffer.  At most one earlier bulk store (the one that used the
+  // other buffer) may still be reading shared memory.
+  __device__ __forceinline__ float* begin(int od) {
     if (lane == 0) bulk_wait_read<1>();
     __syncwarp();
-    return smem + buf * (32 * 28) + lane * od;
+    return smem + cur * (32 * 28) + lane * od;
   }
-  __device__ __forceinline__ void commit(float* gdst_warp, int od, int buf) {
+  __device__ __forceinline__ void commit(float* gdst_warp, int od) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      bulk_store_s2g(gdst_warp, smem + buf * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
+      bulk_store_s2g(gdst_warp, smem + cur * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
       bulk_commit();
     }
+    cur ^= 1;
   }
   __device__ __forceinline__ void drain() {
     if (lane == 0) bulk_wait_read<0>();
@@ -91,12 +98,12 @@ struct ObsStager {
 template <bool IDENT, typename T, typename E>
 __device__ __forceinline__ void write_obs(ObsStager& st, const E& e, const DevSpec<T>& sp, bool terminal,
                                           float* __restrict__ gobs, int64_t env, int64_t n, int od, bool valid,
-                                          int buf, bool use_tma) {
+                                          bool use_tma) {
   const int64_t env0 = env - st.lane;
   if (use_tma && env0 + 32 <= n) {
-    float* row = st.begin(od, buf);
+    float* row = st.begin(od);
     emit_obs<IDENT>(e, sp, terminal, row);
-    st.commit(gobs + env0 * od, od, buf);
+    st.commit(gobs + env0 * od, od);
   } else if (valid) {
     emit_obs<IDENT>(e, sp, terminal, gobs + env * od);
   }
@@ -140,6 +147,28 @@ __device__ __forceinline__ void store_actions_f32(float* __restrict__ dst, int64
   }
 }
 
+// the same from a shared-memory tile of action rows ([tile][n_agents], row `row`)
+template <bool IDENT, typename T>
+__device__ __forceinline__ void load_actions_smem(const T* s_act, int row, const DevSpec<T>& sp, T (&a)[kF]) {
+  if (IDENT) {
+    if (sizeof(T) == 4) {
+      const int4 v = *reinterpret_cast<const int4*>(s_act + row * 4);
+      a[0] = *reinterpret_cast<const T*>(&v.x);
+      a[1] = *reinterpret_cast<const T*>(&v.y);
+      a[2] = *reinterpret_cast<const T*>(&v.z);
+      a[3] = *reinterpret_cast<const T*>(&v.w);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kF; ++k) a[k] = s_act[row * 4 + k];
+    }
+  } else {
+    const T* p = s_act + row * sp.n_agents;
+#pragma unroll
+    for (int k = 0; k < kF; ++k)
+      if (sp.slot[k] >= 0) a[k] = p[sp.slot[k]];
+  }
+}
+
 // block-level reduction of per-thread totals into stats[] (one atomic per block per word)
 template <int NV, int WARPS>
 __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __restrict__ stats, double* red /*[WARPS][NV]*/) {
@@ -165,9 +194,13 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* __rest
 template <typename T>
 struct StdOps {
   static constexpr bool kWide = false;
+  static constexpr int kWords = kStateWords;       // rows of the state buffer
+  static constexpr int kMaxSrc = 1;                // demand rows per period
   using E = Env<T>;
   using D = T;                                     // demand of one period: one number per env
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
+  static __device__ __forceinline__ int n_src(const DevSpec<T>&) { return 1; }
+  static __device__ __forceinline__ D load_demand_smem(const T* row, int, int col, const DevSpec<T>&) { return row[col]; }
   static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t, int64_t env, const DevSpec<T>&) {
     return __ldg(row + env);
   }
@@ -286,7 +319,7 @@ k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* _
   }
   if (obs != nullptr) {
     ObsStager st(smem_f);
-    write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
     st.drain();
   }
 }
@@ -301,7 +334,7 @@ k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T*
   typename Ops::E e;
   if (valid) Ops::load(sp, state, ld, env, e);
   ObsStager st(smem_f);
-  write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
+  write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
   st.drain();
 }
 
@@ -312,19 +345,63 @@ struct StepPtrs {
   double* cost;
   double* ep_return;
   double* stats;
+  float* env_reward;        // multi-item batches: reward of env = sum over its n_items adjacent chains, [n/n_items]
+  int32_t* ctl;             // device control words (SN_CTL_*) or NULL: period read from / advanced in device memory
+  // fused VecNormalize statistics (tiled kernel only; all NULL = off)
+  double* vn_scratch;       // [2*od + 2], zero between launches
+  double* vn_obs_rms;       // mean[od], var[od], count  (updated in place by the last block)
+  double* vn_ret_rms;       // mean, var, count
+  double* vn_returns;       // [n] discounted returns (NULL = observations only)
+  double vn_gamma;
 };
+
+// Period of this launch: the host's argument, or the device counter ctl[SN_CTL_PERIOD] (one captured CUDA graph
+// then serves every period of an episode).  The counter is advanced by the launch itself, by whichever block
+// finishes last (ticket in ctl[SN_CTL_TICKET]); every block reads it before it takes its ticket.
+__device__ __forceinline__ int launch_period(const int32_t* ctl, int period_arg) {
+  return ctl != nullptr ? *reinterpret_cast<const volatile int32_t*>(ctl + SN_CTL_PERIOD) : period_arg;
+}
+// true for exactly one thread of the grid: thread 0 of the block that finishes last
+__device__ __forceinline__ bool last_block_ticket(int32_t* ctl) {
+  __threadfence();
+  return atomicAdd(ctl + SN_CTL_TICKET, 1) == (int)gridDim.x - 1;
+}
+
+// Sum of the step rewards of the n_items adjacent chains of one env (item-minor batches, n_items 2 or 4: an
+// env never straddles a warp), in item order, in double.  Every lane of the warp must call; the lane of item 0
+// gets the total.
+__device__ __forceinline__ double env_reward_sum(double r, int n_items) {
+  const int lane = threadIdx.x & 31;
+  if (n_items == 2) {
+    const double o = __shfl_xor_sync(0xffffffffu, r, 1);
+    return (lane & 1) ? o + r : r + o;
+  }
+  const int base = lane & ~3;
+  const double r0 = __shfl_sync(0xffffffffu, r, base), r1 = __shfl_sync(0xffffffffu, r, base + 1);
+  const double r2 = __shfl_sync(0xffffffffu, r, base + 2), r3 = __shfl_sync(0xffffffffu, r, base + 3);
+  return ((r0 + r1) + r2) + r3;
+}
 
 template <typename T, bool IDENT, typename Ops>
 __global__ void __launch_bounds__(kBlock, SN_STEP_MIN_BLOCKS)
-k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
-       const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out, int use_tma) {
+k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int period_arg, T* __restrict__ state,
+       const T* __restrict__ actions, const T* __restrict__ demand, const StepPtrs out, int use_tma) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[kWarpsPerBlock * 13];
+  __shared__ double red[kWarpsPerBlock * 14];
+  const int period = launch_period(out.ctl, period_arg);
+  if (period >= sp.t_max) {                    // only reachable through the device counter (the host checks its own)
+    if (out.ctl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_STEP_AFTER_TERMINAL);
+    return;
+  }
+  const bool terminal = period + 1 >= sp.t_max;
+  // with a device counter `demand` is the whole table and the row of period+1 is picked here
+  const T* __restrict__ demand_next = out.ctl != nullptr ? demand + (int64_t)(period + 1) * Ops::dstride(sp, ld) : demand;
   const int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = env < n;
   typename Ops::E e;
   StepOut so;
   so.reward = 0.0;
+  bool over = false;
 #pragma unroll
   for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
   if (valid) {
@@ -334,8 +411,9 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     const typename Ops::D dn = Ops::load_demand(demand_next, ld, env, sp);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
-    if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal != 0, so);
-    else Ops::template step<false>(e, sp, 0, q, dn, terminal != 0, so);
+    if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal, so);
+    else Ops::template step<false>(e, sp, 0, q, dn, terminal, so);
+    over = qty_overflow(e, a, q);
     Ops::store(state, ld, env, e);
     if (out.reward) out.reward[env] = (float)so.reward;
     if (out.reward64) out.reward64[env] = so.reward;
@@ -348,26 +426,41 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int termina
     }
     if (out.ep_return) out.ep_return[env] += so.reward;
   }
+  if (out.env_reward != nullptr) {             // uniform branch: every lane takes part in the shuffles
+    const double tot = env_reward_sum(so.reward, sp.n_items);
+    if (valid && (env % sp.n_items) == 0) out.env_reward[env / sp.n_items] = (float)tot;
+  }
   if (out.obs != nullptr) {
     ObsStager st(smem_f);
-    write_obs<IDENT>(st, e, sp, terminal != 0, out.obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, terminal, out.obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
     st.drain();
   }
+  if (over && out.ctl != nullptr) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_QTY_RANGE);
   if (out.stats != nullptr) {
-    double v[13];
+    double v[14];
     v[0] = valid ? 1.0 : 0.0;
     v[1] = so.reward;
 #pragma unroll
     for (int k = 0; k < kF; ++k) { v[2 + k] = so.hold[k]; v[6 + k] = so.back[k]; }
     // episode moments (Monitor's episode statistics) when this step ends the episode
-    const bool ep = valid && terminal != 0 && out.ep_return != nullptr;
+    const bool ep = valid && terminal && out.ep_return != nullptr;
     const double ret = ep ? out.ep_return[env] : 0.0;
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ret;
     v[12] = ret * ret;
-    block_reduce_add<13, kWarpsPerBlock>(v, out.stats, red);
+    v[13] = over ? 1.0 : 0.0;
+    block_reduce_add<14, kWarpsPerBlock>(v, out.stats, red);
+  }
+  if (out.ctl != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0 && last_block_ticket(out.ctl)) {
+      out.ctl[SN_CTL_TICKET] = 0;
+      out.ctl[SN_CTL_PERIOD] = period + 1;
+    }
   }
 }
+
+#include "supplynet_step_tiled.cuh"
 
 struct RolloutPtrs {
   float* traj_obs;
@@ -407,13 +500,14 @@ rollout_body(const DevSpec<T>& sp, const DevPolicy<T>& pol, int64_t n, int64_t l
   if (init != nullptr) {
     // episode mode (sn_episode): reset in-kernel, the state never has to exist in HBM
     Ops::reset(e, sp, init, ld, envc, Ops::load_demand(demand, ld, envc, sp));
-    if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, 1, use_tma != 0);
+    if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, use_tma != 0);
   } else {
     Ops::load(sp, state, ld, envc, e);
   }
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+  uint32_t qmask = 0;                               // range guard of the integer path (supplynet_core.cuh: qty_mask)
   const int item = MULTI ? chain_item(sp, envc) : 0;
 
   // software pipeline: inputs of step s+1 are requested before step s is computed
@@ -446,17 +540,18 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     env_orders<IDENT>(e, sp, a, q);
     StepOut so;
     Ops::template step<MULTI>(e, sp, item, q, dn, terminal, so);
+    qmask |= qty_mask<POLICY == SN_POLICY_ACTIONS>(e, a, q);
     acc[0] += 1.0;
     acc[1] += so.reward;
 #pragma unroll
     for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
     if (out.traj_reward != nullptr && valid) out.traj_reward[(int64_t)s * n + env] = (float)so.reward;
     if (out.traj_obs != nullptr)
-      write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, s & 1, use_tma != 0);
+      write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, use_tma != 0);
   }
 
   const bool ended = (period0 + n_steps >= sp.t_max);
-  if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
+  if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, use_tma != 0);
   st.drain();
   double ep_total = acc[1];                 // return of the whole episode, if this launch can know it
   if (valid) {
@@ -467,7 +562,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     }
   }
   if (out.stats != nullptr) {
-    double v[13];
+    double v[14];
 #pragma unroll
     for (int i = 0; i < 10; ++i) v[i] = valid ? acc[i] : 0.0;
     // episode moments when the episode ends in this launch and its full return is known here
@@ -475,7 +570,8 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ep ? ep_total : 0.0;
     v[12] = ep ? ep_total * ep_total : 0.0;
-    block_reduce_add<13, kRolloutBlock / 32>(v, out.stats, red);
+    v[13] = (valid && qty_mask_over(qmask)) ? 1.0 : 0.0;       // envs (not env-steps) that left the exact int32 range
+    block_reduce_add<14, kRolloutBlock / 32>(v, out.stats, red);
   }
 }
 
@@ -489,7 +585,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
 template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 __global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock) k_rollout(SN_ROLLOUT_PARAMS) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[(kRolloutBlock / 32) * 13];
+  __shared__ double red[(kRolloutBlock / 32) * 14];
   rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
 }
 
@@ -498,7 +594,7 @@ __global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock) k_rollout(
 template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
 __global__ void __maxnreg__(144) k_rollout_wide(SN_ROLLOUT_PARAMS) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[(kRolloutBlock / 32) * 13];
+  __shared__ double red[(kRolloutBlock / 32) * 14];
   rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
 }
 
@@ -543,12 +639,28 @@ k_net_observe(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, cons
   lane_write_obs(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
 }
 
+// range guard of the integer path for one lane (= one node): see qty_mask in supplynet_core.cuh
+template <typename T>
+__device__ __forceinline__ uint32_t lane_qty_mask(const LaneEnv<T>& e, T a, T q) {
+  if constexpr (std::is_same<T, int32_t>::value)
+    return (uint32_t)e.inv | (uint32_t)e.B | (uint32_t)e.unf | (uint32_t)e.dem | (uint32_t)q | (uint32_t)(a ^ (a >> 31));
+  else
+    return 0u;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kNetBlock)
-k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int terminal, T* __restrict__ state,
-           const T* __restrict__ actions, const T* __restrict__ demand_next, const StepPtrs out) {
-  __shared__ double red[(kNetBlock / 32) * 13];
+k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int period_arg, T* __restrict__ state,
+           const T* __restrict__ actions, const T* __restrict__ demand, const StepPtrs out) {
+  __shared__ double red[(kNetBlock / 32) * 14];
   SN_NET_PROLOGUE;
+  const int period = launch_period(out.ctl, period_arg);
+  if (period >= sp.t_max) {
+    if (out.ctl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_STEP_AFTER_TERMINAL);
+    return;
+  }
+  const bool terminal = period + 1 >= sp.t_max;
+  const T* __restrict__ demand_next = out.ctl != nullptr ? demand + (int64_t)(period + 1) * ld * sp.n_src : demand;
   const NetPolicy<T> none{};
   const LaneCfg<T> c = lane_cfg(sp, none, valid);
   LaneEnv<T> e;
@@ -559,9 +671,10 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int ter
   T taken;
   const T q = lane_order<SN_POLICY_ACTIONS>(e, c, sp, none, masked_sum(bj, c.cust), a, taken);
   double hold, back;
-  lane_step(e, c, sp, q, lane_demand(c, demand_next, ld, env), terminal != 0, bj, hold, back);
+  lane_step(e, c, sp, q, lane_demand(c, demand_next, ld, env), terminal, bj, hold, back);
   const double reward = group_reward(hold, back, c.base, sp.exact_costs != 0);
   const T cb = masked_sum(bj, c.cust);
+  const bool over = c.active && qty_mask_over(lane_qty_mask(e, a, q));
   lane_store(e, c, state, ld, env);
   const bool head = valid && c.k == 0;                 // one lane per env reports
   if (c.active && out.cost) {
@@ -573,19 +686,28 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int ter
     if (out.reward64) out.reward64[env] = reward;
     if (out.ep_return) out.ep_return[env] += reward;
   }
-  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, terminal != 0, stage, out.obs + warp_env0 * od, n_valid);
+  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, terminal, stage, out.obs + warp_env0 * od, n_valid);
+  if (over && out.ctl != nullptr) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_QTY_RANGE);
   if (out.stats != nullptr) {
-    double v[13];
+    double v[14];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) v[i] = 0.0;          // [2..9]: per-facility sums are not kept for these networks
+    for (int i = 0; i < 14; ++i) v[i] = 0.0;          // [2..9]: per-facility sums are not kept for these networks
     v[0] = head ? 1.0 : 0.0;
     v[1] = head ? reward : 0.0;
-    const bool ep = head && terminal != 0 && out.ep_return != nullptr;
+    const bool ep = head && terminal && out.ep_return != nullptr;
     const double ret = ep ? out.ep_return[env] : 0.0;
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ret;
     v[12] = ret * ret;
-    block_reduce_add<13, kNetBlock / 32>(v, out.stats, red);
+    v[13] = over ? 1.0 : 0.0;                         // node-steps here (a lane is a node)
+    block_reduce_add<14, kNetBlock / 32>(v, out.stats, red);
+  }
+  if (out.ctl != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0 && last_block_ticket(out.ctl)) {
+      out.ctl[SN_CTL_TICKET] = 0;
+      out.ctl[SN_CTL_PERIOD] = period + 1;
+    }
   }
 }
 
@@ -595,9 +717,10 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
               int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
               const T* __restrict__ actions, const RolloutPtrs out, const T* __restrict__ init,
               float* __restrict__ obs0) {
-  __shared__ double red[(kNetBlock / 32) * 13];
+  __shared__ double red[(kNetBlock / 32) * 14];
   SN_NET_PROLOGUE;
   const LaneCfg<T> c = lane_cfg(sp, pol, valid);
+  uint32_t qmask = 0;
   const int64_t dstride = ld * sp.n_src, act_stride = n * sp.n_agents;
   const bool head = valid && c.k == 0;
   const bool acts = POLICY == SN_POLICY_ACTIONS && c.active && c.slot >= 0;
@@ -627,6 +750,7 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
       out.traj_actions[(int64_t)s * act_stride + act_off] = (float)taken;
     double hold, back;
     lane_step(e, c, sp, q, dn, terminal, bj, hold, back);
+    qmask |= lane_qty_mask(e, a, q);
     cb = weighted_sum(bj, c.cust_m);
     const double r = group_reward(hold, back, c.base, sp.exact_costs != 0);
     total += r;
@@ -643,16 +767,17 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
     out.ep_return[env] = ep_total;
   }
   if (out.stats != nullptr) {
-    double v[13];
+    double v[14];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) v[i] = 0.0;
+    for (int i = 0; i < 14; ++i) v[i] = 0.0;
     v[0] = head ? (double)n_steps : 0.0;
     v[1] = head ? total : 0.0;
     const bool ep = head && ended && (init != nullptr || out.ep_return != nullptr || period0 == 0);
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ep ? ep_total : 0.0;
     v[12] = ep ? ep_total * ep_total : 0.0;
-    block_reduce_add<13, kNetBlock / 32>(v, out.stats, red);
+    v[13] = (c.active && qty_mask_over(qmask)) ? 1.0 : 0.0;      // nodes that left the exact int32 range
+    block_reduce_add<14, kNetBlock / 32>(v, out.stats, red);
   }
 }
 #undef SN_NET_PROLOGUE
@@ -1062,15 +1187,103 @@ int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, fl
   return cuda_ok("sn_observe launch");
 }
 
+// SMs of the current device (the persistent tiled step launches one CTA per SM)
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+// SN_STEP_KERNEL=plain|tiled forces one implementation of the period step (A/B runs); default: by batch size
+int step_kernel_choice() {      // read per call: tests switch it between launches
+  const char* v = std::getenv("SN_STEP_KERNEL");
+  return (v && !std::strcmp(v, "plain")) ? 1 : (v && !std::strcmp(v, "tiled")) ? 2 : 0;
+}
+#ifndef SN_TILED_MIN_ENVS
+#define SN_TILED_MIN_ENVS 32768        // below this one period is launch latency either way; the plain kernel has the shorter prologue
+#endif
+
+// cuTensorMapEncodeTiled, fetched from the driver at run time (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+template <typename T> CUtensorMapDataType tensor_dtype();
+template <> CUtensorMapDataType tensor_dtype<int32_t>() { return CU_TENSOR_MAP_DATA_TYPE_INT32; }
+template <> CUtensorMapDataType tensor_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+template <> CUtensorMapDataType tensor_dtype<double>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT64; }
+
+template <typename T, bool IDENT>
+int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period, void* state, const void* actions,
+                      const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
+  using Ops = sn::StdOps<T>;
+  using C = sn::TileCfg<T, Ops>;
+  constexpr int kStages = SN_TILED_STAGES;
+  auto kern = &sn::k_step_tiled<T, IDENT, Ops, kStages>;
+  const size_t smem = C::smem_bytes(kStages);
+  static bool opted_in[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !opted_in[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail(SN_ERR_CUDA, "sn_step: %zu bytes of shared memory per block are not available", smem);
+    opted_in[dev] = true;
+  }
+  // the state matrix [words][ld] as a 2-D tensor: dim0 = env (contiguous), dim1 = state word (stride ld elements);
+  // one TMA copy moves a [words][kTile] box
+  const EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) return fail(SN_ERR_CUDA, "sn_step: cuTensorMapEncodeTiled is not available from this driver");
+  alignas(64) CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)C::kWords};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)C::kTile, (cuuint32_t)C::kWords};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult rc = enc(&tm, tensor_dtype<T>(), 2, state, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(SN_ERR_CUDA, "sn_step: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  const int64_t tiles = (n + C::kTile - 1) / C::kTile;
+  const int64_t sms = sm_count();
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  kern<<<grid, C::kThreads, smem, st>>>(d, tm, n, ld, period, (const T*)actions, (const T*)demand, out, tma_ok(out.obs));
+  return cuda_ok("sn_step launch");
+}
+
 template <typename T>
-int do_step(const sn_spec* spec, int64_t n, int64_t ld, int terminal, void* state, const void* actions,
-            const void* demand_next, const sn::StepPtrs& out, cudaStream_t st) {
+int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state, const void* actions,
+            const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
   if (is_net(spec)) {
-    sn::k_net_step<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out);
+    sn::k_net_step<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out);
     return cuda_ok("sn_step launch");
   }
   const auto d = lower<T>(spec);
-#define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, terminal, (T*)state, (const T*)actions, (const T*)demand_next, out, tma_ok(out.obs))
+  // beer-game lead times: the TMA-tiled persistent kernel for HBM-sized batches (and whenever the VecNormalize
+  // statistics are fused in), the plain one-thread-per-env kernel for small ones
+  const bool tiled_ok = is_standard(spec) && aligned16(state) && aligned16(demand) && aligned16(actions) &&
+                        (out.reward == nullptr || aligned16(out.reward)) && (out.env_reward == nullptr || aligned16(out.env_reward));
+  const int choice = step_kernel_choice();
+  const bool want_tiled = out.vn_scratch != nullptr || choice == 2 || (choice == 0 && n >= SN_TILED_MIN_ENVS);
+  if (out.vn_scratch != nullptr && !tiled_ok)
+    return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: fused VecNormalize statistics need the beer game's lead times and 16-byte aligned buffers");
+  if (tiled_ok && want_tiled) {
+    if (is_identity(spec)) return launch_step_tiled<T, true>(d, n, ld, period, state, actions, demand, out, st);
+    return launch_step_tiled<T, false>(d, n, ld, period, state, actions, demand, out, st);
+  }
+#define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out, tma_ok(out.obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
 #undef SN_CALL
   return cuda_ok("sn_step launch");
@@ -1202,25 +1415,52 @@ int32_t sn_observe(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   }
 }
 
-int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period, void* state,
-                const void* actions, const void* demand_next, float* obs, float* reward, double* reward64,
-                double* cost, double* ep_return, double* stats, void* stream) {
+int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const sn_step_io* io, void* stream) {
   int rc = validate(spec, dtype);
   if (rc != SN_OK) return rc;
   if ((rc = check_batch(n_envs, ld)) != SN_OK) return rc;
-  if (period < 0) return fail(SN_ERR_INVALID, "period=%d", period);
-  if (period >= spec->max_episode_steps)
-    return fail(SN_ERR_TERMINAL, "Cannot take action when the state is terminal.");     // envs.py:88-89
-  if (!state || !actions || !demand_next) return fail(SN_ERR_INVALID, "sn_step: state, actions and demand_next must be non-NULL");
-  if (spec->n_agents == 4 && !aligned16(actions)) return fail(SN_ERR_INVALID, "sn_step: actions must be 16-byte aligned");
-  const int terminal = (period + 1 >= spec->max_episode_steps) ? 1 : 0;
-  const sn::StepPtrs out{obs, reward, reward64, cost, ep_return, stats};
+  if (io == nullptr) return fail(SN_ERR_INVALID, "sn_step_ex: io is NULL");
+  if (io->ctl == nullptr) {
+    if (io->period < 0) return fail(SN_ERR_INVALID, "period=%d", io->period);
+    if (io->period >= spec->max_episode_steps)
+      return fail(SN_ERR_TERMINAL, "Cannot take action when the state is terminal.");     // envs.py:88-89
+  }
+  if (!io->state || !io->actions || !io->demand) return fail(SN_ERR_INVALID, "sn_step: state, actions and demand must be non-NULL");
+  if (spec->n_agents == 4 && !aligned16(io->actions)) return fail(SN_ERR_INVALID, "sn_step: actions must be 16-byte aligned");
+  if (io->env_reward != nullptr) {
+    if (is_tree(spec) || (spec->n_items != 2 && spec->n_items != 4))
+      return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: env_reward needs a multi-item chain batch with 2 or 4 items (n_items=%d)", spec->n_items);
+    if (n_envs % spec->n_items != 0) return fail(SN_ERR_INVALID, "sn_step_ex: n_envs=%lld is not a multiple of n_items=%d", (long long)n_envs, spec->n_items);
+  }
+  const bool vn = io->vn_scratch || io->vn_obs_rms || io->vn_ret_rms || io->vn_returns;
+  if (vn) {
+    if (!io->vn_scratch || !io->vn_obs_rms) return fail(SN_ERR_INVALID, "sn_step_ex: vn_scratch and vn_obs_rms must be given together");
+    if (io->vn_returns && !io->vn_ret_rms) return fail(SN_ERR_INVALID, "sn_step_ex: vn_returns needs vn_ret_rms");
+    if (!io->ctl || !io->obs) return fail(SN_ERR_INVALID, "sn_step_ex: fused VecNormalize statistics need ctl and obs");
+    if (io->vn_returns && !io->reward) return fail(SN_ERR_INVALID, "sn_step_ex: vn_returns needs reward");
+    if (spec->n_items > 1 || !is_standard(spec)) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: fused VecNormalize statistics need the single-item beer-game chain");
+  }
+  sn::StepPtrs out{};
+  out.obs = io->obs; out.reward = io->reward; out.reward64 = io->reward64; out.cost = io->cost;
+  out.ep_return = io->ep_return; out.stats = io->stats; out.env_reward = io->env_reward; out.ctl = io->ctl;
+  out.vn_scratch = io->vn_scratch; out.vn_obs_rms = io->vn_obs_rms; out.vn_ret_rms = io->vn_ret_rms;
+  out.vn_returns = io->vn_returns; out.vn_gamma = io->vn_gamma;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_step<int32_t>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
-    case SN_F32: return do_step<float>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
-    default: return do_step<double>(spec, n_envs, ld, terminal, state, actions, demand_next, out, st);
+    case SN_I32: return do_step<int32_t>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
+    case SN_F32: return do_step<float>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
+    default: return do_step<double>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
   }
+}
+
+int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period, void* state,
+                const void* actions, const void* demand_next, float* obs, float* reward, double* reward64,
+                double* cost, double* ep_return, double* stats, void* stream) {
+  sn_step_io io;
+  std::memset(&io, 0, sizeof(io));
+  io.state = state; io.actions = actions; io.demand = demand_next; io.period = period;
+  io.obs = obs; io.reward = reward; io.reward64 = reward64; io.cost = cost; io.ep_return = ep_return; io.stats = stats;
+  return sn_step_ex(spec, dtype, n_envs, ld, &io, stream);
 }
 
 int32_t sn_heuristic(const sn_policy* policy, int32_t n_cols, int64_t n_envs, const float* obs, float* actions,

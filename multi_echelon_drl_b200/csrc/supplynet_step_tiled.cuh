@@ -1,0 +1,347 @@
+// supplynet_step_tiled.cuh — the single-period step (envs.py:82-113 for all envs) as a persistent, TMA-fed
+// pipeline.  Included by supplynet_kernels.cu inside namespace sn (after StepPtrs / k_step).
+//
+// Why: the plain k_step issues 40 scalar loads per thread behind 164-176 registers and runs at 17 % occupancy:
+// not enough bytes in flight for the 345-457 B that one env-step moves (profiles/r1_ncu_k_step_summary.json).
+// Here one CTA per SM walks over tiles of kTile consecutive envs.  A tile is, in the structure-of-arrays state,
+// a [words][kTile] box of the [words][ld] matrix; a producer warp moves it with ONE tensor-map TMA copy
+// (cp.async.bulk.tensor.2d, SASS UTMALDG / UTMASTG) into one of kStages shared-memory stages, completion counted on
+// an mbarrier, next to the tile's action rows ([kTile][n_agents], contiguous: one cp.async.bulk, UBLKCP) and
+// demand row(s).  (A first version moved the box as `words` separate 512-byte bulk copies: the TMA unit then
+// spends its time on per-copy overhead, ~84 copies per tile = 3.2 us, 0.31-0.40 of the HBM peak; profiles/r2_notes.md.)  The consumer warps (one thread
+// per env) read their column from shared memory, run the same per-env code as every other kernel
+// (env_orders / Ops::step), write the new state back IN PLACE, the observation rows ([kTile][obs_dim] f32, one
+// contiguous span) and the rewards next to it, and hand the stage back; the producer stores it with bulk
+// copies and refills it kStages tiles later.  Loads of kStages-1 tiles are in flight while one is computed, with
+// no register cost, and the stores drain asynchronously.
+//
+// A partial last tile keeps the tensor path for the state box (columns beyond `ld` are clipped by the TMA unit:
+// zero-filled on load, dropped on store) and uses per-thread accesses for the row-major tensors.
+#pragma once
+
+#ifndef SN_TILED_STAGES
+#define SN_TILED_STAGES 4
+#endif
+
+// ---- mbarrier + bulk-copy PTX ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded: a protocol error traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 22)) __trap();
+}
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// [rows][kTile] box of the state matrix at column c0 (tensor map: dim0 = env, dim1 = state word)
+__device__ __forceinline__ void tensor_load_2d(void* sdst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(sdst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap* tm, int c0, int c1, const void* ssrc) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(ssrc)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- stage geometry ----------------------------------------------------------------------------------------
+template <typename T, typename Ops>
+struct TileCfg {
+  static constexpr int kTile = sizeof(T) == 8 ? 64 : 128;          // envs per tile: 512-byte row segments
+  static constexpr int kConsumerWarps = kTile / 32;
+  static constexpr int kThreads = kTile + 32;                      // + one producer warp
+  static constexpr int kWords = Ops::kWords;
+  static constexpr int kStateBytes = kWords * kTile * (int)sizeof(T);
+  static constexpr int kActBytes = kTile * kF * (int)sizeof(T);
+  static constexpr int kDemBytes = Ops::kMaxSrc * kTile * (int)sizeof(T);
+  static constexpr int kObsBytes = kTile * 28 * 4;
+  static constexpr int kRewBytes = kTile * 4;
+  static constexpr int kOffAct = kStateBytes;
+  static constexpr int kOffDem = kOffAct + kActBytes;
+  static constexpr int kOffObs = kOffDem + kDemBytes;
+  static constexpr int kOffRew = kOffObs + kObsBytes;
+  static constexpr int kOffERew = kOffRew + kRewBytes;
+  static constexpr int kStageBytes = kOffERew + kRewBytes;         // every part a multiple of 128 bytes
+  static constexpr int kBarBytes = 128;                            // full[kStages], done[kStages]
+  static constexpr int kRedDoubles = (kConsumerWarps + 1) * 14;   // block_reduce_add scratch
+  static constexpr int kVnDoubles = 2 * kTile;                      // column-moment partials of the fused VecNormalize
+  static constexpr int kRedBytes = ((kRedDoubles + kVnDoubles) * 8 + 16 + 127) & ~127;
+  static constexpr size_t smem_bytes(int stages) { return 128 + kBarBytes + kRedBytes + (size_t)stages * kStageBytes; }
+};
+
+// RunningMeanStd.update for one column / the returns: parallel-variance merge of (mean, var, count) with the
+// batch moments (sum, sum of squares over bn samples); SURVEY Appendix D, same formulas as vecnorm_kernels.cu.
+__device__ __forceinline__ void rms_merge_inplace(double* mean, double* var, double count, double sum, double sumsq, double bn) {
+  const double bmean = sum / bn;
+  const double bvar = fmax(sumsq / bn - bmean * bmean, 0.0);
+  const double delta = bmean - *mean;
+  const double tot = count + bn;
+  const double m2 = *var * count + bvar * bn + delta * delta * count * bn / tot;
+  *mean = *mean + delta * bn / tot;
+  *var = m2 / tot;
+}
+
+template <typename T, bool IDENT, typename Ops, int kStages>
+__global__ void __launch_bounds__(TileCfg<T, Ops>::kThreads, 1)
+k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUtensorMap tm_state, int64_t n, int64_t ld,
+             int period_arg, const T* __restrict__ actions, const T* __restrict__ demand, const StepPtrs out, int obs_tma) {
+  using C = TileCfg<T, Ops>;
+  constexpr int kTile = C::kTile;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);              // [kStages] producer -> consumers (tx bytes)
+  uint64_t* done = full + kStages;                                 // [kStages] consumers -> producer
+  double* red = reinterpret_cast<double*>(smem + C::kBarBytes);    // block reductions
+  double* vn_red = red + C::kRedDoubles;                           // [2][kTile]
+  int* last_flag = reinterpret_cast<int*>(vn_red + C::kVnDoubles);
+  uint8_t* stages = smem + C::kBarBytes + C::kRedBytes;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int period = launch_period(out.ctl, period_arg);
+  if (period >= sp.t_max) {
+    if (out.ctl != nullptr && blockIdx.x == 0 && tid == 0) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_STEP_AFTER_TERMINAL);
+    return;
+  }
+  const bool terminal = period + 1 >= sp.t_max;
+  const int64_t dstride = Ops::dstride(sp, ld);
+  const T* __restrict__ demand_next = out.ctl != nullptr ? demand + (int64_t)(period + 1) * dstride : demand;
+  const int od = 7 * sp.n_obs, na = sp.n_agents, n_src = Ops::n_src(sp);
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&done[s], C::kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  double acc[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) acc[i] = 0.0;
+  double vsx = 0.0, vsxx = 0.0, vsr = 0.0, vsrr = 0.0;             // fused VecNormalize partial sums
+
+  if (warp == C::kConsumerWarps) {
+    // ================= producer warp: every lane moves its share of the rows of a tile =====================
+    for (int64_t it = 0; it < my_tiles + kStages - 1; ++it) {
+      const int64_t j = it - (kStages - 1);                        // tile whose results leave now
+      if (j >= 0) {
+        const int s = (int)(j % kStages);
+        const int64_t env0 = (blockIdx.x + j * gridDim.x) * kTile;
+        const bool full_tile = env0 + kTile <= n;
+        uint8_t* st = stages + (size_t)s * C::kStageBytes;
+        mbar_wait(&done[s], (uint32_t)((j / kStages) & 1));
+        if (lane == 0) tensor_store_2d(&tm_state, (int)env0, 0, st);
+        if (full_tile) {
+          if (lane == 31 && obs_tma) bulk_store_s2g(out.obs + env0 * od, st + C::kOffObs, (uint32_t)(kTile * od * 4));
+          if (lane == 30 && out.reward != nullptr) bulk_store_s2g(out.reward + env0, st + C::kOffRew, (uint32_t)(kTile * 4));
+          if (lane == 29 && out.env_reward != nullptr)
+            bulk_store_s2g(out.env_reward + env0 / sp.n_items, st + C::kOffERew, (uint32_t)(kTile / sp.n_items * 4));
+        }
+        bulk_commit();
+      }
+      if (it < my_tiles) {
+        bulk_wait_read<1>();                                       // the stores of tile it-kStages have left this stage
+        __syncwarp();
+        const int s = (int)(it % kStages);
+        const int64_t env0 = (blockIdx.x + it * gridDim.x) * kTile;
+        const int cols = (int)((ld - env0) < kTile ? (ld - env0) : kTile);
+        const bool full_tile = env0 + kTile <= n;
+        uint8_t* st = stages + (size_t)s * C::kStageBytes;
+        const uint32_t row_bytes = (uint32_t)(cols * sizeof(T));
+        if (lane == 0) {                                           // the whole box counts, clipped columns included
+          mbar_arrive_expect_tx(&full[s], (uint32_t)C::kStateBytes + (uint32_t)n_src * row_bytes +
+                                              (full_tile ? (uint32_t)(kTile * na * sizeof(T)) : 0u));
+          tensor_load_2d(st, &tm_state, (int)env0, 0, &full[s]);
+        }
+        __syncwarp();
+        if (lane == 31 && full_tile) bulk_load_g2s(st + C::kOffAct, actions + env0 * na, (uint32_t)(kTile * na * sizeof(T)), &full[s]);
+        if (lane >= 24 && lane < 24 + n_src)
+          bulk_load_g2s(st + C::kOffDem + (size_t)(lane - 24) * kTile * sizeof(T), demand_next + (int64_t)(lane - 24) * ld + env0,
+                        row_bytes, &full[s]);
+      }
+    }
+    bulk_wait_read<0>();
+  } else {
+    // ================= consumer warps: thread = env of the tile ==========================================
+    // per-env accumulators that live in global memory (episode return, VecNormalize's discounted return) are
+    // requested one tile ahead: with one consumer warp per scheduler nothing else would hide a load issued here
+    double epr_pre = 0.0, vnr_pre = 0.0;
+    {
+      const int64_t e0 = (int64_t)blockIdx.x * kTile + tid;
+      if (my_tiles > 0 && e0 < n) {
+        if (out.ep_return) epr_pre = out.ep_return[e0];
+        if (out.vn_returns) vnr_pre = out.vn_returns[e0];
+      }
+    }
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % kStages);
+      const int64_t env0 = (blockIdx.x + it * gridDim.x) * kTile;
+      const int64_t env = env0 + tid;
+      const bool valid = env < n, full_tile = env0 + kTile <= n;
+      const double epr = epr_pre, vnr = vnr_pre;
+      {
+        const int64_t en = env + (int64_t)gridDim.x * kTile;
+        if (it + 1 < my_tiles && en < n) {
+          if (out.ep_return) epr_pre = out.ep_return[en];
+          if (out.vn_returns) vnr_pre = out.vn_returns[en];
+        }
+      }
+      uint8_t* st = stages + (size_t)s * C::kStageBytes;
+      T* s_state = reinterpret_cast<T*>(st);
+      const T* s_act = reinterpret_cast<const T*>(st + C::kOffAct);
+      const T* s_dem = reinterpret_cast<const T*>(st + C::kOffDem);
+      float* s_obs = reinterpret_cast<float*>(st + C::kOffObs);
+      float* s_rew = reinterpret_cast<float*>(st + C::kOffRew);
+      float* s_erew = reinterpret_cast<float*>(st + C::kOffERew);
+      mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+
+      typename Ops::E e;
+      StepOut so;
+      so.reward = 0.0;
+      bool over = false;
+#pragma unroll
+      for (int k = 0; k < kF; ++k) so.hold[k] = so.back[k] = 0.0;
+      if (valid) {
+        Ops::load(sp, s_state, kTile, tid, e);
+        T a[kF] = {T(0), T(0), T(0), T(0)};
+        if (full_tile) load_actions_smem<IDENT>(s_act, tid, sp, a);
+        else load_actions<IDENT>(actions, env, sp, a);
+        const typename Ops::D dn = Ops::load_demand_smem(s_dem, kTile, tid, sp);
+        T q[kF];
+        env_orders<IDENT>(e, sp, a, q);
+        if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal, so);
+        else Ops::template step<false>(e, sp, 0, q, dn, terminal, so);
+        over = qty_overflow(e, a, q);
+        Ops::store(s_state, kTile, tid, e);
+        const float rf = (float)so.reward;
+        if (out.reward != nullptr) { if (full_tile) s_rew[tid] = rf; else out.reward[env] = rf; }
+        if (out.reward64) out.reward64[env] = so.reward;
+        if (out.cost) {
+#pragma unroll
+          for (int k = 0; k < kF; ++k) {
+            out.cost[k * ld + env] = so.hold[k];
+            out.cost[(kF + k) * ld + env] = so.back[k];
+          }
+        }
+        double ret_ep = 0.0;
+        if (out.ep_return) { ret_ep = epr + so.reward; out.ep_return[env] = ret_ep; }
+        if (out.vn_returns != nullptr) {                           // VecNormalize: ret <- ret*gamma + r (the float reward)
+          const double r = vnr * out.vn_gamma + (double)rf;
+          out.vn_returns[env] = r;
+          vsr += r;
+          vsrr += r * r;
+        }
+        if (out.obs != nullptr) emit_obs<IDENT>(e, sp, terminal, s_obs + tid * od);
+        acc[0] += 1.0;
+        acc[1] += so.reward;
+#pragma unroll
+        for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
+        if (terminal && out.ep_return != nullptr) { acc[10] += 1.0; acc[11] += ret_ep; acc[12] += ret_ep * ret_ep; }
+        if (over) acc[13] += 1.0;
+      }
+      if (out.env_reward != nullptr) {                             // every lane takes part in the shuffles
+        const double tot = env_reward_sum(so.reward, sp.n_items);
+        if (valid && (tid % sp.n_items) == 0) {
+          if (full_tile) s_erew[tid / sp.n_items] = (float)tot;
+          else out.env_reward[env / sp.n_items] = (float)tot;
+        }
+      }
+      const bool obs_by_threads = out.obs != nullptr && !(full_tile && obs_tma);
+      if (obs_by_threads || out.vn_scratch != nullptr) {
+        named_bar_sync(1, kTile);                                  // the tile's observation rows are complete
+        const int rows = (int)((n - env0) < kTile ? (n - env0) : kTile);
+        if (obs_by_threads)                                        // partial tile / unaligned output: coalesced copy
+          for (int i = tid; i < rows * od; i += kTile) out.obs[env0 * od + i] = s_obs[i];
+        if (out.vn_scratch != nullptr && tid < (od <= 32 ? (kTile / od) * od : 0)) {
+          // column moments of this tile: thread = (row group g, column c); groups interleave the rows
+          const int c = tid % od, g = tid / od, ng = kTile / od;
+          for (int r = g; r < rows; r += ng) {
+            const double x = (double)s_obs[r * od + c];
+            vsx += x;
+            vsxx += x * x;
+          }
+        }
+      }
+      fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the bulk stores
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[s]);
+    }
+  }
+
+  // ---- epilogue: statistics, VecNormalize moments, device period counter ---------------------------------
+  if (out.stats != nullptr) block_reduce_add<14, C::kConsumerWarps + 1>(acc, out.stats, red);
+  if (out.vn_scratch != nullptr) {
+    // per-thread partials -> one atomic per block and column into scratch; the last block merges them into the
+    // running statistics (in place: nothing reads them before the next kernel) and clears scratch
+    __syncthreads();
+    const int ng = od <= 32 ? kTile / od : 0;
+    if (tid < ng * od) { vn_red[tid] = vsx; vn_red[kTile + tid] = vsxx; }
+    double sr = vsr, srr = vsrr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); srr += __shfl_xor_sync(0xffffffffu, srr, o); }
+    if (lane == 0) { red[2 * warp] = sr; red[2 * warp + 1] = srr; }
+    __syncthreads();
+    if (tid < od) {
+      double a = 0.0, b = 0.0;
+      for (int g = 0; g < ng; ++g) { a += vn_red[g * od + tid]; b += vn_red[kTile + g * od + tid]; }
+      atomicAdd(&out.vn_scratch[tid], a);
+      atomicAdd(&out.vn_scratch[od + tid], b);
+    } else if (tid == 32 + (od & ~31) && out.vn_returns != nullptr) {   // a thread outside the column range
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < C::kConsumerWarps; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+      atomicAdd(&out.vn_scratch[2 * od], a);
+      atomicAdd(&out.vn_scratch[2 * od + 1], b);
+    }
+  }
+  if (out.ctl != nullptr) {
+    __syncthreads();
+    if (tid == 0) *last_flag = last_block_ticket(out.ctl) ? 1 : 0;
+    __syncthreads();
+    if (*last_flag) {
+      if (out.vn_scratch != nullptr) {
+        __threadfence();
+        volatile double* sc = out.vn_scratch;
+        const double bn = (double)n;
+        if (tid < od) {
+          const double count = out.vn_obs_rms[2 * od];
+          rms_merge_inplace(&out.vn_obs_rms[tid], &out.vn_obs_rms[od + tid], count, sc[tid], sc[od + tid], bn);
+        }
+        if (tid == 64 && out.vn_returns != nullptr) {
+          rms_merge_inplace(&out.vn_ret_rms[0], &out.vn_ret_rms[1], out.vn_ret_rms[2], sc[2 * od], sc[2 * od + 1], bn);
+          out.vn_ret_rms[2] += bn;
+        }
+        __syncthreads();                                           // every column has read the old count
+        if (tid == 0) out.vn_obs_rms[2 * od] += bn;
+        if (tid < 2 * od + 2) out.vn_scratch[tid] = 0.0;
+      }
+      if (tid == 0) {
+        out.ctl[SN_CTL_TICKET] = 0;
+        out.ctl[SN_CTL_PERIOD] = period + 1;
+      }
+    }
+  }
+}

@@ -41,6 +41,12 @@ struct TEnv {
   }
   __device__ __forceinline__ T latest(int k) const { return latI[k] + dem[k]; }
   static __device__ __forceinline__ bool pre_agent(int k, const DevSpec<T>& sp) { return sp.pre[k] != 0; }
+  __device__ __forceinline__ uint32_t extra_qty_mask() const {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) m |= (uint32_t)unf_ind[k] | (uint32_t)dem[k];
+    return m;
+  }
 };
 
 // backlog of all customer arcs of node k

@@ -82,32 +82,35 @@ __device__ __forceinline__ void merge(double mean, double var, double count, dou
   ncount = tot;
 }
 
-// rms layout: obs_rms = mean[od], var[od], count ; ret_rms = mean, var, count
-__global__ void k_finalize(int64_t n, int od, int has_reward, const double* __restrict__ scratch,
-                           const double* __restrict__ obs_in, double* __restrict__ obs_out,
-                           const double* __restrict__ ret_in, double* __restrict__ ret_out) {
+// rms layout: obs_rms = mean[od], var[od], count ; ret_rms = mean, var, count.  In and out buffers may be the
+// same (every input is read before the barrier, every output written after it).
+__global__ void k_finalize(int64_t n, int od, int has_reward, const double* scratch,
+                           const double* obs_in, double* obs_out, const double* ret_in, double* ret_out) {
   const int c = threadIdx.x;
   const double bn = (double)n;
+  double m = 0.0, v = 0.0, k = 0.0;
   if (c < od) {
     const double bmean = scratch[c] / bn;
     const double bvar = fmax(scratch[od + c] / bn - bmean * bmean, 0.0);
-    double m, v, k;
     merge(obs_in[c], obs_in[od + c], obs_in[2 * od], bmean, bvar, bn, m, v, k);
+  }
+  double rm = 0.0, rv = 0.0, rk = 0.0;
+  if (c == 63) {                               // obs_dim <= 56: thread 63 never owns a column
+    if (has_reward) {
+      const double bmean = scratch[2 * od] / bn;
+      const double bvar = fmax(scratch[2 * od + 1] / bn - bmean * bmean, 0.0);
+      merge(ret_in[0], ret_in[1], ret_in[2], bmean, bvar, bn, rm, rv, rk);
+    } else {
+      rm = ret_in[0]; rv = ret_in[1]; rk = ret_in[2];
+    }
+  }
+  __syncthreads();
+  if (c < od) {
     obs_out[c] = m;
     obs_out[od + c] = v;
     if (c == 0) obs_out[2 * od] = k;
   }
-  if (c == 32) {
-    if (has_reward) {
-      const double bmean = scratch[2 * od] / bn;
-      const double bvar = fmax(scratch[2 * od + 1] / bn - bmean * bmean, 0.0);
-      double m, v, k;
-      merge(ret_in[0], ret_in[1], ret_in[2], bmean, bvar, bn, m, v, k);
-      ret_out[0] = m; ret_out[1] = v; ret_out[2] = k;
-    } else {
-      ret_out[0] = ret_in[0]; ret_out[1] = ret_in[1]; ret_out[2] = ret_in[2];
-    }
-  }
+  if (c == 63) { ret_out[0] = rm; ret_out[1] = rv; ret_out[2] = rk; }
 }
 
 __global__ void __launch_bounds__(256)

@@ -34,7 +34,7 @@ def combine_item_specs(specs: Sequence[ScenarioSpec]) -> ScenarioSpec:
 
 
 class MultiItemSupplyNetwork:
-    def __init__(self, specs: Sequence[ScenarioSpec], n_envs: int, device="cuda", dtype="int32"):
+    def __init__(self, specs: Sequence[ScenarioSpec], n_envs: int, device="cuda", dtype="int32", use_graph: bool = False):
         self.spec = combine_item_specs(specs)
         self.n_items, self.n_envs = len(specs), int(n_envs)
         self.sim = BatchedSupplyNetwork(self.spec, self.n_envs * self.n_items, device, dtype)
@@ -43,8 +43,13 @@ class MultiItemSupplyNetwork:
         self.item_obs_dim, self.item_agents = s.obs_dim, s.n_agents
         self.obs_dim, self.n_agents = self.n_items * s.obs_dim, self.n_items * s.n_agents
         self.obs = s.obs.view(self.n_envs, self.obs_dim)                       # same memory, concatenated view
-        self._r64 = torch.zeros((self.n_envs * self.n_items,), dtype=torch.float64, device=self.device)
         self.reward = torch.zeros((self.n_envs,), dtype=torch.float32, device=self.device)
+        self._fused_reward = self.n_items in (2, 4)         # in-kernel reduction over the adjacent item chains
+        self._r64 = None if self._fused_reward else torch.zeros((self.n_envs * self.n_items,), dtype=torch.float64,
+                                                                device=self.device)
+        self.use_graph = bool(use_graph) and self._fused_reward
+        self._graph = None
+        self._act = torch.zeros((self.n_envs * self.n_items, self.item_agents), dtype=s.tdtype, device=self.device)
 
     @property
     def period(self):
@@ -64,16 +69,45 @@ class MultiItemSupplyNetwork:
         self.sim.reset()
         return self.obs
 
+    def _capture(self):
+        sim = self.sim
+        sim._graph_period_valid = True
+        sim.ctl[0:1].fill_(sim.period)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            sim.launch_step_device_period(self._act, sim.obs, sim.reward, env_reward=self.reward)
+        # capture does not execute: state and counter are untouched
+        self._graph = g
+
     def step(self, actions):
         """actions [n, I*n_agents] (item-major columns) -> (obs [n, I*obs_dim], reward [n], done)."""
         actions = torch.as_tensor(actions)
         if tuple(actions.shape) != (self.n_envs, self.n_agents):
             raise ValueError(f"actions must have shape {(self.n_envs, self.n_agents)}, got {tuple(actions.shape)}")
         a = actions.reshape(self.n_envs * self.n_items, self.item_agents)     # a view when contiguous
-        _, _, done = self.sim.step(a, reward64_out=self._r64)
-        # summed over the items of an env in double, rounded once like the single-item reward
-        self.reward.copy_(self._r64.view(self.n_envs, self.n_items).sum(1))
+        sim = self.sim
+        if self.use_graph and not sim.terminal and sim.period + 1 < sim.T:
+            if a.data_ptr() != self._act.data_ptr():
+                self._act.copy_(sim._check_actions(a))
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+            sim.advance_host_period()
+            return self.obs, self.reward, sim.terminal
+        if self._fused_reward:
+            _, _, done = sim.step(a, env_reward_out=self.reward)
+        else:
+            _, _, done = sim.step(a, reward64_out=self._r64)
+            # summed over the items of an env in double, rounded once like the single-item reward
+            self.reward.copy_(self._r64.view(self.n_envs, self.n_items).sum(1))
         return self.obs, self.reward, done
+
+    @property
+    def action_buffer(self):
+        """[n, I*n_agents] view of the static action buffer of the graph-replayed step: write actions here to
+        skip the copy."""
+        return self._act.view(self.n_envs, self.n_agents)
 
     @property
     def ep_return(self):

@@ -82,6 +82,8 @@ class BatchedSupplyNetwork:
         self.reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self.ep_return = torch.zeros((n,), dtype=torch.float64, device=dev)
         self.stats = torch.zeros((_lib.SN_STATS_WORDS,), dtype=torch.float64, device=dev)
+        # device control words (SN_CTL_*): period counter of the graph-replayed step, ticket, sticky flags
+        self.ctl = torch.zeros((_lib.SN_CTL_WORDS,), dtype=torch.int32, device=dev)
         self.period = 0
         self.terminal = True          # no episode loaded yet
         self.track_stats = False
@@ -133,6 +135,8 @@ class BatchedSupplyNetwork:
         self.period = 0
         self.terminal = False
         self.ep_return.zero_()
+        if self._graph_period_valid:
+            self.ctl[_lib.SN_CTL_PERIOD:_lib.SN_CTL_PERIOD + 1].zero_()
         return obs
 
     def _check_actions(self, actions: torch.Tensor, lead=()) -> torch.Tensor:
@@ -148,21 +152,66 @@ class BatchedSupplyNetwork:
                 raise TypeError("integer simulator (dtype='int32') needs integral order quantities")
         return actions.to(device=self.device, dtype=self.tdtype).contiguous()
 
-    def step(self, actions, obs_out=None, reward_out=None, reward64_out=None, cost_out=None):
+    def step(self, actions, obs_out=None, reward_out=None, reward64_out=None, cost_out=None, env_reward_out=None):
         """envs.py:82-113 for all envs.  Returns (obs, reward, done) with obs/reward on the device;
-        `done` is a python bool because all envs run in lockstep."""
+        `done` is a python bool because all envs run in lockstep.  `env_reward_out` (multi-item batches):
+        float32 [n_envs / n_items], the per-env sum of the items' rewards, reduced inside the kernel."""
         if self.terminal:
             raise ValueError("Cannot take action when the state is terminal.")       # envs.py:88-89
         a = self._check_actions(actions)
         obs = self.obs if obs_out is None else obs_out
         rew = self.reward if reward_out is None else reward_out
-        _lib.check(self.lib.sn_step(
-            C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, self.period, _ptr(self.state), _ptr(a),
-            _ptr(self.demand[self.period + 1]), _ptr(obs), _ptr(rew), _ptr(reward64_out), _ptr(cost_out),
-            _ptr(self.ep_return), _ptr(self.stats) if self.track_stats else None, self._stream()))
+        io = _lib.SnStepIo()
+        io.state, io.actions, io.demand = self.state.data_ptr(), a.data_ptr(), self.demand[self.period + 1].data_ptr()
+        io.period = self.period
+        io.obs, io.reward = obs.data_ptr(), rew.data_ptr()
+        io.env_reward = None if env_reward_out is None else env_reward_out.data_ptr()
+        io.reward64 = None if reward64_out is None else reward64_out.data_ptr()
+        io.cost = None if cost_out is None else cost_out.data_ptr()
+        io.ep_return = self.ep_return.data_ptr()
+        io.stats = self.stats.data_ptr() if self.track_stats else None
+        _lib.check(self.lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
+                                       self._stream()))
         self.period += 1
         self.terminal = self.period >= self.T
+        if self._graph_period_valid:                # keep the device counter of the graph-replayed step in sync
+            self.ctl[_lib.SN_CTL_PERIOD:_lib.SN_CTL_PERIOD + 1].fill_(self.period)
         return obs, rew, self.terminal
+
+    # ------------------------------------------------------------------ graph-replayed step (device period counter)
+    _graph_period_valid = False
+
+    def launch_step_device_period(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor,
+                                  env_reward: Optional[torch.Tensor] = None, vecnorm: Optional[dict] = None):
+        """One period step whose period is read from (and advanced in) device memory (`self.ctl`, sn_step_ex):
+        the launch has no host-side state, so it can be captured ONCE in a CUDA graph and replayed for every
+        period of every episode.  All tensors must keep their addresses between replays.  `vecnorm` = dict(scratch,
+        obs_rms, ret_rms, returns, gamma) fuses the VecNormalize statistics update into the launch.
+        The caller mirrors the period on the host with `advance_host_period()` after each replay and must not
+        replay at the terminal period (the launch would raise SN_FLAG_STEP_AFTER_TERMINAL and do nothing)."""
+        io = _lib.SnStepIo()
+        io.state, io.actions, io.demand = self.state.data_ptr(), actions.data_ptr(), self.demand.data_ptr()
+        io.ctl = self.ctl.data_ptr()
+        io.obs, io.reward = obs.data_ptr(), reward.data_ptr()
+        io.env_reward = None if env_reward is None else env_reward.data_ptr()
+        io.ep_return = self.ep_return.data_ptr()
+        io.stats = self.stats.data_ptr() if self.track_stats else None
+        if vecnorm is not None:
+            io.vn_scratch, io.vn_obs_rms = vecnorm["scratch"].data_ptr(), vecnorm["obs_rms"].data_ptr()
+            if vecnorm.get("returns") is not None:
+                io.vn_ret_rms, io.vn_returns = vecnorm["ret_rms"].data_ptr(), vecnorm["returns"].data_ptr()
+            io.vn_gamma = float(vecnorm["gamma"])
+        _lib.check(self.lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
+                                       self._stream()))
+
+    def advance_host_period(self):
+        """Host mirror of what a replayed `launch_step_device_period` did on the device."""
+        self.period += 1
+        self.terminal = self.period >= self.T
+
+    def device_flags(self) -> int:
+        """Sticky SN_FLAG_* bits raised by device-period launches (synchronises)."""
+        return int(self.ctl[_lib.SN_CTL_FLAGS].item())
 
     def observe(self, obs_out=None) -> torch.Tensor:
         obs = self.obs if obs_out is None else obs_out

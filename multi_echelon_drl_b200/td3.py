@@ -237,6 +237,11 @@ class HgeTD3:
         if c.action_noise_std > 0:
             noise = torch.randn(scaled.shape, device=self.device, generator=self.gen) * c.action_noise_std
             scaled = torch.clamp(scaled + noise, -1.0, 1.0)
+        # the env's static action buffer (graph-replayed step) receives the result directly: no copy launch
+        buf = getattr(self.env, "action_buffer", None) if getattr(self.env, "use_graph", False) else None
+        if buf is not None and buf.dtype == torch.float32 and buf.shape == scaled.shape:
+            torch.add((scaled + 1.0) * (0.5 * (self.high - self.low)), self.low, out=buf)
+            return buf, scaled
         return self.unscale_action(scaled), scaled
 
     def _normalize(self, obs, rew, stats=None):
@@ -389,8 +394,8 @@ class HgeTD3:
         sync_envs_normalization) and frozen; returns are the ORIGINAL (un-normalised) episode returns.
         Returns (mean, std, number of episodes)."""
         if self.vec_normalize is not None and isinstance(eval_env, VecNormalize):
-            eval_env._obs_rms[0].copy_(self.vec_normalize._obs_rms[0])
-            eval_env._ret_rms[0].copy_(self.vec_normalize._ret_rms[0])
+            eval_env._obs_rms.copy_(self.vec_normalize._obs_rms)
+            eval_env._ret_rms.copy_(self.vec_normalize._ret_rms)
             eval_env.training = False
         rets = []
         obs = eval_env.reset()

@@ -68,10 +68,14 @@ class SupplyNetVecEnv(_VecEnvBase):
     close, seed, get_attr, set_attr, env_method, env_is_wrapped)."""
 
     metadata = {"render.modes": []}
+    kRing = 3
 
     def __init__(self, spec: ScenarioSpec, n_envs: int, device="cuda", dtype="float32", seed: int = 0,
                  episode_source: str = "device", output: str = "torch", box_action_space: bool = True,
-                 multi_discrete: bool = False):
+                 multi_discrete: bool = False, use_graph: bool = False):
+        """use_graph (output="torch"): non-terminal steps replay ONE captured CUDA graph (the period lives in device
+        memory, sn_step_ex) instead of issuing the launch from Python; a wrapping device VecNormalize joins the same
+        graph with its statistics fused into the step kernel.  Actions written into `action_buffer` skip a copy."""
         if episode_source not in ("device", "numpy_bulk", "numpy_seeded"):
             raise ValueError("episode_source must be 'device', 'numpy_bulk' or 'numpy_seeded'")
         if output not in ("torch", "numpy"):
@@ -85,6 +89,10 @@ class SupplyNetVecEnv(_VecEnvBase):
         self.sim = BatchedSupplyNetwork(spec, n_envs, device, dtype)
         self.device = self.sim.device
         self.output = output
+        self.use_graph = bool(use_graph) and output == "torch"
+        self._graph, self._graph_key, self._vn = None, None, None
+        self._act_buf = torch.zeros((int(n_envs), spec.n_agents), dtype=self.sim.tdtype, device=self.sim.device)
+        self.last_step_graphed = False
         self.episode_source = episode_source
         # spaces exactly as the factories build them (envs.py:269-277, 397-405, 587-588)
         if multi_discrete:
@@ -104,14 +112,18 @@ class SupplyNetVecEnv(_VecEnvBase):
         self._term_obs = torch.zeros((n, od), dtype=torch.float32, device=self.device)
         self._all_false = torch.zeros((n,), dtype=torch.bool, device=self.device)
         self._all_true = torch.ones((n,), dtype=torch.bool, device=self.device)
-        self._np_false, self._np_true = np.zeros((n,), dtype=bool), np.ones((n,), dtype=bool)
         self._no_infos = LazyInfos(n)
         self._last_returns = torch.zeros((n,), dtype=torch.float64, device=self.device)
         if output == "numpy":
             self._h_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype).pin_memory()
             self._d_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype, device=self.device)
-            self._h_obs = torch.zeros((n, od), dtype=torch.float32).pin_memory()
-            self._h_rew = torch.zeros((n,), dtype=torch.float32).pin_memory()
+            # Results are handed out as views of pinned staging buffers, rotated over kRing sets: an array returned
+            # by step()/reset() stays untouched for the next kRing-1 calls (SB3 keeps `_last_obs` across one
+            # env.step(); DummyVecEnv allocates fresh arrays instead, which at this batch size would cost a
+            # host memcpy of megabytes per step).  Copy what must live longer.
+            self._ring = [(torch.zeros((n, od), dtype=torch.float32).pin_memory(),
+                           torch.zeros((n,), dtype=torch.float32).pin_memory()) for _ in range(self.kRing)]
+            self._ring_pos = 0
             self._h_term = torch.zeros((n, od), dtype=torch.float32).pin_memory()
         self.seed(seed)
 
@@ -155,15 +167,21 @@ class SupplyNetVecEnv(_VecEnvBase):
 
         # one launch per table, written in place in the structure-of-arrays layout (sn_fill_* in random_fill.cu)
         if sp.is_tree and len(set(sp.source_demand_params)) > 1:
-            # demand sources with their own parameters: one strided [T+3][ld] slice of the table per source
+            # demand sources with their own parameters: each source's rows are drawn into a contiguous scratch
+            # table from the same seeded Philox counter stream, then copied into its strided slice of the table
+            if not hasattr(self, "_src_scratch"):
+                self._src_scratch = torch.empty((sim.demand.shape[0], sim.ld), dtype=sim.tdtype, device=self.device)
+            t = self._src_scratch
             for s, (pa, pb) in enumerate(sp.source_demand_params):
                 if sp.demand_pattern == "uniform":
-                    sim.demand[:, s].random_(int(pa), int(pb) + 1)
+                    fill_uniform(t, pa, int(pb) + 1)
                 elif sp.demand_pattern == "normal":
-                    t = torch.randn(sim.demand[:, s].shape, device=self.device) * float(pb) + float(pa)
-                    sim.demand[:, s].copy_(t.clamp_(min=0).round_())
+                    _lib.check(lib.sn_fill_normal_demand(dt, C.c_void_p(t.data_ptr()), t.numel(), float(pa), float(pb),
+                                                         seed, self._ctr, st))
+                    self._ctr += (t.numel() + 3) // 4
                 else:
                     raise NotImplementedError("tree networks draw uniform or normal demand")
+                sim.demand[:, s].copy_(t)
         elif sp.demand_pattern == "uniform":
             fill_uniform(sim.demand, a, int(b) + 1)
         elif sp.demand_pattern == "normal":
@@ -192,13 +210,54 @@ class SupplyNetVecEnv(_VecEnvBase):
     def step_async(self, actions):
         self._actions = actions
 
+    # ------------------------------------------------------------------ graph-replayed step
+    @property
+    def action_buffer(self):
+        """Static [n_envs, n_agents] action tensor of the graph-replayed step (quantity dtype)."""
+        return self._act_buf
+
+    def attach_vecnorm(self, vn):
+        """A device VecNormalize wrapping this env joins the step graph (vec_normalize.py)."""
+        self._vn, self._graph = vn, None
+
+    def _capture(self, key):
+        sim, vn = self.sim, self._vn
+        sim._graph_period_valid = True
+        sim.ctl[0:1].fill_(sim.period)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            sim.launch_step_device_period(self._act_buf, self._obs, sim.reward,
+                                          vecnorm=vn.fused_args() if (vn is not None and key[0]) else None)
+            if vn is not None and key[1]:
+                vn.graph_tail()
+        self._graph, self._graph_key = g, key
+
+    def _graph_step(self, actions):
+        """Non-terminal period through the captured graph.  key = (fuse the VecNormalize update, apply in graph)."""
+        sim, vn = self.sim, self._vn
+        key = vn.graph_key() if vn is not None else (False, False)
+        if not (isinstance(actions, torch.Tensor) and actions.data_ptr() == self._act_buf.data_ptr()):
+            self._act_buf.copy_(sim._check_actions(actions))
+        if self._graph is None or self._graph_key != key:
+            self._capture(key)
+        self._graph.replay()
+        sim.advance_host_period()
+        self.last_step_graphed = True
+        return self._obs, sim.reward, self._all_false, self._no_infos
+
     def step_wait(self):
         sim = self.sim
         actions = self._actions
+        self.last_step_graphed = False
+        if self.use_graph and not sim.terminal and sim.period + 1 < sim.T:
+            return self._graph_step(actions)
         if self.output == "numpy":
             a = np.asarray(actions)
             if a.ndim == 1:
                 a = a[:, None]
+            if sim.dtype_code == _lib.SN_I32 and a.dtype.kind == "f" and not np.array_equal(a, np.round(a)):
+                raise TypeError("integer simulator (dtype='int32') needs integral order quantities")
             self._h_act.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(self._h_act.dtype))
             self._d_act.copy_(self._h_act, non_blocking=True)
             actions = self._d_act
@@ -216,14 +275,17 @@ class SupplyNetVecEnv(_VecEnvBase):
         else:
             infos = self._no_infos
         if self.output == "numpy":
-            self._h_obs.copy_(self._obs, non_blocking=True)
-            self._h_rew.copy_(rew, non_blocking=True)
+            h_obs, h_rew = self._next_ring()
+            h_obs.copy_(self._obs, non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
             if done:
                 self._h_term.copy_(self._term_obs, non_blocking=True)
-                infos.terminal_observation = self._h_term.numpy()
                 infos.episode_return = self._last_returns.cpu().numpy()
             torch.cuda.current_stream(self.device).synchronize()
-            return (self._h_obs.numpy(), self._h_rew.numpy(), self._np_true if done else self._np_false, infos)
+            if done:
+                infos.terminal_observation = self._h_term.numpy().copy()
+            return (h_obs.numpy(), h_rew.numpy(),
+                    np.ones((self.num_envs,), dtype=bool) if done else np.zeros((self.num_envs,), dtype=bool), infos)
         return self._obs, rew, (self._all_true if done else self._all_false), infos
 
     def step(self, actions):
@@ -232,10 +294,15 @@ class SupplyNetVecEnv(_VecEnvBase):
 
     def _out_obs(self):
         if self.output == "numpy":
-            self._h_obs.copy_(self._obs, non_blocking=True)
+            h_obs, _ = self._next_ring()
+            h_obs.copy_(self._obs, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            return self._h_obs.numpy()
+            return h_obs.numpy()
         return self._obs
+
+    def _next_ring(self):
+        self._ring_pos = (self._ring_pos + 1) % self.kRing
+        return self._ring[self._ring_pos]
 
     def run_policy_episodes(self, policy, n_episodes: int = 1):
         """Config-3 mode: play `n_episodes` whole episodes with a base-stock policy evaluated inside the

@@ -41,16 +41,20 @@ class VecNormalize:
         n, od, dev = self.num_envs, venv.spec.obs_dim, self.device
         self.od = od
         f64 = dict(dtype=torch.float64, device=dev)
-        # RunningMeanStd(epsilon=1e-4): mean 0, var 1, count 1e-4; two buffers each (in / out, swapped)
-        self._obs_rms = [self._fresh(od, f64), self._fresh(od, f64)]
-        self._ret_rms = [self._fresh(1, f64), self._fresh(1, f64)]
+        # RunningMeanStd(epsilon=1e-4): mean 0, var 1, count 1e-4.  ONE buffer each with a fixed address: the eager
+        # kernels update it in place, and so does the step kernel when the update is fused into a replayed graph
+        self._obs_rms = self._fresh(od, f64)
+        self._ret_rms = self._fresh(1, f64)
         self.returns = torch.zeros(n, **f64)
         self._scratch = torch.zeros(2 * od + 2, **f64)
+        self._fused_scratch = torch.zeros(2 * od + 2, **f64)     # owned by the fused path: stays zero between launches
         self.old_obs = torch.zeros((n, od), dtype=torch.float32, device=dev)
         self.old_reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._nobs = torch.zeros((n, od), dtype=torch.float32, device=dev)
         self._nrew = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._nterm = torch.zeros((n, od), dtype=torch.float32, device=dev)
+        if getattr(venv, "use_graph", False) and hasattr(venv, "attach_vecnorm"):
+            venv.attach_vecnorm(self)
 
     @staticmethod
     def _fresh(d, kw):
@@ -62,12 +66,12 @@ class VecNormalize:
     # ------------------------------------------------------------------ statistics access
     @property
     def obs_rms(self):
-        r = self._obs_rms[0]
+        r = self._obs_rms
         return {"mean": r[: self.od], "var": r[self.od: 2 * self.od], "count": r[2 * self.od]}
 
     @property
     def ret_rms(self):
-        r = self._ret_rms[0]
+        r = self._ret_rms
         return {"mean": r[0], "var": r[1], "count": r[2]}
 
     def _stream(self):
@@ -75,27 +79,44 @@ class VecNormalize:
 
     def _update(self, obs, reward):
         rc = self.lib.sn_vecnorm_update(self.num_envs, self.od, _p(obs), _p(reward), self.gamma, _p(self.returns),
-                                        _p(self._obs_rms[0]), _p(self._obs_rms[1]), _p(self._ret_rms[0]),
-                                        _p(self._ret_rms[1]), _p(self._scratch), self._stream())
+                                        _p(self._obs_rms), _p(self._obs_rms), _p(self._ret_rms), _p(self._ret_rms),
+                                        _p(self._scratch), self._stream())
         _lib.check(rc)
-        self._obs_rms.reverse()
-        self._ret_rms.reverse()
 
     def frozen_stats(self):
-        """Copy of the current statistics in buffers whose addresses never change (the live ones are
-        ping-pong pairs): what a captured CUDA graph normalises with; refresh by calling this again."""
+        """Copy of the current statistics in buffers of their own: what a captured CUDA graph of the TD3 update
+        normalises replay samples with while the live statistics move on; refresh by calling this again."""
         if not hasattr(self, "_frozen"):
-            self._frozen = (torch.empty_like(self._obs_rms[0]), torch.empty_like(self._ret_rms[0]))
-        self._frozen[0].copy_(self._obs_rms[0])
-        self._frozen[1].copy_(self._ret_rms[0])
+            self._frozen = (torch.empty_like(self._obs_rms), torch.empty_like(self._ret_rms))
+        self._frozen[0].copy_(self._obs_rms)
+        self._frozen[1].copy_(self._ret_rms)
         return self._frozen
 
     def _apply(self, obs, obs_out, reward, reward_out, reset_returns, n=None, stats=None):
-        obs_rms, ret_rms = stats if stats is not None else (self._obs_rms[0], self._ret_rms[0])
+        obs_rms, ret_rms = stats if stats is not None else (self._obs_rms, self._ret_rms)
         rc = self.lib.sn_vecnorm_apply(self.num_envs if n is None else n, self.od, _p(obs), _p(obs_out), _p(reward), _p(reward_out),
                                        _p(obs_rms), _p(ret_rms), self.clip_obs, self.clip_reward,
                                        self.epsilon, int(reset_returns), _p(self.returns), self._stream())
         _lib.check(rc)
+
+    # ------------------------------------------------------------------ joining the wrapped env's step graph
+    def graph_key(self):
+        """(fuse the statistics update into the step kernel, normalise inside the graph).  Fusion needs what the
+        kernel supports: observations normalised (their moments come from the step's own tile), single-item
+        beer-game chain; anything else keeps the eager kernels after the replay."""
+        spec = self.venv.spec
+        can_fuse = self.norm_obs and not spec.is_tree and spec.n_items <= 1 and self.venv.sim.state_words == _lib.SN_STATE_WORDS
+        return (bool(self.training and can_fuse), bool(can_fuse or not self.training))
+
+    def fused_args(self):
+        return dict(scratch=self._fused_scratch, obs_rms=self._obs_rms, ret_rms=self._ret_rms,
+                    returns=self.returns if self.norm_reward else None, gamma=self.gamma)
+
+    def graph_tail(self):
+        """Captured right after the step launch: normalise the step's outputs with the (just updated) statistics."""
+        venv = self.venv
+        self._apply(venv._obs if self.norm_obs else None, self._nobs, venv.sim.reward if self.norm_reward else None,
+                    self._nrew, False)
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
@@ -116,12 +137,16 @@ class VecNormalize:
         obs, rew, dones, infos = self.venv.step_wait()
         # the wrapped env hands out the same two device buffers at every step: keep references, not copies
         self.old_obs, self.old_reward = obs, rew
+        if getattr(self.venv, "last_step_graphed", False) and self.venv._graph_key[1]:
+            # statistics update (if training) and normalisation ran inside the replayed graph
+            return (self._nobs if self.norm_obs else obs), (self._nrew if self.norm_reward else rew), dones, infos
         done = infos.terminal_observation is not None
         if self.training:
-            # obs statistics and (if rewards are normalised) the discounted returns in one pass
-            self._update(obs if self.norm_obs else self.old_obs, rew if self.norm_reward else None)
-            if not self.norm_obs:                      # statistics of obs were updated needlessly: undo the swap
-                self._obs_rms.reverse()
+            if self.norm_obs:
+                # obs statistics and (if rewards are normalised) the discounted returns in one pass
+                self._update(obs, rew if self.norm_reward else None)
+            elif self.norm_reward:
+                self._update_returns_only(rew)
         out_obs, out_rew = obs, rew
         self._apply(obs if self.norm_obs else None, self._nobs, rew if self.norm_reward else None, self._nrew,
                     done and self.norm_reward)
@@ -132,9 +157,17 @@ class VecNormalize:
         elif done:
             self.returns.zero_()
         if done and self.norm_obs:
+            # SB3 normalises infos[i]["terminal_observation"] with the statistics of this step
             self._apply(infos.terminal_observation, self._nterm, None, None, False)
             infos = LazyInfos(infos.n, self._nterm, infos.episode_return, infos.episode_length, infos.elapsed)
         return out_obs, out_rew, dones, infos
+
+    def _update_returns_only(self, rew):
+        """norm_obs=False, norm_reward=True: only the return statistics move (the obs statistics pass through a
+        throw-away copy)."""
+        keep = self._obs_rms.clone()
+        self._update(self.old_obs, rew)
+        self._obs_rms.copy_(keep)
 
     def step(self, actions):
         self.step_async(actions)
@@ -178,13 +211,13 @@ class VecNormalize:
 
     # ------------------------------------------------------------------ persistence
     def state_dict(self):
-        return {"obs_rms": self._obs_rms[0].cpu(), "ret_rms": self._ret_rms[0].cpu(), "clip_obs": self.clip_obs,
+        return {"obs_rms": self._obs_rms.cpu(), "ret_rms": self._ret_rms.cpu(), "clip_obs": self.clip_obs,
                 "clip_reward": self.clip_reward, "gamma": self.gamma, "epsilon": self.epsilon,
                 "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
 
     def load_state_dict(self, sd):
-        self._obs_rms[0].copy_(sd["obs_rms"])
-        self._ret_rms[0].copy_(sd["ret_rms"])
+        self._obs_rms.copy_(sd["obs_rms"])
+        self._ret_rms.copy_(sd["ret_rms"])
         for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
             setattr(self, k, sd[k])
 

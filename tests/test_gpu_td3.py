@@ -76,7 +76,7 @@ def test_evaluate_and_checkpoint_roundtrip(tmp_path):
     eval_env = mk(99)
     mean, std, n = model.evaluate(eval_env, n_episodes=2)
     assert n == 256 and np.isfinite(mean) and mean < 0 and std > 0
-    assert torch.equal(eval_env._obs_rms[0], model.vec_normalize._obs_rms[0]) and eval_env.training is False
+    assert torch.equal(eval_env._obs_rms, model.vec_normalize._obs_rms) and eval_env.training is False
     mean2, _, _ = model.evaluate(mk(99), n_episodes=2)
     assert mean2 == mean                                    # deterministic policy + same env seed
     path = str(tmp_path / "best_model.pt")
@@ -85,7 +85,7 @@ def test_evaluate_and_checkpoint_roundtrip(tmp_path):
     assert other.num_timesteps == model.num_timesteps
     for a, b in zip(other.actor.parameters(), model.actor.parameters()):
         assert torch.equal(a, b)
-    assert torch.equal(other.vec_normalize._obs_rms[0], model.vec_normalize._obs_rms[0])
+    assert torch.equal(other.vec_normalize._obs_rms, model.vec_normalize._obs_rms)
     assert other.evaluate(mk(99), n_episodes=2)[0] == mean
 
 

@@ -57,13 +57,13 @@ def test_vecnormalize_matches_numpy_restatement(tmp_path):
     assert abs(env.obs_rms["count"].item() - obs_rms.count) < 1e-6
     # frozen statistics (evaluation env): no update, same normalisation; save / load round trip
     env.training = False
-    before = env._obs_rms[0].clone()
+    before = env._obs_rms.clone()
     env.step(torch.zeros((n, 4), device="cuda"))
-    assert torch.equal(before, env._obs_rms[0])
+    assert torch.equal(before, env._obs_rms)
     path = str(tmp_path / "vecnormalize.pkl")
     env.save(path)
     env2 = VecNormalize.load(path, R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=5, dtype="float32"))
-    assert torch.equal(env2._obs_rms[0], env._obs_rms[0]) and env2.clip_obs == 100.0
+    assert torch.equal(env2._obs_rms, env._obs_rms) and env2.clip_obs == 100.0
     x = torch.rand((n, 28), device="cuda") * 30
     assert torch.equal(env.normalize_obs(x), env2.normalize_obs(x))
 
