@@ -35,8 +35,12 @@ sys.path.insert(0, ROOT)
 
 N_ENVS = 65536
 T = 100
-BYTES_PER_ENV_STEP_ROLLOUT = 137      # in: action 16 + demand 4; out: obs 112 + reward 4 + done 1
-BYTES_PER_ENV_STEP_SINGLE = 345       # single-step VecEnv mode (state r/w + action + demand + reward + done)
+# SURVEY 8(d) counts one more byte per env-step for `done`; all envs run in lockstep, `done` is a host bool and no
+# kernel writes it, so it is not counted here
+BYTES_PER_ENV_STEP_ROLLOUT = 136      # in: action 16 + demand 4; out: obs 112 + reward 4
+BYTES_PER_ENV_STEP_SINGLE = 344       # single-step VecEnv mode (state 160 r + 160 w, action 16, demand 4, reward 4)
+WORKLOAD = ("config2: complex (uniform) scenario, MultiFacility centralized full-info, {n} envs/GPU x {T} periods "
+            "fixed-action parity rollout, full trajectory out")
 
 
 def measured_peak_gbs():
@@ -126,6 +130,60 @@ def cpu_port_throughput(init, demand, actions, threads, budget_s, with_traj=True
     return n * T * reps / dt, f"{reps} x ({n} envs x {T} periods, trajectory {'written' if with_traj else 'discarded'}) in {dt:.1f}s"
 
 
+def _py_ref_worker(args):
+    """One worker of the reference's own Python stepping loop: 16 envs stepped round-robin,
+    per-env np.random.seed before reset, fixed action [4,4,4,4]; timing inside the worker."""
+    wid, n_envs, episodes, ref_root = args
+    import warnings
+    os.environ["SUPPLYNET_REFERENCE_ROOT"] = ref_root
+    from oracle import ref_harness as H
+    warnings.simplefilter("ignore")
+    envs = [H.make_env("uniform", H.NODE_NAMES, True, True, 100) for _ in range(n_envs)]
+    a = np.array([4, 4, 4, 4])
+    t0 = time.perf_counter()
+    steps = 0
+    for ep in range(episodes):
+        for i, e in enumerate(envs):
+            np.random.seed(1000 * wid + 16 * ep + i)
+            e.reset()
+        for _ in range(100):
+            for e in envs:
+                e.step(a)
+                steps += 1
+    return steps, time.perf_counter() - t0
+
+
+def python_reference_throughput(episodes=6):
+    """The UNMODIFIED reference (make_beer_game_uniform_multi_facility + env.step, envs.py:289-414, 82-113) on the host
+    cores: multiprocessing.Pool(P = os.cpu_count()) x 16 envs x `episodes` episodes, plus a 1-process run.  The
+    reference travels to the GPU box as the git-ignored copy baseline/_ref (made by __graft_entry__.build() where
+    /root/reference is mounted); without it this leg reports why it is absent."""
+    import multiprocessing as mp
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_root, "supplynetwork.py")):
+        ref_root = "/root/reference"
+    if not os.path.isfile(os.path.join(ref_root, "supplynetwork.py")):
+        return {"unavailable": "baseline/_ref (copy of the reference) is not present on this box"}
+    P = os.cpu_count() or 1
+    out = {"unit": "env-steps/s", "kind": "reference", "envs_per_worker": 16, "episodes": episodes,
+           "source": os.path.relpath(ref_root, ROOT) if ref_root.startswith(ROOT) else ref_root,
+           "workload": "make_beer_game_uniform_multi_facility(all four facilities, box_action_space=True, random_init=True, "
+                       "global_observable=True), fixed action [4,4,4,4], per-env np.random.seed, resets included"}
+    ctx = mp.get_context("spawn")                    # no CUDA context / pinned buffers inherited by the workers
+    for procs in sorted({1, P}):
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_py_ref_worker, [(w, 16, episodes, ref_root) for w in range(procs)])
+        total, slowest = sum(r[0] for r in res), max(r[1] for r in res)
+        key = "value" if procs == P else "single_process_value"
+        out[key] = total / slowest
+        if procs == P:
+            out.update(cores=P, per_core_value=total / slowest / P,
+                       sample=f"{procs} processes x 16 envs x {episodes} episodes x 100 periods = {total} env-steps, slowest worker {slowest:.1f}s")
+        if P == 1:
+            out["single_process_value"] = out["value"]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,12 +205,12 @@ def run_reference(args):
         "impl": "reference", "metric": "env-steps/sec (batched beer game)", "value": v, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": N_ENVS * T / v * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i64", "data": "synthetic",
-        "config": {"workload": "config2: complex scenario, MultiFacility centralized full-info, 65,536 envs x 100 "
-                               "periods fixed-action parity rollout with full trajectory out (CPU port of the oracle)"},
+        "config": {"workload": WORKLOAD.format(n=N_ENVS, T=T),
+                   "implementation": "C port of the reference algorithm (oracle/beergame_c.c) on all host threads; the reference's own Python loop is timed beside it (cpu_baseline.python_reference)"},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
                          "single_thread_value": v1,
-                         "note": "C port of the reference algorithm (oracle/beergame_c.c); the reference itself is "
-                                 "pure Python (~5e3 env-steps/s/core measured in the build container, DESIGN.md)"},
+                         "note": "C port of the reference algorithm (oracle/beergame_c.c): the stronger CPU baseline, used as this line's value",
+                         "python_reference": None if args.no_python_ref else python_reference_throughput()},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -278,6 +336,15 @@ def run_native(args):
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
         extra = single_step_numbers(torch, dev, peak)
+    # the other BASELINE configs that shard over the GPUs, under the same launch at every N (collective: all ranks)
+    blocks = {}
+    h2d = init.nbytes + demand.nbytes + actions.nbytes
+    d2h = h_traj_obs.numel() * 4 + h_traj_rew.numel() * 4
+    if not args.no_configs:
+        del traj_obs, traj_rew, d_actions, h_traj_obs, h_traj_rew
+        torch.cuda.empty_cache()
+        blocks["config3"] = config3_block(torch, world, rank, dev, 10, 3)
+        blocks["config5"] = config5_block(torch, world, rank, dev, 256, 128)
 
     if rank == 0:
         cpu = None
@@ -287,15 +354,13 @@ def run_native(args):
             v, sample = cpu_port_throughput(init, demand, actions, threads, 10.0)
             v1, _ = cpu_port_throughput(init, demand, actions, 1, 3.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
-                   "single_thread_value": v1}
-        h2d = init.nbytes + demand.nbytes + actions.nbytes
-        d2h = h_traj_obs.numel() * 4 + h_traj_rew.numel() * 4
+                   "single_thread_value": v1,
+                   "python_reference": None if args.no_python_ref else python_reference_throughput()}
         line = {
             "metric": "env-steps/sec (batched beer game)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-            "config": {"workload": "config2: complex (uniform) scenario, MultiFacility centralized full-info, "
-                                   f"{n} envs/GPU x {T} periods fixed-action parity rollout, full trajectory out",
+            "config": {"workload": WORKLOAD.format(n=n, T=T),
                        "envs_per_gpu": n, "periods": T, "step": "one sn_episode launch (in-kernel reset + 100 periods, 1 episode of the batch)",
                        "l2": "inputs+outputs ~0.9 GB per step >> 126 MB L2, no flush needed",
                        "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of the 16-double statistics vector every {args.stats_interval} episodes"},
@@ -305,13 +370,15 @@ def run_native(args):
                     "cpu_binding": (f"{len(cpus)} CPUs next to the GPU (NVML affinity)" if cpus else "none")},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(n), "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic(n), "traffic_source": "static ncu capture (profiles/ncu_traffic.json), not measured in this run",
+                         "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,
         }
         if world > 1:
             line["per_rank_ms_per_step"] = per_rank_ms      # device time of every rank (value uses the max)
         line.update(extra)
+        line.update(blocks)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -368,7 +435,9 @@ def single_step_numbers(torch, dev, peak):
             res["with_obs" if with_obs else "state_only"] = {
                 "env_steps_per_s": n / (ms * 1e-3), "us_per_launch": ms * 1e3,
                 "achieved_gbs": n * bps / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": n * bps / (ms * 1e-3) / 1e9 / peak,
-                "bytes_per_env_step": bps, "launch": "CUDA graph of 94 sn_step launches"}
+                "bytes_per_env_step": bps, "launch": "CUDA graph of 94 sn_step launches",
+                "kernel": ("k_step_tiled (persistent, TMA tensor-map tiles, mbarrier pipeline)" if n * (bps + 0) >= (112 << 20)
+                           else "k_step (one thread per env; the batch is L2-resident)")}
         out[tag] = res
         del sim
     # the literal drop-in call: SB3-style VecEnv.step with numpy in / numpy out (pinned staging, H2D of the
@@ -428,31 +497,45 @@ def single_step_numbers(torch, dev, peak):
                                            "std_episode_return": summ["std_episode_return"],
                                            "note": "incl. per-episode demand/init generation (torch Philox) and episode moments"}
     del venv
-    # config-4 mode: 262,144 envs x 2 items (independent item chains, per-item costs), single-step API
+    # config-4 mode: 262,144 envs x 2 items (independent item chains, per-item costs), single-step API; the per-env
+    # reward is reduced over the two adjacent item chains inside the step kernel
     from multi_echelon_drl_b200.multi_item import MultiItemSupplyNetwork
     from dataclasses import replace
     n = 262144
     specs = [spec, replace(spec, holding_cost=(0.75,) * 4)]
-    mi = MultiItemSupplyNetwork(specs, n, dev, "int32")
-    mi.sim.demand.random_(0, 9, generator=g)
-    mi.sim.init.random_(0, 9, generator=g)
-    acts = torch.randint(0, 17, (n, 8), generator=g, device=dev, dtype=torch.int32)
-    mi.reset()
-    for _ in range(5):
-        mi.step(acts)
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    reps = 60
-    for _ in range(reps):
-        mi.step(acts)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / reps
-    out["multi_item_262144x2_step"] = {"env_steps_per_s": n / (ms * 1e-3), "item_chain_steps_per_s": 2 * n / (ms * 1e-3),
-                                       "us_per_step": ms * 1e3,
-                                       "config": "config 4: 262,144 envs x 2 items (one interleaved batch of 524,288 chains, per-item costs in-kernel), obs 56 / action 8, eager per-period calls"}
-    del mi
+    # per chain: state 160 r + 160 w, action 16, demand 4, chain reward 4, observation 112, episode return 8 r + 8 w,
+    # env reward 4 per env = 2 per chain
+    bpc = BYTES_PER_ENV_STEP_SINGLE + 112 + 16 + 2
+    res = {}
+    for mode in ("eager", "graph"):
+        mi = MultiItemSupplyNetwork(specs, n, dev, "int32", use_graph=(mode == "graph"))
+        mi.sim.demand.random_(0, 9, generator=g)
+        mi.sim.init.random_(0, 9, generator=g)
+        mi.action_buffer.copy_(torch.randint(0, 17, (n, 8), generator=g, device=dev, dtype=torch.int32))
+        acts = mi.action_buffer
+        mi.reset()
+        for _ in range(5):
+            mi.step(acts)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        reps = 60
+        for _ in range(reps):
+            mi.step(acts)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        res[mode] = {"us_per_step": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3), "achieved_gbs": 2 * n * bpc / (ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": 2 * n * bpc / (ms * 1e-3) / 1e9 / peak}
+        del mi
+    out["multi_item_262144x2_step"] = {
+        "env_steps_per_s": res["eager"]["env_steps_per_s"], "item_chain_steps_per_s": 2 * res["eager"]["env_steps_per_s"],
+        "us_per_step": res["eager"]["us_per_step"], "frac_of_hbm_peak": res["eager"]["frac_of_hbm_peak"],
+        "achieved_gbs": res["eager"]["achieved_gbs"], "bytes_per_chain_step": bpc,
+        "graph_replay_per_period": res["graph"],
+        "config": "config 4: 262,144 envs x 2 items (one interleaved batch of 524,288 chains, per-item costs and the per-env "
+                  "reward sum in-kernel), obs 56 / action 8, MultiItemSupplyNetwork.step called per period from Python "
+                  "(k_step_tiled); graph_replay_per_period = the same period as one replayed CUDA graph (device period counter)"}
     # other networks, same fixed-action rollout with trajectory out at config-2 size
     from multi_echelon_drl_b200.spec import tree_spec
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
@@ -497,30 +580,25 @@ def single_step_numbers(torch, dev, peak):
     return out
 
 
-def run_config3(args):
-    """BASELINE config 3: base-stock (HGE heuristic) rollouts over 1M envs sharded across the GPUs of the box
-    (131,072 envs per GPU), policy evaluated in-kernel, fresh device-generated demand / initial state per
-    episode, statistics all-reduced over NCCL at the end.  One step = one 100-period episode of every env."""
-    import torch
+def config3_block(torch, world, rank, dev, steps, warmup):
+    """BASELINE config 3: base-stock (HGE heuristic) rollouts, 131,072 envs per GPU (1,048,576 on 8), policy evaluated
+    in-kernel, fresh device-generated demand / initial state per episode, statistics all-reduced over NCCL at the end.
+    One step = one 100-period episode of every env.  Collective over the ranks: every rank calls it, every rank gets
+    the result (time = max over ranks)."""
     import torch.distributed as dist
-    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     from multi_echelon_drl_b200.distributed import allreduce_stats, summarize
     from multi_echelon_drl_b200.register_envs import make
     from multi_echelon_drl_b200.simulator import BasePolicyParams
     n = 131072
     venv = make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="int32", seed=1000 + rank)
     pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
-    venv.run_policy_episodes(pol, max(args.warmup, 3))
+    venv.run_policy_episodes(pol, max(warmup, 3))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    stats = venv.run_policy_episodes(pol, args.steps)
+    stats = venv.run_policy_episodes(pol, steps)
     allreduce_stats(stats)
     e.record()
     if world > 1:
@@ -529,46 +607,35 @@ def run_config3(args):
     ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        summ = summarize(stats)
-        assert summ["env_steps"] == n * T * args.steps * world
-        print(json.dumps({
-            "metric": "env-steps/sec (batched beer game)", "value": n * T * args.steps * world / (ms.item() * 1e-3),
-            "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i32", "data": "synthetic",
-            "config": {"workload": f"config3: base-stock [19,20,20,14] rollouts, {n} envs/GPU x {world} GPUs = {n * world} envs, "
-                                   "policy in-kernel, demand / initial state regenerated on the device per episode",
-                       "step": "one 100-period episode of every env (1 sn_episode launch + generation)"},
-            "gpu_launches": args.steps, "mean_episode_return": summ["mean_episode_return"],
-            "std_episode_return": summ["std_episode_return"],
-            "roofline": {"bound": "alu/issue", "note": "state on-chip, 4 B/env-step of HBM: not bandwidth bound; "
-                                                       "197 instructions per warp-period, issue slots 66 % busy (profiles/r1_notes.md)"}}))
-    if world > 1:
-        dist.destroy_process_group()
+    summ = summarize(stats)
+    assert summ["env_steps"] == n * T * steps * world
+    return {"value": n * T * steps * world / (ms.item() * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+            "envs_total": n * world, "ms_per_step": ms.item() / steps,
+            "mean_episode_return": summ["mean_episode_return"], "std_episode_return": summ["std_episode_return"],
+            "qty_range_flags": float(stats[13].item()),
+            "workload": f"config3: base-stock [19,20,20,14] rollouts, {n} envs/GPU x {world} GPUs = {n * world} envs, policy "
+                        "in-kernel, demand / initial state regenerated on the device per episode; one step = one 100-period "
+                        "episode of every env (generation + 1 sn_episode launch)",
+            "bound": "alu/issue (state on-chip, 4 B/env-step of HBM)"}
 
 
-def run_config5(args):
+def config5_block(torch, world, rank, dev, steps, warmup):
     """BASELINE config 5: TD3 with heuristic-guided exploration on 4,096 complex-scenario envs per GPU (hyper-parameters
     of setup_example_centralized.yaml), env -> VecNormalize -> policy -> replay buffer -> update all on the device.
-    One step = one vector step of every env plus one gradient update (train_freq 32, 32 updates per 32 steps)."""
-    import torch
-    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
-    torch.cuda.set_device(local)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    One step = one vector step of every env plus one gradient update (train_freq 32, 32 updates per 32 steps).
+    Collective over the ranks (gradients are averaged over NCCL inside the update graph)."""
     from multi_echelon_drl_b200.register_envs import make
     from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
     from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
     from multi_echelon_drl_b200.vec_normalize import VecNormalize
     n = 4096
-    env = VecNormalize(make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=1000 * rank),
-                       clip_obs=100.0, clip_reward=1000.0)
+    env = VecNormalize(make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=1000 * rank,
+                            use_graph=True), clip_obs=100.0, clip_reward=1000.0)
     cfg = TD3Config(batch_size=128, net_arch=(768,), learning_rate=1e-3, tau=0.01, train_freq=32, gradient_steps=32,
                     action_noise_std=0.4, gamma=0.95, hge_rate_at_start=0.5, seed=rank)
     model = HgeTD3(env, BaseStockPolicy([19, 20, 20, 14]), cfg, ddp=world > 1)
-    steps = max(32, args.steps // 32 * 32)
-    warm = max(128, args.warmup // 32 * 32)                    # covers the eager warm-up cycles and the graph captures
+    steps = max(32, steps // 32 * 32)
+    warm = max(128, warmup // 32 * 32)                    # covers the eager warm-up cycles and the graph captures
     model.learn(n * warm)
     torch.cuda.synchronize()
     model.timers = type(model.timers)()
@@ -577,20 +644,60 @@ def run_config5(args):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     split = model.time_split()
+    flags = env.venv.sim.device_flags()
     model.close()
     if world > 1:
-        w = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        w = torch.tensor([wall], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(w, op=torch.distributed.ReduceOp.MAX)
         wall = float(w.item())
+    return {"value": n * steps * world / wall, "unit": "env-steps/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": wall / steps * 1e3, "updates": steps,
+            "time_split_s": {k: v for k, v in split.items() if k.endswith("_s")},
+            "us_per_vector_step": {k[:-2]: round(v / steps * 1e6, 2) for k, v in split.items() if k.endswith("_s")},
+            "device_flags": flags,
+            "workload": f"config5: TD3+HGE, {n} envs/GPU x {world}, batch 128, one 768-unit hidden layer, train_freq 32 / 32 "
+                        "updates, device replay buffer; env step + VecNormalize = ONE replayed cooperative kernel (device "
+                        "period counter), update and actor forward as CUDA graphs; one step = one vector step of all envs + "
+                        "one gradient update (wall clock, max over ranks); GPU-time split per vector step in us"}
+
+
+def _init_dist(torch):
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    return world, rank, dev
+
+
+def run_config3(args):
+    import torch
+    world, rank, dev = _init_dist(torch)
+    b = config3_block(torch, world, rank, dev, args.steps, args.warmup)
     if rank == 0:
         print(json.dumps({
-            "metric": "env-steps/sec (TD3+HGE training loop)", "value": n * steps * world / wall, "unit": "env-steps/s",
-            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config5: TD3+HGE, {n} envs/GPU x {world}, batch 128, one 768-unit hidden layer, "
-                                   "train_freq 32 / 32 updates, device replay buffer, update and actor forward as CUDA graphs",
-                       "step": "one vector step of all envs + one gradient update (wall clock, max over ranks)"},
-            "time_split_s": {k: v for k, v in split.items() if k.endswith("_s")}, "updates": steps}))
+            "metric": "env-steps/sec (batched beer game)", "value": b["value"], "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": b["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": b["workload"]}, "gpu_launches": args.steps,
+            "mean_episode_return": b["mean_episode_return"], "std_episode_return": b["std_episode_return"],
+            "roofline": {"bound": "alu/issue", "note": "state on-chip, 4 B/env-step of HBM: not bandwidth bound; "
+                                                       "197 instructions per warp-period, issue slots 66 % busy (profiles/r1_notes.md)"}}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_config5(args):
+    import torch
+    world, rank, dev = _init_dist(torch)
+    b = config5_block(torch, world, rank, dev, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env-steps/sec (TD3+HGE training loop)", "value": b["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": b["steps"], "warmup": b["warmup"], "ms_per_step": b["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": b["workload"]}, "time_split_s": b["time_split_s"],
+            "us_per_vector_step": b["us_per_vector_step"], "updates": b["updates"]}))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -609,6 +716,8 @@ def main():
     ap.add_argument("--stats-interval", type=int, default=10, help="episodes between statistics all-reduces (N>1)")
     ap.add_argument("--e2e-chunks", type=int, default=5, help="period spans of the pipelined host path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-python-ref", action="store_true", help="skip the reference's own Python loop inside cpu_baseline")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-5 blocks of the default line")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's socket")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
     args = ap.parse_args()

@@ -45,10 +45,12 @@ extern "C" {
 
 /* Device control words of sn_step_ex (int32[SN_CTL_WORDS], caller-owned, zero-initialised):
  * the period lives in device memory so that ONE captured CUDA graph serves every period of an episode. */
-#define SN_CTL_WORDS 4
+#define SN_CTL_WORDS 8
 #define SN_CTL_PERIOD 0         /* period to play; read by the launch and advanced by it (set to 0 to start an episode) */
 #define SN_CTL_TICKET 1         /* internal (block ticket); leave at 0                                               */
 #define SN_CTL_FLAGS 2          /* sticky SN_FLAG_* bits                                                             */
+#define SN_CTL_BARRIER 3        /* internal (grid barrier of the one-kernel VecNormalize mode); leave at 0           */
+#define SN_CTL_SEQ 4            /* internal (launch sequence number of that mode); never reset                       */
 #define SN_FLAG_STEP_AFTER_TERMINAL 1   /* a launch found period >= max_episode_steps and did nothing (envs.py:88-89) */
 #define SN_FLAG_QTY_RANGE 2             /* SN_I32: a quantity reached 2^SN_QTY_LIMIT_LOG2, results may have wrapped    */
 
@@ -204,7 +206,14 @@ int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, 
  *                vn_returns != NULL, returns <- returns*vn_gamma + reward and RunningMeanStd.update(returns) into
  *                vn_ret_rms (mean, var, count); vn_scratch is 2*obs_dim+2 doubles, zero before the first launch (the
  *                launch leaves it zero).  Follow with sn_vecnorm_apply.  Not for the terminal step of an episode:
- *                SB3 feeds the statistics the observation of the NEXT episode there (DummyVecEnv auto-reset). */
+ *                SB3 feeds the statistics the observation of the NEXT episode there (DummyVecEnv auto-reset).
+ *   vn_nobs      one-kernel mode (n_envs <= SMs x 128, i.e. one tile per SM; float32/int32 quantities): the same
+ *                launch also writes the normalised observation [n_envs][obs_dim] (and vn_nrew [n_envs], if given):
+ *                clip((obs-mean)/sqrt(var+vn_epsilon), +-vn_clip_obs), clip(reward/sqrt(ret_var+eps), +-vn_clip_reward),
+ *                with the statistics AFTER this step's update when vn_scratch is given (then vn_scratch is
+ *                2*(2*obs_dim+2) doubles, zero before the first launch, and the launch is cooperative: its blocks
+ *                meet at a grid barrier between the moments and the normalisation), else with vn_obs_rms / vn_ret_rms
+ *                as they are (evaluation).  Replaces the sn_vecnorm_apply launch. */
 typedef struct sn_step_io {
   void* state;
   const void* actions;
@@ -224,6 +233,11 @@ typedef struct sn_step_io {
   double* vn_ret_rms;
   double* vn_returns;
   double vn_gamma;
+  float* vn_nobs;
+  float* vn_nrew;
+  float vn_clip_obs;
+  float vn_clip_reward;
+  double vn_epsilon;
 } sn_step_io;
 int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const sn_step_io* io, void* stream);
 

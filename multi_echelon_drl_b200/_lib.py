@@ -18,7 +18,7 @@ SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
 ABI_VERSION = 8
-SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS = 4, 0, 1, 2
+SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS, SN_CTL_BARRIER, SN_CTL_SEQ = 8, 0, 1, 2, 3, 4
 SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
 SN_QTY_LIMIT_LOG2 = 26
 
@@ -74,6 +74,8 @@ class SnStepIo(C.Structure):
         ("reward64", C.c_void_p), ("cost", C.c_void_p), ("ep_return", C.c_void_p), ("stats", C.c_void_p),
         ("vn_scratch", C.c_void_p), ("vn_obs_rms", C.c_void_p), ("vn_ret_rms", C.c_void_p),
         ("vn_returns", C.c_void_p), ("vn_gamma", C.c_double),
+        ("vn_nobs", C.c_void_p), ("vn_nrew", C.c_void_p), ("vn_clip_obs", C.c_float), ("vn_clip_reward", C.c_float),
+        ("vn_epsilon", C.c_double),
     ]
 
 

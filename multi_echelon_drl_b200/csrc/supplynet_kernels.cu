@@ -353,6 +353,11 @@ struct StepPtrs {
   double* vn_ret_rms;       // mean, var, count
   double* vn_returns;       // [n] discounted returns (NULL = observations only)
   double vn_gamma;
+  // one-kernel mode (tiled kernel, at most one tile per SM): normalised outputs written by the same launch
+  float* vn_nobs;           // [n][od]
+  float* vn_nrew;           // [n] (NULL = rewards are not normalised)
+  float vn_clip_obs, vn_clip_rew;
+  double vn_eps;
 };
 
 // Period of this launch: the host's argument, or the device counter ctl[SN_CTL_PERIOD] (one captured CUDA graph
@@ -1205,8 +1210,11 @@ int step_kernel_choice() {      // read per call: tests switch it between launch
   const char* v = std::getenv("SN_STEP_KERNEL");
   return (v && !std::strcmp(v, "plain")) ? 1 : (v && !std::strcmp(v, "tiled")) ? 2 : 0;
 }
-#ifndef SN_TILED_MIN_ENVS
-#define SN_TILED_MIN_ENVS 32768        // below this one period is launch latency either way; the plain kernel has the shorter prologue
+#ifndef SN_TILED_MIN_BYTES
+// Batches whose per-period traffic fits the 126 MB L2 are served faster by the plain kernel (shorter prologue, the
+// state never leaves L2); beyond that the stream comes from HBM and the tiled kernel wins (measured cross-over:
+// 262,144 envs with the observation output, profiles/r2_notes.md)
+#define SN_TILED_MIN_BYTES (112ll << 20)
 #endif
 
 // cuTensorMapEncodeTiled, fetched from the driver at run time (libcuda is not linked)
@@ -1259,6 +1267,27 @@ int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period
   const int64_t tiles = (n + C::kTile - 1) / C::kTile;
   const int64_t sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (out.vn_nobs != nullptr) {
+    if (tiles > sms) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes at most %lld envs on this device (one tile per SM)", (long long)(sms * C::kTile));
+    if (!aligned16(out.vn_nobs) != !tma_ok(out.obs) || (out.vn_nrew != nullptr && !aligned16(out.vn_nrew)))
+      return fail(SN_ERR_INVALID, "sn_step_ex: obs / vn_nobs / vn_nrew must share their 16-byte alignment");
+  }
+  if (out.vn_nobs != nullptr && out.vn_scratch != nullptr) {
+    // blocks meet at a grid barrier: cooperative launch (the runtime guarantees that all of them are resident)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, d, tm, n, ld, period, (const T*)actions, (const T*)demand, out, tma_ok(out.obs));
+    if (err != cudaSuccess) return fail(SN_ERR_CUDA, "sn_step cooperative launch: %s", cudaGetErrorString(err));
+    return cuda_ok("sn_step launch");
+  }
   kern<<<grid, C::kThreads, smem, st>>>(d, tm, n, ld, period, (const T*)actions, (const T*)demand, out, tma_ok(out.obs));
   return cuda_ok("sn_step launch");
 }
@@ -1274,10 +1303,12 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
   // beer-game lead times: the TMA-tiled persistent kernel for HBM-sized batches (and whenever the VecNormalize
   // statistics are fused in), the plain one-thread-per-env kernel for small ones
   const bool tiled_ok = is_standard(spec) && aligned16(state) && aligned16(demand) && aligned16(actions) &&
-                        (out.reward == nullptr || aligned16(out.reward)) && (out.env_reward == nullptr || aligned16(out.env_reward));
+                        (out.reward == nullptr || aligned16(out.reward)) && (out.env_reward == nullptr || aligned16(out.env_reward)) &&
+                        (out.ep_return == nullptr || aligned16(out.ep_return)) && (out.vn_returns == nullptr || aligned16(out.vn_returns));
   const int choice = step_kernel_choice();
-  const bool want_tiled = out.vn_scratch != nullptr || choice == 2 || (choice == 0 && n >= SN_TILED_MIN_ENVS);
-  if (out.vn_scratch != nullptr && !tiled_ok)
+  const int64_t bytes_per_env = 2 * (int64_t)sn::kStateWords * (int64_t)sizeof(T) + 24 + (out.obs != nullptr ? 28 * 4 : 0);
+  const bool want_tiled = out.vn_scratch != nullptr || out.vn_nobs != nullptr || choice == 2 || (choice == 0 && n * bytes_per_env >= SN_TILED_MIN_BYTES);
+  if ((out.vn_scratch != nullptr || out.vn_nobs != nullptr) && !tiled_ok)
     return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: fused VecNormalize statistics need the beer game's lead times and 16-byte aligned buffers");
   if (tiled_ok && want_tiled) {
     if (is_identity(spec)) return launch_step_tiled<T, true>(d, n, ld, period, state, actions, demand, out, st);
@@ -1432,10 +1463,14 @@ int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
       return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: env_reward needs a multi-item chain batch with 2 or 4 items (n_items=%d)", spec->n_items);
     if (n_envs % spec->n_items != 0) return fail(SN_ERR_INVALID, "sn_step_ex: n_envs=%lld is not a multiple of n_items=%d", (long long)n_envs, spec->n_items);
   }
-  const bool vn = io->vn_scratch || io->vn_obs_rms || io->vn_ret_rms || io->vn_returns;
+  const bool vn = io->vn_scratch || io->vn_obs_rms || io->vn_ret_rms || io->vn_returns || io->vn_nobs || io->vn_nrew;
   if (vn) {
-    if (!io->vn_scratch || !io->vn_obs_rms) return fail(SN_ERR_INVALID, "sn_step_ex: vn_scratch and vn_obs_rms must be given together");
+    if (!io->vn_obs_rms) return fail(SN_ERR_INVALID, "sn_step_ex: the VecNormalize extras need vn_obs_rms");
+    if (!io->vn_scratch && !io->vn_nobs) return fail(SN_ERR_INVALID, "sn_step_ex: give vn_scratch (update), vn_nobs (normalise) or both");
     if (io->vn_returns && !io->vn_ret_rms) return fail(SN_ERR_INVALID, "sn_step_ex: vn_returns needs vn_ret_rms");
+    if (io->vn_nrew && (!io->vn_nobs || !io->vn_ret_rms)) return fail(SN_ERR_INVALID, "sn_step_ex: vn_nrew needs vn_nobs and vn_ret_rms");
+    if (io->vn_returns && !io->vn_scratch) return fail(SN_ERR_INVALID, "sn_step_ex: vn_returns needs vn_scratch (the statistics update)");
+    if (io->vn_nobs && dtype == SN_F64) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes SN_I32 / SN_F32 quantities");
     if (!io->ctl || !io->obs) return fail(SN_ERR_INVALID, "sn_step_ex: fused VecNormalize statistics need ctl and obs");
     if (io->vn_returns && !io->reward) return fail(SN_ERR_INVALID, "sn_step_ex: vn_returns needs reward");
     if (spec->n_items > 1 || !is_standard(spec)) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: fused VecNormalize statistics need the single-item beer-game chain");
@@ -1445,6 +1480,8 @@ int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   out.ep_return = io->ep_return; out.stats = io->stats; out.env_reward = io->env_reward; out.ctl = io->ctl;
   out.vn_scratch = io->vn_scratch; out.vn_obs_rms = io->vn_obs_rms; out.vn_ret_rms = io->vn_ret_rms;
   out.vn_returns = io->vn_returns; out.vn_gamma = io->vn_gamma;
+  out.vn_nobs = io->vn_nobs; out.vn_nrew = io->vn_nrew; out.vn_clip_obs = io->vn_clip_obs; out.vn_clip_rew = io->vn_clip_reward;
+  out.vn_eps = io->vn_epsilon;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case SN_I32: return do_step<int32_t>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);

@@ -63,6 +63,24 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Grid-wide barrier of the one-kernel VecNormalize mode (cooperative launch: every CTA is resident).  The block
+// that arrives last advances the period and releases the others by bumping the launch sequence number, which
+// every block read before arriving.  Bounded spin: a protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier_and_advance(int32_t* ctl, int period, int seq) {
+  __threadfence();
+  if (atomicAdd(ctl + SN_CTL_BARRIER, 1) == (int)gridDim.x - 1) {
+    ctl[SN_CTL_BARRIER] = 0;
+    ctl[SN_CTL_PERIOD] = period + 1;
+    __threadfence();
+    atomicExch(ctl + SN_CTL_SEQ, seq + 1);
+  } else {
+    const volatile int32_t* p = ctl + SN_CTL_SEQ;
+    for (uint32_t spins = 0; *p == seq; ++spins)
+      if (spins > (1u << 24)) __trap();
+  }
+  __threadfence();
+}
+
 // ---- stage geometry ----------------------------------------------------------------------------------------
 template <typename T, typename Ops>
 struct TileCfg {
@@ -80,11 +98,14 @@ struct TileCfg {
   static constexpr int kOffObs = kOffDem + kDemBytes;
   static constexpr int kOffRew = kOffObs + kObsBytes;
   static constexpr int kOffERew = kOffRew + kRewBytes;
-  static constexpr int kStageBytes = kOffERew + kRewBytes;         // every part a multiple of 128 bytes
+  static constexpr int kOffEpr = kOffERew + kRewBytes;            // episode returns of the tile (double, in/out)
+  static constexpr int kOffVnr = kOffEpr + kTile * 8;              // VecNormalize's discounted returns (double, in/out)
+  static constexpr int kStageBytes = kOffVnr + kTile * 8;          // every part a multiple of 128 bytes
   static constexpr int kBarBytes = 128;                            // full[kStages], done[kStages]
   static constexpr int kRedDoubles = (kConsumerWarps + 1) * 14;   // block_reduce_add scratch
   static constexpr int kVnDoubles = 2 * kTile;                      // column-moment partials of the fused VecNormalize
-  static constexpr int kRedBytes = ((kRedDoubles + kVnDoubles) * 8 + 16 + 127) & ~127;
+  static constexpr int kStatFloats = 80;                           // one-kernel VecNormalize: mean[32], 1/std[32], 1/std of the returns
+  static constexpr int kRedBytes = ((kRedDoubles + kVnDoubles) * 8 + 16 + kStatFloats * 4 + 127) & ~127;
   static constexpr size_t smem_bytes(int stages) { return 128 + kBarBytes + kRedBytes + (size_t)stages * kStageBytes; }
 };
 
@@ -122,6 +143,10 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
     return;
   }
   const bool terminal = period + 1 >= sp.t_max;
+  // one-kernel VecNormalize: statistics (optionally updated across the grid) and normalisation in this launch
+  const bool vn_onepass = out.vn_nobs != nullptr;
+  const bool vn_barrier = vn_onepass && out.vn_scratch != nullptr;
+  const int seq = vn_barrier ? *reinterpret_cast<const volatile int32_t*>(out.ctl + SN_CTL_SEQ) : 0;
   const int64_t dstride = Ops::dstride(sp, ld);
   const T* __restrict__ demand_next = out.ctl != nullptr ? demand + (int64_t)(period + 1) * dstride : demand;
   const int od = 7 * sp.n_obs, na = sp.n_agents, n_src = Ops::n_src(sp);
@@ -159,9 +184,23 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
           if (lane == 31 && obs_tma) bulk_store_s2g(out.obs + env0 * od, st + C::kOffObs, (uint32_t)(kTile * od * 4));
           if (lane == 30 && out.reward != nullptr) bulk_store_s2g(out.reward + env0, st + C::kOffRew, (uint32_t)(kTile * 4));
           if (lane == 29 && out.env_reward != nullptr)
-            bulk_store_s2g(out.env_reward + env0 / sp.n_items, st + C::kOffERew, (uint32_t)(kTile / sp.n_items * 4));
+            bulk_store_s2g(out.env_reward + (env0 >> (sp.n_items == 2 ? 1 : 2)), st + C::kOffERew, (uint32_t)(kTile / sp.n_items * 4));
+          if (lane == 28 && out.ep_return != nullptr) bulk_store_s2g(out.ep_return + env0, st + C::kOffEpr, (uint32_t)(kTile * 8));
+          if (lane == 27 && out.vn_returns != nullptr) bulk_store_s2g(out.vn_returns + env0, st + C::kOffVnr, (uint32_t)(kTile * 8));
         }
         bulk_commit();
+        if (vn_onepass) {
+          // the normalised tile is built in the next stage's buffers, after the grid barrier: the step's own results
+          // above are already on their way while the blocks meet
+          const int s1 = (s + 1) % kStages;
+          uint8_t* st1 = stages + (size_t)s1 * C::kStageBytes;
+          mbar_wait(&done[s1], (uint32_t)((j / kStages) & 1));
+          if (full_tile) {
+            if (lane == 26 && obs_tma) bulk_store_s2g(out.vn_nobs + env0 * od, st1 + C::kOffObs, (uint32_t)(kTile * od * 4));
+            if (lane == 25 && out.vn_nrew != nullptr) bulk_store_s2g(out.vn_nrew + env0, st1 + C::kOffRew, (uint32_t)(kTile * 4));
+          }
+          bulk_commit();
+        }
       }
       if (it < my_tiles) {
         bulk_wait_read<1>();                                       // the stores of tile it-kStages have left this stage
@@ -173,12 +212,21 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         uint8_t* st = stages + (size_t)s * C::kStageBytes;
         const uint32_t row_bytes = (uint32_t)(cols * sizeof(T));
         if (lane == 0) {                                           // the whole box counts, clipped columns included
-          mbar_arrive_expect_tx(&full[s], (uint32_t)C::kStateBytes + (uint32_t)n_src * row_bytes +
-                                              (full_tile ? (uint32_t)(kTile * na * sizeof(T)) : 0u));
+          uint32_t tx = (uint32_t)C::kStateBytes + (uint32_t)n_src * row_bytes;
+          if (full_tile) {
+            tx += (uint32_t)(kTile * na * sizeof(T));
+            if (out.ep_return != nullptr) tx += (uint32_t)(kTile * 8);
+            if (out.vn_returns != nullptr) tx += (uint32_t)(kTile * 8);
+          }
+          mbar_arrive_expect_tx(&full[s], tx);
           tensor_load_2d(st, &tm_state, (int)env0, 0, &full[s]);
         }
         __syncwarp();
         if (lane == 31 && full_tile) bulk_load_g2s(st + C::kOffAct, actions + env0 * na, (uint32_t)(kTile * na * sizeof(T)), &full[s]);
+        // per-env accumulators that live in global memory travel with the tile: a load issued by a consumer warp
+        // would stall it for the full memory latency (one warp per scheduler: nothing else to run meanwhile)
+        if (lane == 23 && full_tile && out.ep_return != nullptr) bulk_load_g2s(st + C::kOffEpr, out.ep_return + env0, (uint32_t)(kTile * 8), &full[s]);
+        if (lane == 22 && full_tile && out.vn_returns != nullptr) bulk_load_g2s(st + C::kOffVnr, out.vn_returns + env0, (uint32_t)(kTile * 8), &full[s]);
         if (lane >= 24 && lane < 24 + n_src)
           bulk_load_g2s(st + C::kOffDem + (size_t)(lane - 24) * kTile * sizeof(T), demand_next + (int64_t)(lane - 24) * ld + env0,
                         row_bytes, &full[s]);
@@ -187,29 +235,11 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
     bulk_wait_read<0>();
   } else {
     // ================= consumer warps: thread = env of the tile ==========================================
-    // per-env accumulators that live in global memory (episode return, VecNormalize's discounted return) are
-    // requested one tile ahead: with one consumer warp per scheduler nothing else would hide a load issued here
-    double epr_pre = 0.0, vnr_pre = 0.0;
-    {
-      const int64_t e0 = (int64_t)blockIdx.x * kTile + tid;
-      if (my_tiles > 0 && e0 < n) {
-        if (out.ep_return) epr_pre = out.ep_return[e0];
-        if (out.vn_returns) vnr_pre = out.vn_returns[e0];
-      }
-    }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int s = (int)(it % kStages);
       const int64_t env0 = (blockIdx.x + it * gridDim.x) * kTile;
       const int64_t env = env0 + tid;
       const bool valid = env < n, full_tile = env0 + kTile <= n;
-      const double epr = epr_pre, vnr = vnr_pre;
-      {
-        const int64_t en = env + (int64_t)gridDim.x * kTile;
-        if (it + 1 < my_tiles && en < n) {
-          if (out.ep_return) epr_pre = out.ep_return[en];
-          if (out.vn_returns) vnr_pre = out.vn_returns[en];
-        }
-      }
       uint8_t* st = stages + (size_t)s * C::kStageBytes;
       T* s_state = reinterpret_cast<T*>(st);
       const T* s_act = reinterpret_cast<const T*>(st + C::kOffAct);
@@ -217,6 +247,15 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
       float* s_obs = reinterpret_cast<float*>(st + C::kOffObs);
       float* s_rew = reinterpret_cast<float*>(st + C::kOffRew);
       float* s_erew = reinterpret_cast<float*>(st + C::kOffERew);
+      double* s_epr = reinterpret_cast<double*>(st + C::kOffEpr);
+      double* s_vnr = reinterpret_cast<double*>(st + C::kOffVnr);
+      // one-kernel VecNormalize: the running statistics as they are before this step, requested before the tile
+      // arrives (read before the grid barrier in any case: block 0 rewrites them after it)
+      double vn_m = 0.0, vn_v = 1.0, vn_cnt = 0.0;
+      if (vn_onepass) {
+        if (tid < od) { vn_m = out.vn_obs_rms[tid]; vn_v = out.vn_obs_rms[od + tid]; vn_cnt = out.vn_obs_rms[2 * od]; }
+        if (tid == 32 && out.vn_ret_rms != nullptr) { vn_m = out.vn_ret_rms[0]; vn_v = out.vn_ret_rms[1]; vn_cnt = out.vn_ret_rms[2]; }
+      }
       mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
 
       typename Ops::E e;
@@ -248,10 +287,13 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
           }
         }
         double ret_ep = 0.0;
-        if (out.ep_return) { ret_ep = epr + so.reward; out.ep_return[env] = ret_ep; }
+        if (out.ep_return) {
+          ret_ep = (full_tile ? s_epr[tid] : out.ep_return[env]) + so.reward;
+          if (full_tile) s_epr[tid] = ret_ep; else out.ep_return[env] = ret_ep;
+        }
         if (out.vn_returns != nullptr) {                           // VecNormalize: ret <- ret*gamma + r (the float reward)
-          const double r = vnr * out.vn_gamma + (double)rf;
-          out.vn_returns[env] = r;
+          const double r = (full_tile ? s_vnr[tid] : out.vn_returns[env]) * out.vn_gamma + (double)rf;
+          if (full_tile) s_vnr[tid] = r; else out.vn_returns[env] = r;
           vsr += r;
           vsrr += r * r;
         }
@@ -265,13 +307,105 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
       }
       if (out.env_reward != nullptr) {                             // every lane takes part in the shuffles
         const double tot = env_reward_sum(so.reward, sp.n_items);
-        if (valid && (tid % sp.n_items) == 0) {
-          if (full_tile) s_erew[tid / sp.n_items] = (float)tot;
-          else out.env_reward[env / sp.n_items] = (float)tot;
+        const int sh = sp.n_items == 2 ? 1 : 2;                    // n_items is 2 or 4 here
+        if (valid && (tid & (sp.n_items - 1)) == 0) {
+          if (full_tile) s_erew[tid >> sh] = (float)tot;
+          else out.env_reward[env >> sh] = (float)tot;
         }
       }
       const bool obs_by_threads = out.obs != nullptr && !(full_tile && obs_tma);
-      if (obs_by_threads || out.vn_scratch != nullptr) {
+      if (vn_onepass) {
+        // ---- one-kernel VecNormalize (one tile per CTA): moments -> grid barrier -> merged statistics -> normalise
+        uint8_t* st1 = stages + (size_t)((s + 1) % kStages) * C::kStageBytes;
+        float* s_nobs = reinterpret_cast<float*>(st1 + C::kOffObs);
+        float* s_nrew = reinterpret_cast<float*>(st1 + C::kOffRew);
+        float* s_stat = reinterpret_cast<float*>(last_flag + 4);                           // mean[32], 1/std[32], 1/std of the returns
+        const int rows = (int)((n - env0) < kTile ? (n - env0) : kTile);
+        const int ng = od <= 32 ? kTile / od : 0;
+        const int ret_thread = 32;                                 // od <= 28 on this kernel: thread 32 owns the return statistics
+        // the step's own results can leave now: hand stage s to the producer (it only reads it; so do we from here on)
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
+        named_bar_sync(1, kTile);                                  // the tile's observation rows are complete
+        double m = vn_m, v = vn_v;
+        const double cnt = vn_cnt;
+        if (vn_barrier) {
+          double* scr = out.vn_scratch + (seq & 1) * (2 * od + 2);           // double-buffered across launches
+          double* scr_other = out.vn_scratch + ((seq & 1) ^ 1) * (2 * od + 2);
+          if (tid < ng * od) {
+            const int c = tid % od, g = tid / od;
+            double sx = 0.0, sxx = 0.0;
+            for (int r = g; r < rows; r += ng) {
+              const double x = (double)s_obs[r * od + c];
+              sx += x;
+              sxx += x * x;
+            }
+            vn_red[tid] = sx;
+            vn_red[kTile + tid] = sxx;
+          }
+          double sr = vsr, srr = vsrr;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); srr += __shfl_xor_sync(0xffffffffu, srr, o); }
+          if (lane == 0) { red[2 * warp] = sr; red[2 * warp + 1] = srr; }
+          named_bar_sync(1, kTile);
+          if (tid < od) {
+            double a = 0.0, b = 0.0;
+            for (int g = 0; g < ng; ++g) { a += vn_red[g * od + tid]; b += vn_red[kTile + g * od + tid]; }
+            atomicAdd(&scr[tid], a);
+            atomicAdd(&scr[od + tid], b);
+          } else if (tid == ret_thread && out.vn_returns != nullptr) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < C::kConsumerWarps; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+            atomicAdd(&scr[2 * od], a);
+            atomicAdd(&scr[2 * od + 1], b);
+          }
+          named_bar_sync(1, kTile);                                // this block's contributions are issued
+          if (tid == 0) grid_barrier_and_advance(out.ctl, period, seq);
+          named_bar_sync(1, kTile);
+          const double bn = (double)n;
+          if (tid < od) {
+            rms_merge_inplace(&m, &v, cnt, __ldcg(&scr[tid]), __ldcg(&scr[od + tid]), bn);
+            if (blockIdx.x == 0) {
+              out.vn_obs_rms[tid] = m;
+              out.vn_obs_rms[od + tid] = v;
+              if (tid == 0) out.vn_obs_rms[2 * od] = cnt + bn;
+            }
+          } else if (tid == ret_thread && out.vn_returns != nullptr) {
+            rms_merge_inplace(&m, &v, cnt, __ldcg(&scr[2 * od]), __ldcg(&scr[2 * od + 1]), bn);
+            if (blockIdx.x == 0) { out.vn_ret_rms[0] = m; out.vn_ret_rms[1] = v; out.vn_ret_rms[2] = cnt + bn; }
+          }
+          if (blockIdx.x == 0 && tid >= 64 && tid < 64 + 2 * od + 2) scr_other[tid - 64] = 0.0;   // the previous launch's sums
+        }
+        if (tid < od) { s_stat[tid] = (float)m; s_stat[32 + tid] = (float)(1.0 / sqrt(v + out.vn_eps)); }
+        if (tid == ret_thread) s_stat[64] = (float)(1.0 / sqrt(v + out.vn_eps));
+        named_bar_sync(1, kTile);
+        if (valid) {                                               // same arithmetic as sn_vecnorm_apply
+          const float co = out.vn_clip_obs;
+          for (int j = 0; j < od; j += 4) {                        // od is a multiple of 7; rows are 16-byte aligned when it is one of 4 too
+            if ((od & 3) == 0) {
+              const float4 x = *reinterpret_cast<const float4*>(s_obs + tid * od + j);
+              float4 z;
+              z.x = fminf(fmaxf((x.x - s_stat[j]) * s_stat[32 + j], -co), co);
+              z.y = fminf(fmaxf((x.y - s_stat[j + 1]) * s_stat[32 + j + 1], -co), co);
+              z.z = fminf(fmaxf((x.z - s_stat[j + 2]) * s_stat[32 + j + 2], -co), co);
+              z.w = fminf(fmaxf((x.w - s_stat[j + 3]) * s_stat[32 + j + 3], -co), co);
+              *reinterpret_cast<float4*>(s_nobs + tid * od + j) = z;
+            } else {
+              for (int jj = j; jj < j + 4 && jj < od; ++jj)
+                s_nobs[tid * od + jj] = fminf(fmaxf((s_obs[tid * od + jj] - s_stat[jj]) * s_stat[32 + jj], -co), co);
+            }
+          }
+          if (out.vn_nrew != nullptr) {
+            const float z = fminf(fmaxf((float)so.reward * s_stat[64], -out.vn_clip_rew), out.vn_clip_rew);
+            if (full_tile) s_nrew[tid] = z; else out.vn_nrew[env] = z;
+          }
+        }
+        if (obs_by_threads) {
+          named_bar_sync(1, kTile);
+          for (int i = tid; i < rows * od; i += kTile) { out.obs[env0 * od + i] = s_obs[i]; out.vn_nobs[env0 * od + i] = s_nobs[i]; }
+        }
+      } else if (obs_by_threads || out.vn_scratch != nullptr) {
         named_bar_sync(1, kTile);                                  // the tile's observation rows are complete
         const int rows = (int)((n - env0) < kTile ? (n - env0) : kTile);
         if (obs_by_threads)                                        // partial tile / unaligned output: coalesced copy
@@ -288,13 +422,13 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
       }
       fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the bulk stores
       __syncwarp();
-      if (lane == 0) mbar_arrive(&done[s]);
+      if (lane == 0) mbar_arrive(&done[vn_onepass ? (s + 1) % kStages : s]);
     }
   }
 
   // ---- epilogue: statistics, VecNormalize moments, device period counter ---------------------------------
   if (out.stats != nullptr) block_reduce_add<14, C::kConsumerWarps + 1>(acc, out.stats, red);
-  if (out.vn_scratch != nullptr) {
+  if (out.vn_scratch != nullptr && !vn_onepass) {
     // per-thread partials -> one atomic per block and column into scratch; the last block merges them into the
     // running statistics (in place: nothing reads them before the next kernel) and clears scratch
     __syncthreads();
@@ -317,7 +451,7 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
       atomicAdd(&out.vn_scratch[2 * od + 1], b);
     }
   }
-  if (out.ctl != nullptr) {
+  if (out.ctl != nullptr && !vn_barrier) {                       // (the grid barrier has advanced the period already)
     __syncthreads();
     if (tid == 0) *last_flag = last_block_ticket(out.ctl) ? 1 : 0;
     __syncthreads();

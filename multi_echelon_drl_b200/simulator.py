@@ -197,10 +197,13 @@ class BatchedSupplyNetwork:
         io.ep_return = self.ep_return.data_ptr()
         io.stats = self.stats.data_ptr() if self.track_stats else None
         if vecnorm is not None:
-            io.vn_scratch, io.vn_obs_rms = vecnorm["scratch"].data_ptr(), vecnorm["obs_rms"].data_ptr()
-            if vecnorm.get("returns") is not None:
-                io.vn_ret_rms, io.vn_returns = vecnorm["ret_rms"].data_ptr(), vecnorm["returns"].data_ptr()
-            io.vn_gamma = float(vecnorm["gamma"])
+            ptr = lambda k: None if vecnorm.get(k) is None else vecnorm[k].data_ptr()       # noqa: E731
+            io.vn_scratch, io.vn_obs_rms, io.vn_ret_rms = ptr("scratch"), ptr("obs_rms"), ptr("ret_rms")
+            io.vn_returns, io.vn_gamma = ptr("returns"), float(vecnorm["gamma"])
+            io.vn_nobs, io.vn_nrew = ptr("nobs"), ptr("nrew")       # one-kernel mode: normalised outputs of this launch
+            if vecnorm.get("nobs") is not None:
+                io.vn_clip_obs, io.vn_clip_reward = float(vecnorm["clip_obs"]), float(vecnorm["clip_reward"])
+                io.vn_epsilon = float(vecnorm["epsilon"])
         _lib.check(self.lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
                                        self._stream()))
 

@@ -228,15 +228,15 @@ class SupplyNetVecEnv(_VecEnvBase):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             sim.launch_step_device_period(self._act_buf, self._obs, sim.reward,
-                                          vecnorm=vn.fused_args() if (vn is not None and key[0]) else None)
-            if vn is not None and key[1]:
+                                          vecnorm=vn.fused_args(key) if (vn is not None and (key[0] or key[2])) else None)
+            if vn is not None and key[1] and not key[2]:
                 vn.graph_tail()
         self._graph, self._graph_key = g, key
 
     def _graph_step(self, actions):
-        """Non-terminal period through the captured graph.  key = (fuse the VecNormalize update, apply in graph)."""
+        """Non-terminal period through the captured graph.  key = VecNormalize.graph_key()."""
         sim, vn = self.sim, self._vn
-        key = vn.graph_key() if vn is not None else (False, False)
+        key = vn.graph_key() if vn is not None else (False, False, False)
         if not (isinstance(actions, torch.Tensor) and actions.data_ptr() == self._act_buf.data_ptr()):
             self._act_buf.copy_(sim._check_actions(actions))
         if self._graph is None or self._graph_key != key:

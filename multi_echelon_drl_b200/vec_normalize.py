@@ -47,7 +47,8 @@ class VecNormalize:
         self._ret_rms = self._fresh(1, f64)
         self.returns = torch.zeros(n, **f64)
         self._scratch = torch.zeros(2 * od + 2, **f64)
-        self._fused_scratch = torch.zeros(2 * od + 2, **f64)     # owned by the fused path: stays zero between launches
+        # owned by the fused paths (zero between launches; the one-kernel mode alternates between the two halves)
+        self._fused_scratch = torch.zeros(2 * (2 * od + 2), **f64)
         self.old_obs = torch.zeros((n, od), dtype=torch.float32, device=dev)
         self.old_reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._nobs = torch.zeros((n, od), dtype=torch.float32, device=dev)
@@ -101,16 +102,27 @@ class VecNormalize:
 
     # ------------------------------------------------------------------ joining the wrapped env's step graph
     def graph_key(self):
-        """(fuse the statistics update into the step kernel, normalise inside the graph).  Fusion needs what the
-        kernel supports: observations normalised (their moments come from the step's own tile), single-item
-        beer-game chain; anything else keeps the eager kernels after the replay."""
-        spec = self.venv.spec
-        can_fuse = self.norm_obs and not spec.is_tree and spec.n_items <= 1 and self.venv.sim.state_words == _lib.SN_STATE_WORDS
-        return (bool(self.training and can_fuse), bool(can_fuse or not self.training))
+        """(fuse the statistics update into the step kernel, normalise inside the graph, one-kernel mode).  Fusion
+        needs what the kernel supports: observations normalised (their moments come from the step's own tile),
+        single-item beer-game chain; anything else keeps the eager kernels after the replay.  One-kernel mode: at most
+        one 128-env tile per SM and 4-byte quantities - then the step launch normalises too (grid barrier between the
+        moments and the normalisation) and the graph is that single kernel."""
+        venv = self.venv
+        spec, sim = venv.spec, venv.sim
+        can_fuse = self.norm_obs and not spec.is_tree and spec.n_items <= 1 and sim.state_words == _lib.SN_STATE_WORDS
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        onepass = can_fuse and sim.dtype != "float64" and self.num_envs <= sms * 128 and not getattr(self, "no_onepass", False)
+        return (bool(self.training and can_fuse), bool(can_fuse or not self.training), bool(onepass))
 
-    def fused_args(self):
-        return dict(scratch=self._fused_scratch, obs_rms=self._obs_rms, ret_rms=self._ret_rms,
-                    returns=self.returns if self.norm_reward else None, gamma=self.gamma)
+    def fused_args(self, key=None):
+        update, _, onepass = key if key is not None else self.graph_key()
+        d = dict(obs_rms=self._obs_rms, ret_rms=self._ret_rms, gamma=self.gamma,
+                 scratch=self._fused_scratch if update else None,
+                 returns=self.returns if (update and self.norm_reward) else None)
+        if onepass:
+            d.update(nobs=self._nobs, nrew=self._nrew if self.norm_reward else None, clip_obs=self.clip_obs,
+                     clip_reward=self.clip_reward, epsilon=self.epsilon)
+        return d
 
     def graph_tail(self):
         """Captured right after the step launch: normalise the step's outputs with the (just updated) statistics."""

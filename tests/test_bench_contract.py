@@ -29,6 +29,17 @@ def test_reference_arm_emits_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e5          # a compiled port on any host does far more than the Python reference's ~5e3/s
+    # the reference's own Python loop beside it, when the reference (or its shipped copy baseline/_ref) is there
+    pr = cb["python_reference"]
+    if "unavailable" not in pr:
+        assert pr["kind"] == "reference" and pr["cores"] == (os.cpu_count() or 1)
+        assert 1e2 < pr["single_process_value"] < 1e5 and pr["value"] >= 0.5 * pr["single_process_value"]
+        assert d["value"] > 20 * pr["value"]
+
+
+def test_both_arms_name_the_same_workload():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"workload": WORKLOAD.format(') == 2      # GPU arm and reference arm share one string
 
 
 def test_reference_arm_other_ranks_are_silent():
