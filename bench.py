@@ -644,7 +644,23 @@ def config5_block(torch, world, rank, dev, steps, warmup):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     split = model.time_split()
-    flags = env.venv.sim.device_flags()
+    # device time of the env step alone: the env's captured graph (step + VecNormalize in one cooperative kernel)
+    # replayed back to back inside one episode; the in-loop figure above it includes the Python launch path
+    venv = env.venv
+    env.reset()
+    for _ in range(5):
+        env.step(venv.action_buffer)
+    reps = min(80, venv.sim.T - venv.sim.period - 2)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        venv._graph.replay()
+        venv.sim.advance_host_period()
+    e.record()
+    torch.cuda.synchronize()
+    env_step_graph_us = s.elapsed_time(e) / reps * 1e3
+    flags = venv.sim.device_flags()
     model.close()
     if world > 1:
         w = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -654,7 +670,7 @@ def config5_block(torch, world, rank, dev, steps, warmup):
             "ms_per_step": wall / steps * 1e3, "updates": steps,
             "time_split_s": {k: v for k, v in split.items() if k.endswith("_s")},
             "us_per_vector_step": {k[:-2]: round(v / steps * 1e6, 2) for k, v in split.items() if k.endswith("_s")},
-            "device_flags": flags,
+            "env_step_graph_gpu_us": round(env_step_graph_us, 2), "device_flags": flags,
             "workload": f"config5: TD3+HGE, {n} envs/GPU x {world}, batch 128, one 768-unit hidden layer, train_freq 32 / 32 "
                         "updates, device replay buffer; env step + VecNormalize = ONE replayed cooperative kernel (device "
                         "period counter), update and actor forward as CUDA graphs; one step = one vector step of all envs + "

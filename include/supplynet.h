@@ -184,7 +184,9 @@ int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
  *                 [11] sum of episode returns, [12] sum of squared episode returns;
  *                 [13] SN_I32 only: env-steps in which an action magnitude, order, inventory or backlog reached
  *                 2^SN_QTY_LIMIT_LOG2 (the reference computes with unbounded Python ints; beyond that bound int32
- *                 intermediates may wrap, so a non-zero count voids the bit-exactness claim for that run)
+ *                 intermediates may wrap, so a non-zero count voids the bit-exactness claim for that run); sn_rollout /
+ *                 sn_episode count envs instead of env-steps and do not watch distribution trees of up to four nodes
+ *                 (their rollout kernel has no register to spare: step such a network with sn_step to have it watched)
  * Returns SN_ERR_TERMINAL if period >= max_episode_steps. */
 int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period,
                 void* state, const void* actions, const void* demand_next,

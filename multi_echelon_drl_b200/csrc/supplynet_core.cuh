@@ -236,29 +236,33 @@ __device__ __forceinline__ void emit_obs(const E& e, const DevSpec<T>& sp, bool 
 // (never correct) an env-step whose action magnitude, order, inventory or backlog reached that bound: a sticky count
 // in stats[13] / bit 1 of ctl[2].  Floating-point paths have no such limit.
 constexpr int kQtyLimitLog2 = 26;
-// OR of the magnitudes to be watched after a step; ORDERS = also the raw actions and the orders placed (not needed
-// when both come from a clipped in-kernel policy).  The remaining words are bounded by these: pipelines hold
-// earlier orders, shipments are min(inventory, backlog), on-order sums have at most eight such terms.
-template <bool ORDERS, typename T, typename E>
-__device__ __forceinline__ uint32_t qty_mask(const E& e, const T (&a)[kF], const T (&q)[kF]) {
+// OR of the magnitudes to be watched: the raw actions and the orders placed (taken BEFORE the step, so that the
+// action registers can die there; not needed when both come from a clipped in-kernel policy) and, after the step, the
+// stocks and backlogs.  The remaining words are bounded by these: pipelines hold earlier orders, shipments are
+// min(inventory, backlog), on-order sums have at most eight such terms.
+template <typename T>
+__device__ __forceinline__ uint32_t qty_mask_orders(const T (&a)[kF], const T (&q)[kF]) {
+  if constexpr (std::is_same<T, int32_t>::value) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) m |= (uint32_t)q[k] | (uint32_t)(a[k] ^ (a[k] >> 31));
+    return m;
+  } else {
+    return 0u;
+  }
+}
+template <typename T, typename E>
+__device__ __forceinline__ uint32_t qty_mask_state(const E& e) {
   if constexpr (std::is_same<T, int32_t>::value) {
     uint32_t m = e.extra_qty_mask();
 #pragma unroll
-    for (int k = 0; k < kF; ++k) {
-      m |= (uint32_t)e.inv[k] | (uint32_t)e.B[k];
-      if (ORDERS) m |= (uint32_t)q[k] | (uint32_t)(a[k] ^ (a[k] >> 31));
-    }
+    for (int k = 0; k < kF; ++k) m |= (uint32_t)e.inv[k] | (uint32_t)e.B[k];
     return m;
   } else {
     return 0u;
   }
 }
 __device__ __forceinline__ bool qty_mask_over(uint32_t m) { return (m >> kQtyLimitLog2) != 0; }
-template <typename T, typename E>
-__device__ __forceinline__ bool qty_overflow(const E& e, const T (&a)[kF], const T (&q)[kF]) {
-  return qty_mask_over(qty_mask<true>(e, a, q));
-}
-
 struct StepOut {
   double reward;
   double hold[kF], back[kF];

@@ -64,28 +64,25 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 struct ObsStager {
   float* smem;     // this warp's staging area: [2][32*28] floats
   int lane;
-  int cur;         // staging buffer of the next store; toggled by every commit, so two consecutive stores of a
-                   // warp never share a buffer whatever the caller's step parity is
   __device__ __forceinline__ ObsStager(float* block_smem) {
     lane = threadIdx.x & 31;
-    cur = 0;
     smem = block_smem + (threadIdx.x >> 5) * (2 * 32 * 28);
   }
-  // Staging row of this lane in the current buffer.  At most one earlier bulk store (the one that used the
-  // other buffer) may still be reading shared memory.
-  __device__ __forceinline__ float* begin(int od) {
+  // Staging row of this lane in buffer `buf`.  `buf` must alternate 0/1 between consecutive stores of the same
+  // warp (at most one earlier bulk store, the one that used the other buffer, may still be reading shared memory);
+  // a caller that cannot guarantee the alternation drains first.
+  __device__ __forceinline__ float* begin(int od, int buf) {
     if (lane == 0) bulk_wait_read<1>();
     __syncwarp();
-    return smem + cur * (32 * 28) + lane * od;
+    return smem + buf * (32 * 28) + lane * od;
   }
-  __device__ __forceinline__ void commit(float* gdst_warp, int od) {
+  __device__ __forceinline__ void commit(float* gdst_warp, int od, int buf) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      bulk_store_s2g(gdst_warp, smem + cur * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
+      bulk_store_s2g(gdst_warp, smem + buf * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
       bulk_commit();
     }
-    cur ^= 1;
   }
   __device__ __forceinline__ void drain() {
     if (lane == 0) bulk_wait_read<0>();
@@ -98,12 +95,12 @@ struct ObsStager {
 template <bool IDENT, typename T, typename E>
 __device__ __forceinline__ void write_obs(ObsStager& st, const E& e, const DevSpec<T>& sp, bool terminal,
                                           float* __restrict__ gobs, int64_t env, int64_t n, int od, bool valid,
-                                          bool use_tma) {
+                                          int buf, bool use_tma) {
   const int64_t env0 = env - st.lane;
   if (use_tma && env0 + 32 <= n) {
-    float* row = st.begin(od);
+    float* row = st.begin(od, buf);
     emit_obs<IDENT>(e, sp, terminal, row);
-    st.commit(gobs + env0 * od, od);
+    st.commit(gobs + env0 * od, od, buf);
   } else if (valid) {
     emit_obs<IDENT>(e, sp, terminal, gobs + env * od);
   }
@@ -319,7 +316,7 @@ k_reset(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T* _
   }
   if (obs != nullptr) {
     ObsStager st(smem_f);
-    write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
     st.drain();
   }
 }
@@ -334,7 +331,7 @@ k_observe(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, const T*
   typename Ops::E e;
   if (valid) Ops::load(sp, state, ld, env, e);
   ObsStager st(smem_f);
-  write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
+  write_obs<IDENT>(st, e, sp, false, obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
   st.drain();
 }
 
@@ -416,9 +413,10 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int period_
     const typename Ops::D dn = Ops::load_demand(demand_next, ld, env, sp);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
+    const uint32_t om = qty_mask_orders(a, q);
     if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal, so);
     else Ops::template step<false>(e, sp, 0, q, dn, terminal, so);
-    over = qty_overflow(e, a, q);
+    over = qty_mask_over(om | qty_mask_state<T>(e));
     Ops::store(state, ld, env, e);
     if (out.reward) out.reward[env] = (float)so.reward;
     if (out.reward64) out.reward64[env] = so.reward;
@@ -437,7 +435,7 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int period_
   }
   if (out.obs != nullptr) {
     ObsStager st(smem_f);
-    write_obs<IDENT>(st, e, sp, terminal, out.obs, env, n, 7 * sp.n_obs, valid, use_tma != 0);
+    write_obs<IDENT>(st, e, sp, terminal, out.obs, env, n, 7 * sp.n_obs, valid, 0, use_tma != 0);
     st.drain();
   }
   if (over && out.ctl != nullptr) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_QTY_RANGE);
@@ -505,14 +503,14 @@ rollout_body(const DevSpec<T>& sp, const DevPolicy<T>& pol, int64_t n, int64_t l
   if (init != nullptr) {
     // episode mode (sn_episode): reset in-kernel, the state never has to exist in HBM
     Ops::reset(e, sp, init, ld, envc, Ops::load_demand(demand, ld, envc, sp));
-    if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, use_tma != 0);
+    if (obs0 != nullptr) write_obs<IDENT>(st, e, sp, false, obs0, env, n, od, valid, 1, use_tma != 0);
   } else {
     Ops::load(sp, state, ld, envc, e);
   }
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
-  uint32_t qmask = 0;                               // range guard of the integer path (supplynet_core.cuh: qty_mask)
+  bool qover = false;                               // range guard of the integer path (supplynet_core.cuh); a predicate, not a register
   const int item = MULTI ? chain_item(sp, envc) : 0;
 
   // software pipeline: inputs of step s+1 are requested before step s is computed
@@ -543,20 +541,28 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     if (out.traj_actions != nullptr && valid) store_actions_f32<IDENT>(out.traj_actions + (int64_t)s * act_stride, env, sp, a);
     T q[kF];
     env_orders<IDENT>(e, sp, a, q);
+    // (not in the tree rollouts: their register budget is spent, the guard's few registers cost them 45 % in
+    // spills; sn_step guards every topology)
+    if (POLICY == SN_POLICY_ACTIONS && !Ops::kWide) qover |= qty_mask_over(qty_mask_orders(a, q));
     StepOut so;
     Ops::template step<MULTI>(e, sp, item, q, dn, terminal, so);
-    qmask |= qty_mask<POLICY == SN_POLICY_ACTIONS>(e, a, q);
+    if (!Ops::kWide) qover |= qty_mask_over(qty_mask_state<T>(e));
     acc[0] += 1.0;
     acc[1] += so.reward;
 #pragma unroll
     for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
     if (out.traj_reward != nullptr && valid) out.traj_reward[(int64_t)s * n + env] = (float)so.reward;
     if (out.traj_obs != nullptr)
-      write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, use_tma != 0);
+      write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, s & 1, use_tma != 0);
   }
 
   const bool ended = (period0 + n_steps >= sp.t_max);
-  if (out.obs != nullptr) write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, use_tma != 0);
+  if (out.obs != nullptr) {
+    // without a trajectory nothing has alternated the staging buffers since the obs0 store (buffer 1): with an odd
+    // n_steps this store would reuse that buffer while the bulk copy may still be reading it
+    if (out.traj_obs == nullptr) st.drain();
+    write_obs<IDENT>(st, e, sp, ended, out.obs, env, n, od, valid, n_steps & 1, use_tma != 0);
+  }
   st.drain();
   double ep_total = acc[1];                 // return of the whole episode, if this launch can know it
   if (valid) {
@@ -575,7 +581,7 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     v[10] = ep ? 1.0 : 0.0;
     v[11] = ep ? ep_total : 0.0;
     v[12] = ep ? ep_total * ep_total : 0.0;
-    v[13] = (valid && qty_mask_over(qmask)) ? 1.0 : 0.0;       // envs (not env-steps) that left the exact int32 range
+    v[13] = (valid && qover) ? 1.0 : 0.0;                      // envs (not env-steps) that left the exact int32 range
     block_reduce_add<14, kRolloutBlock / 32>(v, out.stats, red);
   }
 }

@@ -272,9 +272,10 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         const typename Ops::D dn = Ops::load_demand_smem(s_dem, kTile, tid, sp);
         T q[kF];
         env_orders<IDENT>(e, sp, a, q);
+        const uint32_t om = qty_mask_orders(a, q);
         if (sp.n_items > 1) Ops::template step<true>(e, sp, chain_item(sp, env), q, dn, terminal, so);
         else Ops::template step<false>(e, sp, 0, q, dn, terminal, so);
-        over = qty_overflow(e, a, q);
+        over = qty_mask_over(om | qty_mask_state<T>(e));
         Ops::store(s_state, kTile, tid, e);
         const float rf = (float)so.reward;
         if (out.reward != nullptr) { if (full_tile) s_rew[tid] = rf; else out.reward[env] = rf; }

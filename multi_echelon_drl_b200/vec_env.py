@@ -237,7 +237,7 @@ class SupplyNetVecEnv(_VecEnvBase):
         """Non-terminal period through the captured graph.  key = VecNormalize.graph_key()."""
         sim, vn = self.sim, self._vn
         key = vn.graph_key() if vn is not None else (False, False, False)
-        if not (isinstance(actions, torch.Tensor) and actions.data_ptr() == self._act_buf.data_ptr()):
+        if actions is not self._act_buf and not (isinstance(actions, torch.Tensor) and actions.data_ptr() == self._act_buf.data_ptr()):
             self._act_buf.copy_(sim._check_actions(actions))
         if self._graph is None or self._graph_key != key:
             self._capture(key)

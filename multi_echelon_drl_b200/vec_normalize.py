@@ -107,12 +107,18 @@ class VecNormalize:
         single-item beer-game chain; anything else keeps the eager kernels after the replay.  One-kernel mode: at most
         one 128-env tile per SM and 4-byte quantities - then the step launch normalises too (grid barrier between the
         moments and the normalisation) and the graph is that single kernel."""
+        tag = (self.training, self.norm_obs, self.norm_reward, getattr(self, "no_onepass", False))
+        cached = getattr(self, "_key_cache", None)
+        if cached is not None and cached[0] == tag:          # called once per step: keep it to a tuple compare
+            return cached[1]
         venv = self.venv
         spec, sim = venv.spec, venv.sim
         can_fuse = self.norm_obs and not spec.is_tree and spec.n_items <= 1 and sim.state_words == _lib.SN_STATE_WORDS
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        onepass = can_fuse and sim.dtype != "float64" and self.num_envs <= sms * 128 and not getattr(self, "no_onepass", False)
-        return (bool(self.training and can_fuse), bool(can_fuse or not self.training), bool(onepass))
+        onepass = can_fuse and sim.dtype != "float64" and self.num_envs <= sms * 128 and not tag[3]
+        key = (bool(self.training and can_fuse), bool(can_fuse or not self.training), bool(onepass))
+        self._key_cache = (tag, key)
+        return key
 
     def fused_args(self, key=None):
         update, _, onepass = key if key is not None else self.graph_key()
@@ -182,6 +188,17 @@ class VecNormalize:
         self._obs_rms.copy_(keep)
 
     def step(self, actions):
+        venv = self.venv
+        if getattr(venv, "use_graph", False) and venv._graph is not None and actions is venv._act_buf:
+            # fast path of the replayed graph (the general path below does the same with more Python in between)
+            sim = venv.sim
+            if not sim.terminal and sim.period + 1 < sim.T and venv._graph_key[1] and venv._graph_key == self.graph_key():
+                venv._graph.replay()
+                sim.period += 1
+                venv.last_step_graphed = True
+                self.old_obs, self.old_reward = venv._obs, sim.reward
+                return ((self._nobs if self.norm_obs else venv._obs), (self._nrew if self.norm_reward else sim.reward),
+                        venv._all_false, venv._no_infos)
         self.step_async(actions)
         return self.step_wait()
 
