@@ -57,10 +57,13 @@ def main(argv=None):
         targets, demand_type, (lb, ub), offset = [19, 20, 20, 14], "Uniform", (0, 16), -8
     if p.get("hge_rate_at_start", 0) > 0 and args.role != "MultiFacility":
         raise NotImplementedError("For now the TD3 with HGE only supports centralized setting")    # train_td3.py:65-66
-    env_name = f"BeerGame{demand_type}{args.role}{'FullInfo' * bool(args.global_info)}-v0"
+    # the centralized ids exist as ...MultiFacilityFullInfo-v0 only (register_envs.py:74-110; the reference's docs always
+    # pass -g 1 there): -g is implied for MultiFacility, so the flag-less default is a registered id
+    full = bool(args.global_info) or args.role == "MultiFacility"
+    env_name = f"BeerGame{demand_type}{args.role}{'FullInfo' * full}-v0"
     bsp = BaseStockPolicy(targets, {"on_hand": 0, "unreceived_pipeline": [3, 4, 5, 6], "unfilled_demand": 1,
                                     "latest_demand": 2}, 7, lb, ub, args.ordering_rule)
-    env = make(env_name, n_envs=args.n_envs, dtype="float32", seed=1000 * rank)
+    env = make(env_name, n_envs=args.n_envs, dtype="float32", seed=1000 * rank, use_graph=True)
     if args.ordering_rule == "d+a":
         env = wrap_action_d_plus_a(env, offset=-(ub - lb) / 2, lb=lb, ub=ub)  # train_td3.py:86-91
     env = VecNormalize(env, clip_obs=100.0, clip_reward=1000.0)

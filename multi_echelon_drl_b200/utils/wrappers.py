@@ -19,4 +19,6 @@ def wrap_action_d_plus_a(env, offset=-8, lb: int = 0, ub: int = 16):
     _lib.check(sim.lib.sn_spec_validate(C.byref(c_spec), sim.dtype_code))
     base.spec = spec
     sim.spec, sim._c_spec = spec, c_spec
+    if getattr(base, "_graph", None) is not None:      # a step graph captured before the switch has the old rule baked in
+        base._graph = None
     return env

@@ -39,10 +39,15 @@ def test_step_matches_reference_golden(case):
     T = case["actions"].shape[0]
     cost = torch.zeros((8, sim.ld), dtype=torch.float64, device="cuda")
     r64 = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    # float cases: BASELINE.json's tolerance, 1e-6 relative - to the scale of the trajectory (max |obs|, max |reward|),
+    # the only meaningful reference for a state in which 0.0 is a legitimate value.  The reference itself computes
+    # these rollouts in float32 scalars (numpy >= 2); measured worst case over the 24 float goldens on a B200:
+    # 4.5e-7 (obs), 6.9e-7 (reward) - profiles/float_error_probe.py
+    oscale, rscale = max(1.0, float(np.abs(case["obs"]).max())), max(1.0, float(np.abs(case["rew"]).max()))
     if is_int:
         assert np.array_equal(obs0[0], case["obs0"])
     else:
-        np.testing.assert_allclose(obs0[0], case["obs0"], rtol=1e-6, atol=2e-4)
+        assert np.abs(obs0[0] - case["obs0"]).max() <= 1e-6 * oscale
     for t in range(T):
         obs, rew, done = sim.step(torch.as_tensor(case["actions"][t][None]), reward64_out=r64, cost_out=cost)
         o, r, c = obs.cpu().numpy()[0], r64.item(), cost[:, 0].cpu().numpy()
@@ -51,10 +56,9 @@ def test_step_matches_reference_golden(case):
             assert r == case["rew"][t], t
             assert np.array_equal(c[:4], case["holding"][t]) and np.array_equal(c[4:], case["backorder"][t]), t
             assert rew.item() == np.float32(case["rew"][t])
-        else:           # float32 arithmetic vs the reference's mixed float32/python arithmetic:
-            # 1e-6 relative to the state scale (quantities reach a few hundred => atol 2e-4 * scale-ish)
-            np.testing.assert_allclose(o, case["obs"][t], rtol=1e-6, atol=5e-4)
-            np.testing.assert_allclose(r, case["rew"][t], rtol=1e-6, atol=5e-3)
+        else:           # float32 arithmetic vs the reference's mixed float32/python arithmetic
+            assert np.abs(o.astype(np.float64) - case["obs"][t]).max() <= 1e-6 * oscale, t
+            assert abs(r - case["rew"][t]) <= 1e-6 * rscale, t
         assert done == bool(case["done"][t])
     with pytest.raises(ValueError):
         sim.step(torch.as_tensor(case["actions"][0][None]))            # envs.py:88-89
@@ -185,22 +189,24 @@ def test_heuristic_kernel_vs_reference_golden():
 
 
 def test_float_paths_vs_oracle():
-    """Fractional (TD3-like) orders: f32 and f64 kernels vs the float64 oracle.
-    f64: 1e-9 relative (same arithmetic up to aggregation order); f32: 1e-6 of the state scale."""
+    """Fractional (TD3-like) orders: f32 and f64 kernels vs the float64 oracle, BASELINE.json's 1e-6 relative (to the
+    scale of the trajectory).  f64: the float32 outputs are the correctly rounded oracle values (1e-7 covers the
+    rounding of the output itself; measured 0 / 4.6e-8); f32: 1e-6 (measured 4.7e-7 obs, 3.1e-7 reward after 100
+    compounding periods, profiles/float_error_probe.py)."""
     n, T = 1500, 100
     init, demand = _seeded_batch("uniform", n, T, 9)
     acts = (np.random.RandomState(2).rand(T, n, 4) * 16).astype(np.float32)
     ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init, demand, acts.astype(np.float64), dtype=np.float64)
     scale = max(1.0, np.abs(ref["obs"]).max())
-    for dt, tol in (("float64", 1e-9), ("float32", 1e-6)):
+    for dt, tol in (("float64", 1e-7), ("float32", 1e-6)):
         sim = _make("uniform", (0, 1, 2, 3), True, "a", T, n, dt)
         sim.load_episode(init, demand)
         sim.reset()
         out = sim.rollout(T, actions=torch.as_tensor(acts), record_obs=True, record_reward=True)
         err = np.abs(out["traj_obs"].cpu().numpy().astype(np.float64) - ref["obs"]).max()
-        assert err <= max(tol, 1.2e-7) * scale * 8, (dt, err, scale)     # obs itself is rounded to f32
+        assert err <= tol * scale, (dt, err, scale)
         rerr = np.abs(out["traj_reward"].cpu().numpy() - ref["rew"]).max()
-        assert rerr <= max(tol, 1.2e-7) * np.abs(ref["rew"]).max() * 8, (dt, rerr)
+        assert rerr <= tol * np.abs(ref["rew"]).max(), (dt, rerr)
 
 
 def test_full_size_config2_properties():
@@ -234,6 +240,15 @@ def test_full_size_config2_properties():
     ref = oracle_rollout("uniform", (0, 1, 2, 3), True, "a", T, init[:m], demand[:m], acts[:, :m])
     assert np.array_equal(out["traj_obs"][:, :m].cpu().numpy(), ref["obs"])
     assert np.array_equal(ret_fused[:m].cpu().numpy(), ref["rew"].sum(0))
+    # (iv) ALL 65,536 envs x 100 periods against the C restatement of the reference (itself pinned to the goldens and
+    # to the numpy restatement by tests/test_oracle_c.py): observations, rewards, episode returns, bit-exact
+    import os
+    from oracle import beergame_c as OC
+    from oracle import beergame_np as O
+    full = OC.rollout(O.scenario_spec("uniform", (0, 1, 2, 3), True, T), init, demand, acts, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(out["traj_obs"].cpu().numpy(), full["obs"])
+    assert np.array_equal(out["traj_reward"].cpu().numpy(), full["rew"].astype(np.float32))
+    assert np.array_equal(ret_fused.cpu().numpy(), full["rew"].sum(0))
 
 
 @pytest.mark.parametrize("scenario,agents,glob,rule", [
@@ -446,5 +461,5 @@ def test_config5_shape_float_actions_vs_oracle():
     scale = max(1.0, float(np.abs(ref["obs"]).max()))
     for t in range(T):
         obs, rew, _ = sim.step(torch.as_tensor(acts[t]))
-        assert np.abs(obs.cpu().numpy() - ref["obs"][t]).max() <= 1e-6 * scale * 8, t
-    assert np.abs(sim.ep_return.cpu().numpy() - ref["rew"].sum(0)).max() <= 1e-6 * np.abs(ref["rew"].sum(0)).max() * 8
+        assert np.abs(obs.cpu().numpy() - ref["obs"][t]).max() <= 1e-6 * scale, t
+    assert np.abs(sim.ep_return.cpu().numpy() - ref["rew"].sum(0)).max() <= 1e-6 * np.abs(ref["rew"].sum(0)).max()

@@ -61,6 +61,36 @@ def test_td3_learns_to_beat_random_on_basic_retailer():
     assert best_late > 0.6 * first, (first, model.episode_returns)
 
 
+def test_td3_hge_centralized_learns_to_the_heuristics_level():
+    """BASELINE config 5 (centralized complex scenario, 4,096 envs, TD3 with heuristic-guided exploration whose rate
+    decays linearly like HgeRateCallback, utils/callbacks.py:5-23; step + VecNormalize as one replayed kernel): 40
+    episodes with batch 1,024 and 4 updates per vector step bring the deterministic policy from the uniform-random
+    level (about -16,900 per episode) to the level of the base-stock heuristic that guided it (-1,337; measured
+    -1,027 +- 248, profiles/r2_td3_learning.json).  Thresholds leave a wide margin for seed / atomics noise."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
+    from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    n, episodes = 4096, 40
+    env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0, use_graph=True),
+                       clip_obs=100.0, clip_reward=1000.0)
+    total = n * 100 * episodes
+    cfg = TD3Config(batch_size=1024, net_arch=(768,), learning_rate=1e-3, tau=0.01, train_freq=32, gradient_steps=128,
+                    action_noise_std=0.3, gamma=0.95, hge_rate_at_start=0.5, hge_decay_periods=total // 200,
+                    learning_starts=n * 100, seed=0)
+    model = HgeTD3(env, BaseStockPolicy([19, 20, 20, 14]), cfg)
+    model.learn(total)
+    assert env.venv.sim.device_flags() == 0
+    assert model.hge_rate == 0.0                                  # decayed to zero half-way through the run
+    first, late = model.episode_returns[0], float(np.mean(model.episode_returns[-5:]))
+    assert first < -12000 and late > -3000, model.episode_returns  # training episodes (with exploration noise)
+    eval_env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=123),
+                            clip_obs=100.0, clip_reward=1000.0)
+    mean, std, cnt = model.evaluate(eval_env, n_episodes=1)
+    assert cnt == n and mean > -2000, (mean, std)                 # heuristic: -1,337; uniform random: -16,858
+    model.close()
+
+
 def test_evaluate_and_checkpoint_roundtrip(tmp_path):
     """EvalCallback-style deterministic evaluation on a frozen, statistics-synchronised VecNormalize, and the
     best-model + env-statistics checkpoint (SaveEnvStatsCallback)."""

@@ -47,8 +47,13 @@ def test_vecnormalize_matches_numpy_restatement(tmp_path):
                                    rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(nrew.cpu().numpy(), np.clip(r / np.sqrt(ret_rms.var + eps), -1000, 1000), rtol=1e-5, atol=1e-6)
         if dones.all():
+            # SB3's VecNormalize.step_wait normalises infos[i]["terminal_observation"] with the statistics as they
+            # are AFTER this step's update (the update itself saw the reset observation, not the terminal one)
             tr = infos.terminal_observation.cpu().numpy()
-            assert np.abs(tr).max() <= 100.0 and np.isfinite(tr).all()
+            raw_term = env.venv._term_obs.cpu().numpy().astype(np.float64)
+            np.testing.assert_allclose(tr, np.clip((raw_term - obs_rms.mean) / np.sqrt(obs_rms.var + eps), -100, 100),
+                                       rtol=1e-5, atol=1e-5)
+            assert np.abs(raw_term - raw).max() > 0          # it really is another observation than the returned one
             ret[:] = 0
         np.testing.assert_allclose(env.returns.cpu().numpy(), ret, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(env.obs_rms["mean"].cpu().numpy(), obs_rms.mean, rtol=1e-9, atol=1e-9)
