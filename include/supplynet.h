@@ -318,6 +318,16 @@ int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, in
 int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
                               uint64_t offset, void* stream);
 
+/* ---- episode tables: row-major per-env arrays -> the structure-of-arrays rows the kernels read ----------------
+ * What the reference's reset leaves per env (initial inventories / pipelines, network_components.py:138-168,
+ * 293-319; the demand stream, utils/demands.py:37-67) arrives as [n_envs][width] arrays (any of the four source
+ * types, src_stride elements between envs).  sn_pack_rows transposes and converts them into `rows` rows of `ld`
+ * elements (dst_row_stride apart; demand tables of trees interleave the sources, hence the stride), zero-filling
+ * the padding columns n_envs..ld-1 and the rows width..rows-1.  One launch per table. */
+enum { SN_SRC_I32 = 0, SN_SRC_I64 = 1, SN_SRC_F32 = 2, SN_SRC_F64 = 3 };
+int32_t sn_pack_rows(int32_t src_dtype, const void* src, int64_t n_envs, int32_t width, int64_t src_stride, int32_t dtype,
+                     void* dst, int32_t rows, int64_t ld, int64_t dst_row_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

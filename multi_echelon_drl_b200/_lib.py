@@ -21,6 +21,7 @@ ABI_VERSION = 8
 SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS, SN_CTL_BARRIER, SN_CTL_SEQ = 8, 0, 1, 2, 3, 4
 SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
 SN_QTY_LIMIT_LOG2 = 26
+SN_SRC_I32, SN_SRC_I64, SN_SRC_F32, SN_SRC_F64 = 0, 1, 2, 3
 
 
 MAXF = 8            # SN_MAX_FACILITIES: size of the per-facility arrays (chains use the first four)
@@ -99,6 +100,7 @@ SIGNATURES = {
     "sn_vecnorm_apply": (_I32, [_I64, _I32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_double, _I32, _P, _P]),
     "sn_fill_uniform": (_I32, [_I32, _P, _I64, _I32, _I32, C.c_uint64, C.c_uint64, _P]),
     "sn_fill_normal_demand": (_I32, [_I32, _P, _I64, C.c_double, C.c_double, C.c_uint64, C.c_uint64, _P]),
+    "sn_pack_rows": (_I32, [_I32, _P, _I64, _I32, _I64, _I32, _P, _I32, _I64, _I64, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -69,6 +69,32 @@ k_fill_normal_demand(T* __restrict__ dst, int64_t count, float mean, float sd, u
     if (i + j < count) dst[i + j] = (T)rintf(fmaxf(mean + sd * z[j], 0.0f));
 }
 
+// Row-major per-env table [n][width] (what the reference's reset produces per env: init values, demand stream) ->
+// structure-of-arrays rows [rows >= width][ld] of the quantity type, converting on the way: 32 x 32 tiles through
+// shared memory, both sides coalesced.  Columns n..ld-1 (row padding) and rows width..rows-1 are zero-filled.
+template <typename S, typename T>
+__global__ void __launch_bounds__(256)
+k_pack_rows(const S* __restrict__ src, int64_t n, int width, int64_t src_stride, T* __restrict__ dst, int rows, int64_t ld,
+            int64_t dst_row_stride) {
+  __shared__ T tile[32][33];
+  const int64_t env0 = (int64_t)blockIdx.x * 32;
+  const int w0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t e = env0 + ty + 8 * i;
+    const int w = w0 + tx;
+    tile[ty + 8 * i][tx] = (e < n && w < width) ? (T)src[e * src_stride + w] : T(0);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int w = w0 + ty + 8 * i;
+    const int64_t e = env0 + tx;
+    if (w < rows && e < ld) dst[(int64_t)w * dst_row_stride + e] = tile[tx][ty + 8 * i];
+  }
+}
+
 }  // namespace snr
 
 extern "C" {
@@ -103,6 +129,34 @@ int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double me
     default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
   }
   return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
+}
+
+int32_t sn_pack_rows(int32_t src_dtype, const void* src, int64_t n_envs, int32_t width, int64_t src_stride, int32_t dtype,
+                     void* dst, int32_t rows, int64_t ld, int64_t dst_row_stride, void* stream) {
+  using sn_detail::fail;
+  if (!src || !dst) return fail(SN_ERR_INVALID, "sn_pack_rows: NULL argument");
+  if (n_envs < 1 || width < 1 || rows < width || ld < n_envs || src_stride < width || dst_row_stride < ld)
+    return fail(SN_ERR_INVALID, "sn_pack_rows: n_envs=%lld width=%d rows=%d ld=%lld", (long long)n_envs, width, rows, (long long)ld);
+  const dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((rows + 31) / 32));
+  cudaStream_t st = (cudaStream_t)stream;
+#define SN_PACK(S, T) snr::k_pack_rows<S, T><<<grid, 256, 0, st>>>((const S*)src, n_envs, width, src_stride, (T*)dst, rows, ld, dst_row_stride)
+#define SN_PACK_TO(S)                                                             \
+  switch (dtype) {                                                               \
+    case SN_I32: SN_PACK(S, int32_t); break;                                     \
+    case SN_F32: SN_PACK(S, float); break;                                       \
+    case SN_F64: SN_PACK(S, double); break;                                      \
+    default: return fail(SN_ERR_INVALID, "sn_pack_rows: unknown dtype %d", dtype); \
+  }
+  switch (src_dtype) {
+    case SN_SRC_I32: SN_PACK_TO(int32_t); break;
+    case SN_SRC_I64: SN_PACK_TO(int64_t); break;
+    case SN_SRC_F32: SN_PACK_TO(float); break;
+    case SN_SRC_F64: SN_PACK_TO(double); break;
+    default: return fail(SN_ERR_INVALID, "sn_pack_rows: unknown source dtype %d", src_dtype);
+  }
+#undef SN_PACK_TO
+#undef SN_PACK
+  return cudaGetLastError() == cudaSuccess ? SN_OK : fail(SN_ERR_CUDA, "sn_pack_rows: kernel launch failed");
 }
 
 }  // extern "C"

@@ -92,39 +92,47 @@ class BatchedSupplyNetwork:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _to_rows(self, x, width) -> torch.Tensor:
-        """[n, width] host/device array -> [width, ld] device tensor of the quantity dtype."""
+    _SRC = {torch.int32: _lib.SN_SRC_I32, torch.int64: _lib.SN_SRC_I64, torch.float32: _lib.SN_SRC_F32,
+            torch.float64: _lib.SN_SRC_F64}
+
+    def _pack_rows(self, x, width, dst: torch.Tensor, rows: int, row_stride: int):
+        """[n, width] host/device array -> `rows` structure-of-arrays rows of `dst` (sn_pack_rows: transpose, dtype
+        conversion and zero padding in one launch; the host->device copy before it is the only other step)."""
         t = torch.as_tensor(x)
         if t.dim() != 2 or t.shape[0] != self.n_envs or t.shape[1] != width:
             raise ValueError(f"expected shape ({self.n_envs}, {width}), got {tuple(t.shape)}")
         if self.dtype_code == _lib.SN_I32 and t.is_floating_point():
             if not bool((t == t.round()).all()):
                 raise TypeError("integer simulator (dtype='int32') needs integral quantities")
-        t = t.to(device=self.device, dtype=self.tdtype, non_blocking=True)
-        out = torch.zeros((width, self.ld), dtype=self.tdtype, device=self.device)
-        out[:, : self.n_envs] = t.t()
-        return out
+        if t.dtype not in self._SRC:
+            t = t.to(torch.float64 if t.is_floating_point() else torch.int64)
+        if t.stride(1) != 1:
+            t = t.contiguous()
+        t = t.to(device=self.device, non_blocking=True)
+        _lib.check(self.lib.sn_pack_rows(self._SRC[t.dtype], C.c_void_p(t.data_ptr()), self.n_envs, width, t.stride(0),
+                                         self.dtype_code, C.c_void_p(dst.data_ptr()), rows, self.ld, row_stride,
+                                         self._stream()))
+        return t            # keeps the staging tensor alive until the caller returns (the launch is asynchronous)
 
     # ------------------------------------------------------------------ episode inputs
     def load_episode(self, init, demand):
         """init [n, init_words] (19: inv[4]; so[k][j]; sh[k][j] packed for the beer game's lead times; 36:
         inv[4]; so[k][0..3]; sh[k][0..3] for other lead times), demand [n, >=T+1] (utils/demands.py streams)."""
         d = torch.as_tensor(demand)
+        rows = self.T + 3
         if self.spec.is_tree:            # demand [n, n_sources, >=T+1]: one stream per demand source, node order
             if d.dim() != 3 or d.shape[1] != self.n_sources or d.shape[2] < self.T + 1:
                 raise ValueError(f"demand must be [n_envs, {self.n_sources}, >= {self.T + 1}]")
-            width = min(d.shape[2], self.T + 3)
-            self.init.copy_(self._to_rows(init, self.init_words))
-            self.demand.zero_()
+            width = min(d.shape[2], rows)
+            keep = [self._pack_rows(init, self.init_words, self.init, self.init_words, self.ld)]
             for s in range(self.n_sources):
-                self.demand[:width, s].copy_(self._to_rows(d[:, s, :width], width))
+                keep.append(self._pack_rows(d[:, s, :width], width, self.demand[0, s], rows, self.n_sources * self.ld))
             return
         if d.dim() != 2 or d.shape[1] < self.T + 1:
             raise ValueError(f"demand must be [n_envs, >= {self.T + 1}]")
-        width = min(d.shape[1], self.T + 3)
-        self.init.copy_(self._to_rows(init, self.init_words))
-        self.demand.zero_()
-        self.demand[:width].copy_(self._to_rows(d[:, :width], width))
+        width = min(d.shape[1], rows)
+        keep = [self._pack_rows(init, self.init_words, self.init, self.init_words, self.ld),       # noqa: F841
+                self._pack_rows(d[:, :width], width, self.demand, rows, self.ld)]
 
     # ------------------------------------------------------------------ env API
     def reset(self, obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -116,6 +116,7 @@ class SupplyNetVecEnv(_VecEnvBase):
         self._last_returns = torch.zeros((n,), dtype=torch.float64, device=self.device)
         if output == "numpy":
             self._h_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype).pin_memory()
+            self._h_act_np = self._h_act.numpy()
             self._d_act = torch.zeros((n, spec.n_agents), dtype=self.sim.tdtype, device=self.device)
             # Results are handed out as views of pinned staging buffers, rotated over kRing sets: an array returned
             # by step()/reset() stays untouched for the next kRing-1 calls (SB3 keeps `_last_obs` across one
@@ -256,9 +257,11 @@ class SupplyNetVecEnv(_VecEnvBase):
             a = np.asarray(actions)
             if a.ndim == 1:
                 a = a[:, None]
+            if a.shape != self._h_act_np.shape:
+                raise ValueError(f"actions must have shape {self._h_act_np.shape}, got {a.shape}")
             if sim.dtype_code == _lib.SN_I32 and a.dtype.kind == "f" and not np.array_equal(a, np.round(a)):
                 raise TypeError("integer simulator (dtype='int32') needs integral order quantities")
-            self._h_act.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(self._h_act.dtype))
+            np.copyto(self._h_act_np, a, casting="unsafe")      # one pass: dtype conversion straight into pinned memory
             self._d_act.copy_(self._h_act, non_blocking=True)
             actions = self._d_act
         elif isinstance(actions, torch.Tensor) and actions.dim() == 1:
