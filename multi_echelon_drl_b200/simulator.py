@@ -109,7 +109,8 @@ class BatchedSupplyNetwork:
         if t.stride(1) != 1:
             t = t.contiguous()
         t = t.to(device=self.device, non_blocking=True)
-        _lib.check(self.lib.sn_pack_rows(self._SRC[t.dtype], C.c_void_p(t.data_ptr()), self.n_envs, width, t.stride(0),
+        src_stride = t.stride(0) if self.n_envs > 1 else width       # (the stride of a size-1 dimension is arbitrary)
+        _lib.check(self.lib.sn_pack_rows(self._SRC[t.dtype], C.c_void_p(t.data_ptr()), self.n_envs, width, src_stride,
                                          self.dtype_code, C.c_void_p(dst.data_ptr()), rows, self.ld, row_stride,
                                          self._stream()))
         return t            # keeps the staging tensor alive until the caller returns (the launch is asynchronous)

@@ -70,6 +70,33 @@ def test_numpy_output_mode_and_decentralized_roles():
     assert np.allclose(infos.episode_return, ref["rew"].sum(0))
 
 
+def test_numpy_outputs_survive_the_next_steps():
+    """SB3 algorithms keep `self._last_obs = new_obs` across env.step() (DummyVecEnv hands out fresh arrays): what a
+    step returned must not change under the caller when the env steps again.  The staging buffers rotate over
+    kRing = 3 sets, so an array stays intact for the next two calls; wrong-shaped and fractional-for-int32 numpy
+    actions are rejected like torch ones."""
+    from multi_echelon_drl_b200 import register_envs as R
+    n = 257
+    env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="int32", seed=3, output="numpy")
+    rs = np.random.RandomState(0)
+    prev = env.reset()
+    keep = prev.copy()
+    history = []
+    for t in range(6):
+        obs, rew, dones, infos = env.step(rs.randint(0, 17, (n, 4)))
+        assert np.array_equal(prev, keep), t            # the previous observation is untouched by this step
+        assert not np.shares_memory(obs, prev)
+        history.append((obs, obs.copy(), rew, rew.copy(), dones, dones.copy()))
+        if len(history) >= 2:                           # ... and still is one step later
+            o, oc, r, rc, d, dc = history[-2]
+            assert np.array_equal(o, oc) and np.array_equal(r, rc) and np.array_equal(d, dc)
+        prev, keep = obs, obs.copy()
+    with pytest.raises(ValueError):
+        env.step(np.zeros((n, 3)))
+    with pytest.raises(TypeError):
+        env.step(np.full((n, 4), 0.5))
+
+
 def test_dplusa_registry_id_and_wrapper():
     """BeerGameUniformMultiFacilityDPlusA-v0 = wrap_action_d_plus_a(env, -8, 0, 16) (register_envs.py:8-15)."""
     from multi_echelon_drl_b200 import register_envs as R
