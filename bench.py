@@ -559,12 +559,22 @@ def single_step_numbers(torch, dev, peak):
                      ("hub", "r1", 2, 2), ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)],
                     ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"], True)
     others = {"rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
-              "rollout_distribution_tree_65536": tree, "rollout_tree_8_nodes_65536": big}
+              "rollout_distribution_tree_65536": tree, "rollout_distribution_tree_65536_specialised": tree,
+              "rollout_tree_8_nodes_65536": big}
     t_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+    from multi_echelon_drl_b200 import specialize
     for key, sp in others.items():
         acts = torch.randint(0, 17, (T, n, sp.n_agents), generator=g, device=dev, dtype=torch.int32)
         t_obs = torch.empty((T, n, sp.obs_dim), dtype=torch.float32, device=dev)
+        # the general tree kernels take the topology at run time; a library compiled for this very network
+        # (multi_echelon_drl_b200/specialize.py, prebuilt by __graft_entry__.build()) is measured beside them
+        os.environ["SN_NO_SPECIALIZED"] = "0" if key.endswith("_specialised") else "1"
+        specialize._loaded.clear()
         sim = BatchedSupplyNetwork(sp, n, dev, "int32")
+        os.environ.pop("SN_NO_SPECIALIZED", None)
+        if key.endswith("_specialised") and sim.fast is None:
+            out[key] = {"unavailable": "no specialised library for this network has been built"}
+            continue
         sim.load_episode(*bulk_episode_inputs(sp, n, np.random.RandomState(0)))
         for _ in range(3):
             sim.episode(T, actions=acts, traj_obs=t_obs, traj_reward=t_rew, write_state=False)
@@ -578,9 +588,12 @@ def single_step_numbers(torch, dev, peak):
         ms = s.elapsed_time(e) / 10
         nbytes = n * T * (4 * sp.n_agents + 4 * sp.n_sources + 4 * sp.obs_dim + 4)
         out[key] = {"env_steps_per_s": n * T / (ms * 1e-3), "kernel_ms": ms, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
-                    "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "bound": "instruction issue (run-time topology / lead times as 0/1 multipliers)",
+                    "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                    "bound": ("hbm / issue (topology and lead times folded at compile time)" if key.endswith("_specialised") else
+                              "instruction issue (run-time topology / lead times as 0/1 multipliers)"),
                     "config": ("serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
-                               "two-level distribution tree, two demand sources (tree kernels)" if "distribution" in key else
+                               "two-level distribution tree, two demand sources (library specialised for this network)" if key.endswith("_specialised") else
+                               "two-level distribution tree, two demand sources (general tree kernels)" if "distribution" in key else
                                "8-node tree: factory -> {annex, hub -> 5 retailers}, 6 demand sources, obs 56 / action 8 "
                                "(one lane per node)")}
         del sim

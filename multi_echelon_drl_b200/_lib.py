@@ -131,11 +131,12 @@ def load():
     return lib
 
 
-def check(rc: int):
-    """Map status codes to the exceptions the reference raises at the same places."""
+def check(rc: int, lib=None):
+    """Map status codes to the exceptions the reference raises at the same places.  `lib`: the library that
+    returned `rc` when it is not the main one (a specialised build keeps its own error text)."""
     if rc >= 0:
         return rc
-    msg = load().sn_last_error().decode()
+    msg = (lib if lib is not None else load()).sn_last_error().decode()
     if rc == SN_ERR_TERMINAL or rc == SN_ERR_INVALID:
         raise ValueError(msg)                      # envs.py:88-89
     if rc == SN_ERR_TYPE:

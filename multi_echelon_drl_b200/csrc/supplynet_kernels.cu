@@ -265,7 +265,11 @@ struct GenOps {
 // distribution trees (supplynet_tree.cuh, 64 words): one demand row per source and period
 template <typename T>
 struct TreeOps {
+#if defined(SN_STATIC_TOPO) && !defined(SN_ST_WIDE)
+  static constexpr bool kWide = false;            // specialised builds fit the 128 registers of the single-wave geometry
+#else
   static constexpr bool kWide = true;             // k_rollout_wide, 144 registers: 0.315 ms vs 0.355 ms with 128 + ~100 spill accesses
+#endif
   using E = TEnv<T>;
   using D = TreeDem<T>;
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>& sp, int64_t ld) { return ld * sp.n_src; }
@@ -280,6 +284,7 @@ struct TreeOps {
 #pragma unroll
     for (int i = 0; i < kTStateWords; ++i) w[i] = state[i * ld + env];
     tenv_from_words(e, w);
+    tenv_static_zeros(e);
   }
   static __device__ __forceinline__ void store(T* __restrict__ state, int64_t ld, int64_t env, const E& e) {
     T w[kTStateWords];
@@ -293,6 +298,7 @@ struct TreeOps {
 #pragma unroll
     for (int w = 0; w < kGInitWords; ++w) in[w] = __ldg(init + w * ld + env);
     tenv_reset(e, sp, in, d0);
+    tenv_static_zeros(e);
   }
   template <bool MULTI>
   static __device__ __forceinline__ void step(E& e, const DevSpec<T>& sp, int, const T (&q)[kF], const D& dn, bool terminal,
@@ -871,6 +877,26 @@ const char* last_error() { return g_err; }
 namespace {
 using sn_detail::fail;
 
+// Specialised builds (specialize.py) serve one quantity type and distribution trees of up to four nodes only
+#ifndef SN_ONLY_DTYPE
+#define SN_ONLY_DTYPE -1
+#endif
+#if SN_ONLY_DTYPE < 0 || SN_ONLY_DTYPE == 0
+#define SN_CASE_I32(EXPR) case SN_I32: return EXPR;
+#else
+#define SN_CASE_I32(EXPR)
+#endif
+#if SN_ONLY_DTYPE < 0 || SN_ONLY_DTYPE == 1
+#define SN_CASE_F32(EXPR) case SN_F32: return EXPR;
+#else
+#define SN_CASE_F32(EXPR)
+#endif
+#if SN_ONLY_DTYPE < 0 || SN_ONLY_DTYPE == 2
+#define SN_CASE_F64(EXPR) case SN_F64: return EXPR;
+#else
+#define SN_CASE_F64(EXPR)
+#endif
+
 bool is_integral(double x) { return std::isfinite(x) && std::floor(x) == x && std::fabs(x) < 2147483647.0; }
 
 // the beer game's lead times (envs.py:355-392): tuned kernels; anything else takes the generic path
@@ -885,6 +911,8 @@ bool is_standard(const sn_spec* s) {
     if (s->info_leadtime[k] != li[k] || s->ship_leadtime[k] != 2) return false;
   return true;
 }
+
+template <typename T> sn::DevSpec<T> lower(const sn_spec* s);
 
 int validate(const sn_spec* s, int dtype) {
   if (s == nullptr) return fail(SN_ERR_INVALID, "spec is NULL");
@@ -957,6 +985,17 @@ int validate(const sn_spec* s, int dtype) {
     if (s->rule == SN_RULE_D_PLUS_A && (!is_integral(s->dpa_offset) || !is_integral(s->dpa_lb) || !is_integral(s->dpa_ub)))
       return fail(SN_ERR_TYPE, "d+a offset/bounds must be integral for SN_I32");
   }
+#ifdef SN_STATIC_TOPO
+  {   // a specialised build serves exactly the network it was compiled for (specialize.py)
+    if (!is_tree(s) || is_net(s)) return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only");
+    const auto d = lower<int32_t>(s);
+    bool same = d.nf == sn::st_nf() && d.max_rank == sn::st_max_rank();
+    for (int k = 0; k < 4; ++k)
+      same = same && d.sup[k] == sn::st_sup(k) && d.rank[k] == sn::st_rank(k) && d.lat_src[k] == sn::st_lat(k) &&
+             d.li[k] == sn::st_li(k) && d.ls[k] == sn::st_ls(k);
+    if (!same) return fail(SN_ERR_UNSUPPORTED, "this specialised build was compiled for another network");
+  }
+#endif
   return SN_OK;
 }
 
@@ -1163,6 +1202,13 @@ inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetB
 
 // launch with <IDENT, Ops> chosen from the spec: tuned standard kernels (identity specialised or not)
 // or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
+#ifdef SN_TREE_ONLY
+#define SN_DISPATCH_TOPO(spec, CALL)                                   \
+  do {                                                                 \
+    if (is_tree(spec)) { CALL(false, sn::TreeOps<T>); }                \
+    else return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only"); \
+  } while (0)
+#else
 #define SN_DISPATCH_TOPO(spec, CALL)                                   \
   do {                                                                 \
     if (is_tree(spec)) { CALL(false, sn::TreeOps<T>); }                \
@@ -1170,14 +1216,17 @@ inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetB
     else if (is_identity(spec)) { CALL(true, sn::StdOps<T>); }         \
     else { CALL(false, sn::StdOps<T>); }                               \
   } while (0)
+#endif
 
 template <typename T>
 int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const void* demand0, void* state,
              float* obs, cudaStream_t st) {
+#ifndef SN_TREE_ONLY
   if (is_net(spec)) {
     sn::k_net_reset<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs);
     return cuda_ok("sn_reset launch");
   }
+#endif
   const auto d = lower<T>(spec);
 #define SN_CALL(ID, OPS) sn::k_reset<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
@@ -1187,10 +1236,12 @@ int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const
 
 template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
+#ifndef SN_TREE_ONLY
   if (is_net(spec)) {
     sn::k_net_observe<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs);
     return cuda_ok("sn_observe launch");
   }
+#endif
   const auto d = lower<T>(spec);
 #define SN_CALL(ID, OPS) sn::k_observe<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
@@ -1301,11 +1352,14 @@ int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period
 template <typename T>
 int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state, const void* actions,
             const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
+#ifndef SN_TREE_ONLY
   if (is_net(spec)) {
     sn::k_net_step<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out);
     return cuda_ok("sn_step launch");
   }
+#endif
   const auto d = lower<T>(spec);
+#ifndef SN_TREE_ONLY
   // beer-game lead times: the TMA-tiled persistent kernel for HBM-sized batches (and whenever the VecNormalize
   // statistics are fused in), the plain one-thread-per-env kernel for small ones
   const bool tiled_ok = is_standard(spec) && aligned16(state) && aligned16(demand) && aligned16(actions) &&
@@ -1320,6 +1374,7 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
     if (is_identity(spec)) return launch_step_tiled<T, true>(d, n, ld, period, state, actions, demand, out, st);
     return launch_step_tiled<T, false>(d, n, ld, period, state, actions, demand, out, st);
   }
+#endif
 #define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out, tma_ok(out.obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
 #undef SN_CALL
@@ -1351,6 +1406,7 @@ void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::
                         const sn::RolloutPtrs& out, int tma, cudaStream_t st, const void* init, float* obs0) {
 #define SN_ARGS d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0
   if (is_tree(spec)) launch_rollout<T, POLICY, false, false, sn::TreeOps<T>>(SN_ARGS);
+#ifndef SN_TREE_ONLY
   else if (!is_standard(spec)) {
     if (d.n_items > 1) launch_rollout<T, POLICY, false, true, sn::GenOps<T>>(SN_ARGS);
     else launch_rollout<T, POLICY, false, false, sn::GenOps<T>>(SN_ARGS);
@@ -1362,6 +1418,7 @@ void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::
     if (d.n_items > 1) launch_rollout<T, POLICY, false, true, sn::StdOps<T>>(SN_ARGS);
     else launch_rollout<T, POLICY, false, false, sn::StdOps<T>>(SN_ARGS);
   }
+#endif
 #undef SN_ARGS
 }
 
@@ -1369,6 +1426,7 @@ template <typename T>
 int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period0, int n_steps, void* state,
                const void* demand, int policy_kind, const void* actions, const sn_policy* policy,
                const sn::RolloutPtrs& out, cudaStream_t st, const void* init = nullptr, float* obs0 = nullptr) {
+#ifndef SN_TREE_ONLY
   if (is_net(spec)) {
     sn::NetPolicy<T> np;
     const int nrc = lower_net_policy<T>(policy, spec, dtype, &np);
@@ -1383,6 +1441,7 @@ int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period
     }
     return cuda_ok("sn_rollout launch");
   }
+#endif
   const auto d = lower<T>(spec);
   sn::DevPolicy<T> p;
   const int rc = lower_policy<T>(policy, spec, dtype, &p);
@@ -1432,10 +1491,11 @@ int32_t sn_reset(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld,
   if (!init || !demand0 || !state) return fail(SN_ERR_INVALID, "sn_reset: init, demand0 and state must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_reset<int32_t>(spec, n_envs, ld, init, demand0, state, obs, st);
-    case SN_F32: return do_reset<float>(spec, n_envs, ld, init, demand0, state, obs, st);
-    default: return do_reset<double>(spec, n_envs, ld, init, demand0, state, obs, st);
+    SN_CASE_I32(do_reset<int32_t>(spec, n_envs, ld, init, demand0, state, obs, st))
+    SN_CASE_F32(do_reset<float>(spec, n_envs, ld, init, demand0, state, obs, st))
+    SN_CASE_F64(do_reset<double>(spec, n_envs, ld, init, demand0, state, obs, st))
   }
+  return fail(SN_ERR_UNSUPPORTED, "this build of the library does not serve dtype %d", dtype);
 }
 
 int32_t sn_observe(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const void* state, float* obs,
@@ -1446,10 +1506,11 @@ int32_t sn_observe(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   if (!state || !obs) return fail(SN_ERR_INVALID, "sn_observe: state and obs must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_observe<int32_t>(spec, n_envs, ld, state, obs, st);
-    case SN_F32: return do_observe<float>(spec, n_envs, ld, state, obs, st);
-    default: return do_observe<double>(spec, n_envs, ld, state, obs, st);
+    SN_CASE_I32(do_observe<int32_t>(spec, n_envs, ld, state, obs, st))
+    SN_CASE_F32(do_observe<float>(spec, n_envs, ld, state, obs, st))
+    SN_CASE_F64(do_observe<double>(spec, n_envs, ld, state, obs, st))
   }
+  return fail(SN_ERR_UNSUPPORTED, "this build of the library does not serve dtype %d", dtype);
 }
 
 int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, const sn_step_io* io, void* stream) {
@@ -1490,10 +1551,11 @@ int32_t sn_step_ex(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   out.vn_eps = io->vn_epsilon;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_step<int32_t>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
-    case SN_F32: return do_step<float>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
-    default: return do_step<double>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st);
+    SN_CASE_I32(do_step<int32_t>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st))
+    SN_CASE_F32(do_step<float>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st))
+    SN_CASE_F64(do_step<double>(spec, n_envs, ld, io->period, io->state, io->actions, io->demand, out, st))
   }
+  return fail(SN_ERR_UNSUPPORTED, "this build of the library does not serve dtype %d", dtype);
 }
 
 int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t period, void* state,
@@ -1544,10 +1606,11 @@ int32_t sn_rollout(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   const sn::RolloutPtrs out{traj_obs, traj_reward, traj_actions, obs, ep_return, stats};
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_rollout<int32_t>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
-    case SN_F32: return do_rollout<float>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
-    default: return do_rollout<double>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st);
+    SN_CASE_I32(do_rollout<int32_t>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st))
+    SN_CASE_F32(do_rollout<float>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st))
+    SN_CASE_F64(do_rollout<double>(spec, dtype, n_envs, ld, period0, n_steps, state, demand, policy_kind, actions, policy, out, st))
   }
+  return fail(SN_ERR_UNSUPPORTED, "this build of the library does not serve dtype %d", dtype);
 }
 
 int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, int32_t n_steps, const void* init,
@@ -1573,10 +1636,11 @@ int32_t sn_episode(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t l
   const sn::RolloutPtrs out{traj_obs, traj_reward, traj_actions, obs, ep_return, stats};
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: return do_rollout<int32_t>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
-    case SN_F32: return do_rollout<float>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
-    default: return do_rollout<double>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0);
+    SN_CASE_I32(do_rollout<int32_t>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0))
+    SN_CASE_F32(do_rollout<float>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0))
+    SN_CASE_F64(do_rollout<double>(spec, dtype, n_envs, ld, 0, n_steps, state, demand, policy_kind, actions, policy, out, st, init, obs0))
   }
+  return fail(SN_ERR_UNSUPPORTED, "this build of the library does not serve dtype %d", dtype);
 }
 
 }  // extern "C"

@@ -17,12 +17,50 @@
 //   7k+0 inv[k]   7k+1 unf_ind[k]   7k+2 latI[k] (latest internal demand)   7k+3..6 U[k][0..3]
 //   28+3k+j info[k][j]   40+4k+j ship[k][j]   56+k B[k] (backlog of node k's upstream arc)   60+k dem[k]
 // Init words: as the generic path (36).  Demand tables: one row per demand source and period.
+// SPECIALISED BUILDS (-DSN_STATIC_TOPO, multi_echelon_drl_b200/specialize.py): the supplier table, the customer ranks,
+// the latest-demand sources and the lead times of ONE network are baked in as constants (SN_ST_*), every `pick` below
+// folds at compile time, and what is left is the straight-line code of that network - the 0/1-multiplier arithmetic
+// of the run-time path (861 instructions per warp-period against 342 for the tuned chain) disappears.  Same state
+// layout, same results bit for bit; the entry points of such a library refuse any other network.
 #pragma once
 #include "supplynet_generic.cuh"
 
 namespace sn {
 
 constexpr int kTStateWords = 64;
+
+#ifdef SN_STATIC_TOPO
+constexpr bool kStaticTopo = true;
+__host__ __device__ constexpr int st4(int k, int a, int b, int c, int d) { return k == 0 ? a : k == 1 ? b : k == 2 ? c : d; }
+__host__ __device__ constexpr int st_nf() { return SN_ST_NF; }
+__host__ __device__ constexpr int st_sup(int k) { return st4(k, SN_ST_SUP0, SN_ST_SUP1, SN_ST_SUP2, SN_ST_SUP3); }
+__host__ __device__ constexpr int st_rank(int k) { return st4(k, SN_ST_RANK0, SN_ST_RANK1, SN_ST_RANK2, SN_ST_RANK3); }
+__host__ __device__ constexpr int st_lat(int k) { return st4(k, SN_ST_LAT0, SN_ST_LAT1, SN_ST_LAT2, SN_ST_LAT3); }
+__host__ __device__ constexpr int st_li(int k) { return st4(k, SN_ST_LI0, SN_ST_LI1, SN_ST_LI2, SN_ST_LI3); }
+__host__ __device__ constexpr int st_ls(int k) { return st4(k, SN_ST_LS0, SN_ST_LS1, SN_ST_LS2, SN_ST_LS3); }
+__host__ __device__ constexpr int st_max_rank() { return SN_ST_MAX_RANK; }
+#else
+constexpr bool kStaticTopo = false;
+__host__ __device__ constexpr int st_nf() { return kF; }
+__host__ __device__ constexpr int st_sup(int) { return 0; }
+__host__ __device__ constexpr int st_rank(int) { return 0; }
+__host__ __device__ constexpr int st_lat(int) { return 0; }
+__host__ __device__ constexpr int st_li(int) { return 0; }
+__host__ __device__ constexpr int st_ls(int) { return 0; }
+__host__ __device__ constexpr int st_max_rank() { return kF; }
+#endif
+
+// v (+|-)= x where the table says so: a 0/1 multiplier from the constant bank at run time (no branch, no register
+// select), a compile-time condition in specialised builds (`c` is a constant after unrolling: the statement either
+// stays as a plain add or vanishes)
+template <typename T>
+__device__ __forceinline__ void pick_add(T& v, T x, T m, bool c) {
+  if (kStaticTopo) { if (c) v = v + x; } else { v = v + x * m; }
+}
+template <typename T>
+__device__ __forceinline__ void pick_sub(T& v, T x, T m, bool c) {
+  if (kStaticTopo) { if (c) v = v - x; } else { v = v - x * m; }
+}
 
 template <typename T>
 struct TreeDem { T v[kF]; };      // current external demand per NODE (0 for nodes without a stream)
@@ -36,7 +74,7 @@ struct TEnv {
   __device__ __forceinline__ T unfilled(int k, const DevSpec<T>& sp) const {
     T cb = T(0);
 #pragma unroll
-    for (int c = 0; c < kF; ++c) cb = cb + B[c] * sp.m_sup[c][k];
+    for (int c = 0; c < kF; ++c) pick_add(cb, B[c], sp.m_sup[c][k], st_sup(c) == k);
     return cb + (dem[k] + unf_ind[k]);
   }
   __device__ __forceinline__ T latest(int k) const { return latI[k] + dem[k]; }
@@ -54,7 +92,7 @@ template <typename T>
 __device__ __forceinline__ T customers_backlog(const TEnv<T>& e, const DevSpec<T>& sp, int k) {
   T cb = T(0);
 #pragma unroll
-  for (int c = 0; c < kF; ++c) cb = cb + e.B[c] * sp.m_sup[c][k];
+  for (int c = 0; c < kF; ++c) pick_add(cb, e.B[c], sp.m_sup[c][k], st_sup(c) == k);
   return cb;
 }
 
@@ -94,6 +132,24 @@ __device__ __forceinline__ void tenv_to_words(const TEnv<T>& e, T (&w)[kTStateWo
   }
 }
 
+// Specialised builds: pipeline slots beyond an arc's lead time never hold anything (reset leaves them 0, the step only
+// ever adds into slot lead time - 1 and shifts down).  Saying so after every load lets the compiler drop them from the
+// loop: up to 18 of the 64 state registers for the beer-game-like lead times.
+template <typename T>
+__device__ __forceinline__ void tenv_static_zeros(TEnv<T>& e) {
+  if (kStaticTopo) {
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+#pragma unroll
+      for (int j = 0; j < kGI; ++j)
+        if (k >= st_nf() || j >= st_li(k) - 1) e.info[k][j] = T(0);
+#pragma unroll
+      for (int j = 0; j < kGS; ++j)
+        if (k >= st_nf() || j >= st_ls(k)) e.ship[k][j] = T(0);
+    }
+  }
+}
+
 // latest internal demand of every node from the slips that just reached the suppliers
 template <typename T>
 __device__ __forceinline__ void set_latest(TEnv<T>& e, const DevSpec<T>& sp, const T (&arrived)[kF]) {
@@ -101,7 +157,7 @@ __device__ __forceinline__ void set_latest(TEnv<T>& e, const DevSpec<T>& sp, con
   for (int j = 0; j < kF; ++j) {
     T v = T(0);
 #pragma unroll
-    for (int k = 0; k < kF; ++k) v = v + arrived[k] * sp.m_lat[j][k];
+    for (int k = 0; k < kF; ++k) pick_add(v, arrived[k], sp.m_lat[j][k], st_lat(j) == k);
     e.latI[j] = v;                       // nodes without customers keep sum([]) = 0 (network_components.py:309)
   }
 }
@@ -152,6 +208,7 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
   T U4[kF];
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
+    if (kStaticTopo && k >= st_nf()) { U4[k] = T(0); continue; }     // phantom node: nothing moves
     T u[5] = {q[k], e.U[k][0], e.U[k][1], e.U[k][2], e.U[k][3]};
     const T arr = e.ship[k][0];
     e.inv[k] = e.inv[k] + arr;
@@ -170,18 +227,19 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
   // ---- fills, one round per customer rank (Arc.fill_orders in aggregate: min(inventory, backlog), :260-262)
 #pragma unroll
   for (int r = 0; r < kF - 1; ++r) {
-    if (r <= sp.max_rank) {                        // uniform over the grid
+    if (kStaticTopo ? r <= st_max_rank() : r <= sp.max_rank) {                   // uniform over the grid
 #pragma unroll
       for (int k = 0; k < kF; ++k) {
-        T inv_s = sp.big * sp.m_ext[k];            // external supplier: unlimited
+        if (kStaticTopo && (k >= st_nf() || st_rank(k) != r)) continue;          // node k is served in round rank[k] only
+        T inv_s = kStaticTopo ? (st_sup(k) < 0 ? sp.big : T(0)) : sp.big * sp.m_ext[k];      // external supplier: unlimited
 #pragma unroll
-        for (int j = 0; j < kF; ++j) inv_s = inv_s + e.inv[j] * sp.m_sup[k][j];
-        const T amt = tmin(inv_s, e.B[k]) * sp.m_rank[r][k];
+        for (int j = 0; j < kF; ++j) pick_add(inv_s, e.inv[j], sp.m_sup[k][j], st_sup(k) == j);
+        const T amt = kStaticTopo ? tmin(inv_s, e.B[k]) : tmin(inv_s, e.B[k]) * sp.m_rank[r][k];
 #pragma unroll
-        for (int j = 0; j < kF; ++j) e.inv[j] = e.inv[j] - amt * sp.m_sup[k][j];
+        for (int j = 0; j < kF; ++j) pick_sub(e.inv[j], amt, sp.m_sup[k][j], st_sup(k) == j);
         e.B[k] = e.B[k] - amt;
 #pragma unroll
-        for (int j = 0; j < kGS; ++j) e.ship[k][j] = e.ship[k][j] + amt * sp.m_ls[k][j];
+        for (int j = 0; j < kGS; ++j) pick_add(e.ship[k][j], amt, sp.m_ls[k][j], st_ls(k) - 1 == j);
       }
     }
   }
@@ -210,11 +268,13 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
     T arrived[kF];
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
-      arrived[k] = e.info[k][0] + q[k] * sp.m_li1[k];       // lead time 1: the head slot is empty, q arrives now
+      arrived[k] = e.info[k][0];                             // lead time 1: the head slot is empty, q arrives now
+      pick_add(arrived[k], q[k], sp.m_li1[k], st_li(k) == 1);
 #pragma unroll
       for (int j = 0; j < kGI; ++j) {
-        const T next = (j + 1 < kGI) ? e.info[k][j + 1] : T(0);
-        e.info[k][j] = next + q[k] * sp.m_li[k][j];
+        T next = (j + 1 < kGI) ? e.info[k][j + 1] : T(0);
+        pick_add(next, q[k], sp.m_li[k][j], st_li(k) - 2 == j);
+        e.info[k][j] = next;
       }
       e.B[k] = e.B[k] + arrived[k];
       e.U[k][3] = e.U[k][3] + U4[k];

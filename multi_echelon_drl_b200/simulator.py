@@ -87,6 +87,11 @@ class BatchedSupplyNetwork:
         self.period = 0
         self.terminal = True          # no episode loaded yet
         self.track_stats = False
+        # distribution trees: a library specialised for this very network (specialize.py), if one has been built,
+        # serves the period step and the fused rollouts; everything else stays on the general library
+        from . import specialize
+        self.fast = specialize.load(spec, dtype) if spec.is_tree else None
+        self._step_lib = self.fast if self.fast is not None else self.lib
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -179,8 +184,8 @@ class BatchedSupplyNetwork:
         io.cost = None if cost_out is None else cost_out.data_ptr()
         io.ep_return = self.ep_return.data_ptr()
         io.stats = self.stats.data_ptr() if self.track_stats else None
-        _lib.check(self.lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
-                                       self._stream()))
+        _lib.check(self._step_lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
+                                             self._stream()), self._step_lib)
         self.period += 1
         self.terminal = self.period >= self.T
         if self._graph_period_valid:                # keep the device counter of the graph-replayed step in sync
@@ -213,8 +218,8 @@ class BatchedSupplyNetwork:
             if vecnorm.get("nobs") is not None:
                 io.vn_clip_obs, io.vn_clip_reward = float(vecnorm["clip_obs"]), float(vecnorm["clip_reward"])
                 io.vn_epsilon = float(vecnorm["epsilon"])
-        _lib.check(self.lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
-                                       self._stream()))
+        _lib.check(self._step_lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
+                                             self._stream()), self._step_lib)
 
     def advance_host_period(self):
         """Host mirror of what a replayed `launch_step_device_period` did on the device."""
@@ -255,10 +260,11 @@ class BatchedSupplyNetwork:
             traj_reward = torch.empty((n_steps, n), dtype=torch.float32, device=dev)
         if record_actions and traj_actions is None:
             traj_actions = torch.empty((n_steps, n, self.n_agents), dtype=torch.float32, device=dev)
-        _lib.check(self.lib.sn_rollout(
+        _lib.check(self._step_lib.sn_rollout(
             C.byref(self._c_spec), self.dtype_code, n, self.ld, self.period, n_steps, _ptr(self.state),
             _ptr(self.demand), kind, _ptr(a), pol, _ptr(traj_obs), _ptr(traj_reward), _ptr(traj_actions),
-            _ptr(self.obs), _ptr(self.ep_return), _ptr(self.stats) if self.track_stats else None, self._stream()))
+            _ptr(self.obs), _ptr(self.ep_return), _ptr(self.stats) if self.track_stats else None, self._stream()),
+            self._step_lib)
         self.period += n_steps
         self.terminal = self.period >= self.T
         return dict(obs=self.obs, traj_obs=traj_obs, traj_reward=traj_reward, traj_actions=traj_actions,
@@ -287,11 +293,11 @@ class BatchedSupplyNetwork:
             traj_reward = torch.empty((n_steps, n), dtype=torch.float32, device=dev)
         if record_actions and traj_actions is None:
             traj_actions = torch.empty((n_steps, n, self.n_agents), dtype=torch.float32, device=dev)
-        _lib.check(self.lib.sn_episode(
+        _lib.check(self._step_lib.sn_episode(
             C.byref(self._c_spec), self.dtype_code, n, self.ld, n_steps, _ptr(self.init), _ptr(self.demand), kind,
             _ptr(a), pol, _ptr(obs0_out), _ptr(traj_obs), _ptr(traj_reward), _ptr(traj_actions), _ptr(self.obs),
             _ptr(self.state) if write_state else None, _ptr(self.ep_return),
-            _ptr(self.stats) if self.track_stats else None, self._stream()))
+            _ptr(self.stats) if self.track_stats else None, self._stream()), self._step_lib)
         self.period = n_steps
         self.terminal = self.period >= self.T
         return dict(obs=self.obs, obs0=obs0_out, traj_obs=traj_obs, traj_reward=traj_reward,

@@ -10,15 +10,34 @@ pytestmark = pytest.mark.gpu
 from test_oracle_trees import BIG_TREE_CASES, TREE_CASES, tree_oracle_rollout, tree_product_spec  # noqa: E402
 
 
-def _sim(case, n, dtype="int32"):
+def _sim(case, n, dtype="int32", lib="general"):
+    """lib = "general": the run-time-topology kernels of libsupplynet.so; "specialised": the library compiled for this
+    very network (multi_echelon_drl_b200/specialize.py; __graft_entry__.build() prebuilds the int32 ones of the
+    golden topologies), which BatchedSupplyNetwork picks up on its own when it exists."""
+    import os
+    from multi_echelon_drl_b200 import specialize
     from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
-    return BatchedSupplyNetwork(tree_product_spec(case), n, "cuda", dtype)
+    os.environ["SN_NO_SPECIALIZED"] = "0" if lib == "specialised" else "1"
+    try:
+        sim = BatchedSupplyNetwork(tree_product_spec(case), n, "cuda", dtype)
+    finally:
+        os.environ.pop("SN_NO_SPECIALIZED", None)
+    if lib == "specialised":
+        assert sim.fast is not None, f"no specialised library for {case['id']}: run __graft_entry__.build()"
+        assert os.path.basename(specialize.lib_path(sim.spec, dtype)).startswith("libsupplynet_tree_")
+    else:
+        assert sim.fast is None
+    return sim
 
 
+@pytest.mark.parametrize("lib", ["general", "specialised"])
 @pytest.mark.parametrize("case", TREE_CASES + BIG_TREE_CASES, ids=[c["id"] for c in TREE_CASES + BIG_TREE_CASES])
-def test_tree_step_and_rollout_match_reference_golden(case):
-    """Up to four nodes: register-resident tree kernels (64 state words); five to eight: shared-memory kernels (128)."""
-    sim = _sim(case, 1)
+def test_tree_step_and_rollout_match_reference_golden(case, lib):
+    """Up to four nodes: register-resident tree kernels (64 state words), general and specialised for the network;
+    five to eight: lane-per-node kernels (128)."""
+    if lib == "specialised" and len(case["names"]) > 4:
+        pytest.skip("specialised builds exist for trees of up to four nodes")
+    sim = _sim(case, 1, lib=lib)
     N = len(case["names"])
     half = 8 if N > 4 else 4                      # rows of the per-facility cost output: holding[half], backorder[half]
     assert sim.state_words == (128 if N > 4 else 64) and sim.obs_dim == case["obs0"].shape[0]
@@ -42,14 +61,17 @@ def test_tree_step_and_rollout_match_reference_golden(case):
                                        (37, "float32"), (55, "float64"),
                                        (1000, "int32"), (1013, "int32"), (1024, "int32"), (1037, "int32"), (1049, "int32"),
                                        (1001, "float32"), (1024, "float64")])
-def test_tree_batch_vs_oracle(cid, dtype):
+@pytest.mark.parametrize("lib", ["general", "specialised"])
+def test_tree_batch_vs_oracle(cid, dtype, lib):
     """3,001 envs (ragged) x 100 with bulk-drawn initial states and per-source demand streams: step kernel, fused
     rollout, rollout resumed mid-episode, in-kernel base-stock policy."""
     from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
     case = BIG_TREE_CASES[cid - 1000] if cid >= 1000 else TREE_CASES[cid]      # 1000+: five to eight nodes
+    if lib == "specialised" and (cid >= 1000 or dtype != "int32"):
+        pytest.skip("prebuilt specialised libraries: int32, trees of up to four nodes")
     n = 3001
-    sim = _sim(case, n, dtype)
+    sim = _sim(case, n, dtype, lib=lib)
     init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(cid))
     rs = np.random.RandomState(cid + 1)
     acts = rs.randint(-1, 19, (100, n, len(case["agents"])))
