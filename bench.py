@@ -334,6 +334,32 @@ def run_native(args):
     assert float(sim.stats[0].item()) == n * T, "stats vector: wrong env-step count"
     assert float(sim.stats[1].item()) == float(traj_rew.double().sum().item()), "stats vector disagrees with trajectory"
 
+    # shard invariance across real devices: the envs of one global batch, sharded by index over the ranks,
+    # give bit for bit what the whole batch gives on ONE GPU (rank 0 runs it and compares every env)
+    shard_check = None
+    if world > 1:
+        m = 8192
+        g_spec, g_init, g_demand, g_actions = make_inputs(m * world, 4321)
+        lo = rank * m
+
+        def per_env(sim_x, init_x, demand_x, actions_x, k):
+            sim_x.load_episode(init_x, demand_x)
+            to = torch.empty((T, k, 28), dtype=torch.float32, device=dev)
+            sim_x.episode(T, actions=torch.as_tensor(actions_x).to(dev), traj_obs=to, write_state=False)
+            # (position-weighted so that a permutation inside a trajectory would show)
+            w = torch.arange(1, T * 28 + 1, dtype=torch.float64, device=dev).view(T, 1, 28)
+            return torch.stack([(to.double() * w).sum((0, 2)), sim_x.ep_return.clone()])
+
+        mine = per_env(BatchedSupplyNetwork(g_spec, m, dev, "int32"), g_init[lo:lo + m], g_demand[lo:lo + m],
+                       g_actions[:, lo:lo + m], m)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        if rank == 0:
+            whole = per_env(BatchedSupplyNetwork(g_spec, m * world, dev, "int32"), g_init, g_demand, g_actions, m * world)
+            shard_check = bool(torch.equal(torch.cat(parts, dim=1), whole))
+            assert shard_check, "sharded envs differ from the same envs on one GPU"
+        del parts, mine
+
     env_steps_per_step = n * T * world
     value = env_steps_per_step / (ms_dev / args.steps * 1e-3)
     e2e_value = env_steps_per_step / (ms_e2e / e2e_steps * 1e-3)
@@ -384,6 +410,10 @@ def run_native(args):
         }
         if world > 1:
             line["per_rank_ms_per_step"] = per_rank_ms      # device time of every rank (value uses the max)
+            line["shard_invariance"] = {"ok": shard_check, "envs": 8192 * world,
+                                        "what": "every env of a global batch sharded by index over the ranks equals, bit for bit "
+                                                "(position-weighted trajectory checksum, episode return), the same env when "
+                                                "rank 0 runs the whole batch on one GPU"}
         line.update(extra)
         line.update(blocks)
         print(json.dumps(line))
