@@ -49,8 +49,8 @@ extern "C" {
 #define SN_CTL_PERIOD 0         /* period to play; read by the launch and advanced by it (set to 0 to start an episode) */
 #define SN_CTL_TICKET 1         /* internal (block ticket); leave at 0                                               */
 #define SN_CTL_FLAGS 2          /* sticky SN_FLAG_* bits                                                             */
-#define SN_CTL_BARRIER 3        /* internal (grid barrier of the one-kernel VecNormalize mode); leave at 0           */
-#define SN_CTL_SEQ 4            /* internal (launch sequence number of that mode); never reset                       */
+#define SN_CTL_SEQ 4            /* internal (launch sequence number of the one-kernel VecNormalize mode); never reset */
+#define SN_VN_ONEPASS_SCRATCH_DOUBLES (256 * 64)   /* vn_scratch of that mode: one 512-byte slot per block            */
 #define SN_FLAG_STEP_AFTER_TERMINAL 1   /* a launch found period >= max_episode_steps and did nothing (envs.py:88-89) */
 #define SN_FLAG_QTY_RANGE 2             /* SN_I32: a quantity reached 2^SN_QTY_LIMIT_LOG2, results may have wrapped    */
 
@@ -213,8 +213,9 @@ int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, 
  *                launch also writes the normalised observation [n_envs][obs_dim] (and vn_nrew [n_envs], if given):
  *                clip((obs-mean)/sqrt(var+vn_epsilon), +-vn_clip_obs), clip(reward/sqrt(ret_var+eps), +-vn_clip_reward),
  *                with the statistics AFTER this step's update when vn_scratch is given (then vn_scratch is
- *                2*(2*obs_dim+2) doubles, zero before the first launch, and the launch is cooperative: its blocks
- *                meet at a grid barrier between the moments and the normalisation), else with vn_obs_rms / vn_ret_rms
+ *                SN_VN_ONEPASS_SCRATCH_DOUBLES doubles, zero before the first launch, and the launch is cooperative:
+ *                every block publishes its tile's moments, they meet, and each adds the blocks up in block order - the
+ *                statistics are reproducible bit for bit, unlike atomic accumulation), else with vn_obs_rms / vn_ret_rms
  *                as they are (evaluation).  Replaces the sn_vecnorm_apply launch. */
 typedef struct sn_step_io {
   void* state;

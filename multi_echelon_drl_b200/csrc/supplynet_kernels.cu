@@ -1325,11 +1325,12 @@ int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period
   const int64_t sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   if (out.vn_nobs != nullptr) {
-    if (tiles > sms) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes at most %lld envs on this device (one tile per SM)", (long long)(sms * C::kTile));
+    if (tiles > sms || tiles * sn::kVnSlot > SN_VN_ONEPASS_SCRATCH_DOUBLES) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes at most %lld envs on this device (one tile per SM)", (long long)(sms * C::kTile));
     if (!aligned16(out.vn_nobs) != !tma_ok(out.obs) || (out.vn_nrew != nullptr && !aligned16(out.vn_nrew)))
       return fail(SN_ERR_INVALID, "sn_step_ex: obs / vn_nobs / vn_nrew must share their 16-byte alignment");
   }
-  if (out.vn_nobs != nullptr && out.vn_scratch != nullptr) {
+  static const bool no_coop = [] { const char* v = std::getenv("SN_NO_COOP"); return v && v[0] == '1'; }();   // experiments only
+  if (out.vn_nobs != nullptr && out.vn_scratch != nullptr && !no_coop) {
     // blocks meet at a grid barrier: cooperative launch (the runtime guarantees that all of them are resident)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -63,23 +63,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Grid-wide barrier of the one-kernel VecNormalize mode (cooperative launch: every CTA is resident).  The block
-// that arrives last advances the period and releases the others by bumping the launch sequence number, which
-// every block read before arriving.  Bounded spin: a protocol error traps instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier_and_advance(int32_t* ctl, int period, int seq) {
-  __threadfence();
-  if (atomicAdd(ctl + SN_CTL_BARRIER, 1) == (int)gridDim.x - 1) {
-    ctl[SN_CTL_BARRIER] = 0;
-    ctl[SN_CTL_PERIOD] = period + 1;
-    __threadfence();
-    atomicExch(ctl + SN_CTL_SEQ, seq + 1);
-  } else {
-    const volatile int32_t* p = ctl + SN_CTL_SEQ;
-    for (uint32_t spins = 0; *p == seq; ++spins)
-      if (spins > (1u << 24)) __trap();
-  }
-  __threadfence();
-}
+constexpr int kVnSlot = 64;          // doubles per block in the scratch of the one-kernel VecNormalize mode (512 B)
 
 // ---- stage geometry ----------------------------------------------------------------------------------------
 template <typename T, typename Ops>
@@ -332,11 +316,16 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         double m = vn_m, v = vn_v;
         const double cnt = vn_cnt;
         if (vn_barrier) {
-          double* scr = out.vn_scratch + (seq & 1) * (2 * od + 2);           // double-buffered across launches
-          double* scr_other = out.vn_scratch + ((seq & 1) ^ 1) * (2 * od + 2);
+          // Every block publishes the moments of its tile in a slot of its own (plain stores), raises the slot's flag
+          // to this launch's sequence number + 1, and waits until all slots carry it; then every block adds the slots
+          // up in block order (deterministic, unlike atomics) and merges them into the statistics it read before.
+          // One store-flag-load chain instead of atomics + a counter barrier + a reload.
+          double* slots = out.vn_scratch;                          // [gridDim.x][kVnSlot]: sums, ..., flag in the last word
+          double* mine = slots + (size_t)blockIdx.x * kVnSlot;
           if (tid < ng * od) {
             const int c = tid % od, g = tid / od;
             double sx = 0.0, sxx = 0.0;
+#pragma unroll 8
             for (int r = g; r < rows; r += ng) {
               const double x = (double)s_obs[r * od + c];
               sx += x;
@@ -353,30 +342,66 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
           if (tid < od) {
             double a = 0.0, b = 0.0;
             for (int g = 0; g < ng; ++g) { a += vn_red[g * od + tid]; b += vn_red[kTile + g * od + tid]; }
-            atomicAdd(&scr[tid], a);
-            atomicAdd(&scr[od + tid], b);
+            __stcg(&mine[tid], a);
+            __stcg(&mine[od + tid], b);
+            __threadfence();
           } else if (tid == ret_thread && out.vn_returns != nullptr) {
             double a = 0.0, b = 0.0;
             for (int w = 0; w < C::kConsumerWarps; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
-            atomicAdd(&scr[2 * od], a);
-            atomicAdd(&scr[2 * od + 1], b);
+            __stcg(&mine[2 * od], a);
+            __stcg(&mine[2 * od + 1], b);
+            __threadfence();
           }
-          named_bar_sync(1, kTile);                                // this block's contributions are issued
-          if (tid == 0) grid_barrier_and_advance(out.ctl, period, seq);
-          named_bar_sync(1, kTile);
+          named_bar_sync(1, kTile);                                // this block's sums are written and fenced
+          const long long want = (long long)seq + 1;
+          if (tid == 0) {
+            *reinterpret_cast<volatile long long*>(mine + kVnSlot - 1) = want;
+          }
+          for (int bq = tid; bq < (int)gridDim.x; bq += kTile) {   // bounded spin: a protocol error traps, never hangs
+            const volatile long long* f = reinterpret_cast<const volatile long long*>(slots + (size_t)bq * kVnSlot + kVnSlot - 1);
+            for (uint32_t spins = 0; *f != want; ++spins)
+              if (spins > (1u << 24)) __trap();
+          }
+          __threadfence();
+          named_bar_sync(1, kTile);                                // every block has arrived (and has read period / seq)
           const double bn = (double)n;
-          if (tid < od) {
-            rms_merge_inplace(&m, &v, cnt, __ldcg(&scr[tid]), __ldcg(&scr[od + tid]), bn);
-            if (blockIdx.x == 0) {
-              out.vn_obs_rms[tid] = m;
-              out.vn_obs_rms[od + tid] = v;
-              if (tid == 0) out.vn_obs_rms[2 * od] = cnt + bn;
+          {
+            // all consumer threads fetch: thread = (block group g, column c); the loads of a thread are independent,
+            // so one L2 latency covers them (a single thread walking over the blocks would pay it per block)
+            const int c = tid & 31, g = tid >> 5;
+            double a = 0.0, b = 0.0;
+            if (c <= od) {
+              const int ia = c < od ? c : 2 * od, ib = c < od ? od + c : 2 * od + 1;     // column c; c == od: the returns
+#pragma unroll 4
+              for (int bq = g; bq < (int)gridDim.x; bq += C::kConsumerWarps) {
+                a += __ldcg(slots + (size_t)bq * kVnSlot + ia);
+                b += __ldcg(slots + (size_t)bq * kVnSlot + ib);
+              }
             }
-          } else if (tid == ret_thread && out.vn_returns != nullptr) {
-            rms_merge_inplace(&m, &v, cnt, __ldcg(&scr[2 * od]), __ldcg(&scr[2 * od + 1]), bn);
-            if (blockIdx.x == 0) { out.vn_ret_rms[0] = m; out.vn_ret_rms[1] = v; out.vn_ret_rms[2] = cnt + bn; }
+            vn_red[tid] = a;
+            vn_red[kTile + tid] = b;
           }
-          if (blockIdx.x == 0 && tid >= 64 && tid < 64 + 2 * od + 2) scr_other[tid - 64] = 0.0;   // the previous launch's sums
+          named_bar_sync(1, kTile);
+          if (tid < od || (tid == ret_thread && out.vn_returns != nullptr)) {
+            const int c = tid < od ? tid : od;
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int g = 0; g < C::kConsumerWarps; ++g) { a += vn_red[g * 32 + c]; b += vn_red[kTile + g * 32 + c]; }   // fixed order
+            rms_merge_inplace(&m, &v, cnt, a, b, bn);
+            if (blockIdx.x == 0) {
+              if (tid < od) {
+                out.vn_obs_rms[tid] = m;
+                out.vn_obs_rms[od + tid] = v;
+                if (tid == 0) out.vn_obs_rms[2 * od] = cnt + bn;
+              } else {
+                out.vn_ret_rms[0] = m; out.vn_ret_rms[1] = v; out.vn_ret_rms[2] = cnt + bn;
+              }
+            }
+          }
+          if (blockIdx.x == 0 && tid == 0) {                       // everybody has read them: advance period and sequence
+            out.ctl[SN_CTL_PERIOD] = period + 1;
+            out.ctl[SN_CTL_SEQ] = seq + 1;
+          }
         }
         if (tid < od) { s_stat[tid] = (float)m; s_stat[32 + tid] = (float)(1.0 / sqrt(v + out.vn_eps)); }
         if (tid == ret_thread) s_stat[64] = (float)(1.0 / sqrt(v + out.vn_eps));
@@ -414,6 +439,7 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         if (out.vn_scratch != nullptr && tid < (od <= 32 ? (kTile / od) * od : 0)) {
           // column moments of this tile: thread = (row group g, column c); groups interleave the rows
           const int c = tid % od, g = tid / od, ng = kTile / od;
+#pragma unroll 8
           for (int r = g; r < rows; r += ng) {
             const double x = (double)s_obs[r * od + c];
             vsx += x;

@@ -47,8 +47,9 @@ class VecNormalize:
         self._ret_rms = self._fresh(1, f64)
         self.returns = torch.zeros(n, **f64)
         self._scratch = torch.zeros(2 * od + 2, **f64)
-        # owned by the fused paths (zero between launches; the one-kernel mode alternates between the two halves)
-        self._fused_scratch = torch.zeros(2 * (2 * od + 2), **f64)
+        # owned by the fused paths: sums that are zero between launches (two-kernel mode); one slot per block (one-kernel mode)
+        self._fused_scratch = torch.zeros(2 * od + 2, **f64)
+        self._fused_slots = torch.zeros(_lib.SN_VN_ONEPASS_SCRATCH_DOUBLES, **f64)
         self.old_obs = torch.zeros((n, od), dtype=torch.float32, device=dev)
         self.old_reward = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._nobs = torch.zeros((n, od), dtype=torch.float32, device=dev)
@@ -123,7 +124,7 @@ class VecNormalize:
     def fused_args(self, key=None):
         update, _, onepass = key if key is not None else self.graph_key()
         d = dict(obs_rms=self._obs_rms, ret_rms=self._ret_rms, gamma=self.gamma,
-                 scratch=self._fused_scratch if update else None,
+                 scratch=(self._fused_slots if onepass else self._fused_scratch) if update else None,
                  returns=self.returns if (update and self.norm_reward) else None)
         if onepass:
             d.update(nobs=self._nobs, nrew=self._nrew if self.norm_reward else None, clip_obs=self.clip_obs,
