@@ -342,3 +342,45 @@ def test_graph_vecenv_equals_eager_vecenv_without_vecnormalize():
         if d0.all():
             assert torch.equal(i0.terminal_observation, i1.terminal_observation)
             assert torch.equal(i0.episode_return, i1.episode_return)
+
+
+@pytest.mark.parametrize("n", [300, 1000, 128 * 148 + 37])
+def test_tiled_writes_nothing_outside_its_buffers(n):
+    """Canaries around every buffer the tiled kernel stores to (the TMA box of the last tile reaches beyond `ld`: the
+    tensor map must clip it), padding columns n..ld-1 of the state included (compute-sanitizer is closed on this pool)."""
+    from multi_echelon_drl_b200 import _lib
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    T = 6
+    sp = _spec("uniform", (0, 1, 2, 3), True, "a", T)
+    init, demand, acts = _inputs(sp, n, T, 17, 0, 17)
+    ld = (n + 31) // 32 * 32
+    pad = 4096
+    with _Kernel("tiled"):
+        sim = BatchedSupplyNetwork(sp, n, "cuda", "int32")
+        sim.load_episode(init, demand)
+
+        def guarded(numel, dtype, fill):
+            store = torch.full((numel + 2 * pad,), fill, dtype=dtype, device="cuda")
+            return store, store[pad:pad + numel]
+
+        st_store, st = guarded(40 * ld, torch.int32, -77)
+        obs_store, obs = guarded(n * 28, torch.float32, -7.0)
+        rew_store, rew = guarded(n, torch.float32, -7.0)
+        ret_store, ret = guarded(n, torch.float64, -7.0)
+        sim.reset()
+        st.view(40, ld).copy_(sim.state)
+        st.view(40, ld)[:, n:] = -55                                   # padding columns: must come back untouched
+        ret.zero_()
+        a = torch.as_tensor(acts[0].astype(np.int32)).cuda()
+        io = _lib.SnStepIo()
+        io.state, io.actions, io.demand, io.period = st.data_ptr(), a.data_ptr(), sim.demand[1].data_ptr(), 0
+        io.obs, io.reward, io.ep_return = obs.data_ptr(), rew.data_ptr(), ret.data_ptr()
+        _lib.check(sim.lib.sn_step_ex(C.byref(sim._c_spec), sim.dtype_code, n, ld, C.byref(io),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        want_obs, want_rew, _ = sim.step(a)                            # the same period on the simulator's own buffers
+        assert torch.equal(obs.view(n, 28), want_obs) and torch.equal(rew, want_rew)
+        assert torch.equal(st.view(40, ld)[:, :n], sim.state[:, :n]) and torch.equal(ret, sim.ep_return)
+        assert (st.view(40, ld)[:, n:] == -55).all()
+        for store, fill in ((st_store, -77), (obs_store, -7.0), (rew_store, -7.0), (ret_store, -7.0)):
+            assert (store[:pad] == fill).all() and (store[-pad:] == fill).all()
