@@ -128,3 +128,45 @@ def test_vecnormalize_on_56_dim_observations_of_an_eight_node_tree():
         np.testing.assert_allclose(nrew.cpu().numpy(), np.clip(r / np.sqrt(ret_rms.var + 1e-8), -1000, 1000), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(env.obs_rms["mean"].cpu().numpy(), obs_rms.mean, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(env.obs_rms["var"].cpu().numpy(), obs_rms.var, rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_running_statistics_equal_numpy_on_the_concatenated_data(use_graph):
+    """Pins the running statistics to something that is not our own restatement: after any number of updates
+    RunningMeanStd's (mean, var, count) must be the moments of ALL samples seen so far, taken by numpy over their
+    concatenation, combined with the initial pseudo-sample (mean 0, var 1, weight 1e-4) - Chan et al.'s parallel
+    variance is exact, so however the batches were merged (eager kernels, fused into the step kernel, one-kernel
+    mode) the result is the same closed form."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.vec_normalize import VecNormalize
+    n = 1536
+    env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=11, dtype="float32", use_graph=use_graph),
+                       clip_obs=100.0, clip_reward=1000.0, gamma=0.95)
+    seen_obs, seen_ret, ret = [], [], np.zeros(n)
+    env.reset()
+    seen_obs.append(env.get_original_obs().cpu().numpy().astype(np.float64))
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for t in range(130):                                       # crosses one auto-reset
+        a = torch.rand((n, 4), device="cuda", generator=g) * 16
+        _, _, dones, _ = env.step(a)
+        seen_obs.append(env.get_original_obs().cpu().numpy().astype(np.float64))
+        ret = ret * 0.95 + env.get_original_reward().cpu().numpy().astype(np.float64)
+        seen_ret.append(ret.copy())
+        if dones.all():
+            ret[:] = 0
+
+    def closed_form(samples):
+        x = np.concatenate(samples, axis=0)
+        w0, cnt = 1e-4, x.shape[0]
+        mean = x.sum(0) / (cnt + w0)                           # prior mean 0
+        m2 = ((x - mean) ** 2).sum(0) + w0 * (1.0 + mean ** 2)  # prior: variance 1 about mean 0, moved to the new mean
+        return mean, m2 / (cnt + w0), cnt + w0
+
+    mean, var, cnt = closed_form(seen_obs)
+    np.testing.assert_allclose(env.obs_rms["mean"].cpu().numpy(), mean, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(env.obs_rms["var"].cpu().numpy(), var, rtol=1e-8, atol=1e-9)
+    assert abs(env.obs_rms["count"].item() - cnt) < 1e-6
+    rmean, rvar, rcnt = closed_form([r[:, None] for r in seen_ret])
+    np.testing.assert_allclose(env.ret_rms["mean"].item(), rmean[0], rtol=1e-9)
+    np.testing.assert_allclose(env.ret_rms["var"].item(), rvar[0], rtol=1e-8)
+    assert abs(env.ret_rms["count"].item() - rcnt) < 1e-6
