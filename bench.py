@@ -590,7 +590,7 @@ def single_step_numbers(torch, dev, peak):
                     ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"], True)
     others = {"rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
               "rollout_distribution_tree_65536": tree, "rollout_distribution_tree_65536_specialised": tree,
-              "rollout_tree_8_nodes_65536": big}
+              "rollout_tree_8_nodes_65536": big, "rollout_tree_8_nodes_65536_specialised": big}
     t_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     from multi_echelon_drl_b200 import specialize
     for key, sp in others.items():
@@ -622,7 +622,9 @@ def single_step_numbers(torch, dev, peak):
                     "bound": ("hbm / issue (topology and lead times folded at compile time)" if key.endswith("_specialised") else
                               "instruction issue (run-time topology / lead times as 0/1 multipliers)"),
                     "config": ("serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
-                               "two-level distribution tree, two demand sources (library specialised for this network)" if key.endswith("_specialised") else
+                               "two-level distribution tree, two demand sources (library specialised for this network)" if key == "rollout_distribution_tree_65536_specialised" else
+                               "8-node tree: factory -> {annex, hub -> 5 retailers} (library specialised for this network: eight "
+                               "facilities per thread, register-resident)" if key.endswith("_specialised") else
                                "two-level distribution tree, two demand sources (general tree kernels)" if "distribution" in key else
                                "8-node tree: factory -> {annex, hub -> 5 retailers}, 6 demand sources, obs 56 / action 8 "
                                "(one lane per node)")}

@@ -26,7 +26,13 @@
 
 namespace sn {
 
-constexpr int kF = 4;
+// Facilities per env held by one thread.  4 everywhere except in a library specialised for a tree of five to eight
+// nodes (specialize.py builds it with -DSN_KF=8: the tree code is written against kF, the chain code is not
+// instantiated there).
+#ifndef SN_KF
+#define SN_KF 4
+#endif
+constexpr int kF = SN_KF;
 constexpr int kObsPerNode = 7;
 constexpr int kStateWords = 40;
 constexpr int kInitWords = 19;
@@ -226,6 +232,9 @@ __device__ __forceinline__ void emit_obs(const E& e, const DevSpec<T>& sp, bool 
       _Pragma("unroll") for (int j = 0; j < 7; ++j) d[j] = v[j]; \
     }
     SN_EMIT_NODE(0) SN_EMIT_NODE(1) SN_EMIT_NODE(2) SN_EMIT_NODE(3)
+#if SN_KF > 4
+    SN_EMIT_NODE(4) SN_EMIT_NODE(5) SN_EMIT_NODE(6) SN_EMIT_NODE(7)
+#endif
 #undef SN_EMIT_NODE
   }
 }
@@ -337,28 +346,30 @@ __device__ __forceinline__ void env_step(Env<T>& e, const DevSpec<T>& sp, int it
   e.inv[0] = e.inv[0] - sold;
   e.unf_ind = tot - sold;
 
-  // ---- get_cost (supplynetwork.py:285-310): node-list order, c_h and c_b accumulated apart
+  // ---- get_cost (supplynetwork.py:285-310): node-list order, c_h and c_b accumulated apart.  Explicitly rounded
+  // products and sums (__dmul_rn / __dadd_rn are never contracted into fused multiply-adds): the reference rounds
+  // after every operation, and with cost coefficients that are not dyadic a fused multiply-add would differ
   double ch = 0.0, cb = 0.0;
   if (MULTI) {                     // per-chain cost vector (dynamic constant-bank index)
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
       const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
-      out.hold[k] = -(double)e.inv[k] * sp.h[item][k];
-      out.back[k] = -(double)unfk * sp.b[item][k];
-      ch += out.hold[k];
-      cb += out.back[k];
+      out.hold[k] = __dmul_rn(-(double)e.inv[k], sp.h[item][k]);
+      out.back[k] = __dmul_rn(-(double)unfk, sp.b[item][k]);
+      ch = __dadd_rn(ch, out.hold[k]);
+      cb = __dadd_rn(cb, out.back[k]);
     }
   } else {                         // single item: coefficients fold into the multiply as constant operands
 #pragma unroll
     for (int k = 0; k < kF; ++k) {
       const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
-      out.hold[k] = -(double)e.inv[k] * sp.h[0][k];
-      out.back[k] = -(double)unfk * sp.b[0][k];
-      ch += out.hold[k];
-      cb += out.back[k];
+      out.hold[k] = __dmul_rn(-(double)e.inv[k], sp.h[0][k]);
+      out.back[k] = __dmul_rn(-(double)unfk, sp.b[0][k]);
+      ch = __dadd_rn(ch, out.hold[k]);
+      cb = __dadd_rn(cb, out.back[k]);
     }
   }
-  out.reward = ch + cb;
+  out.reward = __dadd_rn(ch, cb);
 
   e.lat[0] = d_next;                                                       // Node.update_demand (:266-268)
   // ---- next period (envs.py:96-101)

@@ -23,7 +23,7 @@ namespace sn {
 constexpr int kGI = 3;                                   // live slips per arc after before_action (Li - 1 <= 3)
 constexpr int kGS = 4;                                   // shipment slots per arc
 constexpr int kGStateWords = 28 + kF * kGI + kF * kGS + 1;   // 57
-constexpr int kGInitWords = 4 + 4 * kF + 4 * kF;             // 36
+constexpr int kGInitWords = kF + 4 * kF + 4 * kF;            // 36 (72 with eight nodes)
 
 template <typename T>
 struct GEnv {
@@ -157,12 +157,12 @@ __device__ __forceinline__ void genv_step(GEnv<T>& e, const DevSpec<T>& sp, int 
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     const T unfk = (k == 0) ? e.unf_ind : e.B[k - 1];
-    out.hold[k] = -(double)e.inv[k] * sp.h[item][k];        // item: cost vector of this chain (0 for single-item batches)
-    out.back[k] = -(double)unfk * sp.b[item][k];
-    ch += out.hold[k];
-    cb += out.back[k];
+    out.hold[k] = __dmul_rn(-(double)e.inv[k], sp.h[item][k]);        // item: cost vector of this chain (0 for single-item batches)
+    out.back[k] = __dmul_rn(-(double)unfk, sp.b[item][k]);
+    ch = __dadd_rn(ch, out.hold[k]);
+    cb = __dadd_rn(cb, out.back[k]);
   }
-  out.reward = ch + cb;
+  out.reward = __dadd_rn(ch, cb);
 
   e.lat[0] = d_next;
   if (!terminal) {

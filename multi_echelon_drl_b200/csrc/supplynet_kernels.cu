@@ -61,12 +61,13 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // 32*od floats in the row-major output.  Lanes deposit their `od` floats in shared memory
 // (stride od words: conflict-free for od = 7, 21 and for od = 28 written as float4), then lane 0
 // issues one bulk store.  Partial warps (tail of the batch) and unaligned outputs use plain stores.
+constexpr int kObsMax = 7 * kF;       // floats of the widest observation row (28; 56 in eight-node builds)
 struct ObsStager {
-  float* smem;     // this warp's staging area: [2][32*28] floats
+  float* smem;     // this warp's staging area: [2][32*kObsMax] floats
   int lane;
   __device__ __forceinline__ ObsStager(float* block_smem) {
     lane = threadIdx.x & 31;
-    smem = block_smem + (threadIdx.x >> 5) * (2 * 32 * 28);
+    smem = block_smem + (threadIdx.x >> 5) * (2 * 32 * kObsMax);
   }
   // Staging row of this lane in buffer `buf`.  `buf` must alternate 0/1 between consecutive stores of the same
   // warp (at most one earlier bulk store, the one that used the other buffer, may still be reading shared memory);
@@ -74,13 +75,13 @@ struct ObsStager {
   __device__ __forceinline__ float* begin(int od, int buf) {
     if (lane == 0) bulk_wait_read<1>();
     __syncwarp();
-    return smem + buf * (32 * 28) + lane * od;
+    return smem + buf * (32 * kObsMax) + lane * od;
   }
   __device__ __forceinline__ void commit(float* gdst_warp, int od, int buf) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      bulk_store_s2g(gdst_warp, smem + buf * (32 * 28), (uint32_t)(32 * od * sizeof(float)));
+      bulk_store_s2g(gdst_warp, smem + buf * (32 * kObsMax), (uint32_t)(32 * od * sizeof(float)));
       bulk_commit();
     }
   }
@@ -450,7 +451,10 @@ k_step(const __grid_constant__ DevSpec<T> sp, int64_t n, int64_t ld, int period_
     v[0] = valid ? 1.0 : 0.0;
     v[1] = so.reward;
 #pragma unroll
-    for (int k = 0; k < kF; ++k) { v[2 + k] = so.hold[k]; v[6 + k] = so.back[k]; }
+    for (int k = 0; k < 4; ++k) {          // per-facility sums: four-node builds only (like the lane-per-node kernels)
+      v[2 + k] = kF == 4 ? so.hold[k] : 0.0;
+      v[6 + k] = kF == 4 ? so.back[k] : 0.0;
+    }
     // episode moments (Monitor's episode statistics) when this step ends the episode
     const bool ep = valid && terminal && out.ep_return != nullptr;
     const double ret = ep ? out.ep_return[env] : 0.0;
@@ -555,8 +559,10 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
     if (!Ops::kWide) qover |= qty_mask_over(qty_mask_state<T>(e));
     acc[0] += 1.0;
     acc[1] += so.reward;
+    if (kF == 4) {
 #pragma unroll
-    for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
+      for (int k = 0; k < 4; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
+    }
     if (out.traj_reward != nullptr && valid) out.traj_reward[(int64_t)s * n + env] = (float)so.reward;
     if (out.traj_obs != nullptr)
       write_obs<IDENT>(st, e, sp, terminal, out.traj_obs + (int64_t)s * n * od, env, n, od, valid, s & 1, use_tma != 0);
@@ -599,8 +605,11 @@ SN_PRAGMA_UNROLL(SN_ROLLOUT_UNROLL)
 #define SN_ROLLOUT_ARGS sp, pol, n, ld, period0, n_steps, state, demand, actions, out, use_tma, init, obs0
 
 // tuned beer-game chain: 7 blocks of 64 threads per SM: 65,536 envs = 1,024 blocks fit the 148 SMs in ONE wave
+#ifndef SN_ROLLOUT_MINB8
+#define SN_ROLLOUT_MINB8 4              // eight-node specialised builds: up to 255 registers per thread
+#endif
 template <typename T, int POLICY, bool IDENT, bool MULTI, typename Ops>
-__global__ void __launch_bounds__(kRolloutBlock, 448 / kRolloutBlock) k_rollout(SN_ROLLOUT_PARAMS) {
+__global__ void __launch_bounds__(kRolloutBlock, kF == 4 ? 448 / kRolloutBlock : SN_ROLLOUT_MINB8) k_rollout(SN_ROLLOUT_PARAMS) {
   extern __shared__ __align__(16) float smem_f[];
   __shared__ double red[(kRolloutBlock / 32) * 14];
   rollout_body<T, POLICY, IDENT, MULTI, Ops>(SN_ROLLOUT_ARGS, smem_f, red);
@@ -987,10 +996,10 @@ int validate(const sn_spec* s, int dtype) {
   }
 #ifdef SN_STATIC_TOPO
   {   // a specialised build serves exactly the network it was compiled for (specialize.py)
-    if (!is_tree(s) || is_net(s)) return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only");
+    if (!is_tree(s) || s->n_facilities > sn::kF) return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only");
     const auto d = lower<int32_t>(s);
     bool same = d.nf == sn::st_nf() && d.max_rank == sn::st_max_rank();
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < sn::kF; ++k)
       same = same && d.sup[k] == sn::st_sup(k) && d.rank[k] == sn::st_rank(k) && d.lat_src[k] == sn::st_lat(k) &&
              d.li[k] == sn::st_li(k) && d.ls[k] == sn::st_ls(k);
     if (!same) return fail(SN_ERR_UNSUPPORTED, "this specialised build was compiled for another network");
@@ -1009,11 +1018,12 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   sn::DevSpec<T> d;
   std::memset(&d, 0, sizeof(d));
   const int nf = s->n_facilities;
-  const int std_li[4] = {2, 2, 2, 1};
-  int lo = 4;
+  constexpr int KF = sn::kF;                    // 4; 8 in a library specialised for a tree of five to eight nodes
+  const int std_li[8] = {2, 2, 2, 1, 1, 1, 1, 1};
+  int lo = KF;
   d.nf = nf;
   d.big = big_quantity<T>();
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KF; ++k) {
     const bool real = k < nf;
     // phantom nodes (k >= nf): a target far below any inventory position makes their order clip to 0,
     // zero cost coefficients keep them out of the reward, any valid lead times will do
@@ -1049,14 +1059,14 @@ sn::DevSpec<T> lower(const sn_spec* s) {
   d.t_max = s->max_episode_steps;
   // topology tables (supplynet_tree.cuh); a chain is the tree k -> k+1 with the retailer as the only source
   const bool tree = is_tree(s);
-  int first_agent_pos = 4;
+  int first_agent_pos = KF;
   for (int i = 0; i < s->n_agents; ++i) {
     const int op = tree ? s->order_pos[s->agents[i]] : s->agents[i];
     first_agent_pos = op < first_agent_pos ? op : first_agent_pos;
   }
   d.n_src = 0;
   d.max_rank = 0;
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KF; ++k) {
     const bool real = k < nf;
     d.sup[k] = !real ? -1 : tree ? s->supplier[k] : (k + 1 < nf ? k + 1 : -1);
     d.rank[k] = (real && tree && d.sup[k] >= 0) ? s->customer_rank[k] : 0;   // the external supplier serves all at once
@@ -1066,13 +1076,13 @@ sn::DevSpec<T> lower(const sn_spec* s) {
     d.pre[k] = real && (tree ? s->order_pos[k] : k) < first_agent_pos ? 1 : 0;
     d.lat_src[k] = -1;
   }
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KF; ++k) {
     for (int j = 0; j < 4; ++j) d.m_ls[k][j] = (T)(j == d.ls[k] - 1 ? 1 : 0);
     for (int j = 0; j < 3; ++j) d.m_li[k][j] = (T)(j == d.li[k] - 2 ? 1 : 0);
     d.m_li1[k] = (T)(d.li[k] == 1 ? 1 : 0);
-    for (int j = 0; j < 4; ++j) d.m_sup[k][j] = (T)(d.sup[k] == j ? 1 : 0);
+    for (int j = 0; j < KF; ++j) d.m_sup[k][j] = (T)(d.sup[k] == j ? 1 : 0);
     d.m_ext[k] = (T)(d.sup[k] < 0 ? 1 : 0);
-    for (int r = 0; r < 3; ++r) d.m_rank[r][k] = (T)(d.rank[k] == r ? 1 : 0);
+    for (int r = 0; r < KF - 1; ++r) d.m_rank[r][k] = (T)(d.rank[k] == r ? 1 : 0);
   }
   for (int j = 0; j < nf; ++j) {          // the customer latest in the order sequence provides latest_demand
     int best = -1;
@@ -1080,8 +1090,8 @@ sn::DevSpec<T> lower(const sn_spec* s) {
       if (d.sup[c] == j && (best < 0 || (tree ? s->order_pos[c] > s->order_pos[best] : c > best))) best = c;
     d.lat_src[j] = best;
   }
-  for (int j = 0; j < 4; ++j)
-    for (int k = 0; k < 4; ++k) d.m_lat[j][k] = (T)(d.lat_src[j] == k ? 1 : 0);
+  for (int j = 0; j < KF; ++j)
+    for (int k = 0; k < KF; ++k) d.m_lat[j][k] = (T)(d.lat_src[j] == k ? 1 : 0);
   return d;
 }
 
@@ -1193,10 +1203,15 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // always a multiple of 16) and a 16-byte multiple size.
 inline int tma_ok(const float* obs) { return obs != nullptr && aligned16(obs) ? 1 : 0; }
 
-constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * 28 * sizeof(float);                 // 28,672 B
-constexpr size_t kRolloutSmem = (sn::kRolloutBlock / 32) * 2 * 32 * 28 * sizeof(float);         // 14,336 B
+constexpr size_t kObsSmem = sn::kWarpsPerBlock * 2 * 32 * sn::kObsMax * sizeof(float);        // 28,672 B
+constexpr size_t kRolloutSmem = (sn::kRolloutBlock / 32) * 2 * 32 * sn::kObsMax * sizeof(float); // 14,336 B
 
 inline unsigned grid_for(int64_t n, int block = sn::kBlock) { return (unsigned)((n + block - 1) / block); }
+// eight-node builds stage 56-float observation rows: more than the 48 KB of dynamic shared memory a kernel gets unasked
+template <typename K>
+inline void allow_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 // net kernels: eight lanes per env
 inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetBlock - 1) / sn::kNetBlock); }
 
@@ -1228,7 +1243,7 @@ int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const
   }
 #endif
   const auto d = lower<T>(spec);
-#define SN_CALL(ID, OPS) sn::k_reset<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs))
+#define SN_CALL(ID, OPS) allow_smem(sn::k_reset<T, ID, OPS>, kObsSmem); sn::k_reset<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)init, (const T*)demand0, (T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
 #undef SN_CALL
   return cuda_ok("sn_reset launch");
@@ -1243,7 +1258,7 @@ int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, fl
   }
 #endif
   const auto d = lower<T>(spec);
-#define SN_CALL(ID, OPS) sn::k_observe<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs))
+#define SN_CALL(ID, OPS) allow_smem(sn::k_observe<T, ID, OPS>, kObsSmem); sn::k_observe<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, (const T*)state, obs, tma_ok(obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
 #undef SN_CALL
   return cuda_ok("sn_observe launch");
@@ -1376,7 +1391,7 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
     return launch_step_tiled<T, false>(d, n, ld, period, state, actions, demand, out, st);
   }
 #endif
-#define SN_CALL(ID, OPS) sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out, tma_ok(out.obs))
+#define SN_CALL(ID, OPS) allow_smem(sn::k_step<T, ID, OPS>, kObsSmem); sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out, tma_ok(out.obs))
   SN_DISPATCH_TOPO(spec, SN_CALL);
 #undef SN_CALL
   return cuda_ok("sn_step launch");

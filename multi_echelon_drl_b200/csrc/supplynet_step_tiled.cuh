@@ -286,7 +286,7 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         acc[0] += 1.0;
         acc[1] += so.reward;
 #pragma unroll
-        for (int k = 0; k < kF; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
+        for (int k = 0; k < 4; ++k) { acc[2 + k] += so.hold[k]; acc[6 + k] += so.back[k]; }
         if (terminal && out.ep_return != nullptr) { acc[10] += 1.0; acc[11] += ret_ep; acc[12] += ret_ep * ret_ep; }
         if (over) acc[13] += 1.0;
       }

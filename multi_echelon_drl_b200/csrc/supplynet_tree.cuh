@@ -27,17 +27,33 @@
 
 namespace sn {
 
-constexpr int kTStateWords = 64;
+// state / init word maps.  Four nodes: the map above (64 words).  Eight nodes (specialised builds only): the map of the
+// lane-per-node kernels, 16 words per node (supplynet_net.cuh), so that reset / observe of the general library and
+// the specialised step / rollout share one state buffer.  Init words: inv[kF]; so[k][0..3] at kF+4k; sh[k][0..3]
+// at 5kF+4k in both (36 / 72 words).
+constexpr int kTStateWords = kF == 4 ? 64 : 16 * kF;
+__host__ __device__ constexpr int tw_inv(int k) { return kF == 4 ? 7 * k : 16 * k; }
+__host__ __device__ constexpr int tw_unf(int k) { return tw_inv(k) + 1; }
+__host__ __device__ constexpr int tw_lat(int k) { return tw_inv(k) + 2; }
+__host__ __device__ constexpr int tw_U(int k, int j) { return tw_inv(k) + 3 + j; }
+__host__ __device__ constexpr int tw_info(int k, int j) { return kF == 4 ? 28 + kGI * k + j : 16 * k + 7 + j; }
+__host__ __device__ constexpr int tw_ship(int k, int j) { return kF == 4 ? 40 + kGS * k + j : 16 * k + 10 + j; }
+__host__ __device__ constexpr int tw_B(int k) { return kF == 4 ? 56 + k : 16 * k + 14; }
+__host__ __device__ constexpr int tw_dem(int k) { return kF == 4 ? 60 + k : 16 * k + 15; }
 
 #ifdef SN_STATIC_TOPO
 constexpr bool kStaticTopo = true;
-__host__ __device__ constexpr int st4(int k, int a, int b, int c, int d) { return k == 0 ? a : k == 1 ? b : k == 2 ? c : d; }
+__host__ __device__ constexpr int st8(int k, int a, int b, int c, int d, int e, int f, int g, int h) {
+  return k == 0 ? a : k == 1 ? b : k == 2 ? c : k == 3 ? d : k == 4 ? e : k == 5 ? f : k == 6 ? g : h;
+}
+#define SN_ST8(NAME) st8(k, SN_ST_##NAME##0, SN_ST_##NAME##1, SN_ST_##NAME##2, SN_ST_##NAME##3, SN_ST_##NAME##4, \
+                         SN_ST_##NAME##5, SN_ST_##NAME##6, SN_ST_##NAME##7)
 __host__ __device__ constexpr int st_nf() { return SN_ST_NF; }
-__host__ __device__ constexpr int st_sup(int k) { return st4(k, SN_ST_SUP0, SN_ST_SUP1, SN_ST_SUP2, SN_ST_SUP3); }
-__host__ __device__ constexpr int st_rank(int k) { return st4(k, SN_ST_RANK0, SN_ST_RANK1, SN_ST_RANK2, SN_ST_RANK3); }
-__host__ __device__ constexpr int st_lat(int k) { return st4(k, SN_ST_LAT0, SN_ST_LAT1, SN_ST_LAT2, SN_ST_LAT3); }
-__host__ __device__ constexpr int st_li(int k) { return st4(k, SN_ST_LI0, SN_ST_LI1, SN_ST_LI2, SN_ST_LI3); }
-__host__ __device__ constexpr int st_ls(int k) { return st4(k, SN_ST_LS0, SN_ST_LS1, SN_ST_LS2, SN_ST_LS3); }
+__host__ __device__ constexpr int st_sup(int k) { return SN_ST8(SUP); }
+__host__ __device__ constexpr int st_rank(int k) { return SN_ST8(RANK); }
+__host__ __device__ constexpr int st_lat(int k) { return SN_ST8(LAT); }
+__host__ __device__ constexpr int st_li(int k) { return SN_ST8(LI); }
+__host__ __device__ constexpr int st_ls(int k) { return SN_ST8(LS); }
 __host__ __device__ constexpr int st_max_rank() { return SN_ST_MAX_RANK; }
 #else
 constexpr bool kStaticTopo = false;
@@ -100,17 +116,17 @@ template <typename T>
 __device__ __forceinline__ void tenv_from_words(TEnv<T>& e, const T (&w)[kTStateWords]) {
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
-    e.inv[k] = w[7 * k];
-    e.unf_ind[k] = w[7 * k + 1];
-    e.latI[k] = w[7 * k + 2];
+    e.inv[k] = w[tw_inv(k)];
+    e.unf_ind[k] = w[tw_unf(k)];
+    e.latI[k] = w[tw_lat(k)];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) e.U[k][j] = w[7 * k + 3 + j];
+    for (int j = 0; j < 4; ++j) e.U[k][j] = w[tw_U(k, j)];
 #pragma unroll
-    for (int j = 0; j < kGI; ++j) e.info[k][j] = w[28 + kGI * k + j];
+    for (int j = 0; j < kGI; ++j) e.info[k][j] = w[tw_info(k, j)];
 #pragma unroll
-    for (int j = 0; j < kGS; ++j) e.ship[k][j] = w[40 + kGS * k + j];
-    e.B[k] = w[56 + k];
-    e.dem[k] = w[60 + k];
+    for (int j = 0; j < kGS; ++j) e.ship[k][j] = w[tw_ship(k, j)];
+    e.B[k] = w[tw_B(k)];
+    e.dem[k] = w[tw_dem(k)];
   }
 }
 
@@ -118,17 +134,17 @@ template <typename T>
 __device__ __forceinline__ void tenv_to_words(const TEnv<T>& e, T (&w)[kTStateWords]) {
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
-    w[7 * k] = e.inv[k];
-    w[7 * k + 1] = e.unf_ind[k];
-    w[7 * k + 2] = e.latI[k];
+    w[tw_inv(k)] = e.inv[k];
+    w[tw_unf(k)] = e.unf_ind[k];
+    w[tw_lat(k)] = e.latI[k];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[7 * k + 3 + j] = e.U[k][j];
+    for (int j = 0; j < 4; ++j) w[tw_U(k, j)] = e.U[k][j];
 #pragma unroll
-    for (int j = 0; j < kGI; ++j) w[28 + kGI * k + j] = e.info[k][j];
+    for (int j = 0; j < kGI; ++j) w[tw_info(k, j)] = e.info[k][j];
 #pragma unroll
-    for (int j = 0; j < kGS; ++j) w[40 + kGS * k + j] = e.ship[k][j];
-    w[56 + k] = e.B[k];
-    w[60 + k] = e.dem[k];
+    for (int j = 0; j < kGS; ++j) w[tw_ship(k, j)] = e.ship[k][j];
+    w[tw_B(k)] = e.B[k];
+    w[tw_dem(k)] = e.dem[k];
   }
 }
 
@@ -173,8 +189,8 @@ __device__ __forceinline__ void tenv_reset(TEnv<T>& e, const DevSpec<T>& sp, con
     T so[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      so[j] = in[4 + 4 * k + j] * mask_of<T>(real && j < li);
-      sh[j] = in[20 + 4 * k + j] * mask_of<T>(real && j < ls);
+      so[j] = in[kF + 4 * k + j] * mask_of<T>(real && j < li);
+      sh[j] = in[5 * kF + 4 * k + j] * mask_of<T>(real && j < ls);
     }
     e.inv[k] = real ? in[k] : sp.big;
     T seq[5];
@@ -256,12 +272,12 @@ __device__ __forceinline__ void tenv_step(TEnv<T>& e, const DevSpec<T>& sp, cons
 #pragma unroll
   for (int k = 0; k < kF; ++k) {
     const T unfk = customers_backlog(e, sp, k) + e.unf_ind[k];
-    out.hold[k] = -(double)e.inv[k] * sp.h[0][k];
-    out.back[k] = -(double)unfk * sp.b[0][k];
-    ch += out.hold[k];
-    cb += out.back[k];
+    out.hold[k] = __dmul_rn(-(double)e.inv[k], sp.h[0][k]);
+    out.back[k] = __dmul_rn(-(double)unfk, sp.b[0][k]);
+    ch = __dadd_rn(ch, out.hold[k]);
+    cb = __dadd_rn(cb, out.back[k]);
   }
-  out.reward = ch + cb;
+  out.reward = __dadd_rn(ch, cb);
 #pragma unroll
   for (int k = 0; k < kF; ++k) e.dem[k] = d_next.v[k];                         // Node.update_demand
   if (!terminal) {

@@ -31,29 +31,30 @@ _loaded = {}
 
 
 def tables(spec: ScenarioSpec) -> dict:
-    """The tables `lower()` derives from an sn_spec (csrc/supplynet_kernels.cu), for trees of up to four nodes;
-    phantom entries (k >= n_facilities) as there: external supplier, rank 0, lead times 2,2,2,1 / 2."""
-    if not spec.is_tree or spec.n_facilities > 4:
-        raise ValueError("specialisation is offered for distribution trees of up to four nodes")
+    """The tables `lower()` derives from an sn_spec (csrc/supplynet_kernels.cu) for a tree of up to eight nodes, eight
+    entries each; phantom entries (k >= n_facilities) as there: external supplier, rank 0, lead times 2,2,2,1,1.. / 2.
+    Trees of five to eight nodes are compiled with eight facilities per thread (-DSN_KF=8)."""
+    if not spec.is_tree or spec.n_facilities > 8:
+        raise ValueError("specialisation is offered for distribution trees of up to eight nodes")
     nf = spec.n_facilities
-    sup = [spec.suppliers[k] if k < nf else -1 for k in range(4)]
-    rank = [spec.customer_rank[k] if (k < nf and sup[k] >= 0) else 0 for k in range(4)]
+    sup = [spec.suppliers[k] if k < nf else -1 for k in range(8)]
+    rank = [spec.customer_rank[k] if (k < nf and sup[k] >= 0) else 0 for k in range(8)]
     lat = []
-    for j in range(4):
+    for j in range(8):
         best = -1
         for c in range(nf):
             if j < nf and sup[c] == j and (best < 0 or spec.order_pos[c] > spec.order_pos[best]):
                 best = c
         lat.append(best)
-    std_li = (2, 2, 2, 1)
-    li = [spec.info_leadtime[k] if k < nf else std_li[k] for k in range(4)]
-    ls = [spec.ship_leadtime[k] if k < nf else 2 for k in range(4)]
-    return dict(nf=nf, sup=sup, rank=rank, lat=lat, li=li, ls=ls, max_rank=max(rank))
+    std_li = (2, 2, 2, 1, 1, 1, 1, 1)
+    li = [spec.info_leadtime[k] if k < nf else std_li[k] for k in range(8)]
+    ls = [spec.ship_leadtime[k] if k < nf else 2 for k in range(8)]
+    return dict(nf=nf, kf=4 if nf <= 4 else 8, sup=sup, rank=rank, lat=lat, li=li, ls=ls, max_rank=max(rank))
 
 
 def key(spec: ScenarioSpec, dtype: str) -> str:
     t = tables(spec)
-    text = f"{t['nf']}|{t['sup']}|{t['rank']}|{t['lat']}|{t['li']}|{t['ls']}|{_DT[dtype]}|abi{_lib.ABI_VERSION}"
+    text = f"{t['nf']}|{t['kf']}|{t['sup']}|{t['rank']}|{t['lat']}|{t['li']}|{t['ls']}|{_DT[dtype]}|abi{_lib.ABI_VERSION}"
     return hashlib.sha1(text.encode()).hexdigest()[:12]
 
 
@@ -71,18 +72,18 @@ def build(spec: ScenarioSpec, dtype: str = "int32", force: bool = False) -> str:
     os.makedirs(SPEC_DIR, exist_ok=True)
     t = tables(spec)
     defs = ["-DSN_STATIC_TOPO", "-DSN_TREE_ONLY", f"-DSN_ONLY_DTYPE={_DT[dtype]}", f"-DSN_ST_NF={t['nf']}",
-            f"-DSN_ST_MAX_RANK={t['max_rank']}"]
+            f"-DSN_ST_MAX_RANK={t['max_rank']}", f"-DSN_KF={t['kf']}"]
     for name, vals in (("SUP", t["sup"]), ("RANK", t["rank"]), ("LAT", t["lat"]), ("LI", t["li"]), ("LS", t["ls"])):
-        defs += [f"-DSN_ST_{name}{k}={vals[k]}" for k in range(4)]
+        defs += [f"-DSN_ST_{name}{k}={vals[k]}" for k in range(8)]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-           "-diag-suppress", "177", *defs, "-shared", "-o", out, src]
+           "-diag-suppress", "177", *defs, *os.environ.get("SN_SPEC_EXTRA_FLAGS", "").split(), "-shared", "-o", out, src]
     subprocess.run(cmd, check=True, cwd=CSRC)
     return out
 
 
 def load(spec: ScenarioSpec, dtype: str) -> Optional[C.CDLL]:
     """The specialised library for this network and quantity type if it has been built, else None."""
-    if not spec.is_tree or spec.n_facilities > 4 or os.environ.get("SN_NO_SPECIALIZED") == "1":
+    if not spec.is_tree or spec.n_facilities > 8 or os.environ.get("SN_NO_SPECIALIZED") == "1":
         return None
     path = lib_path(spec, dtype)
     if path in _loaded:

@@ -13,11 +13,19 @@ tree = tree_spec([dict(name="shop", demand=(0, 8), target=19), dict(name="dist_a
 star = tree_spec([dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=12), dict(name="r3", demand=(0, 3), target=9),
                   dict(name="hub", target=40)],
                  [("ext", "hub", 2, 3), ("hub", "r3", 1, 1), ("hub", "r1", 2, 2), ("hub", "r2", 2, 1)], ["r1", "r2", "r3", "hub"], True)
-SPECS = {"tree, 2 levels, 2 sources": tree, "star, 3 retailers": star}
+big = tree_spec([dict(name="hub", target=60), dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=14),
+                 dict(name="r3", demand=(0, 4), target=10), dict(name="r4", demand=(0, 3), target=8), dict(name="r5", demand=(0, 2), target=6),
+                 dict(name="factory", target=40), dict(name="annex", demand=(0, 5), target=12)],
+                [("ext", "factory", 1, 2), ("factory", "annex", 1, 3), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1), ("hub", "r1", 2, 2),
+                 ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)],
+                ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"], True)
+SPECS = {"tree, 2 levels, 2 sources": tree, "star, 3 retailers": star, "8 nodes: factory, annex, hub, 5 retailers": big}
+if os.environ.get("PROBE_ONLY"):
+    SPECS = {k: v for k, v in SPECS.items() if os.environ["PROBE_ONLY"] in k}
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     for name, sp in SPECS.items():
-        print(name, specialize.build(sp, "int32"))
+        print(name, specialize.build(sp, "int32", force=bool(os.environ.get("SN_SPEC_EXTRA_FLAGS"))))
     sys.exit(0)
 
 import numpy as np, torch
@@ -48,6 +56,6 @@ for name, sp in SPECS.items():
         steps = [tuple(x.clone() for x in sim.step(acts[t])[:2]) for t in range(5)]
         res[mode] = dict(ms=a.elapsed_time(b) / 20, obs=obs.clone(), rew=rew.clone(), ret=sim.ep_return.clone(), state=sim.state.clone(), steps=steps)
     g, s = res["general"], res["specialised"]
-    same = all(torch.equal(g[k], s[k]) for k in ("obs", "rew", "state")) and all(
+    same = all(torch.equal(g[k], s[k]) for k in ("obs", "rew", "state", "ret")) and all(
         torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) for x, y in zip(g["steps"], s["steps"]))
     print(f"{name:28s} general {g['ms']:.4f} ms   specialised {s['ms']:.4f} ms   bit-identical: {same}")

@@ -33,10 +33,9 @@ def _sim(case, n, dtype="int32", lib="general"):
 @pytest.mark.parametrize("lib", ["general", "specialised"])
 @pytest.mark.parametrize("case", TREE_CASES + BIG_TREE_CASES, ids=[c["id"] for c in TREE_CASES + BIG_TREE_CASES])
 def test_tree_step_and_rollout_match_reference_golden(case, lib):
-    """Up to four nodes: register-resident tree kernels (64 state words), general and specialised for the network;
-    five to eight: lane-per-node kernels (128)."""
-    if lib == "specialised" and len(case["names"]) > 4:
-        pytest.skip("specialised builds exist for trees of up to four nodes")
+    """Up to four nodes: register-resident tree kernels (64 state words); five to eight: lane-per-node kernels (128
+    state words).  Each also through the library specialised for the network (register-resident for every size: eight
+    facilities per thread for the larger ones, same 128-word state buffer)."""
     sim = _sim(case, 1, lib=lib)
     N = len(case["names"])
     half = 8 if N > 4 else 4                      # rows of the per-facility cost output: holding[half], backorder[half]
@@ -68,8 +67,8 @@ def test_tree_batch_vs_oracle(cid, dtype, lib):
     from multi_echelon_drl_b200.simulator import BasePolicyParams, heuristic_actions
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
     case = BIG_TREE_CASES[cid - 1000] if cid >= 1000 else TREE_CASES[cid]      # 1000+: five to eight nodes
-    if lib == "specialised" and (cid >= 1000 or dtype != "int32"):
-        pytest.skip("prebuilt specialised libraries: int32, trees of up to four nodes")
+    if lib == "specialised" and dtype != "int32":
+        pytest.skip("prebuilt specialised libraries are int32")
     n = 3001
     sim = _sim(case, n, dtype, lib=lib)
     init, demand = bulk_episode_inputs(sim.spec, n, np.random.RandomState(cid))
