@@ -9,8 +9,10 @@ beer-game chain.  A deployment that simulates one network millions of times can 
 compiles `csrc/supplynet_kernels.cu` once more with -DSN_STATIC_TOPO -DSN_ST_*=... (nvcc, sm_100a) into
 `csrc/spec/libsupplynet_tree_<key>.so`, a library with the same C ABI that serves exactly that network and refuses
 any other.  `BatchedSupplyNetwork` loads it, when present, for `sn_step` / `sn_rollout` / `sn_episode` (reset and
-observe stay on the general library: same state layout).  Results are bit-identical to the general kernels
-(tests/test_gpu_trees.py); nothing is compiled at run time unless `build()` is called.
+observe stay on the general library: same state layout).  Trees of five to eight nodes are compiled with eight
+facilities per thread (-DSN_KF=8): a register-resident env where the general library spreads it over eight lanes.
+Results are bit-identical to the general kernels (tests/test_gpu_trees.py); nothing is compiled at run time unless
+`build()` is called.
 """
 from __future__ import annotations
 
