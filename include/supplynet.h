@@ -318,6 +318,14 @@ int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, in
                         uint64_t offset, void* stream);
 int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
                               uint64_t offset, void* stream);
+/* The same fills with the stream position in device memory: element i is drawn at counter offset *counter + offset + i/4
+ * (counter: device uint64, may be NULL = 0).  Identical launches then draw fresh tables at every replay of a captured
+ * CUDA graph; sn_counter_add advances the position (one thread) between replays. */
+int32_t sn_fill_uniform_at(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
+                           const uint64_t* counter, uint64_t offset, void* stream);
+int32_t sn_fill_normal_demand_at(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
+                                 const uint64_t* counter, uint64_t offset, void* stream);
+int32_t sn_counter_add(uint64_t* counter, uint64_t delta, void* stream);
 
 /* ---- episode tables: row-major per-env arrays -> the structure-of-arrays rows the kernels read ----------------
  * What the reference's reset leaves per env (initial inventories / pipelines, network_components.py:138-168,

@@ -101,6 +101,9 @@ SIGNATURES = {
     "sn_vecnorm_apply": (_I32, [_I64, _I32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_double, _I32, _P, _P]),
     "sn_fill_uniform": (_I32, [_I32, _P, _I64, _I32, _I32, C.c_uint64, C.c_uint64, _P]),
     "sn_fill_normal_demand": (_I32, [_I32, _P, _I64, C.c_double, C.c_double, C.c_uint64, C.c_uint64, _P]),
+    "sn_fill_uniform_at": (_I32, [_I32, _P, _I64, _I32, _I32, C.c_uint64, _P, C.c_uint64, _P]),
+    "sn_fill_normal_demand_at": (_I32, [_I32, _P, _I64, C.c_double, C.c_double, C.c_uint64, _P, C.c_uint64, _P]),
+    "sn_counter_add": (_I32, [_P, C.c_uint64, _P]),
     "sn_pack_rows": (_I32, [_I32, _P, _I64, _I32, _I64, _I32, _P, _I32, _I64, _I64, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -27,11 +27,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_fill_uniform(T* __restrict__ dst, int64_t count, int32_t lo, uint32_t range, uint64_t seed, uint64_t offset) {
+k_fill_uniform(T* __restrict__ dst, int64_t count, int32_t lo, uint32_t range, uint64_t seed, uint64_t offset,
+               const uint64_t* __restrict__ counter) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // quad index
   const int64_t i = q * 4;
   if (i >= count) return;
-  const uint64_t c = offset + (uint64_t)q;
+  const uint64_t c = offset + (uint64_t)q + (counter != nullptr ? *counter : 0ull);   // device-side stream position
   const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t u[4] = {r.x, r.y, r.z, r.w};
@@ -50,11 +51,12 @@ k_fill_uniform(T* __restrict__ dst, int64_t count, int32_t lo, uint32_t range, u
 // round(max(mean + sd * z, 0)) with z ~ N(0,1) by Box-Muller (utils/demands.py:47)
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_fill_normal_demand(T* __restrict__ dst, int64_t count, float mean, float sd, uint64_t seed, uint64_t offset) {
+k_fill_normal_demand(T* __restrict__ dst, int64_t count, float mean, float sd, uint64_t seed, uint64_t offset,
+                     const uint64_t* __restrict__ counter) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = q * 4;
   if (i >= count) return;
-  const uint64_t c = offset + (uint64_t)q;
+  const uint64_t c = offset + (uint64_t)q + (counter != nullptr ? *counter : 0ull);
   const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float k = 2.3283064365386963e-10f;                   // 2^-32
@@ -68,6 +70,8 @@ k_fill_normal_demand(T* __restrict__ dst, int64_t count, float mean, float sd, u
   for (int j = 0; j < 4; ++j)
     if (i + j < count) dst[i + j] = (T)rintf(fmaxf(mean + sd * z[j], 0.0f));
 }
+
+__global__ void k_counter_add(uint64_t* counter, uint64_t delta) { *counter += delta; }
 
 // Row-major per-env table [n][width] (what the reference's reset produces per env: init values, demand stream) ->
 // structure-of-arrays rows [rows >= width][ld] of the quantity type, converting on the way: 32 x 32 tiles through
@@ -99,8 +103,8 @@ k_pack_rows(const S* __restrict__ src, int64_t n, int width, int64_t src_stride,
 
 extern "C" {
 
-int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
-                        uint64_t offset, void* stream) {
+int32_t sn_fill_uniform_at(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
+                           const uint64_t* counter, uint64_t offset, void* stream) {
   using sn_detail::fail;
   if (!dst || count < 1 || high_exclusive <= low) return fail(SN_ERR_INVALID, "sn_fill_uniform: dst NULL, count < 1 or empty range");
   if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) return fail(SN_ERR_INVALID, "sn_fill_uniform: dst must be 16-byte aligned");
@@ -108,9 +112,29 @@ int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, in
   const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case SN_I32: snr::k_fill_uniform<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, low, range, seed, offset); break;
-    case SN_F32: snr::k_fill_uniform<float><<<grid, 256, 0, st>>>((float*)dst, count, low, range, seed, offset); break;
-    case SN_F64: snr::k_fill_uniform<double><<<grid, 256, 0, st>>>((double*)dst, count, low, range, seed, offset); break;
+    case SN_I32: snr::k_fill_uniform<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, low, range, seed, offset, counter); break;
+    case SN_F32: snr::k_fill_uniform<float><<<grid, 256, 0, st>>>((float*)dst, count, low, range, seed, offset, counter); break;
+    case SN_F64: snr::k_fill_uniform<double><<<grid, 256, 0, st>>>((double*)dst, count, low, range, seed, offset, counter); break;
+    default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
+  }
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
+}
+
+int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, int32_t high_exclusive, uint64_t seed,
+                        uint64_t offset, void* stream) {
+  return sn_fill_uniform_at(dtype, dst, count, low, high_exclusive, seed, nullptr, offset, stream);
+}
+
+int32_t sn_fill_normal_demand_at(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
+                                 const uint64_t* counter, uint64_t offset, void* stream) {
+  using sn_detail::fail;
+  if (!dst || count < 1 || sd < 0) return fail(SN_ERR_INVALID, "sn_fill_normal_demand: dst NULL, count < 1 or negative sd");
+  const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case SN_I32: snr::k_fill_normal_demand<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, (float)mean, (float)sd, seed, offset, counter); break;
+    case SN_F32: snr::k_fill_normal_demand<float><<<grid, 256, 0, st>>>((float*)dst, count, (float)mean, (float)sd, seed, offset, counter); break;
+    case SN_F64: snr::k_fill_normal_demand<double><<<grid, 256, 0, st>>>((double*)dst, count, (float)mean, (float)sd, seed, offset, counter); break;
     default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
   }
   return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
@@ -118,17 +142,13 @@ int32_t sn_fill_uniform(int32_t dtype, void* dst, int64_t count, int32_t low, in
 
 int32_t sn_fill_normal_demand(int32_t dtype, void* dst, int64_t count, double mean, double sd, uint64_t seed,
                               uint64_t offset, void* stream) {
-  using sn_detail::fail;
-  if (!dst || count < 1 || sd < 0) return fail(SN_ERR_INVALID, "sn_fill_normal_demand: dst NULL, count < 1 or negative sd");
-  const unsigned grid = (unsigned)(((count + 3) / 4 + 255) / 256);
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (dtype) {
-    case SN_I32: snr::k_fill_normal_demand<int32_t><<<grid, 256, 0, st>>>((int32_t*)dst, count, (float)mean, (float)sd, seed, offset); break;
-    case SN_F32: snr::k_fill_normal_demand<float><<<grid, 256, 0, st>>>((float*)dst, count, (float)mean, (float)sd, seed, offset); break;
-    case SN_F64: snr::k_fill_normal_demand<double><<<grid, 256, 0, st>>>((double*)dst, count, (float)mean, (float)sd, seed, offset); break;
-    default: return sn_detail::fail(SN_ERR_INVALID, "sn_fill: unknown dtype %d", dtype);
-  }
-  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_fill: kernel launch failed");
+  return sn_fill_normal_demand_at(dtype, dst, count, mean, sd, seed, nullptr, offset, stream);
+}
+
+int32_t sn_counter_add(uint64_t* counter, uint64_t delta, void* stream) {
+  if (!counter) return sn_detail::fail(SN_ERR_INVALID, "sn_counter_add: counter is NULL");
+  snr::k_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  return cudaGetLastError() == cudaSuccess ? SN_OK : sn_detail::fail(SN_ERR_CUDA, "sn_counter_add: kernel launch failed");
 }
 
 int32_t sn_pack_rows(int32_t src_dtype, const void* src, int64_t n_envs, int32_t width, int64_t src_stride, int32_t dtype,

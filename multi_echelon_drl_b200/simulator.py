@@ -362,6 +362,8 @@ class BatchedSupplyNetwork:
         self.state.copy_(snap["state"]); self.demand.copy_(snap["demand"]); self.init.copy_(snap["init"])
         self.ep_return.copy_(snap["ep_return"])
         self.period, self.terminal = int(snap["period"]), bool(snap["terminal"])
+        if self._graph_period_valid:
+            self.ctl[_lib.SN_CTL_PERIOD:_lib.SN_CTL_PERIOD + 1].fill_(self.period)
 
 
 def heuristic_actions(policy: BasePolicyParams, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

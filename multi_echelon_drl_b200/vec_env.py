@@ -145,6 +145,10 @@ class SupplyNetVecEnv(_VecEnvBase):
     def _next_episode(self):
         sp, sim = self.spec, self.sim
         if self.episode_source == "device":
+            if getattr(self, "_tables_ahead", 0):      # run_policy_episodes left the next episode's tables in place
+                self._ctr += self._tables_ahead
+                self._tables_ahead = 0
+                return
             self._device_episode()
         elif self.episode_source == "numpy_bulk":
             init, demand = _dem.bulk_episode_inputs(sp, self.num_envs, self._rs)
@@ -153,18 +157,27 @@ class SupplyNetVecEnv(_VecEnvBase):
             init, demand = _dem.seeded_episode_inputs_from_streams(sp, self._streams)
             sim.load_episode(init, demand)
 
-    def _device_episode(self):
+    def _device_episode(self, counter=None, rel0=0, advance=True):
         """Same distributions as utils/demands.py / Arc.reset / Node.reset, drawn on the device with
         the library's Philox-4x32-10 counter streams directly in the structure-of-arrays layout (throughput
-        path; not stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity)."""
+        path; not stream-compatible with numpy - use episode_source='numpy_seeded' for reference parity).
+        The stream position is `self._ctr` (host) or, with `counter` (device uint64 tensor), *counter + rel0: the
+        form a captured graph replays.  Returns the number of counter steps one episode consumes."""
         sp, sim = self.spec, self.sim
         lib, dt, st = sim.lib, sim.dtype_code, sim._stream()
         a, b = sp.demand_params
         seed = self._seed & 0xFFFFFFFFFFFFFFFF
+        cptr = None if counter is None else C.c_void_p(counter.data_ptr())
+        pos = [rel0 if counter is not None else self._ctr]
 
         def fill_uniform(t, lo, hi):
-            _lib.check(lib.sn_fill_uniform(dt, C.c_void_p(t.data_ptr()), t.numel(), int(lo), int(hi), seed, self._ctr, st))
-            self._ctr += (t.numel() + 3) // 4
+            _lib.check(lib.sn_fill_uniform_at(dt, C.c_void_p(t.data_ptr()), t.numel(), int(lo), int(hi), seed, cptr, pos[0], st))
+            pos[0] += (t.numel() + 3) // 4
+
+        def fill_normal(t, mean, sd):
+            _lib.check(lib.sn_fill_normal_demand_at(dt, C.c_void_p(t.data_ptr()), t.numel(), float(mean), float(sd), seed,
+                                                    cptr, pos[0], st))
+            pos[0] += (t.numel() + 3) // 4
 
         # one launch per table, written in place in the structure-of-arrays layout (sn_fill_* in random_fill.cu)
         if sp.is_tree and len(set(sp.source_demand_params)) > 1:
@@ -177,18 +190,14 @@ class SupplyNetVecEnv(_VecEnvBase):
                 if sp.demand_pattern == "uniform":
                     fill_uniform(t, pa, int(pb) + 1)
                 elif sp.demand_pattern == "normal":
-                    _lib.check(lib.sn_fill_normal_demand(dt, C.c_void_p(t.data_ptr()), t.numel(), float(pa), float(pb),
-                                                         seed, self._ctr, st))
-                    self._ctr += (t.numel() + 3) // 4
+                    fill_normal(t, pa, pb)
                 else:
                     raise NotImplementedError("tree networks draw uniform or normal demand")
                 sim.demand[:, s].copy_(t)
         elif sp.demand_pattern == "uniform":
             fill_uniform(sim.demand, a, int(b) + 1)
         elif sp.demand_pattern == "normal":
-            _lib.check(lib.sn_fill_normal_demand(dt, C.c_void_p(sim.demand.data_ptr()), sim.demand.numel(), float(a),
-                                                 float(b), seed, self._ctr, st))
-            self._ctr += (sim.demand.numel() + 3) // 4
+            fill_normal(sim.demand, a, b)
         else:
             sim.demand[:4].fill_(4)
             sim.demand[4:].fill_(8)
@@ -200,6 +209,10 @@ class SupplyNetVecEnv(_VecEnvBase):
         else:
             sim.init.copy_(torch.as_tensor(_dem._fixed_init(sp), device=self.device).to(sim.tdtype)[:, None]
                            .expand(sim.init_words, sim.ld))
+        total = pos[0] - (rel0 if counter is not None else self._ctr)
+        if counter is None and advance:
+            self._ctr = pos[0]
+        return total
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
@@ -307,23 +320,65 @@ class SupplyNetVecEnv(_VecEnvBase):
         self._ring_pos = (self._ring_pos + 1) % self.kRing
         return self._ring[self._ring_pos]
 
-    def run_policy_episodes(self, policy, n_episodes: int = 1):
+    def run_policy_episodes(self, policy, n_episodes: int = 1, use_graph: bool = True):
         """Config-3 mode: play `n_episodes` whole episodes with a base-stock policy evaluated inside the
         rollout kernel (one `sn_episode` launch per episode, state on-chip), drawing fresh demand /
         initial states per episode from this env's episode source.  `policy` is a
         `utils.heuristics.BaseStockPolicy` or `simulator.BasePolicyParams`.  Returns the statistics
-        vector (float64 [16], see distributed.py) accumulated over the episodes, on the device."""
+        vector (float64 [16], see distributed.py) accumulated over the episodes, on the device.
+        `use_graph` (device episode source): pairs of episodes are replayed as ONE captured CUDA graph in which the
+        tables of the next episode are drawn (second set of buffers, parallel branch) while the current one is played -
+        the rollout is ALU-bound, the fills HBM-write-bound - and the Philox stream position lives in device memory
+        (`sn_fill_*_at`, `sn_counter_add`).  Same counters in the same order, hence the same episodes as the loop."""
         params = getattr(policy, "params", policy)
         sim = self.sim
         keep = sim.track_stats
         sim.track_stats = True
         sim.stats.zero_()
-        for _ in range(int(n_episodes)):
+        n_episodes = int(n_episodes)
+        done = 0
+        if use_graph and self.episode_source == "device" and n_episodes >= 2:
+            done = self._replay_episode_pairs(params, n_episodes // 2)
+        for _ in range(n_episodes - done):
             self._next_episode()
-            sim.episode(policy=params, write_state=False)      # statistics incl. episode moments accumulate in-kernel
+            sim.episode(policy=params, write_state=False)          # statistics incl. episode moments accumulate in-kernel
             self.episodes_done += self.num_envs
         sim.track_stats = keep
         return sim.stats
+
+    def _replay_episode_pairs(self, params, pairs: int) -> int:
+        sim, dev = self.sim, self.device
+        if not getattr(self, "_tables_ahead", 0):                  # tables of the next episode, position not yet advanced
+            self._tables_ahead = self._device_episode(advance=False)
+        per = self._tables_ahead
+        key = (bytes(params.c), sim.init.data_ptr(), sim.demand.data_ptr(), sim.track_stats)
+        if getattr(self, "_pair_key", None) != key:
+            if not hasattr(self, "_d_ctr"):
+                self._d_ctr = torch.zeros((1,), dtype=torch.int64, device=dev)       # read as uint64 by the fills
+                self._alt_tables = (torch.empty_like(sim.init), torch.empty_like(sim.demand))
+                self._side = torch.cuda.Stream(dev)
+            cur, alt, side = (sim.init, sim.demand), self._alt_tables, self._side
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                main = torch.cuda.current_stream(dev)
+                for (play, fill, rel) in ((cur, alt, per), (alt, cur, 2 * per)):
+                    side.wait_stream(main)
+                    sim.init, sim.demand = fill
+                    with torch.cuda.stream(side):
+                        self._device_episode(counter=self._d_ctr, rel0=rel)        # next episode's tables, parallel branch
+                    sim.init, sim.demand = play
+                    sim.episode(policy=params, write_state=False)
+                    main.wait_stream(side)
+                sim.init, sim.demand = cur
+                _lib.check(sim.lib.sn_counter_add(C.c_void_p(self._d_ctr.data_ptr()), 2 * per, sim._stream()))
+            self._pair_graph, self._pair_key = g, key
+        self._d_ctr.fill_(self._ctr)
+        for _ in range(pairs):
+            self._pair_graph.replay()
+        self._ctr += 2 * per * pairs                                # `cur` again holds the next episode's tables
+        self.episodes_done += 2 * pairs * self.num_envs
+        return 2 * pairs
 
     def close(self):
         pass

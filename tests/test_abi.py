@@ -49,6 +49,22 @@ def test_struct_layout_matches_header(tmp_path):
                    P.lb.offset, S.n_items.offset, S.item_backorder_cost.offset]
 
 
+def test_step_io_layout_matches_header(tmp_path):
+    """struct sn_step_io (the argument block of sn_step_ex) as gcc lays it out vs the ctypes mirror."""
+    from multi_echelon_drl_b200 import _lib
+    fields = ["state", "period", "ctl", "env_reward", "stats", "vn_scratch", "vn_gamma", "vn_nobs", "vn_clip_obs", "vn_epsilon"]
+    src = tmp_path / "layout_io.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "supplynet.h"\nint main(){printf("%zu", sizeof(sn_step_io));'
+                   + "".join(f'printf(" %zu", offsetof(sn_step_io, {f}));' for f in fields)
+                   + 'printf(" %d %d %d\\n", SN_CTL_WORDS, SN_CTL_SEQ, SN_VN_ONEPASS_SCRATCH_DOUBLES);return 0;}\n')
+    exe = tmp_path / "layout_io"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    S = _lib.SnStepIo
+    assert got == [C.sizeof(S)] + [getattr(S, f).offset for f in fields] + [_lib.SN_CTL_WORDS, _lib.SN_CTL_SEQ,
+                                                                           _lib.SN_VN_ONEPASS_SCRATCH_DOUBLES]
+
+
 def test_spec_validation_and_error_mapping(lib):
     from multi_echelon_drl_b200 import _lib, uniform_spec
     spec = uniform_spec(["retailer", "wholesaler", "distributor", "manufacturer"], True)

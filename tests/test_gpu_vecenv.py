@@ -356,3 +356,24 @@ def test_heuristic_dict_path_matches_reference_golden():
                                           "latest_demand": 2})
 
 
+
+
+def test_policy_episodes_replayed_as_graphs_are_the_same_episodes():
+    """run_policy_episodes(use_graph=True) replays pairs of episodes as one captured graph that draws the next
+    episode's tables in a parallel branch, with the Philox stream position in device memory: same counters in the
+    same order, so the statistics are bit-identical to the serial loop - also across calls, odd counts, and a
+    reset() / step() in between."""
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    pol = BasePolicyParams([19, 20, 20, 14], 0, 16, "a")
+    out = []
+    for use_graph in (False, True):
+        env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=20000, dtype="int32", seed=5)
+        st = env.run_policy_episodes(pol, 7, use_graph=use_graph).clone()
+        st2 = env.run_policy_episodes(pol, 4, use_graph=use_graph).clone()    # a second call continues the streams
+        obs = env.reset().clone()                                             # ... and so does an ordinary reset
+        st3 = env.run_policy_episodes(pol, 3, use_graph=use_graph).clone()
+        out.append((st, st2, obs, st3))
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
+    assert out[0][0][0].item() == 20000 * 100 * 7 and out[0][0][10].item() == 20000 * 7
