@@ -376,7 +376,7 @@ def run_native(args):
     if not args.no_configs:
         del traj_obs, traj_rew, d_actions, h_traj_obs, h_traj_rew
         torch.cuda.empty_cache()
-        blocks["config3"] = config3_block(torch, world, rank, dev, 10, 3)
+        blocks["config3"] = config3_block(torch, world, rank, dev, 40, 4)
         blocks["config5"] = config5_block(torch, world, rank, dev, 256, 128)
 
     if rank == 0:
