@@ -1218,10 +1218,15 @@ inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetB
 // launch with <IDENT, Ops> chosen from the spec: tuned standard kernels (identity specialised or not)
 // or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
 #ifdef SN_TREE_ONLY
+// (specialised builds also compile the centralized full layout - action column k = node k, all four nodes observed in
+// node order - with vector action loads and observation stores, like the tuned chain)
 #define SN_DISPATCH_TOPO(spec, CALL)                                   \
   do {                                                                 \
-    if (is_tree(spec)) { CALL(false, sn::TreeOps<T>); }                \
-    else return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only"); \
+    if (!is_tree(spec)) return fail(SN_ERR_UNSUPPORTED, "this specialised build serves its own distribution tree only"); \
+    if constexpr (sn::kF == 4) {                                       \
+      if (is_identity(spec)) { CALL(true, sn::TreeOps<T>); break; }    \
+    }                                                                  \
+    CALL(false, sn::TreeOps<T>);                                       \
   } while (0)
 #else
 #define SN_DISPATCH_TOPO(spec, CALL)                                   \
@@ -1421,6 +1426,11 @@ void launch_rollout_for(const sn_spec* spec, const sn::DevSpec<T>& d, const sn::
                         int period0, int n_steps, void* state, const void* demand, const void* actions,
                         const sn::RolloutPtrs& out, int tma, cudaStream_t st, const void* init, float* obs0) {
 #define SN_ARGS d, p, n, ld, period0, n_steps, state, demand, actions, out, tma, st, init, obs0
+#ifdef SN_TREE_ONLY
+  if constexpr (sn::kF == 4) {
+    if (is_tree(spec) && is_identity(spec)) { launch_rollout<T, POLICY, true, false, sn::TreeOps<T>>(SN_ARGS); return; }
+  }
+#endif
   if (is_tree(spec)) launch_rollout<T, POLICY, false, false, sn::TreeOps<T>>(SN_ARGS);
 #ifndef SN_TREE_ONLY
   else if (!is_standard(spec)) {
