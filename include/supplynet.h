@@ -17,6 +17,9 @@
  *     rollouts), SN_F32 / SN_F64 (fractional orders, e.g. TD3 actions).
  *   - Return value: SN_OK (0) or a negative SN_ERR_* code; sn_last_error() gives text.
  *   - There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - Environment switches, read per call, for A/B runs and tests only: SN_STEP_KERNEL=plain|tiled forces one of the
+ *     two implementations of the period step (default: by batch size, see sn_step); SN_NO_COOP=1 launches the
+ *     one-kernel VecNormalize mode without the cooperative attribute (experiments).
  */
 #ifndef SUPPLYNET_H
 #define SUPPLYNET_H
