@@ -221,6 +221,11 @@ class BatchedSupplyNetwork:
         _lib.check(self._step_lib.sn_step_ex(C.byref(self._c_spec), self.dtype_code, self.n_envs, self.ld, C.byref(io),
                                              self._stream()), self._step_lib)
 
+    def _sync_device_period(self):
+        """Keeps the device counter of the graph-replayed step equal to the host's period after host-driven calls."""
+        if self._graph_period_valid:
+            self.ctl[_lib.SN_CTL_PERIOD:_lib.SN_CTL_PERIOD + 1].fill_(self.period)
+
     def advance_host_period(self):
         """Host mirror of what a replayed `launch_step_device_period` did on the device."""
         self.period += 1
@@ -267,6 +272,7 @@ class BatchedSupplyNetwork:
             self._step_lib)
         self.period += n_steps
         self.terminal = self.period >= self.T
+        self._sync_device_period()
         return dict(obs=self.obs, traj_obs=traj_obs, traj_reward=traj_reward, traj_actions=traj_actions,
                     done=self.terminal)
 
@@ -300,6 +306,7 @@ class BatchedSupplyNetwork:
             _ptr(self.stats) if self.track_stats else None, self._stream()), self._step_lib)
         self.period = n_steps
         self.terminal = self.period >= self.T
+        self._sync_device_period()
         return dict(obs=self.obs, obs0=obs0_out, traj_obs=traj_obs, traj_reward=traj_reward,
                     traj_actions=traj_actions, done=self.terminal)
 

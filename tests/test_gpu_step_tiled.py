@@ -284,15 +284,17 @@ def test_int32_range_guard_flags_wrapped_quantities():
     assert sim.device_flags() & _lib.SN_FLAG_QTY_RANGE
 
 
-@pytest.mark.parametrize("mode,n", [("onepass", 4096), ("onepass", 128 * 148 - 5), ("two_kernels", 4096), ("two_kernels", 128 * 148 + 300)])
-def test_fused_vecnormalize_equals_eager_kernels(mode, n):
+@pytest.mark.parametrize("mode,n,dtype", [("onepass", 4096, "float32"), ("onepass", 128 * 148 - 5, "float32"),
+                                          ("two_kernels", 4096, "float32"), ("two_kernels", 128 * 148 + 300, "float32"),
+                                          ("two_kernels", 3000, "float64")])
+def test_fused_vecnormalize_equals_eager_kernels(mode, n, dtype):
     """VecNormalize inside the replayed step graph gives what the three eager kernels give: identical observations /
     rewards from the env, statistics equal to 1e-12 relative (atomic accumulation orders differ), normalised outputs
     to float32 rounding; across two auto-resets.  onepass: statistics, grid barrier and normalisation in the step
     kernel itself (cooperative launch, one tile per SM); two_kernels: statistics fused, sn_vecnorm_apply behind it."""
     from multi_echelon_drl_b200 import register_envs as R
     from multi_echelon_drl_b200.vec_normalize import VecNormalize
-    envs = [VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=4, dtype="float32", use_graph=ug),
+    envs = [VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, seed=4, dtype=dtype, use_graph=ug),
                          clip_obs=100.0, clip_reward=1000.0) for ug in (False, True)]
     envs[1].no_onepass = mode == "two_kernels"
     assert envs[1].graph_key()[2] == (mode == "onepass")
