@@ -386,3 +386,32 @@ def test_tiled_writes_nothing_outside_its_buffers(n):
         assert (st.view(40, ld)[:, n:] == -55).all()
         for store, fill in ((st_store, -77), (obs_store, -7.0), (rew_store, -7.0), (ret_store, -7.0)):
             assert (store[:pad] == fill).all() and (store[-pad:] == fill).all()
+
+
+def test_tiled_equals_plain_at_hbm_scale():
+    """4 Mi + 77 envs (221 tiles per CTA, the size of the bench's `single_step_4M` line): state, observation and reward of
+    three periods, tiled vs plain, bit for bit; inputs drawn on the device (host generation would dominate)."""
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    n, T = 4 * 1024 * 1024 + 77, 8
+    sp = _spec("uniform", (0, 1, 2, 3), True, "a", T)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    ld = (n + 31) // 32 * 32
+    init = torch.randint(0, 9, (19, ld), generator=g, device="cuda", dtype=torch.int32)
+    demand = torch.randint(0, 9, (T + 3, ld), generator=g, device="cuda", dtype=torch.int32)
+    acts = torch.randint(-1, 18, (3, n, 4), generator=g, device="cuda", dtype=torch.int32)
+    res = []
+    for which in ("plain", "tiled"):
+        with _Kernel(which):
+            sim = BatchedSupplyNetwork(sp, n, "cuda", "int32")
+            sim.track_stats = True
+            sim.init.copy_(init); sim.demand.copy_(demand)
+            sim.reset()
+            sums = []
+            for t in range(3):
+                obs, rew, _ = sim.step(acts[t])
+                sums.append((obs.clone(), rew.clone()))
+            res.append((sums, sim.state.clone(), sim.stats.clone(), sim.ep_return.clone()))
+            del sim
+    for (o0, r0), (o1, r1) in zip(res[0][0], res[1][0]):
+        assert torch.equal(o0, o1) and torch.equal(r0, r1)
+    assert torch.equal(res[0][1][:, :n], res[1][1][:, :n]) and torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
