@@ -477,6 +477,56 @@ def single_step_numbers(torch, dev, peak):
                            else "k_step (one thread per env; the batch is L2-resident)")}
         out[tag] = res
         del sim
+    # the same period step at 4 Mi envs on other networks: chain with other lead times (57 state
+    # words), two-level distribution tree (64 words, two demand rows), general kernels, observation out
+    from dataclasses import replace as _replace
+    from multi_echelon_drl_b200.spec import tree_spec as _tree_spec
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    n = 4 * 1024 * 1024
+    base = uniform_spec(("retailer", "wholesaler", "distributor", "manufacturer"), True, T, True)
+    nets = {"other_leadtimes": (_replace(base, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)), 57),
+            "distribution_tree": (_tree_spec([dict(name="shop", demand=(0, 8), target=19), dict(name="dist_a", target=20),
+                                              dict(name="dist_b", demand=(0, 5), target=14), dict(name="maker", target=25)],
+                                             [("ext", "maker", 1, 2), ("maker", "dist_b", 1, 2), ("maker", "dist_a", 2, 2),
+                                              ("dist_a", "shop", 2, 2)], ["shop", "dist_a", "dist_b", "maker"], True), 64)}
+    out["single_step_4M_other_networks"] = {}
+    os.environ["SN_NO_SPECIALIZED"] = "1"
+    for name, (sp, words) in nets.items():
+        sim = BatchedSupplyNetwork(sp, n, dev, "int32")
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        sim.demand.copy_(torch.randint(0, 9, sim.demand.shape, generator=g, device=dev, dtype=torch.int32))
+        sim.init.copy_(torch.randint(0, 9, sim.init.shape, generator=g, device=dev, dtype=torch.int32))
+        acts = torch.randint(0, 17, (n, 4), generator=g, device=dev, dtype=torch.int32)
+        sim.reset()
+
+        def one(t):
+            _lib.check(sim.lib.sn_step(C.byref(sim._c_spec), sim.dtype_code, n, sim.ld, t, C.c_void_p(sim.state.data_ptr()),
+                                       C.c_void_p(acts.data_ptr()), C.c_void_p(sim.demand[t + 1].data_ptr()),
+                                       C.c_void_p(sim.obs.data_ptr()), C.c_void_p(sim.reward.data_ptr()), None, None, None, None,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for t in range(3):
+            one(t)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for t in range(3, 43):
+                one(t)
+        graph.replay()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 120
+        bps = 2 * words * 4 + 16 + 4 * sp.n_sources + 4 + 112
+        out["single_step_4M_other_networks"][name] = {
+            "us_per_launch": ms * 1e3, "env_steps_per_s": n / (ms * 1e-3), "bytes_per_env_step": bps,
+            "frac_of_hbm_peak": n * bps / (ms * 1e-3) / 1e9 / peak, "kernel": "k_step_tiled (same pipeline, wider state box)"}
+        del sim
+    os.environ.pop("SN_NO_SPECIALIZED", None)
     # the literal drop-in call: SB3-style VecEnv.step with numpy in / numpy out (pinned staging, H2D of the
     # actions and D2H of obs + reward every step), BeerGameUniformMultiFacilityFullInfo-v0, 65,536 envs
     from multi_echelon_drl_b200.register_envs import make

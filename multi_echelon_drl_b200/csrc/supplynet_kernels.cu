@@ -231,9 +231,13 @@ struct StdOps {
 template <typename T>
 struct GenOps {
   static constexpr bool kWide = false;            // measured: 0.209 ms with 128 registers + 14 spill accesses, 0.245 ms wide
+  static constexpr int kWords = kGStateWords;
+  static constexpr int kMaxSrc = 1;
   using E = GEnv<T>;
   using D = T;
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>&, int64_t ld) { return ld; }
+  static __device__ __forceinline__ int n_src(const DevSpec<T>&) { return 1; }
+  static __device__ __forceinline__ D load_demand_smem(const T* row, int, int col, const DevSpec<T>&) { return row[col]; }
   static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t, int64_t env, const DevSpec<T>&) {
     return __ldg(row + env);
   }
@@ -271,9 +275,18 @@ struct TreeOps {
 #else
   static constexpr bool kWide = true;             // k_rollout_wide, 144 registers: 0.315 ms vs 0.355 ms with 128 + ~100 spill accesses
 #endif
+  static constexpr int kWords = kTStateWords;
+  static constexpr int kMaxSrc = kF;               // one demand row per source
   using E = TEnv<T>;
   using D = TreeDem<T>;
   static __device__ __forceinline__ int64_t dstride(const DevSpec<T>& sp, int64_t ld) { return ld * sp.n_src; }
+  static __device__ __forceinline__ int n_src(const DevSpec<T>& sp) { return sp.n_src; }
+  static __device__ __forceinline__ D load_demand_smem(const T* rows, int tile, int col, const DevSpec<T>& sp) {
+    D d;
+#pragma unroll
+    for (int k = 0; k < kF; ++k) d.v[k] = sp.src[k] >= 0 ? rows[sp.src[k] * tile + col] : T(0);
+    return d;
+  }
   static __device__ __forceinline__ D load_demand(const T* __restrict__ row, int64_t ld, int64_t env, const DevSpec<T>& sp) {
     D d;
 #pragma unroll
@@ -1313,10 +1326,9 @@ template <> CUtensorMapDataType tensor_dtype<int32_t>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType tensor_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
 template <> CUtensorMapDataType tensor_dtype<double>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT64; }
 
-template <typename T, bool IDENT>
+template <typename T, bool IDENT, typename Ops>
 int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period, void* state, const void* actions,
                       const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
-  using Ops = sn::StdOps<T>;
   using C = sn::TileCfg<T, Ops>;
   constexpr int kStages = SN_TILED_STAGES;
   auto kern = &sn::k_step_tiled<T, IDENT, Ops, kStages>;
@@ -1381,19 +1393,22 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
 #endif
   const auto d = lower<T>(spec);
 #ifndef SN_TREE_ONLY
-  // beer-game lead times: the TMA-tiled persistent kernel for HBM-sized batches (and whenever the VecNormalize
-  // statistics are fused in), the plain one-thread-per-env kernel for small ones
-  const bool tiled_ok = is_standard(spec) && aligned16(state) && aligned16(demand) && aligned16(actions) &&
+  // the TMA-tiled persistent kernel for HBM-sized batches (and whenever the VecNormalize statistics are fused in: beer-game
+  // lead times only), the plain one-thread-per-env kernel for small ones
+  const bool tiled_ok = aligned16(state) && aligned16(demand) && aligned16(actions) &&
                         (out.reward == nullptr || aligned16(out.reward)) && (out.env_reward == nullptr || aligned16(out.env_reward)) &&
                         (out.ep_return == nullptr || aligned16(out.ep_return)) && (out.vn_returns == nullptr || aligned16(out.vn_returns));
   const int choice = step_kernel_choice();
-  const int64_t bytes_per_env = 2 * (int64_t)sn::kStateWords * (int64_t)sizeof(T) + 24 + (out.obs != nullptr ? 28 * 4 : 0);
+  const int words = is_tree(spec) ? sn::kTStateWords : is_standard(spec) ? sn::kStateWords : sn::kGStateWords;
+  const int64_t bytes_per_env = 2 * (int64_t)words * (int64_t)sizeof(T) + 24 + (out.obs != nullptr ? 7 * d.n_obs * 4 : 0);
   const bool want_tiled = out.vn_scratch != nullptr || out.vn_nobs != nullptr || choice == 2 || (choice == 0 && n * bytes_per_env >= SN_TILED_MIN_BYTES);
-  if ((out.vn_scratch != nullptr || out.vn_nobs != nullptr) && !tiled_ok)
+  if ((out.vn_scratch != nullptr || out.vn_nobs != nullptr) && !(tiled_ok && is_standard(spec)))
     return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: fused VecNormalize statistics need the beer game's lead times and 16-byte aligned buffers");
   if (tiled_ok && want_tiled) {
-    if (is_identity(spec)) return launch_step_tiled<T, true>(d, n, ld, period, state, actions, demand, out, st);
-    return launch_step_tiled<T, false>(d, n, ld, period, state, actions, demand, out, st);
+    if (is_tree(spec)) return launch_step_tiled<T, false, sn::TreeOps<T>>(d, n, ld, period, state, actions, demand, out, st);
+    if (!is_standard(spec)) return launch_step_tiled<T, false, sn::GenOps<T>>(d, n, ld, period, state, actions, demand, out, st);
+    if (is_identity(spec)) return launch_step_tiled<T, true, sn::StdOps<T>>(d, n, ld, period, state, actions, demand, out, st);
+    return launch_step_tiled<T, false, sn::StdOps<T>>(d, n, ld, period, state, actions, demand, out, st);
   }
 #endif
 #define SN_CALL(ID, OPS) allow_smem(sn::k_step<T, ID, OPS>, kObsSmem); sn::k_step<T, ID, OPS><<<grid_for(n), sn::kBlock, kObsSmem, st>>>(d, n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out, tma_ok(out.obs))

@@ -415,3 +415,60 @@ def test_tiled_equals_plain_at_hbm_scale():
     for (o0, r0), (o1, r1) in zip(res[0][0], res[1][0]):
         assert torch.equal(o0, o1) and torch.equal(r0, r1)
     assert torch.equal(res[0][1][:, :n], res[1][1][:, :n]) and torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+
+
+@pytest.mark.parametrize("kind,dtype", [("leadtimes", "int32"), ("leadtimes", "float32"), ("short_chain", "int32"),
+                                        ("tree", "int32"), ("tree", "float64"), ("star", "int32")])
+def test_tiled_equals_plain_on_other_networks(kind, dtype):
+    """The tiled period step also serves chains with other lead times / fewer facilities (57 state words) and
+    distribution trees of up to four nodes (64 words, one demand row per source): same results as the plain kernel."""
+    from dataclasses import replace
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    from multi_echelon_drl_b200.spec import tree_spec
+    from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
+    T, n = 20, 128 * 148 + 4133
+    base = _spec("uniform", (0, 1, 2, 3), True, "a", T)
+    if kind == "leadtimes":
+        sp = replace(base, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1))
+    elif kind == "short_chain":
+        sp = replace(_spec("uniform", (0, 1), False, "a", T), n_facilities=3, info_leadtime=(2, 1, 2), ship_leadtime=(1, 2, 3),
+                     holding_cost=(0.5,) * 3, backorder_cost=(1.0,) * 3, coplayer_target=(19, 20, 14))
+    elif kind == "tree":
+        sp = tree_spec([dict(name="shop", demand=(0, 8), target=19), dict(name="dist_a", target=20), dict(name="dist_b", demand=(0, 5), target=14),
+                        dict(name="maker", target=25)],
+                       [("ext", "maker", 1, 2), ("maker", "dist_b", 1, 2), ("maker", "dist_a", 2, 2), ("dist_a", "shop", 2, 2)],
+                       ["dist_a", "dist_b"], True, max_episode_steps=T)
+    else:
+        sp = tree_spec([dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=12), dict(name="r3", demand=(0, 3), target=9),
+                        dict(name="hub", target=40)],
+                       [("ext", "hub", 2, 3), ("hub", "r3", 1, 1), ("hub", "r1", 2, 2), ("hub", "r2", 2, 1)], ["r1", "r2", "r3", "hub"], False,
+                       max_episode_steps=T)
+    init, demand = bulk_episode_inputs(sp, n, np.random.RandomState(31))
+    acts = np.random.RandomState(32).randint(-1, 18, (T, n, sp.n_agents)).astype(np.float64)
+    if dtype != "int32":
+        acts = acts + np.random.RandomState(33).rand(*acts.shape)
+    res = []
+    for which in ("plain", "tiled"):
+        os.environ["SN_NO_SPECIALIZED"] = "1"                       # the general library's kernels on both sides
+        try:
+            with _Kernel(which):
+                sim = BatchedSupplyNetwork(sp, n, "cuda", dtype)
+                sim.track_stats = True
+                sim.load_episode(init, demand)
+                sim.reset()
+                r64 = torch.zeros((n,), dtype=torch.float64, device="cuda")
+                cost = torch.zeros((8, sim.ld), dtype=torch.float64, device="cuda")
+                tr = []
+                for t in range(T):
+                    obs, rew, done = sim.step(torch.as_tensor(acts[t]), reward64_out=r64, cost_out=cost)
+                    tr.append((obs.clone(), r64.clone(), cost.clone()))
+                res.append((tr, sim.state.clone(), sim.ep_return.clone(), sim.stats.clone(), done))
+        finally:
+            os.environ.pop("SN_NO_SPECIALIZED", None)
+    for (o0, r0, c0), (o1, r1, c1) in zip(res[0][0], res[1][0]):
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(c0[:, :n], c1[:, :n])
+    assert torch.equal(res[0][1][:, :n], res[1][1][:, :n]) and torch.equal(res[0][2], res[1][2]) and res[0][4] and res[1][4]
+    if dtype == "int32":
+        assert torch.equal(res[0][3], res[1][3])
+    else:
+        np.testing.assert_allclose(res[0][3].cpu().numpy(), res[1][3].cpu().numpy(), rtol=1e-12)
