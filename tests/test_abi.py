@@ -148,3 +148,44 @@ def test_every_entry_point_reports_through_sn_last_error(lib):
     assert rc == _lib.SN_ERR_INVALID and b"sn_fill_uniform" in lib.sn_last_error()
     with pytest.raises(ValueError, match="sn_fill_uniform"):
         _lib.check(rc)
+
+
+def test_specialised_tree_library_serves_its_own_network_only():
+    """specialize.build -> csrc/spec/libsupplynet_tree_<key>.so (nvcc, about 7 s): same ABI version and symbols for the
+    period step / rollouts; its sn_spec_validate accepts exactly the network it was compiled for (host-only calls)."""
+    import shutil
+    if shutil.which("nvcc") is None:
+        pytest.skip("needs nvcc")
+    from multi_echelon_drl_b200 import _lib, specialize, uniform_spec
+    from multi_echelon_drl_b200.spec import tree_spec
+    star = tree_spec([dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=12), dict(name="r3", demand=(0, 3), target=9),
+                      dict(name="hub", target=40)],
+                     [("ext", "hub", 2, 3), ("hub", "r3", 1, 1), ("hub", "r1", 2, 2), ("hub", "r2", 2, 1)], ["r1", "r2", "r3", "hub"], True)
+    t = specialize.tables(star)
+    assert t["nf"] == 4 and t["kf"] == 4 and t["sup"][:4] == [3, 3, 3, -1] and t["rank"][:4] == [1, 2, 0, 0]
+    assert t["max_rank"] == 2 and t["lat"][3] in (0, 1, 2) and t["li"][:4] == [2, 2, 1, 2] and t["ls"][:4] == [2, 1, 1, 3]
+    path = specialize.build(star, "int32")
+    assert os.path.isfile(path) and os.path.basename(path) == f"libsupplynet_tree_{specialize.key(star, 'int32')}.so"
+    lib = C.CDLL(path)
+    for name in ("sn_abi_version", "sn_spec_validate", "sn_step_ex", "sn_rollout", "sn_episode", "sn_last_error"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = _lib.SIGNATURES[name]
+    assert lib.sn_abi_version() == _lib.ABI_VERSION
+    assert lib.sn_spec_validate(C.byref(star.to_c()), _lib.SN_I32) == 0
+    # other agents / observation mode: same tables, still served; another topology, other lead times, a chain: refused
+    assert lib.sn_spec_validate(C.byref(tree_spec([dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=12),
+                                                     dict(name="r3", demand=(0, 3), target=9), dict(name="hub", target=40)],
+                                                    [("ext", "hub", 2, 3), ("hub", "r3", 1, 1), ("hub", "r1", 2, 2), ("hub", "r2", 2, 1)],
+                                                    ["hub"], False).to_c()), _lib.SN_I32) == 0
+    other = tree_spec([dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=12), dict(name="r3", demand=(0, 3), target=9),
+                       dict(name="hub", target=40)],
+                      [("ext", "hub", 2, 3), ("hub", "r1", 2, 2), ("hub", "r3", 1, 1), ("hub", "r2", 2, 1)], ["r1", "r2", "r3", "hub"], True)
+    assert lib.sn_spec_validate(C.byref(other.to_c()), _lib.SN_I32) == _lib.SN_ERR_UNSUPPORTED      # other service order
+    chain = uniform_spec(["retailer", "wholesaler", "distributor", "manufacturer"], True)
+    assert lib.sn_spec_validate(C.byref(chain.to_c()), _lib.SN_I32) == _lib.SN_ERR_UNSUPPORTED
+    assert lib.sn_spec_validate(C.byref(star.to_c()), _lib.SN_F32) == _lib.SN_OK     # validation is dtype-agnostic ...
+    # ... the compute entry points are not: this library was built for int32 only
+    rc = lib.sn_rollout(C.byref(star.to_c()), _lib.SN_F32, 8, 8, 0, 1, C.c_void_p(8), C.c_void_p(8), _lib.SN_POLICY_BASE_STOCK, None,
+                        C.byref(_lib.SnPolicy()), None, None, None, None, None, None, None)
+    assert rc == _lib.SN_ERR_UNSUPPORTED and b"dtype" in lib.sn_last_error()
+    assert specialize.key(star, "int32") != specialize.key(other, "int32") != specialize.key(star, "float32")
