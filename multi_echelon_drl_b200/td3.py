@@ -55,6 +55,8 @@ class ReplayBuffer:
         self.rew = torch.zeros((capacity,), **kw)
         self.done = torch.zeros((capacity,), **kw)
         self.size_t = torch.zeros((), dtype=torch.float64, device=device)   # len(self) on the device (graph replays read it)
+        self.pos_t = torch.zeros((), dtype=torch.int64, device=device)      # write position on the device (add_on_device)
+        self._lane = None
 
     def __len__(self):
         return self.capacity if self.full else self.pos
@@ -69,6 +71,23 @@ class ReplayBuffer:
         self.full = self.full or (self.pos + n >= self.capacity)
         self.pos = (self.pos + n) % self.capacity
         self.size_t.fill_(float(len(self)))
+        self.pos_t.fill_(self.pos)
+
+    def add_on_device(self, obs, next_obs, act, rew, done):
+        """`add` with the write position and the length read from / advanced in device memory: nothing of it depends
+        on host state, so one captured graph stores every vector step.  The host mirrors move with `advance_host`."""
+        n = obs.shape[0]
+        if self._lane is None or self._lane.shape[0] != n:
+            self._lane = torch.arange(n, device=obs.device)
+        idx = (self._lane + self.pos_t) % self.capacity
+        self.obs[idx], self.next_obs[idx], self.act[idx] = obs, next_obs, act
+        self.rew[idx], self.done[idx] = rew, done.to(torch.float32)
+        self.pos_t.add_(n).remainder_(self.capacity)
+        self.size_t.add_(float(n)).clamp_(max=float(self.capacity))
+
+    def advance_host(self, n):
+        self.full = self.full or (self.pos + n >= self.capacity)
+        self.pos = (self.pos + n) % self.capacity
 
     def sample(self, batch_size, generator=None):
         idx = torch.randint(0, len(self), (batch_size,), device=self.obs.device, generator=generator)
@@ -104,6 +123,7 @@ class TD3Config:
     # replay `policy_delay` consecutive updates (sampling, normalisation, both losses, Adam, Polyak) as ONE CUDA graph:
     # the update is ~150 small launches on [128 x 768] tensors, i.e. launch-bound when run eagerly
     cuda_graph: bool = True
+    fused_adam: bool = True               # with cuda_graph: torch's single-launch Adam instead of the foreach form
 
 
 @dataclass
@@ -162,10 +182,14 @@ class HgeTD3:
         self.critics_target.load_state_dict(self.critics.state_dict())
         if ddp:
             self._broadcast_parameters()
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
-        self.critic_opt = torch.optim.Adam(self.critics.parameters(), lr=c.learning_rate, capturable=c.cuda_graph)
+        # fused: one multi-tensor launch per optimizer step instead of a dozen foreach launches (the update graph is
+        # bound by the latency of its chain of small kernels)
+        adam = dict(lr=c.learning_rate, capturable=True, fused=c.fused_adam) if c.cuda_graph else dict(lr=c.learning_rate)
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), **adam)
+        self.critic_opt = torch.optim.Adam(self.critics.parameters(), **adam)
         self._graph, self._graph_warm = None, 0
         self._pi_graphs, self._pi_seen = {}, {}
+        self._collect, self._collect_warm, self._orig = None, 0, None
         self.buffer = ReplayBuffer(c.buffer_size, od, ad, self.device)
         self.hge_schedule = HgeRateSchedule(c.hge_rate_at_start, c.hge_decay_periods)
         self.hge_rate = c.hge_rate_at_start if heuristic is not None else 0.0
@@ -243,6 +267,97 @@ class HgeTD3:
             torch.add((scaled + 1.0) * (0.5 * (self.high - self.low)), self.low, out=buf)
             return buf, scaled
         return self.unscale_action(scaled), scaled
+
+    # ---- collection as three graph replays per vector step: action (actor or heuristic + noise), env step, store
+    def _collect_graph_ok(self, obs, orig):
+        """The env hands out fixed device buffers and steps through its own replayed graph (VecNormalize over a
+        use_graph SupplyNetVecEnv), exploration is past the uniform warm-up, and a few eager steps have run."""
+        c, env = self.cfg, self.vec_normalize
+        if not c.cuda_graph or env is None or self.num_timesteps < c.learning_starts:
+            return False
+        venv = env.venv
+        buf = getattr(venv, "action_buffer", None) if getattr(venv, "use_graph", False) else None
+        if buf is None or getattr(venv, "_graph", None) is None or buf.dtype != torch.float32 or buf.shape[1] != self.low.shape[0]:
+            return False
+        cg = self._collect
+        if cg is not None:
+            return obs is cg.obs and orig is cg.orig and buf is cg.buf
+        self._collect_warm += 1
+        return self._collect_warm > 3
+
+    def _capture(self, fn):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            fn()
+        return graph
+
+    @torch.no_grad()
+    def _act_graphed(self, obs, orig):
+        """`_sample_action` as one replay: unscale(actor(obs)) or the heuristic's orders, scaled to [-1, 1], Gaussian
+        noise (default CUDA generator: graph-safe), clipped; the scaled action stays in `cg.scaled` for the replay
+        buffer and the env's action buffer receives the un-scaled one.  The coin is HgeTD3.predict's (hge.py:144-172)."""
+        from types import SimpleNamespace
+        from .utils.heuristics import BaseStockPolicy
+        c, cg = self.cfg, self._collect
+        if cg is None:
+            buf = self.env.venv.action_buffer
+            cg = self._collect = SimpleNamespace(obs=obs, orig=orig, buf=buf, scaled=torch.empty_like(buf), store=None, store_key=None)
+            # constants of the two affine maps, kept alive: the graphs read them at every replay
+            cg.half_span = 0.5 * (self.high - self.low)
+            cg.to_scaled_mul = 2.0 / (self.high - self.low)                   # scale_action(a) = a * mul + add
+            cg.to_scaled_add = -2.0 * self.low / (self.high - self.low) - 1.0
+            cg.to_order_add = self.low + cg.half_span                          # unscale_action(s) = s * half_span + add
+
+            def explore(scaled):
+                """noise, clip, both forms of the action: four launches."""
+                if c.action_noise_std > 0:
+                    scaled = torch.add(scaled, torch.randn_like(scaled), alpha=c.action_noise_std)
+                torch.clamp(scaled, -1.0, 1.0, out=cg.scaled)
+                torch.addcmul(cg.to_order_add, cg.scaled, cg.half_span, out=buf)
+
+            def from_orders(orders):
+                explore(torch.addcmul(cg.to_scaled_add, orders.to(torch.float32), cg.to_scaled_mul))
+            cg.from_orders = from_orders
+            # the actor's tanh output IS the scaled action (eager: scale_action(unscale_action(.)), equal up to rounding)
+            cg.pi = self._capture(lambda: explore(self.actor(obs)))
+            cg.heur = (self._capture(lambda: from_orders(self.heuristic.get_order_quantity(orig)))
+                       if isinstance(self.heuristic, BaseStockPolicy) else None)
+        p = float(self.hge_rate) ** 2
+        if self.heuristic is not None and p > 0.0 and self.rng.rand() < p:
+            with self.timers.span("heuristic"):
+                if cg.heur is not None:
+                    cg.heur.replay()
+                else:
+                    cg.from_orders(torch.as_tensor(self.heuristic.get_order_quantity(orig), device=self.device))
+        else:
+            with self.timers.span("policy_forward"):
+                cg.pi.replay()
+        return cg.buf, cg.scaled
+
+    @torch.no_grad()
+    def _store_graphed(self, orig, new_orig, raw_rew, dones):
+        """buffer.add(orig, new_orig, scaled action, reward, dones) and orig <- new_orig as one replay (non-terminal
+        steps of the env's replayed graph: every operand is a fixed device buffer)."""
+        cg = self._collect
+        key = (new_orig.data_ptr(), raw_rew.data_ptr())
+        if cg.store is None:
+            cg.no_done = torch.zeros(orig.shape[0], dtype=torch.float32, device=self.device)
+        dones = cg.no_done                 # this path stores non-terminal steps only (float already: no cast launch)
+        if cg.store is None:
+            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)      # eagerly once (sets up the lane index)
+            orig.copy_(new_orig)
+            cg.keep = (new_orig, raw_rew, dones)
+
+            def store():
+                self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)
+                orig.copy_(new_orig)
+            cg.store, cg.store_key = self._capture(store), key
+        elif key == cg.store_key:
+            cg.store.replay()
+        else:
+            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)
+            orig.copy_(new_orig)
+        self.buffer.advance_host(orig.shape[0])
 
     def _normalize(self, obs, rew, stats=None):
         if self.vec_normalize is None:
@@ -354,17 +469,27 @@ class HgeTD3:
         c, env = self.cfg, self.env
         n = env.num_envs
         obs = env.reset()
-        orig = env.get_original_obs().clone()
+        first = env.get_original_obs()
+        if self._orig is None or self._orig.shape != first.shape or self._orig.dtype != first.dtype:
+            self._orig = first.clone()        # ONE buffer for the model's lifetime: the collection graphs read it
+        else:
+            self._orig.copy_(first)
+        orig = self._orig
         t0 = time.time()
         while self.num_timesteps < total_timesteps:
             for _ in range(c.train_freq):
                 self.hge_rate = self.hge_schedule(self.num_timesteps) if self.heuristic is not None else 0.0
-                action, buffer_action = self._sample_action(obs, orig)
+                graphed = self._collect_graph_ok(obs, orig)
+                action, buffer_action = self._act_graphed(obs, orig) if graphed else self._sample_action(obs, orig)
                 with self.timers.span("env_step"):
                     new_obs, rew, dones, infos = env.step(action)
                 new_orig = env.get_original_obs()
                 raw_rew = env.get_original_reward() if self.vec_normalize is not None else rew
                 done = bool(infos.terminal_observation is not None)
+                if graphed and not done and new_obs is obs and getattr(env.venv, "last_step_graphed", False):
+                    self._store_graphed(orig, new_orig, raw_rew, dones)
+                    self.num_timesteps += n
+                    continue
                 # at an episode end the stored next observation is the terminal one, not the reset one
                 next_for_buffer = new_orig
                 if done:
@@ -372,7 +497,8 @@ class HgeTD3:
                         self.vec_normalize.venv._term_obs
                     self.episode_returns.append(float(infos.episode_return.mean().item()))
                 self.buffer.add(orig, next_for_buffer, buffer_action, raw_rew, dones)
-                obs, orig = new_obs, new_orig.clone()
+                obs = new_obs
+                orig.copy_(new_orig)          # `orig` is one fixed buffer (the collection graphs read it)
                 self.num_timesteps += n
             if self.num_timesteps >= c.learning_starts and len(self.buffer) >= c.batch_size:
                 steps = c.gradient_steps if c.gradient_steps >= 0 else c.train_freq * n

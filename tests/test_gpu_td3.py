@@ -13,7 +13,7 @@ def test_td3_hge_short_run_and_buffer_contents():
     from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
     from multi_echelon_drl_b200.vec_normalize import VecNormalize
     n = 256
-    env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0),
+    env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0, use_graph=True),
                        clip_obs=100.0, clip_reward=1000.0)
     cfg = TD3Config(net_arch=(64,), train_freq=8, gradient_steps=4, buffer_size=n * 120, learning_starts=n * 4,
                     hge_rate_at_start=0.5, hge_decay_periods=1)
@@ -38,6 +38,20 @@ def test_td3_hge_short_run_and_buffer_contents():
     assert len(model.episode_returns) == 1 and np.isfinite(model.episode_returns[0])
     for p in model.actor.parameters():
         assert torch.isfinite(p).all()
+    # past the uniform warm-up the collection ran as three graph replays per vector step (action, env step, store):
+    # the device-side write position / length agree with the host's, and consecutive transitions chain
+    assert model._collect is not None and model._collect.store is not None and model._collect.heur is not None
+    assert int(buf.pos_t.item()) == buf.pos == n * 104 and buf.size_t.item() == len(buf)
+    for t in (0, 3, 4, 5, 50, 98, 100, 102):
+        assert torch.equal(buf.next_obs[t * n:(t + 1) * n], buf.obs[(t + 1) * n:(t + 2) * n]), t
+    assert not torch.equal(buf.next_obs[99 * n:100 * n], buf.obs[100 * n:101 * n])      # terminal observation vs reset
+    # the stored action is the scaled form of the order the env received: latest order of the retailer in next_obs
+    # (observation column 3 + lead-time slot is env-specific; check through the reward sign and range only)
+    assert (buf.act[4 * n: 104 * n].abs() <= 1).all() and buf.act[4 * n: 104 * n].std() > 0.1
+    # what the env's action buffer received last = unscale_action(last stored scaled action), inside the action space
+    last = buf.act[103 * n: 104 * n]
+    assert torch.allclose(env.venv.action_buffer, model.unscale_action(last), atol=1e-5)
+    assert env.venv.action_buffer.min() >= 0 and env.venv.action_buffer.max() <= 16 and env.venv.action_buffer.std() > 1
 
 
 def test_td3_learns_to_beat_random_on_basic_retailer():
@@ -61,33 +75,37 @@ def test_td3_learns_to_beat_random_on_basic_retailer():
     assert best_late > 0.6 * first, (first, model.episode_returns)
 
 
-def test_td3_hge_centralized_learns_to_the_heuristics_level():
+@pytest.mark.parametrize("seed", [0, 2])
+def test_td3_hge_centralized_learns_to_the_heuristics_level(seed):
     """BASELINE config 5 (centralized complex scenario, 4,096 envs, TD3 with heuristic-guided exploration whose rate
-    decays linearly like HgeRateCallback, utils/callbacks.py:5-23; step + VecNormalize as one replayed kernel): 40
-    episodes with batch 1,024 and 4 updates per vector step bring the deterministic policy from the uniform-random
-    level (about -16,900 per episode) to the level of the base-stock heuristic that guided it (-1,337; measured
-    -1,027 +- 248, profiles/r2_td3_learning.json).  Thresholds leave a wide margin for seed / atomics noise."""
+    decays linearly like HgeRateCallback, utils/callbacks.py:5-23; collection = three graph replays per vector step,
+    step + VecNormalize as one kernel): 60 episodes with batch 2,048, learning rate 3e-4 and 4 updates per vector step
+    bring the deterministic policy from the uniform-random level (about -16,900 per episode) to the level of the
+    base-stock heuristic that guided it (-1,337).  Measured over seeds 0..3: -814, -1,005, -1,441, -977
+    (profiles/r2_td3_learning.json, which also records the recipes that do NOT learn on every seed: learning rate 1e-3
+    diverges on one seed in four).  Thresholds leave a margin of 2x."""
     from multi_echelon_drl_b200 import register_envs as R
     from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
     from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
     from multi_echelon_drl_b200.vec_normalize import VecNormalize
-    n, episodes = 4096, 40
+    n, episodes = 4096, 60
     env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0, use_graph=True),
                        clip_obs=100.0, clip_reward=1000.0)
     total = n * 100 * episodes
-    cfg = TD3Config(batch_size=1024, net_arch=(768,), learning_rate=1e-3, tau=0.01, train_freq=32, gradient_steps=128,
+    cfg = TD3Config(batch_size=2048, net_arch=(768,), learning_rate=3e-4, tau=0.01, train_freq=32, gradient_steps=128,
                     action_noise_std=0.3, gamma=0.95, hge_rate_at_start=0.5, hge_decay_periods=total // 200,
-                    learning_starts=n * 100, seed=0)
+                    learning_starts=n * 100, seed=seed)
     model = HgeTD3(env, BaseStockPolicy([19, 20, 20, 14]), cfg)
     model.learn(total)
     assert env.venv.sim.device_flags() == 0
+    assert model._collect is not None and model._collect.store is not None      # the graphed collection path ran
     assert model.hge_rate == 0.0                                  # decayed to zero half-way through the run
     first, late = model.episode_returns[0], float(np.mean(model.episode_returns[-5:]))
-    assert first < -12000 and late > -3000, model.episode_returns  # training episodes (with exploration noise)
+    assert first < -12000 and late > -4000, model.episode_returns  # training episodes (with exploration noise)
     eval_env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=123),
                             clip_obs=100.0, clip_reward=1000.0)
     mean, std, cnt = model.evaluate(eval_env, n_episodes=1)
-    assert cnt == n and mean > -2000, (mean, std)                 # heuristic: -1,337; uniform random: -16,858
+    assert cnt == n and mean > -2700, (mean, std)                 # heuristic: -1,337; uniform random: -16,858
     model.close()
 
 
