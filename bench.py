@@ -775,7 +775,7 @@ def config5_block(torch, world, rank, dev, steps, warmup):
             "env_step_graph_gpu_us": round(env_step_graph_us, 2), "device_flags": flags,
             "workload": f"config5: TD3+HGE, {n} envs/GPU x {world}, batch 128, one 768-unit hidden layer, train_freq 32 / 32 "
                         "updates, device replay buffer; env step + VecNormalize = ONE replayed cooperative kernel (device "
-                        "period counter), update and actor forward as CUDA graphs; one step = one vector step of all envs + "
+                        "period counter); per vector step three graph replays (action, env step, store) + one replayed update (fused Adam); one step = one vector step of all envs + "
                         "one gradient update (wall clock, max over ranks); GPU-time split per vector step in us"}
 
 
