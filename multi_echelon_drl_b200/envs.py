@@ -78,15 +78,23 @@ def make_beer_game(agent_managed_facilities=None, demand_type="classic_beer_game
                    episode_source="numpy_bulk", output="torch", use_graph=False):
     """The classic beer game (envs.py:501-596): demand 4,4,4,4,8,8,...; MultiDiscrete([17]*F) actions.
     `random_init` is accepted and ignored exactly as in the reference (never passed to Arc, Q16)."""
-    if demand_type == "deterministic_random":
-        raise NotImplementedError("demand_type='deterministic_random' (envs.py:519-520) is not offered")
-    if demand_type not in ("classic_beer_game", "normal", "uniform"):
+    if demand_type not in ("classic_beer_game", "normal", "uniform", "deterministic_random"):
         raise ValueError()
-    sp = _spec.classic_spec(agent_managed_facilities, max_period, demand_type)
+    import numpy as np
+    if n_envs is None and seed:
+        np.random.seed(seed)                         # envs.py:511-512
+    if demand_type == "deterministic_random":
+        # envs.py:519-520: ONE sequence of max_period values drawn from the global generator when the env is built and
+        # replayed by every episode.  The period advance reads one value more than the list holds, so the reference's
+        # episode ends in an IndexError at its last step; the single env reproduces that, the batched env is not offered.
+        if n_envs is not None:
+            raise NotImplementedError("demand_type='deterministic_random' cannot finish an episode in the reference "
+                                      "(IndexError at the last step, envs.py:519-520): single env only")
+        sp = _spec.classic_spec(agent_managed_facilities, max_period, "list",
+                                (8 + 2 * np.random.randn(max_period)).astype(int))
+    else:
+        sp = _spec.classic_spec(agent_managed_facilities, max_period, demand_type)
     if n_envs is None:
-        if seed:
-            import numpy as np
-            np.random.seed(seed)                     # envs.py:511-512
         return BeerGameEnv(sp, device, dtype, spaces.MultiDiscrete([17] * sp.n_agents), None, return_dict)
     if return_dict:
         raise NotImplementedError("return_dict=True (per-agent dict observations) is offered by the single env only")

@@ -92,6 +92,11 @@ class BeerGameEnv:
                           category=RuntimeWarning)
         if q.shape[1] != self.spec.n_agents:
             raise ValueError(f"expected {self.spec.n_agents} order quantities, got {q.shape[1]}")
+        if self.spec.demand_pattern == "list" and self.period + 1 >= len(self.spec.demand_list):
+            # the period advance reads demand[period + 1] (supplynetwork.py:266-268): past the end of a list pattern the
+            # reference dies with numpy's IndexError (make_beer_game's 'deterministic_random' does so at its last step)
+            size = len(self.spec.demand_list)
+            raise IndexError(f"index {size} is out of bounds for axis 0 with size {size}")
         obs, _, done = self.sim.step(torch.as_tensor(q), reward64_out=self._r64)
         self.period, self.terminal = self.sim.period, done
         return self._format(obs.cpu().numpy()[0]), float(self._r64.item()), bool(done), {}

@@ -48,7 +48,8 @@ class ScenarioSpec:
     action_low: float = 0.0                          # action space bounds (envs.py:269-272, 397-400)
     action_high: float = 16.0
     # demand / initial-state generators (host side, utils/demands.py + Arc/Node.reset)
-    demand_pattern: str = "uniform"                  # 'uniform' | 'normal' | 'classic_beer_game' | 'samples'
+    demand_pattern: str = "uniform"                  # 'uniform' | 'normal' | 'classic_beer_game' | 'samples' | 'list'
+    demand_list: Tuple[int, ...] = ()                # 'list': the fixed sequence every episode replays (utils/demands.py:38-39)
     demand_params: Tuple[float, float] = (0, 8)      # (low, high) or (mean, sd)
     demand_path: Optional[str] = None                # .npy of demand rows for 'samples' (utils/demands.py:26-29)
     random_init: bool = True
@@ -267,15 +268,16 @@ def normal_spec(agent_managed_facilities=None, global_observable=False, max_epis
         init_pipeline=(0, 21), fixed_inventory=10, fixed_shipments=(10, 0), fixed_sales_orders=(10, 0))
 
 
-def classic_spec(agent_managed_facilities=None, max_episode_steps=35, demand_pattern="classic_beer_game") -> ScenarioSpec:
+def classic_spec(agent_managed_facilities=None, max_episode_steps=35, demand_pattern="classic_beer_game",
+                 demand_list=()) -> ScenarioSpec:
     """make_beer_game (envs.py:501-596): fixed initial state only (random_init is never wired, Q16)."""
-    params = {"classic_beer_game": (4, 8), "normal": (10, 2), "uniform": (0, 2)}[demand_pattern]
+    params = {"classic_beer_game": (4, 8), "normal": (10, 2), "uniform": (0, 2), "list": (0, 0)}[demand_pattern]
     return ScenarioSpec(
         name="classic", holding_cost=(0.5,) * 4, backorder_cost=(1.0,) * 4, coplayer_target=(32, 32, 32, 24),
         agents=_agents(agent_managed_facilities, ("retailer",)), global_observable=False,
         max_episode_steps=max_episode_steps, action_low=0, action_high=16, demand_pattern=demand_pattern,
-        demand_params=params, random_init=False, fixed_inventory=12, fixed_shipments=(4, 4),
-        fixed_sales_orders=(4, 4))
+        demand_params=params, demand_list=tuple(int(x) for x in demand_list), random_init=False, fixed_inventory=12,
+        fixed_shipments=(4, 4), fixed_sales_orders=(4, 4))
 
 
 def tree_spec(nodes, arcs, agent_managed_facilities, global_observable=False, max_episode_steps=100, random_init=True,

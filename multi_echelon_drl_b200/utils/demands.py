@@ -59,6 +59,15 @@ class Demand:
         self.sample_pointer += 1
         return np.asarray(row)
 
+    def row(self, rs) -> np.ndarray:
+        """`draw` as a row of exactly `size` values for the batched demand table: a list pattern (passed through as
+        is by `draw`, like the reference) is cut or zero-padded - the single env raises the reference's IndexError
+        before a period past the end of the list is read (gym_env.py)."""
+        row = self.draw(rs)
+        if row.shape[0] >= self.size:
+            return row[: self.size]
+        return np.concatenate([row, np.zeros(self.size - row.shape[0], dtype=row.dtype)])
+
     def sample(self, n: int, rs) -> np.ndarray:
         """[n, size] demands in a few vectorised draws."""
         p = self.demands_pattern
@@ -89,6 +98,8 @@ def demand_for(spec: ScenarioSpec, source: int = 0) -> Demand:
             _SAMPLE_DEMANDS[key] = Demand("samples", data_path=spec.demand_path, size=spec.max_episode_steps)
         return _SAMPLE_DEMANDS[key]
     a, b = spec.demand_params
+    if spec.demand_pattern == "list":
+        return Demand(list(spec.demand_list), size=spec.max_episode_steps)
     if spec.demand_pattern == "uniform":
         return Demand("uniform", low=int(a), high=int(b), size=spec.max_episode_steps)
     if spec.demand_pattern == "normal":
@@ -186,12 +197,12 @@ def seeded_episode_inputs_from_streams(spec: ScenarioSpec, streams):
     for i, rs in enumerate(streams):
         if not spec.random_init:
             init[i] = fixed
-            demand[i] = dem.draw(rs)
+            demand[i] = dem.row(rs)
             continue
         lo, hi = spec.init_inventory
         plo, phi = spec.init_pipeline
         init[i, 0] = rs.randint(lo, hi)
-        demand[i] = dem.draw(rs)
+        demand[i] = dem.row(rs)
         for k in range(1, spec.n_facilities):
             init[i, k] = rs.randint(lo, hi)
         for k in range(spec.n_facilities - 1, -1, -1):

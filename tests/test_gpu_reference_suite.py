@@ -143,3 +143,33 @@ def test_return_dict_observations_like_the_reference():
     obs, r, d, _ = env.step(np.array([3, 5]))
     f2, r2, _, _ = flat_env.step(np.array([3, 5]))
     assert r == r2 and [v for a in obs.values() for v in a.values()] == f2.tolist()
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2])
+def test_deterministic_random_demand_replays_the_reference_up_to_its_index_error(cid):
+    """make_beer_game(demand_type='deterministic_random') (envs.py:519-520): one list of max_period values drawn from
+    the global generator when the env is built (after np.random.seed(seed)), replayed by every episode.  The period
+    advance reads one value more than the list holds, so the reference's episode dies at its last step with numpy's
+    IndexError; golden episodes recorded from the live reference (tests/golden/make_deterministic_random.py)."""
+    import os
+    from multi_echelon_drl_b200.envs import make_beer_game
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "deterministic_random.npz"))
+    p = f"c{cid}_"
+    names = ["retailer", "wholesaler", "distributor", "manufacturer"]
+    agents = [names[i] for i in z[p + "agents"]]
+    T = int(z[p + "max_period"])
+    env = make_beer_game(agents, demand_type="deterministic_random", max_period=T, seed=int(z[p + "seed"]))
+    assert len(env.spec.demand_list) == T
+    for episode in range(2):                                  # the same list again after a reset
+        obs0 = env.reset()
+        assert np.array_equal(obs0, z[p + "obs0"]) and np.array_equal(obs0, z[p + "obs0_again"])
+        err_at = int(z[p + "err_at"])
+        assert err_at == T - 1
+        for t in range(err_at):
+            o, r, d, info = env.step(z[p + "actions"][t])
+            assert np.array_equal(o, z[p + "obs"][t]), (t, o, z[p + "obs"][t])
+            assert r == z[p + "rew"][t] and not d
+        with pytest.raises(IndexError, match=str(z[p + "err"])):
+            env.step(z[p + "actions"][err_at])
+    with pytest.raises(NotImplementedError):
+        make_beer_game(agents, demand_type="deterministic_random", max_period=T, n_envs=8)

@@ -326,3 +326,26 @@ def test_bind_to_gpu_cpus_is_a_no_op_without_a_gpu():
     assert bind_to_gpu_cpus(0) is None or isinstance(bind_to_gpu_cpus(0), list)
     assert os.sched_getaffinity(0) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_list_pattern_rows_are_padded_to_the_episode_size_and_replayed_every_episode():
+    """utils/demands.py:38-39: a list / array pattern is the episode's demand as is.  make_beer_game's
+    'deterministic_random' builds one of max_period values (envs.py:519-520), three short of what Demand.size says;
+    the batched table row is zero-padded and the single env raises the reference's IndexError before the padding is
+    read (tests/test_gpu_reference_suite.py)."""
+    from multi_echelon_drl_b200 import spec as S
+    from multi_echelon_drl_b200.utils import demands as D
+    np.random.seed(3)
+    lst = (8 + 2 * np.random.randn(35)).astype(int)
+    sp = S.classic_spec(["retailer"], 35, "list", lst)
+    assert sp.demand_pattern == "list" and sp.demand_list == tuple(int(x) for x in lst) and hash(sp) is not None
+    dem = D.demand_for(sp)
+    assert dem.size == 38
+    state = np.random.get_state()[1].copy()
+    for _ in range(2):
+        init, rows = D.seeded_episode_inputs_from_streams(sp, [np.random])
+        assert rows.shape == (1, 38) and np.array_equal(rows[0, :35], lst) and not rows[0, 35:].any()
+    assert np.array_equal(np.random.get_state()[1], state)          # a list pattern draws nothing at reset
+    assert np.array_equal(dem.sample(3, np.random), np.broadcast_to(lst, (3, 35)))      # passed through as is
+    long = D.Demand(list(range(50)), size=10)
+    assert np.array_equal(long.draw(np.random), np.arange(50)) and np.array_equal(long.row(np.random), np.arange(13))
