@@ -451,18 +451,24 @@ class HgeTD3:
 
     @staticmethod
     def _allreduce_grads(module):
-        """Data-parallel training across GPUs: average gradients over ranks (NCCL over NVLink)."""
+        """Data-parallel training across GPUs: average gradients over ranks (NCCL over NVLink): one flat buffer, one
+        all-reduce that averages in the collective itself, one multi-tensor copy back: three launches per call inside
+        the update graph (a division and one copy per parameter tensor before)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         grads = [p.grad for p in module.parameters() if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat /= dist.get_world_size()
-        off = 0
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:                                   # gloo has no averaging reduction
+            dist.all_reduce(flat)
+            flat /= dist.get_world_size()
+        views, off = [], 0
         for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
+            views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+        torch._foreach_copy_(grads, views)
 
     def learn(self, total_timesteps, log_interval=None):
         """OffPolicyAlgorithm.learn: collect train_freq vector steps, then train (train_td3.py:138-143)."""
