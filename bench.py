@@ -643,15 +643,16 @@ def single_step_numbers(torch, dev, peak):
             sim._graph_period_valid = False
             del many
         del mi
+    g90 = res["graph_of_periods"]
     out["multi_item_262144x2_step"] = {
-        "env_steps_per_s": res["eager"]["env_steps_per_s"], "item_chain_steps_per_s": 2 * res["eager"]["env_steps_per_s"],
-        "us_per_step": res["eager"]["us_per_step"], "frac_of_hbm_peak": res["eager"]["frac_of_hbm_peak"],
-        "achieved_gbs": res["eager"]["achieved_gbs"], "bytes_per_chain_step": bpc,
-        "graph_replay_per_period": res["graph"], "graph_of_90_periods": res["graph_of_periods"],
+        "env_steps_per_s": g90["env_steps_per_s"], "item_chain_steps_per_s": 2 * g90["env_steps_per_s"],
+        "us_per_step": g90["us_per_step"], "frac_of_hbm_peak": g90["frac_of_hbm_peak"],
+        "achieved_gbs": g90["achieved_gbs"], "bytes_per_chain_step": bpc, "launch": g90["launch"],
+        "python_issued_per_period": res["eager"], "graph_replay_per_period": res["graph"],
         "config": "config 4: 262,144 envs x 2 items (one interleaved batch of 524,288 chains, per-item costs and the per-env "
-                  "reward sum in-kernel), obs 56 / action 8, MultiItemSupplyNetwork.step called per period from Python "
-                  "(k_step_tiled); graph_replay_per_period = the same period as one replayed CUDA graph (device period counter), "
-                  "graph_of_90_periods = 90 of them in one graph, timed like single_step_*"}
+                  "reward sum in-kernel), obs 56 / action 8, k_step_tiled; timed like single_step_*: 90 period launches in one "
+                  "CUDA graph (device period counter); python_issued_per_period = MultiItemSupplyNetwork.step called per "
+                  "period from Python, graph_replay_per_period = one replayed single-period graph per call"}
     # other networks, same fixed-action rollout with trajectory out at config-2 size
     from multi_echelon_drl_b200.spec import tree_spec
     from multi_echelon_drl_b200.utils.demands import bulk_episode_inputs
