@@ -792,7 +792,24 @@ def config5_block(torch, world, rank, dev, steps, warmup):
     e.record()
     torch.cuda.synchronize()
     env_step_graph_us = s.elapsed_time(e) / reps * 1e3
+    # the same launch 40 times in ONE graph (no launch gap between replays): the kernel's own device time
+    sim = venv.sim
+    env.reset()
+    torch.cuda.synchronize()
+    many = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(many):
+        for _ in range(40):
+            sim.launch_step_device_period(venv.action_buffer, venv._obs, sim.reward, vecnorm=env.fused_args(venv._graph_key))
+    env.reset()
+    torch.cuda.synchronize()
+    s.record()
+    many.replay()
+    many.replay()
+    e.record()
+    torch.cuda.synchronize()
+    env_step_kernel_us = s.elapsed_time(e) / 80 * 1e3
     flags = venv.sim.device_flags()
+    del many
     model.close()
     if world > 1:
         w = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -802,7 +819,8 @@ def config5_block(torch, world, rank, dev, steps, warmup):
             "ms_per_step": wall / steps * 1e3, "updates": steps,
             "time_split_s": {k: v for k, v in split.items() if k.endswith("_s")},
             "us_per_vector_step": {k[:-2]: round(v / steps * 1e6, 2) for k, v in split.items() if k.endswith("_s")},
-            "env_step_graph_gpu_us": round(env_step_graph_us, 2), "device_flags": flags,
+            "env_step_graph_gpu_us": round(env_step_graph_us, 2), "env_step_kernel_gpu_us": round(env_step_kernel_us, 2),
+            "device_flags": flags,
             "workload": f"config5: TD3+HGE, {n} envs/GPU x {world}, batch 128, one 768-unit hidden layer, train_freq 32 / 32 "
                         "updates, device replay buffer; env step + VecNormalize = ONE replayed cooperative kernel (device "
                         "period counter); per vector step three graph replays (action, env step, store) + one replayed update (fused Adam); one step = one vector step of all envs + "
@@ -845,7 +863,9 @@ def run_config5(args):
             "n_gpus": world, "steps": b["steps"], "warmup": b["warmup"], "ms_per_step": b["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": b["workload"]}, "time_split_s": b["time_split_s"],
-            "us_per_vector_step": b["us_per_vector_step"], "updates": b["updates"]}))
+            "us_per_vector_step": b["us_per_vector_step"], "updates": b["updates"],
+            "env_step_graph_gpu_us": b["env_step_graph_gpu_us"], "env_step_kernel_gpu_us": b["env_step_kernel_gpu_us"],
+            "device_flags": b["device_flags"]}))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
