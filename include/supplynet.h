@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 8
+#define SN_ABI_VERSION 9
 
 #define SN_MAX_FACILITIES 8     /* size of the per-facility arrays; chains and the register-resident kernels use up to 4 */
 #define SN_MAX_CHAIN 4          /* chains, and trees on the register-resident kernels */
@@ -53,7 +53,7 @@ extern "C" {
 #define SN_CTL_TICKET 1         /* internal (block ticket); leave at 0                                               */
 #define SN_CTL_FLAGS 2          /* sticky SN_FLAG_* bits                                                             */
 #define SN_CTL_SEQ 4            /* internal (launch sequence number of the one-kernel VecNormalize mode); never reset */
-#define SN_VN_ONEPASS_SCRATCH_DOUBLES (256 * 64)   /* vn_scratch of that mode: one 512-byte slot per block            */
+#define SN_VN_ONEPASS_SCRATCH_DOUBLES (256 * 128)  /* vn_scratch of that mode: per block 64 entries of 16 bytes         */
 #define SN_FLAG_STEP_AFTER_TERMINAL 1   /* a launch found period >= max_episode_steps and did nothing (envs.py:88-89) */
 #define SN_FLAG_QTY_RANGE 2             /* SN_I32: a quantity reached 2^SN_QTY_LIMIT_LOG2, results may have wrapped    */
 
@@ -217,8 +217,10 @@ int32_t sn_step(const sn_spec* spec, int32_t dtype, int64_t n_envs, int64_t ld, 
  *                clip((obs-mean)/sqrt(var+vn_epsilon), +-vn_clip_obs), clip(reward/sqrt(ret_var+eps), +-vn_clip_reward),
  *                with the statistics AFTER this step's update when vn_scratch is given (then vn_scratch is
  *                SN_VN_ONEPASS_SCRATCH_DOUBLES doubles, zero before the first launch, and the launch is cooperative:
- *                every block publishes its tile's moments, they meet, and each adds the blocks up in block order - the
- *                statistics are reproducible bit for bit, unlike atomic accumulation), else with vn_obs_rms / vn_ret_rms
+ *                every block publishes its tile's moments as 16-byte entries that carry value and launch tag together,
+ *                reads everybody else's, and adds the blocks up in block order - one trip through the L2, and the
+ *                statistics are reproducible bit for bit, unlike atomic accumulation; the buffer belongs to ONE ctl /
+ *                VecNormalize pair: tags are the ctl's launch sequence numbers), else with vn_obs_rms / vn_ret_rms
  *                as they are (evaluation).  Replaces the sn_vecnorm_apply launch. */
 typedef struct sn_step_io {
   void* state;

@@ -17,9 +17,9 @@ SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 8
+ABI_VERSION = 9
 SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS, SN_CTL_SEQ = 8, 0, 1, 2, 4
-SN_VN_ONEPASS_SCRATCH_DOUBLES = 256 * 64
+SN_VN_ONEPASS_SCRATCH_DOUBLES = 256 * 128
 SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
 SN_QTY_LIMIT_LOG2 = 26
 SN_SRC_I32, SN_SRC_I64, SN_SRC_F32, SN_SRC_F64 = 0, 1, 2, 3

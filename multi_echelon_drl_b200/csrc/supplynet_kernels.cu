@@ -1326,12 +1326,12 @@ template <> CUtensorMapDataType tensor_dtype<int32_t>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType tensor_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
 template <> CUtensorMapDataType tensor_dtype<double>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT64; }
 
-template <typename T, bool IDENT, typename Ops>
+template <typename T, bool IDENT, typename Ops, bool ONEPASS = false>
 int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period, void* state, const void* actions,
                       const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
   using C = sn::TileCfg<T, Ops>;
   constexpr int kStages = SN_TILED_STAGES;
-  auto kern = &sn::k_step_tiled<T, IDENT, Ops, kStages>;
+  auto kern = &sn::k_step_tiled<T, IDENT, Ops, kStages, ONEPASS>;
   const size_t smem = C::smem_bytes(kStages);
   static bool opted_in[64] = {false};
   int dev = 0;
@@ -1357,7 +1357,7 @@ int launch_step_tiled(const sn::DevSpec<T>& d, int64_t n, int64_t ld, int period
   const int64_t sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   if (out.vn_nobs != nullptr) {
-    if (tiles > sms || tiles * sn::kVnSlot > SN_VN_ONEPASS_SCRATCH_DOUBLES) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes at most %lld envs on this device (one tile per SM)", (long long)(sms * C::kTile));
+    if (tiles > sms || tiles * sn::kVnSlot * 2 > SN_VN_ONEPASS_SCRATCH_DOUBLES) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes at most %lld envs on this device (one tile per SM)", (long long)(sms * C::kTile));
     if (!aligned16(out.vn_nobs) != !tma_ok(out.obs) || (out.vn_nrew != nullptr && !aligned16(out.vn_nrew)))
       return fail(SN_ERR_INVALID, "sn_step_ex: obs / vn_nobs / vn_nrew must share their 16-byte alignment");
   }
@@ -1407,6 +1407,13 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
   if (tiled_ok && want_tiled) {
     if (is_tree(spec)) return launch_step_tiled<T, false, sn::TreeOps<T>>(d, n, ld, period, state, actions, demand, out, st);
     if (!is_standard(spec)) return launch_step_tiled<T, false, sn::GenOps<T>>(d, n, ld, period, state, actions, demand, out, st);
+    if constexpr (sizeof(T) == 4) {
+      if (out.vn_nobs != nullptr) {          // one-kernel VecNormalize: its own instantiation
+        if (is_identity(spec)) return launch_step_tiled<T, true, sn::StdOps<T>, true>(d, n, ld, period, state, actions, demand, out, st);
+        return launch_step_tiled<T, false, sn::StdOps<T>, true>(d, n, ld, period, state, actions, demand, out, st);
+      }
+    }
+    if (out.vn_nobs != nullptr) return fail(SN_ERR_UNSUPPORTED, "sn_step_ex: the one-kernel VecNormalize mode takes float32 / int32 quantities");
     if (is_identity(spec)) return launch_step_tiled<T, true, sn::StdOps<T>>(d, n, ld, period, state, actions, demand, out, st);
     return launch_step_tiled<T, false, sn::StdOps<T>>(d, n, ld, period, state, actions, demand, out, st);
   }

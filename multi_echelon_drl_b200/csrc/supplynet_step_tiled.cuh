@@ -63,7 +63,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-constexpr int kVnSlot = 64;          // doubles per block in the scratch of the one-kernel VecNormalize mode (512 B)
+// Low-latency slot entries (one-kernel VecNormalize): a double travels as two 8-byte words, each = 32 bits of the value
+// + the 32-bit tag of the launch that wrote it.  8-byte accesses are single-copy atomic, so a word whose tag matches
+// carries that launch's half of the value: no fence and no separate flag between writer and reader.
+__device__ __forceinline__ void ll_store(double* entry, double v, uint32_t tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  const unsigned long long w0 = (bits & 0xffffffffull) | t, w1 = (bits >> 32) | t;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(entry), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ll_load(const double* entry, unsigned long long& w0, unsigned long long& w1) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(entry) : "memory");
+}
+__device__ __forceinline__ bool ll_value(unsigned long long w0, unsigned long long w1, uint32_t tag, double& v) {
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return (uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag;
+}
+
+constexpr int kVnSlot = 64;          // 16-byte entries per block in the scratch of the one-kernel VecNormalize mode (1 KB)
 
 // ---- stage geometry ----------------------------------------------------------------------------------------
 template <typename T, typename Ops>
@@ -105,7 +121,9 @@ __device__ __forceinline__ void rms_merge_inplace(double* mean, double* var, dou
   *var = m2 / tot;
 }
 
-template <typename T, bool IDENT, typename Ops, int kStages>
+// ONEPASS: the instantiation that carries the one-kernel VecNormalize section (its sixteen loads in flight cost 60
+// registers; kept out of the streaming instantiation, whose allocation it would disturb).
+template <typename T, bool IDENT, typename Ops, int kStages, bool ONEPASS>
 __global__ void __launch_bounds__(TileCfg<T, Ops>::kThreads, 1)
 k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUtensorMap tm_state, int64_t n, int64_t ld,
              int period_arg, const T* __restrict__ actions, const T* __restrict__ demand, const StepPtrs out, int obs_tma) {
@@ -128,7 +146,7 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
   }
   const bool terminal = period + 1 >= sp.t_max;
   // one-kernel VecNormalize: statistics (optionally updated across the grid) and normalisation in this launch
-  const bool vn_onepass = out.vn_nobs != nullptr;
+  const bool vn_onepass = ONEPASS && out.vn_nobs != nullptr;
   const bool vn_barrier = vn_onepass && out.vn_scratch != nullptr;
   const int seq = vn_barrier ? *reinterpret_cast<const volatile int32_t*>(out.ctl + SN_CTL_SEQ) : 0;
   const int64_t dstride = Ops::dstride(sp, ld);
@@ -316,12 +334,15 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
         double m = vn_m, v = vn_v;
         const double cnt = vn_cnt;
         if (vn_barrier) {
-          // Every block publishes the moments of its tile in a slot of its own (plain stores), raises the slot's flag
-          // to this launch's sequence number + 1, and waits until all slots carry it; then every block adds the slots
-          // up in block order (deterministic, unlike atomics) and merges them into the statistics it read before.
-          // One store-flag-load chain instead of atomics + a counter barrier + a reload.
-          double* slots = out.vn_scratch;                          // [gridDim.x][kVnSlot]: sums, ..., flag in the last word
-          double* mine = slots + (size_t)blockIdx.x * kVnSlot;
+          // Every block publishes the moments of its tile in a slot of its own and reads everybody else's: flag and
+          // data travel together (each 8-byte half of an entry carries 32 bits of the value and this launch's tag,
+          // the low-latency protocol of collective libraries), so a reader that sees the tag has the value - no
+          // fence, no separate flag, ONE trip through the L2 between "my sums are ready" and "I have all sums".
+          // Every block adds the slots up in block order (deterministic, unlike atomics).
+          double* slots = out.vn_scratch;                          // [gridDim.x][kVnSlot] entries of 16 bytes
+          double* mine = slots + (size_t)blockIdx.x * kVnSlot * 2;
+          const uint32_t tag = (uint32_t)seq + 1u;
+          const bool has_ret = out.vn_returns != nullptr;
           if (tid < ng * od) {
             const int c = tid % od, g = tid / od;
             double sx = 0.0, sxx = 0.0;
@@ -342,40 +363,51 @@ k_step_tiled(const __grid_constant__ DevSpec<T> sp, const __grid_constant__ CUte
           if (tid < od) {
             double a = 0.0, b = 0.0;
             for (int g = 0; g < ng; ++g) { a += vn_red[g * od + tid]; b += vn_red[kTile + g * od + tid]; }
-            __stcg(&mine[tid], a);
-            __stcg(&mine[od + tid], b);
-            __threadfence();
-          } else if (tid == ret_thread && out.vn_returns != nullptr) {
+            ll_store(mine + 2 * tid, a, tag);
+            ll_store(mine + 2 * (od + tid), b, tag);
+          } else if (tid == ret_thread && has_ret) {
             double a = 0.0, b = 0.0;
             for (int w = 0; w < C::kConsumerWarps; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
-            __stcg(&mine[2 * od], a);
-            __stcg(&mine[2 * od + 1], b);
-            __threadfence();
+            ll_store(mine + 2 * (2 * od), a, tag);
+            ll_store(mine + 2 * (2 * od + 1), b, tag);
           }
-          named_bar_sync(1, kTile);                                // this block's sums are written and fenced
-          const long long want = (long long)seq + 1;
-          if (tid == 0) {
-            *reinterpret_cast<volatile long long*>(mine + kVnSlot - 1) = want;
-          }
-          for (int bq = tid; bq < (int)gridDim.x; bq += kTile) {   // bounded spin: a protocol error traps, never hangs
-            const volatile long long* f = reinterpret_cast<const volatile long long*>(slots + (size_t)bq * kVnSlot + kVnSlot - 1);
-            for (uint32_t spins = 0; *f != want; ++spins)
-              if (spins > (1u << 24)) __trap();
-          }
-          __threadfence();
-          named_bar_sync(1, kTile);                                // every block has arrived (and has read period / seq)
+          named_bar_sync(1, kTile);                                // vn_red is free again (the group sums have been read)
           const double bn = (double)n;
           {
-            // all consumer threads fetch: thread = (block group g, column c); the loads of a thread are independent,
-            // so one L2 latency covers them (a single thread walking over the blocks would pay it per block)
+            // all consumer threads fetch: thread = (block group g, column c; c == od: the returns).  Eight blocks per
+            // round: sixteen independent loads in flight, then the tags are checked; a round is repeated until every
+            // entry carries this launch's tag (bounded: a protocol error traps, never hangs)
             const int c = tid & 31, g = tid >> 5;
             double a = 0.0, b = 0.0;
-            if (c <= od) {
-              const int ia = c < od ? c : 2 * od, ib = c < od ? od + c : 2 * od + 1;     // column c; c == od: the returns
-#pragma unroll 4
-              for (int bq = g; bq < (int)gridDim.x; bq += C::kConsumerWarps) {
-                a += __ldcg(slots + (size_t)bq * kVnSlot + ia);
-                b += __ldcg(slots + (size_t)bq * kVnSlot + ib);
+            if (c < od || (c == od && has_ret)) {
+              const int ia = c < od ? c : 2 * od, ib = c < od ? od + c : 2 * od + 1;
+              for (int b0 = g; b0 < (int)gridDim.x; b0 += C::kConsumerWarps * 8) {
+                double va[8], vb[8];
+                bool ok;
+                uint32_t spins = 0;
+                do {
+                  unsigned long long w[8][4];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    const int bq = b0 + C::kConsumerWarps * u;
+                    if (bq < (int)gridDim.x) {
+                      ll_load(slots + ((size_t)bq * kVnSlot + ia) * 2, w[u][0], w[u][1]);
+                      ll_load(slots + ((size_t)bq * kVnSlot + ib) * 2, w[u][2], w[u][3]);
+                    }
+                  }
+                  ok = true;
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    const int bq = b0 + C::kConsumerWarps * u;
+                    if (bq < (int)gridDim.x) {
+                      ok = ok && ll_value(w[u][0], w[u][1], tag, va[u]) && ll_value(w[u][2], w[u][3], tag, vb[u]);
+                    }
+                  }
+                  if (++spins > (1u << 22)) __trap();
+                } while (!ok);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (b0 + C::kConsumerWarps * u < (int)gridDim.x) { a += va[u]; b += vb[u]; }
               }
             }
             vn_red[tid] = a;
