@@ -175,12 +175,14 @@ def test_graphed_update_equals_eager_in_effect_and_is_faster():
     for graph, m in models.items():
         m.train(7)                                        # graph: 3 eager warm-up cycles, then capture is pending
         assert m.n_updates == 7
+        m.train(3)                                        # from an odd count: one eager step to align, capture, one replay
+        assert m.n_updates == 10                          # (the capture takes half a second of CPU time: outside the timed region)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
-        m.train(401)                                      # from an odd count: one eager step to align, then 200 replays
+        m.train(401)                                      # 200 replays and one eager step for the odd remainder
         e1.record(); torch.cuda.synchronize()
         times[graph] = e0.elapsed_time(e1)
-        assert m.n_updates == 408
+        assert m.n_updates == 411
         for p in list(m.actor.parameters()) + list(m.critics.parameters()) + list(m.actor_target.parameters()):
             assert torch.isfinite(p).all()
     assert b._graph is not None and a._graph is None
