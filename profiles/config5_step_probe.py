@@ -6,7 +6,10 @@ from multi_echelon_drl_b200.register_envs import make
 from multi_echelon_drl_b200.vec_normalize import VecNormalize
 out = {}
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-for tag in ("step_plain", "step_tiled", "step_tiled_vn", "step_tiled_vn+apply", "apply_only", "onepass", "onepass_eval"):
+TAGS = ("step_plain", "step_tiled", "step_tiled_vn", "step_tiled_vn+apply", "apply_only", "onepass", "onepass_eval")
+if os.environ.get("SN_PROBE_TAGS"):                      # e.g. SN_PROBE_TAGS=onepass under ncu
+    TAGS = tuple(os.environ["SN_PROBE_TAGS"].split(","))
+for tag in TAGS:
     env = VecNormalize(make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0, use_graph=True),
                        clip_obs=100.0, clip_reward=1000.0)
     env.reset()
