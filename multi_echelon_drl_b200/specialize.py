@@ -12,7 +12,8 @@ any other.  `BatchedSupplyNetwork` loads it, when present, for `sn_step` / `sn_r
 observe stay on the general library: same state layout).  Trees of five to eight nodes are compiled with eight
 facilities per thread (-DSN_KF=8): a register-resident env where the general library spreads it over eight lanes.
 Results are bit-identical to the general kernels (tests/test_gpu_trees.py); nothing is compiled at run time unless
-`build()` is called.
+`build()` is called or the environment says SN_SPECIALIZE=auto (then the first env built for a tree network compiles
+its library if nvcc is on the path); SN_NO_SPECIALIZED=1 keeps every network on the general library.
 """
 from __future__ import annotations
 
@@ -91,6 +92,10 @@ def load(spec: ScenarioSpec, dtype: str) -> Optional[C.CDLL]:
     if path in _loaded:
         return _loaded[path]
     lib = None
+    if not os.path.isfile(path) and os.environ.get("SN_SPECIALIZE") == "auto":
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "nvcc")):       # 7-10 s of nvcc once per network and quantity type
+            build(spec, dtype)
     if os.path.isfile(path):
         lib = C.CDLL(path)
         for name in ("sn_abi_version", "sn_last_error", "sn_spec_validate", "sn_step_ex", "sn_rollout", "sn_episode"):

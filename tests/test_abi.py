@@ -189,3 +189,30 @@ def test_specialised_tree_library_serves_its_own_network_only():
                         C.byref(_lib.SnPolicy()), None, None, None, None, None, None, None)
     assert rc == _lib.SN_ERR_UNSUPPORTED and b"dtype" in lib.sn_last_error()
     assert specialize.key(star, "int32") != specialize.key(other, "int32") != specialize.key(star, "float32")
+
+
+def test_sn_specialize_auto_builds_the_missing_library_on_first_load(monkeypatch):
+    """SN_SPECIALIZE=auto: specialize.load compiles the library of a tree network that has none yet (nvcc on the path)
+    and serves it; without the switch a missing library means the general kernels (None)."""
+    import shutil
+    if shutil.which("nvcc") is None:
+        pytest.skip("needs nvcc")
+    from multi_echelon_drl_b200 import specialize
+    from multi_echelon_drl_b200.spec import tree_spec
+    tree = tree_spec([dict(name="a", demand=(0, 7), target=11), dict(name="b", target=21), dict(name="c", demand=(0, 3), target=9)],
+                     [("ext", "b", 1, 1), ("b", "c", 1, 2), ("b", "a", 2, 1)], ["a", "b", "c"], True)
+    path = specialize.lib_path(tree, "int32")
+    if os.path.isfile(path):
+        os.remove(path)
+    specialize._loaded.pop(path, None)
+    monkeypatch.delenv("SN_SPECIALIZE", raising=False)
+    assert specialize.load(tree, "int32") is None
+    specialize._loaded.pop(path, None)
+    monkeypatch.setenv("SN_SPECIALIZE", "auto")
+    try:
+        lib = specialize.load(tree, "int32")
+        assert lib is not None and os.path.isfile(path) and lib.sn_abi_version() == specialize._lib.ABI_VERSION
+    finally:
+        specialize._loaded.pop(path, None)
+        if os.path.isfile(path):
+            os.remove(path)          # not one of the libraries build() ships
