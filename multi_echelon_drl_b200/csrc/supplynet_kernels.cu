@@ -11,7 +11,7 @@
 // Every env kernel is written against an `Ops` trait: StdOps = the beer game's lead times (tuned,
 // supplynet_core.cuh), GenOps = run-time per-arc lead times and shorter chains (supplynet_generic.cuh),
 // TreeOps = distribution trees of up to four nodes (supplynet_tree.cuh).  Trees of five to eight nodes have
-// their own kernels with the env in shared memory (k_net_*, supplynet_net.cuh).  The device-side VecNormalize
+// their own kernels with one lane per node, five to eight lanes per env (k_net_*, supplynet_net.cuh).  The device-side VecNormalize
 // kernels live in vecnorm_kernels.cu.
 // Row-major float observations ([n_envs][obs_dim], what a VecEnv returns) are staged per warp
 // in shared memory and written with one TMA bulk store (cp.async.bulk.global.shared::cta) so
@@ -638,44 +638,46 @@ __global__ void __maxnreg__(144) k_rollout_wide(SN_ROLLOUT_PARAMS) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Trees of five to eight nodes (supplynet_net.cuh): one lane per node, four envs per warp, 16 envs per block.
+// Trees of five to eight nodes (supplynet_net.cuh): one lane per node, L lanes per env (L = 5, 6 or 8), 32 / L envs per
+// warp (six, five or four), 16 to 24 envs per block.
 #define SN_NET_PROLOGUE                                                                                        \
-  __shared__ float stage_all[(kNetBlock / 32) * kNetEnvsPerWarp * 7 * kNF];                                    \
+  constexpr int kEnvsPerWarp = 32 / L;                                                                         \
+  __shared__ float stage_all[(kNetBlock / 32) * kEnvsPerWarp * 7 * kNF];                                       \
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                                  \
-  const int64_t warp_env0 = ((int64_t)blockIdx.x * (kNetBlock / 32) + warp) * kNetEnvsPerWarp;                 \
-  const int64_t env = warp_env0 + (lane >> 3);                                                                 \
-  const bool valid = env < n;                                                                                  \
+  const int64_t warp_env0 = ((int64_t)blockIdx.x * (kNetBlock / 32) + warp) * kEnvsPerWarp;                    \
+  const int64_t env = warp_env0 + lane / L;                                                                    \
+  const bool valid = env < n && lane < kEnvsPerWarp * L;          /* (spare lanes of a warp: L = 5, 6) */     \
   const int od = 7 * sp.n_obs;                                                                                 \
-  float* const stage = stage_all + warp * (kNetEnvsPerWarp * 7 * kNF);                                         \
-  const int n_valid = (int)(n - warp_env0 < kNetEnvsPerWarp ? (n - warp_env0 > 0 ? n - warp_env0 : 0) : kNetEnvsPerWarp)
+  float* const stage = stage_all + warp * (kEnvsPerWarp * 7 * kNF);                                            \
+  const int n_valid = (int)(n - warp_env0 < kEnvsPerWarp ? (n - warp_env0 > 0 ? n - warp_env0 : 0) : kEnvsPerWarp)
 
-template <typename T>
+template <typename T, int L>
 __global__ void __launch_bounds__(kNetBlock)
 k_net_reset(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ init,
             const T* __restrict__ demand0, T* __restrict__ state, float* __restrict__ obs) {
   SN_NET_PROLOGUE;
   const NetPolicy<T> none{};
-  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  const LaneCfg<T> c = lane_cfg<L>(sp, none, valid);
   LaneEnv<T> e;
   lane_reset(e, c, init, ld, env, demand0);
   lane_store(e, c, state, ld, env);
   if (obs != nullptr) {
-    const T cb = group_sum(e.B, c.cust, c.base);
-    lane_write_obs(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
+    const T cb = group_sum<L>(e.B, c.cust, c.base);
+    lane_write_obs<L>(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
   }
 }
 
-template <typename T>
+template <typename T, int L>
 __global__ void __launch_bounds__(kNetBlock)
 k_net_observe(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, const T* __restrict__ state,
               float* __restrict__ obs) {
   SN_NET_PROLOGUE;
   const NetPolicy<T> none{};
-  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  const LaneCfg<T> c = lane_cfg<L>(sp, none, valid);
   LaneEnv<T> e;
   lane_load(e, c, state, ld, env);
-  const T cb = group_sum(e.B, c.cust, c.base);
-  lane_write_obs(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
+  const T cb = group_sum<L>(e.B, c.cust, c.base);
+  lane_write_obs<L>(e, c, sp, cb, false, stage, obs + warp_env0 * od, n_valid);
 }
 
 // range guard of the integer path for one lane (= one node): see qty_mask in supplynet_core.cuh
@@ -687,7 +689,7 @@ __device__ __forceinline__ uint32_t lane_qty_mask(const LaneEnv<T>& e, T a, T q)
     return 0u;
 }
 
-template <typename T>
+template <typename T, int L>
 __global__ void __launch_bounds__(kNetBlock)
 k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int period_arg, T* __restrict__ state,
            const T* __restrict__ actions, const T* __restrict__ demand, const StepPtrs out) {
@@ -701,18 +703,18 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int per
   const bool terminal = period + 1 >= sp.t_max;
   const T* __restrict__ demand_next = out.ctl != nullptr ? demand + (int64_t)(period + 1) * ld * sp.n_src : demand;
   const NetPolicy<T> none{};
-  const LaneCfg<T> c = lane_cfg(sp, none, valid);
+  const LaneCfg<T> c = lane_cfg<L>(sp, none, valid);
   LaneEnv<T> e;
   lane_load(e, c, state, ld, env);
   T bj[kNF];
-  group_all(e.B, c.base, bj);
+  group_all<L>(e.B, c.base, bj);
   const T a = (c.active && c.slot >= 0) ? __ldg(actions + env * sp.n_agents + c.slot) : T(0);
   T taken;
-  const T q = lane_order<SN_POLICY_ACTIONS>(e, c, sp, none, masked_sum(bj, c.cust), a, taken);
+  const T q = lane_order<SN_POLICY_ACTIONS>(e, c, sp, none, masked_sum<L>(bj, c.cust), a, taken);
   double hold, back;
-  lane_step(e, c, sp, q, lane_demand(c, demand_next, ld, env), terminal, bj, hold, back);
-  const double reward = group_reward(hold, back, c.base, sp.exact_costs != 0);
-  const T cb = masked_sum(bj, c.cust);
+  lane_step<L>(e, c, sp, q, lane_demand(c, demand_next, ld, env), terminal, bj, hold, back);
+  const double reward = group_reward<L>(hold, back, c.base, sp.exact_costs != 0);
+  const T cb = masked_sum<L>(bj, c.cust);
   const bool over = c.active && qty_mask_over(lane_qty_mask(e, a, q));
   lane_store(e, c, state, ld, env);
   const bool head = valid && c.k == 0;                 // one lane per env reports
@@ -725,7 +727,7 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int per
     if (out.reward64) out.reward64[env] = reward;
     if (out.ep_return) out.ep_return[env] += reward;
   }
-  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, terminal, stage, out.obs + warp_env0 * od, n_valid);
+  if (out.obs != nullptr) lane_write_obs<L>(e, c, sp, cb, terminal, stage, out.obs + warp_env0 * od, n_valid);
   if (over && out.ctl != nullptr) atomicOr(out.ctl + SN_CTL_FLAGS, SN_FLAG_QTY_RANGE);
   if (out.stats != nullptr) {
     double v[14];
@@ -750,7 +752,7 @@ k_net_step(const __grid_constant__ NetSpec<T> sp, int64_t n, int64_t ld, int per
   }
 }
 
-template <typename T, int POLICY>
+template <typename T, int POLICY, int L>
 __global__ void __launch_bounds__(kNetBlock)
 k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ NetPolicy<T> pol, int64_t n, int64_t ld,
               int period0, int n_steps, T* __restrict__ state, const T* __restrict__ demand,
@@ -758,7 +760,7 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
               float* __restrict__ obs0) {
   __shared__ double red[(kNetBlock / 32) * 14];
   SN_NET_PROLOGUE;
-  const LaneCfg<T> c = lane_cfg(sp, pol, valid);
+  const LaneCfg<T> c = lane_cfg<L>(sp, pol, valid);
   uint32_t qmask = 0;
   const int64_t dstride = ld * sp.n_src, act_stride = n * sp.n_agents;
   const bool head = valid && c.k == 0;
@@ -768,9 +770,9 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
   T bj[kNF];                                   // backlog of the eight upstream arcs of this env (same copy in every lane)
   if (init != nullptr) lane_reset(e, c, init, ld, env, demand);
   else lane_load(e, c, state, ld, env);
-  group_all(e.B, c.base, bj);
-  T cb = masked_sum(bj, c.cust);
-  if (init != nullptr && obs0 != nullptr) lane_write_obs(e, c, sp, cb, false, stage, obs0 + warp_env0 * od, n_valid);
+  group_all<L>(e.B, c.base, bj);
+  T cb = masked_sum<L>(bj, c.cust);
+  if (init != nullptr && obs0 != nullptr) lane_write_obs<L>(e, c, sp, cb, false, stage, obs0 + warp_env0 * od, n_valid);
   double total = 0.0;
   // inputs of the next period are requested before this one is computed
   T a_pre = acts ? __ldg(actions + act_off) : T(0);
@@ -788,17 +790,17 @@ k_net_rollout(const __grid_constant__ NetSpec<T> sp, const __grid_constant__ Net
     if (out.traj_actions != nullptr && c.active && c.slot >= 0)
       out.traj_actions[(int64_t)s * act_stride + act_off] = (float)taken;
     double hold, back;
-    lane_step(e, c, sp, q, dn, terminal, bj, hold, back);
+    lane_step<L>(e, c, sp, q, dn, terminal, bj, hold, back);
     qmask |= lane_qty_mask(e, a, q);
-    cb = weighted_sum(bj, c.cust_m);
-    const double r = group_reward(hold, back, c.base, sp.exact_costs != 0);
+    cb = weighted_sum<L>(bj, c.cust_m);
+    const double r = group_reward<L>(hold, back, c.base, sp.exact_costs != 0);
     total += r;
     if (out.traj_reward != nullptr && head) out.traj_reward[(int64_t)s * n + env] = (float)r;
     if (out.traj_obs != nullptr)
-      lane_write_obs(e, c, sp, cb, terminal, stage, out.traj_obs + ((int64_t)s * n + warp_env0) * od, n_valid);
+      lane_write_obs<L>(e, c, sp, cb, terminal, stage, out.traj_obs + ((int64_t)s * n + warp_env0) * od, n_valid);
   }
   const bool ended = (period0 + n_steps >= sp.t_max);
-  if (out.obs != nullptr) lane_write_obs(e, c, sp, cb, ended, stage, out.obs + warp_env0 * od, n_valid);
+  if (out.obs != nullptr) lane_write_obs<L>(e, c, sp, cb, ended, stage, out.obs + warp_env0 * od, n_valid);
   if (state != nullptr) lane_store(e, c, state, ld, env);
   double ep_total = total;
   if (head && out.ep_return) {
@@ -1226,7 +1228,19 @@ inline void allow_smem(K kern, size_t bytes) {
   if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 // net kernels: eight lanes per env
-inline unsigned net_grid(int64_t n) { return (unsigned)((n * sn::kNF + sn::kNetBlock - 1) / sn::kNetBlock); }
+// lanes per env by node count (sn::net_lanes): 5, 6 or 8; a block of four warps holds 4 x (32 / L) envs
+inline unsigned net_grid(int64_t n, int lanes) {
+  const int64_t per_block = (int64_t)(sn::kNetBlock / 32) * (32 / lanes);
+  return (unsigned)((n + per_block - 1) / per_block);
+}
+#define SN_NET_LANES(NF, CALL)            \
+  do {                                    \
+    switch (sn::net_lanes(NF)) {          \
+      case 5: { CALL(5); } break;         \
+      case 6: { CALL(6); } break;         \
+      default: { CALL(8); } break;        \
+    }                                     \
+  } while (0)
 
 // launch with <IDENT, Ops> chosen from the spec: tuned standard kernels (identity specialised or not)
 // or the generic lead-time kernels (always the non-identity code path: fewer instantiations)
@@ -1256,7 +1270,9 @@ int do_reset(const sn_spec* spec, int64_t n, int64_t ld, const void* init, const
              float* obs, cudaStream_t st) {
 #ifndef SN_TREE_ONLY
   if (is_net(spec)) {
-    sn::k_net_reset<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs);
+#define SN_CALL(LN) sn::k_net_reset<T, LN><<<net_grid(n, LN), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)init, (const T*)demand0, (T*)state, obs)
+    SN_NET_LANES(spec->n_facilities, SN_CALL);
+#undef SN_CALL
     return cuda_ok("sn_reset launch");
   }
 #endif
@@ -1271,7 +1287,9 @@ template <typename T>
 int do_observe(const sn_spec* spec, int64_t n, int64_t ld, const void* state, float* obs, cudaStream_t st) {
 #ifndef SN_TREE_ONLY
   if (is_net(spec)) {
-    sn::k_net_observe<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs);
+#define SN_CALL(LN) sn::k_net_observe<T, LN><<<net_grid(n, LN), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, (const T*)state, obs)
+    SN_NET_LANES(spec->n_facilities, SN_CALL);
+#undef SN_CALL
     return cuda_ok("sn_observe launch");
   }
 #endif
@@ -1387,7 +1405,9 @@ int do_step(const sn_spec* spec, int64_t n, int64_t ld, int period, void* state,
             const void* demand, const sn::StepPtrs& out, cudaStream_t st) {
 #ifndef SN_TREE_ONLY
   if (is_net(spec)) {
-    sn::k_net_step<T><<<net_grid(n), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out);
+#define SN_CALL(LN) sn::k_net_step<T, LN><<<net_grid(n, LN), sn::kNetBlock, 0, st>>>(lower_net<T>(spec), n, ld, period, (T*)state, (const T*)actions, (const T*)demand, out)
+    SN_NET_LANES(spec->n_facilities, SN_CALL);
+#undef SN_CALL
     return cuda_ok("sn_step launch");
   }
 #endif
@@ -1481,11 +1501,15 @@ int do_rollout(const sn_spec* spec, int dtype, int64_t n, int64_t ld, int period
     if (nrc != SN_OK) return nrc;
     const auto nd = lower_net<T>(spec);
     if (policy_kind == SN_POLICY_ACTIONS) {
-      sn::k_net_rollout<T, SN_POLICY_ACTIONS><<<net_grid(n), sn::kNetBlock, 0, st>>>(
-          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, (const T*)init, obs0);
+#define SN_CALL(LN) sn::k_net_rollout<T, SN_POLICY_ACTIONS, LN><<<net_grid(n, LN), sn::kNetBlock, 0, st>>>( \
+          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, (const T*)actions, out, (const T*)init, obs0)
+      SN_NET_LANES(spec->n_facilities, SN_CALL);
+#undef SN_CALL
     } else {
-      sn::k_net_rollout<T, SN_POLICY_BASE_STOCK><<<net_grid(n), sn::kNetBlock, 0, st>>>(
-          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, (const T*)init, obs0);
+#define SN_CALL(LN) sn::k_net_rollout<T, SN_POLICY_BASE_STOCK, LN><<<net_grid(n, LN), sn::kNetBlock, 0, st>>>( \
+          nd, np, n, ld, period0, n_steps, (T*)state, (const T*)demand, nullptr, out, (const T*)init, obs0)
+      SN_NET_LANES(spec->n_facilities, SN_CALL);
+#undef SN_CALL
     }
     return cuda_ok("sn_rollout launch");
   }

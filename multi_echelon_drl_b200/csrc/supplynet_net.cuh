@@ -11,7 +11,11 @@
 //   * a supplier subtracts what its customers took and sums their backlog for its observation / cost (8 shuffles);
 //   * the latest demand of a node is the order that just reached it from one particular customer (one shuffle);
 //   * the reward is summed over the nodes in node order (the reference's order) with 2 x 8 double shuffles.
-// Observation rows are assembled per warp in shared memory (4 envs x 7 x n_obs floats) and leave coalesced.
+// Observation rows are assembled per warp in shared memory (envs x 7 x n_obs floats) and leave coalesced.
+// An env takes L lanes, L = 5, 6 or 8 by the node count (template constant): six envs of five nodes, five of six or
+// four of seven / eight share a warp (the two spare lanes of the first two cases idle), and every loop over the
+// nodes of an env is L long.  (Seven lanes for seven nodes: the same four envs per warp and no butterfly for the
+// reward sum: measured slower than eight, 0.758 vs 0.719 ms.)
 // An earlier version kept each env in shared memory under one thread (profiles/r1_notes.md): 4-5x slower.
 //
 // State word map in HBM ([SN_NET_STATE_WORDS = 128][ld]; node k owns words 16k .. 16k+15):
@@ -24,11 +28,12 @@
 
 namespace sn {
 
-constexpr int kNF = 8;                        // lanes per env
-constexpr int kNetEnvsPerWarp = 32 / kNF;     // 4
+constexpr int kNF = 8;                        // most nodes per env (array extents; lanes per env: L <= kNF)
+constexpr int kNetMaxEnvsPerWarp = 6;         // L = 5
 constexpr int kNetStateWords = 16 * kNF;      // 128
 constexpr int kNetInitWords = kNF + 8 * kNF;  // 72
-constexpr int kNetBlock = 128;                // 4 warps = 16 envs per block
+constexpr int kNetBlock = 128;                // 4 warps = 16 .. 24 envs per block
+__host__ __device__ constexpr int net_lanes(int nf) { return nf <= 5 ? 5 : nf == 6 ? 6 : 8; }
 constexpr unsigned kFullMask = 0xffffffffu;
 
 template <typename T>
@@ -68,13 +73,13 @@ struct LaneCfg {
   double h, b;
 };
 
-template <typename T>
+template <int L, typename T>
 __device__ __forceinline__ LaneCfg<T> lane_cfg(const NetSpec<T>& sp, const NetPolicy<T>& pol, bool valid_env) {
   LaneCfg<T> c;
   const int lane = threadIdx.x & 31;
-  c.k = lane & (kNF - 1);
-  c.base = lane & ~(kNF - 1);
-  c.active = valid_env && c.k < sp.nf;
+  c.k = lane % L;
+  c.base = lane - c.k;
+  c.active = valid_env && c.k < sp.nf;               // (valid_env is false on the spare lanes of a warp)
   c.li = sp.li[c.k]; c.ls = sp.ls[c.k]; c.sup = sp.sup[c.k]; c.slot = sp.slot[c.k]; c.pos = sp.pos[c.k];
   c.src = sp.src[c.k]; c.pre = sp.pre[c.k]; c.lat_src = sp.lat_src[c.k];
   c.cust = sp.cust[c.k]; c.before = sp.before[c.k];
@@ -110,38 +115,38 @@ __device__ __forceinline__ void lane_zero(LaneEnv<T>& e) {
 }
 
 // sum of `v` over the lanes of this env whose bit is set in `mask` (all 32 lanes take part)
-template <typename T>
+template <int L, typename T>
 __device__ __forceinline__ T group_sum(T v, unsigned mask, int base) {
   T s = T(0);
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) {
+  for (int j = 0; j < L; ++j) {
     const T x = __shfl_sync(kFullMask, v, base + j);
     s = s + x * (T)((mask >> j) & 1u);
   }
   return s;
 }
 
-// the values of `v` held by the eight nodes of this env
-template <typename T>
+// the values of `v` held by the nodes of this env (entries L.. of `out` are never touched nor read)
+template <int L, typename T>
 __device__ __forceinline__ void group_all(T v, int base, T (&out)[kNF]) {
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) out[j] = __shfl_sync(kFullMask, v, base + j);
+  for (int j = 0; j < L; ++j) out[j] = __shfl_sync(kFullMask, v, base + j);
 }
 
 // sum over the nodes whose bit is set in `mask` of values every lane already holds
-template <typename T>
+template <int L, typename T>
 __device__ __forceinline__ T masked_sum(const T (&v)[kNF], unsigned mask) {
   T s = T(0);
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) s = s + v[j] * (T)((mask >> j) & 1u);
+  for (int j = 0; j < L; ++j) s = s + v[j] * (T)((mask >> j) & 1u);
   return s;
 }
 
-template <typename T>
+template <int L, typename T>
 __device__ __forceinline__ T weighted_sum(const T (&v)[kNF], const T (&w)[kNF]) {
   T s = T(0);
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) s = s + v[j] * w[j];
+  for (int j = 0; j < L; ++j) s = s + v[j] * w[j];
   return s;
 }
 
@@ -247,7 +252,7 @@ __device__ __forceinline__ T lane_order(const LaneEnv<T>& e, const LaneCfg<T>& c
 // One period of this lane's node.  `bj` holds the backlog of all eight upstream arcs of this env (every lane keeps the
 // same copy: it is what customers-served-before-me and my-customers sums are taken from without further shuffles); it
 // is updated to the new state.  Returns the period's holding / backorder cost terms of the node.
-template <typename T>
+template <int L, typename T>
 __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, const NetSpec<T>& sp, T q, T d_next,
                                           bool terminal, T (&bj)[kNF], double& hold, double& back) {
   // receipt on the node's upstream arc (supplynetwork.py:243-255)
@@ -265,12 +270,12 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
   // fills (Arc.fill_orders in aggregate, :260-262): closed form of the rank-ordered service, see the header
   const T a_sup = group_get(e.inv, c.sup, c.base);
   const T avail = c.sup < 0 ? sp.big : a_sup;
-  const T amt = c.active ? tmin(e.B, tmax(T(0), avail - weighted_sum(bj, c.before_m))) : T(0);
+  const T amt = c.active ? tmin(e.B, tmax(T(0), avail - weighted_sum<L>(bj, c.before_m))) : T(0);
   T amt_j[kNF];
-  group_all(amt, c.base, amt_j);
+  group_all<L>(amt, c.base, amt_j);
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) bj[j] = bj[j] - amt_j[j];
-  e.inv = e.inv - weighted_sum(amt_j, c.cust_m);
+  for (int j = 0; j < L; ++j) bj[j] = bj[j] - amt_j[j];
+  e.inv = e.inv - weighted_sum<L>(amt_j, c.cust_m);
   e.B = e.B - amt;
 #pragma unroll
   for (int j = 0; j < 4; ++j) e.ship[j] = e.ship[j] + amt * c.ship_m[j];
@@ -282,7 +287,7 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
     e.unf = tot - sold;
   }
   // cost terms of this node (supplynetwork.py:285-310)
-  const T unf_post = weighted_sum(bj, c.cust_m) + e.unf;
+  const T unf_post = weighted_sum<L>(bj, c.cust_m) + e.unf;
   hold = -(double)e.inv * c.h;
   back = -(double)unf_post * c.b;
   e.dem = d_next;                                                                      // Node.update_demand
@@ -296,10 +301,10 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
     e.B = e.B + arrived;
     e.U[3] = u[3] + u[4];
     T arr_j[kNF];
-    group_all(arrived, c.base, arr_j);
+    group_all<L>(arrived, c.base, arr_j);
     T lat = T(0);
 #pragma unroll
-    for (int j = 0; j < kNF; ++j) {
+    for (int j = 0; j < L; ++j) {
       bj[j] = bj[j] + arr_j[j];
       lat = lat + arr_j[j] * c.lat_m[j];
     }
@@ -313,8 +318,9 @@ __device__ __forceinline__ void lane_step(LaneEnv<T>& e, const LaneCfg<T>& c, co
 // term is an exact multiple of 2^-10 below 2^52 (integer quantities, cost coefficients that are multiples of 2^-10:
 // NetSpec::exact_costs) no addition rounds, the order is immaterial and a 3-step butterfly does (12 shuffles
 // instead of 32); otherwise the terms are added strictly in node order.
+template <int L>
 __device__ __forceinline__ double group_reward(double hold, double back, int base, bool exact) {
-  if (exact) {
+  if (L == 8 && exact) {                     // (the butterfly needs groups aligned to a power of two)
 #pragma unroll
     for (int o = 1; o < kNF; o <<= 1) {
       hold += __shfl_xor_sync(kFullMask, hold, o);
@@ -324,16 +330,16 @@ __device__ __forceinline__ double group_reward(double hold, double back, int bas
   }
   double ch = 0.0, cb = 0.0;
 #pragma unroll
-  for (int j = 0; j < kNF; ++j) {
+  for (int j = 0; j < L; ++j) {
     ch += __shfl_sync(kFullMask, hold, base + j);
     cb += __shfl_sync(kFullMask, back, base + j);
   }
   return ch + cb;
 }
 
-// Observation rows of the warp's four envs, assembled in `stage` ([4][7*n_obs] floats) and copied out coalesced.
-//   dst       global address of the row of the warp's first env;  n_valid: real envs in this warp (0..4)
-template <typename T>
+// Observation rows of the warp's envs, assembled in `stage` ([32 / L][7*n_obs] floats) and copied out coalesced.
+//   dst       global address of the row of the warp's first env;  n_valid: real envs in this warp (0 .. 32 / L)
+template <int L, typename T>
 __device__ __forceinline__ void lane_write_obs(const LaneEnv<T>& e, const LaneCfg<T>& c, const NetSpec<T>& sp, T cust_backlog,
                                                bool terminal, float* stage, float* __restrict__ dst, int n_valid) {
   const int lane = threadIdx.x & 31, od = 7 * sp.n_obs;
@@ -344,7 +350,7 @@ __device__ __forceinline__ void lane_write_obs(const LaneEnv<T>& e, const LaneCf
       const T q = tmax(base_stock(c.target, e.inv, e.U, unf, lat, sp.clb, sp.cub, 0), T(0));
       u3 = u2; u2 = u1; u1 = u0; u0 = q;
     }
-    float* d = stage + (lane >> 3) * od + 7 * c.pos;
+    float* d = stage + (lane / L) * od + 7 * c.pos;
     d[0] = (float)e.inv; d[1] = (float)unf; d[2] = (float)lat;
     d[3] = (float)u0; d[4] = (float)u1; d[5] = (float)u2; d[6] = (float)u3;
   }

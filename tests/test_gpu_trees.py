@@ -321,3 +321,33 @@ def test_single_env_on_big_trees_replays_the_reference_episodes():
         if c["glob"]:
             assert st["on_hand"] == c["obs"][-1][7 * (len(c["names"]) - 1)]
         assert set(st) == {"on_hand", "unfilled_demand", "latest_demand"} | {f"unreceived_pipeline_{i}" for i in range(4)}
+
+
+@pytest.mark.parametrize("nf", [5, 6, 7])
+def test_lane_packed_trees_at_warp_and_block_boundaries(nf):
+    """Trees of five / six nodes take five / six lanes per env: six / five envs share a warp, 24 / 20 a block, two lanes
+    of every warp idle (seven and eight nodes: eight lanes, four envs).  Batch sizes around those boundaries, fused
+    episode + stepwise kernels + observe vs the tree oracle, bit-exact; the buffers' tails stay untouched."""
+    from test_oracle_trees import random_tree_case, random_tree_inputs
+    from multi_echelon_drl_b200.simulator import BatchedSupplyNetwork
+    rs = np.random.RandomState(500 + nf)
+    c = random_tree_case(rs, nf)
+    for n in (1, 4, 5, 6, 7, 19, 20, 21, 23, 24, 25, 47, 49):
+        init, dem, acts = random_tree_inputs(c, n, rs)
+        obs0, obs, rew = tree_oracle_rollout(c, init, dem, acts)
+        sim = BatchedSupplyNetwork(tree_product_spec(c), n, "cuda", "int32")
+        assert sim.fast is None                      # a random topology: the general lane-per-node kernels
+        sim.load_episode(init, dem)
+        T = obs.shape[0]
+        traj = torch.full((T * n * sim.obs_dim + 64,), -7.0, dtype=torch.float32, device="cuda")     # canary tail
+        out = sim.episode(T, actions=torch.as_tensor(acts), traj_obs=traj[: T * n * sim.obs_dim].view(T, n, sim.obs_dim),
+                          record_reward=True)
+        assert np.array_equal(out["traj_obs"].cpu().numpy(), obs), (nf, n)
+        assert (traj[T * n * sim.obs_dim:] == -7.0).all(), (nf, n)
+        assert np.array_equal(out["traj_reward"].cpu().numpy().astype(np.float64), rew.astype(np.float32).astype(np.float64)), (nf, n)
+        assert np.array_equal(sim.ep_return.cpu().numpy(), rew.sum(0)), (nf, n)
+        assert np.array_equal(sim.reset().cpu().numpy(), obs0)
+        for t in range(5):
+            o, _, _ = sim.step(torch.as_tensor(acts[t]))
+            assert np.array_equal(o.cpu().numpy(), obs[t]), (nf, n, t)
+            assert np.array_equal(sim.observe(torch.empty_like(o)).cpu().numpy(), obs[t])
