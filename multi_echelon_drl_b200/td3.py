@@ -19,6 +19,7 @@ explicit here (default: train_freq).  `gradient_steps=-1` reproduces SB3's rule.
 """
 from __future__ import annotations
 
+import math
 import time
 from dataclasses import dataclass, field
 from typing import Optional
@@ -41,6 +42,46 @@ def mlp(inp, hidden, out, out_act=None):
     if out_act is not None:
         layers.append(out_act)
     return nn.Sequential(*layers)
+
+
+class TwinQ(nn.Module):
+    """The twin critics (SB3 `ContinuousCritic(n_critics=2)`): two MLPs of the same shape, initialised like nn.Linear,
+    with their parameters STACKED so that both are evaluated by one batched GEMM per layer - the update graph is bound
+    by its number of small launches, and this halves the critics' share.  `both(x)` -> [2, B]; `self[i](x)` -> [B, 1]
+    is critic i alone (the actor loss uses critic 0 only, SB3 `q1_forward`)."""
+
+    def __init__(self, d_in, hidden, n=2):
+        super().__init__()
+        dims = [d_in, *hidden, 1]
+        self.n = n
+        self.weights, self.biases = nn.ParameterList(), nn.ParameterList()
+        for a, b in zip(dims[:-1], dims[1:]):
+            bound = 1.0 / math.sqrt(a)                  # nn.Linear's default: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both
+            self.weights.append(nn.Parameter(torch.empty(n, a, b).uniform_(-bound, bound)))
+            self.biases.append(nn.Parameter(torch.empty(n, 1, b).uniform_(-bound, bound)))
+
+    def both(self, x):
+        h = x.unsqueeze(0).expand(self.n, -1, -1)
+        last = len(self.weights) - 1
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            h = torch.baddbmm(b, h, w)
+            if i < last:
+                h = torch.relu(h)
+        return h.squeeze(-1)
+
+    def one(self, i, x):
+        last = len(self.weights) - 1
+        for j, (w, b) in enumerate(zip(self.weights, self.biases)):
+            x = torch.addmm(b[i], x, w[i])
+            if j < last:
+                x = torch.relu(x)
+        return x
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return lambda x: self.one(i, x)
 
 
 class ReplayBuffer:
@@ -176,8 +217,8 @@ class HgeTD3:
         mk = lambda m: m.to(self.device)
         self.actor = mk(mlp(od, c.net_arch, ad, nn.Tanh()))
         self.actor_target = mk(mlp(od, c.net_arch, ad, nn.Tanh()))
-        self.critics = nn.ModuleList([mk(mlp(od + ad, c.net_arch, 1)) for _ in range(2)])
-        self.critics_target = nn.ModuleList([mk(mlp(od + ad, c.net_arch, 1)) for _ in range(2)])
+        self.critics = mk(TwinQ(od + ad, c.net_arch))
+        self.critics_target = mk(TwinQ(od + ad, c.net_arch))
         self.actor_target.load_state_dict(self.actor.state_dict())
         self.critics_target.load_state_dict(self.critics.state_dict())
         if ddp:
@@ -377,11 +418,11 @@ class HgeTD3:
                      ).clamp(-c.target_noise_clip, c.target_noise_clip)
             na = (self.actor_target(nobs) + noise).clamp(-1.0, 1.0)
             x = torch.cat([nobs, na], dim=1)
-            q_next = torch.min(self.critics_target[0](x), self.critics_target[1](x)).squeeze(1)
+            q_next = self.critics_target.both(x).amin(0)
             target = rew + (1.0 - done) * c.gamma * q_next
         x = torch.cat([obs, act], dim=1)
-        qs = [m(x).squeeze(1) for m in self.critics]
-        critic_loss = sum(F.mse_loss(q, target) for q in qs)
+        qs = self.critics.both(x)                            # sum over the critics of each one's mean squared error
+        critic_loss = F.mse_loss(qs, target.unsqueeze(0).expand_as(qs), reduction="sum") / qs.shape[1]
         self.critic_opt.zero_grad(set_to_none=True)
         critic_loss.backward()
         self._allreduce_grads(self.critics)

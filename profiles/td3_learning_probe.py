@@ -23,6 +23,8 @@ VARIANTS = {
     "g128_noise02": dict(n=4096, episodes=40, batch_size=1024, lr=1e-3, tau=0.01, noise=0.2, gsteps=128, decay=0.5),
     "g128_lr3e4_e60": dict(n=4096, episodes=60, batch_size=1024, lr=3e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.5),
     "lr3e4_b2048_e60": dict(n=4096, episodes=60, batch_size=2048, lr=3e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.5),
+    "lr3e4_b2048_e80": dict(n=4096, episodes=80, batch_size=2048, lr=3e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.5),
+    "lr3e4_b2048_e80_d35": dict(n=4096, episodes=80, batch_size=2048, lr=3e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.35),
     "lr3e4_b2048_g256": dict(n=4096, episodes=40, batch_size=2048, lr=3e-4, tau=0.01, noise=0.3, gsteps=256, decay=0.5),
     "lr5e4_b2048": dict(n=4096, episodes=40, batch_size=2048, lr=5e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.5),
     "lr3e4_b4096": dict(n=4096, episodes=40, batch_size=4096, lr=3e-4, tau=0.01, noise=0.3, gsteps=128, decay=0.5),

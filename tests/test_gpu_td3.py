@@ -79,16 +79,16 @@ def test_td3_learns_to_beat_random_on_basic_retailer():
 def test_td3_hge_centralized_learns_to_the_heuristics_level(seed):
     """BASELINE config 5 (centralized complex scenario, 4,096 envs, TD3 with heuristic-guided exploration whose rate
     decays linearly like HgeRateCallback, utils/callbacks.py:5-23; collection = three graph replays per vector step,
-    step + VecNormalize as one kernel): 60 episodes with batch 2,048, learning rate 3e-4 and 4 updates per vector step
-    bring the deterministic policy from the uniform-random level (about -16,900 per episode) to the level of the
-    base-stock heuristic that guided it (-1,337).  Measured over seeds 0..3: -814, -1,005, -1,441, -977
-    (profiles/r2_td3_learning.json, which also records the recipes that do NOT learn on every seed: learning rate 1e-3
-    diverges on one seed in four).  Thresholds leave a margin of 2x."""
+    step + VecNormalize as one kernel): 80 episodes with batch 2,048, learning rate 3e-4 and 4 updates per vector step
+    bring the deterministic policy from the uniform-random level (about -16,900 per episode) past the base-stock
+    heuristic that guided it (-1,337).  Measured over seeds 0..7: -840 .. -1,167 (profiles/r2_td3_learning.json, which
+    also records what does NOT hold up: learning rate 1e-3 diverges on one seed in four, 60 episodes leave three
+    seeds in eight near -3,000 .. -5,000)."""
     from multi_echelon_drl_b200 import register_envs as R
     from multi_echelon_drl_b200.td3 import HgeTD3, TD3Config
     from multi_echelon_drl_b200.utils.heuristics import BaseStockPolicy
     from multi_echelon_drl_b200.vec_normalize import VecNormalize
-    n, episodes = 4096, 60
+    n, episodes = 4096, 80
     env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=0, use_graph=True),
                        clip_obs=100.0, clip_reward=1000.0)
     total = n * 100 * episodes
@@ -101,11 +101,11 @@ def test_td3_hge_centralized_learns_to_the_heuristics_level(seed):
     assert model._collect is not None and model._collect.store is not None      # the graphed collection path ran
     assert model.hge_rate == 0.0                                  # decayed to zero half-way through the run
     first, late = model.episode_returns[0], float(np.mean(model.episode_returns[-5:]))
-    assert first < -12000 and late > -4000, model.episode_returns  # training episodes (with exploration noise)
+    assert first < -12000 and late > -3000, model.episode_returns  # training episodes (with exploration noise)
     eval_env = VecNormalize(R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=n, dtype="float32", seed=123),
                             clip_obs=100.0, clip_reward=1000.0)
     mean, std, cnt = model.evaluate(eval_env, n_episodes=1)
-    assert cnt == n and mean > -2700, (mean, std)                 # heuristic: -1,337; uniform random: -16,858
+    assert cnt == n and mean > -2000, (mean, std)                 # heuristic: -1,337; uniform random: -16,858
     model.close()
 
 
