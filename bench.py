@@ -668,19 +668,28 @@ def single_step_numbers(torch, dev, peak):
                     [("ext", "factory", 1, 2), ("factory", "annex", 1, 3), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1),
                      ("hub", "r1", 2, 2), ("hub", "r5", 3, 1), ("hub", "r2", 1, 1), ("hub", "r4", 1, 2)],
                     ["hub", "r1", "r2", "r3", "r4", "r5", "factory", "annex"], True)
-    others = {"rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
+    five = tree_spec([dict(name="hub", target=60), dict(name="r1", demand=(0, 8), target=19), dict(name="r2", demand=(0, 6), target=14),
+                      dict(name="r3", demand=(0, 4), target=10), dict(name="factory", target=40)],
+                     [("ext", "factory", 1, 2), ("factory", "hub", 2, 2), ("hub", "r3", 2, 1), ("hub", "r1", 2, 2), ("hub", "r2", 1, 1)],
+                     ["hub", "r1", "r2", "r3", "factory"], True)
+    others = {"rollout_float32_65536": spec,
+              "rollout_other_leadtimes_65536": replace(spec, info_leadtime=(3, 2, 1, 2), ship_leadtime=(2, 3, 4, 1)),
               "rollout_distribution_tree_65536": tree, "rollout_distribution_tree_65536_specialised": tree,
+              "rollout_tree_5_nodes_65536": five,
               "rollout_tree_8_nodes_65536": big, "rollout_tree_8_nodes_65536_specialised": big}
     t_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     from multi_echelon_drl_b200 import specialize
     for key, sp in others.items():
+        qdtype = "float32" if "float32" in key else "int32"
         acts = torch.randint(0, 17, (T, n, sp.n_agents), generator=g, device=dev, dtype=torch.int32)
+        if qdtype == "float32":                     # TD3's quantities: fractional orders
+            acts = acts.to(torch.float32) + torch.rand(acts.shape, generator=g, device=dev)
         t_obs = torch.empty((T, n, sp.obs_dim), dtype=torch.float32, device=dev)
         # the general tree kernels take the topology at run time; a library compiled for this very network
         # (multi_echelon_drl_b200/specialize.py, prebuilt by __graft_entry__.build()) is measured beside them
         os.environ["SN_NO_SPECIALIZED"] = "0" if key.endswith("_specialised") else "1"
         specialize._loaded.clear()
-        sim = BatchedSupplyNetwork(sp, n, dev, "int32")
+        sim = BatchedSupplyNetwork(sp, n, dev, qdtype)
         os.environ.pop("SN_NO_SPECIALIZED", None)
         if key.endswith("_specialised") and sim.fast is None:
             out[key] = {"unavailable": "no specialised library for this network has been built"}
@@ -699,9 +708,12 @@ def single_step_numbers(torch, dev, peak):
         nbytes = n * T * (4 * sp.n_agents + 4 * sp.n_sources + 4 * sp.obs_dim + 4)
         out[key] = {"env_steps_per_s": n * T / (ms * 1e-3), "kernel_ms": ms, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
                     "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak,
-                    "bound": ("hbm / issue (topology and lead times folded at compile time)" if key.endswith("_specialised") else
+                    "bound": ("hbm (the headline kernel with float32 quantities)" if "float32" in key else
+                              "hbm / issue (topology and lead times folded at compile time)" if key.endswith("_specialised") else
                               "instruction issue (run-time topology / lead times as 0/1 multipliers)"),
-                    "config": ("serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
+                    "config": ("config-2 rollout with float32 quantities and fractional orders (what TD3 feeds the env)" if "float32" in key else
+                               "5-node tree: factory -> hub -> 3 retailers (one lane per node, five lanes per env: six envs per warp)" if "5_nodes" in key else
+                               "serial chain, lead times 3,2,1,2 / 2,3,4,1 (generic kernels)" if "leadtimes" in key else
                                "two-level distribution tree, two demand sources (library specialised for this network)" if key == "rollout_distribution_tree_65536_specialised" else
                                "8-node tree: factory -> {annex, hub -> 5 retailers} (library specialised for this network: eight "
                                "facilities per thread, register-resident)" if key.endswith("_specialised") else
