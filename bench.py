@@ -253,7 +253,7 @@ def run_native(args):
     traj_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     stats_bufs = [torch.zeros(16, dtype=torch.float64, device=dev) for _ in range(2)]
     pending, step_no = [], [0]
-    per_rank_ms = {}
+    per_rank_ms, local_ms = {}, {}
 
     def barrier():
         if world > 1:
@@ -302,6 +302,7 @@ def run_native(args):
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        local_ms[fn.__name__] = float(ms.item())
         if world > 1:
             allms = [torch.zeros_like(ms) for _ in range(world)]
             dist.all_gather(allms, ms)
@@ -321,8 +322,17 @@ def run_native(args):
             b.copy_(sim.stats)
             dist.all_reduce(b, async_op=True).wait()
         step_no[0] = 0
-    ms_dev = timed(device_step, args.steps, 0, record=True)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
+    # the timed region holds the K launches and nothing else (an event pair around every launch keeps consecutive
+    # launches from overlapping their launch latency with the previous kernel's tail: 4-6 us per 152 us step); one step
+    # = one launch, so this rank's time / K is the kernel's average launch duration, gaps included
+    ms_dev = timed(device_step, args.steps, 0, record=False)
+    kernel_ms = local_ms["device_step"] / args.steps
+    for _ in range(min(args.steps, 10)):                  # for the record: the same launches with an event pair each
+        device_step(True)
+    while pending:
+        pending.pop(0).wait()
+    torch.cuda.synchronize()
+    kernel_ms_event_pairs = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
     ms_e2e = timed(e2e_step, max(1, min(args.steps, 10)), min(args.warmup, 3))
     e2e_steps = max(1, min(args.steps, 10))
     clocks = sampler.finish() if sampler else None       # sampled across both timed regions
@@ -405,6 +415,8 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n), "traffic_source": "static ncu capture (profiles/ncu_traffic.json), not measured in this run",
                          "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
+                         "kernel_ms_how": "CUDA events around the K back-to-back launches of the timed region on this rank / K",
+                         "kernel_ms_event_pair_per_launch": kernel_ms_event_pairs,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP_ROLLOUT, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,
         }

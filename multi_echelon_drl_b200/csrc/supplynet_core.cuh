@@ -271,7 +271,11 @@ __device__ __forceinline__ uint32_t qty_mask_state(const E& e) {
     return 0u;
   }
 }
+#ifdef SN_NO_RANGE_GUARD                     /* experiments only: what the guard costs */
+__device__ __forceinline__ bool qty_mask_over(uint32_t) { return false; }
+#else
 __device__ __forceinline__ bool qty_mask_over(uint32_t m) { return (m >> kQtyLimitLog2) != 0; }
+#endif
 struct StepOut {
   double reward;
   double hold[kF], back[kF];
