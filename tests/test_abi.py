@@ -216,3 +216,63 @@ def test_sn_specialize_auto_builds_the_missing_library_on_first_load(monkeypatch
         specialize._loaded.pop(path, None)
         if os.path.isfile(path):
             os.remove(path)          # not one of the libraries build() ships
+
+
+def test_sn_step_ex_and_pack_rows_reject_inconsistent_arguments_before_any_launch(lib):
+    """Host-side validation of the round-2 entry points (no GPU needed: every call fails before its first CUDA call):
+    the combinations of VecNormalize extras that make no sense, multi-item rewards on single-item batches, the terminal
+    period, unknown table types - each with its own message through sn_last_error."""
+    from multi_echelon_drl_b200 import _lib, uniform_spec
+    from multi_echelon_drl_b200.spec import tree_spec
+    spec = uniform_spec(["retailer", "wholesaler", "distributor", "manufacturer"], True).to_c()
+    fake = 1 << 20                                           # an aligned, never dereferenced address
+
+    def call(dtype=_lib.SN_F32, n=64, ld=64, spec=spec, **kw):
+        io = _lib.SnStepIo()
+        io.state, io.actions, io.demand, io.period = fake, fake, fake, 0
+        for k, v in kw.items():
+            setattr(io, k, v)
+        rc = lib.sn_step_ex(C.byref(spec), dtype, n, ld, C.byref(io), None)
+        return rc, lib.sn_last_error().decode()
+
+    assert lib.sn_step_ex(C.byref(spec), _lib.SN_F32, 64, 64, None, None) == _lib.SN_ERR_INVALID
+    rc, msg = call(period=100)
+    assert rc == _lib.SN_ERR_TERMINAL and "terminal" in msg                       # envs.py:88-89
+    rc, msg = call(period=-1)
+    assert rc == _lib.SN_ERR_INVALID and "period=-1" in msg
+    rc, msg = call(actions=fake + 4)
+    assert rc == _lib.SN_ERR_INVALID and "16-byte" in msg
+    rc, msg = call(env_reward=fake)
+    assert rc == _lib.SN_ERR_UNSUPPORTED and "n_items=1" in msg
+    rc, msg = call(vn_scratch=fake)
+    assert rc == _lib.SN_ERR_INVALID and "vn_obs_rms" in msg
+    rc, msg = call(vn_obs_rms=fake)
+    assert rc == _lib.SN_ERR_INVALID and "vn_scratch (update), vn_nobs (normalise)" in msg
+    rc, msg = call(vn_obs_rms=fake, vn_scratch=fake, vn_returns=fake)
+    assert rc == _lib.SN_ERR_INVALID and "vn_ret_rms" in msg
+    rc, msg = call(vn_obs_rms=fake, vn_nobs=fake, vn_ret_rms=fake, vn_returns=fake)
+    assert rc == _lib.SN_ERR_INVALID and "needs vn_scratch" in msg
+    rc, msg = call(vn_obs_rms=fake, vn_scratch=fake, vn_nrew=fake)
+    assert rc == _lib.SN_ERR_INVALID and "vn_nrew needs vn_nobs" in msg
+    rc, msg = call(vn_obs_rms=fake, vn_scratch=fake)
+    assert rc == _lib.SN_ERR_INVALID and "need ctl and obs" in msg
+    rc, msg = call(dtype=_lib.SN_F64, vn_obs_rms=fake, vn_nobs=fake, ctl=fake, obs=fake)
+    assert rc == _lib.SN_ERR_UNSUPPORTED and "SN_I32 / SN_F32" in msg
+    tree = tree_spec([dict(name="a", demand=(0, 7), target=11), dict(name="b", target=21)], [("ext", "b", 1, 1), ("b", "a", 2, 1)],
+                     ["a", "b"], True).to_c()
+    rc, msg = call(spec=tree, vn_obs_rms=fake, vn_scratch=fake, ctl=fake, obs=fake)
+    assert rc == _lib.SN_ERR_UNSUPPORTED and "single-item beer-game chain" in msg
+    rc, msg = call(n=0)
+    assert rc == _lib.SN_ERR_INVALID
+    rc, msg = call(n=64, ld=32)
+    assert rc == _lib.SN_ERR_INVALID
+
+    def pack(src_dtype=_lib.SN_SRC_I64, src=fake, n=8, width=19, stride=19, dtype=_lib.SN_I32, dst=fake, rows=19, ld=32, drs=32):
+        rc = lib.sn_pack_rows(src_dtype, src, n, width, stride, dtype, dst, rows, ld, drs, None)
+        return rc, lib.sn_last_error().decode()
+    assert pack(src=None)[0] == _lib.SN_ERR_INVALID and "NULL" in lib.sn_last_error().decode()
+    for kw in (dict(n=0), dict(rows=18), dict(ld=4), dict(stride=18), dict(drs=16)):
+        rc, msg = pack(**kw)
+        assert rc == _lib.SN_ERR_INVALID and "sn_pack_rows: n_envs=" in msg, kw
+    rc = lib.sn_counter_add(None, 5, None)
+    assert rc == _lib.SN_ERR_INVALID
