@@ -412,14 +412,16 @@ class HgeTD3:
         obs, act, nobs, rew, done = (self.buffer.sample_on_device(c.batch_size) if on_device_sampling
                                      else self.buffer.sample(c.batch_size, self.gen))
         obs, rew = self._normalize(obs, rew, stats)
-        nobs, _ = self._normalize(nobs, rew, stats)
+        if self.vec_normalize is not None:
+            nobs = self.vec_normalize.normalize_obs(nobs, stats)
         with torch.no_grad():
-            noise = (torch.randn(act.shape, device=self.device, generator=gen) * c.target_policy_noise
-                     ).clamp(-c.target_noise_clip, c.target_noise_clip)
-            na = (self.actor_target(nobs) + noise).clamp(-1.0, 1.0)
+            # (few launches on purpose: the update graph is bound by the latency of its chain of small kernels)
+            noise = torch.empty_like(act).normal_(0.0, c.target_policy_noise, generator=gen
+                                                  ).clamp_(-c.target_noise_clip, c.target_noise_clip)
+            na = (self.actor_target(nobs) + noise).clamp_(-1.0, 1.0)
             x = torch.cat([nobs, na], dim=1)
             q_next = self.critics_target.both(x).amin(0)
-            target = rew + (1.0 - done) * c.gamma * q_next
+            target = torch.addcmul(rew, torch.rsub(done, 1.0), q_next, value=c.gamma)      # rew + gamma (1 - done) q
         x = torch.cat([obs, act], dim=1)
         qs = self.critics.both(x)                            # sum over the critics of each one's mean squared error
         critic_loss = F.mse_loss(qs, target.unsqueeze(0).expand_as(qs), reduction="sum") / qs.shape[1]

@@ -81,7 +81,8 @@ def test_td3_hge_centralized_learns_to_the_heuristics_level(seed):
     decays linearly like HgeRateCallback, utils/callbacks.py:5-23; collection = three graph replays per vector step,
     step + VecNormalize as one kernel): 80 episodes with batch 2,048, learning rate 3e-4 and 4 updates per vector step
     bring the deterministic policy from the uniform-random level (about -16,900 per episode) past the base-stock
-    heuristic that guided it (-1,337).  Measured over seeds 0..7: -840 .. -1,167 (profiles/r2_td3_learning.json, which
+    heuristic that guided it (-1,337).  Measured over seeds 0..7 and two builds: -795 .. -1,167 in 15 of 16 runs, one at
+    -2,147 (profiles/r2_td3_learning.json, which
     also records what does NOT hold up: learning rate 1e-3 diverges on one seed in four, 60 episodes leave three
     seeds in eight near -3,000 .. -5,000)."""
     from multi_echelon_drl_b200 import register_envs as R
