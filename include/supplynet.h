@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 9
+#define SN_ABI_VERSION 10
 
 #define SN_MAX_FACILITIES 8     /* size of the per-facility arrays; chains and the register-resident kernels use up to 4 */
 #define SN_MAX_CHAIN 4          /* chains, and trees on the register-resident kernels */
@@ -341,6 +341,31 @@ int32_t sn_counter_add(uint64_t* counter, uint64_t delta, void* stream);
 enum { SN_SRC_I32 = 0, SN_SRC_I64 = 1, SN_SRC_F32 = 2, SN_SRC_F64 = 3 };
 int32_t sn_pack_rows(int32_t src_dtype, const void* src, int64_t n_envs, int32_t width, int64_t src_stride, int32_t dtype,
                      void* dst, int32_t rows, int64_t ld, int64_t dst_row_stride, void* stream);
+
+/* ---- replay buffer of the off-policy trainers (SB3 ReplayBuffer.add / .sample behind train_td3.py:109-123) --------
+ * Five caller-owned float32 arrays of `capacity` rows; the write position, the number of rows stored and the
+ * sampler's stream position live in DEVICE memory, so that one captured launch serves every step of a training loop
+ * whose collection and updates are replayed CUDA graphs.
+ *   sn_replay_add     rows (*pos + r) % capacity <- (obs[r], next_obs[r], act[r], rew[r], done[r]), r = 0..n-1 (done NULL =
+ *                     zeros); obs_carry (NULL or [n][obs_dim], may be `obs` itself) receives next_obs - the loop's "current
+ *                     observation" for the next step; then *pos <- (*pos + n) % capacity, *size <- min(*size + n, capacity).
+ *   sn_replay_sample  row b of the batch = stored row floor(u_b * *size), u_b uniform in [0, 1) drawn from the Philox
+ *                     stream (seed, *counter + b); then *counter += batch.  Uniform with replacement, like SB3. */
+typedef struct sn_replay {
+  float* obs;          /* [capacity][obs_dim] */
+  float* next_obs;     /* [capacity][obs_dim] */
+  float* act;          /* [capacity][act_dim] */
+  float* rew;          /* [capacity]          */
+  float* done;         /* [capacity]          */
+  int64_t capacity;
+  int32_t obs_dim, act_dim;
+  int64_t* pos;        /* device: next row to write       */
+  double* size;        /* device: rows stored so far (<= capacity) */
+} sn_replay;
+int32_t sn_replay_add(const sn_replay* rb, int64_t n, const float* obs, const float* next_obs, const float* act,
+                      const float* rew, const float* done, float* obs_carry, void* stream);
+int32_t sn_replay_sample(const sn_replay* rb, int64_t batch, uint64_t seed, uint64_t* counter, float* obs, float* next_obs,
+                         float* act, float* rew, float* done, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 9
+ABI_VERSION = 10
 SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS, SN_CTL_SEQ = 8, 0, 1, 2, 4
 SN_VN_ONEPASS_SCRATCH_DOUBLES = 256 * 128
 SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
@@ -81,6 +81,15 @@ class SnStepIo(C.Structure):
     ]
 
 
+class SnReplay(C.Structure):
+    """sn_replay of include/supplynet.h: the device replay buffer's arrays and its counters in device memory."""
+    _fields_ = [
+        ("obs", C.c_void_p), ("next_obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p),
+        ("capacity", C.c_int64), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
+        ("pos", C.c_void_p), ("size", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/supplynet.h one to one
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
@@ -105,6 +114,8 @@ SIGNATURES = {
     "sn_fill_normal_demand_at": (_I32, [_I32, _P, _I64, C.c_double, C.c_double, C.c_uint64, _P, C.c_uint64, _P]),
     "sn_counter_add": (_I32, [_P, C.c_uint64, _P]),
     "sn_pack_rows": (_I32, [_I32, _P, _I64, _I32, _I64, _I32, _P, _I32, _I64, _I64, _P]),
+    "sn_replay_add": (_I32, [C.POINTER(SnReplay), _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_replay_sample": (_I32, [C.POINTER(SnReplay), _I64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -19,6 +19,7 @@ explicit here (default: train_freq).  `gradient_steps=-1` reproduces SB3's rule.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import time
 from dataclasses import dataclass, field
@@ -97,7 +98,9 @@ class ReplayBuffer:
         self.done = torch.zeros((capacity,), **kw)
         self.size_t = torch.zeros((), dtype=torch.float64, device=device)   # len(self) on the device (graph replays read it)
         self.pos_t = torch.zeros((), dtype=torch.int64, device=device)      # write position on the device (add_on_device)
-        self._lane = None
+        self.draws_t = torch.zeros((), dtype=torch.int64, device=device)    # stream position of the device sampler
+        self.sample_seed = 0
+        self._c, self._lib = None, None
 
     def __len__(self):
         return self.capacity if self.full else self.pos
@@ -114,17 +117,39 @@ class ReplayBuffer:
         self.size_t.fill_(float(len(self)))
         self.pos_t.fill_(self.pos)
 
-    def add_on_device(self, obs, next_obs, act, rew, done):
-        """`add` with the write position and the length read from / advanced in device memory: nothing of it depends
-        on host state, so one captured graph stores every vector step.  The host mirrors move with `advance_host`."""
+    def _c_buffer(self):
+        """sn_replay view of the tensors (include/supplynet.h); None off the GPU (unit tests of the host logic)."""
+        if self.obs.device.type != "cuda":
+            return None
+        if self._c is None:
+            from . import _lib
+            self._lib = _lib.load()
+            c = _lib.SnReplay()
+            c.obs, c.next_obs, c.act = self.obs.data_ptr(), self.next_obs.data_ptr(), self.act.data_ptr()
+            c.rew, c.done = self.rew.data_ptr(), self.done.data_ptr()
+            c.capacity, c.obs_dim, c.act_dim = self.capacity, self.obs.shape[1], self.act.shape[1]
+            c.pos, c.size = self.pos_t.data_ptr(), self.size_t.data_ptr()
+            self._c = c
+        return self._c
+
+    @staticmethod
+    def _f32(t):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("the device replay buffer takes contiguous float32 tensors")
+        return t.data_ptr()
+
+    def add_on_device(self, obs, next_obs, act, rew, done=None, carry=None):
+        """`add` with the write position and the length read from / advanced in device memory (sn_replay_add: two
+        launches): nothing of it depends on host state, so one captured graph stores every vector step.  `done` None =
+        zeros; `carry` (may be `obs` itself) receives next_obs - the loop's current observation for the next step.
+        The host mirrors move with `advance_host`."""
+        from . import _lib
+        c = self._c_buffer()
         n = obs.shape[0]
-        if self._lane is None or self._lane.shape[0] != n:
-            self._lane = torch.arange(n, device=obs.device)
-        idx = (self._lane + self.pos_t) % self.capacity
-        self.obs[idx], self.next_obs[idx], self.act[idx] = obs, next_obs, act
-        self.rew[idx], self.done[idx] = rew, done.to(torch.float32)
-        self.pos_t.add_(n).remainder_(self.capacity)
-        self.size_t.add_(float(n)).clamp_(max=float(self.capacity))
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        _lib.check(self._lib.sn_replay_add(C.byref(c), n, self._f32(obs), self._f32(next_obs), self._f32(act), self._f32(rew),
+                                           None if done is None else self._f32(done),
+                                           None if carry is None else self._f32(carry), stream))
 
     def advance_host(self, n):
         self.full = self.full or (self.pos + n >= self.capacity)
@@ -135,12 +160,18 @@ class ReplayBuffer:
         return self.obs[idx], self.act[idx], self.next_obs[idx], self.rew[idx], self.done[idx]
 
     def sample_on_device(self, batch_size):
-        """Same draw with the buffer length read from device memory and the default CUDA generator: safe to
-        capture in a CUDA graph (the length baked into `sample` would go stale across replays)."""
-        u = torch.rand(batch_size, device=self.obs.device, dtype=torch.float64)
-        idx = (u * self.size_t).long()
-        return self.obs[idx], self.act[idx], self.next_obs[idx], self.rew[idx], self.done[idx]
-
+        """The same draw with the buffer length read from device memory and the sampler's stream position kept there
+        (sn_replay_sample: Philox stream (sample_seed, draws_t), two launches instead of eight indexing kernels): safe
+        to capture in a CUDA graph (the length baked into `sample` would go stale across replays)."""
+        from . import _lib
+        c = self._c_buffer()
+        kw = dict(dtype=torch.float32, device=self.obs.device)
+        obs, nobs = torch.empty((batch_size, self.obs.shape[1]), **kw), torch.empty((batch_size, self.obs.shape[1]), **kw)
+        act, rew, done = torch.empty((batch_size, self.act.shape[1]), **kw), torch.empty(batch_size, **kw), torch.empty(batch_size, **kw)
+        stream = C.c_void_p(torch.cuda.current_stream(self.obs.device).cuda_stream)
+        _lib.check(self._lib.sn_replay_sample(C.byref(c), batch_size, self.sample_seed, self.draws_t.data_ptr(), obs.data_ptr(),
+                                              nobs.data_ptr(), act.data_ptr(), rew.data_ptr(), done.data_ptr(), stream))
+        return obs, act, nobs, rew, done
 
 @dataclass
 class TD3Config:
@@ -232,6 +263,7 @@ class HgeTD3:
         self._pi_graphs, self._pi_seen = {}, {}
         self._collect, self._collect_warm, self._orig = None, 0, None
         self.buffer = ReplayBuffer(c.buffer_size, od, ad, self.device)
+        self.buffer.sample_seed = int(c.seed)
         self.hge_schedule = HgeRateSchedule(c.hge_rate_at_start, c.hge_decay_periods)
         self.hge_rate = c.hge_rate_at_start if heuristic is not None else 0.0
         self.num_timesteps, self.n_updates = 0, 0
@@ -382,22 +414,16 @@ class HgeTD3:
         cg = self._collect
         key = (new_orig.data_ptr(), raw_rew.data_ptr())
         if cg.store is None:
-            cg.no_done = torch.zeros(orig.shape[0], dtype=torch.float32, device=self.device)
-        dones = cg.no_done                 # this path stores non-terminal steps only (float already: no cast launch)
-        if cg.store is None:
-            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)      # eagerly once (sets up the lane index)
-            orig.copy_(new_orig)
-            cg.keep = (new_orig, raw_rew, dones)
-
-            def store():
-                self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)
-                orig.copy_(new_orig)
-            cg.store, cg.store_key = self._capture(store), key
+            # eagerly once, then the same two launches as a graph: (orig, new_orig, scaled action, reward, done = 0) into
+            # the buffer at its device-side position, and orig <- new_orig in the same kernel
+            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, None, carry=orig)
+            cg.keep = (new_orig, raw_rew)
+            cg.store = self._capture(lambda: self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, None, carry=orig))
+            cg.store_key = key
         elif key == cg.store_key:
             cg.store.replay()
         else:
-            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, dones)
-            orig.copy_(new_orig)
+            self.buffer.add_on_device(orig, new_orig, cg.scaled, raw_rew, None, carry=orig)
         self.buffer.advance_host(orig.shape[0])
 
     def _normalize(self, obs, rew, stats=None):

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"libsupplynet.so does not export {name}"
     assert set(_lib.SIGNATURES) == declared, "ctypes binding and header disagree on the entry points"
-    assert lib.sn_abi_version() == 9
+    assert lib.sn_abi_version() == 10
 
 
 def test_struct_layout_matches_header(tmp_path):
