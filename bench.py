@@ -253,6 +253,15 @@ def run_native(args):
     traj_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     stats_bufs = [torch.zeros(16, dtype=torch.float64, device=dev) for _ in range(2)]
     pending, step_no = [], [0]
+    # the statistics all-reduce: one kernel over peer memory (sn_stats_allreduce) where the ranks can map each other's
+    # mailboxes, NCCL otherwise; the JSON line says which ran
+    peer_ar, peer_ar_why = None, None
+    if world > 1 and not args.nccl_stats:
+        try:
+            from multi_echelon_drl_b200.distributed import PeerStatsAllReduce
+            peer_ar = PeerStatsAllReduce(dev)
+        except Exception as exc:          # noqa: BLE001  (no peer mapping on this box: NCCL carries the vector)
+            peer_ar_why = f"{type(exc).__name__}: {exc}"[:200]
     per_rank_ms, local_ms = {}, {}
 
     def barrier():
@@ -277,6 +286,9 @@ def run_native(args):
             # episodes, and once more at the end of the timed region).  Issued asynchronously on NCCL's
             # stream with two alternating buffers so that it overlaps the next episode's kernel.
             buf = stats_bufs[(step_no[0] // args.stats_interval) % 2]
+            if peer_ar is not None:       # one small launch on this stream: stores to the peers, sum of what arrived
+                peer_ar(sim.stats, buf)
+                return
             while len(pending) >= 2:
                 pending.pop(0).wait()
             buf.copy_(sim.stats)
@@ -295,8 +307,11 @@ def run_native(args):
         for _ in range(steps):
             fn(**kw) if kw else fn()
         if world > 1 and fn is device_step:           # end-of-interval reduction of the accumulated statistics
-            stats_bufs[0].copy_(sim.stats)
-            pending.append(dist.all_reduce(stats_bufs[0], async_op=True))
+            if peer_ar is not None:
+                peer_ar(sim.stats, stats_bufs[0])
+            else:
+                stats_bufs[0].copy_(sim.stats)
+                pending.append(dist.all_reduce(stats_bufs[0], async_op=True))
         while pending:
             pending.pop(0).wait()
         e.record()
@@ -319,8 +334,11 @@ def run_native(args):
         # the statistics all-reduce is part of the steady state: warm it up too (the first collectives of a process
         # set up channels and load kernels, milliseconds that do not belong to a 50-step window)
         for b in stats_bufs * 2:
-            b.copy_(sim.stats)
-            dist.all_reduce(b, async_op=True).wait()
+            if peer_ar is not None:
+                peer_ar(sim.stats, b)
+            else:
+                b.copy_(sim.stats)
+                dist.all_reduce(b, async_op=True).wait()
         step_no[0] = 0
     # the timed region holds the K launches and nothing else (an event pair around every launch keeps consecutive
     # launches from overlapping their launch latency with the previous kernel's tail: 4-6 us per 152 us step); one step
@@ -343,6 +361,22 @@ def run_native(args):
     torch.cuda.synchronize()
     assert float(sim.stats[0].item()) == n * T, "stats vector: wrong env-step count"
     assert float(sim.stats[1].item()) == float(traj_rew.double().sum().item()), "stats vector disagrees with trajectory"
+
+    # the peer-memory all-reduce against NCCL on the same vector (each rank contributes something different)
+    stats_exchange = None
+    if world > 1:
+        if peer_ar is not None:
+            probe = sim.stats.clone() * (1.0 + rank) + rank
+            via_nccl = probe.clone()
+            dist.all_reduce(via_nccl)
+            via_peer = peer_ar(probe, torch.empty_like(probe))
+            torch.cuda.synchronize()
+            same = bool(torch.allclose(via_peer, via_nccl, rtol=1e-13, atol=0.0))
+            assert same, "sn_stats_allreduce disagrees with NCCL"
+            stats_exchange = {"how": "one kernel over peer memory (sn_stats_allreduce: stores into every rank's mailbox over NVLink, sum in rank order)",
+                              "equals_nccl": same, "calls": peer_ar.seq}
+        else:
+            stats_exchange = {"how": "NCCL all-reduce", "why_not_peer_memory": peer_ar_why or "--nccl-stats"}
 
     # shard invariance across real devices: the envs of one global batch, sharded by index over the ranks,
     # give bit for bit what the whole batch gives on ONE GPU (rank 0 runs it and compares every env)
@@ -406,7 +440,8 @@ def run_native(args):
             "config": {"workload": WORKLOAD.format(n=n, T=T),
                        "envs_per_gpu": n, "periods": T, "step": "one sn_episode launch (in-kernel reset + 100 periods, 1 episode of the batch)",
                        "l2": "inputs+outputs ~0.9 GB per step >> 126 MB L2, no flush needed",
-                       "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of the 16-double statistics vector every {args.stats_interval} episodes"},
+                       "parallelism": f"env-sharded x{world}, no data-path collective; all-reduce of the 16-double statistics vector every {args.stats_interval} episodes"
+                                      + ("" if world == 1 else " (one kernel over peer memory)" if peer_ar is not None else " (NCCL)")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks,
@@ -422,6 +457,7 @@ def run_native(args):
         }
         if world > 1:
             line["per_rank_ms_per_step"] = per_rank_ms      # device time of every rank (value uses the max)
+            line["stats_exchange"] = stats_exchange
             line["shard_invariance"] = {"ok": shard_check, "envs": 8192 * world,
                                         "what": "every env of a global batch sharded by index over the ranks equals, bit for bit "
                                                 "(position-weighted trajectory checksum, episode return), the same env when "
@@ -430,6 +466,8 @@ def run_native(args):
         line.update(blocks)
         print(json.dumps(line))
     if world > 1:
+        if peer_ar is not None:
+            peer_ar.close()
         dist.destroy_process_group()
 
 
@@ -915,6 +953,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-5 blocks of the default line")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's socket")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-step / heuristic figures")
+    ap.add_argument("--nccl-stats", action="store_true", help="N>1: carry the statistics vector with NCCL instead of the peer-memory kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

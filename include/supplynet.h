@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SN_ABI_VERSION 10
+#define SN_ABI_VERSION 11
 
 #define SN_MAX_FACILITIES 8     /* size of the per-facility arrays; chains and the register-resident kernels use up to 4 */
 #define SN_MAX_CHAIN 4          /* chains, and trees on the register-resident kernels */
@@ -366,6 +366,37 @@ int32_t sn_replay_add(const sn_replay* rb, int64_t n, const float* obs, const fl
                       const float* rew, const float* done, float* obs_carry, void* stream);
 int32_t sn_replay_sample(const sn_replay* rb, int64_t batch, uint64_t seed, uint64_t* counter, float* obs, float* next_obs,
                          float* act, float* rew, float* done, void* stream);
+
+/* ---- the path's only collective: all-reduce (sum) of the statistics vector, ONE kernel over peer memory ------------
+ * Ranks (one process per GPU, envs sharded by index) exchange nothing but the SN_STATS_WORDS doubles that sn_step /
+ * sn_rollout / sn_episode accumulate (the reference has no multi-device path: train_td3.py:82,100 builds
+ * n_env = 2 sequential envs in one process).  Every rank owns a MAILBOX in device memory that all peers map over
+ * NVLink; sn_stats_allreduce stores this rank's vector into every rank's mailbox (16-byte entries carrying value and
+ * sequence tag together), waits until its own mailbox holds all ranks' vectors of this call, and writes their sum in
+ * rank order (bit-identical on every rank) to stats_out (may be stats_in).  One launch of 16 x world threads on the
+ * caller's stream; no library stream, no copy, nothing to synchronise on the host.
+ *   sn_mail_bytes(world)          size of one mailbox (2 parities x world slots x 16 entries of 16 bytes)
+ *   sn_mail_alloc(world, &mail, handle)   cudaMalloc + zero fill on the CURRENT device; handle: SN_MAIL_HANDLE_BYTES
+ *                                 bytes to send to the peers (all zero if the memory cannot be exported: then it
+ *                                 serves ranks inside this process only, see sn_enable_peer_access)
+ *   sn_mail_open(handle, &peer)   maps a peer's mailbox into this process (peer access enabled by the driver)
+ *   sn_mail_close / sn_mail_free  release what sn_mail_open / sn_mail_alloc returned
+ *   sn_enable_peer_access(d, p)   one process driving several GPUs: lets kernels on device d write to device p
+ *   sn_stats_allreduce(in, out, mails, rank, world, seq, stream)
+ *                                 mails: DEVICE array of `world` mailbox pointers as mapped in this process
+ *                                 (entry `rank` = the own mailbox); seq = 1, 2, 3, ... the same on every rank, one
+ *                                 per call; all ranks make the same calls in the same order, each on one stream.
+ *                                 A peer that does not arrive within about half a minute traps the kernel. */
+#define SN_MAIL_MAX_RANKS 16
+#define SN_MAIL_HANDLE_BYTES 64
+int64_t sn_mail_bytes(int32_t world);
+int32_t sn_mail_alloc(int32_t world, void** mail, unsigned char* handle);
+int32_t sn_mail_open(const unsigned char* handle, void** peer_mail);
+int32_t sn_mail_close(void* peer_mail);
+int32_t sn_mail_free(void* mail);
+int32_t sn_enable_peer_access(int32_t device, int32_t peer);
+int32_t sn_stats_allreduce(const double* stats_in, double* stats_out, void* const* mails, int32_t rank, int32_t world,
+                           uint32_t seq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ SN_TOPO_CHAIN, SN_TOPO_TREE = 0, 1
 SN_POLICY_ACTIONS, SN_POLICY_BASE_STOCK = 0, 1
 SN_STATE_WORDS, SN_INIT_WORDS, SN_STATS_WORDS = 40, 19, 16
 SN_OK, SN_ERR_INVALID, SN_ERR_UNSUPPORTED, SN_ERR_TERMINAL, SN_ERR_CUDA, SN_ERR_TYPE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 10
+ABI_VERSION = 11
 SN_CTL_WORDS, SN_CTL_PERIOD, SN_CTL_TICKET, SN_CTL_FLAGS, SN_CTL_SEQ = 8, 0, 1, 2, 4
 SN_VN_ONEPASS_SCRATCH_DOUBLES = 256 * 128
 SN_FLAG_STEP_AFTER_TERMINAL, SN_FLAG_QTY_RANGE = 1, 2
@@ -116,6 +116,13 @@ SIGNATURES = {
     "sn_pack_rows": (_I32, [_I32, _P, _I64, _I32, _I64, _I32, _P, _I32, _I64, _I64, _P]),
     "sn_replay_add": (_I32, [C.POINTER(SnReplay), _I64, _P, _P, _P, _P, _P, _P, _P]),
     "sn_replay_sample": (_I32, [C.POINTER(SnReplay), _I64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_mail_bytes": (_I64, [_I32]),
+    "sn_mail_alloc": (_I32, [_I32, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "sn_mail_open": (_I32, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "sn_mail_close": (_I32, [_P]),
+    "sn_mail_free": (_I32, [_P]),
+    "sn_enable_peer_access": (_I32, [_I32, _I32]),
+    "sn_stats_allreduce": (_I32, [_P, _P, _P, _I32, _I32, C.c_uint32, _P]),
     "sn_episode": (_I32, [C.POINTER(SnSpec), _I32, _I64, _I64, _I32, _P, _P, _I32, _P, C.POINTER(SnPolicy),
                           _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

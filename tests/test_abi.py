@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"libsupplynet.so does not export {name}"
     assert set(_lib.SIGNATURES) == declared, "ctypes binding and header disagree on the entry points"
-    assert lib.sn_abi_version() == 10
+    assert lib.sn_abi_version() == 11
 
 
 def test_struct_layout_matches_header(tmp_path):
@@ -276,3 +276,24 @@ def test_sn_step_ex_and_pack_rows_reject_inconsistent_arguments_before_any_launc
         assert rc == _lib.SN_ERR_INVALID and "sn_pack_rows: n_envs=" in msg, kw
     rc = lib.sn_counter_add(None, 5, None)
     assert rc == _lib.SN_ERR_INVALID
+
+
+def test_stats_exchange_argument_validation(lib):
+    """sn_mail_bytes / sn_stats_allreduce (the peer-memory all-reduce of the statistics vector) reject bad arguments
+    before anything is launched (host-only: no GPU here)."""
+    from multi_echelon_drl_b200 import _lib
+    assert lib.sn_mail_bytes(1) == 2 * 1 * 16 * 16 and lib.sn_mail_bytes(8) == 2 * 8 * 16 * 16
+    assert lib.sn_mail_bytes(0) == _lib.SN_ERR_INVALID and lib.sn_mail_bytes(17) == _lib.SN_ERR_INVALID
+    fake = C.c_void_p(0x1000)
+
+    def call(stats=fake, out=fake, mails=fake, rank=0, world=2, seq=1):
+        return lib.sn_stats_allreduce(stats, out, mails, rank, world, seq, None), lib.sn_last_error().decode()
+    assert call(stats=None)[0] == _lib.SN_ERR_INVALID
+    assert call(mails=None)[0] == _lib.SN_ERR_INVALID
+    for kw in (dict(world=0), dict(world=17), dict(rank=2), dict(rank=-1)):
+        rc, msg = call(**kw)
+        assert rc == _lib.SN_ERR_INVALID and "rank" in msg, kw
+    rc, msg = call(seq=0)
+    assert rc == _lib.SN_ERR_INVALID and "seq counts from 1" in msg
+    assert lib.sn_mail_alloc(2, None, None) == _lib.SN_ERR_INVALID
+    assert lib.sn_mail_open(None, None) == _lib.SN_ERR_INVALID

@@ -34,3 +34,74 @@ def test_index_sharding_over_devices_equals_one_device():
     assert torch.equal(torch.cat([p[0] for p in parts], dim=1), whole[0])
     assert torch.equal(torch.cat([p[1] for p in parts], dim=1), whole[1])
     assert torch.equal(torch.cat([p[2] for p in parts]), whole[2])
+
+
+def _mailboxes(lib, devices, world):
+    """One mailbox per device of this process, every device allowed to write to every other one."""
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    mails = []
+    for d in devices:
+        with torch.cuda.device(d):
+            m, h = C.c_void_p(), (C.c_ubyte * 64)()
+            _lib.check(lib.sn_mail_alloc(world, C.byref(m), h))
+            mails.append(m)
+    for a in devices:
+        for b in devices:
+            _lib.check(lib.sn_enable_peer_access(a, b))
+    return mails
+
+
+def test_stats_allreduce_single_rank_is_the_identity_over_many_calls():
+    """sn_stats_allreduce with one rank: the vector goes through the rank's own mailbox (both slot parities, growing
+    sequence tags) and comes back unchanged, in place and out of place."""
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    lib = _lib.load()
+    mails = _mailboxes(lib, [0], 1)
+    ptrs = torch.tensor([mails[0].value], dtype=torch.int64, device="cuda:0")
+    g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+    for seq in range(1, 8):
+        x = torch.randn(16, dtype=torch.float64, device="cuda:0", generator=g) * 1e6
+        y = torch.empty_like(x)
+        _lib.check(lib.sn_stats_allreduce(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(ptrs.data_ptr()), 0, 1,
+                                          seq, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert torch.equal(x, y)
+        keep = x.clone()
+        _lib.check(lib.sn_stats_allreduce(C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(ptrs.data_ptr()), 0, 1,
+                                          seq + 100, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert torch.equal(x, keep)
+    torch.cuda.synchronize()
+    _lib.check(lib.sn_mail_free(mails[0]))
+
+
+def test_stats_allreduce_over_peer_memory_equals_the_sum_in_rank_order():
+    """All visible GPUs as the ranks of one process: every rank's kernel stores into every mailbox over NVLink and sums
+    what arrives; all ranks get the same bits, equal to the float64 sum taken in rank order, call after call."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two or more GPUs")
+    import ctypes as C
+    from multi_echelon_drl_b200 import _lib
+    lib = _lib.load()
+    G = min(torch.cuda.device_count(), 8)
+    mails = _mailboxes(lib, list(range(G)), G)
+    ptrs = [torch.tensor([m.value for m in mails], dtype=torch.int64, device=f"cuda:{d}") for d in range(G)]
+    rs = np.random.RandomState(1)
+    for seq in range(1, 12):
+        host = rs.randn(G, 16) * 10.0 ** rs.randint(-3, 9, (G, 16))
+        xs = [torch.as_tensor(host[d]).to(f"cuda:{d}") for d in range(G)]
+        ys = [torch.empty_like(x) for x in xs]
+        for d in range(G):                                   # every rank launches before anybody synchronises
+            with torch.cuda.device(d):
+                _lib.check(lib.sn_stats_allreduce(C.c_void_p(xs[d].data_ptr()), C.c_void_p(ys[d].data_ptr()),
+                                                  C.c_void_p(ptrs[d].data_ptr()), d, G, seq,
+                                                  C.c_void_p(torch.cuda.current_stream(d).cuda_stream)))
+        want = np.zeros(16)
+        for d in range(G):
+            want = want + host[d]
+        for d in range(G):
+            torch.cuda.synchronize(d)
+            assert np.array_equal(ys[d].cpu().numpy(), want), (seq, d)
+    for d in range(G):
+        with torch.cuda.device(d):
+            _lib.check(lib.sn_mail_free(mails[d]))
