@@ -10,6 +10,7 @@ Statistics vector layout (SN_STATS_WORDS = 16 doubles, include/supplynet.h):
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional, Tuple
 
 import torch
@@ -65,19 +66,29 @@ class PeerStatsAllReduce:
             raise RuntimeError("PeerStatsAllReduce needs an initialised process group")
         self._lib, self._C, self._check = _lib.load(), C, _lib.check
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 16:
             raise NotImplementedError("PeerStatsAllReduce: at most 16 ranks (one node)")
         self._peers, self._mail, self.seq = [], None, 0
-        with torch.cuda.device(self.device):
-            mail, handle = C.c_void_p(), (C.c_ubyte * 64)()
-            _lib.check(self._lib.sn_mail_alloc(self.world, C.byref(mail), handle))
-            self._mail = mail
+        cuda = self.device.type == "cuda" and torch.cuda.is_available()
+        with (torch.cuda.device(self.device) if cuda else contextlib.nullcontext()):
+            # a rank that fails early still takes part in both exchanges below: nobody is left waiting in a collective
+            mail, handle, err = C.c_void_p(), (C.c_ubyte * 64)(), None
+            if not cuda:
+                err = "no CUDA device"
+            elif self._lib.sn_mail_alloc(self.world, C.byref(mail), handle) != 0:
+                err = self._lib.sn_last_error().decode()
+            else:
+                self._mail = mail
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle), group=group)
-            ptrs, err = [], None
+            ptrs = []
             for r, h in enumerate(handles):
+                if err is not None:
+                    break
                 if r == self.rank:
                     ptrs.append(mail.value)
                     continue
@@ -93,7 +104,7 @@ class PeerStatsAllReduce:
             dist.all_gather_object(ok, err is None, group=group)
             if not all(ok):
                 self.close(barrier=False)
-                raise RuntimeError(f"PeerStatsAllReduce: peer mailboxes cannot be mapped on every rank ({err})")
+                raise RuntimeError(f"PeerStatsAllReduce: peer mailboxes cannot be mapped on every rank ({err or 'another rank failed'})")
             self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)
@@ -113,7 +124,7 @@ class PeerStatsAllReduce:
 
     def close(self, barrier: bool = True):
         """Unmaps the peers' mailboxes and frees the own one (after a barrier: nobody may still be writing to it)."""
-        if self._mail is None:
+        if self._mail is None and not self._peers:
             return
         torch.cuda.synchronize(self.device)
         if barrier:
@@ -124,7 +135,8 @@ class PeerStatsAllReduce:
             self._peers = []
             if barrier:
                 dist.barrier(group=self.group)                      # every peer has unmapped it
-            self._lib.sn_mail_free(self._mail)
+            if self._mail is not None:
+                self._lib.sn_mail_free(self._mail)
         self._mail = None
 
 

@@ -76,3 +76,35 @@ def test_allreduce_stats_is_identity_without_process_group():
     assert torch.equal(allreduce_stats(st.clone()), st)
     with pytest.raises(ValueError):
         allreduce_stats(torch.zeros(3, dtype=torch.float64))
+
+
+def _peer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from multi_echelon_drl_b200.distributed import PeerStatsAllReduce, allreduce_stats
+    try:
+        PeerStatsAllReduce(torch.device("cpu"))
+        msg = "constructed"
+    except RuntimeError as exc:
+        msg = str(exc)
+    # the group is still usable afterwards: the NCCL / gloo form carries the vector
+    st = allreduce_stats(torch.full((16,), float(rank + 1), dtype=torch.float64))
+    torch.save((msg, st), f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_peer_memory_allreduce_refuses_together_where_there_is_no_device(tmp_path):
+    """Without a CUDA device the peer-memory exchange cannot be built: every rank learns that in the same two
+    collectives and raises (nobody is left waiting), and the process group keeps working for `allreduce_stats`
+    (the fallback bench.py takes)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "peer")
+    mp.spawn(_peer_worker, args=(2, port, out), nprocs=2, join=True)
+    for rank in range(2):
+        msg, st = torch.load(f"{out}.{rank}")
+        assert "cannot be mapped on every rank" in msg
+        assert torch.equal(st, torch.full((16,), 3.0, dtype=torch.float64))
