@@ -105,3 +105,36 @@ def test_stats_allreduce_over_peer_memory_equals_the_sum_in_rank_order():
     for d in range(G):
         with torch.cuda.device(d):
             _lib.check(lib.sn_mail_free(mails[d]))
+
+
+def test_peer_stats_allreduce_class_on_a_one_rank_group(tmp_path):
+    """distributed.PeerStatsAllReduce end to end on the one GPU of the test box: mailbox allocation, the handle exchange
+    through the process group (one rank), calls in and out of place with a growing sequence number on the statistics
+    vector of a real batch, argument checks, close()."""
+    import torch.distributed as dist
+    from multi_echelon_drl_b200 import register_envs as R
+    from multi_echelon_drl_b200.distributed import PeerStatsAllReduce, summarize
+    from multi_echelon_drl_b200.simulator import BasePolicyParams
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        ar = PeerStatsAllReduce(torch.device("cuda", 0))
+        env = R.make("BeerGameUniformMultiFacilityFullInfo-v0", n_envs=512, dtype="int32", seed=2)
+        sim = env.sim
+        env._next_episode()
+        sim.track_stats = True
+        sim.stats.zero_()
+        sim.episode(policy=BasePolicyParams([19, 20, 20, 14], 0, 16, "a"), write_state=False)
+        total = ar(sim.stats, torch.empty_like(sim.stats))
+        assert torch.equal(total, sim.stats) and summarize(total)["env_steps"] == 512 * 100
+        keep = sim.stats.clone()
+        for _ in range(5):
+            ar(sim.stats)                                   # in place
+        assert torch.equal(sim.stats, keep) and ar.seq == 6
+        with pytest.raises(ValueError):
+            ar(torch.zeros(3, dtype=torch.float64, device="cuda:0"))
+        with pytest.raises(ValueError):
+            ar(torch.zeros(16, dtype=torch.float32, device="cuda:0"))
+        ar.close()
+        ar.close()                                          # idempotent
+    finally:
+        dist.destroy_process_group()
