@@ -283,8 +283,8 @@ def run_native(args):
         if world > 1 and step_no[0] % args.stats_interval == 0:
             # the path's only collective: the statistics vector (16 doubles) that the kernels keep
             # accumulating on every rank, all-reduced once per log interval (every --stats-interval
-            # episodes, and once more at the end of the timed region).  Issued asynchronously on NCCL's
-            # stream with two alternating buffers so that it overlaps the next episode's kernel.
+            # episodes, and once more at the end of the timed region): one kernel over peer memory on this stream,
+            # or (fallback) NCCL, issued asynchronously on its stream with two alternating buffers.
             buf = stats_bufs[(step_no[0] // args.stats_interval) % 2]
             if peer_ar is not None:       # one small launch on this stream: stores to the peers, sum of what arrived
                 peer_ar(sim.stats, buf)
@@ -446,7 +446,8 @@ def run_native(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "api": "BatchedSupplyNetwork.episode_host (pinned host tensors in, trajectory out on the host; H2D/compute/D2H pipelined)", "chunks": args.e2e_chunks,
                     "cpu_binding": (f"{len(cpus)} CPUs next to the GPU (NVML affinity)" if cpus else "none")},
-            "gpu_launches": args.steps,
+            # our kernels inside the timed region: K episode launches (+ the statistics all-reduce launches at N > 1)
+            "gpu_launches": args.steps + ((args.steps // args.stats_interval + 1) if peer_ar is not None else 0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n), "traffic_source": "static ncu capture (profiles/ncu_traffic.json), not measured in this run",
                          "algorithmic_bytes": n * T * BYTES_PER_ENV_STEP_ROLLOUT, "kernel": "k_rollout<int,ACTIONS,IDENT> via sn_episode", "kernel_ms": kernel_ms,
